@@ -1,0 +1,74 @@
+/* oracle.h — CPU restatement of the reference's leaf-evaluation codec and a
+ * perft-pinned chess substrate.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load liboracle.so.  The product library
+ * (libcaissa_b200.so) never links or dlopens it.
+ *
+ * Every function cites the reference file:line it restates (paths relative
+ * to the reference checkout).  Parity pins: the known-answer literals of
+ * tests/unit/board_encoding_tests.rs, tests/unit/tensor_extended_tests.rs,
+ * src/tensor.rs:215-246 and the perft table of tests/perft_tests.rs are
+ * replayed in tests/test_oracle_*.py.
+ */
+#ifndef CAISSA_ORACLE_H
+#define CAISSA_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* 128-byte packed position: the FFI board format (same field layout as the
+ * reference's own C twin of Board, cuda/common.cuh:54-63; semantic source
+ * src/board.rs:14-25).  Square index = rank*8 + file, a1 = 0. */
+typedef struct {
+    uint64_t pieces[12];  /* [color*6 + piece]; WHITE=0 BLACK=1; P N B R Q K = 0..5 */
+    uint64_t occ[2];
+    uint8_t  w_to_move;   /* 1 = white */
+    uint8_t  en_passant;  /* target square or 0xFF */
+    uint8_t  castling;    /* WK=1 WQ=2 BK=4 BQ=8 */
+    uint8_t  halfmove;
+    uint8_t  pad[12];
+} orc_board;
+
+/* Move packing: from | to<<6 | promo<<12, promo 0 none, 1 N, 2 B, 3 R, 4 Q
+ * (the reference's piece constants, src/piece_types.rs:14-23). */
+typedef uint16_t orc_move;
+#define ORC_MV(f, t, p) ((orc_move)((f) | ((t) << 6) | ((p) << 12)))
+#define ORC_FROM(m) ((int)((m) & 63))
+#define ORC_TO(m) ((int)(((m) >> 6) & 63))
+#define ORC_PROMO(m) ((int)(((m) >> 12) & 7))
+
+#define ORC_POLICY 4672
+#define ORC_PLANES 1088
+#define ORC_MAX_MOVES 256
+
+/* ---- codec (src/tensor.rs, src/eval.rs, src/mcts/tactical_mcts.rs) ---- */
+int    orc_parse_fen(const char* fen, orc_board* out);            /* src/board.rs:115-199 */
+void   orc_startpos(orc_board* out);
+void   orc_board_to_planes(const orc_board* b, float* planes);    /* src/tensor.rs:21-77 */
+int    orc_move_to_index(int from, int to, int promo);            /* src/tensor.rs:82-178; -1 where the reference panics */
+int    orc_move_to_index_stm(orc_move m, int w_to_move);          /* + flip for black, src/move_types.rs:374-381 */
+void   orc_policy_to_move_priors(const float* policy, int n_policy, const orc_move* moves, int n,
+                                 int w_to_move, float* priors);   /* src/tensor.rs:184-213 */
+int    orc_pst_eval_cp(const orc_board* b);                       /* src/eval.rs:93-122 */
+double orc_value_fuse(float v_logit, float k, float q, int material_on); /* src/mcts/tactical_mcts.rs:762-765,787-790 */
+
+/* ---- chess substrate (position source; pinned by tests/perft_tests.rs) ---- */
+int      orc_gen_legal(const orc_board* b, orc_move* out);        /* legal list, captures/promotions first */
+void     orc_make_move(const orc_board* b, orc_move m, orc_board* out); /* src/make_move.rs:24-225 rules */
+int      orc_in_check(const orc_board* b, int color);
+uint64_t orc_perft(const orc_board* b, int depth);
+/* Seeded random legal playouts from the start position.  Emits up to n
+ * positions (each with >=1 legal move) and their legal-move CSR as policy
+ * indices (move_to_index of the STM-relative move).  Returns positions written. */
+int      orc_random_positions(uint64_t seed, int n, int max_plies, orc_board* boards,
+                              uint16_t* move_idx, uint32_t* move_off, orc_move* moves_raw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
