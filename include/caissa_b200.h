@@ -1,0 +1,159 @@
+/* caissa_b200.h — C ABI of libcaissa_b200.so, the B200-native batched MCTS
+ * leaf evaluator for Caissawary (aaholmes/neurosymbolic-mcts).
+ *
+ * This is the drop-in boundary for the reference's evaluator: everything the
+ * Rust `NeuralNetPolicy` (src/neural_net.rs:12-363) does through tch/libtorch
+ * — encode boards, run OracleNet, return (policy, v_logit, k) — is reachable
+ * through the functions below with plain pointers and sizes.  A thin Rust
+ * `-sys` crate binds them 1:1; the C++ mirror in
+ * neurosymbolic-mcts_b200/csrc/host and the ctypes binding in
+ * neurosymbolic-mcts_b200/caissa_b200 call the same entry points.
+ *
+ * Conventions
+ *   - Return value: 0 on success, a negative CB_E* code on failure.  The
+ *     library never aborts and never throws; cb_last_error() gives the text
+ *     (the reference answers errors with `None`, src/neural_net.rs:295-313).
+ *   - Ownership: the caller owns every host buffer passed in; the library owns
+ *     device memory, pinned staging and its CUDA stream.
+ *   - Threading: one handle = one owner thread (mirrors `&mut self`, the handle
+ *     is moved into the InferenceServer worker, src/mcts/inference_server.rs:
+ *     29-32).  Distinct handles are independent (own stream, own buffers), so
+ *     two models can coexist in a process (src/bin/evaluate_models.rs:558-584).
+ *   - There is NO CPU fallback: without a CUDA device cb_create fails.
+ */
+#ifndef CAISSA_B200_H
+#define CAISSA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_POLICY_SIZE 4672 /* 8*8*73, src/tensor.rs:82-178 */
+#define CB_PLANES 1088      /* 17*8*8, src/tensor.rs:21-77 */
+#define CB_MAX_MOVES 256
+
+enum {
+    CB_OK = 0,
+    CB_EINVAL = -1,   /* bad argument */
+    CB_ECUDA = -2,    /* CUDA runtime / driver error, see cb_last_error */
+    CB_ENODEV = -3,   /* no usable CUDA device (no CPU fallback exists) */
+    CB_ESTATE = -4,   /* weights not loaded / nothing staged */
+    CB_ENOMEM = -5
+};
+
+/* Arithmetic mode of the convolution tower. */
+enum {
+    CB_DTYPE_FP32 = 0, /* exact mode: fp32 CUDA-core implicit GEMM (validation, |dv| <= 1e-3 bar) */
+    CB_DTYPE_BF16 = 1, /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate in TMEM */
+    CB_DTYPE_FP16 = 2  /* tcgen05 kind::f16 with fp16 operands, fp32 accumulate in TMEM */
+};
+
+/* 128-byte packed position; replaces `Board` (src/board.rs:14-25) at the FFI.
+ * Same field order as the reference's own C twin (cuda/common.cuh:54-63).
+ * Square = rank*8 + file, a1 = 0.  pieces[color*6 + piece], WHITE=0, BLACK=1,
+ * P N B R Q K = 0..5. */
+typedef struct cb_board {
+    uint64_t pieces[12];
+    uint64_t occ[2];
+    uint8_t  w_to_move;  /* 1 = white to move */
+    uint8_t  en_passant; /* target square, 0xFF = none (Option<u8>::None) */
+    uint8_t  castling;   /* WK=1 WQ=2 BK=4 BQ=8 (src/move_types.rs:46-51) */
+    uint8_t  halfmove;
+    uint8_t  pad[12];
+} cb_board;
+
+typedef struct cb_handle cb_handle;
+
+/* Per-phase timing, the counterpart of the reference's three public
+ * TimingAccumulators (src/neural_net.rs:88-90,220,245,271). */
+typedef struct cb_timing {
+    uint64_t calls;
+    uint64_t positions;
+    double   h2d_ms;     /* transfer_to_gpu_timing   */
+    double   forward_ms; /* forward_timing (device time, CUDA events) */
+    double   d2h_ms;     /* transfer_from_gpu_timing */
+} cb_timing;
+
+/* Replaces NeuralNetPolicy::new (src/neural_net.rs:94-108).  `device` is the
+ * CUDA ordinal; (num_blocks, hidden) select the OracleNet shape
+ * (python/model.py:55: 6x128 default, 10x256 scaled; hidden in {128, 256}). */
+int cb_create(cb_handle** out, int device, int num_blocks, int hidden, int dtype);
+
+/* Replaces NeuralNetPolicy::load (src/neural_net.rs:110-125).  `blob` is the
+ * flat f32 parameter vector in the reference's own export order
+ * (python/export_weights_cuda.py:73-107) generalised to (num_blocks, hidden);
+ * cb_weight_count gives the expected length.  BatchNorm is folded and the
+ * operands are packed for the tensor cores here.  Caller keeps `blob`. */
+int    cb_load_weights(cb_handle* h, const float* blob, size_t n_floats);
+size_t cb_weight_count(int num_blocks, int hidden);
+
+/* NeuralNetPolicy::is_available (src/neural_net.rs:131-133). */
+int cb_is_available(const cb_handle* h);
+
+/* Replaces NeuralNetPolicy::predict_batch (src/neural_net.rs:208-315); B=1 is
+ * ::predict (:144-205).  Compat mode: policy_probs[B*4672] are PROBABILITIES
+ * (exp already applied, :279-284), v_logit[B] the raw value logit, k[B] the
+ * position-independent confidence scalar.  qflag (qsearch_completed) is
+ * accepted and ignored exactly like the network does (python/model.py:106).
+ * policy_probs may be NULL to skip the 18.7 KB/position read-back. */
+int cb_predict_batch(cb_handle* h, const cb_board* boards, const float* q, const uint8_t* qflag, int B,
+                     float* policy_probs, float* v_logit, float* k);
+
+/* Fused fast path: predict_batch + policy_to_move_priors (src/tensor.rs:184-213)
+ * + the value fusion of evaluate_leaf_node (src/mcts/tactical_mcts.rs:762-765
+ * material_on: tanh(v_logit + k*q); :787-790 material off: tanh(v_logit)).
+ * move_idx/move_off: CSR (B+1 offsets) of policy indices of each position's
+ * legal moves, i.e. move_to_index(flip-if-black(mv)) (src/tensor.rs:82-178).
+ * priors[move_off[B]] are renormalised over each list in list order with the
+ * uniform fallback when the sum is 0.  v_final is fp32 device tanhf; hosts
+ * that want the reference's f64 tanh recompute it from v_logit and k. */
+int cb_eval_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, int material_on,
+                   const uint16_t* move_idx, const uint32_t* move_off,
+                   float* priors, float* v_logit, float* v_final, float* k);
+
+/* Bit-exactness hook for board_to_planes (src/tensor.rs:21-77): planes[B*1088]
+ * f32, NCHW, exactly the reference's Vec<f32>. */
+int cb_encode(cb_handle* h, const cb_board* boards, int B, float* planes);
+
+/* Static PeSTO stand-pat term of dM on the device, PestoEval::pst_eval_cp
+ * (src/eval.rs:93-122): centipawns, side-to-move perspective, bit-exact. */
+int cb_pst_eval_cp(cb_handle* h, const cb_board* boards, int B, int32_t* cp);
+
+/* Device-resident benchmarking entry points (inputs already in HBM when the
+ * timed region starts).  cb_stage_leaves copies one batch to the device;
+ * cb_time_resident replays the captured forward graph `iters` times on the
+ * handle's stream and returns the CUDA-event time of each iteration in
+ * ms_each[iters] (events recorded on the launching stream).  If flush_l2 is
+ * non-zero a 256 MiB buffer is rewritten before every iteration, outside the
+ * timed events.  conv_ms_total (nullable) receives the event time spent in the
+ * 3x3 convolution kernels alone over all iterations (separate un-graphed
+ * replay), n_conv_launches (nullable) their number per iteration. */
+int cb_stage_leaves(cb_handle* h, const cb_board* boards, const float* q, int B,
+                    const uint16_t* move_idx, const uint32_t* move_off);
+int cb_time_resident(cb_handle* h, int material_on, int iters, int flush_l2, float* ms_each);
+int cb_time_conv_layers(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches);
+int cb_read_resident(cb_handle* h, float* priors, float* v_logit, float* v_final, float* k);
+
+/* Debug / parity hook: copy the backbone activation (after the last residual
+ * block) of the most recent forward as f32 NCHW [B*hidden*64]. */
+int cb_debug_backbone(cb_handle* h, int B, float* out);
+/* Same for activation ring buffer `buf` (0..2); with cb_debug_set_layer_limit(n) the tower stops
+ * after n convolution launches so individual layers can be compared across arithmetic modes. */
+int cb_debug_act(cb_handle* h, int B, int buf, float* out);
+int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches);
+
+/* Kernels launched per forward of the given kind (for gpu_launches accounting). */
+int cb_launches_per_forward(const cb_handle* h);
+
+int         cb_get_timing(const cb_handle* h, cb_timing* out);
+void        cb_reset_timing(cb_handle* h);
+const char* cb_last_error(const cb_handle* h);
+const char* cb_version(void);
+void        cb_destroy(cb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,324 @@
+"""caissa_b200 — ctypes binding of libcaissa_b200.so plus Python mirrors of the
+reference's evaluator interface (`NeuralNetPolicy`, `InferenceServer`).
+
+The compute lives in the CUDA library behind the C ABI of
+include/caissa_b200.h; this module adds no arithmetic of its own and has no
+CPU fallback: if the library or a B200 is missing, calls raise.
+"""
+import ctypes
+import os
+import queue
+import threading
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcaissa_b200.so")
+
+POLICY_SIZE = 4672
+PLANES = 1088
+MAX_MOVES = 256
+DTYPE_FP32, DTYPE_BF16, DTYPE_FP16 = 0, 1, 2
+DTYPES = {"fp32": 0, "bf16": 1, "fp16": 2}
+
+
+class CbTiming(ctypes.Structure):
+    _fields_ = [("calls", ctypes.c_uint64), ("positions", ctypes.c_uint64), ("h2d_ms", ctypes.c_double),
+                ("forward_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double)]
+
+
+class CaissaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_F = ctypes.POINTER(ctypes.c_float)
+_VP = ctypes.c_void_p
+
+# name -> (restype, argtypes): every symbol include/caissa_b200.h declares
+SIGNATURES = {
+    "cb_create": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "cb_load_weights": (ctypes.c_int, [_VP, _VP, ctypes.c_size_t]),
+    "cb_weight_count": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "cb_is_available": (ctypes.c_int, [_VP]),
+    "cb_predict_batch": (ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_int, _VP, _VP, _VP]),
+    "cb_eval_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "cb_encode": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
+    "cb_pst_eval_cp": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
+    "cb_stage_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, _VP, _VP]),
+    "cb_time_resident": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
+    "cb_time_conv_layers": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
+    "cb_read_resident": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "cb_debug_backbone": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
+    "cb_debug_act": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
+    "cb_debug_set_layer_limit": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "cb_launches_per_forward": (ctypes.c_int, [_VP]),
+    "cb_get_timing": (ctypes.c_int, [_VP, ctypes.POINTER(CbTiming)]),
+    "cb_reset_timing": (None, [_VP]),
+    "cb_last_error": (ctypes.c_char_p, [_VP]),
+    "cb_version": (ctypes.c_char_p, []),
+    "cb_destroy": (None, [_VP]),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen the CUDA library (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise CaissaError("libcaissa_b200.so not built: run `python neurosymbolic-mcts_b200/build.py`")
+        L = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_VP)
+
+
+def _boards_u8(boards):
+    b = np.ascontiguousarray(boards, dtype=np.uint8)
+    if b.ndim != 2 or b.shape[1] != 128:
+        raise ValueError("boards must be uint8 [B,128] packed cb_board records")
+    return b
+
+
+class Evaluator:
+    """Thin owner of one cb_handle (one CUDA stream, one set of device buffers)."""
+
+    def __init__(self, num_blocks=6, hidden=128, dtype="bf16", device=0):
+        self._L = load_library()
+        self._h = _VP()
+        self.num_blocks, self.hidden = num_blocks, hidden
+        self.dtype = DTYPES[dtype] if isinstance(dtype, str) else int(dtype)
+        rc = self._L.cb_create(ctypes.byref(self._h), device, num_blocks, hidden, self.dtype)
+        if rc != 0:
+            self._h = _VP()
+            raise CaissaError("cb_create failed with %d (no CUDA device / unsupported shape; there is no CPU fallback)" % rc)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.cb_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CaissaError("caissa_b200 error %d: %s" % (rc, (self._L.cb_last_error(self._h) or b"").decode()))
+
+    def weight_count(self):
+        return self._L.cb_weight_count(self.num_blocks, self.hidden)
+
+    def load_weights(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        self._check(self._L.cb_load_weights(self._h, _ptr(blob), blob.size))
+
+    def is_available(self):
+        return bool(self._L.cb_is_available(self._h))
+
+    def encode(self, boards):
+        b = _boards_u8(boards)
+        out = np.empty((b.shape[0], 17, 8, 8), dtype=np.float32)
+        self._check(self._L.cb_encode(self._h, _ptr(b), b.shape[0], _ptr(out)))
+        return out
+
+    def pst_eval_cp(self, boards):
+        b = _boards_u8(boards)
+        out = np.empty(b.shape[0], dtype=np.int32)
+        self._check(self._L.cb_pst_eval_cp(self._h, _ptr(b), b.shape[0], _ptr(out)))
+        return out
+
+    def predict_batch(self, boards, q=None, qflag=None, want_policy=True):
+        b = _boards_u8(boards)
+        B = b.shape[0]
+        qa = None if q is None else np.ascontiguousarray(q, dtype=np.float32)
+        fa = None if qflag is None else np.ascontiguousarray(qflag, dtype=np.uint8)
+        pol = np.empty((B, POLICY_SIZE), dtype=np.float32) if want_policy else None
+        v = np.empty(B, dtype=np.float32)
+        k = np.empty(B, dtype=np.float32)
+        self._check(self._L.cb_predict_batch(self._h, _ptr(b), _ptr(qa), _ptr(fa), B, _ptr(pol), _ptr(v), _ptr(k)))
+        return pol, v, k
+
+    def eval_leaves(self, boards, q, move_idx, move_off, material_on=True):
+        b = _boards_u8(boards)
+        B = b.shape[0]
+        qa = None if q is None else np.ascontiguousarray(q, dtype=np.float32)
+        mi = np.ascontiguousarray(move_idx, dtype=np.uint16)
+        mo = np.ascontiguousarray(move_off, dtype=np.uint32)
+        assert mo.size == B + 1
+        pri = np.empty(int(mo[B]), dtype=np.float32)
+        v = np.empty(B, dtype=np.float32)
+        vf = np.empty(B, dtype=np.float32)
+        k = np.empty(B, dtype=np.float32)
+        self._check(self._L.cb_eval_leaves(self._h, _ptr(b), _ptr(qa), B, int(material_on), _ptr(mi), _ptr(mo),
+                                           _ptr(pri), _ptr(v), _ptr(vf), _ptr(k)))
+        return pri, v, vf, k
+
+    def stage_leaves(self, boards, q, move_idx, move_off):
+        b = _boards_u8(boards)
+        qa = None if q is None else np.ascontiguousarray(q, dtype=np.float32)
+        mi = None if move_idx is None else np.ascontiguousarray(move_idx, dtype=np.uint16)
+        mo = None if move_off is None else np.ascontiguousarray(move_off, dtype=np.uint32)
+        self._staged = (b.shape[0], 0 if mo is None else int(mo[-1]))
+        self._check(self._L.cb_stage_leaves(self._h, _ptr(b), _ptr(qa), b.shape[0], _ptr(mi), _ptr(mo)))
+
+    def time_resident(self, iters, material_on=True, flush_l2=False):
+        ms = np.zeros(iters, dtype=np.float32)
+        self._check(self._L.cb_time_resident(self._h, int(material_on), iters, int(flush_l2), _ptr(ms)))
+        return ms
+
+    def time_conv_layers(self, iters):
+        ms = ctypes.c_float(0)
+        n = ctypes.c_int(0)
+        self._check(self._L.cb_time_conv_layers(self._h, iters, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def read_resident(self):
+        B, nm = self._staged
+        pri = np.empty(nm, dtype=np.float32)
+        v = np.empty(B, dtype=np.float32)
+        vf = np.empty(B, dtype=np.float32)
+        k = np.empty(B, dtype=np.float32)
+        self._check(self._L.cb_read_resident(self._h, _ptr(pri), _ptr(v), _ptr(vf), _ptr(k)))
+        return pri, v, vf, k
+
+    def debug_backbone(self, B):
+        out = np.empty((B, self.hidden, 8, 8), dtype=np.float32)
+        self._check(self._L.cb_debug_backbone(self._h, B, _ptr(out)))
+        return out
+
+    def debug_act(self, B, buf):
+        out = np.empty((B, self.hidden, 8, 8), dtype=np.float32)
+        self._check(self._L.cb_debug_act(self._h, B, buf, _ptr(out)))
+        return out
+
+    def debug_set_layer_limit(self, n):
+        self._check(self._L.cb_debug_set_layer_limit(self._h, n))
+
+    def launches_per_forward(self):
+        return self._L.cb_launches_per_forward(self._h)
+
+    def timing(self):
+        t = CbTiming()
+        self._check(self._L.cb_get_timing(self._h, ctypes.byref(t)))
+        return {"calls": t.calls, "positions": t.positions, "h2d_ms": t.h2d_ms, "forward_ms": t.forward_ms,
+                "d2h_ms": t.d2h_ms}
+
+
+class NeuralNetPolicy:
+    """Mirror of the reference's `NeuralNetPolicy` (src/neural_net.rs:86-363): same method names,
+    argument meaning and error behaviour (errors answer None per item, never raise from predict*).
+
+    `load` takes a flat f32 weight blob (.bin, or an ndarray) instead of a TorchScript file; boards
+    are packed 128-byte records (uint8 [128])."""
+
+    def __init__(self, num_blocks=6, hidden=128, dtype="bf16", device=0):
+        self._cfg = (num_blocks, hidden, dtype, device)
+        self._ev = None
+        self._warned = False
+
+    def load(self, path_or_blob):
+        try:
+            if isinstance(path_or_blob, (str, os.PathLike)):
+                if not os.path.exists(path_or_blob):
+                    return "Model file not found: %s" % path_or_blob
+                blob = np.fromfile(path_or_blob, dtype=np.float32)
+            else:
+                blob = np.asarray(path_or_blob, dtype=np.float32)
+            ev = Evaluator(*self._cfg)
+            ev.load_weights(blob)
+            self._ev = ev
+            return None  # Ok(())
+        except Exception as e:  # Err(String)
+            return "Failed to load model: %s" % e
+
+    def is_available(self):
+        return self._ev is not None and self._ev.is_available()
+
+    def predict(self, board, qsearch_completed, q_result):
+        res = self.predict_batch([board], [qsearch_completed], [q_result])
+        return res[0]
+
+    def predict_batch(self, boards, qsearch_flags, q_results):
+        n = len(boards)
+        if self._ev is None:
+            return [None] * n
+        try:
+            b = np.stack([np.frombuffer(bytes(x), dtype=np.uint8) if not isinstance(x, np.ndarray) else x for x in boards])
+            pol, v, k = self._ev.predict_batch(b, np.asarray(q_results, dtype=np.float32),
+                                               np.asarray(qsearch_flags, dtype=np.uint8))
+            return [(pol[i], float(v[i]), float(k[i])) for i in range(n)]
+        except Exception as e:
+            if not self._warned:
+                print("[NN-ERROR] predict_batch failed: %s" % e)
+                self._warned = True
+            return [None] * n
+
+    def timing(self):
+        return self._ev.timing() if self._ev else None
+
+    def print_inference_timing(self):
+        t = self.timing()
+        if t and t["calls"]:
+            c = t["calls"]
+            print("NN timing over %d calls: to-gpu %.3f ms, forward %.3f ms, from-gpu %.3f ms (means)"
+                  % (c, t["h2d_ms"] / c, t["forward_ms"] / c, t["d2h_ms"] / c))
+
+
+class InferenceServer:
+    """Mirror of src/mcts/inference_server.rs:29-140: one worker thread owns the evaluator, blocks on
+    the first request, then gathers more until `batch_size` or 500 us, evaluates, and answers each
+    request on its own one-slot reply queue with `(policy, v_logit, k)` or None."""
+
+    def __init__(self, nn, batch_size):
+        self._q = queue.Queue()
+        self._nn = nn
+        self._batch = batch_size
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        while True:
+            first = self._q.get()
+            if first is None:
+                break
+            reqs = [first]
+            t0 = time.perf_counter()
+            while len(reqs) < self._batch and time.perf_counter() - t0 < 500e-6:
+                try:
+                    r = self._q.get_nowait()
+                except queue.Empty:
+                    time.sleep(0)
+                    continue
+                if r is None:
+                    self._q.put(None)
+                    break
+                reqs.append(r)
+            res = self._nn.predict_batch([r[0] for r in reqs], [r[1] for r in reqs], [r[2] for r in reqs])
+            for r, out in zip(reqs, res):
+                r[3].put(out)
+        self._nn.print_inference_timing()
+
+    def predict_async(self, board, qsearch_completed, q_result):
+        reply = queue.Queue(maxsize=1)
+        self._q.put((board, qsearch_completed, q_result, reply))
+        return reply
+
+    def shutdown(self):
+        self._q.put(None)
+        self._t.join(timeout=5)

@@ -1,0 +1,904 @@
+// cb_api.cu — the C ABI of libcaissa_b200.so (include/caissa_b200.h): handle,
+// weight folding / packing, device buffers, TMA descriptors, forward-pass
+// orchestration and CUDA-graph replay.  sm_100a only; no CPU fallback.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <stdlib.h>
+
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/caissa_b200.h"
+#include "conv_umma.cuh"
+#include "kernels_simt.cuh"
+
+namespace {
+
+using namespace cb;
+
+constexpr float kBnEps = 1e-5f;  // torch BatchNorm2d default (python/model.py uses the default)
+constexpr size_t kFlushBytes = 256ull << 20;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct ConvLayer {
+    int cin = 0;          // logical input channels (17 or HID)
+    int cin_pad = 0;      // padded to a multiple of 64 for the tensor-core path
+    void* w16 = nullptr;  // [9][HID][cin_pad] 16-bit, BN scale folded
+    float* w32 = nullptr; // [9][cin][HID] fp32, BN scale folded (exact mode)
+    float* bias = nullptr;
+    CUtensorMap tm_w;
+};
+
+}  // namespace
+
+struct cb_handle {
+    int device = 0, blocks = 0, hid = 0, dtype = 0;
+    int sm_count = 0;
+    bool loaded = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::string err;
+    EncodeTiledFn encode_tiled = nullptr;
+
+    // weights
+    std::vector<ConvLayer> convs;  // start, (conv1, conv2) x blocks, p_conv
+    std::vector<float*> se_w1, se_w2;
+    float* p_wt = nullptr;   // [HID][73]
+    float* p_bias = nullptr; // [73]
+    float* v_w = nullptr;    // [HID]
+    float* fc_wt = nullptr;  // [65][256]
+    float* fc_b = nullptr;
+    float* out_w = nullptr;
+    float v_conv_bias = 0, v_bn_scale = 1, v_bn_bias = 0, out_b = 0, k = 0;
+
+    // device buffers (capacity cap boards, even)
+    int cap = 0;
+    size_t csr_cap = 0;
+    cb_board* d_boards = nullptr;
+    float* d_q = nullptr;
+    void* d_x0 = nullptr;       // encoder output
+    void* d_act[3] = {nullptr, nullptr, nullptr};
+    float* d_tmp32 = nullptr;   // exact mode: pre-SE conv2 output
+    float* d_vpre = nullptr;
+    float* d_probs = nullptr;   // [cap][4672], allocated on first compat call
+    int probs_cap = 0;
+    uint16_t* d_move_idx = nullptr;
+    uint32_t* d_move_off = nullptr;
+    float* d_priors = nullptr;
+    float* d_vlogit = nullptr;
+    float* d_vfinal = nullptr;
+    float* d_k = nullptr;
+    float* d_scratch = nullptr; // debug / encode hook output
+    size_t scratch_floats = 0;
+    void* d_flush = nullptr;
+    CUtensorMap tm_x0, tm_act[3];
+
+    // pinned staging
+    cb_board* h_boards = nullptr;
+    float* h_q = nullptr;
+    uint16_t* h_move_idx = nullptr;
+    uint32_t* h_move_off = nullptr;
+    float* h_priors = nullptr;
+    float* h_small = nullptr;   // v_logit | v_final | k, 3*cap
+
+    // resident state
+    int staged_B = 0;
+    size_t staged_moves = 0;
+
+    std::map<uint64_t, cudaGraphExec_t> graphs;
+    cb_timing timing = {};
+    bool use_graphs = true;
+    int layer_limit = 0;  // debug: stop the tower after this many conv launches (0 = all)
+};
+
+namespace {
+
+#define CB_CUDA(h, expr)                                                                        \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                      \
+            return CB_ECUDA;                                                                    \
+        }                                                                                       \
+    } while (0)
+
+int fail(cb_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+size_t elem_bytes(const cb_handle* h) { return h->dtype == CB_DTYPE_FP32 ? 4 : 2; }
+
+uint16_t to16(float v, int dtype) {
+    if (dtype == CB_DTYPE_BF16) {
+        __nv_bfloat16 b = __float2bfloat16_rn(v);
+        uint16_t u;
+        memcpy(&u, &b, 2);
+        return u;
+    }
+    __half hv = __float2half_rn(v);
+    uint16_t u;
+    memcpy(&u, &hv, 2);
+    return u;
+}
+
+void free_dev(void* p) {
+    if (p) cudaFree(p);
+}
+
+void drop_graphs(cb_handle* h) {
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+}
+
+int make_act_map(cb_handle* h, CUtensorMap* tm, void* base, int channels, int boards) {
+    const cuuint64_t dims[4] = {(cuuint64_t)channels, 8, 8, (cuuint64_t)boards};
+    const cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 16, (cuuint64_t)channels * 128};
+    const cuuint32_t box[4] = {64, 8, 8, 2};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt =
+        h->dtype == CB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = h->encode_tiled(tm, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+    return CB_OK;
+}
+
+int make_weight_map(cb_handle* h, ConvLayer& L) {
+    const cuuint64_t dims[2] = {(cuuint64_t)L.cin_pad, (cuuint64_t)9 * h->hid};
+    const cuuint64_t strides[1] = {(cuuint64_t)L.cin_pad * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)h->hid};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt =
+        h->dtype == CB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = h->encode_tiled(&L.tm_w, dt, 2, L.w16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+    return CB_OK;
+}
+
+void free_buffers(cb_handle* h) {
+    drop_graphs(h);
+    free_dev(h->d_boards); free_dev(h->d_q); free_dev(h->d_x0);
+    for (int i = 0; i < 3; ++i) { free_dev(h->d_act[i]); h->d_act[i] = nullptr; }
+    free_dev(h->d_tmp32); free_dev(h->d_vpre); free_dev(h->d_probs);
+    free_dev(h->d_move_idx); free_dev(h->d_move_off); free_dev(h->d_priors);
+    free_dev(h->d_vlogit); free_dev(h->d_vfinal); free_dev(h->d_k); free_dev(h->d_scratch);
+    h->d_boards = nullptr; h->d_q = nullptr; h->d_x0 = nullptr; h->d_tmp32 = nullptr; h->d_vpre = nullptr;
+    h->d_probs = nullptr; h->d_move_idx = nullptr; h->d_move_off = nullptr; h->d_priors = nullptr;
+    h->d_vlogit = nullptr; h->d_vfinal = nullptr; h->d_k = nullptr; h->d_scratch = nullptr;
+    if (h->h_boards) cudaFreeHost(h->h_boards);
+    if (h->h_q) cudaFreeHost(h->h_q);
+    if (h->h_move_idx) cudaFreeHost(h->h_move_idx);
+    if (h->h_move_off) cudaFreeHost(h->h_move_off);
+    if (h->h_priors) cudaFreeHost(h->h_priors);
+    if (h->h_small) cudaFreeHost(h->h_small);
+    h->h_boards = nullptr; h->h_q = nullptr; h->h_move_idx = nullptr; h->h_move_off = nullptr;
+    h->h_priors = nullptr; h->h_small = nullptr;
+    h->cap = 0; h->csr_cap = 0; h->probs_cap = 0; h->scratch_floats = 0; h->staged_B = 0;
+}
+
+// Grow device + pinned buffers to hold B boards (rounded up to a whole 2-board tile).
+int ensure_capacity(cb_handle* h, int B) {
+    const int need = (B + 1) & ~1;
+    if (need <= h->cap) return CB_OK;
+    int cap = h->cap ? h->cap : 64;
+    while (cap < need) cap *= 2;
+    free_buffers(h);
+    const size_t eb = elem_bytes(h);
+    const size_t csr = (size_t)cap * CB_MAX_MOVES;
+    CB_CUDA(h, cudaMalloc(&h->d_boards, (size_t)cap * sizeof(cb_board)));
+    CB_CUDA(h, cudaMemset(h->d_boards, 0, (size_t)cap * sizeof(cb_board)));
+    CB_CUDA(h, cudaMalloc(&h->d_q, (size_t)cap * 4));
+    CB_CUDA(h, cudaMalloc(&h->d_x0, (size_t)cap * 64 * (h->dtype == CB_DTYPE_FP32 ? 17 * 4 : 64 * 2)));
+    for (int i = 0; i < 3; ++i) CB_CUDA(h, cudaMalloc(&h->d_act[i], (size_t)cap * 64 * h->hid * eb));
+    if (h->dtype == CB_DTYPE_FP32) CB_CUDA(h, cudaMalloc(&h->d_tmp32, (size_t)cap * 64 * h->hid * 4));
+    CB_CUDA(h, cudaMalloc(&h->d_vpre, (size_t)cap * 64 * 4));
+    CB_CUDA(h, cudaMalloc(&h->d_move_idx, csr * 2));
+    CB_CUDA(h, cudaMalloc(&h->d_move_off, ((size_t)cap + 1) * 4));
+    CB_CUDA(h, cudaMalloc(&h->d_priors, csr * 4));
+    CB_CUDA(h, cudaMalloc(&h->d_vlogit, (size_t)cap * 4));
+    CB_CUDA(h, cudaMalloc(&h->d_vfinal, (size_t)cap * 4));
+    CB_CUDA(h, cudaMalloc(&h->d_k, (size_t)cap * 4));
+    CB_CUDA(h, cudaHostAlloc(&h->h_boards, (size_t)cap * sizeof(cb_board), cudaHostAllocDefault));
+    CB_CUDA(h, cudaHostAlloc(&h->h_q, (size_t)cap * 4, cudaHostAllocDefault));
+    CB_CUDA(h, cudaHostAlloc(&h->h_move_idx, csr * 2, cudaHostAllocDefault));
+    CB_CUDA(h, cudaHostAlloc(&h->h_move_off, ((size_t)cap + 1) * 4, cudaHostAllocDefault));
+    CB_CUDA(h, cudaHostAlloc(&h->h_priors, csr * 4, cudaHostAllocDefault));
+    CB_CUDA(h, cudaHostAlloc(&h->h_small, (size_t)cap * 3 * 4, cudaHostAllocDefault));
+    h->cap = cap;
+    h->csr_cap = csr;
+    if (h->dtype != CB_DTYPE_FP32) {
+        int rc = make_act_map(h, &h->tm_x0, h->d_x0, 64, cap);
+        if (rc) return rc;
+        for (int i = 0; i < 3; ++i) {
+            rc = make_act_map(h, &h->tm_act[i], h->d_act[i], h->hid, cap);
+            if (rc) return rc;
+        }
+    }
+    return CB_OK;
+}
+
+int ensure_scratch(cb_handle* h, size_t floats) {
+    if (floats <= h->scratch_floats) return CB_OK;
+    free_dev(h->d_scratch);
+    h->d_scratch = nullptr;
+    h->scratch_floats = 0;
+    CB_CUDA(h, cudaMalloc(&h->d_scratch, floats * 4));
+    h->scratch_floats = floats;
+    return CB_OK;
+}
+
+template <int HID, bool BF16>
+int launch_conv_umma_t(cb_handle* h, const CUtensorMap& tin, const ConvLayer& L, const CUtensorMap& tout, int mode,
+                       const ConvParams& p) {
+    using Cfg = ConvCfg<HID>;
+    const int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+    if (mode == MODE_RELU) {
+        auto kern = conv3x3_umma_kernel<HID, BF16, MODE_RELU>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, h->stream>>>(tin, L.tm_w, tout, p);
+    } else {
+        auto kern = conv3x3_umma_kernel<HID, BF16, MODE_SE_RES>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, h->stream>>>(tin, L.tm_w, tout, p);
+    }
+    CB_CUDA(h, cudaGetLastError());
+    return CB_OK;
+}
+
+int launch_conv_umma(cb_handle* h, const CUtensorMap& tin, const ConvLayer& L, const CUtensorMap& tout, int mode,
+                     const ConvParams& p) {
+    const bool bf = h->dtype == CB_DTYPE_BF16;
+    if (h->hid == 128) return bf ? launch_conv_umma_t<128, true>(h, tin, L, tout, mode, p)
+                                 : launch_conv_umma_t<128, false>(h, tin, L, tout, mode, p);
+    return bf ? launch_conv_umma_t<256, true>(h, tin, L, tout, mode, p)
+              : launch_conv_umma_t<256, false>(h, tin, L, tout, mode, p);
+}
+
+int launch_conv_fp32(cb_handle* h, const float* in, const ConvLayer& L, float* out, int B, int relu) {
+    const size_t smem = (size_t)100 * L.cin * 4;
+    if (h->hid == 128) {
+        auto kern = conv3x3_fp32_kernel<128>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<B, 256, smem, h->stream>>>(in, L.cin, L.w32, L.bias, out, relu);
+    } else {
+        auto kern = conv3x3_fp32_kernel<256>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<B, 256, smem, h->stream>>>(in, L.cin, L.w32, L.bias, out, relu);
+    }
+    CB_CUDA(h, cudaGetLastError());
+    return CB_OK;
+}
+
+template <typename T>
+int launch_policy_t(cb_handle* h, const T* p, int B, const PolicyOut& po) {
+    const size_t smem = ((size_t)64 * h->hid + (size_t)h->hid * 73 + CB_POLICY_SIZE) * 4;
+    if (h->hid == 128) {
+        auto kern = policy_head_kernel<T, 128>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<B, kPolicyThreads, smem, h->stream>>>(p, h->p_wt, h->p_bias, po);
+    } else {
+        auto kern = policy_head_kernel<T, 256>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<B, kPolicyThreads, smem, h->stream>>>(p, h->p_wt, h->p_bias, po);
+    }
+    CB_CUDA(h, cudaGetLastError());
+    return CB_OK;
+}
+
+int launch_policy(cb_handle* h, const void* p, int B, const PolicyOut& po) {
+    if (h->dtype == CB_DTYPE_FP32) return launch_policy_t<float>(h, (const float*)p, B, po);
+    if (h->dtype == CB_DTYPE_BF16) return launch_policy_t<__nv_bfloat16>(h, (const __nv_bfloat16*)p, B, po);
+    return launch_policy_t<__half>(h, (const __half*)p, B, po);
+}
+
+// Index of the buffer holding the backbone output after `blocks` residual blocks.
+int backbone_index(int blocks) { return (blocks & 1) ? 2 : 0; }
+
+// Enqueue the convolution tower only (start conv .. p_conv).  If ev is non-null it
+// receives 2 events per conv launch (timing of individual layers).
+int enqueue_tower(cb_handle* h, int B, std::vector<cudaEvent_t>* ev) {
+    const int Bpad = (B + 1) & ~1;
+    const int last = (int)h->convs.size() - 1;
+    int cur = 0, e = 0, launched = 0;
+    auto stop = [&]() { return h->layer_limit > 0 && launched++ >= h->layer_limit; };
+    auto mark = [&]() -> int {
+        if (ev) CB_CUDA(h, cudaEventRecord((*ev)[e++], h->stream));
+        return CB_OK;
+    };
+    if (h->dtype == CB_DTYPE_FP32) {
+        int rc;
+        if (stop()) return CB_OK;
+        if ((rc = mark())) return rc;
+        if ((rc = launch_conv_fp32(h, (const float*)h->d_x0, h->convs[0], (float*)h->d_act[0], B, 1))) return rc;
+        if ((rc = mark())) return rc;
+        for (int i = 0; i < h->blocks; ++i) {
+            const int nxt = cur == 0 ? 2 : 0;
+            if (stop()) return CB_OK;
+            if ((rc = mark())) return rc;
+            if ((rc = launch_conv_fp32(h, (const float*)h->d_act[cur], h->convs[1 + 2 * i], (float*)h->d_act[1], B, 1))) return rc;
+            if ((rc = mark())) return rc;
+            if (stop()) return CB_OK;
+            if ((rc = mark())) return rc;
+            if ((rc = launch_conv_fp32(h, (const float*)h->d_act[1], h->convs[2 + 2 * i], h->d_tmp32, B, 0))) return rc;
+            if ((rc = mark())) return rc;
+            const bool lastblk = i == h->blocks - 1;
+            if (h->hid == 128)
+                se_res_fp32_kernel<128><<<B, 128, 0, h->stream>>>(h->d_tmp32, (const float*)h->d_act[cur], h->se_w1[i],
+                                                                 h->se_w2[i], (float*)h->d_act[nxt],
+                                                                 lastblk ? h->v_w : nullptr, lastblk ? h->d_vpre : nullptr);
+            else
+                se_res_fp32_kernel<256><<<B, 256, 0, h->stream>>>(h->d_tmp32, (const float*)h->d_act[cur], h->se_w1[i],
+                                                                 h->se_w2[i], (float*)h->d_act[nxt],
+                                                                 lastblk ? h->v_w : nullptr, lastblk ? h->d_vpre : nullptr);
+            CB_CUDA(h, cudaGetLastError());
+            cur = nxt;
+        }
+        if (stop()) return CB_OK;
+        if ((rc = mark())) return rc;
+        if ((rc = launch_conv_fp32(h, (const float*)h->d_act[cur], h->convs[last], (float*)h->d_act[1], B, 1))) return rc;
+        if ((rc = mark())) return rc;
+        return CB_OK;
+    }
+    ConvParams p = {};
+    p.num_tiles = Bpad / 2;
+    int rc;
+    // start conv: x0 (64-channel padded planes) -> act[0]
+    p.kc_in = 1;
+    p.bias = h->convs[0].bias;
+    if (stop()) return CB_OK;
+    if ((rc = mark())) return rc;
+    if ((rc = launch_conv_umma(h, h->tm_x0, h->convs[0], h->tm_act[0], MODE_RELU, p))) return rc;
+    if ((rc = mark())) return rc;
+    for (int i = 0; i < h->blocks; ++i) {
+        const int nxt = cur == 0 ? 2 : 0;
+        ConvParams p1 = {};
+        p1.num_tiles = Bpad / 2;
+        p1.kc_in = h->hid / 64;
+        p1.bias = h->convs[1 + 2 * i].bias;
+        if (stop()) return CB_OK;
+        if ((rc = mark())) return rc;
+        if ((rc = launch_conv_umma(h, h->tm_act[cur], h->convs[1 + 2 * i], h->tm_act[1], MODE_RELU, p1))) return rc;
+        if ((rc = mark())) return rc;
+        ConvParams p2 = p1;
+        p2.bias = h->convs[2 + 2 * i].bias;
+        p2.se_w1 = h->se_w1[i];
+        p2.se_w2 = h->se_w2[i];
+        p2.residual = h->d_act[cur];
+        if (i == h->blocks - 1) {
+            p2.v_w = h->v_w;
+            p2.v_pre = h->d_vpre;
+        }
+        if (stop()) return CB_OK;
+        if ((rc = mark())) return rc;
+        if ((rc = launch_conv_umma(h, h->tm_act[1], h->convs[2 + 2 * i], h->tm_act[nxt], MODE_SE_RES, p2))) return rc;
+        if ((rc = mark())) return rc;
+        cur = nxt;
+    }
+    ConvParams pp = {};
+    pp.num_tiles = Bpad / 2;
+    pp.kc_in = h->hid / 64;
+    pp.bias = h->convs[last].bias;
+    if (stop()) return CB_OK;
+    if ((rc = mark())) return rc;
+    if ((rc = launch_conv_umma(h, h->tm_act[cur], h->convs[last], h->tm_act[1], MODE_RELU, pp))) return rc;
+    if ((rc = mark())) return rc;
+    return CB_OK;
+}
+
+// Enqueue one full forward on the handle's stream (inputs already in d_boards/d_q/CSR).
+int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int material_on, bool use_q) {
+    const int Bpad = (B + 1) & ~1;
+    if (h->dtype == CB_DTYPE_FP32) {
+        encode_nhwc_f32_kernel<<<(B * 64 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, (float*)h->d_x0);
+    } else if (h->dtype == CB_DTYPE_BF16) {
+        encode_nhwc16_kernel<true><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, (uint4*)h->d_x0);
+    } else {
+        encode_nhwc16_kernel<false><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, (uint4*)h->d_x0);
+    }
+    CB_CUDA(h, cudaGetLastError());
+    int rc = enqueue_tower(h, B, nullptr);
+    if (rc) return rc;
+    PolicyOut po = {};
+    po.probs = full_policy ? h->d_probs : nullptr;
+    if (csr) {
+        po.move_idx = h->d_move_idx;
+        po.move_off = h->d_move_off;
+        po.priors = h->d_priors;
+    }
+    if ((rc = launch_policy(h, h->d_act[1], B, po))) return rc;
+    ValueParams vp = {};
+    vp.v_pre = h->d_vpre;
+    vp.q = use_q ? h->d_q : nullptr;
+    vp.conv_bias = h->v_conv_bias;
+    vp.bn_scale = h->v_bn_scale;
+    vp.bn_bias = h->v_bn_bias;
+    vp.fc_wt = h->fc_wt;
+    vp.fc_b = h->fc_b;
+    vp.out_w = h->out_w;
+    vp.out_b = h->out_b;
+    vp.k = h->k;
+    vp.material_on = material_on;
+    vp.B = B;
+    vp.v_logit = h->d_vlogit;
+    vp.v_final = h->d_vfinal;
+    vp.k_out = h->d_k;
+    value_head_kernel<<<(B + kValueBoardsPerCta - 1) / kValueBoardsPerCta, 256, 0, h->stream>>>(vp);
+    CB_CUDA(h, cudaGetLastError());
+    return CB_OK;
+}
+
+// Replay (capturing on first use) the forward graph for this shape.
+int run_forward(cb_handle* h, int B, bool full_policy, bool csr, int material_on, bool use_q) {
+    if (!h->use_graphs) return enqueue_forward(h, B, full_policy, csr, material_on, use_q);
+    const uint64_t key = (uint64_t)B | ((uint64_t)full_policy << 32) | ((uint64_t)csr << 33) |
+                         ((uint64_t)(material_on != 0) << 34) | ((uint64_t)use_q << 35);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        // first call of each kernel sets its smem attribute outside capture
+        int rc = enqueue_forward(h, B, full_policy, csr, material_on, use_q);
+        if (rc) return rc;
+        CB_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaGraph_t g = nullptr;
+        CB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_forward(h, B, full_policy, csr, material_on, use_q);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+        if (rc) {
+            if (g) cudaGraphDestroy(g);
+            return rc;
+        }
+        CB_CUDA(h, ce);
+        cudaGraphExec_t ge = nullptr;
+        cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        CB_CUDA(h, ie);
+        it = h->graphs.emplace(key, ge).first;
+    }
+    CB_CUDA(h, cudaGraphLaunch(it->second, h->stream));
+    return CB_OK;
+}
+
+int upload_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, const uint16_t* move_idx,
+                  const uint32_t* move_off) {
+    int rc = ensure_capacity(h, B);
+    if (rc) return rc;
+    memcpy(h->h_boards, boards, (size_t)B * sizeof(cb_board));
+    CB_CUDA(h, cudaMemcpyAsync(h->d_boards, h->h_boards, (size_t)B * sizeof(cb_board), cudaMemcpyHostToDevice, h->stream));
+    if (q) {
+        memcpy(h->h_q, q, (size_t)B * 4);
+        CB_CUDA(h, cudaMemcpyAsync(h->d_q, h->h_q, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->staged_moves = 0;
+    if (move_idx && move_off) {
+        const size_t n = move_off[B];
+        if (n > h->csr_cap) return fail(h, CB_EINVAL, "legal-move CSR larger than 256 moves per position");
+        memcpy(h->h_move_off, move_off, ((size_t)B + 1) * 4);
+        memcpy(h->h_move_idx, move_idx, n * 2);
+        CB_CUDA(h, cudaMemcpyAsync(h->d_move_off, h->h_move_off, ((size_t)B + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+        if (n) CB_CUDA(h, cudaMemcpyAsync(h->d_move_idx, h->h_move_idx, n * 2, cudaMemcpyHostToDevice, h->stream));
+        h->staged_moves = n;
+    }
+    return CB_OK;
+}
+
+}  // namespace
+
+// ============================================================== C ABI
+extern "C" {
+
+const char* cb_version(void) { return "caissa_b200 0.1 (sm_100a)"; }
+
+size_t cb_weight_count(int num_blocks, int hidden) {
+    const size_t H = hidden, S = hidden / 16;
+    size_t n = H * 17 * 9 + 4 * H;
+    n += (size_t)num_blocks * (2 * (H * H * 9 + 4 * H) + 2 * S * H);
+    n += H * H * 9 + 4 * H + 73 * H + 73;
+    n += H + 1 + 4 + 256 * 65 + 256 + 256 + 1 + 1;
+    return n;
+}
+
+int cb_create(cb_handle** out, int device, int num_blocks, int hidden, int dtype) {
+    if (!out) return CB_EINVAL;
+    *out = nullptr;
+    if ((hidden != 128 && hidden != 256) || num_blocks < 1 || num_blocks > 64 || dtype < 0 || dtype > 2) return CB_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return CB_ENODEV;
+    cb_handle* h = new (std::nothrow) cb_handle();
+    if (!h) return CB_ENOMEM;
+    h->device = device;
+    h->blocks = num_blocks;
+    h->hid = hidden;
+    h->dtype = dtype;
+    const char* ng = getenv("CB_NO_GRAPH");
+    h->use_graphs = !(ng && ng[0] == '1');
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete h;
+        return CB_ENODEV;
+    }
+    if (prop.major != 10) {  // sm_100a cubins only
+        delete h;
+        return CB_ENODEV;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreate(&h->ev2) != cudaSuccess || cudaEventCreate(&h->ev3) != cudaSuccess) {
+        cb_destroy(h);
+        return CB_ECUDA;
+    }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        cb_destroy(h);
+        return CB_ECUDA;
+    }
+    h->encode_tiled = (EncodeTiledFn)fn;
+    *out = h;
+    return CB_OK;
+}
+
+void cb_destroy(cb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_buffers(h);
+    for (auto& L : h->convs) { free_dev(L.w16); free_dev(L.w32); free_dev(L.bias); }
+    for (auto p : h->se_w1) free_dev(p);
+    for (auto p : h->se_w2) free_dev(p);
+    free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
+    free_dev(h->d_flush);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->ev3) cudaEventDestroy(h->ev3);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* cb_last_error(const cb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+int cb_is_available(const cb_handle* h) { return h && h->loaded ? 1 : 0; }
+
+int cb_launches_per_forward(const cb_handle* h) {
+    if (!h) return 0;
+    const int convs = 2 * h->blocks + 2;
+    return 1 + convs + (h->dtype == CB_DTYPE_FP32 ? h->blocks : 0) + 2;
+}
+
+int cb_get_timing(const cb_handle* h, cb_timing* out) {
+    if (!h || !out) return CB_EINVAL;
+    *out = h->timing;
+    return CB_OK;
+}
+void cb_reset_timing(cb_handle* h) {
+    if (h) h->timing = cb_timing{};
+}
+
+int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
+    if (!h || !blob) return CB_EINVAL;
+    if (n_floats != cb_weight_count(h->blocks, h->hid))
+        return fail(h, CB_EINVAL, "weight blob has " + std::to_string(n_floats) + " floats, expected " +
+                                      std::to_string(cb_weight_count(h->blocks, h->hid)));
+    CB_CUDA(h, cudaSetDevice(h->device));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    drop_graphs(h);
+    for (auto& L : h->convs) { free_dev(L.w16); free_dev(L.w32); free_dev(L.bias); }
+    for (auto p : h->se_w1) free_dev(p);
+    for (auto p : h->se_w2) free_dev(p);
+    h->convs.clear(); h->se_w1.clear(); h->se_w2.clear();
+    free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
+    h->p_wt = h->p_bias = h->v_w = h->fc_wt = h->fc_b = h->out_w = nullptr;
+    h->loaded = false;
+
+    const int H = h->hid, S = H / 16;
+    const float* cur = blob;
+    auto take = [&](size_t n) { const float* p = cur; cur += n; return p; };
+    auto upload = [&](const void* src, size_t bytes, void** dst) -> int {
+        CB_CUDA(h, cudaMalloc(dst, bytes));
+        CB_CUDA(h, cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+        return CB_OK;
+    };
+    // conv + BN -> folded layer.  w: [H][cin][3][3]; bn: gamma, beta, mean, var.
+    auto add_conv = [&](int cin) -> int {
+        const float* w = take((size_t)H * cin * 9);
+        const float* gamma = take(H); const float* beta = take(H); const float* mean = take(H); const float* var = take(H);
+        ConvLayer L;
+        L.cin = cin;
+        L.cin_pad = (cin + 63) / 64 * 64;
+        std::vector<float> scale(H), bias(H);
+        for (int co = 0; co < H; ++co) {
+            scale[co] = gamma[co] / sqrtf(var[co] + kBnEps);
+            bias[co] = beta[co] - mean[co] * scale[co];
+        }
+        int rc = upload(bias.data(), (size_t)H * 4, (void**)&L.bias);
+        if (rc) return rc;
+        if (h->dtype == CB_DTYPE_FP32) {
+            std::vector<float> w32((size_t)9 * cin * H);
+            for (int co = 0; co < H; ++co)
+                for (int ci = 0; ci < cin; ++ci)
+                    for (int t = 0; t < 9; ++t)
+                        w32[((size_t)t * cin + ci) * H + co] = w[((size_t)co * cin + ci) * 9 + t] * scale[co];
+            if ((rc = upload(w32.data(), w32.size() * 4, (void**)&L.w32))) return rc;
+        } else {
+            std::vector<uint16_t> w16((size_t)9 * H * L.cin_pad, 0);
+            for (int co = 0; co < H; ++co)
+                for (int ci = 0; ci < cin; ++ci)
+                    for (int t = 0; t < 9; ++t)
+                        w16[((size_t)t * H + co) * L.cin_pad + ci] = to16(w[((size_t)co * cin + ci) * 9 + t] * scale[co], h->dtype);
+            if ((rc = upload(w16.data(), w16.size() * 2, &L.w16))) return rc;
+            if ((rc = make_weight_map(h, L))) return rc;
+        }
+        h->convs.push_back(L);
+        return CB_OK;
+    };
+    int rc;
+    if ((rc = add_conv(17))) return rc;
+    for (int i = 0; i < h->blocks; ++i) {
+        if ((rc = add_conv(H))) return rc;
+        if ((rc = add_conv(H))) return rc;
+        float* d1 = nullptr; float* d2 = nullptr;
+        if ((rc = upload(take((size_t)S * H), (size_t)S * H * 4, (void**)&d1))) return rc;
+        h->se_w1.push_back(d1);
+        if ((rc = upload(take((size_t)H * S), (size_t)H * S * 4, (void**)&d2))) return rc;
+        h->se_w2.push_back(d2);
+    }
+    if ((rc = add_conv(H))) return rc;
+    {   // p_head [73][H] -> transposed [H][73]
+        const float* pw = take((size_t)73 * H);
+        std::vector<float> wt((size_t)H * 73);
+        for (int c = 0; c < 73; ++c)
+            for (int k = 0; k < H; ++k) wt[(size_t)k * 73 + c] = pw[(size_t)c * H + k];
+        if ((rc = upload(wt.data(), wt.size() * 4, (void**)&h->p_wt))) return rc;
+        if ((rc = upload(take(73), 73 * 4, (void**)&h->p_bias))) return rc;
+    }
+    if ((rc = upload(take(H), (size_t)H * 4, (void**)&h->v_w))) return rc;
+    h->v_conv_bias = *take(1);
+    {
+        const float g = *take(1), b = *take(1), m = *take(1), v = *take(1);
+        h->v_bn_scale = g / sqrtf(v + kBnEps);
+        h->v_bn_bias = b - m * h->v_bn_scale;
+    }
+    {   // v_fc [256][65] -> transposed [65][256]
+        const float* fw = take((size_t)256 * 65);
+        std::vector<float> wt((size_t)65 * 256);
+        for (int j = 0; j < 256; ++j)
+            for (int e = 0; e < 65; ++e) wt[(size_t)e * 256 + j] = fw[(size_t)j * 65 + e];
+        if ((rc = upload(wt.data(), wt.size() * 4, (void**)&h->fc_wt))) return rc;
+        if ((rc = upload(take(256), 256 * 4, (void**)&h->fc_b))) return rc;
+        if ((rc = upload(take(256), 256 * 4, (void**)&h->out_w))) return rc;
+    }
+    h->out_b = *take(1);
+    {   // k = 0.47 * softplus(k_logit)  (python/model.py:109), evaluated like torch: log1p(exp(x)), x>20 -> x
+        const float kl = *take(1);
+        const float sp = kl > 20.0f ? kl : log1pf(expf(kl));
+        h->k = 0.47f * sp;
+    }
+    if ((size_t)(cur - blob) != n_floats) return fail(h, CB_EINVAL, "internal: blob walk mismatch");
+    h->loaded = true;
+    return CB_OK;
+}
+
+int cb_encode(cb_handle* h, const cb_board* boards, int B, float* planes) {
+    if (!h || !boards || !planes || B < 0) return CB_EINVAL;
+    if (B == 0) return CB_OK;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    int rc = upload_leaves(h, boards, nullptr, B, nullptr, nullptr);
+    if (rc) return rc;
+    if ((rc = ensure_scratch(h, (size_t)B * CB_PLANES))) return rc;
+    encode_nchw_f32_kernel<<<(B * 64 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, h->d_scratch);
+    CB_CUDA(h, cudaGetLastError());
+    CB_CUDA(h, cudaMemcpyAsync(planes, h->d_scratch, (size_t)B * CB_PLANES * 4, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+
+int cb_pst_eval_cp(cb_handle* h, const cb_board* boards, int B, int32_t* cp) {
+    if (!h || !boards || !cp || B < 0) return CB_EINVAL;
+    if (B == 0) return CB_OK;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    int rc = upload_leaves(h, boards, nullptr, B, nullptr, nullptr);
+    if (rc) return rc;
+    if ((rc = ensure_scratch(h, (size_t)B))) return rc;
+    pst_eval_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->d_boards, B, (int32_t*)h->d_scratch);
+    CB_CUDA(h, cudaGetLastError());
+    CB_CUDA(h, cudaMemcpyAsync(cp, h->d_scratch, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+
+static int read_small(cb_handle* h, int B, float* v_logit, float* v_final, float* k) {
+    float* s = h->h_small;
+    CB_CUDA(h, cudaMemcpyAsync(s, h->d_vlogit, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaMemcpyAsync(s + h->cap, h->d_vfinal, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaMemcpyAsync(s + 2 * (size_t)h->cap, h->d_k, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaEventRecord(h->ev3, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (v_logit) memcpy(v_logit, s, (size_t)B * 4);
+    if (v_final) memcpy(v_final, s + h->cap, (size_t)B * 4);
+    if (k) memcpy(k, s + 2 * (size_t)h->cap, (size_t)B * 4);
+    return CB_OK;
+}
+
+static void account(cb_handle* h, int B) {
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, h->ev0, h->ev1);
+    cudaEventElapsedTime(&b, h->ev1, h->ev2);
+    cudaEventElapsedTime(&c, h->ev2, h->ev3);
+    h->timing.calls++;
+    h->timing.positions += (uint64_t)B;
+    h->timing.h2d_ms += a;
+    h->timing.forward_ms += b;
+    h->timing.d2h_ms += c;
+}
+
+int cb_predict_batch(cb_handle* h, const cb_board* boards, const float* q, const uint8_t* qflag, int B,
+                     float* policy_probs, float* v_logit, float* k) {
+    (void)qflag;  // the network ignores scalars[:,1] (python/model.py:106)
+    if (!h || !boards || B < 0) return CB_EINVAL;
+    if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
+    if (B == 0) return CB_OK;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    CB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    int rc = upload_leaves(h, boards, q, B, nullptr, nullptr);
+    if (rc) return rc;
+    if (policy_probs && h->probs_cap < h->cap) {
+        free_dev(h->d_probs);
+        h->d_probs = nullptr;
+        drop_graphs(h);
+        CB_CUDA(h, cudaMalloc(&h->d_probs, (size_t)h->cap * CB_POLICY_SIZE * 4));
+        h->probs_cap = h->cap;
+    }
+    CB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if ((rc = run_forward(h, B, policy_probs != nullptr, false, 1, q != nullptr))) return rc;
+    CB_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+    if (policy_probs)
+        CB_CUDA(h, cudaMemcpyAsync(policy_probs, h->d_probs, (size_t)B * CB_POLICY_SIZE * 4, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = read_small(h, B, v_logit, nullptr, k))) return rc;
+    account(h, B);
+    return CB_OK;
+}
+
+int cb_eval_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, int material_on,
+                   const uint16_t* move_idx, const uint32_t* move_off, float* priors, float* v_logit,
+                   float* v_final, float* k) {
+    if (!h || !boards || B < 0) return CB_EINVAL;
+    if ((move_idx == nullptr) != (move_off == nullptr) || (move_off && !priors)) return CB_EINVAL;
+    if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
+    if (B == 0) return CB_OK;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    CB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    int rc = upload_leaves(h, boards, q, B, move_idx, move_off);
+    if (rc) return rc;
+    CB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if ((rc = run_forward(h, B, false, move_off != nullptr, material_on, q != nullptr))) return rc;
+    CB_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+    const size_t n = h->staged_moves;
+    if (n) CB_CUDA(h, cudaMemcpyAsync(h->h_priors, h->d_priors, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = read_small(h, B, v_logit, v_final, k))) return rc;
+    if (n) memcpy(priors, h->h_priors, n * 4);
+    account(h, B);
+    return CB_OK;
+}
+
+int cb_stage_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, const uint16_t* move_idx,
+                    const uint32_t* move_off) {
+    if (!h || !boards || B <= 0) return CB_EINVAL;
+    if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    int rc = upload_leaves(h, boards, q, B, move_idx, move_off);
+    if (rc) return rc;
+    if (!q) CB_CUDA(h, cudaMemsetAsync(h->d_q, 0, (size_t)B * 4, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->staged_B = B;
+    return CB_OK;
+}
+
+int cb_time_resident(cb_handle* h, int material_on, int iters, int flush_l2, float* ms_each) {
+    if (!h || iters <= 0 || !ms_each) return CB_EINVAL;
+    if (!h->staged_B) return fail(h, CB_ESTATE, "nothing staged: call cb_stage_leaves first");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    if (flush_l2 && !h->d_flush) CB_CUDA(h, cudaMalloc(&h->d_flush, kFlushBytes));
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters);
+    for (auto& e : ev) CB_CUDA(h, cudaEventCreate(&e));
+    int rc = CB_OK;
+    for (int i = 0; i < iters && !rc; ++i) {
+        if (flush_l2) CB_CUDA(h, cudaMemsetAsync(h->d_flush, i & 0xFF, kFlushBytes, h->stream));
+        CB_CUDA(h, cudaEventRecord(ev[2 * i], h->stream));
+        rc = run_forward(h, h->staged_B, false, h->staged_moves > 0, material_on, true);
+        CB_CUDA(h, cudaEventRecord(ev[2 * i + 1], h->stream));
+    }
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (!rc && se == cudaSuccess)
+        for (int i = 0; i < iters; ++i) cudaEventElapsedTime(&ms_each[i], ev[2 * i], ev[2 * i + 1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
+    CB_CUDA(h, se);
+    return CB_OK;
+}
+
+int cb_time_conv_layers(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches) {
+    if (!h || iters <= 0) return CB_EINVAL;
+    if (!h->staged_B) return fail(h, CB_ESTATE, "nothing staged: call cb_stage_leaves first");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    const int nconv = 2 * h->blocks + 2;
+    std::vector<cudaEvent_t> ev(2 * (size_t)nconv);
+    for (auto& e : ev) CB_CUDA(h, cudaEventCreate(&e));
+    double total = 0.0;
+    int rc = CB_OK;
+    for (int i = 0; i < iters && !rc; ++i) {
+        rc = enqueue_tower(h, h->staged_B, &ev);
+        if (rc) break;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(h, CB_ECUDA, "sync failed in cb_time_conv_layers"); break; }
+        // dominant kernel = the HID->HID layers: every conv launch except the start conv (index 0)
+        for (int l = 1; l < nconv; ++l) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[2 * l], ev[2 * l + 1]);
+            total += ms;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
+    if (conv_ms_total) *conv_ms_total = (float)total;
+    if (n_conv_launches) *n_conv_launches = nconv - 1;
+    return CB_OK;
+}
+
+int cb_read_resident(cb_handle* h, float* priors, float* v_logit, float* v_final, float* k) {
+    if (!h) return CB_EINVAL;
+    if (!h->staged_B) return fail(h, CB_ESTATE, "nothing staged");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    const size_t n = h->staged_moves;
+    if (priors && n) CB_CUDA(h, cudaMemcpyAsync(h->h_priors, h->d_priors, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    int rc = read_small(h, h->staged_B, v_logit, v_final, k);
+    if (rc) return rc;
+    if (priors && n) memcpy(priors, h->h_priors, n * 4);
+    return CB_OK;
+}
+
+int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches) {
+    if (!h) return CB_EINVAL;
+    drop_graphs(h);
+    h->layer_limit = n_conv_launches;
+    return CB_OK;
+}
+
+int cb_debug_backbone(cb_handle* h, int B, float* out) {
+    if (!h) return CB_EINVAL;
+    return cb_debug_act(h, B, backbone_index(h->blocks), out);
+}
+
+int cb_debug_act(cb_handle* h, int B, int buf, float* out) {
+    if (!h || !out || B <= 0 || B > h->cap || buf < 0 || buf > 2) return CB_EINVAL;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    const int total = B * 64 * h->hid;
+    int rc = ensure_scratch(h, (size_t)total);
+    if (rc) return rc;
+    const void* src = h->d_act[buf];
+    const int grid = (total + 255) / 256;
+    if (h->dtype == CB_DTYPE_FP32)
+        nhwc_to_nchw_f32_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)src, h->hid, total, h->d_scratch);
+    else if (h->dtype == CB_DTYPE_BF16)
+        nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, h->stream>>>((const __nv_bfloat16*)src, h->hid, total, h->d_scratch);
+    else
+        nhwc_to_nchw_f32_kernel<__half><<<grid, 256, 0, h->stream>>>((const __half*)src, h->hid, total, h->d_scratch);
+    CB_CUDA(h, cudaGetLastError());
+    CB_CUDA(h, cudaMemcpyAsync(out, h->d_scratch, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+
+}  // extern "C"
