@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py — OracleNet leaf evaluations per second at batch 1024 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of B synthetic leaf positions: packed
+bitboards (+ dM scalar, + legal-move CSR) -> planes -> OracleNet 6x128 -> softmax over the legal
+moves and tanh(v_logit + k*dM).  Workload = BASELINE.json configs[1] at B = 1024 (the batch the
+metric is quoted on).  Positions: seeded random legal playouts; weights: the reference's
+initialisation law with live heads (oracle/weights.py variant B); both synthetic.
+
+  value    whole-job evals/s with inputs already resident in HBM: K replays of the captured
+           forward graph, each timed with CUDA events on the launching stream (inside the
+           library), L2 flushed (256 MiB rewrite) between steps; max over ranks.
+  e2e      same metric through the public C-ABI call cb_eval_leaves with HOST buffers: H2D of
+           boards/q/CSR and D2H of priors/values inside the timed region, every step.
+  roofline the dominant kernel (3x3 conv HID->HID, tcgen05): algorithmic FLOPs per launch /
+           mean CUDA-event duration of its launches, against the measured bf16 peak.
+  cpu_baseline  the reference's own traced TorchScript module (oracle/_ref, built from the
+           reference sources) on the host cores, bounded sample; "port" if _ref is absent.
+
+N > 1: one process per GPU (torchrun), each rank evaluates its own independent batch — the path
+shards by position with no collective — so scaling is "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "neurosymbolic-mcts_b200"))
+
+METRIC = "OracleNet leaf evals/sec @batch 1024"
+UNIT = "evals/s"
+FLOPS_PER_EVAL = {(6, 128): 249144320, (10, 256): 1593082880}
+WEIGHT_SEED = 1803  # variant B seed of tests/golden/net_6x128_B.npz (value head alive)
+
+
+def conv_flops_per_position(hidden):
+    return 2 * 9 * hidden * hidden * 64  # one HID->HID 3x3 layer, 2*MAC, padding not credited
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("bf16_tflops"), "measured"
+    return 1400.0, 1590.0, "fallback"  # B200_PROFILING.md fallback (sustained ~1.4, burst 1.59 PF)
+
+
+def make_workload(args, rank):
+    from oracle import pyoracle, weights as W
+    boards, idx, off, _ = pyoracle.random_positions(20261019 + 7919 * rank, args.batch, 160)
+    q = pyoracle.static_q(boards)
+    blob = W.flatten(W.make_weights(args.blocks, args.hidden, WEIGHT_SEED, "B"), args.blocks, args.hidden)
+    return boards, q, idx, off, blob
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled (NVML, every 5 ms) DURING the measured region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.t = index, [], False, None
+        self.max_mhz = None
+
+    def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+
+            def run():
+                while not self.stop:
+                    try:
+                        self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                          nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.t = threading.Thread(target=run, daemon=True)
+            self.t.start()
+        except Exception:
+            self.t = None
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.t:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        bits = 0
+        for _, r in self.rows:
+            bits |= r
+        return {"sm_mhz": float(np.median([c for c, _ in self.rows])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for n, b in names.items() if bits & b), "samples": len(self.rows)}
+
+
+def cpu_reference_module(blocks, hidden):
+    """The reference's traced TorchScript module if oracle/_ref has it, else the oracle port."""
+    import torch
+    name = "oraclenet_%dx%d_B.pt" % (blocks, hidden)
+    path = os.path.join(REPO, "oracle", "_ref", name)
+    if os.path.exists(path):
+        return torch.jit.load(path, map_location="cpu").eval(), "reference"
+    return None, "port"
+
+
+def time_cpu_path(args, boards, q, idx, off, blob, budget_s, steps, warmup):
+    """Reference CPU implementation of the path on a bounded sample: encode (C restatement of
+    board_to_planes) -> traced OracleNet on libtorch CPU -> exp -> priors (C restatement)."""
+    import torch
+    from oracle import net, pyoracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    module, kind = cpu_reference_module(args.blocks, args.hidden)
+    raw = [pyoracle.array_to_board(b) for b in boards]
+
+    def one_step(n):
+        planes = pyoracle.planes_batch(boards[:n])
+        if module is not None:
+            scal = torch.from_numpy(np.stack([q[:n], np.ones(n, dtype=np.float32)], axis=1))
+            with torch.no_grad():
+                logp, v, k = module(torch.from_numpy(planes), scal)
+            probs = logp.exp().numpy()
+        else:
+            logp, v, k = net.forward(blob, args.blocks, args.hidden, planes, q[:n])
+            probs = np.exp(logp)
+        for i in range(n):
+            m = idx[off[i]:off[i + 1]]
+            p = probs[i][m]
+            s = p.sum()
+            p = p / s if s > 0 else np.full(len(m), 1.0 / max(len(m), 1), dtype=np.float32)
+        return n
+
+    n = min(256, args.batch)
+    one_step(min(n, 32))
+    t0 = time.perf_counter(); one_step(n); t1 = time.perf_counter() - t0
+    # size the per-step sample so the whole (warmup + steps) run fits the budget
+    per_pos = t1 / n
+    n = int(max(16, min(args.batch, budget_s / max(steps + warmup, 1) / per_pos)))
+    for _ in range(warmup):
+        one_step(n)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step(n)
+    dt = time.perf_counter() - t0
+    del raw
+    return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d steps x %d positions of the same batch (encode + traced OracleNet fp32 on libtorch CPU "
+                      "+ exp + legal-move priors), %d torch threads" % (steps, n, cores)}, dt / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--blocks", type=int, default=6)
+    ap.add_argument("--hidden", type=int, default=128)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = "configs[1]: batched leaf eval, OracleNet %dx%d, batch %d, one batch per GPU" % (
+        args.blocks, args.hidden, args.batch)
+    config = {"workload": workload, "batch_per_gpu": args.batch, "blocks": args.blocks, "hidden": args.hidden,
+              "positions": "seeded random legal playouts (oracle chess substrate), material dM = static PeSTO/100",
+              "weights": "reference init law, heads de-zeroed (variant B, numpy seed %d)" % WEIGHT_SEED,
+              "l2": "flushed (256 MiB rewrite) between timed steps", "material_on": True}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        boards, q, idx, off, blob = make_workload(args, 0)
+        cpu, ms = time_cpu_path(args, boards, q, idx, off, blob, 150.0, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import caissa_b200 as cb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    boards, q, idx, off, blob = make_workload(args, rank)
+    ev = cb.Evaluator(args.blocks, args.hidden, args.dtype, device=local_rank)
+    ev.load_weights(blob)
+    B, K, W = args.batch, args.steps, args.warmup
+
+    # ---- device-resident throughput (value)
+    ev.stage_leaves(boards, q, idx, off)
+    ev.time_resident(W, material_on=True, flush_l2=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        ms_each = ev.time_resident(K, material_on=True, flush_l2=True)
+        barrier()
+        wall = time.perf_counter() - t_wall0
+        clk = clocks.summary()
+    dev_ms = float(ms_each.sum())
+    pri, v, vf, kk = ev.read_resident()
+    assert np.isfinite(pri).all() and np.isfinite(vf).all() and np.abs(vf).max() <= 1.0
+
+    # ---- roofline of the dominant kernel (HID->HID 3x3 conv)
+    ev.time_conv_layers(2)
+    conv_ms, n_conv = ev.time_conv_layers(max(K // 2, 5))
+    iters_conv = max(K // 2, 5)
+    launch_ms = conv_ms / (iters_conv * n_conv)
+    flops_launch = conv_flops_per_position(args.hidden) * ((B + 1) // 2 * 2)
+
+    # ---- end to end through the public C ABI with host buffers
+    for _ in range(W):
+        ev.eval_leaves(boards, q, idx, off)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        out = ev.eval_leaves(boards, q, idx, off)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = int(boards.nbytes + q.nbytes + idx.nbytes + off.nbytes)
+    d2h = int(out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes)
+
+    # ---- max over ranks
+    t = torch.tensor([dev_ms, e2e_s * 1e3, launch_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, launch_ms = [float(x) for x in t.tolist()]
+    value = world * B * K / (dev_ms * 1e-3)
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        sustained, burst, how = load_peaks()
+        achieved = flops_launch / (launch_ms * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(REPO, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K, "api": "cb_eval_leaves (host buffers, synchronous)"},
+            "gpu_launches": int(ev.launches_per_forward() * K * world),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                         "frac": achieved / sustained, "traffic": traffic,
+                         "kernel": "conv3x3_umma_kernel<%d> (HID->HID layers, %d launches/step)" % (args.hidden, n_conv),
+                         "flops_per_launch": flops_launch, "launch_ms": launch_ms,
+                         "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json (%s); burst %.1f" % (how, burst)},
+            "whole_path_tflops": value / world * FLOPS_PER_EVAL.get((args.blocks, args.hidden), 0) / 1e12,
+            "wall_s_timed_region": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = time_cpu_path(args, boards, q, idx, off, blob, 20.0, 3, 1)
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
