@@ -134,6 +134,9 @@ int cb_stage_leaves(cb_handle* h, const cb_board* boards, const float* q, int B,
                     const uint16_t* move_idx, const uint32_t* move_off);
 int cb_time_resident(cb_handle* h, int material_on, int iters, int flush_l2, float* ms_each);
 int cb_time_conv_layers(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches);
+/* per_layer_ms[2*blocks+2] (nullable): mean event time of every conv launch, start conv first. */
+int cb_time_conv_layers_detail(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches,
+                               float* per_layer_ms);
 int cb_read_resident(cb_handle* h, float* priors, float* v_logit, float* v_final, float* k);
 
 /* Debug / parity hook: copy the backbone activation (after the last residual

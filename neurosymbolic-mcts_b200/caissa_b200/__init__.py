@@ -50,6 +50,7 @@ SIGNATURES = {
     "cb_stage_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_time_resident": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_time_conv_layers": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
+    "cb_time_conv_layers_detail": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP]),
     "cb_read_resident": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "cb_debug_backbone": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
     "cb_debug_act": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
@@ -187,6 +188,11 @@ class Evaluator:
         n = ctypes.c_int(0)
         self._check(self._L.cb_time_conv_layers(self._h, iters, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def time_conv_layers_detail(self, iters):
+        per = np.zeros(2 * self.num_blocks + 2, dtype=np.float32)
+        self._check(self._L.cb_time_conv_layers_detail(self._h, iters, None, None, _ptr(per)))
+        return per
 
     def read_resident(self):
         B, nm = self._staged

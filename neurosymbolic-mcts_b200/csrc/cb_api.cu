@@ -82,7 +82,7 @@ struct cb_handle {
     float* d_scratch = nullptr; // debug / encode hook output
     size_t scratch_floats = 0;
     void* d_flush = nullptr;
-    CUtensorMap tm_x0, tm_act[3];
+    CUtensorMap tm_x0, tm_act_ld[3], tm_act_st[3];
 
     // pinned staging
     cb_board* h_boards = nullptr;
@@ -142,14 +142,17 @@ void drop_graphs(cb_handle* h) {
     h->graphs.clear();
 }
 
-int make_act_map(cb_handle* h, CUtensorMap* tm, void* base, int channels, int boards) {
-    const cuuint64_t dims[4] = {(cuuint64_t)channels, 8, 8, (cuuint64_t)boards};
-    const cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 16, (cuuint64_t)channels * 128};
-    const cuuint32_t box[4] = {64, 8, 8, 2};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
+// 5-D map over the pair-interleaved activation act[pair][y][b2][x][C]; box_y = 10 for the
+// halo'd slab loads (fetched at y = -1), 8 for residual-free output stores.
+int make_act_map(cb_handle* h, CUtensorMap* tm, void* base, int channels, int boards, int box_y) {
+    const cuuint64_t C = (cuuint64_t)channels;
+    const cuuint64_t dims[5] = {C, 8, 2, 8, (cuuint64_t)boards / 2};
+    const cuuint64_t strides[4] = {C * 2, C * 16, C * 32, C * 256};
+    const cuuint32_t box[5] = {64, 8, 2, (cuuint32_t)box_y, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUtensorMapDataType dt =
         h->dtype == CB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    CUresult r = h->encode_tiled(tm, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = h->encode_tiled(tm, dt, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
@@ -222,11 +225,11 @@ int ensure_capacity(cb_handle* h, int B) {
     h->cap = cap;
     h->csr_cap = csr;
     if (h->dtype != CB_DTYPE_FP32) {
-        int rc = make_act_map(h, &h->tm_x0, h->d_x0, 64, cap);
+        int rc = make_act_map(h, &h->tm_x0, h->d_x0, 64, cap, 10);
         if (rc) return rc;
         for (int i = 0; i < 3; ++i) {
-            rc = make_act_map(h, &h->tm_act[i], h->d_act[i], h->hid, cap);
-            if (rc) return rc;
+            if ((rc = make_act_map(h, &h->tm_act_ld[i], h->d_act[i], h->hid, cap, 10))) return rc;
+            if ((rc = make_act_map(h, &h->tm_act_st[i], h->d_act[i], h->hid, cap, 8))) return rc;
         }
     }
     return CB_OK;
@@ -246,7 +249,8 @@ template <int HID, bool BF16>
 int launch_conv_umma_t(cb_handle* h, const CUtensorMap& tin, const ConvLayer& L, const CUtensorMap& tout, int mode,
                        const ConvParams& p) {
     using Cfg = ConvCfg<HID>;
-    const int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+    const int rounds = (p.num_tiles + Cfg::kTiles - 1) / Cfg::kTiles;
+    const int grid = rounds < h->sm_count ? rounds : h->sm_count;
     if (mode == MODE_RELU) {
         auto kern = conv3x3_umma_kernel<HID, BF16, MODE_RELU>;
         CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -290,11 +294,11 @@ int launch_policy_t(cb_handle* h, const T* p, int B, const PolicyOut& po) {
     if (h->hid == 128) {
         auto kern = policy_head_kernel<T, 128>;
         CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<B, kPolicyThreads, smem, h->stream>>>(p, h->p_wt, h->p_bias, po);
+        kern<<<B, kPolicyThreads, smem, h->stream>>>(p, h->p_wt, h->p_bias, po, h->dtype != CB_DTYPE_FP32);
     } else {
         auto kern = policy_head_kernel<T, 256>;
         CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<B, kPolicyThreads, smem, h->stream>>>(p, h->p_wt, h->p_bias, po);
+        kern<<<B, kPolicyThreads, smem, h->stream>>>(p, h->p_wt, h->p_bias, po, h->dtype != CB_DTYPE_FP32);
     }
     CB_CUDA(h, cudaGetLastError());
     return CB_OK;
@@ -356,23 +360,27 @@ int enqueue_tower(cb_handle* h, int B, std::vector<cudaEvent_t>* ev) {
     }
     ConvParams p = {};
     p.num_tiles = Bpad / 2;
+    const char* dbg_env = getenv("CB_DBG");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    p.dbg = dbg;
     int rc;
     // start conv: x0 (64-channel padded planes) -> act[0]
     p.kc_in = 1;
     p.bias = h->convs[0].bias;
     if (stop()) return CB_OK;
     if ((rc = mark())) return rc;
-    if ((rc = launch_conv_umma(h, h->tm_x0, h->convs[0], h->tm_act[0], MODE_RELU, p))) return rc;
+    if ((rc = launch_conv_umma(h, h->tm_x0, h->convs[0], h->tm_act_st[0], MODE_RELU, p))) return rc;
     if ((rc = mark())) return rc;
     for (int i = 0; i < h->blocks; ++i) {
         const int nxt = cur == 0 ? 2 : 0;
         ConvParams p1 = {};
+        p1.dbg = dbg;
         p1.num_tiles = Bpad / 2;
         p1.kc_in = h->hid / 64;
         p1.bias = h->convs[1 + 2 * i].bias;
         if (stop()) return CB_OK;
         if ((rc = mark())) return rc;
-        if ((rc = launch_conv_umma(h, h->tm_act[cur], h->convs[1 + 2 * i], h->tm_act[1], MODE_RELU, p1))) return rc;
+        if ((rc = launch_conv_umma(h, h->tm_act_ld[cur], h->convs[1 + 2 * i], h->tm_act_st[1], MODE_RELU, p1))) return rc;
         if ((rc = mark())) return rc;
         ConvParams p2 = p1;
         p2.bias = h->convs[2 + 2 * i].bias;
@@ -385,17 +393,18 @@ int enqueue_tower(cb_handle* h, int B, std::vector<cudaEvent_t>* ev) {
         }
         if (stop()) return CB_OK;
         if ((rc = mark())) return rc;
-        if ((rc = launch_conv_umma(h, h->tm_act[1], h->convs[2 + 2 * i], h->tm_act[nxt], MODE_SE_RES, p2))) return rc;
+        if ((rc = launch_conv_umma(h, h->tm_act_ld[1], h->convs[2 + 2 * i], h->tm_act_st[nxt], MODE_SE_RES, p2))) return rc;
         if ((rc = mark())) return rc;
         cur = nxt;
     }
     ConvParams pp = {};
+    pp.dbg = dbg;
     pp.num_tiles = Bpad / 2;
     pp.kc_in = h->hid / 64;
     pp.bias = h->convs[last].bias;
     if (stop()) return CB_OK;
     if ((rc = mark())) return rc;
-    if ((rc = launch_conv_umma(h, h->tm_act[cur], h->convs[last], h->tm_act[1], MODE_RELU, pp))) return rc;
+    if ((rc = launch_conv_umma(h, h->tm_act_ld[cur], h->convs[last], h->tm_act_st[1], MODE_RELU, pp))) return rc;
     if ((rc = mark())) return rc;
     return CB_OK;
 }
@@ -406,9 +415,9 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     if (h->dtype == CB_DTYPE_FP32) {
         encode_nhwc_f32_kernel<<<(B * 64 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, (float*)h->d_x0);
     } else if (h->dtype == CB_DTYPE_BF16) {
-        encode_nhwc16_kernel<true><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, (uint4*)h->d_x0);
+        encode_pair16_kernel<true><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, (uint4*)h->d_x0);
     } else {
-        encode_nhwc16_kernel<false><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, (uint4*)h->d_x0);
+        encode_pair16_kernel<false><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, (uint4*)h->d_x0);
     }
     CB_CUDA(h, cudaGetLastError());
     int rc = enqueue_tower(h, B, nullptr);
@@ -433,6 +442,7 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     vp.out_b = h->out_b;
     vp.k = h->k;
     vp.material_on = material_on;
+    vp.pair_layout = h->dtype != CB_DTYPE_FP32;
     vp.B = B;
     vp.v_logit = h->d_vlogit;
     vp.v_final = h->d_vfinal;
@@ -831,6 +841,11 @@ int cb_time_resident(cb_handle* h, int material_on, int iters, int flush_l2, flo
 }
 
 int cb_time_conv_layers(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches) {
+    return cb_time_conv_layers_detail(h, iters, conv_ms_total, n_conv_launches, nullptr);
+}
+
+int cb_time_conv_layers_detail(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches,
+                               float* per_layer_ms) {
     if (!h || iters <= 0) return CB_EINVAL;
     if (!h->staged_B) return fail(h, CB_ESTATE, "nothing staged: call cb_stage_leaves first");
     CB_CUDA(h, cudaSetDevice(h->device));
@@ -844,10 +859,11 @@ int cb_time_conv_layers(cb_handle* h, int iters, float* conv_ms_total, int* n_co
         if (rc) break;
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(h, CB_ECUDA, "sync failed in cb_time_conv_layers"); break; }
         // dominant kernel = the HID->HID layers: every conv launch except the start conv (index 0)
-        for (int l = 1; l < nconv; ++l) {
+        for (int l = 0; l < nconv; ++l) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev[2 * l], ev[2 * l + 1]);
-            total += ms;
+            if (l >= 1) total += ms;
+            if (per_layer_ms) per_layer_ms[l] = (i == 0 ? 0.0f : per_layer_ms[l]) + ms / iters;
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);
@@ -890,11 +906,11 @@ int cb_debug_act(cb_handle* h, int B, int buf, float* out) {
     const void* src = h->d_act[buf];
     const int grid = (total + 255) / 256;
     if (h->dtype == CB_DTYPE_FP32)
-        nhwc_to_nchw_f32_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)src, h->hid, total, h->d_scratch);
+        act_to_nchw_f32_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)src, h->hid, total, 0, h->d_scratch);
     else if (h->dtype == CB_DTYPE_BF16)
-        nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, h->stream>>>((const __nv_bfloat16*)src, h->hid, total, h->d_scratch);
+        act_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, h->stream>>>((const __nv_bfloat16*)src, h->hid, total, 1, h->d_scratch);
     else
-        nhwc_to_nchw_f32_kernel<__half><<<grid, 256, 0, h->stream>>>((const __half*)src, h->hid, total, h->d_scratch);
+        act_to_nchw_f32_kernel<__half><<<grid, 256, 0, h->stream>>>((const __half*)src, h->hid, total, 1, h->d_scratch);
     CB_CUDA(h, cudaGetLastError());
     CB_CUDA(h, cudaMemcpyAsync(out, h->d_scratch, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
     CB_CUDA(h, cudaStreamSynchronize(h->stream));

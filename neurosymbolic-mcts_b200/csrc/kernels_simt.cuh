@@ -16,6 +16,13 @@
 
 namespace cb {
 
+// Row of (board b, pixel px = y*8 + x) in the pair-interleaved activation layout
+// act[pair][y][b2][x][C] used by the tensor-core tower (see conv_umma.cuh); plain NHWC
+// [b][px] for the exact-mode tower.
+__host__ __device__ __forceinline__ int act_row(int b, int px, bool pair_layout) {
+    return pair_layout ? ((b >> 1) * 128 + (((px >> 3) * 2 + (b & 1)) << 3) + (px & 7)) : (b * 64 + px);
+}
+
 // ------------------------------------------------------------------ encoder
 // 17-bit plane mask of one input pixel (row, col) of the side-to-move view.
 // bit p set <=> planes[p][row][col] == 1.0 in the reference's board_to_planes.
@@ -58,24 +65,26 @@ __global__ void encode_nhwc_f32_kernel(const cb_board* __restrict__ boards, int 
     for (int p = 0; p < 17; ++p) o[p] = (m >> p) & 1u ? 1.0f : 0.0f;
 }
 
-// NHWC 16-bit [Bpad][64][64]: channels 0..16 are the planes, 17..63 zero (K padding
-// of the start conv to one 64-channel TMA/UMMA chunk).  8 threads per pixel, one
-// 16-byte store each => fully coalesced 512 B per warp instruction.  Boards at
-// index >= B (batch padded to a whole tile) are written as zeros.
+// Pair-interleaved 16-bit [Bpad/2][8 y][2 b2][8 x][64]: channels 0..16 are the planes, 17..63
+// zero (K padding of the start conv to one 64-channel TMA/UMMA chunk).  8 threads per pixel
+// row, one 16-byte store each => fully coalesced 512 B per warp instruction.  Boards at index
+// >= B (batch padded to a whole pair) are written as zeros.
 template <bool BF16>
-__global__ void encode_nhwc16_kernel(const cb_board* __restrict__ boards, int B, int Bpad, uint4* __restrict__ out) {
+__global__ void encode_pair16_kernel(const cb_board* __restrict__ boards, int B, int Bpad, uint4* __restrict__ out) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= Bpad * 512) return;
-    const int j = gid & 7, pixel = gid >> 3;
-    const int b = pixel >> 6, px = pixel & 63;
+    const int j = gid & 7, grow = gid >> 3;          // global pixel row = pair*128 + (y*2+b2)*8 + x
+    const int m = grow & 127;
+    const int b = (grow >> 7) * 2 + ((m >> 3) & 1);
+    const int y = m >> 4, x = m & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (j < 3 && b < B) {
-        const uint32_t m = pixel_plane_mask(boards + b, px >> 3, px & 7) >> (j * 8);
+        const uint32_t msk = pixel_plane_mask(boards + b, y, x) >> (j * 8);
         const uint32_t one = BF16 ? 0x3F80u : 0x3C00u;
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            w[i] = ((m >> (2 * i)) & 1u ? one : 0u) | ((m >> (2 * i + 1)) & 1u ? (one << 16) : 0u);
+            w[i] = ((msk >> (2 * i)) & 1u ? one : 0u) | ((msk >> (2 * i + 1)) & 1u ? (one << 16) : 0u);
         v = make_uint4(w[0], w[1], w[2], w[3]);
     }
     out[gid] = v;
@@ -214,7 +223,8 @@ constexpr int kPolicyThreads = 320;  // 4 pixel groups x 73 planes = 292 active 
 // renormalised in list order.
 template <typename T, int HID>
 __global__ void __launch_bounds__(kPolicyThreads)
-policy_head_kernel(const T* __restrict__ p, const float* __restrict__ wt, const float* __restrict__ bias, PolicyOut po) {
+policy_head_kernel(const T* __restrict__ p, const float* __restrict__ wt, const float* __restrict__ bias, PolicyOut po,
+                   int pair_layout) {
     extern __shared__ float sm[];
     float* s_p = sm;                      // [64][HID]
     float* s_w = s_p + 64 * HID;          // [HID][73]
@@ -222,8 +232,10 @@ policy_head_kernel(const T* __restrict__ p, const float* __restrict__ wt, const 
     __shared__ float s_red[16];
     __shared__ float s_total;
     const int b = blockIdx.x, tid = threadIdx.x;
-    const T* pb = p + static_cast<size_t>(b) * 64 * HID;
-    for (int i = tid; i < 64 * HID; i += kPolicyThreads) s_p[i] = to_f32<T>(pb[i]);
+    for (int i = tid; i < 64 * HID; i += kPolicyThreads) {
+        const int px = i / HID, c = i % HID;
+        s_p[i] = to_f32<T>(p[static_cast<size_t>(act_row(b, px, pair_layout != 0)) * HID + c]);
+    }
     for (int i = tid; i < HID * 73; i += kPolicyThreads) s_w[i] = wt[i];
     __syncthreads();
     if (tid < 292) {
@@ -305,6 +317,7 @@ struct ValueParams {
     float out_b;
     float k;               // 0.47 * softplus(k_logit)
     int material_on;
+    int pair_layout;       // v_pre indexed by act_row()
     int B;
     float* v_logit;        // [B]
     float* v_final;        // [B] tanh(v_logit + k q) or tanh(v_logit)
@@ -323,7 +336,7 @@ __global__ void __launch_bounds__(256) value_head_kernel(const ValueParams vp) {
         float v = 0.0f;
         if (b < vp.B) {
             if (e < 64)
-                v = fmaxf((vp.v_pre[static_cast<size_t>(b) * 64 + e] + vp.conv_bias) * vp.bn_scale + vp.bn_bias, 0.0f);
+                v = fmaxf((vp.v_pre[act_row(b, e, vp.pair_layout != 0)] + vp.conv_bias) * vp.bn_scale + vp.bn_bias, 0.0f);
             else
                 v = vp.q ? vp.q[b] : 0.0f;
         }
@@ -356,13 +369,15 @@ __global__ void __launch_bounds__(256) value_head_kernel(const ValueParams vp) {
     }
 }
 
-// fp32 NHWC [B][64][HID] -> f32 NCHW [B][HID][64] (debug/parity hook), any input type.
+// activation rows -> f32 NCHW [B][HID][64] (debug/parity hook), any input type / layout.
 template <typename T>
-__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, int hid, int total, float* __restrict__ out) {
+__global__ void act_to_nchw_f32_kernel(const T* __restrict__ in, int hid, int total, int pair_layout,
+                                       float* __restrict__ out) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     const int c = gid % hid, px = (gid / hid) & 63, b = gid / (hid * 64);
-    out[(static_cast<size_t>(b) * hid + c) * 64 + px] = to_f32<T>(in[gid]);
+    out[gid / (hid * 64) * hid * 64 + c * 64 + px] =
+        to_f32<T>(in[static_cast<size_t>(act_row(b, px, pair_layout != 0)) * hid + c]);
 }
 
 }  // namespace cb
