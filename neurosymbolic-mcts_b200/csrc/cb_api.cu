@@ -19,6 +19,7 @@
 #include "../../include/caissa_b200.h"
 #include "conv_umma.cuh"
 #include "kernels_simt.cuh"
+#include "policy_umma.cuh"
 
 namespace {
 
@@ -56,6 +57,8 @@ struct cb_handle {
     std::vector<float*> se_w1, se_w2;
     float* p_wt = nullptr;   // [HID][73]
     float* p_bias = nullptr; // [73]
+    void* p_w16 = nullptr;   // [80][HID] 16-bit (rows 73..79 zero), tensor-core policy head
+    CUtensorMap tm_pw;
     float* v_w = nullptr;    // [HID]
     float* fc_wt = nullptr;  // [65][256]
     float* fc_b = nullptr;
@@ -304,10 +307,27 @@ int launch_policy_t(cb_handle* h, const T* p, int B, const PolicyOut& po) {
     return CB_OK;
 }
 
+template <int HID, bool BF16>
+int launch_policy_umma_t(cb_handle* h, int B, const PolicyOut& po) {
+    using Cfg = PolicyCfg<HID>;
+    const int tiles = (B + 1) / 2;
+    const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+    auto kern = policy_umma_kernel<HID, BF16>;
+    CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, h->stream>>>(h->tm_act_st[1], h->tm_pw, h->p_bias, tiles, B, po);
+    CB_CUDA(h, cudaGetLastError());
+    return CB_OK;
+}
+
 int launch_policy(cb_handle* h, const void* p, int B, const PolicyOut& po) {
     if (h->dtype == CB_DTYPE_FP32) return launch_policy_t<float>(h, (const float*)p, B, po);
-    if (h->dtype == CB_DTYPE_BF16) return launch_policy_t<__nv_bfloat16>(h, (const __nv_bfloat16*)p, B, po);
-    return launch_policy_t<__half>(h, (const __half*)p, B, po);
+    const bool bf = h->dtype == CB_DTYPE_BF16;
+    if (getenv("CB_SIMT_POLICY")) {
+        if (bf) return launch_policy_t<__nv_bfloat16>(h, (const __nv_bfloat16*)p, B, po);
+        return launch_policy_t<__half>(h, (const __half*)p, B, po);
+    }
+    if (h->hid == 128) return bf ? launch_policy_umma_t<128, true>(h, B, po) : launch_policy_umma_t<128, false>(h, B, po);
+    return bf ? launch_policy_umma_t<256, true>(h, B, po) : launch_policy_umma_t<256, false>(h, B, po);
 }
 
 // Index of the buffer holding the backbone output after `blocks` residual blocks.
@@ -571,6 +591,7 @@ void cb_destroy(cb_handle* h) {
     for (auto p : h->se_w1) free_dev(p);
     for (auto p : h->se_w2) free_dev(p);
     free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
+    free_dev(h->p_w16);
     free_dev(h->d_flush);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -611,6 +632,8 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
     for (auto p : h->se_w2) free_dev(p);
     h->convs.clear(); h->se_w1.clear(); h->se_w2.clear();
     free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
+    free_dev(h->p_w16);
+    h->p_w16 = nullptr;
     h->p_wt = h->p_bias = h->v_w = h->fc_wt = h->fc_b = h->out_w = nullptr;
     h->loaded = false;
 
@@ -674,6 +697,22 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
             for (int k = 0; k < H; ++k) wt[(size_t)k * 73 + c] = pw[(size_t)c * H + k];
         if ((rc = upload(wt.data(), wt.size() * 4, (void**)&h->p_wt))) return rc;
         if ((rc = upload(take(73), 73 * 4, (void**)&h->p_bias))) return rc;
+        if (h->dtype != CB_DTYPE_FP32) {
+            std::vector<uint16_t> w16((size_t)80 * H, 0);
+            for (int c = 0; c < 73; ++c)
+                for (int k = 0; k < H; ++k) w16[(size_t)c * H + k] = to16(pw[(size_t)c * H + k], h->dtype);
+            if ((rc = upload(w16.data(), w16.size() * 2, &h->p_w16))) return rc;
+            const cuuint64_t dims[2] = {(cuuint64_t)H, 80};
+            const cuuint64_t strides[1] = {(cuuint64_t)H * 2};
+            const cuuint32_t box[2] = {64, 80};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUtensorMapDataType dt =
+                h->dtype == CB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+            if (h->encode_tiled(&h->tm_pw, dt, 2, h->p_w16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(policy weights) failed");
+        }
     }
     if ((rc = upload(take(H), (size_t)H * 4, (void**)&h->v_w))) return rc;
     h->v_conv_bias = *take(1);
