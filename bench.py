@@ -43,8 +43,10 @@ FLOPS_PER_EVAL = {(6, 128): 249144320, (10, 256): 1593082880}  # SURVEY.md App. 
 WEIGHT_SEED = 1803  # variant B seed of tests/golden/net_6x128_B.npz (value head alive)
 
 
-def conv_flops_per_position(hidden):
-    return 2 * 9 * hidden * hidden * 64  # one HID->HID 3x3 layer, 2*MAC, padding not credited
+def tower_flops_per_position(blocks, hidden):
+    """Algorithmic FLOPs of the convolution tower (start conv with its real 17 input planes, 2 convs per
+    block, p_conv); 2*MAC, padding not credited."""
+    return 2 * 9 * 64 * (17 * hidden + (2 * blocks + 1) * hidden * hidden)
 
 
 def load_peaks():
@@ -239,12 +241,11 @@ def main():
     pri, v, vf, kk = ev.read_resident()
     assert np.isfinite(pri).all() and np.isfinite(vf).all() and np.abs(vf).max() <= 1.0
 
-    # ---- roofline of the dominant kernel (HID->HID 3x3 conv)
-    ev.time_conv_layers(2)
-    conv_ms, n_conv = ev.time_conv_layers(max(K // 2, 5))
-    iters_conv = max(K // 2, 5)
-    launch_ms = conv_ms / (iters_conv * n_conv)
-    flops_launch = conv_flops_per_position(args.hidden) * ((B + 1) // 2 * 2)
+    # ---- roofline of the dominant kernel: the fused persistent conv tower (one launch per step)
+    ev.time_tower(3)
+    tower_ms, n_tower = ev.time_tower(max(K // 2, 5))
+    launch_ms = float(tower_ms.mean())
+    flops_launch = tower_flops_per_position(args.blocks, args.hidden) * B
 
     # ---- end to end through the public C ABI with host buffers
     for _ in range(W):
@@ -284,7 +285,7 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                          "frac": achieved / sustained, "traffic": traffic,
-                         "kernel": "conv3x3_umma_kernel<%d> (HID->HID layers, %d launches/step)" % (args.hidden, n_conv),
+                         "kernel": "tower_umma_kernel<%d> (whole conv tower, %d launch/step)" % (args.hidden, n_tower),
                          "flops_per_launch": flops_launch, "launch_ms": launch_ms,
                          "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json (%s); burst %.1f" % (how, burst)},
             "whole_path_tflops": value / world * FLOPS_PER_EVAL.get((args.blocks, args.hidden), 0) / 1e12,

@@ -137,6 +137,9 @@ int cb_time_conv_layers(cb_handle* h, int iters, float* conv_ms_total, int* n_co
 /* per_layer_ms[2*blocks+2] (nullable): mean event time of every conv launch, start conv first. */
 int cb_time_conv_layers_detail(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches,
                                float* per_layer_ms);
+/* Event time of the convolution tower alone (the fused persistent kernel in the 16-bit modes,
+ * the per-layer launches otherwise), one entry per iteration; n_launches = kernels per iteration. */
+int cb_time_tower(cb_handle* h, int iters, float* ms_each, int* n_launches);
 int cb_read_resident(cb_handle* h, float* priors, float* v_logit, float* v_final, float* k);
 
 /* Debug / parity hook: copy the backbone activation (after the last residual

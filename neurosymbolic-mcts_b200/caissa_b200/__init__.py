@@ -51,6 +51,7 @@ SIGNATURES = {
     "cb_time_resident": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_time_conv_layers": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
     "cb_time_conv_layers_detail": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP]),
+    "cb_time_tower": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
     "cb_read_resident": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "cb_debug_backbone": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
     "cb_debug_act": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
@@ -193,6 +194,12 @@ class Evaluator:
         per = np.zeros(2 * self.num_blocks + 2, dtype=np.float32)
         self._check(self._L.cb_time_conv_layers_detail(self._h, iters, None, None, _ptr(per)))
         return per
+
+    def time_tower(self, iters):
+        ms = np.zeros(iters, dtype=np.float32)
+        n = ctypes.c_int(0)
+        self._check(self._L.cb_time_tower(self._h, iters, _ptr(ms), ctypes.byref(n)))
+        return ms, n.value
 
     def read_resident(self):
         B, nm = self._staged

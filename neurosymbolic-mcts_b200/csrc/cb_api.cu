@@ -20,6 +20,7 @@
 #include "conv_umma.cuh"
 #include "kernels_simt.cuh"
 #include "policy_umma.cuh"
+#include "tower_umma.cuh"
 
 namespace {
 
@@ -86,6 +87,10 @@ struct cb_handle {
     size_t scratch_floats = 0;
     void* d_flush = nullptr;
     CUtensorMap tm_x0, tm_act_ld[3], tm_act_st[3];
+    CUtensorMap* d_maps = nullptr;    // fused tower: tensor-map table (x0, act loads, act stores, weights)
+    cb::TowerLayer* d_layers = nullptr;
+    bool tower_ready = false;
+    bool use_fused = true;
 
     // pinned staging
     cb_board* h_boards = nullptr;
@@ -197,6 +202,8 @@ void free_buffers(cb_handle* h) {
     h->cap = 0; h->csr_cap = 0; h->probs_cap = 0; h->scratch_floats = 0; h->staged_B = 0;
 }
 
+int build_tower_tables(cb_handle* h);
+
 // Grow device + pinned buffers to hold B boards (rounded up to a whole 2-board tile).
 int ensure_capacity(cb_handle* h, int B) {
     const int need = (B + 1) & ~1;
@@ -234,8 +241,71 @@ int ensure_capacity(cb_handle* h, int B) {
             if ((rc = make_act_map(h, &h->tm_act_ld[i], h->d_act[i], h->hid, cap, 10))) return rc;
             if ((rc = make_act_map(h, &h->tm_act_st[i], h->d_act[i], h->hid, cap, 8))) return rc;
         }
+        if (h->loaded && (rc = build_tower_tables(h))) return rc;
     }
     return CB_OK;
+}
+
+// Device-side tables of the fused tower kernel.  Rebuilt whenever buffers or weights change.
+int build_tower_tables(cb_handle* h) {
+    h->tower_ready = false;
+    if (h->dtype == CB_DTYPE_FP32 || !h->cap || h->convs.empty()) return CB_OK;
+    const int nl = (int)h->convs.size();
+    std::vector<CUtensorMap> maps(7 + nl);
+    maps[0] = h->tm_x0;
+    for (int i = 0; i < 3; ++i) { maps[1 + i] = h->tm_act_ld[i]; maps[4 + i] = h->tm_act_st[i]; }
+    for (int l = 0; l < nl; ++l) maps[7 + l] = h->convs[l].tm_w;
+    std::vector<TowerLayer> ly(nl);
+    memset(ly.data(), 0, sizeof(TowerLayer) * nl);
+    int cur = 0;
+    ly[0].in_map = 0; ly[0].w_map = 7; ly[0].out_map = 4 + 0; ly[0].kc_in = 1; ly[0].mode = MODE_RELU;
+    ly[0].bias = h->convs[0].bias;
+    for (int i = 0; i < h->blocks; ++i) {
+        const int nxt = cur == 0 ? 2 : 0;
+        TowerLayer& a = ly[1 + 2 * i];
+        a.in_map = 1 + cur; a.w_map = 7 + 1 + 2 * i; a.out_map = 4 + 1; a.kc_in = h->hid / 64; a.mode = MODE_RELU;
+        a.bias = h->convs[1 + 2 * i].bias;
+        TowerLayer& b = ly[2 + 2 * i];
+        b.in_map = 1 + 1; b.w_map = 7 + 2 + 2 * i; b.out_map = 4 + nxt; b.kc_in = h->hid / 64; b.mode = MODE_SE_RES;
+        b.bias = h->convs[2 + 2 * i].bias;
+        b.se_w1 = h->se_w1[i]; b.se_w2 = h->se_w2[i]; b.residual = h->d_act[cur];
+        if (i == h->blocks - 1) { b.v_w = h->v_w; b.v_pre = h->d_vpre; }
+        cur = nxt;
+    }
+    TowerLayer& pl = ly[nl - 1];
+    pl.in_map = 1 + cur; pl.w_map = 7 + nl - 1; pl.out_map = 4 + 1; pl.kc_in = h->hid / 64; pl.mode = MODE_RELU;
+    pl.bias = h->convs[nl - 1].bias;
+    free_dev(h->d_maps); free_dev(h->d_layers);
+    h->d_maps = nullptr; h->d_layers = nullptr;
+    CB_CUDA(h, cudaMalloc(&h->d_maps, maps.size() * sizeof(CUtensorMap)));
+    CB_CUDA(h, cudaMalloc(&h->d_layers, ly.size() * sizeof(TowerLayer)));
+    CB_CUDA(h, cudaMemcpy(h->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    CB_CUDA(h, cudaMemcpy(h->d_layers, ly.data(), ly.size() * sizeof(TowerLayer), cudaMemcpyHostToDevice));
+    h->tower_ready = true;
+    return CB_OK;
+}
+
+template <int HID, bool BF16>
+int launch_tower_t(cb_handle* h, int B) {
+    using Cfg = ConvCfg<HID>;
+    TowerParams tp;
+    tp.maps = h->d_maps;
+    tp.layers = h->d_layers;
+    tp.num_layers = (int)h->convs.size();
+    tp.num_tiles = (B + 1) / 2;
+    const int units = (tp.num_tiles + 2 * Cfg::kTiles - 1) / (2 * Cfg::kTiles);
+    const int grid = units < h->sm_count ? units : h->sm_count;
+    auto kern = tower_umma_kernel<HID, BF16>;
+    CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, h->stream>>>(tp);
+    CB_CUDA(h, cudaGetLastError());
+    return CB_OK;
+}
+
+int launch_tower(cb_handle* h, int B) {
+    const bool bf = h->dtype == CB_DTYPE_BF16;
+    if (h->hid == 128) return bf ? launch_tower_t<128, true>(h, B) : launch_tower_t<128, false>(h, B);
+    return bf ? launch_tower_t<256, true>(h, B) : launch_tower_t<256, false>(h, B);
 }
 
 int ensure_scratch(cb_handle* h, size_t floats) {
@@ -440,7 +510,11 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
         encode_pair16_kernel<false><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, (uint4*)h->d_x0);
     }
     CB_CUDA(h, cudaGetLastError());
-    int rc = enqueue_tower(h, B, nullptr);
+    int rc;
+    if (h->use_fused && h->tower_ready && h->layer_limit == 0)
+        rc = launch_tower(h, B);
+    else
+        rc = enqueue_tower(h, B, nullptr);
     if (rc) return rc;
     PolicyOut po = {};
     po.probs = full_policy ? h->d_probs : nullptr;
@@ -555,6 +629,8 @@ int cb_create(cb_handle** out, int device, int num_blocks, int hidden, int dtype
     h->dtype = dtype;
     const char* ng = getenv("CB_NO_GRAPH");
     h->use_graphs = !(ng && ng[0] == '1');
+    const char* nf = getenv("CB_NO_FUSE");
+    h->use_fused = !(nf && nf[0] == '1');
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         delete h;
@@ -592,6 +668,7 @@ void cb_destroy(cb_handle* h) {
     for (auto p : h->se_w2) free_dev(p);
     free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
     free_dev(h->p_w16);
+    free_dev(h->d_maps); free_dev(h->d_layers);
     free_dev(h->d_flush);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -607,6 +684,7 @@ int cb_is_available(const cb_handle* h) { return h && h->loaded ? 1 : 0; }
 int cb_launches_per_forward(const cb_handle* h) {
     if (!h) return 0;
     const int convs = 2 * h->blocks + 2;
+    if (h->dtype != CB_DTYPE_FP32 && h->use_fused) return 4;  // encode, fused tower, policy, value
     return 1 + convs + (h->dtype == CB_DTYPE_FP32 ? h->blocks : 0) + 2;
 }
 
@@ -738,7 +816,7 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
     }
     if ((size_t)(cur - blob) != n_floats) return fail(h, CB_EINVAL, "internal: blob walk mismatch");
     h->loaded = true;
-    return CB_OK;
+    return build_tower_tables(h);
 }
 
 int cb_encode(cb_handle* h, const cb_board* boards, int B, float* planes) {
@@ -909,6 +987,29 @@ int cb_time_conv_layers_detail(cb_handle* h, int iters, float* conv_ms_total, in
     if (rc) return rc;
     if (conv_ms_total) *conv_ms_total = (float)total;
     if (n_conv_launches) *n_conv_launches = nconv - 1;
+    return CB_OK;
+}
+
+int cb_time_tower(cb_handle* h, int iters, float* ms_each, int* n_launches) {
+    if (!h || iters <= 0 || !ms_each) return CB_EINVAL;
+    if (!h->staged_B) return fail(h, CB_ESTATE, "nothing staged: call cb_stage_leaves first");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    const bool fused = h->dtype != CB_DTYPE_FP32 && h->use_fused && h->tower_ready && h->layer_limit == 0;
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters);
+    for (auto& e : ev) CB_CUDA(h, cudaEventCreate(&e));
+    int rc = CB_OK;
+    for (int i = 0; i < iters && !rc; ++i) {
+        CB_CUDA(h, cudaEventRecord(ev[2 * i], h->stream));
+        rc = fused ? launch_tower(h, h->staged_B) : enqueue_tower(h, h->staged_B, nullptr);
+        CB_CUDA(h, cudaEventRecord(ev[2 * i + 1], h->stream));
+    }
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (!rc && se == cudaSuccess)
+        for (int i = 0; i < iters; ++i) cudaEventElapsedTime(&ms_each[i], ev[2 * i], ev[2 * i + 1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
+    CB_CUDA(h, se);
+    if (n_launches) *n_launches = fused ? 1 : 2 * h->blocks + 2 + (h->dtype == CB_DTYPE_FP32 ? h->blocks : 0);
     return CB_OK;
 }
 

@@ -39,12 +39,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (an error the
-// host reports), never as a hung GPU.  ~2^28 polls is seconds, far beyond any
+// host reports), never as a hung GPU.  ~2^22 polls is seconds, far beyond any
 // legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 28)) __trap();
+        if (++spins > (1u << 22)) __trap();
     }
 }
 
@@ -99,6 +99,10 @@ __device__ __forceinline__ void tma_store_wait0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+// async-proxy <-> generic-proxy ordering for global memory too (a TMA store whose result a
+// later TMA load of the same CTA depends on)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ------------------------------------------------------------------ tcgen05
 template <uint32_t kCols>

@@ -240,7 +240,9 @@ def test_resident_path_equals_host_path(cb, golden, positions):
         assert np.array_equal(a, b)
     conv_ms, n = ev.time_conv_layers(2)
     assert n == 13 and conv_ms > 0
-    assert ev.launches_per_forward() == 17
+    tower_ms, launches = ev.time_tower(3)
+    assert launches == 1 and tower_ms.min() > 0            # the fused persistent tower kernel
+    assert ev.launches_per_forward() == 4                  # encode, tower, policy, value
 
 
 # ------------------------------------------------------------------ reference-shaped host interface
