@@ -153,6 +153,47 @@ int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches);
 /* Kernels launched per forward of the given kind (for gpu_launches accounting). */
 int cb_launches_per_forward(const cb_handle* h);
 
+/* ---- host-side chess rules used by the self-play driver (legal-move lists = the path's
+ * "legal-move mask", src/mcts/selection.rs:82-104; perft-pinned, tests/perft_tests.rs). */
+int      cb_chess_startpos(cb_board* out);
+int      cb_chess_legal_moves(const cb_board* b, uint16_t* moves /*256: from|to<<6|promo<<12*/,
+                              uint16_t* policy_idx /*256, nullable: move_to_index(flip-if-black)*/);
+int      cb_chess_make_move(const cb_board* b, uint16_t move, cb_board* out);
+uint64_t cb_chess_perft(const cb_board* b, int depth);
+
+/* ---- self-play driver (src/bin/self_play.rs:29-624 semantics for the sims/s metric): a pool of
+ * concurrent games, one leaf in flight per game per step, PUCT selection
+ * Q + c*P*sqrt(max(N,1))/(1+n) (src/mcts/selection.rs:254-273) with the force-every-root-child
+ * rule (:65-73), sign-flipping backup (src/mcts/node.rs:403-424), mate/stalemate terminals,
+ * proportional-or-greedy move choice (src/bin/self_play.rs:343-351,628-650), subtree reuse, and
+ * game end on mate/stalemate/3-fold/50-move/max plies (+ KOTH centre, :365-381).  Leaves are
+ * evaluated in ONE cb_eval_leaves batch per step.  Tier-1 gates and the Tier-2 q-search are host
+ * CPU searches outside this path: material_on feeds the static PeSTO stand-pat term as dM. */
+typedef struct cb_selfplay_config {
+    int games;            /* concurrent games in the pool */
+    int sims_per_move;    /* 200 / 800 */
+    int max_plies;        /* 200 */
+    int material_on;      /* 1: q = static PeSTO/100, V = tanh(v+k*q); 0: vanilla (config 5) */
+    int koth;             /* King-of-the-Hill game-end rule */
+    int threads;          /* host threads for tree operations (0 = hardware concurrency) */
+    float c_puct;         /* 1.414 (TacticalMctsConfig::default) */
+    float explore_base;   /* 0.80 */
+    uint64_t seed;
+    long long max_sims;   /* stop after this many simulations in total (0 = unlimited) */
+    long long max_games;  /* stop after this many finished games (0 = unlimited) */
+    double max_seconds;   /* wall-clock bound (0 = unlimited) */
+    const char* sample_path; /* nullable: append finished games as 5763-f32 records (src/training_data.rs:24-60) */
+} cb_selfplay_config;
+
+typedef struct cb_selfplay_stats {
+    long long sims, nn_evals, terminal_hits, moves, games_finished, samples, steps;
+    long long white_wins, black_wins, draws;
+    double seconds, eval_seconds, tree_seconds;
+    double mean_batch;
+} cb_selfplay_stats;
+
+int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out);
+
 int         cb_get_timing(const cb_handle* h, cb_timing* out);
 void        cb_reset_timing(cb_handle* h);
 const char* cb_last_error(const cb_handle* h);

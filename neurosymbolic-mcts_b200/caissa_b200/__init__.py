@@ -28,6 +28,20 @@ class CbTiming(ctypes.Structure):
                 ("forward_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double)]
 
 
+class SelfplayConfig(ctypes.Structure):
+    _fields_ = [("games", ctypes.c_int), ("sims_per_move", ctypes.c_int), ("max_plies", ctypes.c_int),
+                ("material_on", ctypes.c_int), ("koth", ctypes.c_int), ("threads", ctypes.c_int),
+                ("c_puct", ctypes.c_float), ("explore_base", ctypes.c_float), ("seed", ctypes.c_uint64),
+                ("max_sims", ctypes.c_longlong), ("max_games", ctypes.c_longlong), ("max_seconds", ctypes.c_double),
+                ("sample_path", ctypes.c_char_p)]
+
+
+class SelfplayStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_longlong) for n in ("sims", "nn_evals", "terminal_hits", "moves", "games_finished",
+                                                 "samples", "steps", "white_wins", "black_wins", "draws")] + \
+               [(n, ctypes.c_double) for n in ("seconds", "eval_seconds", "tree_seconds", "mean_batch")]
+
+
 class CaissaError(RuntimeError):
     pass
 
@@ -56,6 +70,11 @@ SIGNATURES = {
     "cb_debug_backbone": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
     "cb_debug_act": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_debug_set_layer_limit": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "cb_chess_startpos": (ctypes.c_int, [_VP]),
+    "cb_chess_legal_moves": (ctypes.c_int, [_VP, _VP, _VP]),
+    "cb_chess_make_move": (ctypes.c_int, [_VP, ctypes.c_uint16, _VP]),
+    "cb_chess_perft": (ctypes.c_uint64, [_VP, ctypes.c_int]),
+    "cb_selfplay_run": (ctypes.c_int, [_VP, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
     "cb_launches_per_forward": (ctypes.c_int, [_VP]),
     "cb_get_timing": (ctypes.c_int, [_VP, ctypes.POINTER(CbTiming)]),
     "cb_reset_timing": (None, [_VP]),
@@ -223,6 +242,16 @@ class Evaluator:
     def debug_set_layer_limit(self, n):
         self._check(self._L.cb_debug_set_layer_limit(self._h, n))
 
+    def selfplay(self, games=1024, sims_per_move=200, max_plies=200, material_on=False, koth=False, threads=0,
+                 c_puct=1.414, explore_base=0.80, seed=1, max_sims=0, max_games=0, max_seconds=0.0, sample_path=None):
+        """Run the self-play pool on this evaluator; returns the stats as a dict."""
+        cfg = SelfplayConfig(games, sims_per_move, max_plies, int(material_on), int(koth), threads, c_puct,
+                             explore_base, seed, max_sims, max_games, max_seconds,
+                             sample_path.encode() if sample_path else None)
+        st = SelfplayStats()
+        self._check(self._L.cb_selfplay_run(self._h, ctypes.byref(cfg), ctypes.byref(st)))
+        return {n: getattr(st, n) for n, _ in SelfplayStats._fields_}
+
     def launches_per_forward(self):
         return self._L.cb_launches_per_forward(self._h)
 
@@ -231,6 +260,32 @@ class Evaluator:
         self._check(self._L.cb_get_timing(self._h, ctypes.byref(t)))
         return {"calls": t.calls, "positions": t.positions, "h2d_ms": t.h2d_ms, "forward_ms": t.forward_ms,
                 "d2h_ms": t.d2h_ms}
+
+
+def chess_startpos():
+    b = np.zeros(128, dtype=np.uint8)
+    load_library().cb_chess_startpos(_ptr(b))
+    return b
+
+
+def chess_legal_moves(board):
+    b = np.ascontiguousarray(board, dtype=np.uint8)
+    mv = np.zeros(MAX_MOVES, dtype=np.uint16)
+    idx = np.zeros(MAX_MOVES, dtype=np.uint16)
+    n = load_library().cb_chess_legal_moves(_ptr(b), _ptr(mv), _ptr(idx))
+    return mv[:n].copy(), idx[:n].copy()
+
+
+def chess_make_move(board, move):
+    b = np.ascontiguousarray(board, dtype=np.uint8)
+    out = np.zeros(128, dtype=np.uint8)
+    load_library().cb_chess_make_move(_ptr(b), int(move), _ptr(out))
+    return out
+
+
+def chess_perft(board, depth):
+    b = np.ascontiguousarray(board, dtype=np.uint8)
+    return load_library().cb_chess_perft(_ptr(b), depth)
 
 
 class NeuralNetPolicy:

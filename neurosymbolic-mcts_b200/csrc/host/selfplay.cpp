@@ -1,0 +1,494 @@
+// selfplay.cpp — per-GPU self-play game pool feeding the batched leaf evaluator, plus the
+// cb_chess_* C ABI.  Semantics follow src/bin/self_play.rs:191-624 and src/mcts/{selection,node}.rs
+// (citations at the declarations in include/caissa_b200.h); the structure does not: instead of a
+// thread per game blocking on one request each, all games of the pool advance in lock step and
+// their leaves are evaluated in ONE cb_eval_leaves call per step (one leaf in flight per game,
+// exactly like the reference), so the evaluator sees batches of ~`games` positions.
+//
+// Host threading: the select / expand / backup work of a step is split across worker threads by
+// game; the calling thread drives the GPU.  Trees are per-game arenas of 24-byte nodes.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../../include/caissa_b200.h"
+#include "../pesto_tables.h"
+#include "chess.hpp"
+
+using namespace cbchess;
+
+namespace {
+
+struct Node {
+    uint32_t first_child = 0;
+    uint32_t visits = 0;
+    float value_sum = 0.0f;   // from the point of view of the player who moved INTO this node
+    float prior = 0.0f;
+    uint16_t n_children = 0;
+    Move move = 0;
+    uint8_t state = 0;        // 0 unexpanded, 1 expanded, 2 terminal
+    int8_t term_value = 0;    // value for the side to move at a terminal node (-1 mated, 0 stalemate)
+};
+
+struct Sample {
+    cb_board board;
+    float material;
+    std::vector<std::pair<uint16_t, float>> policy;
+};
+
+struct Rng {
+    uint64_t s;
+    uint64_t next() { s ^= s >> 12; s ^= s << 25; s ^= s >> 27; return s * 0x2545F4914F6CDD1Dull; }
+    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+int static_pesto_cp(const cb_board& b) {  // src/eval.rs:93-122 on the host (same tables as the device kernel)
+    int mg[2] = {0, 0}, eg[2] = {0, 0}, phase = 0;
+    for (int c = 0; c < 2; ++c)
+        for (int pt = 0; pt < 6; ++pt)
+            for (uint64_t bb = b.pieces[c * 6 + pt]; bb; bb &= bb - 1) {
+                const int sq = __builtin_ctzll(bb), t = c == 0 ? (sq ^ 56) : sq;
+                mg[c] += CB_MG_VALUE[pt] + CB_MG_PST[pt][t];
+                eg[c] += CB_EG_VALUE[pt] + CB_EG_PST[pt][t];
+                phase += CB_PHASE_INC[pt];
+            }
+    const int mgp = phase < 24 ? phase : 24;
+    const int score = ((mg[0] - mg[1]) * mgp + (eg[0] - eg[1]) * (24 - mgp)) / 24;
+    return b.w_to_move ? score : -score;
+}
+
+struct Game {
+    cb_board root_board;
+    std::vector<Node> nodes;        // nodes[0] = root
+    std::vector<uint64_t> history;  // position keys since the last irreversible move
+    std::vector<Sample> samples;
+    Rng rng;
+    int ply = 0;
+    int sims_done = 0;
+    // per-step scratch
+    std::vector<uint32_t> path;
+    cb_board leaf_board;
+    Move leaf_moves[kMaxMoves];
+    uint16_t leaf_idx[kMaxMoves];
+    int leaf_n = 0;
+    bool wants_eval = false;
+
+    void reset(uint64_t seed) {
+        startpos(&root_board);
+        nodes.clear();
+        nodes.emplace_back();
+        history.clear();
+        history.push_back(position_key(root_board));
+        samples.clear();
+        rng.s = seed | 1;
+        ply = 0;
+        sims_done = 0;
+    }
+};
+
+// One simulation, phase A: walk down with PUCT; stop at an unexpanded or terminal node.
+void select_leaf(Game& g, float c_puct, std::atomic<long long>& terminal_hits) {
+    g.path.clear();
+    g.wants_eval = false;
+    uint32_t cur = 0;
+    cb_board board = g.root_board;
+    g.path.push_back(0);
+    int depth = 0;
+    for (;;) {
+        Node& n = g.nodes[cur];
+        if (n.state != 1) break;
+        uint32_t best = n.first_child;
+        bool forced = false;
+        if (depth == 0) {  // every root child gets one visit first (src/mcts/selection.rs:65-73)
+            for (uint32_t i = 0; i < n.n_children; ++i)
+                if (g.nodes[n.first_child + i].visits == 0) { best = n.first_child + i; forced = true; break; }
+        }
+        if (!forced) {
+            const float sq = sqrtf((float)(n.visits > 1 ? n.visits : 1));
+            float best_u = -1e30f;
+            for (uint32_t i = 0; i < n.n_children; ++i) {
+                const Node& ch = g.nodes[n.first_child + i];
+                const float q = ch.visits ? ch.value_sum / (float)ch.visits : 0.0f;
+                const float u = q + c_puct * ch.prior * sq / (1.0f + (float)ch.visits);
+                if (u > best_u) { best_u = u; best = n.first_child + i; }
+            }
+        }
+        cb_board nb;
+        make_move(board, g.nodes[best].move, &nb);
+        board = nb;
+        cur = best;
+        g.path.push_back(cur);
+        ++depth;
+    }
+    Node& leaf = g.nodes[cur];
+    if (leaf.state == 2) {  // terminal: back its value up again
+        float val = (float)leaf.term_value;
+        for (int i = (int)g.path.size() - 1; i >= 0; --i) {
+            val = -val;
+            Node& n = g.nodes[g.path[i]];
+            n.value_sum += val;
+            n.visits++;
+        }
+        terminal_hits.fetch_add(1, std::memory_order_relaxed);
+        g.sims_done++;
+        return;
+    }
+    g.leaf_n = gen_legal(board, g.leaf_moves);
+    if (g.leaf_n == 0) {  // mate / stalemate (MctsNode::new_child terminal test, src/mcts/node.rs:162-177)
+        leaf.state = 2;
+        leaf.term_value = in_check(board, board.w_to_move ? 0 : 1) ? -1 : 0;
+        float val = (float)leaf.term_value;
+        for (int i = (int)g.path.size() - 1; i >= 0; --i) {
+            val = -val;
+            Node& n = g.nodes[g.path[i]];
+            n.value_sum += val;
+            n.visits++;
+        }
+        terminal_hits.fetch_add(1, std::memory_order_relaxed);
+        g.sims_done++;
+        return;
+    }
+    for (int i = 0; i < g.leaf_n; ++i) g.leaf_idx[i] = (uint16_t)policy_index(g.leaf_moves[i], board.w_to_move != 0);
+    g.leaf_board = board;
+    g.wants_eval = true;
+}
+
+// Phase C: expand the evaluated leaf with its priors and back the value up.
+void expand_and_backup(Game& g, const float* priors, float v_final) {
+    const uint32_t cur = g.path.back();
+    const uint32_t first = (uint32_t)g.nodes.size();
+    g.nodes.resize(g.nodes.size() + g.leaf_n);
+    Node& leaf = g.nodes[cur];
+    leaf.first_child = first;
+    leaf.n_children = (uint16_t)g.leaf_n;
+    leaf.state = 1;
+    for (int i = 0; i < g.leaf_n; ++i) {
+        Node& ch = g.nodes[first + i];
+        ch.move = g.leaf_moves[i];
+        ch.prior = priors[i];
+    }
+    float val = v_final;  // side-to-move perspective at the leaf
+    for (int i = (int)g.path.size() - 1; i >= 0; --i) {
+        val = -val;  // sign flips every ply (src/mcts/node.rs:403-424)
+        Node& n = g.nodes[g.path[i]];
+        n.value_sum += val;
+        n.visits++;
+    }
+    g.sims_done++;
+}
+
+// Keep the subtree under `child` as the new tree (tree reuse, src/bin/self_play.rs:358-363).
+void reroot(Game& g, uint32_t child) {
+    std::vector<Node> fresh;
+    fresh.reserve(g.nodes.size() / 2 + 1);
+    std::vector<std::pair<uint32_t, uint32_t>> todo;  // (old index, new index)
+    fresh.push_back(g.nodes[child]);
+    todo.emplace_back(child, 0u);
+    for (size_t h = 0; h < todo.size(); ++h) {
+        const uint32_t oldi = todo[h].first, newi = todo[h].second;
+        const Node on = g.nodes[oldi];
+        if (on.state == 1) {
+            const uint32_t nf = (uint32_t)fresh.size();
+            for (uint32_t i = 0; i < on.n_children; ++i) {
+                fresh.push_back(g.nodes[on.first_child + i]);
+                todo.emplace_back(on.first_child + i, nf + i);
+            }
+            fresh[newi].first_child = nf;
+        }
+    }
+    g.nodes.swap(fresh);
+}
+
+struct Pool {
+    int nthreads;
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv, done_cv;
+    std::function<void(int, int)> job;  // [begin, end) of games
+    int generation = 0, pending = 0, ngames = 0;
+    bool stop = false;
+
+    Pool(int n, int games) : nthreads(n), ngames(games) {
+        for (int t = 0; t < n; ++t) threads.emplace_back([this, t] { loop(t); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto& t : threads) t.join();
+    }
+    void loop(int t) {
+        int seen = 0;
+        for (;;) {
+            std::function<void(int, int)> j;
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cv.wait(l, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                j = job;
+            }
+            const int per = (ngames + nthreads - 1) / nthreads;
+            const int b = t * per, e = b + per < ngames ? b + per : ngames;
+            if (b < e) j(b, e);
+            {
+                std::lock_guard<std::mutex> l(mu);
+                if (--pending == 0) done_cv.notify_one();
+            }
+        }
+    }
+    void run(std::function<void(int, int)> j) {
+        std::unique_lock<std::mutex> l(mu);
+        job = std::move(j);
+        pending = nthreads;
+        ++generation;
+        cv.notify_all();
+        done_cv.wait(l, [&] { return pending == 0; });
+    }
+};
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb_chess_startpos(cb_board* out) {
+    if (!out) return CB_EINVAL;
+    startpos(out);
+    return CB_OK;
+}
+
+int cb_chess_legal_moves(const cb_board* b, uint16_t* moves, uint16_t* policy_idx) {
+    if (!b || !moves) return CB_EINVAL;
+    const int n = gen_legal(*b, moves);
+    if (policy_idx)
+        for (int i = 0; i < n; ++i) policy_idx[i] = (uint16_t)policy_index(moves[i], b->w_to_move != 0);
+    return n;
+}
+
+int cb_chess_make_move(const cb_board* b, uint16_t move, cb_board* out) {
+    if (!b || !out) return CB_EINVAL;
+    make_move(*b, move, out);
+    return CB_OK;
+}
+
+uint64_t cb_chess_perft(const cb_board* b, int depth) { return b ? perft(*b, depth) : 0; }
+
+int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
+    if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
+    if (!cb_is_available(h)) return CB_ESTATE;
+    memset(out, 0, sizeof(*out));
+    const int G = cfg->games;
+    const int max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
+    const float c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
+    const double explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
+    int nthreads = cfg->threads > 0 ? cfg->threads : (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > G) nthreads = G;
+
+    std::vector<Game> games(G);
+    for (int i = 0; i < G; ++i) games[i].reset(cfg->seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * (uint64_t)(i + 1));
+    Pool pool(nthreads, G);
+    std::atomic<long long> terminal_hits(0), moves_played(0), games_finished(0), samples_written(0);
+    std::atomic<long long> wwins(0), bwins(0), draws(0);
+    std::mutex file_mu;
+    FILE* sample_file = cfg->sample_path ? fopen(cfg->sample_path, "ab") : nullptr;
+
+    std::vector<cb_board> boards(G);
+    std::vector<float> q(G), priors((size_t)G * kMaxMoves), v_logit(G), v_final(G), kk(G);
+    std::vector<uint16_t> move_idx((size_t)G * kMaxMoves);
+    std::vector<uint32_t> move_off(G + 1);
+    std::vector<int> slot_game(G), game_slot(G);
+
+    // Finish a game: assign z to its samples and write them in the reference's 5763-f32 format.
+    auto finish_game = [&](Game& g, int result_white /* +1 white won, -1 black won, 0 draw */) {
+        if (result_white > 0) wwins++; else if (result_white < 0) bwins++; else draws++;
+        if (sample_file) {
+            std::vector<float> rec(5763);
+            std::lock_guard<std::mutex> l(file_mu);
+            for (const Sample& s : g.samples) {
+                std::fill(rec.begin(), rec.end(), 0.0f);
+                const cb_board& b = s.board;
+                const bool white = b.w_to_move != 0;
+                const int stm = white ? 0 : 1;
+                for (int side = 0; side < 2; ++side)
+                    for (int pt = 0; pt < 6; ++pt)
+                        for (uint64_t bb = b.pieces[(side == 0 ? stm : 1 - stm) * 6 + pt]; bb; bb &= bb - 1) {
+                            const int sq = __builtin_ctzll(bb);
+                            const int row = white ? 7 - (sq >> 3) : (sq >> 3);
+                            rec[(side * 6 + pt) * 64 + row * 8 + (sq & 7)] = 1.0f;
+                        }
+                if (b.en_passant != 0xFF) {
+                    const int sq = b.en_passant, row = white ? 7 - (sq >> 3) : (sq >> 3);
+                    rec[12 * 64 + row * 8 + (sq & 7)] = 1.0f;
+                }
+                const int ow[4] = {WK, WQ, BK, BQ}, ob[4] = {BK, BQ, WK, WQ};
+                for (int i = 0; i < 4; ++i)
+                    if (b.castling & (white ? ow[i] : ob[i]))
+                        for (int j = 0; j < 64; ++j) rec[(13 + i) * 64 + j] = 1.0f;
+                rec[1088] = s.material;
+                rec[1089] = 1.0f;  // qsearch_completed
+                rec[1090] = result_white == 0 ? 0.0f : ((result_white > 0) == white ? 1.0f : -1.0f);
+                for (auto& pr : s.policy)
+                    if (pr.first < CB_POLICY_SIZE) rec[1091 + pr.first] = pr.second;
+                fwrite(rec.data(), 4, rec.size(), sample_file);
+            }
+        }
+        samples_written += (long long)g.samples.size();
+        games_finished++;
+    };
+
+    // After sims_per_move simulations: record the sample, choose and play a move, detect game end.
+    auto play_move = [&](Game& g, int gi) {
+        Node& root = g.nodes[0];
+        if (root.state != 1 || root.n_children == 0) {  // cannot happen for a live game; restart defensively
+            g.reset(g.rng.next());
+            return;
+        }
+        uint32_t total = 0;
+        for (uint32_t i = 0; i < root.n_children; ++i) total += g.nodes[root.first_child + i].visits;
+        Sample s;
+        s.board = g.root_board;
+        s.material = cfg->material_on ? (float)static_pesto_cp(g.root_board) / 100.0f : 0.0f;
+        if (total > 0)
+            for (uint32_t i = 0; i < root.n_children; ++i) {
+                const Node& ch = g.nodes[root.first_child + i];
+                s.policy.emplace_back((uint16_t)policy_index(ch.move, g.root_board.w_to_move != 0),
+                                      (float)ch.visits / (float)total);
+            }
+        g.samples.push_back(std::move(s));
+        // proportional to (visits-1) with probability explore_base^(move-1), else greedy
+        const int move_number = g.ply / 2 + 1;
+        uint32_t pick = root.first_child;
+        uint32_t best_v = 0;
+        for (uint32_t i = 0; i < root.n_children; ++i)
+            if (g.nodes[root.first_child + i].visits > best_v) { best_v = g.nodes[root.first_child + i].visits; pick = root.first_child + i; }
+        if (g.rng.uniform() < pow(explore_base, move_number - 1)) {
+            uint32_t tot1 = 0;
+            for (uint32_t i = 0; i < root.n_children; ++i) {
+                const uint32_t v = g.nodes[root.first_child + i].visits;
+                tot1 += v > 0 ? v - 1 : 0;
+            }
+            if (tot1 > 0) {
+                const uint32_t thr = (uint32_t)(g.rng.next() % tot1);
+                uint32_t cum = 0;
+                for (uint32_t i = 0; i < root.n_children; ++i) {
+                    const uint32_t v = g.nodes[root.first_child + i].visits;
+                    cum += v > 0 ? v - 1 : 0;
+                    if (cum > thr) { pick = root.first_child + i; break; }
+                }
+            }
+        }
+        const Move mv = g.nodes[pick].move;
+        const bool white_moved = g.root_board.w_to_move != 0;
+        cb_board nb;
+        make_move(g.root_board, mv, &nb);
+        if (nb.halfmove == 0) g.history.clear();
+        g.root_board = nb;
+        g.history.push_back(position_key(nb));
+        g.ply++;
+        g.sims_done = 0;
+        moves_played++;
+        reroot(g, pick);
+        // game end (src/bin/self_play.rs:358-388)
+        int result = 2;  // 2 = continue
+        Move tmp[kMaxMoves];
+        if (cfg->koth && (nb.pieces[(white_moved ? 0 : 6) + KING] & kKothCenter)) result = white_moved ? 1 : -1;
+        else if (gen_legal(nb, tmp) == 0) result = in_check(nb, nb.w_to_move ? 0 : 1) ? (white_moved ? 1 : -1) : 0;
+        else {
+            int reps = 0;
+            for (uint64_t k : g.history) reps += (k == g.history.back());
+            if (reps >= 3 || nb.halfmove >= 100 || g.ply > max_plies) result = 0;
+        }
+        if (result != 2) {
+            finish_game(g, result);
+            g.reset(g.rng.next() ^ ((uint64_t)gi << 32));
+        }
+    };
+
+    const double t_start = now_s();
+    double eval_s = 0.0, tree_s = 0.0;
+    long long sims = 0, evals = 0, steps = 0;
+    for (;;) {
+        if (cfg->max_sims > 0 && sims >= cfg->max_sims) break;
+        if (cfg->max_games > 0 && games_finished.load() >= cfg->max_games) break;
+        if (cfg->max_seconds > 0 && now_s() - t_start >= cfg->max_seconds) break;
+        double t0 = now_s();
+        pool.run([&](int b, int e) {
+            for (int i = b; i < e; ++i) select_leaf(games[i], c_puct, terminal_hits);
+        });
+        // pack the evaluation batch (CSR of legal policy indices)
+        int nb = 0;
+        uint32_t off = 0;
+        for (int i = 0; i < G; ++i) {
+            Game& g = games[i];
+            if (!g.wants_eval) continue;
+            boards[nb] = g.leaf_board;
+            q[nb] = cfg->material_on ? (float)static_pesto_cp(g.leaf_board) / 100.0f : 0.0f;
+            move_off[nb] = off;
+            memcpy(&move_idx[off], g.leaf_idx, sizeof(uint16_t) * g.leaf_n);
+            off += (uint32_t)g.leaf_n;
+            slot_game[nb] = i;
+            game_slot[i] = nb;
+            nb++;
+        }
+        move_off[nb] = off;
+        double t1 = now_s();
+        tree_s += t1 - t0;
+        if (nb > 0) {
+            const int rc = cb_eval_leaves(h, boards.data(), q.data(), nb, cfg->material_on, move_idx.data(), move_off.data(),
+                                          priors.data(), v_logit.data(), v_final.data(), kk.data());
+            if (rc != CB_OK) {
+                if (sample_file) fclose(sample_file);
+                return rc;
+            }
+        }
+        double t2 = now_s();
+        eval_s += t2 - t1;
+        pool.run([&](int b, int e) {
+            for (int i = b; i < e; ++i) {
+                Game& g = games[i];
+                if (g.wants_eval) {
+                    const int s = game_slot[i];
+                    expand_and_backup(g, &priors[move_off[s]], v_final[s]);
+                }
+                if (g.sims_done >= cfg->sims_per_move) play_move(g, i);
+            }
+        });
+        tree_s += now_s() - t2;
+        sims += G;
+        evals += nb;
+        steps++;
+    }
+    if (sample_file) fclose(sample_file);
+    out->sims = sims;
+    out->nn_evals = evals;
+    out->terminal_hits = terminal_hits.load();
+    out->moves = moves_played.load();
+    out->games_finished = games_finished.load();
+    out->samples = samples_written.load();
+    out->steps = steps;
+    out->white_wins = wwins.load();
+    out->black_wins = bwins.load();
+    out->draws = draws.load();
+    out->seconds = now_s() - t_start;
+    out->eval_seconds = eval_s;
+    out->tree_seconds = tree_s;
+    out->mean_batch = steps ? (double)evals / (double)steps : 0.0;
+    return CB_OK;
+}
+
+}  // extern "C"

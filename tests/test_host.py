@@ -1,0 +1,110 @@
+"""Host side of the path: the product's chess rules (legal-move lists = the path's legal-move
+mask) against the oracle and the reference's perft table; the C++ mirror of the reference's
+evaluator interface; the self-play driver's invariants."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+START = "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1"
+POS1 = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1"
+POS2 = "8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1"
+POS3 = "r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1"
+POS4 = "rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8"
+POS5 = "r4rk1/1pp1qppp/p1np1n2/2b1p1B1/2B1P1b1/P1NP1N2/1PP1QPPP/R4RK1 w - - 0 10"
+
+
+def u8(fen):
+    return O.boards_to_array([O.from_fen(fen)])[0]
+
+
+@pytest.mark.parametrize("fen,depth,nodes", [  # tests/perft_tests.rs:68-291
+    (START, 4, 197281), (POS1, 3, 97862), (POS2, 5, 674624), (POS3, 4, 422333), (POS4, 3, 62379), (POS5, 3, 89890)])
+def test_product_chess_perft(cb, fen, depth, nodes):
+    assert cb.chess_perft(u8(fen), depth) == nodes
+
+
+def test_product_legal_lists_equal_oracle(cb):
+    assert np.array_equal(cb.chess_startpos(), u8(START))
+    boards, idx, off, raw = O.random_positions(4242, 1500)
+    for i in range(1500):
+        mv, pi = cb.chess_legal_moves(boards[i])
+        want = sorted(zip(raw[off[i]:off[i + 1]].tolist(), idx[off[i]:off[i + 1]].tolist()))
+        assert sorted(zip(mv.tolist(), pi.tolist())) == want          # same set, same policy indices: bit-exact mask
+        if len(mv):
+            m = int(mv[i % len(mv)])
+            assert np.array_equal(cb.chess_make_move(boards[i], m),
+                                  O.boards_to_array([O.make_move(O.array_to_board(boards[i]), m)])[0])
+
+
+@pytest.fixture(scope="module")
+def host_test_exe(cb):
+    exe = os.path.join(REPO, "tests", "cpp", "_host_mirror_test")
+    lib_dir = os.path.dirname(cb.lib_path())
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(REPO, "tests", "cpp", "host_mirror_test.cpp"),
+                           "-o", exe, "-L", lib_dir, "-lcaissa_b200", "-Wl,-rpath," + lib_dir, "-lpthread"])
+    yield exe
+    os.remove(exe)
+
+
+def test_cpp_mirror_mock_servers(host_test_exe):
+    # tests/unit/inference_server_tests.rs: reply shape and (policy, v_logit, k) semantics
+    p = subprocess.run([host_test_exe, "mock"], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    assert "mock ok" in p.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_on_gpu(cb, golden, host_test_exe, tmp_path):
+    g, blob = golden("6x128_B")
+    n = 48
+    blob.tofile(tmp_path / "w.bin")
+    g["boards"][:n].tofile(tmp_path / "boards.bin")
+    p = subprocess.run([host_test_exe, "gpu", str(tmp_path / "w.bin"), str(tmp_path / "boards.bin"), str(n)],
+                       capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    rows = [l.split() for l in p.stdout.splitlines() if l and l[0].isdigit()]
+    assert len(rows) == n
+    ev = cb.Evaluator(6, 128, "bf16")
+    ev.load_weights(blob)
+    _, v_ref, k_ref = ev.predict_batch(g["boards"][:n], np.full(n, 0.25, dtype=np.float32), want_policy=False)
+    for i, r in enumerate(rows):
+        v_server, v_direct, psum, k = float(r[1]), float(r[2]), float(r[3]), float(r[4])
+        assert v_server == v_direct == pytest.approx(float(v_ref[i]), abs=1e-6)   # batching does not change results
+        assert abs(psum - 1.0) < 1e-3 and abs(k - k_ref[i]) < 1e-6
+
+
+@pytest.mark.gpu
+def test_selfplay_driver(cb, golden, tmp_path):
+    g, blob = golden("6x128_B")
+    ev = cb.Evaluator(6, 128, "bf16")
+    ev.load_weights(blob)
+    path = str(tmp_path / "games.bin")
+    st = ev.selfplay(games=64, sims_per_move=24, max_plies=30, material_on=True, seed=7, max_games=40, threads=4,
+                     sample_path=path, max_seconds=120)
+    assert st["games_finished"] >= 40
+    assert st["sims"] == st["steps"] * 64 == st["nn_evals"] + st["terminal_hits"]   # one leaf per game per step
+    assert 40 < st["mean_batch"] <= 64
+    assert st["white_wins"] + st["black_wins"] + st["draws"] == st["games_finished"]
+    rec = np.fromfile(path, dtype=np.float32).reshape(-1, 5763)                     # src/training_data.rs:20-60
+    assert rec.shape[0] == st["samples"] > 0
+    planes, material, flag, z, pol = rec[:, :1088], rec[:, 1088], rec[:, 1089], rec[:, 1090], rec[:, 1091:]
+    assert set(np.unique(planes)) <= {0.0, 1.0} and (planes[:, 5 * 64:6 * 64].sum(axis=1) == 1).all()  # one STM king
+    assert (flag == 1.0).all() and set(np.unique(z)) <= {-1.0, 0.0, 1.0}
+    np.testing.assert_allclose(pol.sum(axis=1), 1.0, atol=1e-4)
+    # first sample of a game is the start position: its planes are the oracle's, its policy lives on legal moves
+    start_planes = O.board_to_planes(O.from_fen(START))
+    first = np.where((planes == start_planes).all(axis=1))[0]
+    assert len(first) >= 1
+    legal = {O.move_to_index_stm(m, True) for m in O.legal_moves(O.from_fen(START))}
+    assert set(np.nonzero(pol[first[0]])[0].tolist()) <= legal
+    assert abs(material[first[0]]) < 1e-6
+    # determinism of the whole pipeline for a fixed seed and a single host thread
+    a = ev.selfplay(games=16, sims_per_move=8, max_plies=12, seed=3, max_sims=16 * 8 * 12, threads=1)
+    b = ev.selfplay(games=16, sims_per_move=8, max_plies=12, seed=3, max_sims=16 * 8 * 12, threads=1)
+    for k in ("sims", "nn_evals", "terminal_hits", "moves", "games_finished"):
+        assert a[k] == b[k]
