@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--selfplay-seconds", type=float, default=5.0, help="0 disables the self-play section")
+    ap.add_argument("--selfplay-games", type=int, default=1024)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -247,7 +249,10 @@ def main():
     launch_ms = float(tower_ms.mean())
     flops_launch = tower_flops_per_position(args.blocks, args.hidden) * B
 
-    # ---- end to end through the public C ABI with host buffers
+    # ---- end to end through the public C ABI with host buffers: every step copies boards / q / CSR
+    # host->device and priors / values device->host inside the timed region.  Two evaluator handles
+    # (independent streams, the ABI's documented multi-handle use) are driven by two host threads so
+    # one handle's copies overlap the other's kernels; the single-handle synchronous rate is kept too.
     for _ in range(W):
         ev.eval_leaves(boards, q, idx, off)
     barrier()
@@ -255,18 +260,53 @@ def main():
     for _ in range(K):
         out = ev.eval_leaves(boards, q, idx, off)
     torch.cuda.synchronize()
+    e2e_sync_s = time.perf_counter() - t0
+    ev2 = cb.Evaluator(args.blocks, args.hidden, args.dtype, device=local_rank)
+    ev2.load_weights(blob)
+    for _ in range(W):
+        ev2.eval_leaves(boards, q, idx, off)
+    counts = [K - K // 2, K // 2]
+
+    def pump(e, n):
+        for _ in range(n):
+            e.eval_leaves(boards, q, idx, off)
+    barrier()
+    threads = [threading.Thread(target=pump, args=(e, n)) for e, n in zip((ev, ev2), counts)]
+    t0 = time.perf_counter()
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
     h2d = int(boards.nbytes + q.nbytes + idx.nbytes + off.nbytes)
     d2h = int(out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes)
 
+    # ---- self-play pool on this GPU (config 3 shape: 200 sims/move, 1024 concurrent games, vanilla mode)
+    sp = None
+    if args.selfplay_seconds > 0:
+        ev2.close()
+        nthreads = max(1, (os.cpu_count() or 1) // world)
+        barrier()
+        sp = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=1 + rank,
+                         max_seconds=args.selfplay_seconds, threads=nthreads)
+        barrier()
+
     # ---- max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3, launch_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, launch_ms, e2e_sync_s * 1e3, sp["seconds"] if sp else 0.0],
+                     dtype=torch.float64, device="cuda")
+    tot = torch.tensor([sp["sims"] if sp else 0, sp["nn_evals"] if sp else 0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, launch_ms = [float(x) for x in t.tolist()]
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds = [float(x) for x in t.tolist()]
     value = world * B * K / (dev_ms * 1e-3)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
+    # off the hot path: the one exchange the multi-GPU design has (training-sample gather over NCCL)
+    gathered = None
+    if world > 1:
+        from caissa_b200 import distributed as D
+        rec = np.zeros((4, D.RECORD_FLOATS), dtype=np.float32) + rank
+        gathered = int(D.gather_samples(rec).shape[0])
 
     if rank == 0:
         sustained, burst, how = load_peaks()
@@ -280,7 +320,9 @@ def main():
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / K, "api": "cb_eval_leaves (host buffers, synchronous)"},
+                    "ms_per_step": e2e_ms / K,
+                    "api": "cb_eval_leaves with host buffers, 2 handles x 2 host threads per GPU",
+                    "single_handle_sync_value": world * B * K / (e2e_sync_ms * 1e-3)},
             "gpu_launches": int(ev.launches_per_forward() * K * world),
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
@@ -291,6 +333,16 @@ def main():
             "whole_path_tflops": value / world * FLOPS_PER_EVAL.get((args.blocks, args.hidden), 0) / 1e12,
             "wall_s_timed_region": wall,
         }
+        if sp:
+            line["selfplay"] = {"sims_per_s": float(tot[0].item()) / sp_seconds,
+                                "nn_evals_per_s": float(tot[1].item()) / sp_seconds,
+                                "games_per_gpu": args.selfplay_games, "sims_per_move": 200, "mode": "vanilla (config 5 rules: "
+                                "Tier 1 off, material off), one leaf in flight per game, one eval batch per step",
+                                "host_threads_per_gpu": max(1, (os.cpu_count() or 1) // world),
+                                "seconds": sp_seconds, "mean_batch": sp["mean_batch"],
+                                "eval_fraction": sp["eval_seconds"] / max(sp["seconds"], 1e-9)}
+        if gathered is not None:
+            line["nccl_sample_gather_records"] = gathered
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = time_cpu_path(args, boards, q, idx, off, blob, 20.0, 3, 1)
             line["cpu_baseline"] = cpu

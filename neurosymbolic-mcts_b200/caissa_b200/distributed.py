@@ -1,0 +1,58 @@
+"""Multi-GPU plumbing: one process per GPU, replicas only on the hot path.
+
+Self-play games are independent, so every rank runs its own game pool and evaluator handle with
+replicated weights and there is NO collective on the evaluation path.  The two
+off-path exchanges are here, over torch.distributed (NCCL on NVLink for GPU tensors, gloo for the
+CPU tests):
+
+  gather_samples     finished-game training samples (5763-f32 records, src/training_data.rs:20-60)
+                     from all ranks to every rank (all_gather of padded fixed-size blocks)
+  broadcast_weights  a new generation's flat weight blob from rank 0 to all ranks
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+RECORD_FLOATS = 5763
+
+
+def _device():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced [lo, hi) of `n_items` independent units (games / positions) for `rank`."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_samples(local):
+    """local: float32 [n_local, 5763] (n_local may differ per rank, may be 0) -> float32 [sum n, 5763],
+    rank-major order, identical on every rank."""
+    local = np.ascontiguousarray(local, dtype=np.float32).reshape(-1, RECORD_FLOATS)
+    dev = _device()
+    world = dist.get_world_size()
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    counts[dist.get_rank()] = local.shape[0]
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    n_max = int(counts.max().item())
+    if n_max == 0:
+        return np.zeros((0, RECORD_FLOATS), dtype=np.float32)
+    block = torch.zeros((n_max, RECORD_FLOATS), dtype=torch.float32, device=dev)
+    if local.shape[0]:
+        block[:local.shape[0]] = torch.from_numpy(local).to(dev)
+    out = torch.empty((world, n_max, RECORD_FLOATS), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(out, block) if dev.type == "cuda" else dist.all_gather(list(out.unbind(0)), block)
+    out = out.cpu().numpy()
+    return np.concatenate([out[r, :int(counts[r].item())] for r in range(world)], axis=0)
+
+
+def broadcast_weights(blob, n_floats):
+    """Rank 0 passes the blob, the others pass None; every rank returns the same float32 [n_floats]."""
+    dev = _device()
+    t = torch.empty(n_floats, dtype=torch.float32, device=dev)
+    if dist.get_rank() == 0:
+        t.copy_(torch.from_numpy(np.ascontiguousarray(blob, dtype=np.float32)))
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy()

@@ -1,0 +1,38 @@
+"""N > 1 host logic on CPU: two gloo ranks exchange training samples and weights exactly the way
+the NCCL ranks do on the GPU box (no collective exists on the evaluation path itself)."""
+import os
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.join(REPO, "neurosymbolic-mcts_b200"))
+    import torch.distributed as dist
+    from caissa_b200 import distributed as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    n_local = [3, 0, 5][rank % 3] if world > 1 else 3
+    local = rng.random((n_local, D.RECORD_FLOATS), dtype=np.float32) + rank
+    allrec = D.gather_samples(local)
+    blob = D.broadcast_weights(np.arange(1000, dtype=np.float32) if rank == 0 else None, 1000)
+    lo, hi = D.shard_range(1024 + 1, rank, world)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), local=local, allrec=allrec, blob=blob, lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sample_gather_and_weight_broadcast(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, 29611, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / ("r%d.npz" % i)) for i in range(world)]
+    want = np.concatenate([r[0]["local"], r[1]["local"]], axis=0)
+    for i in range(world):
+        assert np.array_equal(r[i]["allrec"], want)                 # rank-major, ragged counts (3 and 0)
+        assert np.array_equal(r[i]["blob"], np.arange(1000, dtype=np.float32))
+    # the shards of the independent units tile [0, n) exactly
+    assert r[0]["lo"] == 0 and r[0]["hi"] == r[1]["lo"] and r[1]["hi"] == 1025
