@@ -21,6 +21,7 @@
 #include "kernels_simt.cuh"
 #include "policy_umma.cuh"
 #include "tower_umma.cuh"
+#include "tower_t_umma.cuh"
 
 namespace {
 
@@ -91,6 +92,12 @@ struct cb_handle {
     cb::TowerLayer* d_layers = nullptr;
     bool tower_ready = false;
     bool use_fused = true;
+    // transposed (quad-layout) fused tower for the 128-channel net
+    CUtensorMap tm_x0_q, tm_act_ld_q[3], tm_act_st_q[3];
+    CUtensorMap* d_maps_q = nullptr;
+    cb::TowerTLayer* d_layers_q = nullptr;
+    bool tower_q_ready = false;
+    bool use_quad = true;
 
     // pinned staging
     cb_board* h_boards = nullptr;
@@ -152,11 +159,11 @@ void drop_graphs(cb_handle* h) {
 
 // 5-D map over the pair-interleaved activation act[pair][y][b2][x][C]; box_y = 10 for the
 // halo'd slab loads (fetched at y = -1), 8 for residual-free output stores.
-int make_act_map(cb_handle* h, CUtensorMap* tm, void* base, int channels, int boards, int box_y) {
-    const cuuint64_t C = (cuuint64_t)channels;
-    const cuuint64_t dims[5] = {C, 8, 2, 8, (cuuint64_t)boards / 2};
-    const cuuint64_t strides[4] = {C * 2, C * 16, C * 32, C * 256};
-    const cuuint32_t box[5] = {64, 8, 2, (cuuint32_t)box_y, 1};
+int make_act_map(cb_handle* h, CUtensorMap* tm, void* base, int channels, int boards, int box_y, int group = 2) {
+    const cuuint64_t C = (cuuint64_t)channels, G = (cuuint64_t)group;
+    const cuuint64_t dims[5] = {C, 8, G, 8, (cuuint64_t)boards / G};
+    const cuuint64_t strides[4] = {C * 2, C * 16, C * 16 * G, C * 128 * G};
+    const cuuint32_t box[5] = {64, 8, (cuuint32_t)group, (cuuint32_t)box_y, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUtensorMapDataType dt =
         h->dtype == CB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -206,7 +213,7 @@ int build_tower_tables(cb_handle* h);
 
 // Grow device + pinned buffers to hold B boards (rounded up to a whole 2-board tile).
 int ensure_capacity(cb_handle* h, int B) {
-    const int need = (B + 1) & ~1;
+    const int need = (B + 3) & ~3;
     if (need <= h->cap) return CB_OK;
     int cap = h->cap ? h->cap : 64;
     while (cap < need) cap *= 2;
@@ -240,6 +247,13 @@ int ensure_capacity(cb_handle* h, int B) {
         for (int i = 0; i < 3; ++i) {
             if ((rc = make_act_map(h, &h->tm_act_ld[i], h->d_act[i], h->hid, cap, 10))) return rc;
             if ((rc = make_act_map(h, &h->tm_act_st[i], h->d_act[i], h->hid, cap, 8))) return rc;
+        }
+        if (h->hid == 128) {
+            if ((rc = make_act_map(h, &h->tm_x0_q, h->d_x0, 64, cap, 10, 4))) return rc;
+            for (int i = 0; i < 3; ++i) {
+                if ((rc = make_act_map(h, &h->tm_act_ld_q[i], h->d_act[i], h->hid, cap, 10, 4))) return rc;
+                if ((rc = make_act_map(h, &h->tm_act_st_q[i], h->d_act[i], h->hid, cap, 8, 4))) return rc;
+            }
         }
         if (h->loaded && (rc = build_tower_tables(h))) return rc;
     }
@@ -282,6 +296,73 @@ int build_tower_tables(cb_handle* h) {
     CB_CUDA(h, cudaMemcpy(h->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     CB_CUDA(h, cudaMemcpy(h->d_layers, ly.data(), ly.size() * sizeof(TowerLayer), cudaMemcpyHostToDevice));
     h->tower_ready = true;
+    h->tower_q_ready = false;
+    if (h->hid == 128) {
+        // map table: 0 x0 (quad ld) | 1..3 act quad ld | 4..6 act quad st (also residual loads) |
+        //            7 act[1] pair st (p_conv output, read by the policy kernel) | 8.. weights
+        std::vector<CUtensorMap> mq(8 + nl);
+        mq[0] = h->tm_x0_q;
+        for (int i = 0; i < 3; ++i) { mq[1 + i] = h->tm_act_ld_q[i]; mq[4 + i] = h->tm_act_st_q[i]; }
+        mq[7] = h->tm_act_st[1];
+        for (int l = 0; l < nl; ++l) mq[8 + l] = h->convs[l].tm_w;
+        std::vector<TowerTLayer> lq(nl);
+        memset(lq.data(), 0, sizeof(TowerTLayer) * nl);
+        int c2 = 0;
+        lq[0].in_map = 0; lq[0].w_map = 8; lq[0].out_map = 4 + 0; lq[0].kc_in = 1; lq[0].mode = MODE_RELU;
+        lq[0].bias = h->convs[0].bias;
+        for (int i = 0; i < h->blocks; ++i) {
+            const int nxt = c2 == 0 ? 2 : 0;
+            TowerTLayer& a = lq[1 + 2 * i];
+            a.in_map = 1 + c2; a.w_map = 8 + 1 + 2 * i; a.out_map = 4 + 1; a.kc_in = 2; a.mode = MODE_RELU;
+            a.bias = h->convs[1 + 2 * i].bias;
+            TowerTLayer& b = lq[2 + 2 * i];
+            b.in_map = 1 + 1; b.w_map = 8 + 2 + 2 * i; b.out_map = 4 + nxt; b.res_map = 4 + c2; b.kc_in = 2;
+            b.mode = MODE_SE_RES;
+            b.bias = h->convs[2 + 2 * i].bias;
+            b.se_w1 = h->se_w1[i]; b.se_w2 = h->se_w2[i];
+            if (i == h->blocks - 1) { b.v_w = h->v_w; b.v_pre = h->d_vpre; }
+            c2 = nxt;
+        }
+        TowerTLayer& pq = lq[nl - 1];
+        pq.in_map = 1 + c2; pq.w_map = 8 + nl - 1; pq.out_map = 7; pq.out_pair = 1; pq.kc_in = 2; pq.mode = MODE_RELU;
+        pq.bias = h->convs[nl - 1].bias;
+        free_dev(h->d_maps_q); free_dev(h->d_layers_q);
+        h->d_maps_q = nullptr; h->d_layers_q = nullptr;
+        CB_CUDA(h, cudaMalloc(&h->d_maps_q, mq.size() * sizeof(CUtensorMap)));
+        CB_CUDA(h, cudaMalloc(&h->d_layers_q, lq.size() * sizeof(TowerTLayer)));
+        CB_CUDA(h, cudaMemcpy(h->d_maps_q, mq.data(), mq.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        CB_CUDA(h, cudaMemcpy(h->d_layers_q, lq.data(), lq.size() * sizeof(TowerTLayer), cudaMemcpyHostToDevice));
+        h->tower_q_ready = true;
+    }
+    return CB_OK;
+}
+
+// Which fused tower runs for this handle right now (0 none / per-layer, 1 pair-layout, 2 quad-layout transposed).
+int fused_kind(const cb_handle* h) {
+    if (h->dtype == CB_DTYPE_FP32 || !h->use_fused || h->layer_limit != 0) return 0;
+    if (h->hid == 128 && h->use_quad && h->tower_q_ready) return 2;
+    return h->tower_ready ? 1 : 0;
+}
+
+int launch_tower_q(cb_handle* h, int B) {
+    TowerTParams tp;
+    tp.maps = h->d_maps_q;
+    tp.layers = h->d_layers_q;
+    tp.num_layers = (int)h->convs.size();
+    tp.num_quads = (B + 3) / 4;
+    tp.num_boards = B;
+    const int units = (tp.num_quads + 1) / 2;
+    const int grid = units < h->sm_count ? units : h->sm_count;
+    if (h->dtype == CB_DTYPE_BF16) {
+        auto kern = tower_t_umma_kernel<true>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerTCfg::kSmemBytes));
+        kern<<<grid, TowerTCfg::kThreads, TowerTCfg::kSmemBytes, h->stream>>>(tp);
+    } else {
+        auto kern = tower_t_umma_kernel<false>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerTCfg::kSmemBytes));
+        kern<<<grid, TowerTCfg::kThreads, TowerTCfg::kSmemBytes, h->stream>>>(tp);
+    }
+    CB_CUDA(h, cudaGetLastError());
     return CB_OK;
 }
 
@@ -501,17 +582,21 @@ int enqueue_tower(cb_handle* h, int B, std::vector<cudaEvent_t>* ev) {
 
 // Enqueue one full forward on the handle's stream (inputs already in d_boards/d_q/CSR).
 int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int material_on, bool use_q) {
-    const int Bpad = (B + 1) & ~1;
+    const int kind = fused_kind(h);
+    const int glog = kind == 2 ? 2 : 1;                       // boards interleaved per activation group
+    const int Bpad = (B + (1 << glog) - 1) & ~((1 << glog) - 1);
     if (h->dtype == CB_DTYPE_FP32) {
         encode_nhwc_f32_kernel<<<(B * 64 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, (float*)h->d_x0);
     } else if (h->dtype == CB_DTYPE_BF16) {
-        encode_pair16_kernel<true><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, (uint4*)h->d_x0);
+        encode_tiled16_kernel<true><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, glog, (uint4*)h->d_x0);
     } else {
-        encode_pair16_kernel<false><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, (uint4*)h->d_x0);
+        encode_tiled16_kernel<false><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, glog, (uint4*)h->d_x0);
     }
     CB_CUDA(h, cudaGetLastError());
     int rc;
-    if (h->use_fused && h->tower_ready && h->layer_limit == 0)
+    if (kind == 2)
+        rc = launch_tower_q(h, B);
+    else if (kind == 1)
         rc = launch_tower(h, B);
     else
         rc = enqueue_tower(h, B, nullptr);
@@ -536,7 +621,7 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     vp.out_b = h->out_b;
     vp.k = h->k;
     vp.material_on = material_on;
-    vp.pair_layout = h->dtype != CB_DTYPE_FP32;
+    vp.pair_layout = h->dtype == CB_DTYPE_FP32 ? 0 : (kind == 2 ? 0 : 1);  // quad tower emits v_pre in plain order
     vp.B = B;
     vp.v_logit = h->d_vlogit;
     vp.v_final = h->d_vfinal;
@@ -631,6 +716,8 @@ int cb_create(cb_handle** out, int device, int num_blocks, int hidden, int dtype
     h->use_graphs = !(ng && ng[0] == '1');
     const char* nf = getenv("CB_NO_FUSE");
     h->use_fused = !(nf && nf[0] == '1');
+    const char* tp = getenv("CB_TOWER_PAIR");
+    h->use_quad = !(tp && tp[0] == '1');
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         delete h;
@@ -669,6 +756,7 @@ void cb_destroy(cb_handle* h) {
     free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
     free_dev(h->p_w16);
     free_dev(h->d_maps); free_dev(h->d_layers);
+    free_dev(h->d_maps_q); free_dev(h->d_layers_q);
     free_dev(h->d_flush);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -994,13 +1082,14 @@ int cb_time_tower(cb_handle* h, int iters, float* ms_each, int* n_launches) {
     if (!h || iters <= 0 || !ms_each) return CB_EINVAL;
     if (!h->staged_B) return fail(h, CB_ESTATE, "nothing staged: call cb_stage_leaves first");
     CB_CUDA(h, cudaSetDevice(h->device));
-    const bool fused = h->dtype != CB_DTYPE_FP32 && h->use_fused && h->tower_ready && h->layer_limit == 0;
+    const int kind = fused_kind(h);
+    const bool fused = kind != 0;
     std::vector<cudaEvent_t> ev(2 * (size_t)iters);
     for (auto& e : ev) CB_CUDA(h, cudaEventCreate(&e));
     int rc = CB_OK;
     for (int i = 0; i < iters && !rc; ++i) {
         CB_CUDA(h, cudaEventRecord(ev[2 * i], h->stream));
-        rc = fused ? launch_tower(h, h->staged_B) : enqueue_tower(h, h->staged_B, nullptr);
+        rc = kind == 2 ? launch_tower_q(h, h->staged_B) : kind == 1 ? launch_tower(h, h->staged_B) : enqueue_tower(h, h->staged_B, nullptr);
         CB_CUDA(h, cudaEventRecord(ev[2 * i + 1], h->stream));
     }
     cudaError_t se = cudaStreamSynchronize(h->stream);
@@ -1045,12 +1134,14 @@ int cb_debug_act(cb_handle* h, int B, int buf, float* out) {
     if (rc) return rc;
     const void* src = h->d_act[buf];
     const int grid = (total + 255) / 256;
+    // buffer 1 ends a forward holding p_conv's output, always in pair layout; the others follow the tower
+    const int lay = (fused_kind(h) == 2 && buf != 1) ? 2 : 1;
     if (h->dtype == CB_DTYPE_FP32)
         act_to_nchw_f32_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)src, h->hid, total, 0, h->d_scratch);
     else if (h->dtype == CB_DTYPE_BF16)
-        act_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, h->stream>>>((const __nv_bfloat16*)src, h->hid, total, 1, h->d_scratch);
+        act_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, h->stream>>>((const __nv_bfloat16*)src, h->hid, total, lay, h->d_scratch);
     else
-        act_to_nchw_f32_kernel<__half><<<grid, 256, 0, h->stream>>>((const __half*)src, h->hid, total, 1, h->d_scratch);
+        act_to_nchw_f32_kernel<__half><<<grid, 256, 0, h->stream>>>((const __half*)src, h->hid, total, lay, h->d_scratch);
     CB_CUDA(h, cudaGetLastError());
     CB_CUDA(h, cudaMemcpyAsync(out, h->d_scratch, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
     CB_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -16,11 +16,13 @@
 
 namespace cb {
 
-// Row of (board b, pixel px = y*8 + x) in the pair-interleaved activation layout
-// act[pair][y][b2][x][C] used by the tensor-core tower (see conv_umma.cuh); plain NHWC
-// [b][px] for the exact-mode tower.
-__host__ __device__ __forceinline__ int act_row(int b, int px, bool pair_layout) {
-    return pair_layout ? ((b >> 1) * 128 + (((px >> 3) * 2 + (b & 1)) << 3) + (px & 7)) : (b * 64 + px);
+// Row of (board b, pixel px = y*8 + x) in an activation buffer.  layout 0: plain NHWC [b][px]
+// (exact-mode tower); 1: pair-interleaved act[pair][y][b2][x] (conv_umma.cuh / tower_umma.cuh);
+// 2: quad-interleaved act[quad][y][b4][x] (tower_t_umma.cuh).
+__host__ __device__ __forceinline__ int act_row(int b, int px, int layout) {
+    if (layout == 1) return (b >> 1) * 128 + (((px >> 3) * 2 + (b & 1)) << 3) + (px & 7);
+    if (layout == 2) return (b >> 2) * 256 + (((px >> 3) * 4 + (b & 3)) << 3) + (px & 7);
+    return b * 64 + px;
 }
 
 // ------------------------------------------------------------------ encoder
@@ -65,18 +67,20 @@ __global__ void encode_nhwc_f32_kernel(const cb_board* __restrict__ boards, int 
     for (int p = 0; p < 17; ++p) o[p] = (m >> p) & 1u ? 1.0f : 0.0f;
 }
 
-// Pair-interleaved 16-bit [Bpad/2][8 y][2 b2][8 x][64]: channels 0..16 are the planes, 17..63
-// zero (K padding of the start conv to one 64-channel TMA/UMMA chunk).  8 threads per pixel
-// row, one 16-byte store each => fully coalesced 512 B per warp instruction.  Boards at index
-// >= B (batch padded to a whole pair) are written as zeros.
+// Group-interleaved 16-bit planes [Bpad/G][8 y][G boards][8 x][64] with G = 2 (pair) or 4 (quad):
+// channels 0..16 are the planes, 17..63 zero (K padding of the start conv to one 64-channel
+// TMA/UMMA chunk).  8 threads per pixel row, one 16-byte store each => fully coalesced 512 B per
+// warp instruction.  Boards at index >= B (batch padded to a whole group) are written as zeros.
 template <bool BF16>
-__global__ void encode_pair16_kernel(const cb_board* __restrict__ boards, int B, int Bpad, uint4* __restrict__ out) {
+__global__ void encode_tiled16_kernel(const cb_board* __restrict__ boards, int B, int Bpad, int group_log2,
+                                      uint4* __restrict__ out) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= Bpad * 512) return;
-    const int j = gid & 7, grow = gid >> 3;          // global pixel row = pair*128 + (y*2+b2)*8 + x
-    const int m = grow & 127;
-    const int b = (grow >> 7) * 2 + ((m >> 3) & 1);
-    const int y = m >> 4, x = m & 7;
+    const int j = gid & 7, grow = gid >> 3;          // global pixel row = grp*(64*G) + (y*G + bi)*8 + x
+    const int G = 1 << group_log2;
+    const int m = grow & (64 * G - 1);
+    const int b = (grow >> (6 + group_log2)) * G + ((m >> 3) & (G - 1));
+    const int y = m >> (3 + group_log2), x = m & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (j < 3 && b < B) {
         const uint32_t msk = pixel_plane_mask(boards + b, y, x) >> (j * 8);
@@ -234,7 +238,7 @@ policy_head_kernel(const T* __restrict__ p, const float* __restrict__ wt, const 
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int i = tid; i < 64 * HID; i += kPolicyThreads) {
         const int px = i / HID, c = i % HID;
-        s_p[i] = to_f32<T>(p[static_cast<size_t>(act_row(b, px, pair_layout != 0)) * HID + c]);
+        s_p[i] = to_f32<T>(p[static_cast<size_t>(act_row(b, px, pair_layout)) * HID + c]);
     }
     for (int i = tid; i < HID * 73; i += kPolicyThreads) s_w[i] = wt[i];
     __syncthreads();
@@ -317,7 +321,7 @@ struct ValueParams {
     float out_b;
     float k;               // 0.47 * softplus(k_logit)
     int material_on;
-    int pair_layout;       // v_pre indexed by act_row()
+    int pair_layout;       // layout code of v_pre rows, see act_row()
     int B;
     float* v_logit;        // [B]
     float* v_final;        // [B] tanh(v_logit + k q) or tanh(v_logit)
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(256) value_head_kernel(const ValueParams vp) {
         float v = 0.0f;
         if (b < vp.B) {
             if (e < 64)
-                v = fmaxf((vp.v_pre[act_row(b, e, vp.pair_layout != 0)] + vp.conv_bias) * vp.bn_scale + vp.bn_bias, 0.0f);
+                v = fmaxf((vp.v_pre[act_row(b, e, vp.pair_layout)] + vp.conv_bias) * vp.bn_scale + vp.bn_bias, 0.0f);
             else
                 v = vp.q ? vp.q[b] : 0.0f;
         }
@@ -377,7 +381,7 @@ __global__ void act_to_nchw_f32_kernel(const T* __restrict__ in, int hid, int to
     if (gid >= total) return;
     const int c = gid % hid, px = (gid / hid) & 63, b = gid / (hid * 64);
     out[gid / (hid * 64) * hid * 64 + c * 64 + px] =
-        to_f32<T>(in[static_cast<size_t>(act_row(b, px, pair_layout != 0)) * hid + c]);
+        to_f32<T>(in[static_cast<size_t>(act_row(b, px, pair_layout)) * hid + c]);
 }
 
 }  // namespace cb
