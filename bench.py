@@ -325,11 +325,13 @@ def main():
                     "single_handle_sync_value": world * B * K / (e2e_sync_ms * 1e-3)},
             "gpu_launches": int(ev.launches_per_forward() * K * world),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                         "frac": achieved / sustained, "traffic": traffic,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
+                         "frac": achieved / burst, "traffic": traffic,
                          "kernel": "tower_umma_kernel<%d> (whole conv tower, %d launch/step)" % (args.hidden, n_tower),
                          "flops_per_launch": flops_launch, "launch_ms": launch_ms,
-                         "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json (%s); burst %.1f" % (how, burst)},
+                         "peak_source": "bf16_tflops (burst: the tower launch is timed alone with CUDA events) of "
+                                        "MEASURED_PEAKS.json (%s); sustained figure %.1f -> frac %.3f" % (
+                                            how, sustained, achieved / sustained)},
             "whole_path_tflops": value / world * FLOPS_PER_EVAL.get((args.blocks, args.hidden), 0) / 1e12,
             "wall_s_timed_region": wall,
         }

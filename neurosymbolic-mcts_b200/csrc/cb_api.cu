@@ -50,6 +50,8 @@ struct cb_handle {
     int sm_count = 0;
     bool loaded = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;             // side branch: value head runs beside the policy head
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::string err;
     EncodeTiledFn encode_tiled = nullptr;
@@ -608,7 +610,9 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
         po.move_off = h->d_move_off;
         po.priors = h->d_priors;
     }
-    if ((rc = launch_policy(h, h->d_act[1], B, po))) return rc;
+    // the two heads are independent: fork the value head onto the side stream
+    CB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    CB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     ValueParams vp = {};
     vp.v_pre = h->d_vpre;
     vp.q = use_q ? h->d_q : nullptr;
@@ -626,8 +630,11 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     vp.v_logit = h->d_vlogit;
     vp.v_final = h->d_vfinal;
     vp.k_out = h->d_k;
-    value_head_kernel<<<(B + kValueBoardsPerCta - 1) / kValueBoardsPerCta, 256, 0, h->stream>>>(vp);
+    value_head_kernel<<<(B + kValueBoardsPerCta - 1) / kValueBoardsPerCta, 256, 0, h->stream2>>>(vp);
     CB_CUDA(h, cudaGetLastError());
+    CB_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
+    if ((rc = launch_policy(h, h->d_act[1], B, po))) return rc;
+    CB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     return CB_OK;
 }
 
@@ -729,6 +736,9 @@ int cb_create(cb_handle** out, int device, int num_blocks, int hidden, int dtype
     }
     h->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
         cudaEventCreate(&h->ev2) != cudaSuccess || cudaEventCreate(&h->ev3) != cudaSuccess) {
         cb_destroy(h);
@@ -762,6 +772,9 @@ void cb_destroy(cb_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev3) cudaEventDestroy(h->ev3);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
