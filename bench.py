@@ -285,7 +285,7 @@ def main():
     sp = None
     if args.selfplay_seconds > 0:
         ev2.close()
-        nthreads = max(1, (os.cpu_count() or 1) // world)
+        nthreads = max(1, (os.cpu_count() or 1) // world - 2)
         barrier()
         sp = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=1 + rank,
                          max_seconds=args.selfplay_seconds, threads=nthreads)
@@ -340,7 +340,7 @@ def main():
                                 "nn_evals_per_s": float(tot[1].item()) / sp_seconds,
                                 "games_per_gpu": args.selfplay_games, "sims_per_move": 200, "mode": "vanilla (config 5 rules: "
                                 "Tier 1 off, material off), one leaf in flight per game, one eval batch per step",
-                                "host_threads_per_gpu": max(1, (os.cpu_count() or 1) // world),
+                                "host_threads_per_gpu": max(1, (os.cpu_count() or 1) // world - 2),
                                 "seconds": sp_seconds, "mean_batch": sp["mean_batch"],
                                 "eval_fraction": sp["eval_seconds"] / max(sp["seconds"], 1e-9)}
         if gathered is not None:

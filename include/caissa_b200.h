@@ -183,6 +183,8 @@ typedef struct cb_selfplay_config {
     long long max_games;  /* stop after this many finished games (0 = unlimited) */
     double max_seconds;   /* wall-clock bound (0 = unlimited) */
     const char* sample_path; /* nullable: append finished games as 5763-f32 records (src/training_data.rs:24-60) */
+    int pipeline;         /* 0/1: lock step (select, evaluate, expand); 2: two half-pools, the tree work of one
+                             half runs on the host while the other half's leaves are on the GPU */
 } cb_selfplay_config;
 
 typedef struct cb_selfplay_stats {

@@ -207,53 +207,69 @@ void reroot(Game& g, uint32_t child) {
     g.nodes.swap(fresh);
 }
 
+// Worker pool for the per-step tree work.  Dedicated spinning threads: a step's phases last
+// ~100 us, so condition-variable wake-ups (tens of us each) would dominate.
 struct Pool {
     int nthreads;
     std::vector<std::thread> threads;
-    std::mutex mu;
-    std::condition_variable cv, done_cv;
-    std::function<void(int, int)> job;  // [begin, end) of games
-    int generation = 0, pending = 0, ngames = 0;
-    bool stop = false;
+    std::function<void(int, int)> job;
+    std::atomic<int> generation{0}, pending{0};
+    std::atomic<bool> stop{false};
+    int begin = 0, end = 0;
 
-    Pool(int n, int games) : nthreads(n), ngames(games) {
+    explicit Pool(int n) : nthreads(n) {
         for (int t = 0; t < n; ++t) threads.emplace_back([this, t] { loop(t); });
     }
     ~Pool() {
-        {
-            std::lock_guard<std::mutex> l(mu);
-            stop = true;
-        }
-        cv.notify_all();
+        stop.store(true);
+        generation.fetch_add(1);
         for (auto& t : threads) t.join();
+    }
+    static void relax() {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
     }
     void loop(int t) {
         int seen = 0;
         for (;;) {
-            std::function<void(int, int)> j;
-            {
-                std::unique_lock<std::mutex> l(mu);
-                cv.wait(l, [&] { return stop || generation != seen; });
-                if (stop) return;
-                seen = generation;
-                j = job;
+            int spins = 0;
+            while (generation.load(std::memory_order_acquire) == seen) {
+                relax();
+                if (++spins > 4096) { std::this_thread::yield(); spins = 0; }
             }
-            const int per = (ngames + nthreads - 1) / nthreads;
-            const int b = t * per, e = b + per < ngames ? b + per : ngames;
-            if (b < e) j(b, e);
-            {
-                std::lock_guard<std::mutex> l(mu);
-                if (--pending == 0) done_cv.notify_one();
-            }
+            if (stop.load()) return;
+            seen = generation.load(std::memory_order_acquire);
+            const int n = end - begin, per = (n + nthreads - 1) / nthreads;
+            const int b = begin + t * per, e = b + per < end ? b + per : end;
+            if (b < e) job(b, e);
+            pending.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
-    void run(std::function<void(int, int)> j) {
-        std::unique_lock<std::mutex> l(mu);
+    void run(int b, int e, std::function<void(int, int)> j) {
         job = std::move(j);
-        pending = nthreads;
-        ++generation;
-        cv.notify_all();
-        done_cv.wait(l, [&] { return pending == 0; });
+        begin = b;
+        end = e;
+        pending.store(nthreads, std::memory_order_release);
+        generation.fetch_add(1, std::memory_order_acq_rel);
+        while (pending.load(std::memory_order_acquire) != 0) relax();
+    }
+};
+
+// One evaluation batch of a half-pool.  In pipelined mode a dedicated thread owns the evaluator
+// handle and serves these, so the tree work of one half runs under the other half's evaluation.
+struct EvalJob {
+    std::vector<cb_board> boards;
+    std::vector<float> q, priors, v_logit, v_final, kk;
+    std::vector<uint16_t> move_idx;
+    std::vector<uint32_t> move_off;
+    std::vector<int> game_slot;
+    int nb = 0, rc = CB_OK;
+    std::atomic<int> state{0};  // 0 idle, 1 submitted, 2 done
+    void init(int n) {
+        boards.resize(n); q.resize(n); v_logit.resize(n); v_final.resize(n); kk.resize(n);
+        priors.resize((size_t)n * kMaxMoves); move_idx.resize((size_t)n * kMaxMoves); move_off.resize(n + 1);
+        game_slot.resize(n);
     }
 };
 
@@ -295,23 +311,26 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
     const int max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     const float c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
     const double explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
-    int nthreads = cfg->threads > 0 ? cfg->threads : (int)std::thread::hardware_concurrency();
+    // the workers spin between phases: keep two cores for the driving thread and the CUDA runtime
+    int nthreads = cfg->threads > 0 ? cfg->threads : (int)std::thread::hardware_concurrency() - 2;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > G) nthreads = G;
 
+    const int halves = (cfg->pipeline >= 2 && G >= 2) ? 2 : 1;
+    if (halves == 2 && nthreads > 2) nthreads -= 1;   // leave a core to the evaluation thread
+
     std::vector<Game> games(G);
     for (int i = 0; i < G; ++i) games[i].reset(cfg->seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * (uint64_t)(i + 1));
-    Pool pool(nthreads, G);
+    Pool pool(nthreads);
     std::atomic<long long> terminal_hits(0), moves_played(0), games_finished(0), samples_written(0);
     std::atomic<long long> wwins(0), bwins(0), draws(0);
     std::mutex file_mu;
     FILE* sample_file = cfg->sample_path ? fopen(cfg->sample_path, "ab") : nullptr;
 
-    std::vector<cb_board> boards(G);
-    std::vector<float> q(G), priors((size_t)G * kMaxMoves), v_logit(G), v_final(G), kk(G);
-    std::vector<uint16_t> move_idx((size_t)G * kMaxMoves);
-    std::vector<uint32_t> move_off(G + 1);
-    std::vector<int> slot_game(G), game_slot(G);
+    // game ranges of the (one or two) half-pools and their evaluation jobs
+    const int hb[3] = {0, halves == 2 ? G / 2 : G, G};
+    EvalJob jobs[2];
+    for (int hf = 0; hf < halves; ++hf) jobs[hf].init(hb[hf + 1] - hb[hf]);
 
     // Finish a game: assign z to its samples and write them in the reference's 5763-f32 format.
     auto finish_game = [&](Game& g, int result_white /* +1 white won, -1 black won, 0 draw */) {
@@ -422,56 +441,127 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
     const double t_start = now_s();
     double eval_s = 0.0, tree_s = 0.0;
     long long sims = 0, evals = 0, steps = 0;
-    for (;;) {
-        if (cfg->max_sims > 0 && sims >= cfg->max_sims) break;
-        if (cfg->max_games > 0 && games_finished.load() >= cfg->max_games) break;
-        if (cfg->max_seconds > 0 && now_s() - t_start >= cfg->max_seconds) break;
-        double t0 = now_s();
-        pool.run([&](int b, int e) {
+    int failed = CB_OK;
+
+    auto eval_job = [&](EvalJob& j) {
+        j.rc = CB_OK;
+        if (j.nb > 0)
+            j.rc = cb_eval_leaves(h, j.boards.data(), j.q.data(), j.nb, cfg->material_on, j.move_idx.data(), j.move_off.data(),
+                                  j.priors.data(), j.v_logit.data(), j.v_final.data(), j.kk.data());
+    };
+    // phase A for one half-pool: select leaves, pack the evaluation batch
+    auto select_and_pack = [&](int hf) {
+        EvalJob& j = jobs[hf];
+        const int g0 = hb[hf], g1 = hb[hf + 1];
+        pool.run(g0, g1, [&](int b, int e) {
             for (int i = b; i < e; ++i) select_leaf(games[i], c_puct, terminal_hits);
         });
-        // pack the evaluation batch (CSR of legal policy indices)
         int nb = 0;
         uint32_t off = 0;
-        for (int i = 0; i < G; ++i) {
+        for (int i = g0; i < g1; ++i) {
             Game& g = games[i];
             if (!g.wants_eval) continue;
-            boards[nb] = g.leaf_board;
-            q[nb] = cfg->material_on ? (float)static_pesto_cp(g.leaf_board) / 100.0f : 0.0f;
-            move_off[nb] = off;
-            memcpy(&move_idx[off], g.leaf_idx, sizeof(uint16_t) * g.leaf_n);
+            j.boards[nb] = g.leaf_board;
+            j.q[nb] = cfg->material_on ? (float)static_pesto_cp(g.leaf_board) / 100.0f : 0.0f;
+            j.move_off[nb] = off;
+            memcpy(&j.move_idx[off], g.leaf_idx, sizeof(uint16_t) * g.leaf_n);
             off += (uint32_t)g.leaf_n;
-            slot_game[nb] = i;
-            game_slot[i] = nb;
+            j.game_slot[i - g0] = nb;
             nb++;
         }
-        move_off[nb] = off;
-        double t1 = now_s();
-        tree_s += t1 - t0;
-        if (nb > 0) {
-            const int rc = cb_eval_leaves(h, boards.data(), q.data(), nb, cfg->material_on, move_idx.data(), move_off.data(),
-                                          priors.data(), v_logit.data(), v_final.data(), kk.data());
-            if (rc != CB_OK) {
-                if (sample_file) fclose(sample_file);
-                return rc;
-            }
-        }
-        double t2 = now_s();
-        eval_s += t2 - t1;
-        pool.run([&](int b, int e) {
+        j.move_off[nb] = off;
+        j.nb = nb;
+    };
+    // phase C for one half-pool: expand + backup, then play moves where the budget is reached
+    auto expand_half = [&](int hf) {
+        EvalJob& j = jobs[hf];
+        const int g0 = hb[hf], g1 = hb[hf + 1];
+        pool.run(g0, g1, [&](int b, int e) {
             for (int i = b; i < e; ++i) {
                 Game& g = games[i];
                 if (g.wants_eval) {
-                    const int s = game_slot[i];
-                    expand_and_backup(g, &priors[move_off[s]], v_final[s]);
+                    const int s = j.game_slot[i - g0];
+                    expand_and_backup(g, &j.priors[j.move_off[s]], j.v_final[s]);
                 }
                 if (g.sims_done >= cfg->sims_per_move) play_move(g, i);
             }
         });
-        tree_s += now_s() - t2;
-        sims += G;
-        evals += nb;
-        steps++;
+        sims += g1 - g0;
+        evals += j.nb;
+    };
+    auto should_stop = [&] {
+        if (cfg->max_sims > 0 && sims >= cfg->max_sims) return true;
+        if (cfg->max_games > 0 && games_finished.load() >= cfg->max_games) return true;
+        if (cfg->max_seconds > 0 && now_s() - t_start >= cfg->max_seconds) return true;
+        return false;
+    };
+
+    if (halves == 1) {
+        while (!should_stop() && failed == CB_OK) {
+            const double t0 = now_s();
+            select_and_pack(0);
+            const double t1 = now_s();
+            eval_job(jobs[0]);
+            failed = jobs[0].rc;
+            const double t2 = now_s();
+            if (failed == CB_OK) expand_half(0);
+            tree_s += (t1 - t0) + (now_s() - t2);
+            eval_s += t2 - t1;
+            steps++;
+        }
+    } else {
+        // software pipeline: the tree work of one half runs while the other half is on the GPU
+        std::atomic<bool> eval_stop(false);
+        std::thread eval_thread([&] {
+            int next = 0;
+            for (;;) {
+                EvalJob& j = jobs[next];
+                int spins = 0;
+                while (j.state.load(std::memory_order_acquire) != 1) {
+                    if (eval_stop.load()) return;
+                    Pool::relax();
+                    if (++spins > 4096) { std::this_thread::yield(); spins = 0; }
+                }
+                const double t0 = now_s();
+                eval_job(j);
+                eval_s += now_s() - t0;
+                j.state.store(2, std::memory_order_release);
+                next ^= 1;
+            }
+        });
+        auto submit = [&](int hf) {
+            const double t0 = now_s();
+            select_and_pack(hf);
+            tree_s += now_s() - t0;
+            jobs[hf].state.store(1, std::memory_order_release);
+        };
+        auto complete = [&](int hf) {
+            while (jobs[hf].state.load(std::memory_order_acquire) != 2) Pool::relax();
+            jobs[hf].state.store(0, std::memory_order_relaxed);
+            if (jobs[hf].rc != CB_OK) { failed = jobs[hf].rc; return; }
+            const double t0 = now_s();
+            expand_half(hf);
+            tree_s += now_s() - t0;
+        };
+        submit(0);
+        int cur = 0;
+        long long half_steps = 0;
+        for (;;) {
+            submit(cur ^ 1);
+            complete(cur);
+            half_steps++;
+            cur ^= 1;
+            if (failed != CB_OK || should_stop()) break;
+        }
+        complete(cur);  // drain the last submitted half
+        half_steps++;
+        eval_stop.store(true);
+        eval_thread.join();
+        steps = half_steps / 2;  // a step = one simulation for every game of the pool
+    }
+    if (failed != CB_OK) {
+        if (sample_file) fclose(sample_file);
+        return failed;
     }
     if (sample_file) fclose(sample_file);
     out->sims = sims;
