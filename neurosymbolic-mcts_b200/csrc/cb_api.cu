@@ -72,6 +72,13 @@ struct cb_handle {
     // device buffers (capacity cap boards, even)
     int cap = 0;
     size_t csr_cap = 0;
+    // inputs live in ONE device block and ONE pinned block (boards | q | move_off | move_idx) and the
+    // outputs in another (v_logit | v_final | k | priors) so a full batch moves with one copy each way
+    uint8_t* d_in = nullptr;
+    uint8_t* d_out = nullptr;
+    uint8_t* h_in = nullptr;
+    uint8_t* h_out = nullptr;
+    size_t in_idx_off = 0, out_pri_off = 0;   // byte offsets of move_idx / priors inside the blocks
     cb_board* d_boards = nullptr;
     float* d_q = nullptr;
     void* d_x0 = nullptr;       // encoder output
@@ -192,20 +199,17 @@ int make_weight_map(cb_handle* h, ConvLayer& L) {
 
 void free_buffers(cb_handle* h) {
     drop_graphs(h);
-    free_dev(h->d_boards); free_dev(h->d_q); free_dev(h->d_x0);
+    free_dev(h->d_in); free_dev(h->d_out); free_dev(h->d_x0);
+    h->d_in = nullptr; h->d_out = nullptr;
     for (int i = 0; i < 3; ++i) { free_dev(h->d_act[i]); h->d_act[i] = nullptr; }
     free_dev(h->d_tmp32); free_dev(h->d_vpre); free_dev(h->d_probs);
-    free_dev(h->d_move_idx); free_dev(h->d_move_off); free_dev(h->d_priors);
-    free_dev(h->d_vlogit); free_dev(h->d_vfinal); free_dev(h->d_k); free_dev(h->d_scratch);
+    free_dev(h->d_scratch);
     h->d_boards = nullptr; h->d_q = nullptr; h->d_x0 = nullptr; h->d_tmp32 = nullptr; h->d_vpre = nullptr;
     h->d_probs = nullptr; h->d_move_idx = nullptr; h->d_move_off = nullptr; h->d_priors = nullptr;
     h->d_vlogit = nullptr; h->d_vfinal = nullptr; h->d_k = nullptr; h->d_scratch = nullptr;
-    if (h->h_boards) cudaFreeHost(h->h_boards);
-    if (h->h_q) cudaFreeHost(h->h_q);
-    if (h->h_move_idx) cudaFreeHost(h->h_move_idx);
-    if (h->h_move_off) cudaFreeHost(h->h_move_off);
-    if (h->h_priors) cudaFreeHost(h->h_priors);
-    if (h->h_small) cudaFreeHost(h->h_small);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    h->h_in = nullptr; h->h_out = nullptr;
     h->h_boards = nullptr; h->h_q = nullptr; h->h_move_idx = nullptr; h->h_move_off = nullptr;
     h->h_priors = nullptr; h->h_small = nullptr;
     h->cap = 0; h->csr_cap = 0; h->probs_cap = 0; h->scratch_floats = 0; h->staged_B = 0;
@@ -222,25 +226,29 @@ int ensure_capacity(cb_handle* h, int B) {
     free_buffers(h);
     const size_t eb = elem_bytes(h);
     const size_t csr = (size_t)cap * CB_MAX_MOVES;
-    CB_CUDA(h, cudaMalloc(&h->d_boards, (size_t)cap * sizeof(cb_board)));
-    CB_CUDA(h, cudaMemset(h->d_boards, 0, (size_t)cap * sizeof(cb_board)));
-    CB_CUDA(h, cudaMalloc(&h->d_q, (size_t)cap * 4));
+    const size_t off_q = (size_t)cap * sizeof(cb_board), off_mo = off_q + (size_t)cap * 4;
+    const size_t off_mi = (off_mo + ((size_t)cap + 1) * 4 + 15) & ~(size_t)15, in_bytes = off_mi + csr * 2;
+    const size_t off_pri = (size_t)cap * 12, out_bytes = off_pri + csr * 4;
+    CB_CUDA(h, cudaMalloc(&h->d_in, in_bytes));
+    CB_CUDA(h, cudaMemset(h->d_in, 0, in_bytes));
+    CB_CUDA(h, cudaMalloc(&h->d_out, out_bytes));
+    CB_CUDA(h, cudaHostAlloc(&h->h_in, in_bytes, cudaHostAllocDefault));
+    CB_CUDA(h, cudaHostAlloc(&h->h_out, out_bytes, cudaHostAllocDefault));
+    memset(h->h_in, 0, in_bytes);
+    h->in_idx_off = off_mi;
+    h->out_pri_off = off_pri;
+    h->d_boards = (cb_board*)h->d_in;            h->h_boards = (cb_board*)h->h_in;
+    h->d_q = (float*)(h->d_in + off_q);          h->h_q = (float*)(h->h_in + off_q);
+    h->d_move_off = (uint32_t*)(h->d_in + off_mo); h->h_move_off = (uint32_t*)(h->h_in + off_mo);
+    h->d_move_idx = (uint16_t*)(h->d_in + off_mi); h->h_move_idx = (uint16_t*)(h->h_in + off_mi);
+    h->d_vlogit = (float*)h->d_out;              h->h_small = (float*)h->h_out;
+    h->d_vfinal = h->d_vlogit + cap;
+    h->d_k = h->d_vlogit + 2 * (size_t)cap;
+    h->d_priors = (float*)(h->d_out + off_pri);  h->h_priors = (float*)(h->h_out + off_pri);
     CB_CUDA(h, cudaMalloc(&h->d_x0, (size_t)cap * 64 * (h->dtype == CB_DTYPE_FP32 ? 17 * 4 : 64 * 2)));
     for (int i = 0; i < 3; ++i) CB_CUDA(h, cudaMalloc(&h->d_act[i], (size_t)cap * 64 * h->hid * eb));
     if (h->dtype == CB_DTYPE_FP32) CB_CUDA(h, cudaMalloc(&h->d_tmp32, (size_t)cap * 64 * h->hid * 4));
     CB_CUDA(h, cudaMalloc(&h->d_vpre, (size_t)cap * 64 * 4));
-    CB_CUDA(h, cudaMalloc(&h->d_move_idx, csr * 2));
-    CB_CUDA(h, cudaMalloc(&h->d_move_off, ((size_t)cap + 1) * 4));
-    CB_CUDA(h, cudaMalloc(&h->d_priors, csr * 4));
-    CB_CUDA(h, cudaMalloc(&h->d_vlogit, (size_t)cap * 4));
-    CB_CUDA(h, cudaMalloc(&h->d_vfinal, (size_t)cap * 4));
-    CB_CUDA(h, cudaMalloc(&h->d_k, (size_t)cap * 4));
-    CB_CUDA(h, cudaHostAlloc(&h->h_boards, (size_t)cap * sizeof(cb_board), cudaHostAllocDefault));
-    CB_CUDA(h, cudaHostAlloc(&h->h_q, (size_t)cap * 4, cudaHostAllocDefault));
-    CB_CUDA(h, cudaHostAlloc(&h->h_move_idx, csr * 2, cudaHostAllocDefault));
-    CB_CUDA(h, cudaHostAlloc(&h->h_move_off, ((size_t)cap + 1) * 4, cudaHostAllocDefault));
-    CB_CUDA(h, cudaHostAlloc(&h->h_priors, csr * 4, cudaHostAllocDefault));
-    CB_CUDA(h, cudaHostAlloc(&h->h_small, (size_t)cap * 3 * 4, cudaHostAllocDefault));
     h->cap = cap;
     h->csr_cap = csr;
     if (h->dtype != CB_DTYPE_FP32) {
@@ -672,21 +680,27 @@ int upload_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, c
                   const uint32_t* move_off) {
     int rc = ensure_capacity(h, B);
     if (rc) return rc;
-    memcpy(h->h_boards, boards, (size_t)B * sizeof(cb_board));
-    CB_CUDA(h, cudaMemcpyAsync(h->d_boards, h->h_boards, (size_t)B * sizeof(cb_board), cudaMemcpyHostToDevice, h->stream));
-    if (q) {
-        memcpy(h->h_q, q, (size_t)B * 4);
-        CB_CUDA(h, cudaMemcpyAsync(h->d_q, h->h_q, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
-    }
     h->staged_moves = 0;
-    if (move_idx && move_off) {
-        const size_t n = move_off[B];
-        if (n > h->csr_cap) return fail(h, CB_EINVAL, "legal-move CSR larger than 256 moves per position");
+    const bool csr = move_idx && move_off;
+    const size_t n = csr ? move_off[B] : 0;
+    if (n > h->csr_cap) return fail(h, CB_EINVAL, "legal-move CSR larger than 256 moves per position");
+    memcpy(h->h_boards, boards, (size_t)B * sizeof(cb_board));
+    if (q) memcpy(h->h_q, q, (size_t)B * 4);
+    if (csr) {
         memcpy(h->h_move_off, move_off, ((size_t)B + 1) * 4);
         memcpy(h->h_move_idx, move_idx, n * 2);
-        CB_CUDA(h, cudaMemcpyAsync(h->d_move_off, h->h_move_off, ((size_t)B + 1) * 4, cudaMemcpyHostToDevice, h->stream));
-        if (n) CB_CUDA(h, cudaMemcpyAsync(h->d_move_idx, h->h_move_idx, n * 2, cudaMemcpyHostToDevice, h->stream));
         h->staged_moves = n;
+    }
+    if (q && csr && (size_t)B * 4 >= (size_t)h->cap * 3) {
+        // nearly full batch: one transfer for the whole input block (gaps included)
+        CB_CUDA(h, cudaMemcpyAsync(h->d_in, h->h_in, h->in_idx_off + n * 2, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        CB_CUDA(h, cudaMemcpyAsync(h->d_boards, h->h_boards, (size_t)B * sizeof(cb_board), cudaMemcpyHostToDevice, h->stream));
+        if (q) CB_CUDA(h, cudaMemcpyAsync(h->d_q, h->h_q, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+        if (csr) {
+            CB_CUDA(h, cudaMemcpyAsync(h->d_move_off, h->h_move_off, ((size_t)B + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+            if (n) CB_CUDA(h, cudaMemcpyAsync(h->d_move_idx, h->h_move_idx, n * 2, cudaMemcpyHostToDevice, h->stream));
+        }
     }
     return CB_OK;
 }
@@ -948,16 +962,24 @@ int cb_pst_eval_cp(cb_handle* h, const cb_board* boards, int B, int32_t* cp) {
     return CB_OK;
 }
 
-static int read_small(cb_handle* h, int B, float* v_logit, float* v_final, float* k) {
+// Device -> host read-back of the per-position scalars and (n_priors > 0) the gathered priors.
+static int read_results(cb_handle* h, int B, size_t n_priors, float* priors, float* v_logit, float* v_final, float* k) {
     float* s = h->h_small;
-    CB_CUDA(h, cudaMemcpyAsync(s, h->d_vlogit, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
-    CB_CUDA(h, cudaMemcpyAsync(s + h->cap, h->d_vfinal, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
-    CB_CUDA(h, cudaMemcpyAsync(s + 2 * (size_t)h->cap, h->d_k, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (n_priors && (size_t)B * 4 >= (size_t)h->cap * 3) {
+        CB_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_pri_off + n_priors * 4, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        CB_CUDA(h, cudaMemcpyAsync(s, h->d_vlogit, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+        CB_CUDA(h, cudaMemcpyAsync(s + h->cap, h->d_vfinal, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+        CB_CUDA(h, cudaMemcpyAsync(s + 2 * (size_t)h->cap, h->d_k, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (n_priors)
+            CB_CUDA(h, cudaMemcpyAsync(h->h_priors, h->d_priors, n_priors * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
     CB_CUDA(h, cudaEventRecord(h->ev3, h->stream));
     CB_CUDA(h, cudaStreamSynchronize(h->stream));
     if (v_logit) memcpy(v_logit, s, (size_t)B * 4);
     if (v_final) memcpy(v_final, s + h->cap, (size_t)B * 4);
     if (k) memcpy(k, s + 2 * (size_t)h->cap, (size_t)B * 4);
+    if (n_priors && priors) memcpy(priors, h->h_priors, n_priors * 4);
     return CB_OK;
 }
 
@@ -995,7 +1017,7 @@ int cb_predict_batch(cb_handle* h, const cb_board* boards, const float* q, const
     CB_CUDA(h, cudaEventRecord(h->ev2, h->stream));
     if (policy_probs)
         CB_CUDA(h, cudaMemcpyAsync(policy_probs, h->d_probs, (size_t)B * CB_POLICY_SIZE * 4, cudaMemcpyDeviceToHost, h->stream));
-    if ((rc = read_small(h, B, v_logit, nullptr, k))) return rc;
+    if ((rc = read_results(h, B, 0, nullptr, v_logit, nullptr, k))) return rc;
     account(h, B);
     return CB_OK;
 }
@@ -1014,10 +1036,7 @@ int cb_eval_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, 
     CB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     if ((rc = run_forward(h, B, false, move_off != nullptr, material_on, q != nullptr))) return rc;
     CB_CUDA(h, cudaEventRecord(h->ev2, h->stream));
-    const size_t n = h->staged_moves;
-    if (n) CB_CUDA(h, cudaMemcpyAsync(h->h_priors, h->d_priors, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    if ((rc = read_small(h, B, v_logit, v_final, k))) return rc;
-    if (n) memcpy(priors, h->h_priors, n * 4);
+    if ((rc = read_results(h, B, h->staged_moves, priors, v_logit, v_final, k))) return rc;
     account(h, B);
     return CB_OK;
 }
@@ -1119,12 +1138,7 @@ int cb_read_resident(cb_handle* h, float* priors, float* v_logit, float* v_final
     if (!h) return CB_EINVAL;
     if (!h->staged_B) return fail(h, CB_ESTATE, "nothing staged");
     CB_CUDA(h, cudaSetDevice(h->device));
-    const size_t n = h->staged_moves;
-    if (priors && n) CB_CUDA(h, cudaMemcpyAsync(h->h_priors, h->d_priors, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    int rc = read_small(h, h->staged_B, v_logit, v_final, k);
-    if (rc) return rc;
-    if (priors && n) memcpy(priors, h->h_priors, n * 4);
-    return CB_OK;
+    return read_results(h, h->staged_B, priors ? h->staged_moves : 0, priors, v_logit, v_final, k);
 }
 
 int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches) {
