@@ -149,6 +149,9 @@ int cb_debug_backbone(cb_handle* h, int B, float* out);
  * after n convolution launches so individual layers can be compared across arithmetic modes. */
 int cb_debug_act(cb_handle* h, int B, int buf, float* out);
 int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches);
+/* Debug timeline of CTA 0 of the fused 128-channel tower for the staged batch: out[item*8 + slot] SM clock
+ * stamps (slots documented at trace_stamp in tower_t_umma.cuh); returns the number of items written. */
+int cb_debug_tower_trace(cb_handle* h, long long* out, int max_items);
 
 /* Kernels launched per forward of the given kind (for gpu_launches accounting). */
 int cb_launches_per_forward(const cb_handle* h);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "cb_read_resident": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "cb_debug_backbone": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
     "cb_debug_act": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
+    "cb_debug_tower_trace": (ctypes.c_int, [_VP, _VP, ctypes.c_int]),
     "cb_debug_set_layer_limit": (ctypes.c_int, [_VP, ctypes.c_int]),
     "cb_chess_startpos": (ctypes.c_int, [_VP]),
     "cb_chess_legal_moves": (ctypes.c_int, [_VP, _VP, _VP]),
@@ -238,6 +239,14 @@ class Evaluator:
         out = np.empty((B, self.hidden, 8, 8), dtype=np.float32)
         self._check(self._L.cb_debug_act(self._h, B, buf, _ptr(out)))
         return out
+
+    def debug_tower_trace(self):
+        items = 2 * (2 * self.num_blocks + 2)
+        out = np.zeros((items, 8), dtype=np.int64)
+        n = self._L.cb_debug_tower_trace(self._h, _ptr(out), items)
+        if n < 0:
+            self._check(n)
+        return out[:n]
 
     def debug_set_layer_limit(self, n):
         self._check(self._L.cb_debug_set_layer_limit(self._h, n))

@@ -107,6 +107,7 @@ struct cb_handle {
     cb::TowerTLayer* d_layers_q = nullptr;
     bool tower_q_ready = false;
     bool use_quad = true;
+    long long* d_trace = nullptr;   // debug timeline of CTA 0 of the transposed tower (cb_debug_tower_trace)
 
     // pinned staging
     cb_board* h_boards = nullptr;
@@ -361,6 +362,7 @@ int launch_tower_q(cb_handle* h, int B) {
     tp.num_layers = (int)h->convs.size();
     tp.num_quads = (B + 3) / 4;
     tp.num_boards = B;
+    tp.trace = h->d_trace;
     const int units = (tp.num_quads + 1) / 2;
     const int grid = units < h->sm_count ? units : h->sm_count;
     if (h->dtype == CB_DTYPE_BF16) {
@@ -1139,6 +1141,26 @@ int cb_read_resident(cb_handle* h, float* priors, float* v_logit, float* v_final
     if (!h->staged_B) return fail(h, CB_ESTATE, "nothing staged");
     CB_CUDA(h, cudaSetDevice(h->device));
     return read_results(h, h->staged_B, priors ? h->staged_moves : 0, priors, v_logit, v_final, k);
+}
+
+int cb_debug_tower_trace(cb_handle* h, long long* out, int max_items) {
+    if (!h || !out || max_items <= 0) return CB_EINVAL;
+    if (!h->staged_B || fused_kind(h) != 2) return fail(h, CB_ESTATE, "needs staged leaves and the transposed tower");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    const int items = 2 * (int)h->convs.size();
+    const int n = items < max_items ? items : max_items;
+    drop_graphs(h);
+    CB_CUDA(h, cudaMalloc(&h->d_trace, (size_t)items * 8 * sizeof(long long)));
+    CB_CUDA(h, cudaMemsetAsync(h->d_trace, 0, (size_t)items * 8 * sizeof(long long), h->stream));
+    int rc = launch_tower_q(h, h->staged_B);
+    cudaError_t e = cudaMemcpyAsync(out, h->d_trace, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_trace);
+    h->d_trace = nullptr;
+    if (rc) return rc;
+    CB_CUDA(h, e);
+    CB_CUDA(h, e2);
+    return n;
 }
 
 int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches) {

@@ -64,6 +64,7 @@ struct TowerTParams {
     int num_layers;
     int num_quads;
     int num_boards;
+    long long* trace;            // debug timeline (CTA 0): [item][8] SM clock stamps, or nullptr
 };
 
 template <bool BF16>
@@ -83,6 +84,28 @@ __device__ __forceinline__ float from16bits(uint16_t u) {
     } else {
         return __half2float(*reinterpret_cast<__half*>(&u));
     }
+}
+
+// Sum each of 32 per-thread values across the 32 lanes of a warp; lane l ends with the total of
+// v[l].  31 shuffles (butterfly transpose-reduce) instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool upper = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float keep = upper ? v[i + h] : v[i];
+            const float send = upper ? v[i] : v[i + h];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+
+// trace slots per work item: 0 producer got act_ready, 1 producer issued last load, 2 MMA start,
+// 3 MMA last issue, 4 epilogue saw tmem_full, 5 epilogue published the tile, 6 store issued, 7 store complete
+__device__ __forceinline__ void trace_stamp(const TowerTParams& p, int item, int slot) {
+    if (p.trace && blockIdx.x == 0) p.trace[item * 8 + slot] = clock64();
 }
 
 template <bool BF16>
@@ -152,6 +175,7 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                         ready_ph[c] ^= 1;
                         ptx::fence_proxy_async_all();
                     }
+                    if (lane == 0) trace_stamp(p, L * 2 + c, 0);
                     for (int dx = -1; dx <= 1; ++dx) {
                         for (int kc = 0; kc < kc_in; ++kc) {
                             ptx::mbar_wait(&a_empty[as], aph ^ 1);
@@ -173,6 +197,7 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                             }
                         }
                     }
+                    if (lane == 0) trace_stamp(p, L * 2 + c, 1);
                 }
             }
         }
@@ -191,6 +216,7 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                     ptx::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + c * 256;
                     uint32_t accum = 0;
+                    if (lane == 0) trace_stamp(p, L * 2 + c, 2);
                     for (int dxi = 0; dxi < 3; ++dxi) {
                         for (int kc = 0; kc < kc_in; ++kc) {
                             ptx::mbar_wait(&a_full[as], aph);
@@ -218,6 +244,7 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                     }
                     if (ptx::elect_one()) ptx::umma_commit(&tmem_full[c]);
                     __syncwarp();
+                    if (lane == 0) trace_stamp(p, L * 2 + c, 3);
                 }
             }
         }
@@ -231,7 +258,7 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
         //   -> wait stage_ready(j) -> TMA store(j) -> wait_group.read (tile free again)
         uint32_t ready_ph = 0;
         bool have_prev = false, prev_last = false;
-        int prev_c = 0;
+        int prev_c = 0, prev_item = 0;
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
             for (int L = 0; L < p.num_layers; ++L) {
                 const TowerTLayer* ly = p.layers + L;
@@ -247,6 +274,7 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                         if (have_prev) {
                             ptx::mbar_arrive(stage_free);
                             ptx::tma_store_wait0();      // item j-1 complete in global memory
+                            trace_stamp(p, prev_item, 7);
                             ptx::fence_proxy_async_all();
                             if (!prev_last) ptx::mbar_arrive(&act_ready[prev_c]);
                         }
@@ -269,11 +297,13 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                                 ptx::tma_store_5d(tm_out, out_tile + kc * Cfg::kKcBytes, kc * 64, 0, 0, 0, quad);
                         }
                         ptx::tma_store_commit();
+                        trace_stamp(p, L * 2 + c, 6);
                         ptx::tma_store_wait_read0();     // the tile may be overwritten
                     }
                     __syncwarp();
                     have_prev = true;
                     prev_c = c;
+                    prev_item = L * 2 + c;
                     prev_last = (L == p.num_layers - 1);
                 }
             }
@@ -319,6 +349,7 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                     ptx::mbar_wait(&tmem_full[c], full_ph[c]);
                     full_ph[c] ^= 1;
                     ptx::tc_fence_after();
+                    if (et == 0) trace_stamp(p, L * 2 + c, 4);
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quadl * 32) << 16) + c * 256 + part * kCols;
 
                     float scale[4] = {1.0f, 1.0f, 1.0f, 1.0f};
@@ -380,6 +411,7 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                         ptx::tmem_ld_wait();
                         const int n0 = part * kCols + c0;     // first pixel column: y = n0 >> 5, b4/x from j
                         const int y = n0 >> 5;
+                        float tv[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int b4 = (j >> 3) & 3, x = j & 7;
@@ -392,12 +424,12 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                             }
                             v = fmaxf(v, 0.0f);
                             *reinterpret_cast<uint16_t*>(ptr) = to16bits<BF16>(v);
-                            if (want_v) {
-                                float t = v * vw;
-#pragma unroll
-                                for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-                                if (lane == 0) s_vpart[quadl * 256 + n0 + j] = t;
-                            }
+                            tv[j] = v * vw;
+                        }
+                        if (want_v) {
+                            // value 1x1 conv: sum over this warp's 32 channels for each of the 32 pixels
+                            const float t = warp_transpose_sum(tv, lane);
+                            s_vpart[quadl * 256 + n0 + lane] = t;
                         }
                     }
                     ptx::tc_fence_before();
@@ -405,6 +437,7 @@ __global__ void __launch_bounds__(TowerTCfg::kThreads, 1) tower_t_umma_kernel(co
                     // publish the tile to the store warp: generic-proxy writes -> async proxy, then arrive
                     ptx::fence_proxy_async_smem();
                     ptx::mbar_arrive(stage_ready);
+                    if (et == 0) trace_stamp(p, L * 2 + c, 5);
                     if (want_v) {
                         ptx::named_bar_sync(1, kEpi);
                         // pixel column n = (y, b4, x) -> plain [board][y*8+x]; fixed summation order over the
