@@ -22,6 +22,7 @@
 #include "policy_umma.cuh"
 #include "tower_umma.cuh"
 #include "tower_t_umma.cuh"
+#include "tower_r_umma.cuh"
 
 namespace {
 
@@ -108,6 +109,15 @@ struct cb_handle {
     bool tower_q_ready = false;
     bool use_quad = true;
     long long* d_trace = nullptr;   // debug timeline of CTA 0 of the transposed tower (cb_debug_tower_trace)
+    // smem-resident fused tower for the 128-channel net (tower_r_umma.cuh)
+    CUtensorMap tm_pc_st[4], tm_pc_ld;   // p_conv output act[y][board][x][C]: stores for 1..4 boards, policy load
+    CUtensorMap* d_maps_r = nullptr;
+    cb::TowerRLayer* d_layers_r = nullptr;
+    uint4* d_res_scratch = nullptr;
+    void* d_pc = nullptr;                // p_conv output of the resident tower
+    float* d_dbg_backbone = nullptr;     // set only inside cb_debug_backbone
+    bool tower_r_ready = false;
+    bool use_resident = true;
 
     // pinned staging
     cb_board* h_boards = nullptr;
@@ -181,6 +191,24 @@ int make_act_map(cb_handle* h, CUtensorMap* tm, void* base, int channels, int bo
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+    return CB_OK;
+}
+
+// 4-D map over the resident tower's p_conv output act[y][board][9 x-slots][C]: slot 0 of every 9-row
+// group is the tower's zero pad row (stored as is so that every TMA box stays in bounds), pixels are
+// slots 1..8.
+int make_plain_map(cb_handle* h, CUtensorMap* tm, void* base, int channels, int boards, int box_x, int box_b, int box_y) {
+    const cuuint64_t C = (cuuint64_t)channels;
+    const cuuint64_t dims[4] = {C, 9, (cuuint64_t)boards, 8};
+    const cuuint64_t strides[3] = {C * 2, C * 18, C * 18 * (cuuint64_t)boards};
+    const cuuint32_t box[4] = {64, (cuuint32_t)box_x, (cuuint32_t)box_b, (cuuint32_t)box_y};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt =
+        h->dtype == CB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = h->encode_tiled(tm, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(plain activation) failed: " + std::to_string((int)r));
     return CB_OK;
 }
 
@@ -265,6 +293,14 @@ int ensure_capacity(cb_handle* h, int B) {
                 if ((rc = make_act_map(h, &h->tm_act_ld_q[i], h->d_act[i], h->hid, cap, 10, 4))) return rc;
                 if ((rc = make_act_map(h, &h->tm_act_st_q[i], h->d_act[i], h->hid, cap, 8, 4))) return rc;
             }
+            // resident tower: p_conv output buffer act[y][board][9 x-slots][C]
+            free_dev(h->d_res_scratch); free_dev(h->d_pc);
+            h->d_res_scratch = nullptr; h->d_pc = nullptr;
+            CB_CUDA(h, cudaMalloc(&h->d_pc, (size_t)cap * 72 * h->hid * 2));
+            for (int nb = 1; nb <= 4; ++nb)
+                if ((rc = make_plain_map(h, &h->tm_pc_st[nb - 1], h->d_pc, h->hid, cap, 9, nb, 8))) return rc;
+            if ((rc = make_plain_map(h, &h->tm_pc_ld, h->d_pc, h->hid, cap, 8, 2, 8))) return rc;
+            CB_CUDA(h, cudaMalloc(&h->d_res_scratch, (size_t)h->sm_count * TowerRCfg::kScratchPerCta * sizeof(uint4)));
         }
         if (h->loaded && (rc = build_tower_tables(h))) return rc;
     }
@@ -344,15 +380,79 @@ int build_tower_tables(cb_handle* h) {
         CB_CUDA(h, cudaMemcpy(h->d_maps_q, mq.data(), mq.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
         CB_CUDA(h, cudaMemcpy(h->d_layers_q, lq.data(), lq.size() * sizeof(TowerTLayer), cudaMemcpyHostToDevice));
         h->tower_q_ready = true;
+
+        // resident tower: map table 0..3 p_conv stores (1..4 boards) | 4.. weights
+        h->tower_r_ready = false;
+        std::vector<CUtensorMap> mr(4 + nl);
+        for (int i = 0; i < 4; ++i) mr[i] = h->tm_pc_st[i];
+        for (int l = 0; l < nl; ++l) mr[4 + l] = h->convs[l].tm_w;
+        std::vector<TowerRLayer> lr(nl);
+        memset(lr.data(), 0, sizeof(TowerRLayer) * nl);
+        for (int l = 0; l < nl; ++l) {
+            lr[l].w_map = 4 + l;
+            lr[l].kc_in = l == 0 ? 1 : 2;
+            lr[l].mode = (l >= 1 && l < nl - 1 && (l & 1) == 0) ? MODE_SE_RES : MODE_RELU;
+            lr[l].bias = h->convs[l].bias;
+        }
+        lr[0].save_res = 1;
+        for (int i = 0; i < h->blocks; ++i) {
+            TowerRLayer& b = lr[2 + 2 * i];
+            b.se_w1 = h->se_w1[i]; b.se_w2 = h->se_w2[i];
+            b.save_res = i < h->blocks - 1;
+            if (i == h->blocks - 1) { b.v_w = h->v_w; b.v_pre = h->d_vpre; }
+        }
+        free_dev(h->d_maps_r); free_dev(h->d_layers_r);
+        h->d_maps_r = nullptr; h->d_layers_r = nullptr;
+        CB_CUDA(h, cudaMalloc(&h->d_maps_r, mr.size() * sizeof(CUtensorMap)));
+        CB_CUDA(h, cudaMalloc(&h->d_layers_r, lr.size() * sizeof(TowerRLayer)));
+        CB_CUDA(h, cudaMemcpy(h->d_maps_r, mr.data(), mr.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        CB_CUDA(h, cudaMemcpy(h->d_layers_r, lr.data(), lr.size() * sizeof(TowerRLayer), cudaMemcpyHostToDevice));
+        h->tower_r_ready = true;
     }
     return CB_OK;
 }
 
-// Which fused tower runs for this handle right now (0 none / per-layer, 1 pair-layout, 2 quad-layout transposed).
+// Which fused tower runs for this handle right now (0 none / per-layer, 1 pair-layout, 2 quad-layout
+// transposed, 3 smem-resident transposed).
 int fused_kind(const cb_handle* h) {
     if (h->dtype == CB_DTYPE_FP32 || !h->use_fused || h->layer_limit != 0) return 0;
+    if (h->hid == 128 && h->use_resident && h->tower_r_ready) return 3;
     if (h->hid == 128 && h->use_quad && h->tower_q_ready) return 2;
     return h->tower_ready ? 1 : 0;
+}
+
+// Units of the resident tower: boards are spread evenly over the SMs (at least 2 and at most 8 per unit).
+int tower_r_units(const cb_handle* h, int B) {
+    const int rounds = (B + 8 * h->sm_count - 1) / (8 * h->sm_count);
+    const int even = h->sm_count * rounds, pairs = (B + 1) / 2;
+    return even < pairs ? even : pairs;
+}
+
+int launch_tower_r(cb_handle* h, int B) {
+    TowerRParams tp;
+    tp.boards = h->d_boards;
+    tp.maps = h->d_maps_r;
+    tp.layers = h->d_layers_r;
+    tp.num_layers = (int)h->convs.size();
+    tp.num_boards = B;
+    tp.num_units = tower_r_units(h, B);
+    tp.res_scratch = h->d_res_scratch;
+    tp.dbg_backbone = h->d_dbg_backbone;
+    tp.trace = h->d_trace;
+    const char* dbg_env = getenv("CB_DBG_R");
+    tp.dbg = dbg_env ? atoi(dbg_env) : 0;
+    const int grid = tp.num_units < h->sm_count ? tp.num_units : h->sm_count;
+    if (h->dtype == CB_DTYPE_BF16) {
+        auto kern = tower_r_umma_kernel<true>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerRCfg::kSmemBytes));
+        kern<<<grid, TowerRCfg::kThreads, TowerRCfg::kSmemBytes, h->stream>>>(tp);
+    } else {
+        auto kern = tower_r_umma_kernel<false>;
+        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerRCfg::kSmemBytes));
+        kern<<<grid, TowerRCfg::kThreads, TowerRCfg::kSmemBytes, h->stream>>>(tp);
+    }
+    CB_CUDA(h, cudaGetLastError());
+    return CB_OK;
 }
 
 int launch_tower_q(cb_handle* h, int B) {
@@ -477,7 +577,9 @@ int launch_policy_umma_t(cb_handle* h, int B, const PolicyOut& po) {
     const int grid = tiles < h->sm_count ? tiles : h->sm_count;
     auto kern = policy_umma_kernel<HID, BF16>;
     CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, h->stream>>>(h->tm_act_st[1], h->tm_pw, h->p_bias, tiles, B, po);
+    const bool plain = fused_kind(h) == 3;
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, h->stream>>>(plain ? h->tm_pc_ld : h->tm_act_st[1], h->tm_pw, h->p_bias, tiles, B,
+                                                             po, plain ? 1 : 0);
     CB_CUDA(h, cudaGetLastError());
     return CB_OK;
 }
@@ -597,7 +699,9 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     const int kind = fused_kind(h);
     const int glog = kind == 2 ? 2 : 1;                       // boards interleaved per activation group
     const int Bpad = (B + (1 << glog) - 1) & ~((1 << glog) - 1);
-    if (h->dtype == CB_DTYPE_FP32) {
+    if (kind == 3) {
+        // the resident tower encodes the planes itself
+    } else if (h->dtype == CB_DTYPE_FP32) {
         encode_nhwc_f32_kernel<<<(B * 64 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, (float*)h->d_x0);
     } else if (h->dtype == CB_DTYPE_BF16) {
         encode_tiled16_kernel<true><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, glog, (uint4*)h->d_x0);
@@ -606,7 +710,9 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     }
     CB_CUDA(h, cudaGetLastError());
     int rc;
-    if (kind == 2)
+    if (kind == 3)
+        rc = launch_tower_r(h, B);
+    else if (kind == 2)
         rc = launch_tower_q(h, B);
     else if (kind == 1)
         rc = launch_tower(h, B);
@@ -635,7 +741,7 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     vp.out_b = h->out_b;
     vp.k = h->k;
     vp.material_on = material_on;
-    vp.pair_layout = h->dtype == CB_DTYPE_FP32 ? 0 : (kind == 2 ? 0 : 1);  // quad tower emits v_pre in plain order
+    vp.pair_layout = h->dtype == CB_DTYPE_FP32 ? 0 : (kind >= 2 ? 0 : 1);  // quad / resident towers emit v_pre in plain order
     vp.B = B;
     vp.v_logit = h->d_vlogit;
     vp.v_final = h->d_vfinal;
@@ -741,6 +847,8 @@ int cb_create(cb_handle** out, int device, int num_blocks, int hidden, int dtype
     h->use_fused = !(nf && nf[0] == '1');
     const char* tp = getenv("CB_TOWER_PAIR");
     h->use_quad = !(tp && tp[0] == '1');
+    const char* tq = getenv("CB_TOWER_QUAD");   // force the global-round-trip towers (debug / comparison)
+    h->use_resident = h->use_quad && !(tq && tq[0] == '1');
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         delete h;
@@ -783,6 +891,7 @@ void cb_destroy(cb_handle* h) {
     free_dev(h->p_w16);
     free_dev(h->d_maps); free_dev(h->d_layers);
     free_dev(h->d_maps_q); free_dev(h->d_layers_q);
+    free_dev(h->d_maps_r); free_dev(h->d_layers_r); free_dev(h->d_res_scratch); free_dev(h->d_pc);
     free_dev(h->d_flush);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -801,6 +910,7 @@ int cb_is_available(const cb_handle* h) { return h && h->loaded ? 1 : 0; }
 int cb_launches_per_forward(const cb_handle* h) {
     if (!h) return 0;
     const int convs = 2 * h->blocks + 2;
+    if (fused_kind(h) == 3) return 3;                          // resident tower (encodes in-kernel), policy, value
     if (h->dtype != CB_DTYPE_FP32 && h->use_fused) return 4;  // encode, fused tower, policy, value
     return 1 + convs + (h->dtype == CB_DTYPE_FP32 ? h->blocks : 0) + 2;
 }
@@ -1123,7 +1233,10 @@ int cb_time_tower(cb_handle* h, int iters, float* ms_each, int* n_launches) {
     int rc = CB_OK;
     for (int i = 0; i < iters && !rc; ++i) {
         CB_CUDA(h, cudaEventRecord(ev[2 * i], h->stream));
-        rc = kind == 2 ? launch_tower_q(h, h->staged_B) : kind == 1 ? launch_tower(h, h->staged_B) : enqueue_tower(h, h->staged_B, nullptr);
+        rc = kind == 3   ? launch_tower_r(h, h->staged_B)
+             : kind == 2 ? launch_tower_q(h, h->staged_B)
+             : kind == 1 ? launch_tower(h, h->staged_B)
+                         : enqueue_tower(h, h->staged_B, nullptr);
         CB_CUDA(h, cudaEventRecord(ev[2 * i + 1], h->stream));
     }
     cudaError_t se = cudaStreamSynchronize(h->stream);
@@ -1145,14 +1258,15 @@ int cb_read_resident(cb_handle* h, float* priors, float* v_logit, float* v_final
 
 int cb_debug_tower_trace(cb_handle* h, long long* out, int max_items) {
     if (!h || !out || max_items <= 0) return CB_EINVAL;
-    if (!h->staged_B || fused_kind(h) != 2) return fail(h, CB_ESTATE, "needs staged leaves and the transposed tower");
+    const int kind = fused_kind(h);
+    if (!h->staged_B || kind < 2) return fail(h, CB_ESTATE, "needs staged leaves and a transposed tower");
     CB_CUDA(h, cudaSetDevice(h->device));
     const int items = 2 * (int)h->convs.size();
     const int n = items < max_items ? items : max_items;
     drop_graphs(h);
     CB_CUDA(h, cudaMalloc(&h->d_trace, (size_t)items * 8 * sizeof(long long)));
     CB_CUDA(h, cudaMemsetAsync(h->d_trace, 0, (size_t)items * 8 * sizeof(long long), h->stream));
-    int rc = launch_tower_q(h, h->staged_B);
+    int rc = kind == 3 ? launch_tower_r(h, h->staged_B) : launch_tower_q(h, h->staged_B);
     cudaError_t e = cudaMemcpyAsync(out, h->d_trace, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
     cudaError_t e2 = cudaStreamSynchronize(h->stream);
     cudaFree(h->d_trace);
@@ -1172,6 +1286,22 @@ int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches) {
 
 int cb_debug_backbone(cb_handle* h, int B, float* out) {
     if (!h) return CB_EINVAL;
+    if (fused_kind(h) == 3) {
+        // the resident tower never writes the backbone to global memory: rerun it on the boards of the
+        // last call with the debug dump enabled
+        if (!out || B <= 0 || B > h->cap) return CB_EINVAL;
+        CB_CUDA(h, cudaSetDevice(h->device));
+        const size_t total = (size_t)B * 64 * h->hid;
+        int rc = ensure_scratch(h, total);
+        if (rc) return rc;
+        h->d_dbg_backbone = h->d_scratch;
+        rc = launch_tower_r(h, B);
+        h->d_dbg_backbone = nullptr;
+        if (rc) return rc;
+        CB_CUDA(h, cudaMemcpyAsync(out, h->d_scratch, total * 4, cudaMemcpyDeviceToHost, h->stream));
+        CB_CUDA(h, cudaStreamSynchronize(h->stream));
+        return CB_OK;
+    }
     return cb_debug_act(h, B, backbone_index(h->blocks), out);
 }
 

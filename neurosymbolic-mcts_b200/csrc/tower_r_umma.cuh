@@ -1,0 +1,526 @@
+// tower_r_umma.cuh — fused persistent conv tower for the 128-channel net with the activations
+// RESIDENT IN SHARED MEMORY between layers (no global round trip, no halo'd slab reloads).
+//
+//     D^T[c_out = 128 lanes][pixels = N columns] += W_tap[c_out][c_in] * X_tap[pixels][c_in]^T
+//
+// A CTA owns a UNIT of up to 8 boards split into two CHAINS of up to 4 boards; chain c accumulates
+// in TMEM columns [256c, 256c + 64 nb).  The boards of a chain live in one shared-memory buffer as
+// 16-bit K-major SWIZZLE_128B rows (one pixel = 128 B = 64 channels, two 64-channel halves):
+//
+//     row(y, b, x) = ((y + halo) * nb + b) * 9 + 1 + x            (b < nb boards, 9 rows per group)
+//
+// Row 0 of every 9-row group is a zero row: it is x = -1 of its own group and x = 8 of the group
+// before it, so a dx-shifted tap is just the same buffer read from row offset (1 + dx) with an
+// 8-row-group stride (SBO) of 9 rows.  The UMMA swizzle is a function of the absolute shared-memory
+// address (tools/exp_desc.cu), so the start address needs no 1024-byte alignment.  A dy shift is a
+// start offset of nb groups.  For an even board count there are no y-halo rows at all: the dy = -1
+// (+1) taps are issued as N = 56 nb MMAs that only touch output rows y >= 1 (y <= 6), i.e. an
+// accumulator column offset of 8 nb (0) — the padding rows are never multiplied.  An odd board
+// count (56 nb is not a legal N) keeps two zero y-halo group rows and uses N = 64 nb for every tap.
+//
+// The epilogue writes layer L's 16-bit output straight back into the chain's buffer (all MMAs of
+// the layer have completed by then), which makes it the B operand of layer L + 1.  Only the weights
+// stream from L2 (TMA ring, 16 KB per tap and 64-channel half); the block input needed by the
+// residual add is parked by each epilogue thread in a thread-private global scratch (coalesced
+// 16-byte stores, read back by the same thread), and the first layer's input planes are encoded
+// from the packed bitboards in-kernel (src/tensor.rs:21-77).  The last layer (p_conv) is stored
+// with TMA as act[y][board][9 x-slots][C] (pad row included) for the policy kernel.
+//
+// Roles (576 threads): warp 0 weight producer, warp 1 MMA issuer, 16 epilogue warps (one team
+// alternating between the chains; a thread owns ONE output channel = TMEM lane).
+#pragma once
+#include "kernels_simt.cuh"
+#include "tower_t_umma.cuh"
+
+namespace cb {
+
+struct TowerRCfg {
+    static constexpr int HID = 128;
+    static constexpr int kGroupRows = 9;
+    static constexpr int kHalfBytes = 37 * 1024;            // >= (32 * 9 + 1) * 128, 1024-aligned
+    static constexpr int kChainBytes = 2 * kHalfBytes;
+    static constexpr int kWBytes = 128 * 128;
+    static constexpr int kWStages = 4;
+    static constexpr int kParts = 4;
+    static constexpr int kEpiThreads = 128 * kParts;        // 16 epilogue warps
+    static constexpr int kThreads = 64 + kEpiThreads;
+    // barriers (256 B) | part [4 boards][128] (+ spare) | hid [4][8] | vpart [4 lane quarters][4 boards][64 pixels]
+    static constexpr int kMiscBytes = 256 + 4 * (kParts * 512 + 32 + 1024);
+    static constexpr int kSmemBytes = 1024 + 2 * kChainBytes + kWStages * kWBytes + kMiscBytes;
+    static constexpr int kScratchPerCta = 2 * 4 * 8 * 128;  // uint4 entries: [chain][board slot][y][channel]
+    static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
+};
+
+struct TowerRLayer {
+    int w_map;                   // tensor-map table index of this layer's weights
+    int kc_in;                   // C_in / 64
+    int mode;                    // MODE_RELU / MODE_SE_RES
+    int save_res;                // 1: the output is a block input, park it for the residual add
+    const float* bias;
+    const float* se_w1;
+    const float* se_w2;
+    const float* v_w;
+    float* v_pre;                // plain [board][64] layout
+};
+
+struct TowerRParams {
+    const cb_board* boards;
+    const CUtensorMap* maps;     // [0..3] p_conv output store maps for nb = 1..4 | [4..] weights
+    const TowerRLayer* layers;
+    int num_layers;
+    int num_boards;
+    int num_units;
+    uint4* res_scratch;          // [grid][TowerRCfg::kScratchPerCta]
+    float* dbg_backbone;         // optional f32 NCHW [board][128][64] dump of the backbone output
+    long long* trace;            // debug timeline (CTA 0), or nullptr
+    int dbg;                     // CB_DBG_R bits: 1 no MMA issue, 2 no p_conv store, 4 no residual scratch, 8 no plane bits
+};
+
+// boards [b0, b0 + n0) form chain 0 and [b0 + n0, b0 + n0 + n1) chain 1 of a unit
+__device__ __forceinline__ void unit_split(const TowerRParams& p, int unit, int& b0, int& n0, int& n1) {
+    const int s = static_cast<int>((static_cast<long long>(unit) * p.num_boards) / p.num_units);
+    const int e = static_cast<int>((static_cast<long long>(unit + 1) * p.num_boards) / p.num_units);
+    b0 = s;
+    n0 = (e - s + 1) >> 1;
+    n1 = (e - s) >> 1;
+}
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// Sum each of 16 per-thread values across the 32 lanes of a warp; lanes l and l + 16 end with the
+// total of v[l & 15].
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+        const bool upper = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float keep = upper ? v[i + h] : v[i];
+            const float send = upper ? v[i] : v[i + h];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// Sum each of 8 per-thread values across the 32 lanes of a warp; every lane ends with the total of v[lane & 7].
+__device__ __forceinline__ float warp_transpose_sum8(float (&v)[8], int lane) {
+#pragma unroll
+    for (int h = 4; h >= 1; h >>= 1) {
+        const bool upper = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float keep = upper ? v[i + h] : v[i];
+            const float send = upper ? v[i] : v[i + h];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    float t = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 8);
+    return t + __shfl_xor_sync(0xffffffffu, t, 16);
+}
+
+// max(lo, 0), max(hi, 0) rounded to the 16-bit activation type, packed (lo in the low half).
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack_relu16(float lo, float hi) {
+    uint32_t d;
+    if constexpr (BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+__device__ __forceinline__ void trace_stamp(long long* trace, int item, int slot) {
+    if (trace && blockIdx.x == 0) trace[item * 8 + slot] = clock64();
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(const TowerRParams p) {
+    using Cfg = TowerRCfg;
+    constexpr int HID = 128;
+    constexpr int kWStages = Cfg::kWStages, kSE = 8;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* chain_base = smem;                                // [2][2 halves][kHalfBytes]
+    uint8_t* w_base = chain_base + 2 * Cfg::kChainBytes;
+    uint8_t* misc = w_base + kWStages * Cfg::kWBytes;
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(misc);      // [4]
+    uint64_t* w_empty = w_full + kWStages;                     // [4]
+    uint64_t* tmem_full = w_empty + kWStages;                  // [2 chains]
+    uint64_t* chain_ready = tmem_full + 2;                     // [2 chains] buffer written + TMEM drained
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(chain_ready + 2);
+    float* s_part = reinterpret_cast<float*>(misc + 256);      // [kParts][4 boards][128 ch]
+    float* s_hid = s_part + Cfg::kParts * 512;                 // [4][8]
+    float* s_vpart = s_hid + 32;                               // [4 lane quarters][256 pixels]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // tap order: the first tap of a layer must cover every accumulator column (dy = 0)
+    constexpr int kTapOrder[9] = {4, 3, 5, 1, 0, 2, 7, 6, 8};
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
+        for (int c = 0; c < 2; ++c) {
+            ptx::mbar_init(&tmem_full[c], 1);
+            ptx::mbar_init(&chain_ready[c], Cfg::kEpiThreads);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<512>(tmem_ptr);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------------ weight producer
+        int ws = 0;
+        uint32_t wph = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+            int b0, nbc[2];
+            unit_split(p, unit, b0, nbc[0], nbc[1]);
+            for (int L = 0; L < p.num_layers; ++L) {
+                const TowerRLayer* ly = p.layers + L;
+                const CUtensorMap* tm_w = p.maps + ly->w_map;
+                const int kc_in = ly->kc_in;
+                for (int c = 0; c < 2; ++c) {
+                    if (nbc[c] == 0) continue;
+#pragma unroll 1
+                    for (int t = 0; t < 9; ++t) {
+                        const int tap = kTapOrder[t];
+                        for (int kc = 0; kc < kc_in; ++kc) {
+                            if (p.dbg & 64) ptx::mbar_wait(&w_empty[ws], wph ^ 1);
+                            else ptx::mbar_wait_parked(&w_empty[ws], wph ^ 1);
+                            if (ptx::elect_one()) {
+                                if (p.dbg & 16) {
+                                    ptx::mbar_arrive(&w_full[ws]);
+                                } else {
+                                    ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::kWBytes);
+                                    ptx::tma_load_2d(w_base + ws * Cfg::kWBytes, tm_w, &w_full[ws], kc * 64, tap * HID);
+                                }
+                            }
+                            __syncwarp();
+                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------- MMA issuer
+        // Warp-uniform control flow and compile-time taps keep descriptors / idesc / TMEM addresses in
+        // uniform registers (UTCHMMA takes them from there: a divergent issuer pays 6 R2UR per MMA, which
+        // caps the issue rate at ~150 cycles per MMA); the MMAs themselves are issued by one elected lane.
+        int ws = 0;
+        uint32_t wph = 0, ready_ph0 = 0, ready_ph1 = 0;
+        const uint32_t w_addr = ptx::smem_u32(w_base);
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+            int b0, nbc0, nbc1;
+            unit_split(p, unit, b0, nbc0, nbc1);
+            for (int L = 0; L < p.num_layers; ++L) {
+                const int kc_in = p.layers[L].kc_in;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int nb = c ? nbc1 : nbc0;
+                    if (nb == 0) continue;
+                    const int halo = nb & 1;
+                    if (c == 0) { ptx::mbar_wait(&chain_ready[0], ready_ph0); ready_ph0 ^= 1; }
+                    else { ptx::mbar_wait(&chain_ready[1], ready_ph1); ready_ph1 ^= 1; }
+                    ptx::tc_fence_after();
+                    const uint32_t buf = ptx::smem_u32(chain_base + c * Cfg::kChainBytes);
+                    const uint32_t d_tmem = tmem_base + c * 256;
+                    uint32_t accum = 1;   // the epilogue presets the accumulator with the bias
+                    if (lane == 0) trace_stamp(p.trace, L * 2 + c, 2);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int tap = kTapOrder[t];
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        int start_row, n, dcol;
+                        if (halo) {
+                            start_row = (1 + dy) * nb * 9 + 1 + dx;
+                            n = 64 * nb;
+                            dcol = 0;
+                        } else {
+                            start_row = (dy > 0 ? nb * 9 : 0) + 1 + dx;
+                            n = dy == 0 ? 64 * nb : 56 * nb;
+                            dcol = dy < 0 ? 8 * nb : 0;
+                        }
+                        const uint32_t idesc = ptx::umma_idesc_f16(BF16 ? 1 : 0, 128, n);
+                        const uint32_t b_addr0 = buf + start_row * 128;
+                        for (int kc = 0; kc < kc_in; ++kc) {
+                            ptx::mbar_wait(&w_full[ws], wph);
+                            if (ptx::elect_one()) {
+                                const uint64_t a_desc = ptx::umma_desc_sw128(w_addr + ws * Cfg::kWBytes);
+                                const uint64_t b_desc = umma_desc_sw128_sbo(b_addr0 + kc * Cfg::kHalfBytes, Cfg::kGroupRows * 128);
+                                if (!(p.dbg & 1)) {
+                                    ptx::umma_f16(d_tmem + dcol, a_desc, b_desc, idesc, accum);
+#pragma unroll
+                                    for (int k = 1; k < 4; ++k)
+                                        ptx::umma_f16(d_tmem + dcol, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
+                                }
+                                ptx::umma_commit(&w_empty[ws]);
+                            }
+                            __syncwarp();
+                            accum = 1;
+                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                        }
+                    }
+                    if (ptx::elect_one()) ptx::umma_commit(&tmem_full[c]);
+                    __syncwarp();
+                    if (lane == 0) trace_stamp(p.trace, L * 2 + c, 3);
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------- epilogue (16 warps)
+        // Thread = (output channel ch = TMEM lane, board slot bs = part): it owns the 8 rows y = 0..7 of
+        // one board, i.e. 8 groups of 8 accumulator columns.  Board sums for the squeeze-excite block are
+        // therefore thread-local and summed in a fixed order (y, then x), independent of how many boards
+        // the chain holds or where a board sits in the batch.
+        constexpr int kEpi = Cfg::kEpiThreads;
+        const int et = threadIdx.x - 64;          // 0..kEpi-1
+        const int ew = et >> 5;                   // 0..15
+        const int quadl = warp & 3;               // TMEM lane quarter this warp may touch
+        const int bs = ew >> 2;                   // board slot inside the chain
+        const int ch = quadl * 32 + lane;         // my output channel == TMEM lane
+        const uint32_t kc_off = static_cast<uint32_t>(ch >> 6) * Cfg::kHalfBytes;
+        const uint32_t cq = static_cast<uint32_t>((ch & 63) >> 3);
+        const uint32_t cb2 = static_cast<uint32_t>(ch & 7) * 2;
+        uint4* my_res = p.res_scratch + static_cast<size_t>(blockIdx.x) * Cfg::kScratchPerCta + bs * 8 * HID + ch;
+        uint32_t full_ph = 0;                     // bit c: phase of tmem_full[c]
+        bool stores_pending = false;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+            int b0, nbc0, nbc1;
+            unit_split(p, unit, b0, nbc0, nbc1);
+            // ---- input planes of both chains, straight from the packed bitboards
+            if (stores_pending) {
+                if (et == 0) ptx::tma_store_wait_read0();      // p_conv stores of the previous unit have read the buffers
+                ptx::named_bar_sync(1, kEpi);
+            }
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                const int nb = c ? nbc1 : nbc0;
+                if (nb == 0) continue;
+                const int halo = nb & 1;
+                const int groups = (8 + 2 * halo) * nb;
+                const int cb0 = b0 + (c ? nbc0 : 0);
+                uint8_t* buf = chain_base + c * Cfg::kChainBytes;
+                for (int r = et; r <= groups * 9; r += kEpi) {
+                    const int g = r / 9, xr = r - g * 9;
+                    const int yy = g / nb - halo, b = g - (g / nb) * nb;
+                    const bool data = xr >= 1 && g < groups && yy >= 0 && yy < 8;
+                    uint32_t msk = 0;
+                    if (data && !(p.dbg & 8)) msk = pixel_plane_mask(p.boards + cb0 + b, yy, xr - 1);
+                    uint4* row0 = reinterpret_cast<uint4*>(buf + r * 128);
+                    uint4* row1 = reinterpret_cast<uint4*>(buf + Cfg::kHalfBytes + r * 128);
+                    const uint32_t one = BF16 ? 0x3F80u : 0x3C00u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (i < 3) {
+                            const uint32_t m8 = msk >> (8 * i);
+                            v.x = ((m8 >> 0) & 1u ? one : 0u) | ((m8 >> 1) & 1u ? (one << 16) : 0u);
+                            v.y = ((m8 >> 2) & 1u ? one : 0u) | ((m8 >> 3) & 1u ? (one << 16) : 0u);
+                            v.z = ((m8 >> 4) & 1u ? one : 0u) | ((m8 >> 5) & 1u ? (one << 16) : 0u);
+                            v.w = ((m8 >> 6) & 1u ? one : 0u) | ((m8 >> 7) & 1u ? (one << 16) : 0u);
+                        }
+                        row0[i ^ (r & 7)] = v;
+                    }
+                    if (!data) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) row1[i] = make_uint4(0, 0, 0, 0);
+                    }
+                }
+                // accumulator preset: the folded-BN bias of the first layer (every MMA accumulates)
+                if (bs < nb) {
+                    const uint32_t bias0 = __float_as_uint(__ldg(p.layers[0].bias + ch));
+                    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quadl * 32) << 16) + c * 256 + bs * 8;
+#pragma unroll
+                    for (int y = 0; y < 8; ++y) ptx::tmem_st_32x8_bcast(tcol + y * nb * 8, bias0);
+                    ptx::tmem_st_wait();
+                }
+                ptx::tc_fence_before();
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(&chain_ready[c]);
+            }
+            stores_pending = false;
+
+            for (int L = 0; L < p.num_layers; ++L) {
+                const TowerRLayer* ly = p.layers + L;
+                const int mode = ly->mode;
+                const bool last_layer = L == p.num_layers - 1;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    const int nb = c ? nbc1 : nbc0;
+                    if (nb == 0) continue;
+                    const int halo = nb & 1;
+                    const bool active = bs < nb;      // this thread's board slot exists in the chain
+                    const int cb0 = b0 + (c ? nbc0 : 0);
+                    uint8_t* buf = chain_base + c * Cfg::kChainBytes;
+                    constexpr int kFc1 = 32 / (kEpi / 32);   // squeeze-FC outputs per warp
+                    float w1r[kFc1][4], w2r[kSE];
+                    uint4 rr[8];
+                    if (mode == MODE_SE_RES) {
+#pragma unroll
+                        for (int i = 0; i < kFc1; ++i)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                w1r[i][k] = __ldg(&ly->se_w1[((ew * kFc1 + i) & 7) * HID + lane + 32 * k]);
+#pragma unroll
+                        for (int j = 0; j < kSE; ++j) w2r[j] = __ldg(&ly->se_w2[ch * kSE + j]);
+                        // block input of my (channel, board): parked by this same thread earlier
+                        if (active && !(p.dbg & 4)) {
+#pragma unroll
+                            for (int y = 0; y < 8; ++y) rr[y] = __ldcg(my_res + (c * 32 + y) * HID);
+                        }
+                    }
+                    const float bias_next = last_layer ? 0.0f : __ldg(p.layers[L + 1].bias + ch);
+                    ptx::mbar_wait_parked(&tmem_full[c], (full_ph >> c) & 1u);
+                    full_ph ^= 1u << c;
+                    ptx::tc_fence_after();
+                    if (et == 0) trace_stamp(p.trace, L * 2 + c, 4);
+                    // my board's 8 column groups: column (y * nb + bs) * 8
+                    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quadl * 32) << 16) + c * 256 + bs * 8;
+
+                    float scale = 1.0f;
+                    if (mode == MODE_SE_RES) {
+                        // pass 1: my channel's sum over my board (the bias is already in the accumulator)
+                        float sb = 0.0f;
+                        if (active) {
+#pragma unroll
+                            for (int y = 0; y < 8; y += 2) {
+                                uint32_t r0[8], r1[8];
+                                ptx::tmem_ld_32x8(tcol + y * nb * 8, r0);
+                                ptx::tmem_ld_32x8(tcol + (y + 1) * nb * 8, r1);
+                                ptx::tmem_ld_wait();
+                                float g0 = 0.0f, g1 = 0.0f;
+#pragma unroll
+                                for (int x = 0; x < 8; ++x) { g0 += __uint_as_float(r0[x]); g1 += __uint_as_float(r1[x]); }
+                                sb += g0;
+                                sb += g1;
+                            }
+                        }
+                        s_part[bs * HID + ch] = sb;
+                        ptx::named_bar_sync(1, kEpi);
+#pragma unroll
+                        for (int i = 0; i < kFc1; ++i) {
+                            const int o = ew * kFc1 + i, b = o >> 3, j = o & 7;
+                            float s = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) s = fmaf(w1r[i][k], s_part[b * HID + lane + 32 * k], s);
+#pragma unroll
+                            for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+                            if (lane == 0) s_hid[b * kSE + j] = fmaxf(s * (1.0f / 64.0f), 0.0f);
+                        }
+                        ptx::named_bar_sync(1, kEpi);
+                        float s = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < kSE; ++j) s = fmaf(w2r[j], s_hid[bs * kSE + j], s);
+                        scale = 1.0f / (1.0f + __expf(-s));
+                    }
+                    // main pass: (SE scale + residual), ReLU, 16-bit, transpose-store into the chain buffer
+                    const bool want_v = (mode == MODE_SE_RES) && ly->v_pre != nullptr;
+                    const float vw = want_v ? __ldg(ly->v_w + ch) : 0.0f;
+                    const bool save_res = ly->save_res != 0 && !(p.dbg & 4);
+                    const bool dump = want_v && p.dbg_backbone != nullptr;
+                    if (active && !(p.dbg & 32)) {
+                        const uint32_t buf_ch = ptx::smem_u32(buf) + kc_off + cb2;
+#pragma unroll
+                        for (int y = 0; y < 8; ++y) {
+                            uint32_t r[8];
+                            ptx::tmem_ld_32x8(tcol + y * nb * 8, r);
+                            ptx::tmem_ld_wait();
+                            float v[8];
+#pragma unroll
+                            for (int x = 0; x < 8; ++x) v[x] = __uint_as_float(r[x]);
+                            if (mode == MODE_SE_RES) {
+                                const uint32_t w[4] = {rr[y].x, rr[y].y, rr[y].z, rr[y].w};
+#pragma unroll
+                                for (int x = 0; x < 8; ++x) {
+                                    const uint32_t h = (x & 1) ? (w[x >> 1] >> 16) : (w[x >> 1] & 0xFFFFu);
+                                    v[x] = fmaf(v[x], scale, from16bits<BF16>(static_cast<uint16_t>(h)));
+                                }
+                            }
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) pk[q] = pack_relu16<BF16>(v[2 * q], v[2 * q + 1]);
+                            // rows of group (y, bs): ((y + halo) * nb + bs) * 9 + 1 + x, swizzled by absolute address
+                            const uint32_t row0 = static_cast<uint32_t>(((y + halo) * nb + bs) * 9 + 1);
+#pragma unroll
+                            for (int x = 0; x < 8; ++x) {
+                                const uint32_t row = row0 + x;
+                                const uint32_t addr = buf_ch + row * 128 + ((cq ^ (row & 7)) << 4);
+                                const uint16_t h16 = static_cast<uint16_t>((x & 1) ? (pk[x >> 1] >> 16) : (pk[x >> 1] & 0xFFFFu));
+                                asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(h16) : "memory");
+                            }
+                            if (save_res) __stcg(my_res + (c * 32 + y) * HID, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                            if (want_v) {
+                                // value 1x1 conv: sum over this warp's 32 channels for each of the 8 pixels
+                                float tv[8];
+#pragma unroll
+                                for (int x = 0; x < 8; ++x) tv[x] = fmaxf(v[x], 0.0f) * vw;
+                                const float t = warp_transpose_sum8(tv, lane);
+                                if (lane < 8) s_vpart[quadl * 256 + bs * 64 + y * 8 + lane] = t;
+                            }
+                            if (dump) {
+#pragma unroll
+                                for (int x = 0; x < 8; ++x) {
+                                    const uint16_t h16 = static_cast<uint16_t>((x & 1) ? (pk[x >> 1] >> 16) : (pk[x >> 1] & 0xFFFFu));
+                                    p.dbg_backbone[(static_cast<size_t>(cb0 + bs) * HID + ch) * 64 + y * 8 + x] = from16bits<BF16>(h16);
+                                }
+                            }
+                            // accumulator preset for the next layer of this chain
+                            if (!last_layer) ptx::tmem_st_32x8_bcast(tcol + y * nb * 8, __float_as_uint(bias_next));
+                        }
+                        if (!last_layer) ptx::tmem_st_wait();
+                    }
+                    ptx::tc_fence_before();
+                    ptx::fence_proxy_async_smem();
+                    if (!last_layer) {
+                        ptx::mbar_arrive(&chain_ready[c]);
+                        if (et == 0) trace_stamp(p.trace, L * 2 + c, 5);
+                    } else {
+                        // p_conv output: the 8 x nb groups of 9 rows (pad row included, y-halo groups skipped)
+                        // -> act[y][board][9 x-slots][C]
+                        ptx::named_bar_sync(1, kEpi);
+                        if (et == 0 && !(p.dbg & 2)) {
+                            const CUtensorMap* tm_out = p.maps + (nb - 1);
+#pragma unroll
+                            for (int kc = 0; kc < 2; ++kc)
+                                ptx::tma_store_4d(tm_out, buf + kc * Cfg::kHalfBytes + halo * nb * 9 * 128, kc * 64, 0, cb0, 0);
+                            ptx::tma_store_commit();
+                            trace_stamp(p.trace, L * 2 + c, 5);
+                        }
+                        stores_pending = true;
+                    }
+                    if (want_v) {
+                        ptx::named_bar_sync(1, kEpi);
+                        // fixed summation order over the four lane quarters keeps the result independent of batch composition
+                        if (et < 64 * nb) {
+                            const int n = et;     // board slot n >> 6, pixel n & 63
+                            const float v = (s_vpart[n] + s_vpart[256 + n]) + (s_vpart[512 + n] + s_vpart[768 + n]);
+                            ly->v_pre[(cb0 + (n >> 6)) * 64 + (n & 63)] = v;
+                        }
+                    }
+                    // s_part / s_hid / s_vpart of this item are dead for every thread before the next item writes them
+                    if (mode == MODE_SE_RES) ptx::named_bar_sync(1, kEpi);
+                }
+            }
+        }
+        if (stores_pending && et == 0) ptx::tma_store_wait0();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace cb

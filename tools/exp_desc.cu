@@ -1,0 +1,245 @@
+// exp_desc.cu — micro-experiments behind the smem-resident tower design (tools, not product):
+//  1. UMMA K-major SWIZZLE_128B B-operand descriptors whose start is NOT 1024-byte aligned
+//     (row-granular dx shifts) with an 8-row-group stride of 9 rows (SBO = 1152): is the swizzle
+//     a function of the absolute shared-memory address?  (base_offset = 0 vs (addr >> 7) & 7)
+//  2. N = 224 MMAs into a column offset of the accumulator (dy = +-1 taps without y halo rows).
+//  3. Issue-rate of back-to-back MMAs from resident operands (cycles per MMA), N = 256 / 224,
+//     with and without the A collector hint.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I neurosymbolic-mcts_b200/csrc tools/exp_desc.cu -o gpurun_out/exp_desc -lcuda
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_bf16.h>
+#include "ptx.cuh"
+
+using namespace cb;
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr, uint32_t sbo_bytes, uint32_t base_off) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(base_off & 7) << 49;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__device__ __forceinline__ void umma_f16_cu(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_cf(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+constexpr int kRows = 560;   // B buffer rows (128 B each)
+
+struct Params {
+    const __nv_bfloat16* A;  // [128][64]
+    const __nv_bfloat16* Bm; // [kRows][64]
+    float* D;                // [128][256]
+    int r0;                  // start row of the B operand
+    int sbo_rows;            // rows between 8-row groups
+    int base_mode;           // 0: base_offset 0, 1: (addr >> 7) & 7
+    int n;                   // MMA N
+    int dcol;                // accumulator column offset
+    long long* cyc;          // timing out
+    int time_mode;           // 0: none, 1: plain loop, 2: collector fill/use pairs
+    int time_iters;
+};
+
+__global__ void __launch_bounds__(128, 1) exp_kernel(Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* a_tile = smem;                       // 128 rows x 128 B
+    uint8_t* b_tile = smem + 16384;               // kRows x 128 B
+    uint64_t* bar = reinterpret_cast<uint64_t*>(b_tile + kRows * 128);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // software swizzle by ABSOLUTE shared address: 16-byte chunk index ^= (address >> 7) & 7
+    for (int i = tid; i < 128 * 64; i += 128) {
+        const int row = i >> 6, ch = i & 63;
+        const uint32_t base = ptx::smem_u32(a_tile) + row * 128;
+        const uint32_t off = (((ch >> 3) ^ ((base >> 7) & 7)) << 4) + (ch & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(a_tile + row * 128 + off) = p.A[i];
+    }
+    for (int i = tid; i < kRows * 64; i += 128) {
+        const int row = i >> 6, ch = i & 63;
+        const uint32_t base = ptx::smem_u32(b_tile) + row * 128;
+        const uint32_t off = (((ch >> 3) ^ ((base >> 7) & 7)) << 4) + (ch & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(b_tile + row * 128 + off) = p.Bm[i];
+    }
+    if (tid == 0) { ptx::mbar_init(bar, 1); ptx::mbar_init(bar + 1, 1); ptx::fence_barrier_init(); }
+    if (warp == 0) ptx::tmem_alloc<512>(tmem_ptr);
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    // zero the accumulator first with a full N=256 MMA against zero-scaled... simpler: accumulate=0 full-width
+    // MMA of the aligned operand, then overwrite the tested columns with accumulate=0 as well.
+    const uint32_t idesc_full = ptx::umma_idesc_f16(1, 128, 256);
+    const uint32_t idesc = ptx::umma_idesc_f16(1, 128, p.n);
+    uint32_t phase = 0;
+    if (warp == 0) {
+        if (ptx::elect_one()) {
+            const uint32_t a_addr = ptx::smem_u32(a_tile);
+            const uint32_t b_addr = ptx::smem_u32(b_tile) + p.r0 * 128;
+            const uint32_t bo = p.base_mode ? ((b_addr >> 7) & 7) : 0;
+            // full-width clear: D = A * B(aligned rows 0..255) then the test MMA overwrites [dcol, dcol+n)
+            for (int k = 0; k < 4; ++k)
+                ptx::umma_f16(tmem, desc_sw128(a_addr, 1024, 0) + 2 * k, desc_sw128(ptx::smem_u32(b_tile), 1024, 0) + 2 * k,
+                              idesc_full, k ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+                ptx::umma_f16(tmem + p.dcol, desc_sw128(a_addr, 1024, 0) + 2 * k,
+                              desc_sw128(b_addr, p.sbo_rows * 128, bo) + 2 * k, idesc, k ? 1u : 0u);
+            ptx::umma_commit(bar);
+        }
+        __syncwarp();
+    }
+    ptx::mbar_wait(bar, phase);
+    phase ^= 1;
+    ptx::tc_fence_after();
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+        ptx::tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) p.D[(warp * 32 + (tid & 31)) * 256 + c0 + j] = __uint_as_float(r[j]);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (p.time_mode && warp == 0) {
+        ptx::tc_fence_after();
+        long long t0 = 0, t1 = 0;
+        if (ptx::elect_one()) {
+            const uint32_t a_addr = ptx::smem_u32(a_tile);
+            const uint32_t b_addr = ptx::smem_u32(b_tile);
+            const uint64_t ad = desc_sw128(a_addr, 1024, 0), bd = desc_sw128(b_addr + p.r0 * 128, p.sbo_rows * 128, 0);
+            const uint64_t bd2 = desc_sw128(b_addr + 2048 + p.r0 * 128, p.sbo_rows * 128, 0);
+            t0 = clock64();
+            for (int it = 0; it < p.time_iters; ++it) {
+                if (p.time_mode == 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + 256, ad + 2 * k, bd2 + 2 * k, idesc, 1u);
+                } else if (p.time_mode == 3) {
+                    // one long dependent accumulation chain into a single accumulator
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem, ad + 2 * k, bd2 + 2 * k, idesc, 1u);
+                } else if (p.time_mode == 4) {
+                    // single accumulator + a commit after every 4 MMAs (as the tower issues them)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                    ptx::umma_commit(bar + 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem, ad + 2 * k, bd2 + 2 * k, idesc, 1u);
+                    ptx::umma_commit(bar + 1);
+                } else if (p.time_mode == 5) {
+                    // alternate the accumulator on every MMA
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ptx::umma_f16(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                        ptx::umma_f16(tmem + 256, ad + 2 * k, bd2 + 2 * k, idesc, 1u);
+                    }
+                } else {
+                    // same A K-slice back to back on two accumulators: fill then use
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_f16_cf(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                        umma_f16_cu(tmem + 256, ad + 2 * k, bd2 + 2 * k, idesc, 1u);
+                    }
+                }
+            }
+            ptx::umma_commit(bar);
+        }
+        __syncwarp();
+        ptx::mbar_wait(bar, phase);
+        if (ptx::elect_one()) {
+            t1 = clock64();
+            p.cyc[0] = t1 - t0;
+        }
+        __syncwarp();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem); }
+}
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+int main() {
+    std::vector<__nv_bfloat16> hA(128 * 64), hB(kRows * 64);
+    std::vector<float> fA(128 * 64), fB(kRows * 64);
+    srand(7);
+    for (size_t i = 0; i < hA.size(); ++i) { fA[i] = float(rand() % 5 - 2); hA[i] = __float2bfloat16(fA[i]); }
+    for (size_t i = 0; i < hB.size(); ++i) { fB[i] = float(rand() % 7 - 3); hB[i] = __float2bfloat16(fB[i]); }
+    __nv_bfloat16 *dA, *dB; float* dD; long long* dC;
+    CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 128 * 256 * 4)); CK(cudaMalloc(&dC, 8));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+    const int smem = 1024 + 16384 + kRows * 128 + 64;
+    CK(cudaFuncSetAttribute(exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    std::vector<float> hD(128 * 256);
+    auto run = [&](int r0, int sbo_rows, int base_mode, int n, int dcol) {
+        Params p{dA, dB, dD, r0, sbo_rows, base_mode, n, dcol, dC, 0, 0};
+        exp_kernel<<<1, 128, smem>>>(p);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("r0=%d sbo=%d base=%d n=%d dcol=%d: CUDA error %s\n", r0, sbo_rows, base_mode, n, dcol, cudaGetErrorString(e)); exit(1); }
+        CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+        int bad = 0, bad_outside = 0;
+        for (int m = 0; m < 128; ++m)
+            for (int c = 0; c < 256; ++c) {
+                int row;
+                const bool inside = c >= dcol && c < dcol + n;
+                if (inside) { const int nn = c - dcol; row = (nn >> 3) * sbo_rows + r0 + (nn & 7); }
+                else row = c;
+                float ref = 0;
+                for (int k = 0; k < 64; ++k) ref += fA[m * 64 + k] * fB[row * 64 + k];
+                if (ref != hD[m * 256 + c]) { if (inside) ++bad; else ++bad_outside; }
+            }
+        printf("r0=%d sbo_rows=%d base_mode=%d N=%d dcol=%d : %s (mismatch inside %d, outside %d)\n", r0, sbo_rows, base_mode, n,
+               dcol, (bad == 0 && bad_outside == 0) ? "EXACT" : "WRONG", bad, bad_outside);
+    };
+    run(0, 8, 0, 256, 0);
+    for (int base = 0; base < 2; ++base) {
+        run(8, 8, base, 256, 0);
+        run(1, 8, base, 256, 0);
+        run(3, 8, base, 256, 0);
+        run(0, 9, base, 256, 0);
+        run(1, 9, base, 256, 0);
+        run(2, 9, base, 256, 0);
+        run(5, 9, base, 256, 0);
+        run(1, 9, base, 224, 32);
+        run(2, 9, base, 224, 0);
+        run(0, 10, base, 192, 16);
+    }
+    auto timeit = [&](int mode, int n, int r0 = 0, int sbo_rows = 8) {
+        Params p{dA, dB, dD, r0, sbo_rows, 0, n, 0, dC, mode, 500};
+        exp_kernel<<<1, 128, smem>>>(p);
+        CK(cudaDeviceSynchronize());
+        long long c; CK(cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost));
+        printf("time_mode=%d N=%d r0=%d sbo_rows=%d : %.1f cycles per MMA (K=16), %d MMAs\n", mode, n, r0, sbo_rows, double(c) / (500 * 8), 500 * 8);
+    };
+    timeit(1, 256, 1, 8); timeit(1, 256, 4, 8); timeit(1, 256, 0, 9); timeit(1, 256, 1, 9); timeit(1, 224, 1, 9); timeit(1, 192, 1, 9);
+    timeit(1, 128, 1, 9); timeit(1, 256, 0, 16); timeit(1, 256, 1, 16); timeit(1, 128, 1, 8);
+    timeit(3, 256); timeit(3, 224); timeit(3, 192); timeit(3, 128); timeit(3, 64); timeit(4, 256); timeit(4, 192); timeit(5, 256); timeit(5, 192); timeit(5, 128);
+    timeit(3, 256, 1, 9); timeit(4, 192, 1, 9);
+    timeit(1, 256); timeit(2, 256); timeit(1, 224); timeit(2, 224); timeit(1, 192); timeit(1, 128);
+    return 0;
+}

@@ -15,6 +15,7 @@ ev.time_resident(3)
 tr = ev.debug_tower_trace().astype(np.float64)
 t0 = tr[tr > 0].min()
 us = (tr - t0) / 1965.0
+
 names = ["prod_ready", "prod_done", "mma_start", "mma_end", "epi_full", "epi_pub", "st_issue", "st_done"]
 print("item L c " + " ".join("%10s" % n for n in names) + "   mma_us  epi_us  store_us  gap_to_next_mma")
 for i in range(us.shape[0]):
