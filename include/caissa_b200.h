@@ -152,6 +152,9 @@ int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches);
 /* Debug timeline of CTA 0 of the fused 128-channel tower for the staged batch: out[item*8 + slot] SM clock
  * stamps (slots documented at trace_stamp in tower_t_umma.cuh); returns the number of items written. */
 int cb_debug_tower_trace(cb_handle* h, long long* out, int max_items);
+/* Debug: global-timer stamps (ns) of every CTA of the resident tower for the staged batch:
+ * out[cta*4 + {0 kernel entry, 1 first MMA, 2 last epilogue done, 3 exit}]; returns the CTA count. */
+int cb_debug_cta_times(cb_handle* h, unsigned long long* out, int max_ctas);
 
 /* Kernels launched per forward of the given kind (for gpu_launches accounting). */
 int cb_launches_per_forward(const cb_handle* h);

@@ -70,6 +70,7 @@ SIGNATURES = {
     "cb_debug_backbone": (ctypes.c_int, [_VP, ctypes.c_int, _VP]),
     "cb_debug_act": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_debug_tower_trace": (ctypes.c_int, [_VP, _VP, ctypes.c_int]),
+    "cb_debug_cta_times": (ctypes.c_int, [_VP, _VP, ctypes.c_int]),
     "cb_debug_set_layer_limit": (ctypes.c_int, [_VP, ctypes.c_int]),
     "cb_chess_startpos": (ctypes.c_int, [_VP]),
     "cb_chess_legal_moves": (ctypes.c_int, [_VP, _VP, _VP]),
@@ -241,9 +242,16 @@ class Evaluator:
         return out
 
     def debug_tower_trace(self):
-        items = 2 * (2 * self.num_blocks + 2)
+        items = 2 * (2 * self.num_blocks + 3)
         out = np.zeros((items, 8), dtype=np.int64)
         n = self._L.cb_debug_tower_trace(self._h, _ptr(out), items)
+        if n < 0:
+            self._check(n)
+        return out[:n]
+
+    def debug_cta_times(self, max_ctas=256):
+        out = np.zeros((max_ctas, 4), dtype=np.uint64)
+        n = self._L.cb_debug_cta_times(self._h, _ptr(out), max_ctas)
         if n < 0:
             self._check(n)
         return out[:n]

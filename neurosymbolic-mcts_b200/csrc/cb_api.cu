@@ -110,12 +110,14 @@ struct cb_handle {
     bool use_quad = true;
     long long* d_trace = nullptr;   // debug timeline of CTA 0 of the transposed tower (cb_debug_tower_trace)
     // smem-resident fused tower for the 128-channel net (tower_r_umma.cuh)
-    CUtensorMap tm_pc_st[4], tm_pc_ld;   // p_conv output act[y][board][x][C]: stores for 1..4 boards, policy load
+    void* p_w16r = nullptr;              // p_head weights padded to [128][HID] 16-bit (rows 73.. zero)
+    float* p_bias_r = nullptr;           // p_head bias padded to 128
+    CUtensorMap tm_pwr;
     CUtensorMap* d_maps_r = nullptr;
     cb::TowerRLayer* d_layers_r = nullptr;
     uint4* d_res_scratch = nullptr;
-    void* d_pc = nullptr;                // p_conv output of the resident tower
     float* d_dbg_backbone = nullptr;     // set only inside cb_debug_backbone
+    unsigned long long* d_cta_times = nullptr;   // set only inside cb_debug_cta_times
     bool tower_r_ready = false;
     bool use_resident = true;
 
@@ -191,24 +193,6 @@ int make_act_map(cb_handle* h, CUtensorMap* tm, void* base, int channels, int bo
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
-    return CB_OK;
-}
-
-// 4-D map over the resident tower's p_conv output act[y][board][9 x-slots][C]: slot 0 of every 9-row
-// group is the tower's zero pad row (stored as is so that every TMA box stays in bounds), pixels are
-// slots 1..8.
-int make_plain_map(cb_handle* h, CUtensorMap* tm, void* base, int channels, int boards, int box_x, int box_b, int box_y) {
-    const cuuint64_t C = (cuuint64_t)channels;
-    const cuuint64_t dims[4] = {C, 9, (cuuint64_t)boards, 8};
-    const cuuint64_t strides[3] = {C * 2, C * 18, C * 18 * (cuuint64_t)boards};
-    const cuuint32_t box[4] = {64, (cuuint32_t)box_x, (cuuint32_t)box_b, (cuuint32_t)box_y};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUtensorMapDataType dt =
-        h->dtype == CB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    CUresult r = h->encode_tiled(tm, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(plain activation) failed: " + std::to_string((int)r));
     return CB_OK;
 }
 
@@ -293,13 +277,8 @@ int ensure_capacity(cb_handle* h, int B) {
                 if ((rc = make_act_map(h, &h->tm_act_ld_q[i], h->d_act[i], h->hid, cap, 10, 4))) return rc;
                 if ((rc = make_act_map(h, &h->tm_act_st_q[i], h->d_act[i], h->hid, cap, 8, 4))) return rc;
             }
-            // resident tower: p_conv output buffer act[y][board][9 x-slots][C]
-            free_dev(h->d_res_scratch); free_dev(h->d_pc);
-            h->d_res_scratch = nullptr; h->d_pc = nullptr;
-            CB_CUDA(h, cudaMalloc(&h->d_pc, (size_t)cap * 72 * h->hid * 2));
-            for (int nb = 1; nb <= 4; ++nb)
-                if ((rc = make_plain_map(h, &h->tm_pc_st[nb - 1], h->d_pc, h->hid, cap, 9, nb, 8))) return rc;
-            if ((rc = make_plain_map(h, &h->tm_pc_ld, h->d_pc, h->hid, cap, 8, 2, 8))) return rc;
+            free_dev(h->d_res_scratch);
+            h->d_res_scratch = nullptr;
             CB_CUDA(h, cudaMalloc(&h->d_res_scratch, (size_t)h->sm_count * TowerRCfg::kScratchPerCta * sizeof(uint4)));
         }
         if (h->loaded && (rc = build_tower_tables(h))) return rc;
@@ -381,19 +360,23 @@ int build_tower_tables(cb_handle* h) {
         CB_CUDA(h, cudaMemcpy(h->d_layers_q, lq.data(), lq.size() * sizeof(TowerTLayer), cudaMemcpyHostToDevice));
         h->tower_q_ready = true;
 
-        // resident tower: map table 0..3 p_conv stores (1..4 boards) | 4.. weights
+        // resident tower: map table = weights of the nl conv layers, then the padded p_head; the layer table
+        // ends with the policy head as a one-tap layer
         h->tower_r_ready = false;
-        std::vector<CUtensorMap> mr(4 + nl);
-        for (int i = 0; i < 4; ++i) mr[i] = h->tm_pc_st[i];
-        for (int l = 0; l < nl; ++l) mr[4 + l] = h->convs[l].tm_w;
-        std::vector<TowerRLayer> lr(nl);
-        memset(lr.data(), 0, sizeof(TowerRLayer) * nl);
+        std::vector<CUtensorMap> mr(nl + 1);
+        for (int l = 0; l < nl; ++l) mr[l] = h->convs[l].tm_w;
+        mr[nl] = h->tm_pwr;
+        std::vector<TowerRLayer> lr(nl + 1);
+        memset(lr.data(), 0, sizeof(TowerRLayer) * (nl + 1));
         for (int l = 0; l < nl; ++l) {
-            lr[l].w_map = 4 + l;
+            lr[l].w_map = l;
             lr[l].kc_in = l == 0 ? 1 : 2;
             lr[l].mode = (l >= 1 && l < nl - 1 && (l & 1) == 0) ? MODE_SE_RES : MODE_RELU;
             lr[l].bias = h->convs[l].bias;
+            lr[l].ntaps = 9;
         }
+        lr[nl].w_map = nl; lr[nl].kc_in = 2; lr[nl].mode = MODE_POLICY; lr[nl].bias = h->p_bias_r;
+        lr[nl].ntaps = 1; lr[nl].w_row_off = -4 * 128;
         lr[0].save_res = 1;
         for (int i = 0; i < h->blocks; ++i) {
             TowerRLayer& b = lr[2 + 2 * i];
@@ -421,6 +404,27 @@ int fused_kind(const cb_handle* h) {
     return h->tower_ready ? 1 : 0;
 }
 
+ValueParams value_params(const cb_handle* h, int B, int material_on, bool use_q, int pair_layout) {
+    ValueParams vp = {};
+    vp.v_pre = h->d_vpre;
+    vp.q = use_q ? h->d_q : nullptr;
+    vp.conv_bias = h->v_conv_bias;
+    vp.bn_scale = h->v_bn_scale;
+    vp.bn_bias = h->v_bn_bias;
+    vp.fc_wt = h->fc_wt;
+    vp.fc_b = h->fc_b;
+    vp.out_w = h->out_w;
+    vp.out_b = h->out_b;
+    vp.k = h->k;
+    vp.material_on = material_on;
+    vp.pair_layout = pair_layout;   // layout of v_pre rows: the quad / resident towers emit plain order
+    vp.B = B;
+    vp.v_logit = h->d_vlogit;
+    vp.v_final = h->d_vfinal;
+    vp.k_out = h->d_k;
+    return vp;
+}
+
 // Units of the resident tower: boards are spread evenly over the SMs (at least 2 and at most 8 per unit).
 int tower_r_units(const cb_handle* h, int B) {
     const int rounds = (B + 8 * h->sm_count - 1) / (8 * h->sm_count);
@@ -428,17 +432,21 @@ int tower_r_units(const cb_handle* h, int B) {
     return even < pairs ? even : pairs;
 }
 
-int launch_tower_r(cb_handle* h, int B) {
+// One launch = the whole forward: planes, conv tower, policy head and value head.
+int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bool use_q) {
     TowerRParams tp;
     tp.boards = h->d_boards;
     tp.maps = h->d_maps_r;
     tp.layers = h->d_layers_r;
-    tp.num_layers = (int)h->convs.size();
+    tp.po = po;
+    tp.vp = value_params(h, B, material_on, use_q, 0);
+    tp.num_layers = (int)h->convs.size() + 1;
     tp.num_boards = B;
     tp.num_units = tower_r_units(h, B);
     tp.res_scratch = h->d_res_scratch;
     tp.dbg_backbone = h->d_dbg_backbone;
     tp.trace = h->d_trace;
+    tp.cta_times = h->d_cta_times;
     const char* dbg_env = getenv("CB_DBG_R");
     tp.dbg = dbg_env ? atoi(dbg_env) : 0;
     const int grid = tp.num_units < h->sm_count ? tp.num_units : h->sm_count;
@@ -453,6 +461,17 @@ int launch_tower_r(cb_handle* h, int B) {
     }
     CB_CUDA(h, cudaGetLastError());
     return CB_OK;
+}
+
+// The same launch with the outputs of the fast path (priors of the staged legal moves, material on).
+int launch_tower_r_staged(cb_handle* h, int B) {
+    PolicyOut po = {};
+    if (h->staged_moves > 0) {
+        po.move_idx = h->d_move_idx;
+        po.move_off = h->d_move_off;
+        po.priors = h->d_priors;
+    }
+    return launch_tower_r(h, B, po, 1, true);
 }
 
 int launch_tower_q(cb_handle* h, int B) {
@@ -577,9 +596,7 @@ int launch_policy_umma_t(cb_handle* h, int B, const PolicyOut& po) {
     const int grid = tiles < h->sm_count ? tiles : h->sm_count;
     auto kern = policy_umma_kernel<HID, BF16>;
     CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    const bool plain = fused_kind(h) == 3;
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, h->stream>>>(plain ? h->tm_pc_ld : h->tm_act_st[1], h->tm_pw, h->p_bias, tiles, B,
-                                                             po, plain ? 1 : 0);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, h->stream>>>(h->tm_act_st[1], h->tm_pw, h->p_bias, tiles, B, po);
     CB_CUDA(h, cudaGetLastError());
     return CB_OK;
 }
@@ -709,16 +726,6 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
         encode_tiled16_kernel<false><<<(Bpad * 512 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, Bpad, glog, (uint4*)h->d_x0);
     }
     CB_CUDA(h, cudaGetLastError());
-    int rc;
-    if (kind == 3)
-        rc = launch_tower_r(h, B);
-    else if (kind == 2)
-        rc = launch_tower_q(h, B);
-    else if (kind == 1)
-        rc = launch_tower(h, B);
-    else
-        rc = enqueue_tower(h, B, nullptr);
-    if (rc) return rc;
     PolicyOut po = {};
     po.probs = full_policy ? h->d_probs : nullptr;
     if (csr) {
@@ -726,26 +733,19 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
         po.move_off = h->d_move_off;
         po.priors = h->d_priors;
     }
+    int rc;
+    if (kind == 3) return launch_tower_r(h, B, po, material_on, use_q);   // heads included
+    if (kind == 2)
+        rc = launch_tower_q(h, B);
+    else if (kind == 1)
+        rc = launch_tower(h, B);
+    else
+        rc = enqueue_tower(h, B, nullptr);
+    if (rc) return rc;
     // the two heads are independent: fork the value head onto the side stream
     CB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     CB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-    ValueParams vp = {};
-    vp.v_pre = h->d_vpre;
-    vp.q = use_q ? h->d_q : nullptr;
-    vp.conv_bias = h->v_conv_bias;
-    vp.bn_scale = h->v_bn_scale;
-    vp.bn_bias = h->v_bn_bias;
-    vp.fc_wt = h->fc_wt;
-    vp.fc_b = h->fc_b;
-    vp.out_w = h->out_w;
-    vp.out_b = h->out_b;
-    vp.k = h->k;
-    vp.material_on = material_on;
-    vp.pair_layout = h->dtype == CB_DTYPE_FP32 ? 0 : (kind >= 2 ? 0 : 1);  // quad / resident towers emit v_pre in plain order
-    vp.B = B;
-    vp.v_logit = h->d_vlogit;
-    vp.v_final = h->d_vfinal;
-    vp.k_out = h->d_k;
+    const ValueParams vp = value_params(h, B, material_on, use_q, h->dtype == CB_DTYPE_FP32 ? 0 : (kind >= 2 ? 0 : 1));
     value_head_kernel<<<(B + kValueBoardsPerCta - 1) / kValueBoardsPerCta, 256, 0, h->stream2>>>(vp);
     CB_CUDA(h, cudaGetLastError());
     CB_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
@@ -888,10 +888,10 @@ void cb_destroy(cb_handle* h) {
     for (auto p : h->se_w1) free_dev(p);
     for (auto p : h->se_w2) free_dev(p);
     free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
-    free_dev(h->p_w16);
+    free_dev(h->p_w16); free_dev(h->p_w16r); free_dev(h->p_bias_r);
     free_dev(h->d_maps); free_dev(h->d_layers);
     free_dev(h->d_maps_q); free_dev(h->d_layers_q);
-    free_dev(h->d_maps_r); free_dev(h->d_layers_r); free_dev(h->d_res_scratch); free_dev(h->d_pc);
+    free_dev(h->d_maps_r); free_dev(h->d_layers_r); free_dev(h->d_res_scratch);
     free_dev(h->d_flush);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -910,7 +910,7 @@ int cb_is_available(const cb_handle* h) { return h && h->loaded ? 1 : 0; }
 int cb_launches_per_forward(const cb_handle* h) {
     if (!h) return 0;
     const int convs = 2 * h->blocks + 2;
-    if (fused_kind(h) == 3) return 3;                          // resident tower (encodes in-kernel), policy, value
+    if (fused_kind(h) == 3) return 1;                          // resident tower: planes, convs and both heads in one launch
     if (h->dtype != CB_DTYPE_FP32 && h->use_fused) return 4;  // encode, fused tower, policy, value
     return 1 + convs + (h->dtype == CB_DTYPE_FP32 ? h->blocks : 0) + 2;
 }
@@ -937,8 +937,8 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
     for (auto p : h->se_w2) free_dev(p);
     h->convs.clear(); h->se_w1.clear(); h->se_w2.clear();
     free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
-    free_dev(h->p_w16);
-    h->p_w16 = nullptr;
+    free_dev(h->p_w16); free_dev(h->p_w16r); free_dev(h->p_bias_r);
+    h->p_w16 = nullptr; h->p_w16r = nullptr; h->p_bias_r = nullptr;
     h->p_wt = h->p_bias = h->v_w = h->fc_wt = h->fc_b = h->out_w = nullptr;
     h->loaded = false;
 
@@ -1001,7 +1001,8 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
         for (int c = 0; c < 73; ++c)
             for (int k = 0; k < H; ++k) wt[(size_t)k * 73 + c] = pw[(size_t)c * H + k];
         if ((rc = upload(wt.data(), wt.size() * 4, (void**)&h->p_wt))) return rc;
-        if ((rc = upload(take(73), 73 * 4, (void**)&h->p_bias))) return rc;
+        const float* pb = take(73);
+        if ((rc = upload(pb, 73 * 4, (void**)&h->p_bias))) return rc;
         if (h->dtype != CB_DTYPE_FP32) {
             std::vector<uint16_t> w16((size_t)80 * H, 0);
             for (int c = 0; c < 73; ++c)
@@ -1017,6 +1018,21 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(policy weights) failed");
+            if (H == 128) {
+                // resident tower: p_head as a one-tap "layer": weights [128][H] (73 real rows), bias padded to 128
+                std::vector<uint16_t> wr((size_t)128 * H, 0);
+                memcpy(wr.data(), w16.data(), (size_t)73 * H * 2);
+                if ((rc = upload(wr.data(), wr.size() * 2, &h->p_w16r))) return rc;
+                std::vector<float> br(128, 0.0f);
+                memcpy(br.data(), pb, 73 * 4);
+                if ((rc = upload(br.data(), 128 * 4, (void**)&h->p_bias_r))) return rc;
+                const cuuint64_t dims_r[2] = {(cuuint64_t)H, 128};
+                const cuuint32_t box_r[2] = {64, 128};
+                if (h->encode_tiled(&h->tm_pwr, dt, 2, h->p_w16r, dims_r, strides, box_r, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(padded policy weights) failed");
+            }
         }
     }
     if ((rc = upload(take(H), (size_t)H * 4, (void**)&h->v_w))) return rc;
@@ -1233,7 +1249,7 @@ int cb_time_tower(cb_handle* h, int iters, float* ms_each, int* n_launches) {
     int rc = CB_OK;
     for (int i = 0; i < iters && !rc; ++i) {
         CB_CUDA(h, cudaEventRecord(ev[2 * i], h->stream));
-        rc = kind == 3   ? launch_tower_r(h, h->staged_B)
+        rc = kind == 3   ? launch_tower_r_staged(h, h->staged_B)
              : kind == 2 ? launch_tower_q(h, h->staged_B)
              : kind == 1 ? launch_tower(h, h->staged_B)
                          : enqueue_tower(h, h->staged_B, nullptr);
@@ -1261,16 +1277,36 @@ int cb_debug_tower_trace(cb_handle* h, long long* out, int max_items) {
     const int kind = fused_kind(h);
     if (!h->staged_B || kind < 2) return fail(h, CB_ESTATE, "needs staged leaves and a transposed tower");
     CB_CUDA(h, cudaSetDevice(h->device));
-    const int items = 2 * (int)h->convs.size();
+    const int items = 2 * ((int)h->convs.size() + (kind == 3 ? 1 : 0));   // the resident tower's last "layer" is the policy head
     const int n = items < max_items ? items : max_items;
     drop_graphs(h);
     CB_CUDA(h, cudaMalloc(&h->d_trace, (size_t)items * 8 * sizeof(long long)));
     CB_CUDA(h, cudaMemsetAsync(h->d_trace, 0, (size_t)items * 8 * sizeof(long long), h->stream));
-    int rc = kind == 3 ? launch_tower_r(h, h->staged_B) : launch_tower_q(h, h->staged_B);
+    int rc = kind == 3 ? launch_tower_r_staged(h, h->staged_B) : launch_tower_q(h, h->staged_B);
     cudaError_t e = cudaMemcpyAsync(out, h->d_trace, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
     cudaError_t e2 = cudaStreamSynchronize(h->stream);
     cudaFree(h->d_trace);
     h->d_trace = nullptr;
+    if (rc) return rc;
+    CB_CUDA(h, e);
+    CB_CUDA(h, e2);
+    return n;
+}
+
+int cb_debug_cta_times(cb_handle* h, unsigned long long* out, int max_ctas) {
+    if (!h || !out || max_ctas <= 0) return CB_EINVAL;
+    if (!h->staged_B || fused_kind(h) != 3) return fail(h, CB_ESTATE, "needs staged leaves and the resident tower");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    const int units = tower_r_units(h, h->staged_B);
+    const int grid = units < h->sm_count ? units : h->sm_count;
+    const int n = grid < max_ctas ? grid : max_ctas;
+    CB_CUDA(h, cudaMalloc(&h->d_cta_times, (size_t)grid * 4 * sizeof(unsigned long long)));
+    CB_CUDA(h, cudaMemsetAsync(h->d_cta_times, 0, (size_t)grid * 4 * sizeof(unsigned long long), h->stream));
+    int rc = launch_tower_r_staged(h, h->staged_B);
+    cudaError_t e = cudaMemcpyAsync(out, h->d_cta_times, (size_t)n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_cta_times);
+    h->d_cta_times = nullptr;
     if (rc) return rc;
     CB_CUDA(h, e);
     CB_CUDA(h, e2);
@@ -1295,7 +1331,7 @@ int cb_debug_backbone(cb_handle* h, int B, float* out) {
         int rc = ensure_scratch(h, total);
         if (rc) return rc;
         h->d_dbg_backbone = h->d_scratch;
-        rc = launch_tower_r(h, B);
+        rc = launch_tower_r_staged(h, B);
         h->d_dbg_backbone = nullptr;
         if (rc) return rc;
         CB_CUDA(h, cudaMemcpyAsync(out, h->d_scratch, total * 4, cudaMemcpyDeviceToHost, h->stream));

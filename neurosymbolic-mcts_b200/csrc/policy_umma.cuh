@@ -39,7 +39,7 @@ struct PolicyCfg {
 template <int HID, bool BF16>
 __global__ void __launch_bounds__(PolicyCfg<HID>::kThreads, 1)
 policy_umma_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_wp,
-                   const float* __restrict__ bias, int num_tiles, int B, PolicyOut po, int plain) {
+                   const float* __restrict__ bias, int num_tiles, int B, PolicyOut po) {
     using Cfg = PolicyCfg<HID>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -98,13 +98,9 @@ policy_umma_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_consta
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&p_full[st], Cfg::kPBytes);
 #pragma unroll
-                for (int kc = 0; kc < Cfg::kKc; ++kc) {
-                    uint8_t* dst = p_smem + st * Cfg::kPBytes + kc * Cfg::kPChunkBytes;
-                    if (plain)   // act[y][board][9 x-slots][C] (tower_r_umma.cuh): box {64, 8 x from slot 1, 2 boards, 8 y}
-                        ptx::tma_load_4d(dst, &tm_p, &p_full[st], kc * 64, 1, tile * 2, 0);
-                    else
-                        ptx::tma_load_5d(dst, &tm_p, &p_full[st], kc * 64, 0, 0, 0, tile);
-                }
+                for (int kc = 0; kc < Cfg::kKc; ++kc)
+                    ptx::tma_load_5d(p_smem + st * Cfg::kPBytes + kc * Cfg::kPChunkBytes, &tm_p, &p_full[st], kc * 64,
+                                     0, 0, 0, tile);
             }
             __syncwarp();
             if (++st == kStages) { st = 0; ph ^= 1; }

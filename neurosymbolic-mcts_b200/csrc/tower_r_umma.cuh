@@ -51,11 +51,15 @@ struct TowerRCfg {
     static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
 };
 
+enum { MODE_POLICY = 2 };        // p_head 1x1 conv: one tap, epilogue = softmax / legal-move gather + value head
+
 struct TowerRLayer {
     int w_map;                   // tensor-map table index of this layer's weights
     int kc_in;                   // C_in / 64
-    int mode;                    // MODE_RELU / MODE_SE_RES
+    int mode;                    // MODE_RELU / MODE_SE_RES / MODE_POLICY
     int save_res;                // 1: the output is a block input, park it for the residual add
+    int ntaps;                   // 9 (3x3 conv) or 1 (1x1 conv: only the centre tap of the tap order)
+    int w_row_off;               // added to tap * 128 to form the weight row coordinate (-512 for the 1x1 conv)
     const float* bias;
     const float* se_w1;
     const float* se_w2;
@@ -65,14 +69,17 @@ struct TowerRLayer {
 
 struct TowerRParams {
     const cb_board* boards;
-    const CUtensorMap* maps;     // [0..3] p_conv output store maps for nb = 1..4 | [4..] weights
+    const CUtensorMap* maps;     // weights of every layer (conv tower, then p_head)
     const TowerRLayer* layers;
-    int num_layers;
+    PolicyOut po;                // policy outputs (full probabilities and / or priors of the legal moves)
+    ValueParams vp;              // value head weights and outputs (v_pre is produced and consumed in-kernel)
+    int num_layers;              // conv layers + 1 (the policy head)
     int num_boards;
     int num_units;
     uint4* res_scratch;          // [grid][TowerRCfg::kScratchPerCta]
     float* dbg_backbone;         // optional f32 NCHW [board][128][64] dump of the backbone output
     long long* trace;            // debug timeline (CTA 0), or nullptr
+    unsigned long long* cta_times;   // debug: [grid][4] globaltimer ns at kernel entry / first MMA / last epilogue / exit
     int dbg;                     // CB_DBG_R bits: 1 no MMA issue, 2 no p_conv store, 4 no residual scratch, 8 no plane bits
 };
 
@@ -136,8 +143,112 @@ __device__ __forceinline__ uint32_t pack_relu16(float lo, float hi) {
     return d;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ void trace_stamp(long long* trace, int item, int slot) {
     if (trace && blockIdx.x == 0) trace[item * 8 + slot] = clock64();
+}
+
+__device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// Policy + value heads of ONE board, run by its 128-thread board team (the four epilogue warps that
+// share a board slot; tix = the thread's index in the team = its TMEM lane = the p_head plane).
+//   logits[73 planes][64 pixels] (accumulator, bias preset) -> shared memory as the reference's flat
+//   [src * 73 + plane] row (python/model.py:120-125) -> full-row log-sum-exp -> all probabilities
+//   (src/neural_net.rs:279-284) and / or the legal moves gathered and renormalised in list order with
+//   the uniform fallback (src/tensor.rs:184-213);  value head BN(1)+ReLU, cat q, FC 65->256, FC 256->1,
+//   k, tanh fusion (python/model.py:128-132,109-110; src/mcts/tactical_mcts.rs:762-765,787-790).
+__device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board, int bs, int nb, int tix, int lane, int quadl,
+                                               uint32_t tcol, float* lg, float* s_red, float* s_g, float* s_x) {
+    const int bar = 2 + bs;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        uint32_t r[8];
+        ptx::tmem_ld_32x8(tcol + y * nb * 8, r);
+        ptx::tmem_ld_wait();
+        if (tix < 73) {
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                const float v = __uint_as_float(r[x]);
+                lg[(y * 8 + x) * 73 + tix] = v;
+                mx = fmaxf(mx, v);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if (lane == 0) s_red[quadl] = mx;
+    team_bar(bar);
+    const float bmax = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    float se = 0.0f;
+    for (int i = tix; i < CB_POLICY_SIZE; i += 128) se += __expf(lg[i] - bmax);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
+    if (lane == 0) s_red[4 + quadl] = se;
+    // value head input while the sums settle: x[0..63] = relu(bn(v_conv)), x[64] = q
+    if (tix < 64)
+        s_x[tix] = fmaxf((__ldcg(p.vp.v_pre + board * 64 + tix) + p.vp.conv_bias) * p.vp.bn_scale + p.vp.bn_bias, 0.0f);
+    else if (tix == 64)
+        s_x[64] = p.vp.q ? p.vp.q[board] : 0.0f;
+    team_bar(bar);
+    const float lse = bmax + __logf((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
+    if (p.po.probs) {
+        float* o = p.po.probs + static_cast<size_t>(board) * CB_POLICY_SIZE;
+        for (int i = tix; i < CB_POLICY_SIZE; i += 128) o[i] = __expf(lg[i] - lse);
+    }
+    if (p.po.move_idx) {
+        const uint32_t lo = p.po.move_off[board], hi = p.po.move_off[board + 1];
+        const int n = static_cast<int>(hi - lo);
+        // gathered values -> registers (n <= 256 = 2 per thread), total via an ordered sequential sum by one
+        // thread, exactly the reference's loop (src/tensor.rs:186-201)
+        float g0 = 0.0f, g1 = 0.0f;
+        if (tix < n) {
+            const int idx = p.po.move_idx[lo + tix];
+            g0 = idx < CB_POLICY_SIZE ? __expf(lg[idx] - lse) : 0.0f;
+            s_g[tix] = g0;
+        }
+        if (tix + 128 < n) {
+            const int idx = p.po.move_idx[lo + tix + 128];
+            g1 = idx < CB_POLICY_SIZE ? __expf(lg[idx] - lse) : 0.0f;
+            s_g[tix + 128] = g1;
+        }
+        team_bar(bar);
+        if (tix == 0) {
+            float t = 0.0f;
+            for (int i = 0; i < n; ++i) t += s_g[i];
+            s_red[8] = t;
+        }
+        team_bar(bar);
+        const float total = s_red[8];
+        if (tix < n) p.po.priors[lo + tix] = total > 0.0f ? g0 / total : 1.0f / static_cast<float>(n);
+        if (tix + 128 < n) p.po.priors[lo + tix + 128] = total > 0.0f ? g1 / total : 1.0f / static_cast<float>(n);
+    }
+    // value head: thread owns hidden units tix and tix + 128
+    float h0 = __ldg(p.vp.fc_b + tix), h1 = __ldg(p.vp.fc_b + tix + 128);
+#pragma unroll 13
+    for (int e = 0; e < 65; ++e) {
+        const float xe = s_x[e];
+        h0 = fmaf(__ldg(p.vp.fc_wt + e * 256 + tix), xe, h0);
+        h1 = fmaf(__ldg(p.vp.fc_wt + e * 256 + tix + 128), xe, h1);
+    }
+    float t = fmaxf(h0, 0.0f) * __ldg(p.vp.out_w + tix) + fmaxf(h1, 0.0f) * __ldg(p.vp.out_w + tix + 128);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    if (lane == 0) s_red[12 + quadl] = t;
+    team_bar(bar);
+    if (tix == 0) {
+        const float v = p.vp.out_b + ((s_red[12] + s_red[13]) + (s_red[14] + s_red[15]));
+        const float q = p.vp.q ? p.vp.q[board] : 0.0f;
+        p.vp.v_logit[board] = v;
+        p.vp.k_out[board] = p.vp.k;
+        p.vp.v_final[board] = p.vp.material_on ? tanhf(v + p.vp.k * q) : tanhf(v);
+    }
 }
 
 template <bool BF16>
@@ -161,6 +272,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (p.cta_times && threadIdx.x == 0) p.cta_times[blockIdx.x * 4 + 0] = globaltimer_ns();
     // tap order: the first tap of a layer must cover every accumulator column (dy = 0)
     constexpr int kTapOrder[9] = {4, 3, 5, 1, 0, 2, 7, 6, 8};
 
@@ -188,11 +300,11 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
             for (int L = 0; L < p.num_layers; ++L) {
                 const TowerRLayer* ly = p.layers + L;
                 const CUtensorMap* tm_w = p.maps + ly->w_map;
-                const int kc_in = ly->kc_in;
+                const int kc_in = ly->kc_in, ntaps = ly->ntaps, w_row_off = ly->w_row_off;
                 for (int c = 0; c < 2; ++c) {
                     if (nbc[c] == 0) continue;
 #pragma unroll 1
-                    for (int t = 0; t < 9; ++t) {
+                    for (int t = 0; t < ntaps; ++t) {
                         const int tap = kTapOrder[t];
                         for (int kc = 0; kc < kc_in; ++kc) {
                             if (p.dbg & 64) ptx::mbar_wait(&w_empty[ws], wph ^ 1);
@@ -202,7 +314,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                                     ptx::mbar_arrive(&w_full[ws]);
                                 } else {
                                     ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::kWBytes);
-                                    ptx::tma_load_2d(w_base + ws * Cfg::kWBytes, tm_w, &w_full[ws], kc * 64, tap * HID);
+                                    ptx::tma_load_2d(w_base + ws * Cfg::kWBytes, tm_w, &w_full[ws], kc * 64, tap * HID + w_row_off);
                                 }
                             }
                             __syncwarp();
@@ -224,7 +336,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
             int b0, nbc0, nbc1;
             unit_split(p, unit, b0, nbc0, nbc1);
             for (int L = 0; L < p.num_layers; ++L) {
-                const int kc_in = p.layers[L].kc_in;
+                const int kc_in = p.layers[L].kc_in, ntaps = p.layers[L].ntaps;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int nb = c ? nbc1 : nbc0;
@@ -237,8 +349,10 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     const uint32_t d_tmem = tmem_base + c * 256;
                     uint32_t accum = 1;   // the epilogue presets the accumulator with the bias
                     if (lane == 0) trace_stamp(p.trace, L * 2 + c, 2);
+                    if (p.cta_times && lane == 0 && L == 0 && c == 0 && unit == blockIdx.x) p.cta_times[blockIdx.x * 4 + 1] = globaltimer_ns();
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
+                        if (t >= ntaps) break;
                         const int tap = kTapOrder[t];
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                         int start_row, n, dcol;
@@ -294,15 +408,12 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
         const uint32_t cb2 = static_cast<uint32_t>(ch & 7) * 2;
         uint4* my_res = p.res_scratch + static_cast<size_t>(blockIdx.x) * Cfg::kScratchPerCta + bs * 8 * HID + ch;
         uint32_t full_ph = 0;                     // bit c: phase of tmem_full[c]
-        bool stores_pending = false;
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
             int b0, nbc0, nbc1;
             unit_split(p, unit, b0, nbc0, nbc1);
             // ---- input planes of both chains, straight from the packed bitboards
-            if (stores_pending) {
-                if (et == 0) ptx::tma_store_wait_read0();      // p_conv stores of the previous unit have read the buffers
-                ptx::named_bar_sync(1, kEpi);
-            }
+            // (the heads of the previous unit used the chain buffers as logit storage)
+            if (unit != static_cast<int>(blockIdx.x)) ptx::named_bar_sync(1, kEpi);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 const int nb = c ? nbc1 : nbc0;
@@ -349,12 +460,11 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                 ptx::fence_proxy_async_smem();
                 ptx::mbar_arrive(&chain_ready[c]);
             }
-            stores_pending = false;
 
             for (int L = 0; L < p.num_layers; ++L) {
                 const TowerRLayer* ly = p.layers + L;
                 const int mode = ly->mode;
-                const bool last_layer = L == p.num_layers - 1;
+                const bool last_layer = L == p.num_layers - 1;   // the policy head (MODE_POLICY)
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
                     const int nb = c ? nbc1 : nbc0;
@@ -380,13 +490,21 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             for (int y = 0; y < 8; ++y) rr[y] = __ldcg(my_res + (c * 32 + y) * HID);
                         }
                     }
-                    const float bias_next = last_layer ? 0.0f : __ldg(p.layers[L + 1].bias + ch);
+                    const float bias_next = last_layer ? 0.0f : __ldg(p.layers[L + 1].bias + ch);   // p_head: padded to 128
                     ptx::mbar_wait_parked(&tmem_full[c], (full_ph >> c) & 1u);
                     full_ph ^= 1u << c;
                     ptx::tc_fence_after();
                     if (et == 0) trace_stamp(p.trace, L * 2 + c, 4);
                     // my board's 8 column groups: column (y * nb + bs) * 8
                     const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quadl * 32) << 16) + c * 256 + bs * 8;
+                    if (mode == MODE_POLICY) {
+                        if (active)
+                            heads_epilogue(p, cb0 + bs, bs, nb, ch, lane, quadl, tcol,
+                                           reinterpret_cast<float*>(buf) + bs * CB_POLICY_SIZE, s_part + 512 + bs * 32,
+                                           s_vpart + bs * 256, s_part + 1024 + bs * 68);
+                        if (et == 0) trace_stamp(p.trace, L * 2 + c, 5);
+                        continue;
+                    }
 
                     float scale = 1.0f;
                     if (mode == MODE_SE_RES) {
@@ -476,29 +594,14 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                                 }
                             }
                             // accumulator preset for the next layer of this chain
-                            if (!last_layer) ptx::tmem_st_32x8_bcast(tcol + y * nb * 8, __float_as_uint(bias_next));
+                            ptx::tmem_st_32x8_bcast(tcol + y * nb * 8, __float_as_uint(bias_next));
                         }
-                        if (!last_layer) ptx::tmem_st_wait();
+                        ptx::tmem_st_wait();
                     }
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async_smem();
-                    if (!last_layer) {
-                        ptx::mbar_arrive(&chain_ready[c]);
-                        if (et == 0) trace_stamp(p.trace, L * 2 + c, 5);
-                    } else {
-                        // p_conv output: the 8 x nb groups of 9 rows (pad row included, y-halo groups skipped)
-                        // -> act[y][board][9 x-slots][C]
-                        ptx::named_bar_sync(1, kEpi);
-                        if (et == 0 && !(p.dbg & 2)) {
-                            const CUtensorMap* tm_out = p.maps + (nb - 1);
-#pragma unroll
-                            for (int kc = 0; kc < 2; ++kc)
-                                ptx::tma_store_4d(tm_out, buf + kc * Cfg::kHalfBytes + halo * nb * 9 * 128, kc * 64, 0, cb0, 0);
-                            ptx::tma_store_commit();
-                            trace_stamp(p.trace, L * 2 + c, 5);
-                        }
-                        stores_pending = true;
-                    }
+                    ptx::mbar_arrive(&chain_ready[c]);
+                    if (et == 0) trace_stamp(p.trace, L * 2 + c, 5);
                     if (want_v) {
                         ptx::named_bar_sync(1, kEpi);
                         // fixed summation order over the four lane quarters keeps the result independent of batch composition
@@ -513,7 +616,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                 }
             }
         }
-        if (stores_pending && et == 0) ptx::tma_store_wait0();
+        if (p.cta_times && et == 0) p.cta_times[blockIdx.x * 4 + 2] = globaltimer_ns();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -521,6 +624,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
         ptx::tc_fence_after();
         ptx::tmem_dealloc<512>(tmem_base);
     }
+    if (p.cta_times && threadIdx.x == 0) p.cta_times[blockIdx.x * 4 + 3] = globaltimer_ns();
 }
 
 }  // namespace cb

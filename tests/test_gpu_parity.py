@@ -242,7 +242,7 @@ def test_resident_path_equals_host_path(cb, golden, positions):
     assert n == 13 and conv_ms > 0
     tower_ms, launches = ev.time_tower(3)
     assert launches == 1 and tower_ms.min() > 0            # the fused persistent tower kernel
-    assert ev.launches_per_forward() == 3                  # tower (encodes in-kernel), policy, value
+    assert ev.launches_per_forward() == 1                  # planes, tower and both heads in one launch
 
 
 # ------------------------------------------------------------------ reference-shaped host interface

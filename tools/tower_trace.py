@@ -22,3 +22,17 @@ for i in range(us.shape[0]):
     nxt = us[i + 1, 2] - us[i, 3] if i + 1 < us.shape[0] else 0
     print("%3d %2d %d " % (i, i // 2, i % 2) + " ".join("%10.2f" % v for v in us[i]) +
           "   %6.2f  %6.2f  %6.2f  %6.2f" % (us[i, 3] - us[i, 2], us[i, 5] - us[i, 4], us[i, 7] - us[i, 6], nxt))
+
+try:
+    ev.time_tower(3)
+    ct = ev.debug_cta_times().astype(np.float64)
+    t0 = ct[:, 0].min()
+    rel = (ct - t0) / 1e3
+    print("CTA times (us, relative to the first entry): entry min/max %.2f/%.2f | first MMA min/max %.2f/%.2f | last epilogue min/median/max %.2f/%.2f/%.2f | exit max %.2f"
+          % (rel[:, 0].min(), rel[:, 0].max(), rel[:, 1].min(), rel[:, 1].max(), rel[:, 2].min(), np.median(rel[:, 2]), rel[:, 2].max(), rel[:, 3].max()))
+    dur = rel[:, 2] - rel[:, 1]
+    print("per-CTA first MMA -> last epilogue: min %.2f median %.2f max %.2f us" % (dur.min(), np.median(dur), dur.max()))
+    tw, _ = ev.time_tower(10)
+    print("tower launch (CUDA events): %s us" % np.round(tw * 1e3, 1))
+except Exception as e:
+    print("cta times unavailable:", e)
