@@ -163,7 +163,7 @@ __device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 12
 //   the uniform fallback (src/tensor.rs:184-213);  value head BN(1)+ReLU, cat q, FC 65->256, FC 256->1,
 //   k, tanh fusion (python/model.py:128-132,109-110; src/mcts/tactical_mcts.rs:762-765,787-790).
 __device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board, int bs, int nb, int tix, int lane, int quadl,
-                                               uint32_t tcol, float* lg, float* s_red, float* s_g, float* s_x) {
+                                               uint32_t tcol, float* lg, float* s_red, float* s_g) {
     const int bar = 2 + bs;
     float mx = -INFINITY;
 #pragma unroll
@@ -186,16 +186,15 @@ __device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board,
     if (lane == 0) s_red[quadl] = mx;
     team_bar(bar);
     const float bmax = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-    float se = 0.0f;
-    for (int i = tix; i < CB_POLICY_SIZE; i += 128) se += __expf(lg[i] - bmax);
+    // 4672 = 36 * 128 + 64: four independent partial sums, combined in a fixed order
+    float se4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < 36; ++i) se4[i & 3] += __expf(lg[tix + 128 * i] - bmax);
+    if (tix < 64) se4[0] += __expf(lg[tix + 128 * 36] - bmax);
+    float se = (se4[0] + se4[1]) + (se4[2] + se4[3]);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
     if (lane == 0) s_red[4 + quadl] = se;
-    // value head input while the sums settle: x[0..63] = relu(bn(v_conv)), x[64] = q
-    if (tix < 64)
-        s_x[tix] = fmaxf((__ldcg(p.vp.v_pre + board * 64 + tix) + p.vp.conv_bias) * p.vp.bn_scale + p.vp.bn_bias, 0.0f);
-    else if (tix == 64)
-        s_x[64] = p.vp.q ? p.vp.q[board] : 0.0f;
     team_bar(bar);
     const float lse = bmax + __logf((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
     if (p.po.probs) {
@@ -220,8 +219,14 @@ __device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board,
         }
         team_bar(bar);
         if (tix == 0) {
+            // strictly sequential adds in list order; the loads are batched so their latency overlaps
             float t = 0.0f;
-            for (int i = 0; i < n; ++i) t += s_g[i];
+            int i = 0;
+            for (; i + 8 <= n; i += 8) {
+                const float4 a = *reinterpret_cast<const float4*>(s_g + i), b = *reinterpret_cast<const float4*>(s_g + i + 4);
+                t += a.x; t += a.y; t += a.z; t += a.w; t += b.x; t += b.y; t += b.z; t += b.w;
+            }
+            for (; i < n; ++i) t += s_g[i];
             s_red[8] = t;
         }
         team_bar(bar);
@@ -229,21 +234,52 @@ __device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board,
         if (tix < n) p.po.priors[lo + tix] = total > 0.0f ? g0 / total : 1.0f / static_cast<float>(n);
         if (tix + 128 < n) p.po.priors[lo + tix + 128] = total > 0.0f ? g1 / total : 1.0f / static_cast<float>(n);
     }
-    // value head: thread owns hidden units tix and tix + 128
-    float h0 = __ldg(p.vp.fc_b + tix), h1 = __ldg(p.vp.fc_b + tix + 128);
+}
+
+// Value head of every board of the unit, run by the whole epilogue team once both chains' v_pre rows are
+// complete: threads [0, 256) take chain 0, [256, 512) chain 1; a thread owns one of the 256 hidden units and
+// applies each FC weight it loads to the (up to) 4 boards of its chain.
+//   BN(1)+ReLU, cat q, FC 65->256 + ReLU, FC 256->1, k, tanh fusion
+//   (python/model.py:128-132,109-110; src/mcts/tactical_mcts.rs:762-765,787-790)
+__device__ __forceinline__ void value_phase(const TowerRParams& p, int et, int lane, int cb0, int nb, float* s_xT, float* s_red) {
+    const int j = et & 255, vw8 = (et >> 5) & 7;
+    // x[e][b]: e < 64 relu(bn(v_conv)), e = 64 the material scalar q; missing boards read as 0
+    for (int i = j; i < 65 * 4; i += 256) {
+        const int e = i >> 2, b = i & 3;
+        float x = 0.0f;
+        if (b < nb) {
+            const int board = cb0 + b;
+            if (e < 64) x = fmaxf((__ldcg(p.vp.v_pre + board * 64 + e) + p.vp.conv_bias) * p.vp.bn_scale + p.vp.bn_bias, 0.0f);
+            else x = p.vp.q ? p.vp.q[board] : 0.0f;
+        }
+        s_xT[i] = x;
+    }
+    ptx::named_bar_sync(1, TowerRCfg::kEpiThreads);
+    const float fb = __ldg(p.vp.fc_b + j);
+    float h[4] = {fb, fb, fb, fb};
 #pragma unroll 13
     for (int e = 0; e < 65; ++e) {
-        const float xe = s_x[e];
-        h0 = fmaf(__ldg(p.vp.fc_wt + e * 256 + tix), xe, h0);
-        h1 = fmaf(__ldg(p.vp.fc_wt + e * 256 + tix + 128), xe, h1);
+        const float w = __ldg(p.vp.fc_wt + e * 256 + j);
+        const float4 x = *reinterpret_cast<const float4*>(s_xT + e * 4);
+        h[0] = fmaf(w, x.x, h[0]);
+        h[1] = fmaf(w, x.y, h[1]);
+        h[2] = fmaf(w, x.z, h[2]);
+        h[3] = fmaf(w, x.w, h[3]);
     }
-    float t = fmaxf(h0, 0.0f) * __ldg(p.vp.out_w + tix) + fmaxf(h1, 0.0f) * __ldg(p.vp.out_w + tix + 128);
+    const float ow = __ldg(p.vp.out_w + j);
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-    if (lane == 0) s_red[12 + quadl] = t;
-    team_bar(bar);
-    if (tix == 0) {
-        const float v = p.vp.out_b + ((s_red[12] + s_red[13]) + (s_red[14] + s_red[15]));
+    for (int b = 0; b < 4; ++b) {
+        float t = fmaxf(h[b], 0.0f) * ow;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (lane == 0) s_red[vw8 * 4 + b] = t;
+    }
+    ptx::named_bar_sync(1, TowerRCfg::kEpiThreads);
+    if (j < nb) {
+        float v = p.vp.out_b;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += s_red[w * 4 + j];
+        const int board = cb0 + j;
         const float q = p.vp.q ? p.vp.q[board] : 0.0f;
         p.vp.v_logit[board] = v;
         p.vp.k_out[board] = p.vp.k;
@@ -307,8 +343,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     for (int t = 0; t < ntaps; ++t) {
                         const int tap = kTapOrder[t];
                         for (int kc = 0; kc < kc_in; ++kc) {
-                            if (p.dbg & 64) ptx::mbar_wait(&w_empty[ws], wph ^ 1);
-                            else ptx::mbar_wait_parked(&w_empty[ws], wph ^ 1);
+                            ptx::mbar_wait(&w_empty[ws], wph ^ 1);
                             if (ptx::elect_one()) {
                                 if (p.dbg & 16) {
                                     ptx::mbar_arrive(&w_full[ws]);
@@ -331,7 +366,11 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
         // caps the issue rate at ~150 cycles per MMA); the MMAs themselves are issued by one elected lane.
         int ws = 0;
         uint32_t wph = 0, ready_ph0 = 0, ready_ph1 = 0;
-        const uint32_t w_addr = ptx::smem_u32(w_base);
+        // descriptor halves: low = start address >> 4 | LBO field, high = SBO | version | SWIZZLE_128B
+        const uint64_t a_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(w_base));
+        const uint64_t b_desc0 = umma_desc_sw128_sbo(ptx::smem_u32(chain_base), Cfg::kGroupRows * 128);
+        const uint32_t a_lo0 = static_cast<uint32_t>(a_desc0), a_hi = static_cast<uint32_t>(a_desc0 >> 32);
+        const uint32_t b_lo0 = static_cast<uint32_t>(b_desc0), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
             int b0, nbc0, nbc1;
             unit_split(p, unit, b0, nbc0, nbc1);
@@ -345,9 +384,8 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     if (c == 0) { ptx::mbar_wait(&chain_ready[0], ready_ph0); ready_ph0 ^= 1; }
                     else { ptx::mbar_wait(&chain_ready[1], ready_ph1); ready_ph1 ^= 1; }
                     ptx::tc_fence_after();
-                    const uint32_t buf = ptx::smem_u32(chain_base + c * Cfg::kChainBytes);
+                    const uint32_t b_lo_c = b_lo0 + c * (Cfg::kChainBytes >> 4);
                     const uint32_t d_tmem = tmem_base + c * 256;
-                    uint32_t accum = 1;   // the epilogue presets the accumulator with the bias
                     if (lane == 0) trace_stamp(p.trace, L * 2 + c, 2);
                     if (p.cta_times && lane == 0 && L == 0 && c == 0 && unit == blockIdx.x) p.cta_times[blockIdx.x * 4 + 1] = globaltimer_ns();
 #pragma unroll
@@ -366,22 +404,21 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             dcol = dy < 0 ? 8 * nb : 0;
                         }
                         const uint32_t idesc = ptx::umma_idesc_f16(BF16 ? 1 : 0, 128, n);
-                        const uint32_t b_addr0 = buf + start_row * 128;
+                        const uint32_t b_lo_t = b_lo_c + start_row * 8;      // 128-byte rows in 16-byte units
+                        const uint32_t d_t = d_tmem + dcol;
                         for (int kc = 0; kc < kc_in; ++kc) {
-                            ptx::mbar_wait(&w_full[ws], wph);
+                            ptx::mbar_wait(w_full + ws, wph);
                             if (ptx::elect_one()) {
-                                const uint64_t a_desc = ptx::umma_desc_sw128(w_addr + ws * Cfg::kWBytes);
-                                const uint64_t b_desc = umma_desc_sw128_sbo(b_addr0 + kc * Cfg::kHalfBytes, Cfg::kGroupRows * 128);
+                                const uint32_t a_lo = a_lo0 + ws * (Cfg::kWBytes >> 4);
+                                const uint32_t b_lo = b_lo_t + kc * (Cfg::kHalfBytes >> 4);
                                 if (!(p.dbg & 1)) {
-                                    ptx::umma_f16(d_tmem + dcol, a_desc, b_desc, idesc, accum);
 #pragma unroll
-                                    for (int k = 1; k < 4; ++k)
-                                        ptx::umma_f16(d_tmem + dcol, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
+                                    for (int k = 0; k < 4; ++k)
+                                        ptx::umma_f16_lohi(d_t, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);   // bias preset
                                 }
-                                ptx::umma_commit(&w_empty[ws]);
+                                ptx::umma_commit(w_empty + ws);
                             }
                             __syncwarp();
-                            accum = 1;
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
                         }
                     }
@@ -491,7 +528,8 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                         }
                     }
                     const float bias_next = last_layer ? 0.0f : __ldg(p.layers[L + 1].bias + ch);   // p_head: padded to 128
-                    ptx::mbar_wait_parked(&tmem_full[c], (full_ph >> c) & 1u);
+                    if (p.dbg & 64) ptx::mbar_wait(&tmem_full[c], (full_ph >> c) & 1u);
+                    else ptx::mbar_wait_parked(&tmem_full[c], (full_ph >> c) & 1u);
                     full_ph ^= 1u << c;
                     ptx::tc_fence_after();
                     if (et == 0) trace_stamp(p.trace, L * 2 + c, 4);
@@ -501,7 +539,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                         if (active)
                             heads_epilogue(p, cb0 + bs, bs, nb, ch, lane, quadl, tcol,
                                            reinterpret_cast<float*>(buf) + bs * CB_POLICY_SIZE, s_part + 512 + bs * 32,
-                                           s_vpart + bs * 256, s_part + 1024 + bs * 68);
+                                           s_vpart + bs * 256);
                         if (et == 0) trace_stamp(p.trace, L * 2 + c, 5);
                         continue;
                     }
@@ -602,6 +640,13 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     ptx::fence_proxy_async_smem();
                     ptx::mbar_arrive(&chain_ready[c]);
                     if (et == 0) trace_stamp(p.trace, L * 2 + c, 5);
+                    if (L == p.num_layers - 2 && c == 0) {
+                        // both chains' v_pre rows are complete (last SE layer): value heads of the whole unit,
+                        // hidden under chain 1's p_conv MMAs
+                        const int vc = et >> 8;
+                        value_phase(p, et, lane, b0 + (vc ? nbc0 : 0), vc ? nbc1 : nbc0, s_part + 1024 + vc * 260,
+                                    s_part + 640 + vc * 32);
+                    }
                     if (want_v) {
                         ptx::named_bar_sync(1, kEpi);
                         // fixed summation order over the four lane quarters keeps the result independent of batch composition

@@ -59,9 +59,12 @@ struct Params {
     long long* cyc;          // timing out
     int time_mode;           // 0: none, 1: plain loop, 2: collector fill/use pairs
     int time_iters;
+    int ld_mode;             // 0: loader warps idle, 8 / 16 / 32: tcgen05.ld width they loop on
+    int ld_iters;
+    int ld_gap;
 };
 
-__global__ void __launch_bounds__(128, 1) exp_kernel(Params p) {
+__global__ void __launch_bounds__(544, 1) exp_kernel(Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_tile = smem;                       // 128 rows x 128 B
@@ -70,13 +73,13 @@ __global__ void __launch_bounds__(128, 1) exp_kernel(Params p) {
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
     // software swizzle by ABSOLUTE shared address: 16-byte chunk index ^= (address >> 7) & 7
-    for (int i = tid; i < 128 * 64; i += 128) {
+    for (int i = tid; i < 128 * 64; i += blockDim.x) {
         const int row = i >> 6, ch = i & 63;
         const uint32_t base = ptx::smem_u32(a_tile) + row * 128;
         const uint32_t off = (((ch >> 3) ^ ((base >> 7) & 7)) << 4) + (ch & 7) * 2;
         *reinterpret_cast<__nv_bfloat16*>(a_tile + row * 128 + off) = p.A[i];
     }
-    for (int i = tid; i < kRows * 64; i += 128) {
+    for (int i = tid; i < kRows * 64; i += blockDim.x) {
         const int row = i >> 6, ch = i & 63;
         const uint32_t base = ptx::smem_u32(b_tile) + row * 128;
         const uint32_t off = (((ch >> 3) ^ ((base >> 7) & 7)) << 4) + (ch & 7) * 2;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(128, 1) exp_kernel(Params p) {
     ptx::mbar_wait(bar, phase);
     phase ^= 1;
     ptx::tc_fence_after();
-    for (int c0 = 0; c0 < 256; c0 += 32) {
+    if (warp < 4) for (int c0 = 0; c0 < 256; c0 += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
         ptx::tmem_ld_wait();
@@ -121,6 +124,31 @@ __global__ void __launch_bounds__(128, 1) exp_kernel(Params p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (p.ld_mode && warp >= 1) {
+        // loader warps: hammer the second accumulator's columns with tcgen05.ld while warp 0 issues MMAs
+        ptx::tc_fence_after();
+        const uint32_t ta = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 256;
+        uint32_t acc = 0;
+        for (int it = 0; it < p.ld_iters; ++it) {
+            if (p.ld_mode == 8) {
+                uint32_t r[8];
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 8) { ptx::tmem_ld_32x8(ta + ((it * 64 + c0) & 255), r); ptx::tmem_ld_wait(); acc += r[0] + r[7]; }
+            } else if (p.ld_mode == 16) {
+                uint32_t r[16];
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) { ptx::tmem_ld_32x16(ta + ((it * 64 + c0) & 255), r); ptx::tmem_ld_wait(); acc += r[0] + r[15]; }
+            } else {
+                uint32_t r[32];
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) { ptx::tmem_ld_32x32(ta + ((it * 64 + c0) & 255), r); ptx::tmem_ld_wait(); acc += r[0] + r[31]; }
+            }
+            // ~ the arithmetic an epilogue does between loads
+            for (int w = 0; w < p.ld_gap; ++w) acc = acc * 1664525u + 1013904223u;
+        }
+        if (acc == 0x12345678u) p.D[0] = 1.0f;
+        ptx::tc_fence_before();
+    }
     if (p.time_mode && warp == 0) {
         ptx::tc_fence_after();
         long long t0 = 0, t1 = 0;
@@ -197,7 +225,7 @@ int main() {
     CK(cudaFuncSetAttribute(exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     std::vector<float> hD(128 * 256);
     auto run = [&](int r0, int sbo_rows, int base_mode, int n, int dcol) {
-        Params p{dA, dB, dD, r0, sbo_rows, base_mode, n, dcol, dC, 0, 0};
+        Params p{dA, dB, dD, r0, sbo_rows, base_mode, n, dcol, dC, 0, 0, 0, 0, 0};
         exp_kernel<<<1, 128, smem>>>(p);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("r0=%d sbo=%d base=%d n=%d dcol=%d: CUDA error %s\n", r0, sbo_rows, base_mode, n, dcol, cudaGetErrorString(e)); exit(1); }
@@ -230,7 +258,7 @@ int main() {
         run(0, 10, base, 192, 16);
     }
     auto timeit = [&](int mode, int n, int r0 = 0, int sbo_rows = 8) {
-        Params p{dA, dB, dD, r0, sbo_rows, 0, n, 0, dC, mode, 500};
+        Params p{dA, dB, dD, r0, sbo_rows, 0, n, 0, dC, mode, 500, 0, 0, 0};
         exp_kernel<<<1, 128, smem>>>(p);
         CK(cudaDeviceSynchronize());
         long long c; CK(cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost));
@@ -238,6 +266,16 @@ int main() {
     };
     timeit(1, 256, 1, 8); timeit(1, 256, 4, 8); timeit(1, 256, 0, 9); timeit(1, 256, 1, 9); timeit(1, 224, 1, 9); timeit(1, 192, 1, 9);
     timeit(1, 128, 1, 9); timeit(1, 256, 0, 16); timeit(1, 256, 1, 16); timeit(1, 128, 1, 8);
+    auto timeld = [&](int ld_mode, int gap, int warps) {
+        // single accumulator MMA chain (mode 3 uses tmem columns [0,256)); loaders read columns [256,512)
+        Params p{dA, dB, dD, 0, 8, 0, 256, 0, dC, 3, 500, ld_mode, 1000, gap};
+        exp_kernel<<<1, 32 * (1 + warps), smem>>>(p);
+        CK(cudaDeviceSynchronize());
+        long long c; CK(cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost));
+        printf("ld_mode=%d gap=%d loader_warps=%d : %.1f cycles per MMA (N=256)\n", ld_mode, gap, warps, double(c) / (500 * 8));
+    };
+    timeld(0, 0, 16); timeld(8, 0, 16); timeld(16, 0, 16); timeld(32, 0, 16); timeld(8, 40, 16); timeld(16, 40, 16); timeld(32, 40, 16);
+    timeld(8, 200, 16); timeld(32, 200, 16); timeld(8, 0, 4); timeld(32, 0, 4);
     timeit(3, 256); timeit(3, 224); timeit(3, 192); timeit(3, 128); timeit(3, 64); timeit(4, 256); timeit(4, 192); timeit(5, 256); timeit(5, 192); timeit(5, 128);
     timeit(3, 256, 1, 9); timeit(4, 192, 1, 9);
     timeit(1, 256); timeit(2, 256); timeit(1, 224); timeit(2, 224); timeit(1, 192); timeit(1, 128);
