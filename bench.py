@@ -247,7 +247,11 @@ def main():
     ev.time_tower(3)
     tower_ms, n_tower = ev.time_tower(max(K // 2, 5))
     launch_ms = float(tower_ms.mean())
-    flops_launch = tower_flops_per_position(args.blocks, args.hidden) * B
+    single_launch = ev.launches_per_forward() == 1     # resident tower: planes, convs and both heads in one kernel
+    if single_launch:
+        flops_launch = FLOPS_PER_EVAL[(args.blocks, args.hidden)] * B
+    else:
+        flops_launch = tower_flops_per_position(args.blocks, args.hidden) * B
 
     # ---- end to end through the public C ABI with host buffers: every step copies boards / q / CSR
     # host->device and priors / values device->host inside the timed region.  Two evaluator handles
@@ -327,7 +331,9 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
                          "frac": achieved / burst, "traffic": traffic,
-                         "kernel": "tower_umma_kernel<%d> (whole conv tower, %d launch/step)" % (args.hidden, n_tower),
+                         "kernel": ("tower_r_umma_kernel<%s> (whole forward: planes, conv tower, policy and value heads; "
+                                    "%d launch/step)" % (args.dtype, n_tower)) if single_launch else
+                                   ("tower_umma_kernel<%d> (whole conv tower, %d launch/step)" % (args.hidden, n_tower)),
                          "flops_per_launch": flops_launch, "launch_ms": launch_ms,
                          "peak_source": "bf16_tflops (burst: the tower launch is timed alone with CUDA events) of "
                                         "MEASURED_PEAKS.json (%s); sustained figure %.1f -> frac %.3f" % (

@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     if (c == 0) { ptx::mbar_wait(&chain_ready[0], ready_ph0); ready_ph0 ^= 1; }
                     else { ptx::mbar_wait(&chain_ready[1], ready_ph1); ready_ph1 ^= 1; }
                     ptx::tc_fence_after();
+                    uint32_t w_spins = 0;      // debug: weight stages that were not ready when the issuer got to them
                     const uint32_t b_lo_c = b_lo0 + c * (Cfg::kChainBytes >> 4);
                     const uint32_t d_tmem = tmem_base + c * 256;
                     if (lane == 0) trace_stamp(p.trace, L * 2 + c, 2);
@@ -407,7 +408,8 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                         const uint32_t b_lo_t = b_lo_c + start_row * 8;      // 128-byte rows in 16-byte units
                         const uint32_t d_t = d_tmem + dcol;
                         for (int kc = 0; kc < kc_in; ++kc) {
-                            ptx::mbar_wait(w_full + ws, wph);
+                            if (p.trace) w_spins += ptx::mbar_wait_count(w_full + ws, wph) ? 1 : 0;
+                            else ptx::mbar_wait(w_full + ws, wph);
                             if (ptx::elect_one()) {
                                 const uint32_t a_lo = a_lo0 + ws * (Cfg::kWBytes >> 4);
                                 const uint32_t b_lo = b_lo_t + kc * (Cfg::kHalfBytes >> 4);
@@ -425,6 +427,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     if (ptx::elect_one()) ptx::umma_commit(&tmem_full[c]);
                     __syncwarp();
                     if (lane == 0) trace_stamp(p.trace, L * 2 + c, 3);
+                    if (lane == 0 && p.trace && blockIdx.x == 0) p.trace[(L * 2 + c) * 8 + 0] = w_spins;
                 }
             }
         }
@@ -443,6 +446,9 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
         const uint32_t kc_off = static_cast<uint32_t>(ch >> 6) * Cfg::kHalfBytes;
         const uint32_t cq = static_cast<uint32_t>((ch & 63) >> 3);
         const uint32_t cb2 = static_cast<uint32_t>(ch & 7) * 2;
+        const bool odd = (lane & 1) != 0;
+        // byte selectors that merge my half-word with my pair partner's, even channel in the low half
+        const uint32_t sel_lo = odd ? 0x1054u : 0x5410u, sel_hi = odd ? 0x3276u : 0x7632u;
         uint4* my_res = p.res_scratch + static_cast<size_t>(blockIdx.x) * Cfg::kScratchPerCta + bs * 8 * HID + ch;
         uint32_t full_ph = 0;                     // bit c: phase of tmem_full[c]
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
@@ -586,7 +592,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     const bool save_res = ly->save_res != 0 && !(p.dbg & 4);
                     const bool dump = want_v && p.dbg_backbone != nullptr;
                     if (active && !(p.dbg & 32)) {
-                        const uint32_t buf_ch = ptx::smem_u32(buf) + kc_off + cb2;
+                        const uint32_t buf_ch = ptx::smem_u32(buf) + kc_off + (cb2 & ~2u);   // the even channel of my pair
 #pragma unroll
                         for (int y = 0; y < 8; ++y) {
                             uint32_t r[8];
@@ -606,14 +612,21 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             uint32_t pk[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) pk[q] = pack_relu16<BF16>(v[2 * q], v[2 * q + 1]);
-                            // rows of group (y, bs): ((y + halo) * nb + bs) * 9 + 1 + x, swizzled by absolute address
-                            const uint32_t row0 = static_cast<uint32_t>(((y + halo) * nb + bs) * 9 + 1);
+                            // rows of group (y, bs): ((y + halo) * nb + bs) * 9 + 1 + x, swizzled by absolute address.
+                            // Lane pairs (channels ch, ch ^ 1) trade halves of the group so that every store is one
+                            // 32-bit word = two adjacent channels of one pixel: the even lane writes pixels 0..3, the
+                            // odd lane pixels 4..7 (rows 4 apart flip the swizzle half: no bank conflicts).
+                            const uint32_t row0 = static_cast<uint32_t>(((y + halo) * nb + bs) * 9 + 1) + (odd ? 4u : 0u);
+                            const uint32_t o0 = __shfl_xor_sync(0xffffffffu, odd ? pk[0] : pk[2], 1);
+                            const uint32_t o1 = __shfl_xor_sync(0xffffffffu, odd ? pk[1] : pk[3], 1);
+                            const uint32_t m0 = odd ? pk[2] : pk[0], m1 = odd ? pk[3] : pk[1];
+                            const uint32_t wd[4] = {__byte_perm(m0, o0, sel_lo), __byte_perm(m0, o0, sel_hi),
+                                                    __byte_perm(m1, o1, sel_lo), __byte_perm(m1, o1, sel_hi)};
 #pragma unroll
-                            for (int x = 0; x < 8; ++x) {
+                            for (int x = 0; x < 4; ++x) {
                                 const uint32_t row = row0 + x;
                                 const uint32_t addr = buf_ch + row * 128 + ((cq ^ (row & 7)) << 4);
-                                const uint16_t h16 = static_cast<uint16_t>((x & 1) ? (pk[x >> 1] >> 16) : (pk[x >> 1] & 0xFFFFu));
-                                asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(h16) : "memory");
+                                asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(wd[x]) : "memory");
                             }
                             if (save_res) __stcg(my_res + (c * 32 + y) * HID, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                             if (want_v) {

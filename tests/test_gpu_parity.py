@@ -225,6 +225,33 @@ def test_full_size_properties(cb, golden, positions, B):
     assert kl(np.exp(logp), pol).max() <= TOL_KL
 
 
+def test_ragged_batch_sizes_are_bit_identical_to_the_full_batch(cb, golden, positions):
+    """Every way the resident tower splits a batch into units / chains (1..4 boards per chain, with and
+    without y-halo rows, one or several units per SM) must give each position exactly the result it gets
+    inside the full batch: priors, v_logit and v_final bit for bit, for the first B positions."""
+    g, blob = golden("6x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    boards, idx, off, _ = positions
+    Bmax = 2500
+    q = O.static_q(boards[:Bmax])
+    pri, v, vf, k = ev.eval_leaves(boards[:Bmax], q, idx[:off[Bmax]], off[:Bmax + 1])
+    assert np.isfinite(pri).all() and np.isfinite(v).all()
+    for B in (1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 33, 147, 148, 149, 295, 296, 297, 443, 591, 1023, 1183, 1184,
+              1185, 1337, 2049):
+        p_b, v_b, vf_b, _ = ev.eval_leaves(boards[:B], q[:B], idx[:off[B]], off[:B + 1])
+        assert np.array_equal(v_b, v[:B]), "v_logit differs at batch %d" % B
+        assert np.array_equal(vf_b, vf[:B]), "v_final differs at batch %d" % B
+        assert np.array_equal(p_b, pri[:off[B]]), "priors differ at batch %d" % B
+    # compat path (full 4672-wide probabilities) on a ragged size
+    pol, v_c, _ = ev.predict_batch(boards[:37], q[:37])
+    assert np.array_equal(v_c, v[:37])
+    np.testing.assert_allclose(pol.sum(axis=1), 1.0, atol=1e-4)
+    for i in (0, 17, 36):
+        lo, hi = int(off[i]), int(off[i + 1])
+        want = pol[i][idx[lo:hi]]
+        np.testing.assert_allclose(pri[lo:hi], want / want.sum(), rtol=2e-6, atol=1e-9)
+
+
 def test_resident_path_equals_host_path(cb, golden, positions):
     g, blob = golden("6x128_B")
     ev = make_eval(cb, g, blob, "bf16")
