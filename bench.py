@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--selfplay-seconds", type=float, default=5.0, help="0 disables the self-play section")
+    ap.add_argument("--selfplay-seconds", type=float, default=3.0, help="seconds per self-play pool shape (two are run); 0 disables the section")
     ap.add_argument("--selfplay-games", type=int, default=1024)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -285,24 +285,31 @@ def main():
     h2d = int(boards.nbytes + q.nbytes + idx.nbytes + off.nbytes)
     d2h = int(out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes)
 
-    # ---- self-play pool on this GPU (config 3 shape: 200 sims/move, 1024 concurrent games, vanilla mode)
-    sp = None
+    # ---- self-play pool on this GPU (config 3 shape: 200 sims/move, 1024 concurrent games, vanilla mode).
+    # Two half-pools of 512 games, each served by its own evaluator handle, so the host tree work of one half
+    # and the copies of its call run under the other half's kernel; the 2048-game pool (two full 1024 batches)
+    # is measured beside it.
+    sp = sp_big = None
+    nthreads = max(1, (os.cpu_count() or 1) // world - 2)
     if args.selfplay_seconds > 0:
-        ev2.close()
-        nthreads = max(1, (os.cpu_count() or 1) // world - 2)
         barrier()
         sp = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=1 + rank,
-                         max_seconds=args.selfplay_seconds, threads=nthreads)
+                         max_seconds=args.selfplay_seconds, threads=nthreads, pipeline=2, aux=ev2)
         barrier()
+        sp_big = ev.selfplay(games=2 * args.selfplay_games, sims_per_move=200, material_on=False, seed=101 + rank,
+                             max_seconds=args.selfplay_seconds, threads=nthreads, pipeline=2, aux=ev2)
+        barrier()
+    ev2.close()
 
     # ---- max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3, launch_ms, e2e_sync_s * 1e3, sp["seconds"] if sp else 0.0],
-                     dtype=torch.float64, device="cuda")
-    tot = torch.tensor([sp["sims"] if sp else 0, sp["nn_evals"] if sp else 0], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, launch_ms, e2e_sync_s * 1e3, sp["seconds"] if sp else 0.0,
+                      sp_big["seconds"] if sp_big else 0.0], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([sp["sims"] if sp else 0, sp["nn_evals"] if sp else 0, sp_big["sims"] if sp_big else 0],
+                       dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds = [float(x) for x in t.tolist()]
+    dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds, sp_big_seconds = [float(x) for x in t.tolist()]
     value = world * B * K / (dev_ms * 1e-3)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     # off the hot path: the one exchange the multi-GPU design has (training-sample gather over NCCL)
@@ -345,10 +352,12 @@ def main():
             line["selfplay"] = {"sims_per_s": float(tot[0].item()) / sp_seconds,
                                 "nn_evals_per_s": float(tot[1].item()) / sp_seconds,
                                 "games_per_gpu": args.selfplay_games, "sims_per_move": 200, "mode": "vanilla (config 5 rules: "
-                                "Tier 1 off, material off), one leaf in flight per game, one eval batch per step",
-                                "host_threads_per_gpu": max(1, (os.cpu_count() or 1) // world - 2),
+                                "Tier 1 off, material off), one leaf in flight per game; two half-pools, each with its own "
+                                "evaluator handle (tree work and copies of one half under the other half's kernel)",
+                                "host_threads_per_gpu": nthreads,
                                 "seconds": sp_seconds, "mean_batch": sp["mean_batch"],
-                                "eval_fraction": sp["eval_seconds"] / max(sp["seconds"], 1e-9)}
+                                "eval_fraction": sp["eval_seconds"] / max(sp["seconds"], 1e-9),
+                                "sims_per_s_2048_games": float(tot[2].item()) / max(sp_big_seconds, 1e-9)}
         if gathered is not None:
             line["nccl_sample_gather_records"] = gathered
         if world == 1 and not args.no_cpu_baseline:

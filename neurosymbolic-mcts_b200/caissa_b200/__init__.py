@@ -33,7 +33,7 @@ class SelfplayConfig(ctypes.Structure):
                 ("material_on", ctypes.c_int), ("koth", ctypes.c_int), ("threads", ctypes.c_int),
                 ("c_puct", ctypes.c_float), ("explore_base", ctypes.c_float), ("seed", ctypes.c_uint64),
                 ("max_sims", ctypes.c_longlong), ("max_games", ctypes.c_longlong), ("max_seconds", ctypes.c_double),
-                ("sample_path", ctypes.c_char_p), ("pipeline", ctypes.c_int)]
+                ("sample_path", ctypes.c_char_p), ("pipeline", ctypes.c_int), ("aux_handle", ctypes.c_void_p)]
 
 
 class SelfplayStats(ctypes.Structure):
@@ -261,11 +261,12 @@ class Evaluator:
 
     def selfplay(self, games=1024, sims_per_move=200, max_plies=200, material_on=False, koth=False, threads=0,
                  c_puct=1.414, explore_base=0.80, seed=1, max_sims=0, max_games=0, max_seconds=0.0, sample_path=None,
-                 pipeline=1):
-        """Run the self-play pool on this evaluator; returns the stats as a dict."""
+                 pipeline=1, aux=None):
+        """Run the self-play pool on this evaluator; returns the stats as a dict.  `aux`: a second Evaluator
+        with the same weights that serves the second half-pool in pipeline mode 2."""
         cfg = SelfplayConfig(games, sims_per_move, max_plies, int(material_on), int(koth), threads, c_puct,
                              explore_base, seed, max_sims, max_games, max_seconds,
-                             sample_path.encode() if sample_path else None, pipeline)
+                             sample_path.encode() if sample_path else None, pipeline, aux._h if aux is not None else None)
         st = SelfplayStats()
         self._check(self._L.cb_selfplay_run(self._h, ctypes.byref(cfg), ctypes.byref(st)))
         return {n: getattr(st, n) for n, _ in SelfplayStats._fields_}

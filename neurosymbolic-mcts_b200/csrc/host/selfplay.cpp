@@ -317,7 +317,8 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
     if (nthreads > G) nthreads = G;
 
     const int halves = (cfg->pipeline >= 2 && G >= 2) ? 2 : 1;
-    if (halves == 2 && nthreads > 2) nthreads -= 1;   // leave a core to the evaluation thread
+    cb_handle* aux = (halves == 2 && cfg->aux_handle && cb_is_available(cfg->aux_handle)) ? cfg->aux_handle : nullptr;
+    if (halves == 2 && nthreads > 2) nthreads -= aux ? 2 : 1;   // leave cores to the evaluation thread(s)
 
     std::vector<Game> games(G);
     for (int i = 0; i < G; ++i) games[i].reset(cfg->seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * (uint64_t)(i + 1));
@@ -443,10 +444,10 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
     long long sims = 0, evals = 0, steps = 0;
     int failed = CB_OK;
 
-    auto eval_job = [&](EvalJob& j) {
+    auto eval_job = [&](EvalJob& j, cb_handle* eh) {
         j.rc = CB_OK;
         if (j.nb > 0)
-            j.rc = cb_eval_leaves(h, j.boards.data(), j.q.data(), j.nb, cfg->material_on, j.move_idx.data(), j.move_off.data(),
+            j.rc = cb_eval_leaves(eh, j.boards.data(), j.q.data(), j.nb, cfg->material_on, j.move_idx.data(), j.move_off.data(),
                                   j.priors.data(), j.v_logit.data(), j.v_final.data(), j.kk.data());
     };
     // phase A for one half-pool: select leaves, pack the evaluation batch
@@ -501,7 +502,7 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
             const double t0 = now_s();
             select_and_pack(0);
             const double t1 = now_s();
-            eval_job(jobs[0]);
+            eval_job(jobs[0], h);
             failed = jobs[0].rc;
             const double t2 = now_s();
             if (failed == CB_OK) expand_half(0);
@@ -511,9 +512,13 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
         }
     } else {
         // software pipeline: the tree work of one half runs while the other half is on the GPU
+        // One evaluation thread serving both halves in turn, or — with an auxiliary handle (same weights,
+        // own stream and buffers) — one thread and handle per half, so that the copies / synchronisation of
+        // one half's call overlap the other half's kernel on the GPU.
         std::atomic<bool> eval_stop(false);
-        std::thread eval_thread([&] {
-            int next = 0;
+        std::mutex eval_mu;
+        auto serve = [&](int first, int stride, cb_handle* eh) {
+            int next = first;
             for (;;) {
                 EvalJob& j = jobs[next];
                 int spins = 0;
@@ -523,12 +528,22 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
                     if (++spins > 4096) { std::this_thread::yield(); spins = 0; }
                 }
                 const double t0 = now_s();
-                eval_job(j);
-                eval_s += now_s() - t0;
+                eval_job(j, eh);
+                {
+                    std::lock_guard<std::mutex> l(eval_mu);
+                    eval_s += now_s() - t0;
+                }
                 j.state.store(2, std::memory_order_release);
-                next ^= 1;
+                next = (next + stride) & 1;
             }
-        });
+        };
+        std::vector<std::thread> eval_threads;
+        if (aux) {
+            eval_threads.emplace_back([&] { serve(0, 0, h); });
+            eval_threads.emplace_back([&] { serve(1, 0, aux); });
+        } else {
+            eval_threads.emplace_back([&] { serve(0, 1, h); });
+        }
         auto submit = [&](int hf) {
             const double t0 = now_s();
             select_and_pack(hf);
@@ -556,7 +571,7 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
         complete(cur);  // drain the last submitted half
         half_steps++;
         eval_stop.store(true);
-        eval_thread.join();
+        for (auto& t : eval_threads) t.join();
         steps = half_steps / 2;  // a step = one simulation for every game of the pool
     }
     if (failed != CB_OK) {

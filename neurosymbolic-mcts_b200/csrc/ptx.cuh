@@ -71,15 +71,6 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
     }
 }
 
-// Same, returning the number of failed polls (debug: who is waiting on whom).
-__device__ __forceinline__ uint32_t mbar_wait_count(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
-    }
-    return spins;
-}
-
 // ---------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -1,5 +1,7 @@
-// tower_r_umma.cuh — fused persistent conv tower for the 128-channel net with the activations
-// RESIDENT IN SHARED MEMORY between layers (no global round trip, no halo'd slab reloads).
+// tower_r_umma.cuh — the WHOLE leaf evaluation of the 128-channel net as ONE persistent kernel:
+// planes from packed bitboards -> 14 fused 3x3 convolutions (BN, ReLU, squeeze-excite, residual) ->
+// policy head (1x1 conv, softmax over the legal moves) and value head (tanh(v_logit + k dM)), with the
+// activations RESIDENT IN SHARED MEMORY between layers (no global round trip, no halo'd slab reloads).
 //
 //     D^T[c_out = 128 lanes][pixels = N columns] += W_tap[c_out][c_in] * X_tap[pixels][c_in]^T
 //
@@ -19,15 +21,22 @@
 // count (56 nb is not a legal N) keeps two zero y-halo group rows and uses N = 64 nb for every tap.
 //
 // The epilogue writes layer L's 16-bit output straight back into the chain's buffer (all MMAs of
-// the layer have completed by then), which makes it the B operand of layer L + 1.  Only the weights
-// stream from L2 (TMA ring, 16 KB per tap and 64-channel half); the block input needed by the
-// residual add is parked by each epilogue thread in a thread-private global scratch (coalesced
-// 16-byte stores, read back by the same thread), and the first layer's input planes are encoded
-// from the packed bitboards in-kernel (src/tensor.rs:21-77).  The last layer (p_conv) is stored
-// with TMA as act[y][board][9 x-slots][C] (pad row included) for the policy kernel.
+// the layer have completed by then), which makes it the B operand of layer L + 1, and presets the
+// accumulator with layer L + 1's folded-BN bias (tcgen05.st) so that every MMA accumulates.  Only the
+// weights stream from L2 (TMA ring, 16 KB per tap and 64-channel half); the block input needed by
+// the residual add is parked by each epilogue thread in a thread-private global scratch (coalesced
+// 16-byte stores, read back by the same thread); the first layer's input planes are encoded from
+// the packed bitboards in-kernel (src/tensor.rs:21-77).  The p_head 1x1 conv is a 15th, one-tap
+// "layer" on the same buffers; its epilogue is heads_epilogue() below, the value head is
+// value_phase().  Results do not depend on how a batch is split into units (tests: ragged sizes
+// are bit-identical to the full batch).
 //
-// Roles (576 threads): warp 0 weight producer, warp 1 MMA issuer, 16 epilogue warps (one team
-// alternating between the chains; a thread owns ONE output channel = TMEM lane).
+// Roles (576 threads): warp 0 weight producer, warp 1 MMA issuer (warp-uniform control flow: UTCHMMA
+// takes descriptors from uniform registers), 16 epilogue warps = 4 board teams of 128 threads; a
+// thread owns ONE output channel (TMEM lane) of ONE board (8 column groups of 8 pixels).
+// Work-item order on every role: for layer: for chain; chain c's epilogue runs under chain 1 - c's MMAs.
+// mbarriers: w_full / w_empty (weight ring), tmem_full[c] (MMA -> epilogue), chain_ready[c] (epilogue ->
+// MMA: buffer written, accumulator preset).  All waits are bounded (a protocol bug traps).
 #pragma once
 #include "kernels_simt.cuh"
 #include "tower_t_umma.cuh"
@@ -384,7 +393,6 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     if (c == 0) { ptx::mbar_wait(&chain_ready[0], ready_ph0); ready_ph0 ^= 1; }
                     else { ptx::mbar_wait(&chain_ready[1], ready_ph1); ready_ph1 ^= 1; }
                     ptx::tc_fence_after();
-                    uint32_t w_spins = 0;      // debug: weight stages that were not ready when the issuer got to them
                     const uint32_t b_lo_c = b_lo0 + c * (Cfg::kChainBytes >> 4);
                     const uint32_t d_tmem = tmem_base + c * 256;
                     if (lane == 0) trace_stamp(p.trace, L * 2 + c, 2);
@@ -408,8 +416,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                         const uint32_t b_lo_t = b_lo_c + start_row * 8;      // 128-byte rows in 16-byte units
                         const uint32_t d_t = d_tmem + dcol;
                         for (int kc = 0; kc < kc_in; ++kc) {
-                            if (p.trace) w_spins += ptx::mbar_wait_count(w_full + ws, wph) ? 1 : 0;
-                            else ptx::mbar_wait(w_full + ws, wph);
+                            ptx::mbar_wait(w_full + ws, wph);
                             if (ptx::elect_one()) {
                                 const uint32_t a_lo = a_lo0 + ws * (Cfg::kWBytes >> 4);
                                 const uint32_t b_lo = b_lo_t + kc * (Cfg::kHalfBytes >> 4);
@@ -427,7 +434,6 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     if (ptx::elect_one()) ptx::umma_commit(&tmem_full[c]);
                     __syncwarp();
                     if (lane == 0) trace_stamp(p.trace, L * 2 + c, 3);
-                    if (lane == 0 && p.trace && blockIdx.x == 0) p.trace[(L * 2 + c) * 8 + 0] = w_spins;
                 }
             }
         }

@@ -13,8 +13,6 @@ ev.load_weights(W.flatten(W.make_weights(6, 128, 1803, "B"), 6, 128))
 ev.stage_leaves(boards, q, idx, off)
 ev.time_resident(3)
 tr = ev.debug_tower_trace().astype(np.float64)
-print("weight stages not ready when the MMA issuer reached them, per item:", " ".join("%d" % w for w in tr[:, 0]))
-tr[:, 0] = 0
 t0 = tr[tr > 0].min()
 us = (tr - t0) / 1965.0
 
