@@ -190,7 +190,8 @@ typedef struct cb_selfplay_config {
     double max_seconds;   /* wall-clock bound (0 = unlimited) */
     const char* sample_path; /* nullable: append finished games as 5763-f32 records (src/training_data.rs:24-60) */
     int pipeline;         /* 0/1: lock step (select, evaluate, expand); 2: two half-pools, the tree work of one
-                             half runs on the host while the other half's leaves are on the GPU */
+                             half runs on the host while the other half's leaves are on the GPU; 3: tree
+                             operations on the device (cb_selfplay_device) */
     cb_handle* aux_handle; /* nullable, pipeline 2 only: a second evaluator with the same weights (own stream and
                              buffers) that serves the second half-pool, so one half's copies and synchronisation
                              overlap the other half's kernel (the reference's multi-instance use) */
@@ -204,6 +205,12 @@ typedef struct cb_selfplay_stats {
 } cb_selfplay_stats;
 
 int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out);
+/* The same pool with the tree operations on the device (cb_selfplay_run dispatches here
+ * for pipeline = 3): select (src/mcts/selection.rs:65-73,254-273), expand (:82-104), backup
+ * (src/mcts/node.rs:403-424), move choice / tree reuse / game end (src/bin/self_play.rs:300-388) run as two
+ * kernels around the forward kernel, one warp per game; leaves and priors never cross PCIe.  Same statistics;
+ * sample files are not written in this mode (sample_path must be NULL). */
+int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out);
 
 int         cb_get_timing(const cb_handle* h, cb_timing* out);
 void        cb_reset_timing(cb_handle* h);

@@ -77,6 +77,7 @@ SIGNATURES = {
     "cb_chess_make_move": (ctypes.c_int, [_VP, ctypes.c_uint16, _VP]),
     "cb_chess_perft": (ctypes.c_uint64, [_VP, ctypes.c_int]),
     "cb_selfplay_run": (ctypes.c_int, [_VP, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
+    "cb_selfplay_device": (ctypes.c_int, [_VP, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
     "cb_launches_per_forward": (ctypes.c_int, [_VP]),
     "cb_get_timing": (ctypes.c_int, [_VP, ctypes.POINTER(CbTiming)]),
     "cb_reset_timing": (None, [_VP]),

@@ -11,6 +11,7 @@
 
 #include <stdlib.h>
 
+#include <chrono>
 #include <map>
 #include <new>
 #include <string>
@@ -23,6 +24,7 @@
 #include "tower_umma.cuh"
 #include "tower_t_umma.cuh"
 #include "tower_r_umma.cuh"
+#include "mcts_device.cuh"
 
 namespace {
 
@@ -120,6 +122,7 @@ struct cb_handle {
     unsigned long long* d_cta_times = nullptr;   // set only inside cb_debug_cta_times
     bool tower_r_ready = false;
     bool use_resident = true;
+    bool chess_tables_uploaded = false;  // __constant__ attack tables of the device-side tree kernels
 
     // pinned staging
     cb_board* h_boards = nullptr;
@@ -1317,6 +1320,151 @@ int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches) {
     if (!h) return CB_EINVAL;
     drop_graphs(h);
     h->layer_limit = n_conv_launches;
+    return CB_OK;
+}
+
+// Self-play with the tree operations on the device (cb_selfplay_run, pipeline = 3): per simulation step one
+// CUDA graph node each for select, the forward kernel and expand / play; the host only replays the graph
+// and reads the counters.
+int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
+    if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
+    if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
+    if (cfg->sample_path) return fail(h, CB_EINVAL, "device-side self-play does not write sample files yet");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    const int G = cfg->games;
+    int rc = ensure_capacity(h, G);
+    if (rc) return rc;
+    if (fused_kind(h) != 3) return fail(h, CB_ESTATE, "device-side self-play needs the resident single-launch forward (128-channel net, 16-bit mode)");
+    memset(out, 0, sizeof(*out));
+    if (!h->chess_tables_uploaded) {
+        CB_CUDA(h, cudaMemcpyToSymbol(cbchess::d_chess_tables, &cbchess::host_tables(), sizeof(cbchess::Tables)));
+        h->chess_tables_uploaded = true;
+    }
+    MctsParams mp = {};
+    mp.G = G;
+    mp.sims_per_move = cfg->sims_per_move;
+    mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
+    mp.material_on = cfg->material_on;
+    mp.koth = cfg->koth;
+    mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
+    mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
+    mp.node_cap = 32768;
+    mp.seed = cfg->seed;
+    std::vector<void*> owned;
+    auto dalloc = [&](void** ptr, size_t bytes) -> int {
+        CB_CUDA(h, cudaMalloc(ptr, bytes));
+        owned.push_back(*ptr);
+        return CB_OK;
+    };
+    auto release = [&] { for (void* q : owned) cudaFree(q); };
+    if ((rc = dalloc((void**)&mp.root, (size_t)G * sizeof(cb_board))) ||
+        (rc = dalloc((void**)&mp.nodes, (size_t)G * 2 * mp.node_cap * sizeof(MNode))) ||
+        (rc = dalloc((void**)&mp.n_nodes, (size_t)G * 4)) || (rc = dalloc((void**)&mp.arena, (size_t)G)) ||
+        (rc = dalloc((void**)&mp.history, (size_t)G * kMctsHist * 8)) || (rc = dalloc((void**)&mp.hist_n, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.rng, (size_t)G * 8)) || (rc = dalloc((void**)&mp.ply, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.sims_done, (size_t)G * 4)) || (rc = dalloc((void**)&mp.samples_in_game, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.path, (size_t)G * kMctsMaxDepth * 4)) || (rc = dalloc((void**)&mp.path_n, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.wants_eval, (size_t)G)) || (rc = dalloc((void**)&mp.leaf_moves, (size_t)G * CB_MAX_MOVES * 2)) ||
+        (rc = dalloc((void**)&mp.eval_cnt, (size_t)G * 2)) || (rc = dalloc((void**)&mp.stats, MS_COUNT * 8))) {
+        release();
+        return rc;
+    }
+    mp.eval_boards = h->d_boards;
+    mp.eval_q = h->d_q;
+    mp.eval_idx = h->d_move_idx;
+    mp.priors = h->d_priors;
+    mp.v_final = h->d_vfinal;
+    cudaMemsetAsync(mp.stats, 0, MS_COUNT * 8, h->stream);
+    cudaMemsetAsync(h->d_boards, 0, (size_t)G * sizeof(cb_board), h->stream);
+    mcts_init_kernel<<<(G + 127) / 128, 128, 0, h->stream>>>(mp);
+    PolicyOut po = {};
+    po.move_idx = h->d_move_idx;
+    po.priors = h->d_priors;
+    po.move_cnt = mp.eval_cnt;
+    const int grid = (G + kMctsWarps - 1) / kMctsWarps;
+    auto step = [&]() -> int {
+        mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        int r = launch_tower_r(h, G, po, cfg->material_on, true);
+        if (r) return r;
+        mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        return CB_OK;
+    };
+    // one eager step (sets the kernels' attributes outside capture), timed per phase
+    cudaEvent_t e[4];
+    for (auto& x : e) cudaEventCreate(&x);
+    cudaEventRecord(e[0], h->stream);
+    mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+    cudaEventRecord(e[1], h->stream);
+    rc = launch_tower_r(h, G, po, cfg->material_on, true);
+    cudaEventRecord(e[2], h->stream);
+    mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+    cudaEventRecord(e[3], h->stream);
+    cudaError_t ce = cudaStreamSynchronize(h->stream);
+    float ms_sel = 0, ms_fwd = 0, ms_exp = 0;
+    cudaEventElapsedTime(&ms_sel, e[0], e[1]);
+    cudaEventElapsedTime(&ms_fwd, e[1], e[2]);
+    cudaEventElapsedTime(&ms_exp, e[2], e[3]);
+    for (auto& x : e) cudaEventDestroy(x);
+    if (rc || ce != cudaSuccess) {
+        release();
+        if (rc) return rc;
+        return fail(h, CB_ECUDA, std::string("device self-play step: ") + cudaGetErrorString(ce));
+    }
+    constexpr int kStepsPerGraph = 8;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    CB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < kStepsPerGraph && !rc; ++i) rc = step();
+    ce = cudaStreamEndCapture(h->stream, &graph);
+    if (!rc && ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc || ce != cudaSuccess) {
+        release();
+        if (rc) return rc;
+        return fail(h, CB_ECUDA, std::string("device self-play graph: ") + cudaGetErrorString(ce));
+    }
+    unsigned long long st[MS_COUNT] = {0};
+    long long steps = 1;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    for (;;) {
+        ce = cudaMemcpyAsync(st, mp.stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+        if (ce != cudaSuccess) break;
+        const long long sims = steps * G;
+        if (cfg->max_sims > 0 && sims >= cfg->max_sims) break;
+        if (cfg->max_games > 0 && (long long)st[MS_GAMES] >= cfg->max_games) break;
+        if (cfg->max_seconds > 0 && elapsed() >= cfg->max_seconds) break;
+        if (cfg->max_sims > 0 && (cfg->max_sims - sims) < (long long)kStepsPerGraph * G) {
+            // finish the simulation budget exactly with eager steps
+            if ((rc = step())) break;
+            steps += 1;
+        } else {
+            if ((ce = cudaGraphLaunch(gexec, h->stream)) != cudaSuccess) break;
+            steps += kStepsPerGraph;
+        }
+    }
+    const double secs = elapsed();
+    cudaGraphExecDestroy(gexec);
+    release();
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(h, CB_ECUDA, std::string("device self-play: ") + cudaGetErrorString(ce));
+    out->sims = steps * G;
+    out->nn_evals = (long long)st[MS_EVALS];
+    out->terminal_hits = (long long)st[MS_TERMINAL];
+    out->moves = (long long)st[MS_MOVES];
+    out->games_finished = (long long)st[MS_GAMES];
+    out->samples = (long long)st[MS_SAMPLES];
+    out->steps = steps;
+    out->white_wins = (long long)st[MS_WWINS];
+    out->black_wins = (long long)st[MS_BWINS];
+    out->draws = (long long)st[MS_DRAWS];
+    out->seconds = secs;
+    // split of a step measured once with CUDA events: forward kernel vs the two tree kernels
+    const double tot = (double)ms_sel + ms_fwd + ms_exp;
+    out->eval_seconds = tot > 0 ? secs * ms_fwd / tot : 0.0;
+    out->tree_seconds = tot > 0 ? secs * (ms_sel + ms_exp) / tot : 0.0;
+    out->mean_batch = steps ? (double)out->nn_evals / (double)steps : 0.0;
     return CB_OK;
 }
 

@@ -12,11 +12,17 @@
 
 namespace cbchess {
 
+#if defined(__CUDACC__)
+#define CB_HDI __host__ __device__ inline
+#else
+#define CB_HDI inline
+#endif
+
 typedef uint16_t Move;  // from | to << 6 | promo << 12   (promo: 0 none, 1 N, 2 B, 3 R, 4 Q)
-inline int mv_from(Move m) { return m & 63; }
-inline int mv_to(Move m) { return (m >> 6) & 63; }
-inline int mv_promo(Move m) { return (m >> 12) & 7; }
-inline Move make_mv(int f, int t, int p) { return (Move)(f | (t << 6) | (p << 12)); }
+CB_HDI int mv_from(Move m) { return m & 63; }
+CB_HDI int mv_to(Move m) { return (m >> 6) & 63; }
+CB_HDI int mv_promo(Move m) { return (m >> 12) & 7; }
+CB_HDI Move make_mv(int f, int t, int p) { return (Move)(f | (t << 6) | (p << 12)); }
 
 enum { PAWN = 0, KNIGHT, BISHOP, ROOK, QUEEN, KING };
 enum { WK = 1, WQ = 2, BK = 4, BQ = 8 };

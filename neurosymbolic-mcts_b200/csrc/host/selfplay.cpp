@@ -306,6 +306,7 @@ uint64_t cb_chess_perft(const cb_board* b, int depth) { return b ? perft(*b, dep
 int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
     if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
     if (!cb_is_available(h)) return CB_ESTATE;
+    if (cfg->pipeline == 3) return cb_selfplay_device(h, cfg, out);
     memset(out, 0, sizeof(*out));
     const int G = cfg->games;
     const int max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;

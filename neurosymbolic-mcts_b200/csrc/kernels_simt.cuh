@@ -216,6 +216,8 @@ struct PolicyOut {
     const uint16_t* move_idx;  // CSR of legal policy indices or nullptr
     const uint32_t* move_off;  // [B+1]
     float* priors;             // [move_off[B]]
+    const uint16_t* move_cnt;  // nullable: fixed-stride lists instead of CSR (board b: move_idx[b*256 .. +move_cnt[b]),
+                               // priors at the same offsets) — the layout the device-side tree kernels write
 };
 
 constexpr int kPolicyThreads = 320;  // 4 pixel groups x 73 planes = 292 active in the GEMV phase

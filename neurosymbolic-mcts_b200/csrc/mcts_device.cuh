@@ -1,0 +1,432 @@
+// mcts_device.cuh — the tree operations of the self-play pool ON THE DEVICE: one warp
+// per game walks its tree with PUCT, generates the leaf's legal moves and writes the leaf straight into the
+// evaluator's input block; after the forward kernel a second kernel expands the leaf with the priors,
+// backs the value up and — when the simulation budget of the move is spent — picks and plays the move,
+// re-roots the tree and detects the end of the game.  No host work and no PCIe traffic per simulation.
+//
+// Semantics are those of the host driver (host/selfplay.cpp), statement for statement, which follow
+//   selection        src/mcts/selection.rs:65-73 (every root child once), :254-273 (PUCT, sqrt(max(N,1)), Q = 0 unvisited)
+//   expansion        src/mcts/selection.rs:82-104, terminal test src/mcts/node.rs:162-177
+//   backup           src/mcts/node.rs:403-424 (sign flips every ply)
+//   move choice      src/bin/self_play.rs:300-356 (proportional to visits-1 with probability 0.8^(move-1), else greedy)
+//   tree reuse / game end  src/bin/self_play.rs:358-388
+// and the chess rules are the same inline code (host/chess_rules.hpp).  All floating-point steps use
+// explicitly rounded single operations (no FMA contraction), so for identical evaluator outputs the
+// device trees are bit-identical to the host driver's (tests/test_gpu_parity.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "host/chess_rules.hpp"
+#include "pesto_tables.h"
+
+namespace cb {
+
+using cbchess::Move;
+
+struct MNode {
+    uint32_t first_child;
+    uint32_t visits;
+    float value_sum;   // from the point of view of the player who moved INTO this node
+    float prior;
+    uint16_t n_children;
+    uint16_t move;
+    uint8_t state;     // 0 unexpanded, 1 expanded, 2 terminal
+    int8_t term_value; // value for the side to move at a terminal node (-1 mated, 0 stalemate)
+    uint16_t pad;
+};
+static_assert(sizeof(MNode) == 24, "node layout");
+
+constexpr int kMctsHist = 128;      // position keys since the last irreversible move (halfmove clock <= 100)
+constexpr int kMctsMaxDepth = 512;  // longest root-to-leaf path kept
+constexpr int kMctsWarps = 4;       // games per CTA
+
+enum { MS_EVALS = 0, MS_TERMINAL, MS_MOVES, MS_GAMES, MS_SAMPLES, MS_WWINS, MS_BWINS, MS_DRAWS, MS_OVERFLOW, MS_COUNT = 16 };
+
+struct MctsParams {
+    int G, sims_per_move, max_plies, material_on, koth;
+    float c_puct;
+    double explore_base;
+    uint32_t node_cap;              // nodes per arena
+    // per-game state
+    cb_board* root;                 // [G]
+    MNode* nodes;                   // [G][2 arenas][node_cap]
+    uint32_t* n_nodes;              // [G]
+    uint8_t* arena;                 // [G] which arena holds the tree
+    uint64_t* history;              // [G][kMctsHist]
+    int* hist_n;                    // [G]
+    uint64_t* rng;                  // [G]
+    int* ply;                       // [G]
+    int* sims_done;                 // [G]
+    int* samples_in_game;           // [G]
+    // per-step scratch
+    uint32_t* path;                 // [G][kMctsMaxDepth]
+    int* path_n;                    // [G]
+    uint8_t* wants_eval;            // [G]
+    uint16_t* leaf_moves;           // [G][CB_MAX_MOVES]
+    // evaluator input / output block (slot = game)
+    cb_board* eval_boards;          // [G]
+    float* eval_q;                  // [G]
+    uint16_t* eval_idx;             // [G][CB_MAX_MOVES] policy indices of the leaf's legal moves
+    uint16_t* eval_cnt;             // [G]
+    const float* priors;            // [G][CB_MAX_MOVES]
+    const float* v_final;           // [G]
+    unsigned long long* stats;      // [MS_COUNT]
+    uint64_t seed;
+};
+
+__device__ __forceinline__ uint64_t rng_next(uint64_t& s) {
+    s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+    return s * 0x2545F4914F6CDD1Dull;
+}
+__device__ __forceinline__ double rng_uniform(uint64_t& s) { return (double)(rng_next(s) >> 11) * (1.0 / 9007199254740992.0); }
+
+__device__ __forceinline__ int static_pesto_cp_dev(const cb_board& b) {   // src/eval.rs:93-122
+    int mg[2] = {0, 0}, eg[2] = {0, 0}, phase = 0;
+    for (int c = 0; c < 2; ++c)
+        for (int pt = 0; pt < 6; ++pt)
+            for (uint64_t bb = b.pieces[c * 6 + pt]; bb; bb &= bb - 1) {
+                const int sq = cbchess::lsb(bb), t = c == 0 ? (sq ^ 56) : sq;
+                mg[c] += CB_MG_VALUE[pt] + CB_MG_PST[pt][t];
+                eg[c] += CB_EG_VALUE[pt] + CB_EG_PST[pt][t];
+                phase += CB_PHASE_INC[pt];
+            }
+    const int mgp = phase < 24 ? phase : 24;
+    const int score = ((mg[0] - mg[1]) * mgp + (eg[0] - eg[1]) * (24 - mgp)) / 24;
+    return b.w_to_move ? score : -score;
+}
+
+// Start a fresh game in slot g (lane 0 only).
+__device__ __forceinline__ void mcts_reset_game(const MctsParams& p, int g, uint64_t seed) {
+    cb_board b;
+    memset(&b, 0, sizeof(b));
+    const uint64_t back[6] = {0, 0x42, 0x24, 0x81, 0x08, 0x10};
+    b.pieces[cbchess::PAWN] = 0xFF00ull;
+    b.pieces[6 + cbchess::PAWN] = 0xFFull << 48;
+    for (int q = 1; q < 6; ++q) {
+        b.pieces[q] = back[q];
+        b.pieces[6 + q] = back[q] << 56;
+    }
+    b.occ[0] = 0xFFFFull;
+    b.occ[1] = 0xFFFFull << 48;
+    b.w_to_move = 1;
+    b.en_passant = 0xFF;
+    b.castling = cbchess::WK | cbchess::WQ | cbchess::BK | cbchess::BQ;
+    p.root[g] = b;
+    p.arena[g] = 0;
+    MNode z;
+    memset(&z, 0, sizeof(z));
+    p.nodes[(size_t)g * 2 * p.node_cap] = z;
+    p.n_nodes[g] = 1;
+    p.history[(size_t)g * kMctsHist] = cbchess::position_key_hd(b);
+    p.hist_n[g] = 1;
+    p.rng[g] = seed | 1;
+    p.ply[g] = 0;
+    p.sims_done[g] = 0;
+    p.samples_in_game[g] = 0;
+}
+
+__global__ void mcts_init_kernel(const MctsParams p) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.G) return;
+    mcts_reset_game(p, g, p.seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * (uint64_t)(g + 1));
+    p.wants_eval[g] = 0;
+    p.eval_cnt[g] = 0;
+    p.path_n[g] = 0;
+}
+
+// value backed up along the stored path, sign flipping every ply (lane 0)
+__device__ __forceinline__ void mcts_backup(MNode* nodes, const uint32_t* path, int n, float val) {
+    for (int i = n - 1; i >= 0; --i) {
+        val = -val;
+        MNode& nd = nodes[path[i]];
+        nd.value_sum = __fadd_rn(nd.value_sum, val);
+        nd.visits++;
+    }
+}
+
+// Legal moves of `board` in generation order: lane 0 generates the pseudo-legal list, the lanes test
+// legality in parallel, a ballot compacts in order.  Returns the count (uniform); moves in `legal`.
+__device__ __forceinline__ int mcts_gen_legal_warp(const cb_board& board, Move* pseudo, Move* legal, int lane) {
+    int np = 0;
+    if (lane == 0) np = cbchess::gen_pseudo(board, pseudo);
+    np = __shfl_sync(0xffffffffu, np, 0);
+    __syncwarp();
+    const int us = board.w_to_move ? 0 : 1;
+    int n = 0;
+    for (int base = 0; base < np; base += 32) {
+        const int i = base + lane;
+        bool ok = false;
+        Move m = 0;
+        if (i < np) {
+            m = pseudo[i];
+            cb_board nb;
+            cbchess::make_move_hd(board, m, &nb);
+            ok = !cbchess::in_check_hd(nb, us);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+        if (ok) legal[n + __popc(mask & ((1u << lane) - 1u))] = m;
+        n += __popc(mask);
+    }
+    __syncwarp();
+    return n;
+}
+
+// Phase A of a simulation for every game: walk down with PUCT, stop at an unexpanded or terminal node.
+__global__ void __launch_bounds__(32 * kMctsWarps) mcts_select_kernel(const MctsParams p) {
+    __shared__ cb_board s_board[kMctsWarps];
+    __shared__ Move s_pseudo[kMctsWarps][CB_MAX_MOVES];
+    __shared__ Move s_legal[kMctsWarps][CB_MAX_MOVES];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kMctsWarps + wl;
+    if (g >= p.G) return;
+    MNode* nodes = p.nodes + ((size_t)g * 2 + p.arena[g]) * p.node_cap;
+    uint32_t* path = p.path + (size_t)g * kMctsMaxDepth;
+    cb_board& board = s_board[wl];
+    if (lane < 16) reinterpret_cast<uint64_t*>(&board)[lane] = reinterpret_cast<const uint64_t*>(&p.root[g])[lane];
+    __syncwarp();
+    uint32_t cur = 0;
+    int depth = 0;
+    if (lane == 0) path[0] = 0;
+    for (;;) {
+        const MNode n = nodes[cur];
+        if (n.state != 1 || depth >= kMctsMaxDepth - 1) break;
+        uint32_t best = n.first_child;
+        bool forced = false;
+        if (depth == 0) {   // every root child gets one visit first
+            for (uint32_t base = 0; base < n.n_children && !forced; base += 32) {
+                const uint32_t i = base + lane;
+                const bool z = i < n.n_children && nodes[n.first_child + i].visits == 0;
+                const uint32_t mask = __ballot_sync(0xffffffffu, z);
+                if (mask) { best = n.first_child + base + (__ffs(mask) - 1); forced = true; }
+            }
+        }
+        if (!forced) {
+            const float sq = sqrtf((float)(n.visits > 1 ? n.visits : 1));
+            float bu = -1e30f;
+            uint32_t bi = 0xFFFFFFFFu;
+            for (uint32_t i = lane; i < n.n_children; i += 32) {
+                const MNode ch = nodes[n.first_child + i];
+                const float q = ch.visits ? __fdiv_rn(ch.value_sum, (float)ch.visits) : 0.0f;
+                const float u = __fadd_rn(q, __fdiv_rn(__fmul_rn(__fmul_rn(p.c_puct, ch.prior), sq), __fadd_rn(1.0f, (float)ch.visits)));
+                if (u > bu) { bu = u; bi = i; }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const float ou = __shfl_xor_sync(0xffffffffu, bu, d);
+                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                if (ou > bu || (ou == bu && oi < bi)) { bu = ou; bi = oi; }
+            }
+            if (bi != 0xFFFFFFFFu) best = n.first_child + bi;
+        }
+        if (lane == 0) {
+            cb_board nb;
+            cbchess::make_move_hd(board, nodes[best].move, &nb);
+            board = nb;
+            path[depth + 1] = best;
+        }
+        __syncwarp();
+        cur = best;
+        ++depth;
+    }
+    const int path_n = depth + 1;
+    MNode& leaf = nodes[cur];
+    const uint8_t leaf_state = leaf.state;
+    if (leaf_state == 2 || leaf_state == 1) {   // terminal (or the depth cap): back its value up again
+        if (lane == 0) {
+            mcts_backup(nodes, path, path_n, leaf_state == 2 ? (float)leaf.term_value : 0.0f);
+            atomicAdd(&p.stats[MS_TERMINAL], 1ull);
+            p.sims_done[g]++;
+            p.wants_eval[g] = 0;
+            p.eval_cnt[g] = 0;
+        }
+        return;
+    }
+    const int n = mcts_gen_legal_warp(board, s_pseudo[wl], s_legal[wl], lane);
+    if (n == 0) {   // mate / stalemate
+        if (lane == 0) {
+            leaf.state = 2;
+            leaf.term_value = cbchess::in_check_hd(board, board.w_to_move ? 0 : 1) ? -1 : 0;
+            mcts_backup(nodes, path, path_n, (float)leaf.term_value);
+            atomicAdd(&p.stats[MS_TERMINAL], 1ull);
+            p.sims_done[g]++;
+            p.wants_eval[g] = 0;
+            p.eval_cnt[g] = 0;
+        }
+        return;
+    }
+    const bool wtm = board.w_to_move != 0;
+    for (int i = lane; i < n; i += 32) {
+        const Move m = s_legal[wl][i];
+        p.leaf_moves[(size_t)g * CB_MAX_MOVES + i] = m;
+        p.eval_idx[(size_t)g * CB_MAX_MOVES + i] = (uint16_t)cbchess::policy_index_hd(m, wtm);
+    }
+    if (lane < 16) reinterpret_cast<uint64_t*>(&p.eval_boards[g])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
+    if (lane == 0) {
+        p.eval_q[g] = p.material_on ? __fdiv_rn((float)static_pesto_cp_dev(board), 100.0f) : 0.0f;
+        p.eval_cnt[g] = (uint16_t)n;
+        p.path_n[g] = path_n;
+        p.wants_eval[g] = 1;
+        atomicAdd(&p.stats[MS_EVALS], 1ull);
+    }
+}
+
+// Keep the subtree under `child` as the new tree, copied breadth first into the other arena (same node
+// order as the host driver's reroot).  All lanes.
+__device__ __forceinline__ void mcts_reroot(const MctsParams& p, int g, uint32_t child, int lane) {
+    const uint8_t a = p.arena[g];
+    const MNode* old = p.nodes + ((size_t)g * 2 + a) * p.node_cap;
+    MNode* nw = p.nodes + ((size_t)g * 2 + (a ^ 1)) * p.node_cap;
+    if (lane == 0) nw[0] = old[child];
+    __syncwarp();
+    uint32_t tail = 1;
+    for (uint32_t base = 0; base < tail;) {
+        const uint32_t batch = tail - base < 32u ? tail - base : 32u;
+        MNode on;
+        on.state = 0; on.first_child = 0; on.n_children = 0;
+        if ((uint32_t)lane < batch) on = nw[base + lane];
+        uint32_t mask = __ballot_sync(0xffffffffu, (uint32_t)lane < batch && on.state == 1);
+        while (mask) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t fc = __shfl_sync(0xffffffffu, on.first_child, l);
+            const uint32_t nc = __shfl_sync(0xffffffffu, (uint32_t)on.n_children, l);
+            for (uint32_t i = lane; i < nc; i += 32) nw[tail + i] = old[fc + i];
+            if (lane == 0) nw[base + l].first_child = tail;
+            tail += nc;
+        }
+        __syncwarp();
+        base += batch;
+    }
+    if (lane == 0) {
+        p.n_nodes[g] = tail;
+        p.arena[g] = a ^ 1;
+    }
+    __syncwarp();
+}
+
+// Phase C: expand the evaluated leaf with its priors, back the value up; at the end of the move's
+// simulation budget choose and play the move, re-root, detect the end of the game.
+__global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const MctsParams p) {
+    __shared__ Move s_pseudo[kMctsWarps][CB_MAX_MOVES];
+    __shared__ Move s_legal[kMctsWarps][CB_MAX_MOVES];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kMctsWarps + wl;
+    if (g >= p.G) return;
+    MNode* nodes = p.nodes + ((size_t)g * 2 + p.arena[g]) * p.node_cap;
+    if (p.wants_eval[g]) {
+        const uint32_t* path = p.path + (size_t)g * kMctsMaxDepth;
+        const int path_n = p.path_n[g];
+        const uint32_t cur = path[path_n - 1];
+        const int n = p.eval_cnt[g];
+        const uint32_t first = p.n_nodes[g];
+        if (first + (uint32_t)n <= p.node_cap) {
+            for (int i = lane; i < n; i += 32) {
+                MNode ch;
+                ch.first_child = 0; ch.visits = 0; ch.value_sum = 0.0f;
+                ch.prior = p.priors[(size_t)g * CB_MAX_MOVES + i];
+                ch.n_children = 0;
+                ch.move = p.leaf_moves[(size_t)g * CB_MAX_MOVES + i];
+                ch.state = 0; ch.term_value = 0; ch.pad = 0;
+                nodes[first + i] = ch;
+            }
+            if (lane == 0) {
+                nodes[cur].first_child = first;
+                nodes[cur].n_children = (uint16_t)n;
+                nodes[cur].state = 1;
+                p.n_nodes[g] = first + (uint32_t)n;
+            }
+        } else if (lane == 0) {
+            atomicAdd(&p.stats[MS_OVERFLOW], 1ull);   // arena full: the leaf stays unexpanded (evaluated again later)
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mcts_backup(nodes, path, path_n, p.v_final[g]);
+            p.sims_done[g]++;
+        }
+        __syncwarp();
+    }
+    if (p.sims_done[g] < p.sims_per_move) return;
+
+    // ------------------------------------------------------------------ play a move
+    const MNode root = nodes[0];
+    if (root.state != 1 || root.n_children == 0) {   // cannot happen for a live game; restart defensively
+        if (lane == 0) {
+            uint64_t s = p.rng[g];
+            const uint64_t seed = rng_next(s);
+            mcts_reset_game(p, g, seed);
+        }
+        return;
+    }
+    uint32_t pick = root.first_child;
+    uint64_t rs = p.rng[g];
+    if (lane == 0) {
+        uint32_t best_v = 0;
+        for (uint32_t i = 0; i < root.n_children; ++i) {
+            const uint32_t v = nodes[root.first_child + i].visits;
+            if (v > best_v) { best_v = v; pick = root.first_child + i; }
+        }
+        const int move_number = p.ply[g] / 2 + 1;
+        if (rng_uniform(rs) < pow(p.explore_base, (double)(move_number - 1))) {
+            uint32_t tot1 = 0;
+            for (uint32_t i = 0; i < root.n_children; ++i) {
+                const uint32_t v = nodes[root.first_child + i].visits;
+                tot1 += v > 0 ? v - 1 : 0;
+            }
+            if (tot1 > 0) {
+                const uint32_t thr = (uint32_t)(rng_next(rs) % tot1);
+                uint32_t cum = 0;
+                for (uint32_t i = 0; i < root.n_children; ++i) {
+                    const uint32_t v = nodes[root.first_child + i].visits;
+                    cum += v > 0 ? v - 1 : 0;
+                    if (cum > thr) { pick = root.first_child + i; break; }
+                }
+            }
+        }
+        p.samples_in_game[g]++;   // the (board, visit distribution) sample of this move
+    }
+    pick = __shfl_sync(0xffffffffu, pick, 0);
+    __shared__ cb_board s_nb[kMctsWarps];
+    cb_board& nb = s_nb[wl];
+    bool white_moved = false;
+    if (lane == 0) {
+        const cb_board rb = p.root[g];
+        white_moved = rb.w_to_move != 0;
+        cbchess::make_move_hd(rb, nodes[pick].move, &nb);
+        uint64_t* hist = p.history + (size_t)g * kMctsHist;
+        int hn = nb.halfmove == 0 ? 0 : p.hist_n[g];
+        if (hn < kMctsHist) hist[hn++] = cbchess::position_key_hd(nb);
+        p.hist_n[g] = hn;
+        p.root[g] = nb;
+        p.ply[g]++;
+        p.sims_done[g] = 0;
+        atomicAdd(&p.stats[MS_MOVES], 1ull);
+    }
+    __syncwarp();
+    mcts_reroot(p, g, pick, lane);
+    // game end
+    const int n_legal = mcts_gen_legal_warp(nb, s_pseudo[wl], s_legal[wl], lane);
+    if (lane == 0) {
+        int result = 2;   // +1 white won, -1 black won, 0 draw, 2 continue
+        if (p.koth && (nb.pieces[(white_moved ? 0 : 6) + cbchess::KING] & cbchess::kKothCenter)) result = white_moved ? 1 : -1;
+        else if (n_legal == 0) result = cbchess::in_check_hd(nb, nb.w_to_move ? 0 : 1) ? (white_moved ? 1 : -1) : 0;
+        else {
+            const uint64_t* hist = p.history + (size_t)g * kMctsHist;
+            const int hn = p.hist_n[g];
+            int reps = 0;
+            for (int i = 0; i < hn; ++i) reps += (hist[i] == hist[hn - 1]);
+            if (reps >= 3 || nb.halfmove >= 100 || p.ply[g] > p.max_plies) result = 0;
+        }
+        if (result != 2) {
+            atomicAdd(&p.stats[result > 0 ? MS_WWINS : result < 0 ? MS_BWINS : MS_DRAWS], 1ull);
+            atomicAdd(&p.stats[MS_SAMPLES], (unsigned long long)p.samples_in_game[g]);
+            atomicAdd(&p.stats[MS_GAMES], 1ull);
+            const uint64_t seed = rng_next(rs) ^ ((uint64_t)g << 32);
+            mcts_reset_game(p, g, seed);
+        } else {
+            p.rng[g] = rs;
+        }
+    }
+}
+
+}  // namespace cb

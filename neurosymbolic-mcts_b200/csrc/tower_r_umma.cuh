@@ -211,8 +211,15 @@ __device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board,
         for (int i = tix; i < CB_POLICY_SIZE; i += 128) o[i] = __expf(lg[i] - lse);
     }
     if (p.po.move_idx) {
-        const uint32_t lo = p.po.move_off[board], hi = p.po.move_off[board + 1];
-        const int n = static_cast<int>(hi - lo);
+        uint32_t lo;
+        int n;
+        if (p.po.move_cnt) {
+            lo = static_cast<uint32_t>(board) * CB_MAX_MOVES;
+            n = p.po.move_cnt[board];
+        } else {
+            lo = p.po.move_off[board];
+            n = static_cast<int>(p.po.move_off[board + 1] - lo);
+        }
         // gathered values -> registers (n <= 256 = 2 per thread), total via an ordered sequential sum by one
         // thread, exactly the reference's loop (src/tensor.rs:186-201)
         float g0 = 0.0f, g1 = 0.0f;

@@ -272,6 +272,24 @@ def test_resident_path_equals_host_path(cb, golden, positions):
     assert ev.launches_per_forward() == 1                  # planes, tower and both heads in one launch
 
 
+# ------------------------------------------------------------------ device-side tree operations
+@pytest.mark.parametrize("name,material", [("6x128_A", False), ("6x128_B", False), ("6x128_B", True)])
+def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material):
+    """Self-play with select / expand / backup / move choice on the device (pipeline 3) must walk exactly the
+    trees of the host driver: same evaluator outputs (they do not depend on batch composition), same chess
+    rules (shared inline code), same explicitly rounded PUCT arithmetic, same RNG stream => identical counters."""
+    g, blob = golden(name)
+    ev = make_eval(cb, g, blob, "bf16")
+    kw = dict(games=24, sims_per_move=20, max_plies=40, material_on=material, seed=11, max_sims=24 * 20 * 60)
+    host = ev.selfplay(threads=1, pipeline=1, **kw)
+    dev = ev.selfplay(pipeline=3, **kw)
+    for k in ("sims", "steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins",
+              "black_wins", "draws"):
+        assert host[k] == dev[k], (k, host[k], dev[k])
+    assert dev["moves"] > 24 * 40 and dev["games_finished"] >= 24
+    assert dev["sims"] == dev["nn_evals"] + dev["terminal_hits"]
+
+
 # ------------------------------------------------------------------ reference-shaped host interface
 def test_neural_net_policy_and_inference_server(cb, golden):
     import threading

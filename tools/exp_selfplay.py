@@ -16,3 +16,9 @@ for games, pipeline, threads, aux in [(1024, 1, ncpu - 2, None), (1024, 2, ncpu 
     print("games %4d pipeline %d aux %d threads %2d : %.2fM sims/s, mean batch %.0f, eval %.2fs tree %.2fs of %.2fs, steps %d" % (
         games, pipeline, int(aux is not None), threads, st["sims"] / st["seconds"] / 1e6, st["mean_batch"], st["eval_seconds"], st["tree_seconds"],
         st["seconds"], st["steps"]))
+
+for games in (1024, 2048, 4096):
+    st = ev.selfplay(games=games, sims_per_move=200, material_on=False, seed=3, max_seconds=3.0, pipeline=3)
+    print("DEVICE tree ops: games %4d : %.2fM sims/s, mean batch %.0f, forward %.2fs tree kernels %.2fs of %.2fs, steps %d, moves %d, games %d" % (
+        games, st["sims"] / st["seconds"] / 1e6, st["mean_batch"], st["eval_seconds"], st["tree_seconds"], st["seconds"], st["steps"],
+        st["moves"], st["games_finished"]))
