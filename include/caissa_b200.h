@@ -208,8 +208,8 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
 /* The same pool with the tree operations on the device (cb_selfplay_run dispatches here
  * for pipeline = 3): select (src/mcts/selection.rs:65-73,254-273), expand (:82-104), backup
  * (src/mcts/node.rs:403-424), move choice / tree reuse / game end (src/bin/self_play.rs:300-388) run as two
- * kernels around the forward kernel, one warp per game; leaves and priors never cross PCIe.  Same statistics;
- * sample files are not written in this mode (sample_path must be NULL). */
+ * kernels around the forward kernel, one warp per game; leaves and priors never cross PCIe.  Same statistics
+ * and the same sample file: moves are logged on the device and the finished games written by the host. */
 int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out);
 
 int         cb_get_timing(const cb_handle* h, cb_timing* out);

@@ -818,6 +818,66 @@ int upload_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, c
 
 }  // namespace
 
+// One move's training sample as logged by the device-side tree kernels.
+struct DevSample {
+    cb_board board;
+    float material;
+    std::vector<std::pair<uint16_t, float>> policy;
+};
+
+// host/selfplay.cpp: one 5763-f32 record (src/training_data.rs:20-60)
+void cbsp_write_sample(FILE* f, const cb_board& b, float material, const std::pair<uint16_t, float>* policy, size_t n_policy,
+                       int result_white, std::vector<float>& rec);
+
+namespace {
+
+// Copy the records appended since the last drain, rebuild the games and write the finished ones.
+int drain_samples(cb_handle* h, const MctsParams& mp, unsigned long long& ring_read, std::vector<uint8_t>& host,
+                  std::vector<std::vector<DevSample>>& pending, FILE* f) {
+    unsigned long long cursor = 0;
+    CB_CUDA(h, cudaMemcpyAsync(&cursor, mp.ring_cursor, 8, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (cursor == ring_read) return CB_OK;
+    if (cursor - ring_read > mp.ring_slots) return fail(h, CB_ESTATE, "sample ring overflow");
+    const size_t n = (size_t)(cursor - ring_read);
+    host.resize(n * kSampleSlotBytes);
+    const size_t first = (size_t)(ring_read % mp.ring_slots);
+    const size_t run = n < mp.ring_slots - first ? n : mp.ring_slots - first;
+    CB_CUDA(h, cudaMemcpyAsync(host.data(), mp.sample_ring + first * kSampleSlotBytes, run * kSampleSlotBytes,
+                               cudaMemcpyDeviceToHost, h->stream));
+    if (run < n)
+        CB_CUDA(h, cudaMemcpyAsync(host.data() + run * kSampleSlotBytes, mp.sample_ring, (n - run) * kSampleSlotBytes,
+                                   cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::vector<float> rec;
+    for (size_t i = 0; i < n; ++i) {
+        const uint8_t* r = host.data() + i * kSampleSlotBytes;
+        const uint32_t game = reinterpret_cast<const uint32_t*>(r)[0];
+        const uint16_t cnt = reinterpret_cast<const uint16_t*>(r)[5];
+        if (game >= pending.size()) return fail(h, CB_ESTATE, "corrupt sample record");
+        if (cnt == 0xFFFFu) {
+            const int result = reinterpret_cast<const int32_t*>(r)[3];
+            for (const DevSample& s : pending[game])
+                cbsp_write_sample(f, s.board, s.material, s.policy.data(), s.policy.size(), result, rec);
+            pending[game].clear();
+            continue;
+        }
+        DevSample s;
+        memcpy(&s.board, r + 16, sizeof(cb_board));
+        s.material = reinterpret_cast<const float*>(r)[3];
+        const uint32_t* pairs = reinterpret_cast<const uint32_t*>(r + 144);
+        uint32_t total = 0;
+        for (uint16_t k = 0; k < cnt; ++k) total += pairs[k] >> 16;
+        for (uint16_t k = 0; k < cnt && total > 0; ++k)
+            s.policy.emplace_back((uint16_t)(pairs[k] & 0xFFFFu), (float)(pairs[k] >> 16) / (float)total);
+        pending[game].push_back(std::move(s));
+    }
+    ring_read = cursor;
+    return CB_OK;
+}
+
+}  // namespace
+
 // ============================================================== C ABI
 extern "C" {
 
@@ -1329,7 +1389,6 @@ int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches) {
 int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
     if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
     if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
-    if (cfg->sample_path) return fail(h, CB_EINVAL, "device-side self-play does not write sample files yet");
     CB_CUDA(h, cudaSetDevice(h->device));
     const int G = cfg->games;
     int rc = ensure_capacity(h, G);
@@ -1374,6 +1433,26 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     mp.eval_idx = h->d_move_idx;
     mp.priors = h->d_priors;
     mp.v_final = h->d_vfinal;
+    // training samples: device-side log drained between graph replays, games assembled and written on the host
+    FILE* sample_file = nullptr;
+    std::vector<uint8_t> ring_host;
+    std::vector<std::vector<DevSample>> pending;     // per game slot: samples of the game in progress
+    unsigned long long ring_read = 0;
+    if (cfg->sample_path) {
+        sample_file = fopen(cfg->sample_path, "ab");
+        if (!sample_file) { release(); return fail(h, CB_EINVAL, "cannot open the sample file"); }
+        // a game appends at most one record per simulation step (+1 at its end): size the ring for 2 replays
+        mp.ring_slots = (uint32_t)(4 * G * 8 + 1024);
+        if ((rc = dalloc((void**)&mp.sample_ring, (size_t)mp.ring_slots * kSampleSlotBytes)) ||
+            (rc = dalloc((void**)&mp.ring_cursor, 8)) || (rc = dalloc((void**)&mp.game_serial, (size_t)G * 4))) {
+            fclose(sample_file);
+            release();
+            return rc;
+        }
+        cudaMemsetAsync(mp.ring_cursor, 0, 8, h->stream);
+        cudaMemsetAsync(mp.game_serial, 0, (size_t)G * 4, h->stream);
+        pending.resize(G);
+    }
     cudaMemsetAsync(mp.stats, 0, MS_COUNT * 8, h->stream);
     cudaMemsetAsync(h->d_boards, 0, (size_t)G * sizeof(cb_board), h->stream);
     mcts_init_kernel<<<(G + 127) / 128, 128, 0, h->stream>>>(mp);
@@ -1406,6 +1485,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     cudaEventElapsedTime(&ms_exp, e[2], e[3]);
     for (auto& x : e) cudaEventDestroy(x);
     if (rc || ce != cudaSuccess) {
+        if (sample_file) fclose(sample_file);
         release();
         if (rc) return rc;
         return fail(h, CB_ECUDA, std::string("device self-play step: ") + cudaGetErrorString(ce));
@@ -1419,6 +1499,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     if (!rc && ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
     if (graph) cudaGraphDestroy(graph);
     if (rc || ce != cudaSuccess) {
+        if (sample_file) fclose(sample_file);
         release();
         if (rc) return rc;
         return fail(h, CB_ECUDA, std::string("device self-play graph: ") + cudaGetErrorString(ce));
@@ -1431,6 +1512,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         ce = cudaMemcpyAsync(st, mp.stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
         if (ce != cudaSuccess) break;
+        if (sample_file && (rc = drain_samples(h, mp, ring_read, ring_host, pending, sample_file))) break;
         const long long sims = steps * G;
         if (cfg->max_sims > 0 && sims >= cfg->max_sims) break;
         if (cfg->max_games > 0 && (long long)st[MS_GAMES] >= cfg->max_games) break;
@@ -1446,6 +1528,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     }
     const double secs = elapsed();
     cudaGraphExecDestroy(gexec);
+    if (sample_file) fclose(sample_file);
     release();
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(h, CB_ECUDA, std::string("device self-play: ") + cudaGetErrorString(ce));

@@ -273,6 +273,40 @@ struct EvalJob {
     }
 };
 
+}  // namespace
+
+// One training sample in the reference's 5763-f32 record (src/training_data.rs:20-60): 1088 planes, material,
+// qsearch flag, z from the mover's point of view, dense 4672 policy.  `rec` is scratch of 5763 floats.
+void cbsp_write_sample(FILE* f, const cb_board& b, float material, const std::pair<uint16_t, float>* policy, size_t n_policy,
+                       int result_white, std::vector<float>& rec) {
+    rec.assign(5763, 0.0f);
+    const bool white = b.w_to_move != 0;
+    const int stm = white ? 0 : 1;
+    for (int side = 0; side < 2; ++side)
+        for (int pt = 0; pt < 6; ++pt)
+            for (uint64_t bb = b.pieces[(side == 0 ? stm : 1 - stm) * 6 + pt]; bb; bb &= bb - 1) {
+                const int sq = __builtin_ctzll(bb);
+                const int row = white ? 7 - (sq >> 3) : (sq >> 3);
+                rec[(side * 6 + pt) * 64 + row * 8 + (sq & 7)] = 1.0f;
+            }
+    if (b.en_passant != 0xFF) {
+        const int sq = b.en_passant, row = white ? 7 - (sq >> 3) : (sq >> 3);
+        rec[12 * 64 + row * 8 + (sq & 7)] = 1.0f;
+    }
+    const int ow[4] = {WK, WQ, BK, BQ}, ob[4] = {BK, BQ, WK, WQ};
+    for (int i = 0; i < 4; ++i)
+        if (b.castling & (white ? ow[i] : ob[i]))
+            for (int j = 0; j < 64; ++j) rec[(13 + i) * 64 + j] = 1.0f;
+    rec[1088] = material;
+    rec[1089] = 1.0f;  // qsearch_completed
+    rec[1090] = result_white == 0 ? 0.0f : ((result_white > 0) == white ? 1.0f : -1.0f);
+    for (size_t i = 0; i < n_policy; ++i)
+        if (policy[i].first < CB_POLICY_SIZE) rec[1091 + policy[i].first] = policy[i].second;
+    fwrite(rec.data(), 4, rec.size(), f);
+}
+
+namespace {
+
 double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -340,33 +374,8 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
         if (sample_file) {
             std::vector<float> rec(5763);
             std::lock_guard<std::mutex> l(file_mu);
-            for (const Sample& s : g.samples) {
-                std::fill(rec.begin(), rec.end(), 0.0f);
-                const cb_board& b = s.board;
-                const bool white = b.w_to_move != 0;
-                const int stm = white ? 0 : 1;
-                for (int side = 0; side < 2; ++side)
-                    for (int pt = 0; pt < 6; ++pt)
-                        for (uint64_t bb = b.pieces[(side == 0 ? stm : 1 - stm) * 6 + pt]; bb; bb &= bb - 1) {
-                            const int sq = __builtin_ctzll(bb);
-                            const int row = white ? 7 - (sq >> 3) : (sq >> 3);
-                            rec[(side * 6 + pt) * 64 + row * 8 + (sq & 7)] = 1.0f;
-                        }
-                if (b.en_passant != 0xFF) {
-                    const int sq = b.en_passant, row = white ? 7 - (sq >> 3) : (sq >> 3);
-                    rec[12 * 64 + row * 8 + (sq & 7)] = 1.0f;
-                }
-                const int ow[4] = {WK, WQ, BK, BQ}, ob[4] = {BK, BQ, WK, WQ};
-                for (int i = 0; i < 4; ++i)
-                    if (b.castling & (white ? ow[i] : ob[i]))
-                        for (int j = 0; j < 64; ++j) rec[(13 + i) * 64 + j] = 1.0f;
-                rec[1088] = s.material;
-                rec[1089] = 1.0f;  // qsearch_completed
-                rec[1090] = result_white == 0 ? 0.0f : ((result_white > 0) == white ? 1.0f : -1.0f);
-                for (auto& pr : s.policy)
-                    if (pr.first < CB_POLICY_SIZE) rec[1091 + pr.first] = pr.second;
-                fwrite(rec.data(), 4, rec.size(), sample_file);
-            }
+            for (const Sample& s : g.samples)
+                cbsp_write_sample(sample_file, s.board, s.material, s.policy.data(), s.policy.size(), result_white, rec);
         }
         samples_written += (long long)g.samples.size();
         games_finished++;

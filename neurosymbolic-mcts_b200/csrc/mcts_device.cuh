@@ -73,7 +73,19 @@ struct MctsParams {
     const float* v_final;           // [G]
     unsigned long long* stats;      // [MS_COUNT]
     uint64_t seed;
+    // optional training-sample log (nullptr: off): ring of kSampleSlotBytes records appended in program order
+    // per game — one per move played (board, material, visit counts of the root's children) and one per
+    // finished game (the result); the host drains it between graph replays
+    uint8_t* sample_ring;
+    uint32_t ring_slots;
+    unsigned long long* ring_cursor;
+    uint32_t* game_serial;          // [G] games finished so far in this slot
 };
+
+// Sample record: u32 game | u32 serial | u16 ply | u16 n (0xFFFF = game end) | f32 material or i32 result |
+// cb_board (128 B) | n x (u16 policy index, u16 visits)
+constexpr int kSampleSlotBytes = 1024;
+static_assert(16 + 128 + 4 * 218 <= kSampleSlotBytes, "sample slot");
 
 __device__ __forceinline__ uint64_t rng_next(uint64_t& s) {
     s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
@@ -386,6 +398,33 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const Mcts
         p.samples_in_game[g]++;   // the (board, visit distribution) sample of this move
     }
     pick = __shfl_sync(0xffffffffu, pick, 0);
+    if (p.sample_ring) {
+        unsigned long long slot = 0;
+        if (lane == 0) slot = atomicAdd(p.ring_cursor, 1ull);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        uint8_t* rec = p.sample_ring + (size_t)(slot % p.ring_slots) * kSampleSlotBytes;
+        uint32_t total = 0;
+        for (uint32_t i = lane; i < root.n_children; i += 32) total += nodes[root.first_child + i].visits;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+        const cb_board rb = p.root[g];
+        const bool wtm = rb.w_to_move != 0;
+        const uint32_t n = total > 0 ? root.n_children : 0;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const MNode ch = nodes[root.first_child + i];
+            const uint32_t v = ch.visits > 65535u ? 65535u : ch.visits;
+            reinterpret_cast<uint32_t*>(rec + 144)[i] = (uint32_t)(uint16_t)cbchess::policy_index_hd(ch.move, wtm) | (v << 16);
+        }
+        if (lane < 16) reinterpret_cast<uint64_t*>(rec + 16)[lane] = reinterpret_cast<const uint64_t*>(&p.root[g])[lane];
+        if (lane == 0) {
+            reinterpret_cast<uint32_t*>(rec)[0] = (uint32_t)g;
+            reinterpret_cast<uint32_t*>(rec)[1] = p.game_serial[g];
+            reinterpret_cast<uint16_t*>(rec)[4] = (uint16_t)p.ply[g];
+            reinterpret_cast<uint16_t*>(rec)[5] = (uint16_t)n;
+            reinterpret_cast<float*>(rec)[3] = p.material_on ? __fdiv_rn((float)static_pesto_cp_dev(rb), 100.0f) : 0.0f;
+        }
+        __syncwarp();
+    }
     __shared__ cb_board s_nb[kMctsWarps];
     cb_board& nb = s_nb[wl];
     bool white_moved = false;
@@ -421,6 +460,16 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const Mcts
             atomicAdd(&p.stats[result > 0 ? MS_WWINS : result < 0 ? MS_BWINS : MS_DRAWS], 1ull);
             atomicAdd(&p.stats[MS_SAMPLES], (unsigned long long)p.samples_in_game[g]);
             atomicAdd(&p.stats[MS_GAMES], 1ull);
+            if (p.sample_ring) {
+                const unsigned long long slot = atomicAdd(p.ring_cursor, 1ull);
+                uint8_t* rec = p.sample_ring + (size_t)(slot % p.ring_slots) * kSampleSlotBytes;
+                reinterpret_cast<uint32_t*>(rec)[0] = (uint32_t)g;
+                reinterpret_cast<uint32_t*>(rec)[1] = p.game_serial[g];
+                reinterpret_cast<uint16_t*>(rec)[4] = (uint16_t)p.ply[g];
+                reinterpret_cast<uint16_t*>(rec)[5] = 0xFFFFu;
+                reinterpret_cast<int32_t*>(rec)[3] = result;
+                p.game_serial[g]++;
+            }
             const uint64_t seed = rng_next(rs) ^ ((uint64_t)g << 32);
             mcts_reset_game(p, g, seed);
         } else {

@@ -274,20 +274,27 @@ def test_resident_path_equals_host_path(cb, golden, positions):
 
 # ------------------------------------------------------------------ device-side tree operations
 @pytest.mark.parametrize("name,material", [("6x128_A", False), ("6x128_B", False), ("6x128_B", True)])
-def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material):
+def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material, tmp_path):
     """Self-play with select / expand / backup / move choice on the device (pipeline 3) must walk exactly the
     trees of the host driver: same evaluator outputs (they do not depend on batch composition), same chess
     rules (shared inline code), same explicitly rounded PUCT arithmetic, same RNG stream => identical counters."""
     g, blob = golden(name)
     ev = make_eval(cb, g, blob, "bf16")
     kw = dict(games=24, sims_per_move=20, max_plies=40, material_on=material, seed=11, max_sims=24 * 20 * 60)
-    host = ev.selfplay(threads=1, pipeline=1, **kw)
-    dev = ev.selfplay(pipeline=3, **kw)
+    host = ev.selfplay(threads=1, pipeline=1, sample_path=str(tmp_path / "host.bin"), **kw)
+    dev = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "dev.bin"), **kw)
     for k in ("sims", "steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins",
               "black_wins", "draws"):
         assert host[k] == dev[k], (k, host[k], dev[k])
     assert dev["moves"] > 24 * 40 and dev["games_finished"] >= 24
     assert dev["sims"] == dev["nn_evals"] + dev["terminal_hits"]
+    # the training samples too (5763-f32 records, src/training_data.rs:20-60); games that end in the same step
+    # may be written in a different order
+    rh = np.fromfile(tmp_path / "host.bin", dtype=np.float32).reshape(-1, 5763)
+    rd = np.fromfile(tmp_path / "dev.bin", dtype=np.float32).reshape(-1, 5763)
+    assert rh.shape == rd.shape and rh.shape[0] == host["samples"] > 0
+    key = lambda r: r[np.lexsort(r.T[::-1])]
+    assert np.array_equal(key(rh), key(rd))
 
 
 # ------------------------------------------------------------------ reference-shaped host interface
