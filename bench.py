@@ -169,7 +169,21 @@ def time_cpu_path(args, boards, q, idx, off, blob, budget_s, steps, warmup):
                       "+ exp + legal-move priors), %d torch threads" % (steps, n, cores)}, dt / steps * 1e3
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else written to fd 1 while the
+    benchmark runs (NCCL's version banner, library chatter) has been routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -206,7 +220,7 @@ def main():
                 "cpu_baseline": cpu,
                 "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -216,9 +230,6 @@ def main():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -288,31 +299,31 @@ def main():
     h2d = int(boards.nbytes + q.nbytes + idx.nbytes + off.nbytes)
     d2h = int(out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes)
 
-    # ---- self-play pool on this GPU (config 3 shape: 200 sims/move, 1024 concurrent games, vanilla mode).
-    # Two half-pools of 512 games, each served by its own evaluator handle, so the host tree work of one half
-    # and the copies of its call run under the other half's kernel; the 2048-game pool (two full 1024 batches)
-    # is measured beside it.
-    sp = sp_big = None
+    # ---- self-play pool on this GPU (config 3 shape: 200 sims/move, 1024 concurrent games, vanilla mode):
+    # tree operations on the device (select / expand / backup / move choice as two kernels around the forward
+    # kernel, no host work per simulation), and beside it the host-driven pool (two half-pools of 512 games,
+    # each with its own evaluator handle) whose rate depends on the host cores available per GPU.
+    sp = sp_host = None
     nthreads = max(1, (os.cpu_count() or 1) // world - 2)
     if args.selfplay_seconds > 0:
         barrier()
         sp = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=1 + rank,
-                         max_seconds=args.selfplay_seconds, threads=nthreads, pipeline=2, aux=ev2)
+                         max_seconds=args.selfplay_seconds, pipeline=3)
         barrier()
-        sp_big = ev.selfplay(games=2 * args.selfplay_games, sims_per_move=200, material_on=False, seed=101 + rank,
-                             max_seconds=args.selfplay_seconds, threads=nthreads, pipeline=2, aux=ev2)
+        sp_host = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=101 + rank,
+                              max_seconds=args.selfplay_seconds, threads=nthreads, pipeline=2, aux=ev2)
         barrier()
     ev2.close()
 
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3, launch_ms, e2e_sync_s * 1e3, sp["seconds"] if sp else 0.0,
-                      sp_big["seconds"] if sp_big else 0.0], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([sp["sims"] if sp else 0, sp["nn_evals"] if sp else 0, sp_big["sims"] if sp_big else 0],
+                      sp_host["seconds"] if sp_host else 0.0], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([sp["sims"] if sp else 0, sp["nn_evals"] if sp else 0, sp_host["sims"] if sp_host else 0],
                        dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds, sp_big_seconds = [float(x) for x in t.tolist()]
+    dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds, sp_host_seconds = [float(x) for x in t.tolist()]
     value = world * B * K / (dev_ms * 1e-3)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     # off the hot path: the one exchange the multi-GPU design has (training-sample gather over NCCL)
@@ -355,18 +366,18 @@ def main():
             line["selfplay"] = {"sims_per_s": float(tot[0].item()) / sp_seconds,
                                 "nn_evals_per_s": float(tot[1].item()) / sp_seconds,
                                 "games_per_gpu": args.selfplay_games, "sims_per_move": 200, "mode": "vanilla (config 5 rules: "
-                                "Tier 1 off, material off), one leaf in flight per game; two half-pools, each with its own "
-                                "evaluator handle (tree work and copies of one half under the other half's kernel)",
-                                "host_threads_per_gpu": nthreads,
+                                "Tier 1 off, material off), one leaf in flight per game; tree operations on the device "
+                                "(cb_selfplay_run pipeline 3: select, forward, expand/play kernels in one CUDA graph)",
                                 "seconds": sp_seconds, "mean_batch": sp["mean_batch"],
-                                "eval_fraction": sp["eval_seconds"] / max(sp["seconds"], 1e-9),
-                                "sims_per_s_2048_games": float(tot[2].item()) / max(sp_big_seconds, 1e-9)}
+                                "forward_fraction": sp["eval_seconds"] / max(sp["seconds"], 1e-9),
+                                "host_driven_sims_per_s": float(tot[2].item()) / max(sp_host_seconds, 1e-9),
+                                "host_threads_per_gpu": nthreads}
         if gathered is not None:
             line["nccl_sample_gather_records"] = gathered
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = time_cpu_path(args, boards, q, idx, off, blob, 20.0, 3, 1)
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1468,22 +1468,9 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
         return CB_OK;
     };
-    // one eager step (sets the kernels' attributes outside capture), timed per phase
-    cudaEvent_t e[4];
-    for (auto& x : e) cudaEventCreate(&x);
-    cudaEventRecord(e[0], h->stream);
-    mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
-    cudaEventRecord(e[1], h->stream);
-    rc = launch_tower_r(h, G, po, cfg->material_on, true);
-    cudaEventRecord(e[2], h->stream);
-    mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
-    cudaEventRecord(e[3], h->stream);
+    // one eager step (sets the kernels' attributes outside capture)
+    rc = step();
     cudaError_t ce = cudaStreamSynchronize(h->stream);
-    float ms_sel = 0, ms_fwd = 0, ms_exp = 0;
-    cudaEventElapsedTime(&ms_sel, e[0], e[1]);
-    cudaEventElapsedTime(&ms_fwd, e[1], e[2]);
-    cudaEventElapsedTime(&ms_exp, e[2], e[3]);
-    for (auto& x : e) cudaEventDestroy(x);
     if (rc || ce != cudaSuccess) {
         if (sample_file) fclose(sample_file);
         release();
@@ -1527,6 +1514,25 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         }
     }
     const double secs = elapsed();
+    // split of a steady-state step, measured once with CUDA events: forward kernel vs the two tree kernels
+    float ms_sel = 0, ms_fwd = 0, ms_exp = 0;
+    if (!rc && ce == cudaSuccess) {
+        cudaEvent_t e[4];
+        for (auto& x : e) cudaEventCreate(&x);
+        cudaEventRecord(e[0], h->stream);
+        mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        cudaEventRecord(e[1], h->stream);
+        rc = launch_tower_r(h, G, po, cfg->material_on, true);
+        cudaEventRecord(e[2], h->stream);
+        mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        cudaEventRecord(e[3], h->stream);
+        ce = cudaStreamSynchronize(h->stream);
+        cudaEventElapsedTime(&ms_sel, e[0], e[1]);
+        cudaEventElapsedTime(&ms_fwd, e[1], e[2]);
+        cudaEventElapsedTime(&ms_exp, e[2], e[3]);
+        for (auto& x : e) cudaEventDestroy(x);
+        if (getenv("CB_MCTS_TIMES")) fprintf(stderr, "device self-play step: select %.1f us, forward %.1f us, expand %.1f us\n", ms_sel * 1e3, ms_fwd * 1e3, ms_exp * 1e3);
+    }
     cudaGraphExecDestroy(gexec);
     if (sample_file) fclose(sample_file);
     release();
@@ -1543,7 +1549,6 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     out->black_wins = (long long)st[MS_BWINS];
     out->draws = (long long)st[MS_DRAWS];
     out->seconds = secs;
-    // split of a step measured once with CUDA events: forward kernel vs the two tree kernels
     const double tot = (double)ms_sel + ms_fwd + ms_exp;
     out->eval_seconds = tot > 0 ? secs * ms_fwd / tot : 0.0;
     out->tree_seconds = tot > 0 ? secs * (ms_sel + ms_exp) / tot : 0.0;
