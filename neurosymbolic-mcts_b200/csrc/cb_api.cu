@@ -715,7 +715,8 @@ int enqueue_tower(cb_handle* h, int B, std::vector<cudaEvent_t>* ev) {
 }
 
 // Enqueue one full forward on the handle's stream (inputs already in d_boards/d_q/CSR).
-int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int material_on, bool use_q) {
+int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int material_on, bool use_q,
+                    const uint16_t* move_cnt = nullptr) {
     const int kind = fused_kind(h);
     const int glog = kind == 2 ? 2 : 1;                       // boards interleaved per activation group
     const int Bpad = (B + (1 << glog) - 1) & ~((1 << glog) - 1);
@@ -735,6 +736,7 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
         po.move_idx = h->d_move_idx;
         po.move_off = h->d_move_off;
         po.priors = h->d_priors;
+        po.move_cnt = move_cnt;    // device-side tree kernels: fixed-stride lists
     }
     int rc;
     if (kind == 3) return launch_tower_r(h, B, po, material_on, use_q);   // heads included
@@ -1393,7 +1395,6 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     const int G = cfg->games;
     int rc = ensure_capacity(h, G);
     if (rc) return rc;
-    if (fused_kind(h) != 3) return fail(h, CB_ESTATE, "device-side self-play needs the resident single-launch forward (128-channel net, 16-bit mode)");
     memset(out, 0, sizeof(*out));
     if (!h->chess_tables_uploaded) {
         CB_CUDA(h, cudaMemcpyToSymbol(cbchess::d_chess_tables, &cbchess::host_tables(), sizeof(cbchess::Tables)));
@@ -1456,14 +1457,10 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     cudaMemsetAsync(mp.stats, 0, MS_COUNT * 8, h->stream);
     cudaMemsetAsync(h->d_boards, 0, (size_t)G * sizeof(cb_board), h->stream);
     mcts_init_kernel<<<(G + 127) / 128, 128, 0, h->stream>>>(mp);
-    PolicyOut po = {};
-    po.move_idx = h->d_move_idx;
-    po.priors = h->d_priors;
-    po.move_cnt = mp.eval_cnt;
     const int grid = (G + kMctsWarps - 1) / kMctsWarps;
     auto step = [&]() -> int {
         mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
-        int r = launch_tower_r(h, G, po, cfg->material_on, true);
+        int r = enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
         if (r) return r;
         mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
         return CB_OK;
@@ -1522,7 +1519,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         cudaEventRecord(e[0], h->stream);
         mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
         cudaEventRecord(e[1], h->stream);
-        rc = launch_tower_r(h, G, po, cfg->material_on, true);
+        rc = enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
         cudaEventRecord(e[2], h->stream);
         mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
         cudaEventRecord(e[3], h->stream);

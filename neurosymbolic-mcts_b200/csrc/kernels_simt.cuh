@@ -287,7 +287,8 @@ policy_head_kernel(const T* __restrict__ p, const float* __restrict__ wt, const 
         for (int i = tid; i < CB_POLICY_SIZE; i += kPolicyThreads) o[i] = expf(s_logit[i] - lse);
     }
     if (po.move_idx) {
-        const uint32_t lo = po.move_off[b], hi = po.move_off[b + 1];
+        const uint32_t lo = po.move_cnt ? static_cast<uint32_t>(b) * CB_MAX_MOVES : po.move_off[b];
+        const uint32_t hi = po.move_cnt ? lo + po.move_cnt[b] : po.move_off[b + 1];
         const int n = static_cast<int>(hi - lo);
         __syncthreads();
         // gather into the (now free) feature area, then a sequential f32 sum in list

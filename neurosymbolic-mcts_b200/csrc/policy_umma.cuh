@@ -209,7 +209,8 @@ policy_umma_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_consta
                     for (int i = et; i < CB_POLICY_SIZE; i += 128) o[i] = __expf(lg[i] - lse[b]);
                 }
                 if (po.move_idx) {
-                    const uint32_t lo = po.move_off[board], hi = po.move_off[board + 1];
+                    const uint32_t lo = po.move_cnt ? static_cast<uint32_t>(board) * CB_MAX_MOVES : po.move_off[board];
+                    const uint32_t hi = po.move_cnt ? lo + po.move_cnt[board] : po.move_off[board + 1];
                     const int n = static_cast<int>(hi - lo);
                     // gathered values -> registers (n <= 256 = 2 per thread), total via an ordered
                     // sequential sum by one thread, exactly the reference's loop (src/tensor.rs:186-201)
