@@ -36,3 +36,12 @@ try:
     print("tower launch (CUDA events): %s us" % np.round(tw * 1e3, 1))
 except Exception as e:
     print("cta times unavailable:", e)
+
+# effective SM clock during the kernel: SM cycles of CTA 0 (first MMA stamp -> last epilogue stamp) over the
+# global-timer nanoseconds of the same span in a second launch
+try:
+    span_cyc = float(tr[:, 5].max() - tr[tr[:, 2] > 0, 2].min())
+    span_ns = float(ct[0, 2] - ct[0, 1])
+    print("effective SM clock under this kernel: %.0f MHz (%.0f cycles / %.1f us)" % (span_cyc / span_ns * 1e3, span_cyc, span_ns / 1e3))
+except Exception as e:
+    print("clock estimate unavailable:", e)
