@@ -453,15 +453,13 @@ int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bo
     const char* dbg_env = getenv("CB_DBG_R");
     tp.dbg = dbg_env ? atoi(dbg_env) : 0;
     const int grid = tp.num_units < h->sm_count ? tp.num_units : h->sm_count;
-    if (h->dtype == CB_DTYPE_BF16) {
-        auto kern = tower_r_umma_kernel<true>;
-        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerRCfg::kSmemBytes));
-        kern<<<grid, TowerRCfg::kThreads, TowerRCfg::kSmemBytes, h->stream>>>(tp);
-    } else {
-        auto kern = tower_r_umma_kernel<false>;
-        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerRCfg::kSmemBytes));
-        kern<<<grid, TowerRCfg::kThreads, TowerRCfg::kSmemBytes, h->stream>>>(tp);
-    }
+    // debug instantiation only when an experiment switch, the timeline, the per-CTA timers or the backbone dump is on
+    const bool debug = tp.dbg != 0 || tp.trace || tp.cta_times || tp.dbg_backbone;
+    void (*kern)(const TowerRParams) =
+        h->dtype == CB_DTYPE_BF16 ? (debug ? tower_r_umma_kernel<true, true> : tower_r_umma_kernel<true, false>)
+                                  : (debug ? tower_r_umma_kernel<false, true> : tower_r_umma_kernel<false, false>);
+    CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerRCfg::kSmemBytes));
+    kern<<<grid, TowerRCfg::kThreads, TowerRCfg::kSmemBytes, h->stream>>>(tp);
     CB_CUDA(h, cudaGetLastError());
     return CB_OK;
 }

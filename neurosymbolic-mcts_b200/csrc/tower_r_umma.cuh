@@ -303,8 +303,14 @@ __device__ __forceinline__ void value_phase(const TowerRParams& p, int et, int l
     }
 }
 
-template <bool BF16>
+// DBG = true: honour the CB_DBG_R experiment switches, the timeline stamps and the backbone dump (debug
+// entry points only); the product instantiation compiles all of that out of the hot loops.
+template <bool BF16, bool DBG>
 __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(const TowerRParams p) {
+    const int dbg = DBG ? p.dbg : 0;
+    long long* const trace = DBG ? p.trace : nullptr;
+    unsigned long long* const cta_times = DBG ? p.cta_times : nullptr;
+    float* const dbg_backbone = DBG ? p.dbg_backbone : nullptr;
     using Cfg = TowerRCfg;
     constexpr int HID = 128;
     constexpr int kWStages = Cfg::kWStages, kSE = 8;
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    if (p.cta_times && threadIdx.x == 0) p.cta_times[blockIdx.x * 4 + 0] = globaltimer_ns();
+    if (cta_times && threadIdx.x == 0) cta_times[blockIdx.x * 4 + 0] = globaltimer_ns();
     // tap order: the first tap of a layer must cover every accumulator column (dy = 0)
     constexpr int kTapOrder[9] = {4, 3, 5, 1, 0, 2, 7, 6, 8};
 
@@ -361,7 +367,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                         for (int kc = 0; kc < kc_in; ++kc) {
                             ptx::mbar_wait(&w_empty[ws], wph ^ 1);
                             if (ptx::elect_one()) {
-                                if (p.dbg & 16) {
+                                if (dbg & 16) {
                                     ptx::mbar_arrive(&w_full[ws]);
                                 } else {
                                     ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::kWBytes);
@@ -402,8 +408,8 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     ptx::tc_fence_after();
                     const uint32_t b_lo_c = b_lo0 + c * (Cfg::kChainBytes >> 4);
                     const uint32_t d_tmem = tmem_base + c * 256;
-                    if (lane == 0) trace_stamp(p.trace, L * 2 + c, 2);
-                    if (p.cta_times && lane == 0 && L == 0 && c == 0 && unit == blockIdx.x) p.cta_times[blockIdx.x * 4 + 1] = globaltimer_ns();
+                    if (lane == 0) trace_stamp(trace, L * 2 + c, 2);
+                    if (cta_times && lane == 0 && L == 0 && c == 0 && unit == blockIdx.x) cta_times[blockIdx.x * 4 + 1] = globaltimer_ns();
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         if (t >= ntaps) break;
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             if (ptx::elect_one()) {
                                 const uint32_t a_lo = a_lo0 + ws * (Cfg::kWBytes >> 4);
                                 const uint32_t b_lo = b_lo_t + kc * (Cfg::kHalfBytes >> 4);
-                                if (!(p.dbg & 1)) {
+                                if (!(dbg & 1)) {
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
                                         ptx::umma_f16_lohi(d_t, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);   // bias preset
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     }
                     if (ptx::elect_one()) ptx::umma_commit(&tmem_full[c]);
                     __syncwarp();
-                    if (lane == 0) trace_stamp(p.trace, L * 2 + c, 3);
+                    if (lane == 0) trace_stamp(trace, L * 2 + c, 3);
                 }
             }
         }
@@ -483,7 +489,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     const int yy = g / nb - halo, b = g - (g / nb) * nb;
                     const bool data = xr >= 1 && g < groups && yy >= 0 && yy < 8;
                     uint32_t msk = 0;
-                    if (data && !(p.dbg & 8)) msk = pixel_plane_mask(p.boards + cb0 + b, yy, xr - 1);
+                    if (data && !(dbg & 8)) msk = pixel_plane_mask(p.boards + cb0 + b, yy, xr - 1);
                     uint4* row0 = reinterpret_cast<uint4*>(buf + r * 128);
                     uint4* row1 = reinterpret_cast<uint4*>(buf + Cfg::kHalfBytes + r * 128);
                     const uint32_t one = BF16 ? 0x3F80u : 0x3C00u;
@@ -541,17 +547,17 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
 #pragma unroll
                         for (int j = 0; j < kSE; ++j) w2r[j] = __ldg(&ly->se_w2[ch * kSE + j]);
                         // block input of my (channel, board): parked by this same thread earlier
-                        if (active && !(p.dbg & 4)) {
+                        if (active && !(dbg & 4)) {
 #pragma unroll
                             for (int y = 0; y < 8; ++y) rr[y] = __ldcg(my_res + (c * 32 + y) * HID);
                         }
                     }
                     const float bias_next = last_layer ? 0.0f : __ldg(p.layers[L + 1].bias + ch);   // p_head: padded to 128
-                    if (p.dbg & 64) ptx::mbar_wait(&tmem_full[c], (full_ph >> c) & 1u);
+                    if (dbg & 64) ptx::mbar_wait(&tmem_full[c], (full_ph >> c) & 1u);
                     else ptx::mbar_wait_parked(&tmem_full[c], (full_ph >> c) & 1u);
                     full_ph ^= 1u << c;
                     ptx::tc_fence_after();
-                    if (et == 0) trace_stamp(p.trace, L * 2 + c, 4);
+                    if (et == 0) trace_stamp(trace, L * 2 + c, 4);
                     // my board's 8 column groups: column (y * nb + bs) * 8
                     const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quadl * 32) << 16) + c * 256 + bs * 8;
                     if (mode == MODE_POLICY) {
@@ -559,7 +565,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             heads_epilogue(p, cb0 + bs, bs, nb, ch, lane, quadl, tcol,
                                            reinterpret_cast<float*>(buf) + bs * CB_POLICY_SIZE, s_part + 512 + bs * 32,
                                            s_vpart + bs * 256);
-                        if (et == 0) trace_stamp(p.trace, L * 2 + c, 5);
+                        if (et == 0) trace_stamp(trace, L * 2 + c, 5);
                         continue;
                     }
 
@@ -602,9 +608,9 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     // main pass: (SE scale + residual), ReLU, 16-bit, transpose-store into the chain buffer
                     const bool want_v = (mode == MODE_SE_RES) && ly->v_pre != nullptr;
                     const float vw = want_v ? __ldg(ly->v_w + ch) : 0.0f;
-                    const bool save_res = ly->save_res != 0 && !(p.dbg & 4);
-                    const bool dump = want_v && p.dbg_backbone != nullptr;
-                    if (active && !(p.dbg & 32)) {
+                    const bool save_res = ly->save_res != 0 && !(dbg & 4);
+                    const bool dump = want_v && dbg_backbone != nullptr;
+                    if (active && !(dbg & 32)) {
                         const uint32_t buf_ch = ptx::smem_u32(buf) + kc_off + (cb2 & ~2u);   // the even channel of my pair
 #pragma unroll
                         for (int y = 0; y < 8; ++y) {
@@ -654,7 +660,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
 #pragma unroll
                                 for (int x = 0; x < 8; ++x) {
                                     const uint16_t h16 = static_cast<uint16_t>((x & 1) ? (pk[x >> 1] >> 16) : (pk[x >> 1] & 0xFFFFu));
-                                    p.dbg_backbone[(static_cast<size_t>(cb0 + bs) * HID + ch) * 64 + y * 8 + x] = from16bits<BF16>(h16);
+                                    dbg_backbone[(static_cast<size_t>(cb0 + bs) * HID + ch) * 64 + y * 8 + x] = from16bits<BF16>(h16);
                                 }
                             }
                             // accumulator preset for the next layer of this chain
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async_smem();
                     ptx::mbar_arrive(&chain_ready[c]);
-                    if (et == 0) trace_stamp(p.trace, L * 2 + c, 5);
+                    if (et == 0) trace_stamp(trace, L * 2 + c, 5);
                     if (L == p.num_layers - 2 && c == 0) {
                         // both chains' v_pre rows are complete (last SE layer): value heads of the whole unit,
                         // hidden under chain 1's p_conv MMAs
@@ -687,7 +693,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                 }
             }
         }
-        if (p.cta_times && et == 0) p.cta_times[blockIdx.x * 4 + 2] = globaltimer_ns();
+        if (cta_times && et == 0) cta_times[blockIdx.x * 4 + 2] = globaltimer_ns();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -695,7 +701,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
         ptx::tc_fence_after();
         ptx::tmem_dealloc<512>(tmem_base);
     }
-    if (p.cta_times && threadIdx.x == 0) p.cta_times[blockIdx.x * 4 + 3] = globaltimer_ns();
+    if (cta_times && threadIdx.x == 0) cta_times[blockIdx.x * 4 + 3] = globaltimer_ns();
 }
 
 }  // namespace cb
