@@ -162,6 +162,10 @@ __device__ __forceinline__ void trace_stamp(long long* trace, int item, int slot
     if (trace && blockIdx.x == 0) trace[item * 8 + slot] = clock64();
 }
 
+template <bool V>
+struct BoolC { static constexpr bool v = V; };
+
+
 __device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // Policy + value heads of ONE board, run by its 128-thread board team (the four epilogue warps that
@@ -610,7 +614,11 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     const float vw = want_v ? __ldg(ly->v_w + ch) : 0.0f;
                     const bool save_res = ly->save_res != 0 && !(dbg & 4);
                     const bool dump = want_v && dbg_backbone != nullptr;
-                    if (active && !(dbg & 32)) {
+                    // The main pass is instantiated per (SE + residual, park the output, value conv) combination so that
+                    // its 8 x 60 instructions carry no per-group runtime branches (the epilogue warps share their
+                    // schedulers with the MMA issuer).
+                    auto main_pass = [&](auto se_c, auto save_c, auto wantv_c) {
+                        constexpr bool kSe = decltype(se_c)::v, kSave = decltype(save_c)::v, kWantV = decltype(wantv_c)::v;
                         const uint32_t buf_ch = ptx::smem_u32(buf) + kc_off + (cb2 & ~2u);   // the even channel of my pair
 #pragma unroll
                         for (int y = 0; y < 8; ++y) {
@@ -620,7 +628,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             float v[8];
 #pragma unroll
                             for (int x = 0; x < 8; ++x) v[x] = __uint_as_float(r[x]);
-                            if (mode == MODE_SE_RES) {
+                            if constexpr (kSe) {
                                 const uint32_t w[4] = {rr[y].x, rr[y].y, rr[y].z, rr[y].w};
 #pragma unroll
                                 for (int x = 0; x < 8; ++x) {
@@ -647,8 +655,8 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                                 const uint32_t addr = buf_ch + row * 128 + ((cq ^ (row & 7)) << 4);
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(wd[x]) : "memory");
                             }
-                            if (save_res) __stcg(my_res + (c * 32 + y) * HID, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-                            if (want_v) {
+                            if constexpr (kSave) __stcg(my_res + (c * 32 + y) * HID, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                            if constexpr (kWantV) {
                                 // value 1x1 conv: sum over this warp's 32 channels for each of the 8 pixels
                                 float tv[8];
 #pragma unroll
@@ -667,6 +675,16 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             ptx::tmem_st_32x8_bcast(tcol + y * nb * 8, __float_as_uint(bias_next));
                         }
                         ptx::tmem_st_wait();
+                    };
+                    if (active && !(dbg & 32)) {
+                        if (mode == MODE_SE_RES) {
+                            if (want_v) main_pass(BoolC<true>{}, BoolC<false>{}, BoolC<true>{});
+                            else if (save_res) main_pass(BoolC<true>{}, BoolC<true>{}, BoolC<false>{});
+                            else main_pass(BoolC<true>{}, BoolC<false>{}, BoolC<false>{});
+                        } else {
+                            if (save_res) main_pass(BoolC<false>{}, BoolC<true>{}, BoolC<false>{});
+                            else main_pass(BoolC<false>{}, BoolC<false>{}, BoolC<false>{});
+                        }
                     }
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async_smem();
