@@ -97,8 +97,12 @@ __device__ __forceinline__ void unit_split(const TowerRParams& p, int unit, int&
     const int s = static_cast<int>((static_cast<long long>(unit) * p.num_boards) / p.num_units);
     const int e = static_cast<int>((static_cast<long long>(unit + 1) * p.num_boards) / p.num_units);
     b0 = s;
-    n0 = (e - s + 1) >> 1;
-    n1 = (e - s) >> 1;
+    const int n = e - s;
+    // up to 4 boards fit one chain (256 accumulator columns): a single chain pays MMA + epilogue per layer
+    // (~7 us) but two small chains pay two issue-bound MMA phases (~8.4 us); from 5 boards on the two chains
+    // hide each other's epilogue
+    n0 = n <= 4 ? n : (n + 1) >> 1;
+    n1 = n - n0;
 }
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
