@@ -1457,15 +1457,23 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     cudaMemsetAsync(h->d_boards, 0, (size_t)G * sizeof(cb_board), h->stream);
     mcts_init_kernel<<<(G + 127) / 128, 128, 0, h->stream>>>(mp);
     const int grid = (G + kMctsWarps - 1) / kMctsWarps;
-    auto step = [&]() -> int {
-        mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+    // A simulation step = select, forward, expand.  In steady state the expand of step n and the select of
+    // step n + 1 are one launch (mcts_step_kernel), so a step is two kernels; the run starts with a lone
+    // select and ends with a lone expand, which completes the simulation in flight.
+    auto fused = [&]() -> int {
         int r = enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
         if (r) return r;
-        mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
         return CB_OK;
     };
-    // one eager step (sets the kernels' attributes outside capture)
-    rc = step();
+    const long long target = cfg->max_sims > 0 ? (cfg->max_sims + G - 1) / G : 0;   // steps to run (0 = unbounded)
+    long long done = 0;                        // completed steps; one more is always in flight
+    mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+    // one eager fused step (sets the kernels' attributes outside capture)
+    if (target == 0 || target > 1) {
+        rc = fused();
+        done = 1;
+    }
     cudaError_t ce = cudaStreamSynchronize(h->stream);
     if (rc || ce != cudaSuccess) {
         if (sample_file) fclose(sample_file);
@@ -1477,7 +1485,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     CB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    for (int i = 0; i < kStepsPerGraph && !rc; ++i) rc = step();
+    for (int i = 0; i < kStepsPerGraph && !rc; ++i) rc = fused();
     ce = cudaStreamEndCapture(h->stream, &graph);
     if (!rc && ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
     if (graph) cudaGraphDestroy(graph);
@@ -1488,7 +1496,8 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         return fail(h, CB_ECUDA, std::string("device self-play graph: ") + cudaGetErrorString(ce));
     }
     unsigned long long st[MS_COUNT] = {0};
-    long long steps = 1;
+    float ms_fwd = 0, ms_tree = 0;             // split of one steady-state step (CUDA events, measured once mid-run)
+    bool split_done = false;
     const auto t_start = std::chrono::steady_clock::now();
     auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     for (;;) {
@@ -1496,39 +1505,44 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
         if (ce != cudaSuccess) break;
         if (sample_file && (rc = drain_samples(h, mp, ring_read, ring_host, pending, sample_file))) break;
-        const long long sims = steps * G;
-        if (cfg->max_sims > 0 && sims >= cfg->max_sims) break;
+        // the step in flight is completed after the loop: stop once `done + 1` steps suffice
+        if (target > 0 && done + 1 >= target) break;
         if (cfg->max_games > 0 && (long long)st[MS_GAMES] >= cfg->max_games) break;
         if (cfg->max_seconds > 0 && elapsed() >= cfg->max_seconds) break;
-        if (cfg->max_sims > 0 && (cfg->max_sims - sims) < (long long)kStepsPerGraph * G) {
-            // finish the simulation budget exactly with eager steps
-            if ((rc = step())) break;
-            steps += 1;
+        if (!split_done && done >= 3 * kStepsPerGraph) {
+            cudaEvent_t e[3];
+            for (auto& x : e) cudaEventCreate(&x);
+            cudaEventRecord(e[0], h->stream);
+            rc = enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
+            cudaEventRecord(e[1], h->stream);
+            mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+            cudaEventRecord(e[2], h->stream);
+            ce = cudaStreamSynchronize(h->stream);
+            cudaEventElapsedTime(&ms_fwd, e[0], e[1]);
+            cudaEventElapsedTime(&ms_tree, e[1], e[2]);
+            for (auto& x : e) cudaEventDestroy(x);
+            if (rc || ce != cudaSuccess) break;
+            done += 1;
+            split_done = true;
+            if (getenv("CB_MCTS_TIMES")) fprintf(stderr, "device self-play step: forward %.1f us, expand + select %.1f us\n", ms_fwd * 1e3, ms_tree * 1e3);
+        } else if (target > 0 && target - 1 - done < kStepsPerGraph) {
+            if ((rc = fused())) break;          // finish the simulation budget exactly with eager steps
+            done += 1;
         } else {
             if ((ce = cudaGraphLaunch(gexec, h->stream)) != cudaSuccess) break;
-            steps += kStepsPerGraph;
+            done += kStepsPerGraph;
         }
     }
-    const double secs = elapsed();
-    // split of a steady-state step, measured once with CUDA events: forward kernel vs the two tree kernels
-    float ms_sel = 0, ms_fwd = 0, ms_exp = 0;
+    // complete the simulation in flight
     if (!rc && ce == cudaSuccess) {
-        cudaEvent_t e[4];
-        for (auto& x : e) cudaEventCreate(&x);
-        cudaEventRecord(e[0], h->stream);
-        mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
-        cudaEventRecord(e[1], h->stream);
         rc = enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
-        cudaEventRecord(e[2], h->stream);
-        mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
-        cudaEventRecord(e[3], h->stream);
-        ce = cudaStreamSynchronize(h->stream);
-        cudaEventElapsedTime(&ms_sel, e[0], e[1]);
-        cudaEventElapsedTime(&ms_fwd, e[1], e[2]);
-        cudaEventElapsedTime(&ms_exp, e[2], e[3]);
-        for (auto& x : e) cudaEventDestroy(x);
-        if (getenv("CB_MCTS_TIMES")) fprintf(stderr, "device self-play step: select %.1f us, forward %.1f us, expand %.1f us\n", ms_sel * 1e3, ms_fwd * 1e3, ms_exp * 1e3);
+        if (!rc) mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        if (!rc) ce = cudaMemcpyAsync(st, mp.stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream);
+        if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+        if (!rc && ce == cudaSuccess && sample_file) rc = drain_samples(h, mp, ring_read, ring_host, pending, sample_file);
     }
+    const long long steps = done + 1;
+    const double secs = elapsed();
     cudaGraphExecDestroy(gexec);
     if (sample_file) fclose(sample_file);
     release();
@@ -1545,9 +1559,9 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     out->black_wins = (long long)st[MS_BWINS];
     out->draws = (long long)st[MS_DRAWS];
     out->seconds = secs;
-    const double tot = (double)ms_sel + ms_fwd + ms_exp;
+    const double tot = (double)ms_fwd + ms_tree;
     out->eval_seconds = tot > 0 ? secs * ms_fwd / tot : 0.0;
-    out->tree_seconds = tot > 0 ? secs * (ms_sel + ms_exp) / tot : 0.0;
+    out->tree_seconds = tot > 0 ? secs * ms_tree / tot : 0.0;
     out->mean_batch = steps ? (double)out->nn_evals / (double)steps : 0.0;
     return CB_OK;
 }

@@ -185,16 +185,20 @@ __device__ __forceinline__ int mcts_gen_legal_warp(const cb_board& board, Move* 
 }
 
 // Phase A of a simulation for every game: walk down with PUCT, stop at an unexpanded or terminal node.
-__global__ void __launch_bounds__(32 * kMctsWarps) mcts_select_kernel(const MctsParams p) {
-    __shared__ cb_board s_board[kMctsWarps];
-    __shared__ Move s_pseudo[kMctsWarps][CB_MAX_MOVES];
-    __shared__ Move s_legal[kMctsWarps][CB_MAX_MOVES];
-    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * kMctsWarps + wl;
-    if (g >= p.G) return;
+// Per-warp shared scratch of the tree kernels.
+struct MctsSmem {
+    cb_board board[kMctsWarps];
+    cb_board next[kMctsWarps];
+    Move pseudo[kMctsWarps][CB_MAX_MOVES];
+    Move legal[kMctsWarps][CB_MAX_MOVES];
+};
+
+__device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& sm, int g, int wl, int lane) {
+    Move (&s_pseudo)[kMctsWarps][CB_MAX_MOVES] = sm.pseudo;
+    Move (&s_legal)[kMctsWarps][CB_MAX_MOVES] = sm.legal;
     MNode* nodes = p.nodes + ((size_t)g * 2 + p.arena[g]) * p.node_cap;
     uint32_t* path = p.path + (size_t)g * kMctsMaxDepth;
-    cb_board& board = s_board[wl];
+    cb_board& board = sm.board[wl];
     if (lane < 16) reinterpret_cast<uint64_t*>(&board)[lane] = reinterpret_cast<const uint64_t*>(&p.root[g])[lane];
     __syncwarp();
     uint32_t cur = 0;
@@ -283,6 +287,14 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_select_kernel(const Mcts
     }
 }
 
+__global__ void __launch_bounds__(32 * kMctsWarps) mcts_select_kernel(const MctsParams p) {
+    __shared__ MctsSmem sm;
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kMctsWarps + wl;
+    if (g >= p.G) return;
+    mcts_select_body(p, sm, g, wl, lane);
+}
+
 // Keep the subtree under `child` as the new tree, copied breadth first into the other arena (same node
 // order as the host driver's reroot).  All lanes.
 __device__ __forceinline__ void mcts_reroot(const MctsParams& p, int g, uint32_t child, int lane) {
@@ -319,12 +331,9 @@ __device__ __forceinline__ void mcts_reroot(const MctsParams& p, int g, uint32_t
 
 // Phase C: expand the evaluated leaf with its priors, back the value up; at the end of the move's
 // simulation budget choose and play the move, re-root, detect the end of the game.
-__global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const MctsParams p) {
-    __shared__ Move s_pseudo[kMctsWarps][CB_MAX_MOVES];
-    __shared__ Move s_legal[kMctsWarps][CB_MAX_MOVES];
-    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * kMctsWarps + wl;
-    if (g >= p.G) return;
+__device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& sm, int g, int wl, int lane) {
+    Move (&s_pseudo)[kMctsWarps][CB_MAX_MOVES] = sm.pseudo;
+    Move (&s_legal)[kMctsWarps][CB_MAX_MOVES] = sm.legal;
     MNode* nodes = p.nodes + ((size_t)g * 2 + p.arena[g]) * p.node_cap;
     if (p.wants_eval[g]) {
         const uint32_t* path = p.path + (size_t)g * kMctsMaxDepth;
@@ -425,8 +434,7 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const Mcts
         }
         __syncwarp();
     }
-    __shared__ cb_board s_nb[kMctsWarps];
-    cb_board& nb = s_nb[wl];
+    cb_board& nb = sm.next[wl];
     bool white_moved = false;
     if (lane == 0) {
         const cb_board rb = p.root[g];
@@ -476,6 +484,25 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const Mcts
             p.rng[g] = rs;
         }
     }
+}
+
+__global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const MctsParams p) {
+    __shared__ MctsSmem sm;
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kMctsWarps + wl;
+    if (g >= p.G) return;
+    mcts_expand_body(p, sm, g, wl, lane);
+}
+
+// Steady state: expand the leaf of simulation n, then select the leaf of simulation n + 1, in one launch.
+__global__ void __launch_bounds__(32 * kMctsWarps) mcts_step_kernel(const MctsParams p) {
+    __shared__ MctsSmem sm;
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kMctsWarps + wl;
+    if (g >= p.G) return;
+    mcts_expand_body(p, sm, g, wl, lane);
+    __syncwarp();
+    mcts_select_body(p, sm, g, wl, lane);
 }
 
 }  // namespace cb
