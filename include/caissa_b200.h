@@ -212,6 +212,43 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
  * and the same sample file: moves are logged on the device and the finished games written by the host. */
 int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out);
 
+/* Sequential probability ratio test of the model gate (src/mcts/sprt.rs): trinomial GSPRT as in fishtest.
+ * cb_sprt_llr returns 1 and writes the log-likelihood ratio, or 0 when it is undefined (fewer than 2 games,
+ * zero variance: SprtState::compute_llr == None).  cb_sprt_decision: +1 accept H1 (LLR >= ln((1-beta)/alpha)),
+ * -1 accept H0 (LLR <= ln(beta/(1-alpha))), 0 inconclusive (SprtState::check_decision). */
+int cb_sprt_llr(long long wins, long long losses, long long draws, double elo0, double elo1, double* llr);
+int cb_sprt_decision(long long wins, long long losses, long long draws, double elo0, double elo1, double alpha, double beta);
+
+/* Evaluation match candidate vs current (src/bin/evaluate_models.rs:227-470 one game, :698-800 the SPRT loop),
+ * tree operations on the device: `games` concurrent games, the candidate is white in even-numbered games, every
+ * move is a fresh search of sims_per_move simulations by the mover's model, a child that mates is played at
+ * once, otherwise moves are chosen as in self-play; game ends as in self-play.  With use_sprt the test runs
+ * after every finished game (in finish order) and the decision at the trigger stands. */
+typedef struct cb_match_config {
+    int games;            /* concurrent games */
+    int total_games;      /* stop after this many games */
+    int sims_per_move;
+    int max_plies;        /* 200 */
+    int material_on;
+    int koth;
+    float c_puct;         /* 1.414 */
+    float explore_base;   /* 0.80 */
+    uint64_t seed;
+    int use_sprt;
+    double elo0, elo1, alpha, beta;   /* 0, 10, 0.05, 0.05 */
+    double max_seconds;   /* wall-clock bound (0 = unlimited) */
+} cb_match_config;
+
+typedef struct cb_match_stats {
+    long long games, candidate_wins, current_wins, draws, sims;
+    int decision;         /* +1 H1, -1 H0, 0 inconclusive */
+    int llr_valid;
+    double llr;
+    double seconds;
+} cb_match_stats;
+
+int cb_match_run(cb_handle* candidate, cb_handle* current, const cb_match_config* cfg, cb_match_stats* out);
+
 int         cb_get_timing(const cb_handle* h, cb_timing* out);
 void        cb_reset_timing(cb_handle* h);
 const char* cb_last_error(const cb_handle* h);

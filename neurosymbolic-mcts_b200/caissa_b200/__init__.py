@@ -42,6 +42,19 @@ class SelfplayStats(ctypes.Structure):
                [(n, ctypes.c_double) for n in ("seconds", "eval_seconds", "tree_seconds", "mean_batch")]
 
 
+class MatchConfig(ctypes.Structure):
+    _fields_ = [("games", ctypes.c_int), ("total_games", ctypes.c_int), ("sims_per_move", ctypes.c_int),
+                ("max_plies", ctypes.c_int), ("material_on", ctypes.c_int), ("koth", ctypes.c_int),
+                ("c_puct", ctypes.c_float), ("explore_base", ctypes.c_float), ("seed", ctypes.c_uint64),
+                ("use_sprt", ctypes.c_int), ("elo0", ctypes.c_double), ("elo1", ctypes.c_double),
+                ("alpha", ctypes.c_double), ("beta", ctypes.c_double), ("max_seconds", ctypes.c_double)]
+
+
+class MatchStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_longlong) for n in ("games", "candidate_wins", "current_wins", "draws", "sims")] + \
+               [("decision", ctypes.c_int), ("llr_valid", ctypes.c_int), ("llr", ctypes.c_double), ("seconds", ctypes.c_double)]
+
+
 class CaissaError(RuntimeError):
     pass
 
@@ -77,6 +90,11 @@ SIGNATURES = {
     "cb_chess_make_move": (ctypes.c_int, [_VP, ctypes.c_uint16, _VP]),
     "cb_chess_perft": (ctypes.c_uint64, [_VP, ctypes.c_int]),
     "cb_selfplay_run": (ctypes.c_int, [_VP, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
+    "cb_match_run": (ctypes.c_int, [_VP, _VP, ctypes.POINTER(MatchConfig), ctypes.POINTER(MatchStats)]),
+    "cb_sprt_llr": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_double, ctypes.c_double,
+                                   ctypes.POINTER(ctypes.c_double)]),
+    "cb_sprt_decision": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_double, ctypes.c_double,
+                                        ctypes.c_double, ctypes.c_double]),
     "cb_selfplay_device": (ctypes.c_int, [_VP, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
     "cb_launches_per_forward": (ctypes.c_int, [_VP]),
     "cb_get_timing": (ctypes.c_int, [_VP, ctypes.POINTER(CbTiming)]),
@@ -272,6 +290,16 @@ class Evaluator:
         self._check(self._L.cb_selfplay_run(self._h, ctypes.byref(cfg), ctypes.byref(st)))
         return {n: getattr(st, n) for n, _ in SelfplayStats._fields_}
 
+    def match(self, current, games=256, total_games=256, sims_per_move=200, max_plies=200, material_on=False, koth=False,
+              c_puct=1.414, explore_base=0.80, seed=1, use_sprt=False, elo0=0.0, elo1=10.0, alpha=0.05, beta=0.05,
+              max_seconds=0.0):
+        """Evaluation match: this evaluator is the candidate, `current` the incumbent (cb_match_run)."""
+        cfg = MatchConfig(games, total_games, sims_per_move, max_plies, int(material_on), int(koth), c_puct, explore_base,
+                          seed, int(use_sprt), elo0, elo1, alpha, beta, max_seconds)
+        st = MatchStats()
+        self._check(self._L.cb_match_run(self._h, current._h, ctypes.byref(cfg), ctypes.byref(st)))
+        return {n: getattr(st, n) for n, _ in MatchStats._fields_}
+
     def launches_per_forward(self):
         return self._L.cb_launches_per_forward(self._h)
 
@@ -280,6 +308,18 @@ class Evaluator:
         self._check(self._L.cb_get_timing(self._h, ctypes.byref(t)))
         return {"calls": t.calls, "positions": t.positions, "h2d_ms": t.h2d_ms, "forward_ms": t.forward_ms,
                 "d2h_ms": t.d2h_ms}
+
+
+def sprt_llr(wins, losses, draws, elo0=0.0, elo1=10.0):
+    """SprtState::compute_llr (src/mcts/sprt.rs): the LLR, or None when it is undefined."""
+    v = ctypes.c_double(0.0)
+    rc = load_library().cb_sprt_llr(wins, losses, draws, elo0, elo1, ctypes.byref(v))
+    return v.value if rc == 1 else None
+
+
+def sprt_decision(wins, losses, draws, elo0=0.0, elo1=10.0, alpha=0.05, beta=0.05):
+    """SprtState::check_decision: 'H1', 'H0' or 'inconclusive'."""
+    return {1: "H1", -1: "H0", 0: "inconclusive"}[load_library().cb_sprt_decision(wins, losses, draws, elo0, elo1, alpha, beta)]
 
 
 def chess_startpos():

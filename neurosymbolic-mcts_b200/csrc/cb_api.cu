@@ -437,13 +437,19 @@ int tower_r_units(const cb_handle* h, int B) {
 }
 
 // One launch = the whole forward: planes, conv tower, policy head and value head.
-int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bool use_q) {
+// `src` (default: h itself): the handle whose input block (boards, q) is evaluated — a match evaluates one
+// set of leaves with two models; `stream`: where to launch (default: h's own stream).
+int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bool use_q, const cb_handle* src = nullptr,
+                   cudaStream_t stream = nullptr) {
+    if (!src) src = h;
+    if (!stream) stream = h->stream;
     TowerRParams tp;
-    tp.boards = h->d_boards;
+    tp.boards = src->d_boards;
     tp.maps = h->d_maps_r;
     tp.layers = h->d_layers_r;
     tp.po = po;
     tp.vp = value_params(h, B, material_on, use_q, 0);
+    tp.vp.q = use_q ? src->d_q : nullptr;
     tp.num_layers = (int)h->convs.size() + 1;
     tp.num_boards = B;
     tp.num_units = tower_r_units(h, B);
@@ -460,7 +466,7 @@ int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bo
         h->dtype == CB_DTYPE_BF16 ? (debug ? tower_r_umma_kernel<true, true> : tower_r_umma_kernel<true, false>)
                                   : (debug ? tower_r_umma_kernel<false, true> : tower_r_umma_kernel<false, false>);
     CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerRCfg::kSmemBytes));
-    kern<<<grid, TowerRCfg::kThreads, TowerRCfg::kSmemBytes, h->stream>>>(tp);
+    kern<<<grid, TowerRCfg::kThreads, TowerRCfg::kSmemBytes, stream>>>(tp);
     CB_CUDA(h, cudaGetLastError());
     return CB_OK;
 }
@@ -1407,7 +1413,10 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     mp.koth = cfg->koth;
     mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
     mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
-    mp.node_cap = 32768;
+    {   // a move adds sims_per_move expansions of ~35 (at most 218) children to the subtree kept from the last move
+        const long long want = (long long)cfg->sims_per_move * 160;
+        mp.node_cap = (uint32_t)(want < 32768 ? 32768 : want > 262144 ? 262144 : want);
+    }
     mp.seed = cfg->seed;
     std::vector<void*> owned;
     auto dalloc = [&](void** ptr, size_t bytes) -> int {
@@ -1563,6 +1572,179 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     out->eval_seconds = tot > 0 ? secs * ms_fwd / tot : 0.0;
     out->tree_seconds = tot > 0 ? secs * ms_tree / tot : 0.0;
     out->mean_batch = steps ? (double)out->nn_evals / (double)steps : 0.0;
+    return CB_OK;
+}
+
+// ------------------------------------------------------------------ SPRT (src/mcts/sprt.rs)
+int cb_sprt_llr(long long wins, long long losses, long long draws, double elo0, double elo1, double* llr) {
+    const long long n = wins + losses + draws;
+    if (!llr || wins < 0 || losses < 0 || draws < 0) return CB_EINVAL;
+    if (n < 2) return 0;                                      // compute_llr: None for fewer than 2 games
+    const double nf = (double)n, w = (double)wins, d = (double)draws;
+    const double s0 = 1.0 / (1.0 + pow(10.0, -elo0 / 400.0));
+    const double s1 = 1.0 / (1.0 + pow(10.0, -elo1 / 400.0));
+    const double s_obs = (w + 0.5 * d) / nf;
+    const double var = (w + d / 4.0) / nf - s_obs * s_obs;
+    if (var <= 0.0) return 0;                                 // zero variance: None
+    const double var_s = var / nf;
+    *llr = (s1 - s0) * (2.0 * s_obs - s0 - s1) / (2.0 * var_s);
+    return 1;
+}
+
+int cb_sprt_decision(long long wins, long long losses, long long draws, double elo0, double elo1, double alpha, double beta) {
+    double llr = 0.0;
+    if (cb_sprt_llr(wins, losses, draws, elo0, elo1, &llr) != 1) return 0;
+    const double lower = log(beta / (1.0 - alpha)), upper = log((1.0 - beta) / alpha);
+    return llr >= upper ? 1 : llr <= lower ? -1 : 0;
+}
+
+// Evaluation match between two models with the tree operations on the device: every simulation step runs
+// select, the forward kernel of BOTH models on the same leaves, then expand / play (each move is a fresh
+// search by the mover's model).  Results are consumed in finish order; with use_sprt the test runs after every
+// game and the decision taken at the trigger point stands (src/bin/evaluate_models.rs:698-800).
+int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, cb_match_stats* out) {
+    if (!cand || !curr || !cfg || !out || cand == curr || cfg->games <= 0 || cfg->total_games <= 0 || cfg->sims_per_move <= 0)
+        return CB_EINVAL;
+    cb_handle* h = cand;
+    if (!cand->loaded || !curr->loaded) return fail(h, CB_ESTATE, "weights not loaded");
+    if (cand->device != curr->device) return fail(h, CB_EINVAL, "both models must live on the same device");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    const int G = cfg->games;
+    int rc = ensure_capacity(cand, G);
+    if (!rc) rc = ensure_capacity(curr, G);
+    if (rc) return rc;
+    if (fused_kind(cand) != 3 || fused_kind(curr) != 3)
+        return fail(h, CB_ESTATE, "matches need the resident single-launch forward on both models (128-channel nets, 16-bit mode)");
+    memset(out, 0, sizeof(*out));
+    if (!h->chess_tables_uploaded) {
+        CB_CUDA(h, cudaMemcpyToSymbol(cbchess::d_chess_tables, &cbchess::host_tables(), sizeof(cbchess::Tables)));
+        h->chess_tables_uploaded = true;
+    }
+    CB_CUDA(h, cudaStreamSynchronize(curr->stream));
+    MctsParams mp = {};
+    mp.G = G;
+    mp.sims_per_move = cfg->sims_per_move;
+    mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
+    mp.material_on = cfg->material_on;
+    mp.koth = cfg->koth;
+    mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
+    mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
+    {   // fresh tree every move: sims_per_move expansions of ~35 (at most 218) children
+        const long long want = (long long)cfg->sims_per_move * 64;
+        mp.node_cap = (uint32_t)(want < 8192 ? 8192 : want > 65536 ? 65536 : want);
+    }
+    mp.seed = cfg->seed;
+    mp.match_mode = 1;
+    mp.total_games = cfg->total_games;
+    mp.result_cap = (uint32_t)(4 * G + 64);
+    std::vector<void*> owned;
+    auto dalloc = [&](void** ptr, size_t bytes) -> int {
+        CB_CUDA(h, cudaMalloc(ptr, bytes));
+        owned.push_back(*ptr);
+        return CB_OK;
+    };
+    auto release = [&] { for (void* q : owned) cudaFree(q); };
+    if ((rc = dalloc((void**)&mp.root, (size_t)G * sizeof(cb_board))) ||
+        (rc = dalloc((void**)&mp.nodes, (size_t)G * 2 * mp.node_cap * sizeof(MNode))) ||
+        (rc = dalloc((void**)&mp.n_nodes, (size_t)G * 4)) || (rc = dalloc((void**)&mp.arena, (size_t)G)) ||
+        (rc = dalloc((void**)&mp.history, (size_t)G * kMctsHist * 8)) || (rc = dalloc((void**)&mp.hist_n, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.rng, (size_t)G * 8)) || (rc = dalloc((void**)&mp.ply, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.sims_done, (size_t)G * 4)) || (rc = dalloc((void**)&mp.samples_in_game, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.path, (size_t)G * kMctsMaxDepth * 4)) || (rc = dalloc((void**)&mp.path_n, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.wants_eval, (size_t)G)) || (rc = dalloc((void**)&mp.leaf_moves, (size_t)G * CB_MAX_MOVES * 2)) ||
+        (rc = dalloc((void**)&mp.eval_cnt, (size_t)G * 2)) || (rc = dalloc((void**)&mp.stats, MS_COUNT * 8)) ||
+        (rc = dalloc((void**)&mp.cand_white, (size_t)G)) || (rc = dalloc((void**)&mp.idle, (size_t)G)) ||
+        (rc = dalloc((void**)&mp.games_started, 8)) || (rc = dalloc((void**)&mp.result_cursor, 8)) ||
+        (rc = dalloc((void**)&mp.result_log, (size_t)mp.result_cap * 4))) {
+        release();
+        return rc;
+    }
+    mp.eval_boards = cand->d_boards;
+    mp.eval_q = cand->d_q;
+    mp.eval_idx = cand->d_move_idx;
+    mp.priors = cand->d_priors;
+    mp.v_final = cand->d_vfinal;
+    mp.priors_b = curr->d_priors;
+    mp.v_final_b = curr->d_vfinal;
+    const unsigned long long started0 = (unsigned long long)(cfg->total_games < G ? cfg->total_games : G);
+    cudaMemsetAsync(mp.stats, 0, MS_COUNT * 8, h->stream);
+    cudaMemsetAsync(mp.result_cursor, 0, 8, h->stream);
+    cudaMemcpyAsync(mp.games_started, &started0, 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemsetAsync(cand->d_boards, 0, (size_t)G * sizeof(cb_board), h->stream);
+    mcts_init_kernel<<<(G + 127) / 128, 128, 0, h->stream>>>(mp);
+    const int grid = (G + kMctsWarps - 1) / kMctsWarps;
+    PolicyOut po_a = {}, po_b = {};
+    po_a.move_idx = cand->d_move_idx; po_a.move_cnt = mp.eval_cnt; po_a.priors = cand->d_priors;
+    po_b.move_idx = cand->d_move_idx; po_b.move_cnt = mp.eval_cnt; po_b.priors = curr->d_priors;
+    auto forwards = [&]() -> int {
+        int r = launch_tower_r(cand, G, po_a, cfg->material_on, true);
+        if (!r) r = launch_tower_r(curr, G, po_b, cfg->material_on, true, cand, cand->stream);
+        return r;
+    };
+    auto fused = [&]() -> int {
+        int r = forwards();
+        if (r) return r;
+        mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        return CB_OK;
+    };
+    mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+    rc = fused();
+    cudaError_t ce = cudaStreamSynchronize(h->stream);
+    constexpr int kStepsPerGraph = 8;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    if (!rc && ce == cudaSuccess) {
+        ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+        for (int i = 0; i < kStepsPerGraph && !rc && ce == cudaSuccess; ++i) rc = fused();
+        cudaError_t ce2 = cudaStreamEndCapture(h->stream, &graph);
+        if (ce == cudaSuccess) ce = ce2;
+        if (!rc && ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+    }
+    long long steps = 1, wins = 0, losses = 0, draws = 0;
+    unsigned long long read = 0;
+    int decision = 0;
+    double llr_at_decision = 0.0;
+    bool have_llr = false;
+    std::vector<int> log_host(mp.result_cap);
+    const auto t_start = std::chrono::steady_clock::now();
+    auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    while (!rc && ce == cudaSuccess) {
+        unsigned long long cursor = 0;
+        ce = cudaMemcpyAsync(&cursor, mp.result_cursor, 8, cudaMemcpyDeviceToHost, h->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(log_host.data(), mp.result_log, (size_t)mp.result_cap * 4, cudaMemcpyDeviceToHost, h->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+        if (ce != cudaSuccess) break;
+        if (cursor - read > mp.result_cap) { rc = fail(h, CB_ESTATE, "match result log overflow"); break; }
+        for (; read < cursor && decision == 0; ++read) {
+            const int r = log_host[read % mp.result_cap];
+            if (r > 0) ++wins; else if (r < 0) ++losses; else ++draws;
+            if (cfg->use_sprt) {
+                decision = cb_sprt_decision(wins, losses, draws, cfg->elo0, cfg->elo1, cfg->alpha, cfg->beta);
+                if (decision != 0) have_llr = cb_sprt_llr(wins, losses, draws, cfg->elo0, cfg->elo1, &llr_at_decision) == 1;
+            }
+        }
+        if (decision != 0) break;                                    // results after the trigger do not dilute it
+        if (wins + losses + draws >= cfg->total_games) break;
+        if (cfg->max_seconds > 0 && elapsed() >= cfg->max_seconds) break;
+        if ((ce = cudaGraphLaunch(gexec, h->stream)) != cudaSuccess) break;
+        steps += kStepsPerGraph;
+    }
+    cudaStreamSynchronize(h->stream);
+    const double secs = elapsed();
+    if (gexec) cudaGraphExecDestroy(gexec);
+    release();
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(h, CB_ECUDA, std::string("match: ") + cudaGetErrorString(ce));
+    out->games = wins + losses + draws;
+    out->candidate_wins = wins;
+    out->current_wins = losses;
+    out->draws = draws;
+    out->decision = decision;
+    if (decision != 0 && have_llr) { out->llr = llr_at_decision; out->llr_valid = 1; }
+    else out->llr_valid = cb_sprt_llr(wins, losses, draws, cfg->elo0, cfg->elo1, &out->llr) == 1;
+    out->sims = steps * G;
+    out->seconds = secs;
     return CB_OK;
 }
 

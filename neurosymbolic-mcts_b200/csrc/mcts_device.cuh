@@ -80,6 +80,19 @@ struct MctsParams {
     uint32_t ring_slots;
     unsigned long long* ring_cursor;
     uint32_t* game_serial;          // [G] games finished so far in this slot
+    // model-vs-model evaluation matches (src/bin/evaluate_models.rs:227-470,698-800): every move is a fresh
+    // search by the side to move's model; both models evaluate every step's leaves, the expansion takes the
+    // mover's outputs.  match_mode = 0: self-play.
+    int match_mode;
+    const float* priors_b;          // outputs of the second ("current") model, same layout as priors / v_final
+    const float* v_final_b;
+    uint8_t* cand_white;            // [G] the candidate plays white in the slot's current game (even game index)
+    uint8_t* idle;                  // [G] the slot has no game left to play
+    long long total_games;
+    unsigned long long* games_started;
+    int* result_log;                // finished games in finish order: +1 candidate won, -1 current won, 0 draw
+    uint32_t result_cap;
+    unsigned long long* result_cursor;
 };
 
 // Sample record: u32 game | u32 serial | u16 ply | u16 n (0xFFFF = game end) | f32 material or i32 result |
@@ -145,6 +158,10 @@ __global__ void mcts_init_kernel(const MctsParams p) {
     p.wants_eval[g] = 0;
     p.eval_cnt[g] = 0;
     p.path_n[g] = 0;
+    if (p.match_mode) {
+        p.cand_white[g] = (g & 1) == 0;         // game index g: the candidate is white in even games
+        p.idle[g] = g >= p.total_games;
+    }
 }
 
 // value backed up along the stored path, sign flipping every ply (lane 0)
@@ -196,6 +213,10 @@ struct MctsSmem {
 __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& sm, int g, int wl, int lane) {
     Move (&s_pseudo)[kMctsWarps][CB_MAX_MOVES] = sm.pseudo;
     Move (&s_legal)[kMctsWarps][CB_MAX_MOVES] = sm.legal;
+    if (p.match_mode && p.idle[g]) {
+        if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; }
+        return;
+    }
     MNode* nodes = p.nodes + ((size_t)g * 2 + p.arena[g]) * p.node_cap;
     uint32_t* path = p.path + (size_t)g * kMctsMaxDepth;
     cb_board& board = sm.board[wl];
@@ -335,6 +356,11 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
     Move (&s_pseudo)[kMctsWarps][CB_MAX_MOVES] = sm.pseudo;
     Move (&s_legal)[kMctsWarps][CB_MAX_MOVES] = sm.legal;
     MNode* nodes = p.nodes + ((size_t)g * 2 + p.arena[g]) * p.node_cap;
+    if (p.match_mode && p.idle[g]) return;
+    // whose search is this?  (match mode: the model of the side to move at the root)
+    const bool second = p.match_mode && ((p.root[g].w_to_move != 0) != (p.cand_white[g] != 0));
+    const float* priors = second ? p.priors_b : p.priors;
+    const float* v_final = second ? p.v_final_b : p.v_final;
     if (p.wants_eval[g]) {
         const uint32_t* path = p.path + (size_t)g * kMctsMaxDepth;
         const int path_n = p.path_n[g];
@@ -345,7 +371,7 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
             for (int i = lane; i < n; i += 32) {
                 MNode ch;
                 ch.first_child = 0; ch.visits = 0; ch.value_sum = 0.0f;
-                ch.prior = p.priors[(size_t)g * CB_MAX_MOVES + i];
+                ch.prior = priors[(size_t)g * CB_MAX_MOVES + i];
                 ch.n_children = 0;
                 ch.move = p.leaf_moves[(size_t)g * CB_MAX_MOVES + i];
                 ch.state = 0; ch.term_value = 0; ch.pad = 0;
@@ -362,7 +388,7 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
         }
         __syncwarp();
         if (lane == 0) {
-            mcts_backup(nodes, path, path_n, p.v_final[g]);
+            mcts_backup(nodes, path, path_n, v_final[g]);
             p.sims_done[g]++;
         }
         __syncwarp();
@@ -381,7 +407,15 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
     }
     uint32_t pick = root.first_child;
     uint64_t rs = p.rng[g];
-    if (lane == 0) {
+    bool forced_win = false;
+    if (p.match_mode && lane == 0) {
+        // a child where the opponent is mated is played at once (select_eval_move, evaluate_models.rs:98-116)
+        for (uint32_t i = 0; i < root.n_children && !forced_win; ++i) {
+            const MNode ch = nodes[root.first_child + i];
+            if (ch.state == 2 && ch.term_value < 0) { pick = root.first_child + i; forced_win = true; }
+        }
+    }
+    if (lane == 0 && !forced_win) {
         uint32_t best_v = 0;
         for (uint32_t i = 0; i < root.n_children; ++i) {
             const uint32_t v = nodes[root.first_child + i].visits;
@@ -404,8 +438,8 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
                 }
             }
         }
-        p.samples_in_game[g]++;   // the (board, visit distribution) sample of this move
     }
+    if (lane == 0) p.samples_in_game[g]++;   // the (board, visit distribution) sample of this move
     pick = __shfl_sync(0xffffffffu, pick, 0);
     if (p.sample_ring) {
         unsigned long long slot = 0;
@@ -450,7 +484,18 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
         atomicAdd(&p.stats[MS_MOVES], 1ull);
     }
     __syncwarp();
-    mcts_reroot(p, g, pick, lane);
+    if (p.match_mode) {
+        // the next move is searched by the other model: fresh tree
+        if (lane == 0) {
+            MNode z;
+            memset(&z, 0, sizeof(z));
+            nodes[0] = z;
+            p.n_nodes[g] = 1;
+        }
+        __syncwarp();
+    } else {
+        mcts_reroot(p, g, pick, lane);
+    }
     // game end
     const int n_legal = mcts_gen_legal_warp(nb, s_pseudo[wl], s_legal[wl], lane);
     if (lane == 0) {
@@ -464,7 +509,19 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
             for (int i = 0; i < hn; ++i) reps += (hist[i] == hist[hn - 1]);
             if (reps >= 3 || nb.halfmove >= 100 || p.ply[g] > p.max_plies) result = 0;
         }
-        if (result != 2) {
+        if (result != 2 && p.match_mode) {
+            // result from the candidate's point of view, logged in finish order for the SPRT; next game or idle
+            const int cand = result == 0 ? 0 : ((result > 0) == (p.cand_white[g] != 0) ? 1 : -1);
+            atomicAdd(&p.stats[cand > 0 ? MS_WWINS : cand < 0 ? MS_BWINS : MS_DRAWS], 1ull);
+            atomicAdd(&p.stats[MS_GAMES], 1ull);
+            const unsigned long long slot = atomicAdd(p.result_cursor, 1ull);
+            p.result_log[slot % p.result_cap] = cand;
+            const unsigned long long k = atomicAdd(p.games_started, 1ull);
+            const uint64_t seed = rng_next(rs) ^ ((uint64_t)g << 32);
+            mcts_reset_game(p, g, seed);
+            p.cand_white[g] = (k & 1ull) == 0;
+            if ((long long)k >= p.total_games) p.idle[g] = 1;
+        } else if (result != 2) {
             atomicAdd(&p.stats[result > 0 ? MS_WWINS : result < 0 ? MS_BWINS : MS_DRAWS], 1ull);
             atomicAdd(&p.stats[MS_SAMPLES], (unsigned long long)p.samples_in_game[g]);
             atomicAdd(&p.stats[MS_GAMES], 1ull);

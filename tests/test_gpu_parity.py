@@ -299,6 +299,31 @@ def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material, dtype
     assert np.array_equal(key(rh), key(rd))
 
 
+def test_model_match_on_device(cb, golden):
+    """Candidate-vs-current evaluation match (src/bin/evaluate_models.rs): accounting, determinism, SPRT trigger."""
+    g, blob = golden("6x128_B")
+    ga, blob_a = golden("6x128_A")
+    cand = make_eval(cb, g, blob, "bf16")
+    curr = make_eval(cb, ga, blob_a, "bf16")
+    kw = dict(games=32, total_games=48, sims_per_move=16, max_plies=30, seed=5)
+    a = cand.match(curr, **kw)
+    b = cand.match(curr, **kw)
+    assert a["games"] == 48 == a["candidate_wins"] + a["current_wins"] + a["draws"]
+    for k in ("games", "candidate_wins", "current_wins", "draws"):
+        assert a[k] == b[k]                                   # same seed, same match
+    assert a["decision"] == 0 and a["sims"] > 48 * 16
+    want = cb.sprt_llr(a["candidate_wins"], a["current_wins"], a["draws"])
+    assert (want is None) == (a["llr_valid"] == 0) and (want is None or abs(want - a["llr"]) < 1e-12)
+    # a model against itself with SPRT on and generous error rates: the test stops on a decision or plays all games
+    s = cand.match(cand2 := make_eval(cb, g, blob, "bf16"), games=32, total_games=64, sims_per_move=8, max_plies=20, seed=9,
+                   use_sprt=True, elo0=0.0, elo1=400.0, alpha=0.3, beta=0.3)
+    assert s["games"] <= 64 and s["candidate_wins"] + s["current_wins"] + s["draws"] == s["games"]
+    if s["decision"] != 0:
+        assert cb.sprt_decision(s["candidate_wins"], s["current_wins"], s["draws"], 0.0, 400.0, 0.3, 0.3) == \
+            {1: "H1", -1: "H0"}[s["decision"]]
+    del cand2
+
+
 # ------------------------------------------------------------------ reference-shaped host interface
 def test_neural_net_policy_and_inference_server(cb, golden):
     import threading

@@ -108,3 +108,30 @@ def test_selfplay_driver(cb, golden, tmp_path):
     b = ev.selfplay(games=16, sims_per_move=8, max_plies=12, seed=3, max_sims=16 * 8 * 12, threads=1)
     for k in ("sims", "nn_evals", "terminal_hits", "moves", "games_finished"):
         assert a[k] == b[k]
+
+
+# ------------------------------------------------------------------ SPRT gate (src/mcts/sprt.rs)
+def test_sprt_matches_the_reference_known_answers(cb):
+    """The cases of tests/unit/evaluate_models_tests.rs:494-680 (elo0 0, elo1 10, alpha = beta = 0.05) and the
+    closed form of src/mcts/sprt.rs:70-100 recomputed here."""
+    import math
+    assert cb.sprt_llr(60, 30, 10) > 0.0                       # test_sprt_llr_winning
+    assert cb.sprt_llr(30, 60, 10) < 0.0                       # test_sprt_llr_losing
+    assert cb.sprt_llr(0, 0, 100) is None                      # all draws: zero variance
+    assert abs(cb.sprt_llr(2, 2, 96)) < 2.0
+    assert cb.sprt_llr(1, 0, 0) is None                        # fewer than 2 games
+    assert cb.sprt_decision(80, 10, 10) == "H1"
+    assert cb.sprt_decision(10, 80, 10) == "H0"
+    assert cb.sprt_decision(26, 24, 50) == "inconclusive"
+    upper, lower = math.log(0.95 / 0.05), math.log(0.05 / 0.95)
+    # the in-flight dilution regression: 21W/4L/137D triggers H1, 24W/9L/156D no longer does
+    assert cb.sprt_llr(21, 4, 137) >= upper and cb.sprt_decision(21, 4, 137) == "H1"
+    assert cb.sprt_llr(24, 9, 156) < upper and cb.sprt_decision(24, 9, 156) == "inconclusive"
+    for w, l, d in [(60, 30, 10), (21, 4, 137), (3, 5, 2), (500, 480, 1020)]:
+        n = w + l + d
+        s0, s1 = 1 / (1 + 10 ** (-0.0 / 400)), 1 / (1 + 10 ** (-10.0 / 400))
+        s = (w + 0.5 * d) / n
+        var = (w + d / 4) / n - s * s
+        want = (s1 - s0) * (2 * s - s0 - s1) / (2 * var / n)
+        assert abs(cb.sprt_llr(w, l, d) - want) <= 1e-12 * max(1.0, abs(want))
+    assert lower < 0 < upper

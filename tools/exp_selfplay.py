@@ -22,3 +22,8 @@ for games in (1024, 2048, 4096):
     print("DEVICE tree ops: games %4d : %.2fM sims/s, mean batch %.0f, forward %.2fs tree kernels %.2fs of %.2fs, steps %d, moves %d, games %d" % (
         games, st["sims"] / st["seconds"] / 1e6, st["mean_batch"], st["eval_seconds"], st["tree_seconds"], st["seconds"], st["steps"],
         st["moves"], st["games_finished"]))
+
+cand, curr = ev, ev2
+m = cand.match(curr, games=1024, total_games=1 << 30, sims_per_move=200, seed=3, max_seconds=3.0)
+print("DEVICE match: 1024 concurrent games, two models per step: %.2fM sims/s, %d games finished (W %d / L %d / D %d)" % (
+    m["sims"] / m["seconds"] / 1e6, m["games"], m["candidate_wins"], m["current_wins"], m["draws"]))
