@@ -44,6 +44,7 @@ struct ConvLayer {
     float* w32 = nullptr; // [9][cin][HID] fp32, BN scale folded (exact mode)
     float* bias = nullptr;
     CUtensorMap tm_w;
+    CUtensorMap tm_w_half;   // 64-row box (cluster mode of the resident tower)
 };
 
 }  // namespace
@@ -114,7 +115,9 @@ struct cb_handle {
     // smem-resident fused tower for the 128-channel net (tower_r_umma.cuh)
     void* p_w16r = nullptr;              // p_head weights padded to [128][HID] 16-bit (rows 73.. zero)
     float* p_bias_r = nullptr;           // p_head bias padded to 128
-    CUtensorMap tm_pwr;
+    CUtensorMap tm_pwr, tm_pwr_half;
+    CUtensorMap* d_maps_r_half = nullptr;
+    bool use_cluster = false;
     CUtensorMap* d_maps_r = nullptr;
     cb::TowerRLayer* d_layers_r = nullptr;
     uint4* d_res_scratch = nullptr;
@@ -210,6 +213,10 @@ int make_weight_map(cb_handle* h, ConvLayer& L) {
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+    const cuuint32_t box_half[2] = {64, 64};
+    r = h->encode_tiled(&L.tm_w_half, dt, 2, L.w16, dims, strides, box_half, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(half weights) failed: " + std::to_string((int)r));
     return CB_OK;
 }
 
@@ -387,8 +394,13 @@ int build_tower_tables(cb_handle* h) {
             b.save_res = i < h->blocks - 1;
             if (i == h->blocks - 1) { b.v_w = h->v_w; b.v_pre = h->d_vpre; }
         }
-        free_dev(h->d_maps_r); free_dev(h->d_layers_r);
-        h->d_maps_r = nullptr; h->d_layers_r = nullptr;
+        std::vector<CUtensorMap> mrh(nl + 1);
+        for (int l = 0; l < nl; ++l) mrh[l] = h->convs[l].tm_w_half;
+        mrh[nl] = h->tm_pwr_half;
+        free_dev(h->d_maps_r); free_dev(h->d_layers_r); free_dev(h->d_maps_r_half);
+        h->d_maps_r = nullptr; h->d_layers_r = nullptr; h->d_maps_r_half = nullptr;
+        CB_CUDA(h, cudaMalloc(&h->d_maps_r_half, mrh.size() * sizeof(CUtensorMap)));
+        CB_CUDA(h, cudaMemcpy(h->d_maps_r_half, mrh.data(), mrh.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
         CB_CUDA(h, cudaMalloc(&h->d_maps_r, mr.size() * sizeof(CUtensorMap)));
         CB_CUDA(h, cudaMalloc(&h->d_layers_r, lr.size() * sizeof(TowerRLayer)));
         CB_CUDA(h, cudaMemcpy(h->d_maps_r, mr.data(), mr.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
@@ -446,6 +458,7 @@ int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bo
     TowerRParams tp;
     tp.boards = src->d_boards;
     tp.maps = h->d_maps_r;
+    tp.maps_half = h->d_maps_r_half;
     tp.layers = h->d_layers_r;
     tp.po = po;
     tp.vp = value_params(h, B, material_on, use_q, 0);
@@ -462,11 +475,33 @@ int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bo
     const int grid = tp.num_units < h->sm_count ? tp.num_units : h->sm_count;
     // debug instantiation only when an experiment switch, the timeline, the per-CTA timers or the backbone dump is on
     const bool debug = tp.dbg != 0 || tp.trace || tp.cta_times || tp.dbg_backbone;
-    void (*kern)(const TowerRParams) =
-        h->dtype == CB_DTYPE_BF16 ? (debug ? tower_r_umma_kernel<true, true> : tower_r_umma_kernel<true, false>)
-                                  : (debug ? tower_r_umma_kernel<false, true> : tower_r_umma_kernel<false, false>);
+    // cluster mode (pairs of CTAs share the weight stream): one unit per CTA, an even grid, and every unit with
+    // the same number of chains (all of 5..8 boards, or all of 1..4), so both CTAs of a pair walk the same stages
+    const int n_lo = B / tp.num_units, n_hi = (B + tp.num_units - 1) / tp.num_units;
+    const bool cl2 = h->use_cluster && !debug && tp.num_units == grid && (grid & 1) == 0 && (n_lo >= 5 || n_hi <= 4);
+    void (*kern)(const TowerRParams);
+    if (h->dtype == CB_DTYPE_BF16)
+        kern = cl2 ? tower_r_umma_kernel<true, false, true> : debug ? tower_r_umma_kernel<true, true, false> : tower_r_umma_kernel<true, false, false>;
+    else
+        kern = cl2 ? tower_r_umma_kernel<false, false, true> : debug ? tower_r_umma_kernel<false, true, false> : tower_r_umma_kernel<false, false, false>;
     CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerRCfg::kSmemBytes));
-    kern<<<grid, TowerRCfg::kThreads, TowerRCfg::kSmemBytes, stream>>>(tp);
+    if (cl2) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(grid);
+        lc.blockDim = dim3(TowerRCfg::kThreads);
+        lc.dynamicSmemBytes = TowerRCfg::kSmemBytes;
+        lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        CB_CUDA(h, cudaLaunchKernelEx(&lc, kern, tp));
+    } else {
+        kern<<<grid, TowerRCfg::kThreads, TowerRCfg::kSmemBytes, stream>>>(tp);
+    }
     CB_CUDA(h, cudaGetLastError());
     return CB_OK;
 }
@@ -919,6 +954,11 @@ int cb_create(cb_handle** out, int device, int num_blocks, int hidden, int dtype
     h->use_quad = !(tp && tp[0] == '1');
     const char* tq = getenv("CB_TOWER_QUAD");   // force the global-round-trip towers (debug / comparison)
     h->use_resident = h->use_quad && !(tq && tq[0] == '1');
+    // 2-CTA clusters sharing the weight stream (TMA multicast): measured, not the default — it saves power
+    // (+5 % SM clock under the 1000 W cap) but the lock-step of the two CTAs on a 4-stage ring costs 10 % more
+    // cycles (sustained 195.9 us vs 188.1 us per forward at batch 1024).  CB_CLUSTER=1 turns it on.
+    const char* nc = getenv("CB_CLUSTER");
+    h->use_cluster = nc && nc[0] == '1';
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         delete h;
@@ -961,7 +1001,7 @@ void cb_destroy(cb_handle* h) {
     free_dev(h->p_w16); free_dev(h->p_w16r); free_dev(h->p_bias_r);
     free_dev(h->d_maps); free_dev(h->d_layers);
     free_dev(h->d_maps_q); free_dev(h->d_layers_q);
-    free_dev(h->d_maps_r); free_dev(h->d_layers_r); free_dev(h->d_res_scratch);
+    free_dev(h->d_maps_r); free_dev(h->d_layers_r); free_dev(h->d_res_scratch); free_dev(h->d_maps_r_half);
     free_dev(h->d_flush);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1102,6 +1142,11 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                     return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(padded policy weights) failed");
+                const cuuint32_t box_rh[2] = {64, 64};
+                if (h->encode_tiled(&h->tm_pwr_half, dt, 2, h->p_w16r, dims_r, strides, box_rh, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(padded policy weights, half box) failed");
             }
         }
     }

@@ -78,7 +78,8 @@ struct TowerRLayer {
 
 struct TowerRParams {
     const cb_board* boards;
-    const CUtensorMap* maps;     // weights of every layer (conv tower, then p_head)
+    const CUtensorMap* maps;     // weights of every layer (conv tower, then p_head), box {64 ch, 128 rows}
+    const CUtensorMap* maps_half; // the same tensors with a 64-row box (cluster mode: each CTA loads half a stage)
     const TowerRLayer* layers;
     PolicyOut po;                // policy outputs (full probabilities and / or priors of the legal moves)
     ValueParams vp;              // value head weights and outputs (v_pre is produced and consumed in-kernel)
@@ -313,7 +314,13 @@ __device__ __forceinline__ void value_phase(const TowerRParams& p, int et, int l
 
 // DBG = true: honour the CB_DBG_R experiment switches, the timeline stamps and the backbone dump (debug
 // entry points only); the product instantiation compiles all of that out of the hot loops.
-template <bool BF16, bool DBG>
+// CL2 = true (opt-in, CB_CLUSTER=1): launched as clusters of two CTAs (the two SMs of a TPC) that stream the
+// weights TOGETHER: each CTA loads half of every weight stage and TMA multicasts it into both CTAs' rings, so the
+// L2 -> SM weight traffic — a quarter of the kernel's power draw, and the kernel is power-capped — is halved.  A
+// ring slot is refilled when both CTAs' MMAs have released it (commit multicast to both w_empty barriers).
+// Requires the two CTAs to walk the same stage sequence (same number of chains, one unit each): the host
+// checks.  Measured: +5 % SM clock, but the lock-step on a 4-stage ring costs 10 % more cycles: not the default.
+template <bool BF16, bool DBG, bool CL2>
 __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(const TowerRParams p) {
     const int dbg = DBG ? p.dbg : 0;
     long long* const trace = DBG ? p.trace : nullptr;
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
     constexpr int kTapOrder[9] = {4, 3, 5, 1, 0, 2, 7, 6, 8};
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < kWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], CL2 ? 2 : 1); }
         for (int c = 0; c < 2; ++c) {
             ptx::mbar_init(&tmem_full[c], 1);
             ptx::mbar_init(&chain_ready[c], Cfg::kEpiThreads);
@@ -353,6 +360,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
     if (warp == 1) ptx::tmem_alloc<512>(tmem_ptr);
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (CL2) ptx::cluster_sync_all();      // the peer's barriers are initialised before anything targets them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -377,6 +385,12 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             if (ptx::elect_one()) {
                                 if (dbg & 16) {
                                     ptx::mbar_arrive(&w_full[ws]);
+                                } else if constexpr (CL2) {
+                                    // my 64 rows of the stage, delivered to both CTAs; the other 64 arrive from the peer
+                                    const int r64 = static_cast<int>(ptx::cluster_ctarank()) * 64;
+                                    ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::kWBytes);
+                                    ptx::tma_load_2d_mc(w_base + ws * Cfg::kWBytes + r64 * 128, p.maps_half + ly->w_map, &w_full[ws],
+                                                        kc * 64, tap * HID + w_row_off + r64, 3);
                                 } else {
                                     ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::kWBytes);
                                     ptx::tma_load_2d(w_base + ws * Cfg::kWBytes, tm_w, &w_full[ws], kc * 64, tap * HID + w_row_off);
@@ -446,7 +460,8 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                                     for (int k = 0; k < 4; ++k)
                                         ptx::umma_f16_lohi(d_t, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);   // bias preset
                                 }
-                                ptx::umma_commit(w_empty + ws);
+                                if constexpr (CL2) ptx::umma_commit_mc(w_empty + ws, 3);   // release the slot in both CTAs
+                                else ptx::umma_commit(w_empty + ws);
                             }
                             __syncwarp();
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
@@ -719,6 +734,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (CL2) ptx::cluster_sync_all();      // no CTA leaves while its peer may still signal its barriers
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<512>(tmem_base);
