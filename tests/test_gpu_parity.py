@@ -252,6 +252,22 @@ def test_ragged_batch_sizes_are_bit_identical_to_the_full_batch(cb, golden, posi
         np.testing.assert_allclose(pri[lo:hi], want / want.sum(), rtol=2e-6, atol=1e-9)
 
 
+def test_cluster_mode_is_bit_identical(cb, golden, positions, monkeypatch):
+    """CB_CLUSTER=1: pairs of CTAs share the weight stream (TMA multicast, commit multicast).  Same numbers."""
+    g, blob = golden("6x128_B")
+    boards, idx, off, _ = positions
+    ev = make_eval(cb, g, blob, "bf16")
+    monkeypatch.setenv("CB_CLUSTER", "1")
+    evc = make_eval(cb, g, blob, "bf16")
+    monkeypatch.delenv("CB_CLUSTER")
+    for B in (1024, 512, 128, 16, 2048):     # two chains per CTA, one chain per CTA, one board per CTA; 2048: no clusters
+        q = O.static_q(boards[:B])
+        a = ev.eval_leaves(boards[:B], q, idx[:off[B]], off[:B + 1])
+        b = evc.eval_leaves(boards[:B], q, idx[:off[B]], off[:B + 1])
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), B
+
+
 def test_resident_path_equals_host_path(cb, golden, positions):
     g, blob = golden("6x128_B")
     ev = make_eval(cb, g, blob, "bf16")
