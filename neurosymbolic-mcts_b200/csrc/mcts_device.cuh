@@ -164,14 +164,18 @@ __global__ void mcts_init_kernel(const MctsParams p) {
     }
 }
 
-// value backed up along the stored path, sign flipping every ply (lane 0)
-__device__ __forceinline__ void mcts_backup(MNode* nodes, const uint32_t* path, int n, float val) {
-    for (int i = n - 1; i >= 0; --i) {
-        val = -val;
+// Value backed up along the stored path, sign flipping every ply (src/mcts/node.rs:403-424).  The updates of
+// the path's nodes are independent, so the lanes take one node each (their memory round trips overlap); the
+// arithmetic per node is the host's: value_sum += +-val, visits += 1.  All lanes call this.
+__device__ __forceinline__ void mcts_backup(MNode* nodes, const uint32_t* path, int n, float val, int lane) {
+    for (int i = n - 1 - lane; i >= 0; i -= 32) {
+        // node at path index i gets val negated (n - i) times
+        const float v = ((n - i) & 1) ? -val : val;
         MNode& nd = nodes[path[i]];
-        nd.value_sum = __fadd_rn(nd.value_sum, val);
+        nd.value_sum = __fadd_rn(nd.value_sum, v);
         nd.visits++;
     }
+    __syncwarp();
 }
 
 // Legal moves of `board` in generation order: lane 0 generates the pseudo-legal list, the lanes test
@@ -202,6 +206,10 @@ __device__ __forceinline__ int mcts_gen_legal_warp(const cb_board& board, Move* 
 }
 
 // Phase A of a simulation for every game: walk down with PUCT, stop at an unexpanded or terminal node.
+// best still equals first_child because no child was selected by the scan (n_children == 0 cannot reach here; NaN
+// scores could): fall back to loading the node.
+__device__ __forceinline__ bool bi_invalid(uint32_t best, const MNode& n) { return n.n_children == 0 || best < n.first_child; }
+
 // Per-warp shared scratch of the tree kernels.
 struct MctsSmem {
     cb_board board[kMctsWarps];
@@ -225,11 +233,15 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     uint32_t cur = 0;
     int depth = 0;
     if (lane == 0) path[0] = 0;
+    // The node at the top of each level comes from the lane that scanned it as a child one level up (one
+    // dependent memory round trip per level instead of two).
+    MNode n = nodes[0];
     for (;;) {
-        const MNode n = nodes[cur];
         if (n.state != 1 || depth >= kMctsMaxDepth - 1) break;
         uint32_t best = n.first_child;
         bool forced = false;
+        MNode bch;                       // the best child seen by this lane
+        bch.first_child = 0; bch.visits = 0; bch.n_children = 0; bch.move = 0; bch.state = 0; bch.term_value = 0;
         if (depth == 0) {   // every root child gets one visit first
             for (uint32_t base = 0; base < n.n_children && !forced; base += 32) {
                 const uint32_t i = base + lane;
@@ -246,7 +258,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
                 const MNode ch = nodes[n.first_child + i];
                 const float q = ch.visits ? __fdiv_rn(ch.value_sum, (float)ch.visits) : 0.0f;
                 const float u = __fadd_rn(q, __fdiv_rn(__fmul_rn(__fmul_rn(p.c_puct, ch.prior), sq), __fadd_rn(1.0f, (float)ch.visits)));
-                if (u > bu) { bu = u; bi = i; }
+                if (u > bu) { bu = u; bi = i; bch = ch; }
             }
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) {
@@ -256,22 +268,40 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
             }
             if (bi != 0xFFFFFFFFu) best = n.first_child + bi;
         }
+        MNode nxt;
+        if (forced || bi_invalid(best, n)) {
+            nxt = nodes[best];
+        } else {
+            const int owner = static_cast<int>((best - n.first_child) & 31u);   // child i was scanned by lane i & 31
+            nxt.first_child = __shfl_sync(0xffffffffu, bch.first_child, owner);
+            nxt.visits = __shfl_sync(0xffffffffu, bch.visits, owner);
+            const uint32_t pk = __shfl_sync(0xffffffffu, (uint32_t)bch.n_children | ((uint32_t)bch.move << 16), owner);
+            const uint32_t st = __shfl_sync(0xffffffffu, (uint32_t)bch.state | ((uint32_t)(uint8_t)bch.term_value << 8), owner);
+            nxt.n_children = (uint16_t)(pk & 0xFFFFu);
+            nxt.move = (uint16_t)(pk >> 16);
+            nxt.state = (uint8_t)(st & 0xFFu);
+            nxt.term_value = (int8_t)(st >> 8);
+            nxt.value_sum = 0.0f; nxt.prior = 0.0f; nxt.pad = 0;
+        }
         if (lane == 0) {
             cb_board nb;
-            cbchess::make_move_hd(board, nodes[best].move, &nb);
+            cbchess::make_move_hd(board, nxt.move, &nb);
             board = nb;
             path[depth + 1] = best;
         }
         __syncwarp();
         cur = best;
+        n = nxt;
         ++depth;
     }
     const int path_n = depth + 1;
     MNode& leaf = nodes[cur];
-    const uint8_t leaf_state = leaf.state;
+    const uint8_t leaf_state = n.state;
+    const int8_t leaf_term = n.term_value;
     if (leaf_state == 2 || leaf_state == 1) {   // terminal (or the depth cap): back its value up again
+        __syncwarp();
+        mcts_backup(nodes, path, path_n, leaf_state == 2 ? (float)leaf_term : 0.0f, lane);
         if (lane == 0) {
-            mcts_backup(nodes, path, path_n, leaf_state == 2 ? (float)leaf.term_value : 0.0f);
             atomicAdd(&p.stats[MS_TERMINAL], 1ull);
             p.sims_done[g]++;
             p.wants_eval[g] = 0;
@@ -279,12 +309,16 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         }
         return;
     }
-    const int n = mcts_gen_legal_warp(board, s_pseudo[wl], s_legal[wl], lane);
-    if (n == 0) {   // mate / stalemate
+    const int n_moves = mcts_gen_legal_warp(board, s_pseudo[wl], s_legal[wl], lane);
+    if (n_moves == 0) {   // mate / stalemate
+        const int tv = cbchess::in_check_hd(board, board.w_to_move ? 0 : 1) ? -1 : 0;
         if (lane == 0) {
             leaf.state = 2;
-            leaf.term_value = cbchess::in_check_hd(board, board.w_to_move ? 0 : 1) ? -1 : 0;
-            mcts_backup(nodes, path, path_n, (float)leaf.term_value);
+            leaf.term_value = (int8_t)tv;
+        }
+        __syncwarp();
+        mcts_backup(nodes, path, path_n, (float)tv, lane);
+        if (lane == 0) {
             atomicAdd(&p.stats[MS_TERMINAL], 1ull);
             p.sims_done[g]++;
             p.wants_eval[g] = 0;
@@ -293,7 +327,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         return;
     }
     const bool wtm = board.w_to_move != 0;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n_moves; i += 32) {
         const Move m = s_legal[wl][i];
         p.leaf_moves[(size_t)g * CB_MAX_MOVES + i] = m;
         p.eval_idx[(size_t)g * CB_MAX_MOVES + i] = (uint16_t)cbchess::policy_index_hd(m, wtm);
@@ -301,7 +335,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     if (lane < 16) reinterpret_cast<uint64_t*>(&p.eval_boards[g])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
     if (lane == 0) {
         p.eval_q[g] = p.material_on ? __fdiv_rn((float)static_pesto_cp_dev(board), 100.0f) : 0.0f;
-        p.eval_cnt[g] = (uint16_t)n;
+        p.eval_cnt[g] = (uint16_t)n_moves;
         p.path_n[g] = path_n;
         p.wants_eval[g] = 1;
         atomicAdd(&p.stats[MS_EVALS], 1ull);
@@ -387,10 +421,8 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
             atomicAdd(&p.stats[MS_OVERFLOW], 1ull);   // arena full: the leaf stays unexpanded (evaluated again later)
         }
         __syncwarp();
-        if (lane == 0) {
-            mcts_backup(nodes, path, path_n, v_final[g]);
-            p.sims_done[g]++;
-        }
+        mcts_backup(nodes, path, path_n, v_final[g], lane);
+        if (lane == 0) p.sims_done[g]++;
         __syncwarp();
     }
     if (p.sims_done[g] < p.sims_per_move) return;
