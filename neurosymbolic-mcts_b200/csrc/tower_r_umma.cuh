@@ -261,54 +261,69 @@ __device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board,
     }
 }
 
-// Value head of every board of the unit, run by the whole epilogue team once both chains' v_pre rows are
-// complete: threads [0, 256) take chain 0, [256, 512) chain 1; a thread owns one of the 256 hidden units and
-// applies each FC weight it loads to the (up to) 4 boards of its chain.
+// Value head of every board of the unit (both chains: up to 8 boards), run by the whole epilogue team once both
+// chains' v_pre rows are complete.  Thread = (hidden unit j of 256, half of the 65 inputs): every FC weight is
+// loaded once per CTA and applied to all 8 boards; the second half's partial sums go through shared memory.
 //   BN(1)+ReLU, cat q, FC 65->256 + ReLU, FC 256->1, k, tanh fusion
 //   (python/model.py:128-132,109-110; src/mcts/tactical_mcts.rs:762-765,787-790)
-__device__ __forceinline__ void value_phase(const TowerRParams& p, int et, int lane, int cb0, int nb, float* s_xT, float* s_red) {
-    const int j = et & 255, vw8 = (et >> 5) & 7;
-    // x[e][b]: e < 64 relu(bn(v_conv)), e = 64 the material scalar q; missing boards read as 0
-    for (int i = j; i < 65 * 4; i += 256) {
-        const int e = i >> 2, b = i & 3;
+// Summation order per board is fixed: (fc_b + inputs 0..32) + inputs 33..64, then a shuffle tree over 32 hidden
+// units and the 8 warps in order.
+__device__ __forceinline__ void value_phase(const TowerRParams& p, int et, int lane, int b0, int nb0, int nb1, float* s_part,
+                                            float* s_xT, float* s_red) {
+    const int j = et & 255, half = et >> 8, vw8 = (et >> 5) & 7;
+    // x[e][slot]: slot = chain * 4 + board; e < 64 relu(bn(v_conv)), e = 64 the material scalar q; empty slots read 0
+    for (int i = et; i < 65 * 8; i += TowerRCfg::kEpiThreads) {
+        const int e = i >> 3, slot = i & 7, c = slot >> 2, b = slot & 3;
         float x = 0.0f;
-        if (b < nb) {
-            const int board = cb0 + b;
+        if (b < (c ? nb1 : nb0)) {
+            const int board = b0 + (c ? nb0 : 0) + b;
             if (e < 64) x = fmaxf((__ldcg(p.vp.v_pre + board * 64 + e) + p.vp.conv_bias) * p.vp.bn_scale + p.vp.bn_bias, 0.0f);
             else x = p.vp.q ? p.vp.q[board] : 0.0f;
         }
         s_xT[i] = x;
     }
     ptx::named_bar_sync(1, TowerRCfg::kEpiThreads);
-    const float fb = __ldg(p.vp.fc_b + j);
-    float h[4] = {fb, fb, fb, fb};
-#pragma unroll 13
-    for (int e = 0; e < 65; ++e) {
-        const float w = __ldg(p.vp.fc_wt + e * 256 + j);
-        const float4 x = *reinterpret_cast<const float4*>(s_xT + e * 4);
-        h[0] = fmaf(w, x.x, h[0]);
-        h[1] = fmaf(w, x.y, h[1]);
-        h[2] = fmaf(w, x.z, h[2]);
-        h[3] = fmaf(w, x.w, h[3]);
+    const float fb = half ? 0.0f : __ldg(p.vp.fc_b + j);
+    float h[8] = {fb, fb, fb, fb, fb, fb, fb, fb};
+    const int e0 = half ? 33 : 0;
+#pragma unroll 11
+    for (int i = 0; i < 33; ++i) {
+        const int e = e0 + i;
+        if (e < 65) {
+            const float w = __ldg(p.vp.fc_wt + e * 256 + j);
+            const float4 xa = *reinterpret_cast<const float4*>(s_xT + e * 8), xb = *reinterpret_cast<const float4*>(s_xT + e * 8 + 4);
+            h[0] = fmaf(w, xa.x, h[0]); h[1] = fmaf(w, xa.y, h[1]); h[2] = fmaf(w, xa.z, h[2]); h[3] = fmaf(w, xa.w, h[3]);
+            h[4] = fmaf(w, xb.x, h[4]); h[5] = fmaf(w, xb.y, h[5]); h[6] = fmaf(w, xb.z, h[6]); h[7] = fmaf(w, xb.w, h[7]);
+        }
     }
-    const float ow = __ldg(p.vp.out_w + j);
+    if (half) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        float t = fmaxf(h[b], 0.0f) * ow;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-        if (lane == 0) s_red[vw8 * 4 + b] = t;
+        for (int s8 = 0; s8 < 8; ++s8) s_part[s8 * 256 + j] = h[s8];
     }
     ptx::named_bar_sync(1, TowerRCfg::kEpiThreads);
-    if (j < nb) {
-        float v = p.vp.out_b;
+    if (!half) {
+        const float ow = __ldg(p.vp.out_w + j);
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += s_red[w * 4 + j];
-        const int board = cb0 + j;
-        const float q = p.vp.q ? p.vp.q[board] : 0.0f;
-        p.vp.v_logit[board] = v;
-        p.vp.k_out[board] = p.vp.k;
-        p.vp.v_final[board] = p.vp.material_on ? tanhf(v + p.vp.k * q) : tanhf(v);
+        for (int s8 = 0; s8 < 8; ++s8) {
+            float t = fmaxf(h[s8] + s_part[s8 * 256 + j], 0.0f) * ow;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            if (lane == 0) s_red[vw8 * 8 + s8] = t;
+        }
+    }
+    ptx::named_bar_sync(1, TowerRCfg::kEpiThreads);
+    if (et < 8) {
+        const int c = et >> 2, b = et & 3;
+        if (b < (c ? nb1 : nb0)) {
+            float v = p.vp.out_b;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += s_red[w * 8 + et];
+            const int board = b0 + (c ? nb0 : 0) + b;
+            const float q = p.vp.q ? p.vp.q[board] : 0.0f;
+            p.vp.v_logit[board] = v;
+            p.vp.k_out[board] = p.vp.k;
+            p.vp.v_final[board] = p.vp.material_on ? tanhf(v + p.vp.k * q) : tanhf(v);
+        }
     }
 }
 
@@ -712,9 +727,8 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     if (L == p.num_layers - 2 && c == 0) {
                         // both chains' v_pre rows are complete (last SE layer): value heads of the whole unit,
                         // hidden under chain 1's p_conv MMAs
-                        const int vc = et >> 8;
-                        value_phase(p, et, lane, b0 + (vc ? nbc0 : 0), vc ? nbc1 : nbc0, s_part + 1024 + vc * 260,
-                                    s_part + 640 + vc * 32);
+                        // (scratch: the SE partial sums and the v_conv staging are dead by now)
+                        value_phase(p, et, lane, b0, nbc0, nbc1, s_part, s_vpart, s_vpart + 528);
                     }
                     if (want_v) {
                         ptx::named_bar_sync(1, kEpi);
