@@ -173,13 +173,14 @@ uint64_t cb_chess_perft(const cb_board* b, int depth);
  * rule (:65-73), sign-flipping backup (src/mcts/node.rs:403-424), mate/stalemate terminals,
  * proportional-or-greedy move choice (src/bin/self_play.rs:343-351,628-650), subtree reuse, and
  * game end on mate/stalemate/3-fold/50-move/max plies (+ KOTH centre, :365-381).  Leaves are
- * evaluated in ONE cb_eval_leaves batch per step.  Tier-1 gates and the Tier-2 q-search are host
- * CPU searches outside this path: material_on feeds the static PeSTO stand-pat term as dM. */
+ * evaluated in ONE cb_eval_leaves batch per step.  dM (material_on) is the static PeSTO stand pat, or with
+ * qsearch = 1 the reference's principal-exchange line on top of it (`--qsearch pe`,
+ * src/mcts/tactical_mcts.rs:715-731); Tier-1 gates and the wider q-searches are host CPU searches outside this path. */
 typedef struct cb_selfplay_config {
     int games;            /* concurrent games in the pool */
     int sims_per_move;    /* 200 / 800 */
     int max_plies;        /* 200 */
-    int material_on;      /* 1: q = static PeSTO/100, V = tanh(v+k*q); 0: vanilla (config 5) */
+    int material_on;      /* 1: V = tanh(v + k*q), q chosen by `qsearch`; 0: vanilla (config 5) */
     int koth;             /* King-of-the-Hill game-end rule */
     int threads;          /* host threads for tree operations (0 = hardware concurrency) */
     float c_puct;         /* 1.414 (TacticalMctsConfig::default) */
@@ -195,6 +196,9 @@ typedef struct cb_selfplay_config {
     cb_handle* aux_handle; /* nullable, pipeline 2 only: a second evaluator with the same weights (own stream and
                              buffers) that serves the second half-pool, so one half's copies and synchronisation
                              overlap the other half's kernel (the reference's multi-instance use) */
+    int qsearch;          /* dM when material_on: 0 static PeSTO/100 (stand pat), 1 principal exchange
+                             (QSearchVariant::PrincipalExchange; leaf input and the sample's material scalar,
+                             src/bin/self_play.rs:315-329) */
 } cb_selfplay_config;
 
 typedef struct cb_selfplay_stats {
@@ -237,6 +241,7 @@ typedef struct cb_match_config {
     int use_sprt;
     double elo0, elo1, alpha, beta;   /* 0, 10, 0.05, 0.05 */
     double max_seconds;   /* wall-clock bound (0 = unlimited) */
+    int qsearch;          /* as cb_selfplay_config.qsearch (src/bin/evaluate_models.rs:343-357) */
 } cb_match_config;
 
 typedef struct cb_match_stats {
@@ -246,6 +251,15 @@ typedef struct cb_match_stats {
     double llr;
     double seconds;
 } cb_match_stats;
+
+/* Principal-exchange material balance: forced_principal_exchange of
+ * src/search/quiescence.rs:756-804 — stand pat, then only the first legal capture of the MVV-LVA ordered list
+ * (src/move_generation.rs:426-446) at every ply, window (-100000, 100000), depth 20 — in pawn units (cp / 100 as
+ * f32).  cb_principal_exchange runs on the calling host thread (nodes nullable: positions visited per board);
+ * cb_principal_exchange_device runs one warp per board on the handle's GPU (host buffers, like cb_eval_leaves).
+ * Both are bit-identical. */
+int cb_principal_exchange(const cb_board* boards, int n, float* q, uint32_t* nodes);
+int cb_principal_exchange_device(cb_handle* h, const cb_board* boards, int n, float* q);
 
 int cb_match_run(cb_handle* candidate, cb_handle* current, const cb_match_config* cfg, cb_match_stats* out);
 

@@ -125,7 +125,7 @@ struct cb_handle {
     unsigned long long* d_cta_times = nullptr;   // set only inside cb_debug_cta_times
     bool tower_r_ready = false;
     bool use_resident = true;
-    bool chess_tables_uploaded = false;  // __constant__ attack tables of the device-side tree kernels
+    bool chess_tables_uploaded = false;  // attack tables of the device-side tree kernels
 
     // pinned staging
     cb_board* h_boards = nullptr;
@@ -1205,6 +1205,37 @@ int cb_pst_eval_cp(cb_handle* h, const cb_board* boards, int B, int32_t* cp) {
     return CB_OK;
 }
 
+// One warp per board: the principal-exchange line of host/qsearch.hpp.
+__global__ void __launch_bounds__(256) principal_exchange_kernel(const cb_board* __restrict__ boards, int n, float* __restrict__ q) {
+    __shared__ cb_board s_b[8], s_nb[8];
+    __shared__ uint8_t s_mailbox[8][64];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + wl;
+    if (i >= n) return;
+    if (lane < 16) reinterpret_cast<uint64_t*>(&s_b[wl])[lane] = reinterpret_cast<const uint64_t*>(&boards[i])[lane];
+    __syncwarp();
+    const int cp = cbchess::principal_exchange_cp_warp(s_b[wl], s_nb[wl], s_mailbox[wl], lane);
+    if (lane == 0) q[i] = __fdiv_rn((float)cp, 100.0f);
+}
+
+int cb_principal_exchange_device(cb_handle* h, const cb_board* boards, int n, float* q) {
+    if (!h || n < 0 || (n > 0 && (!boards || !q))) return CB_EINVAL;
+    if (n == 0) return CB_OK;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->chess_tables_uploaded) {
+        CB_CUDA(h, cudaMemcpyToSymbol(cbchess::d_chess_tables, &cbchess::host_tables(), sizeof(cbchess::Tables)));
+        h->chess_tables_uploaded = true;
+    }
+    int rc = upload_leaves(h, boards, nullptr, n, nullptr, nullptr);
+    if (rc) return rc;
+    if ((rc = ensure_scratch(h, (size_t)n))) return rc;
+    principal_exchange_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(h->d_boards, n, h->d_scratch);
+    CB_CUDA(h, cudaGetLastError());
+    CB_CUDA(h, cudaMemcpyAsync(q, h->d_scratch, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+
 // Device -> host read-back of the per-position scalars and (n_priors > 0) the gathered priors.
 static int read_results(cb_handle* h, int B, size_t n_priors, float* priors, float* v_logit, float* v_final, float* k) {
     float* s = h->h_small;
@@ -1455,6 +1486,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     mp.sims_per_move = cfg->sims_per_move;
     mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     mp.material_on = cfg->material_on;
+    mp.qsearch = cfg->qsearch;
     mp.koth = cfg->koth;
     mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
     mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
@@ -1671,6 +1703,7 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     mp.sims_per_move = cfg->sims_per_move;
     mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     mp.material_on = cfg->material_on;
+    mp.qsearch = cfg->qsearch;
     mp.koth = cfg->koth;
     mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
     mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;

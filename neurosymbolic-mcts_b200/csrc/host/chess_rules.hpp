@@ -2,7 +2,8 @@
 // host self-play driver (selfplay.cpp) and the device-side tree kernels (mcts_device.cuh) run the SAME
 // move generator: identical legal sets in identical order (captures / promotions first), identical
 // make-move side effects (src/make_move.rs:99-185), identical policy indices (src/tensor.rs:82-178).
-// Attack tables (4.6 KB) are a static object on the host and a __constant__ object on the device.
+// Attack tables (6 KB) are a static object on the host and a global-memory object on the device (L1-resident;
+// the warp forms index them with a different square in every lane, which the constant cache would serialise).
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -50,7 +51,7 @@ inline void build_tables(Tables* t) {
 
 const Tables& host_tables();   // chess.cpp
 #if defined(__CUDACC__)
-__constant__ Tables d_chess_tables;   // one CUDA translation unit (cb_api.cu) includes this; uploaded per device there
+__device__ Tables d_chess_tables;   // one CUDA translation unit (cb_api.cu) includes this; uploaded per device there
 #endif
 
 CB_HD const Tables& tables() {

@@ -20,7 +20,7 @@
 #include <vector>
 
 #include "../../../include/caissa_b200.h"
-#include "../pesto_tables.h"
+#include "qsearch.hpp"
 #include "chess.hpp"
 
 using namespace cbchess;
@@ -50,19 +50,9 @@ struct Rng {
     double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
 };
 
-int static_pesto_cp(const cb_board& b) {  // src/eval.rs:93-122 on the host (same tables as the device kernel)
-    int mg[2] = {0, 0}, eg[2] = {0, 0}, phase = 0;
-    for (int c = 0; c < 2; ++c)
-        for (int pt = 0; pt < 6; ++pt)
-            for (uint64_t bb = b.pieces[c * 6 + pt]; bb; bb &= bb - 1) {
-                const int sq = __builtin_ctzll(bb), t = c == 0 ? (sq ^ 56) : sq;
-                mg[c] += CB_MG_VALUE[pt] + CB_MG_PST[pt][t];
-                eg[c] += CB_EG_VALUE[pt] + CB_EG_PST[pt][t];
-                phase += CB_PHASE_INC[pt];
-            }
-    const int mgp = phase < 24 ? phase : 24;
-    const int score = ((mg[0] - mg[1]) * mgp + (eg[0] - eg[1]) * (24 - mgp)) / 24;
-    return b.w_to_move ? score : -score;
+// dM of a position in pawn units: stand pat or the principal-exchange line (qsearch.hpp)
+float material_q(const cb_board& b, int qsearch) {
+    return (float)(qsearch == 1 ? cbchess::principal_exchange_cp(b) : cbchess::pesto_cp(b)) / 100.0f;
 }
 
 struct Game {
@@ -337,6 +327,16 @@ int cb_chess_make_move(const cb_board* b, uint16_t move, cb_board* out) {
 
 uint64_t cb_chess_perft(const cb_board* b, int depth) { return b ? perft(*b, depth) : 0; }
 
+int cb_principal_exchange(const cb_board* boards, int n, float* q, uint32_t* nodes) {
+    if (n < 0 || (n > 0 && (!boards || !q))) return 1;
+    for (int i = 0; i < n; ++i) {
+        uint32_t nd = 0;
+        q[i] = (float)cbchess::principal_exchange_cp(boards[i], &nd) / 100.0f;
+        if (nodes) nodes[i] = nd;
+    }
+    return 0;
+}
+
 int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
     if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
     if (!cb_is_available(h)) return CB_ESTATE;
@@ -392,7 +392,7 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
         for (uint32_t i = 0; i < root.n_children; ++i) total += g.nodes[root.first_child + i].visits;
         Sample s;
         s.board = g.root_board;
-        s.material = cfg->material_on ? (float)static_pesto_cp(g.root_board) / 100.0f : 0.0f;
+        s.material = cfg->material_on ? material_q(g.root_board, cfg->qsearch) : 0.0f;
         if (total > 0)
             for (uint32_t i = 0; i < root.n_children; ++i) {
                 const Node& ch = g.nodes[root.first_child + i];
@@ -473,7 +473,7 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
             Game& g = games[i];
             if (!g.wants_eval) continue;
             j.boards[nb] = g.leaf_board;
-            j.q[nb] = cfg->material_on ? (float)static_pesto_cp(g.leaf_board) / 100.0f : 0.0f;
+            j.q[nb] = cfg->material_on ? material_q(g.leaf_board, cfg->qsearch) : 0.0f;
             j.move_off[nb] = off;
             memcpy(&j.move_idx[off], g.leaf_idx, sizeof(uint16_t) * g.leaf_n);
             off += (uint32_t)g.leaf_n;

@@ -18,7 +18,7 @@
 #include <stdint.h>
 
 #include "host/chess_rules.hpp"
-#include "pesto_tables.h"
+#include "host/qsearch.hpp"
 
 namespace cb {
 
@@ -45,6 +45,7 @@ enum { MS_EVALS = 0, MS_TERMINAL, MS_MOVES, MS_GAMES, MS_SAMPLES, MS_WWINS, MS_B
 
 struct MctsParams {
     int G, sims_per_move, max_plies, material_on, koth;
+    int qsearch;                  // dM: 0 stand pat, 1 principal exchange (host/qsearch.hpp)
     float c_puct;
     double explore_base;
     uint32_t node_cap;              // nodes per arena
@@ -106,19 +107,11 @@ __device__ __forceinline__ uint64_t rng_next(uint64_t& s) {
 }
 __device__ __forceinline__ double rng_uniform(uint64_t& s) { return (double)(rng_next(s) >> 11) * (1.0 / 9007199254740992.0); }
 
-__device__ __forceinline__ int static_pesto_cp_dev(const cb_board& b) {   // src/eval.rs:93-122
-    int mg[2] = {0, 0}, eg[2] = {0, 0}, phase = 0;
-    for (int c = 0; c < 2; ++c)
-        for (int pt = 0; pt < 6; ++pt)
-            for (uint64_t bb = b.pieces[c * 6 + pt]; bb; bb &= bb - 1) {
-                const int sq = cbchess::lsb(bb), t = c == 0 ? (sq ^ 56) : sq;
-                mg[c] += CB_MG_VALUE[pt] + CB_MG_PST[pt][t];
-                eg[c] += CB_EG_VALUE[pt] + CB_EG_PST[pt][t];
-                phase += CB_PHASE_INC[pt];
-            }
-    const int mgp = phase < 24 ? phase : 24;
-    const int score = ((mg[0] - mg[1]) * mgp + (eg[0] - eg[1]) * (24 - mgp)) / 24;
-    return b.w_to_move ? score : -score;
+// dM of the position in `b` (shared memory; overwritten when the exchange line runs) in pawn units.  All lanes.
+__device__ __forceinline__ float mcts_material_q(const MctsParams& p, cb_board& b, cb_board& scratch, uint8_t* mailbox, int lane) {
+    if (!p.material_on) return 0.0f;
+    const int cp = p.qsearch == 1 ? cbchess::principal_exchange_cp_warp(b, scratch, mailbox, lane) : cbchess::pesto_cp_warp(b, mailbox, lane);
+    return __fdiv_rn((float)cp, 100.0f);
 }
 
 // Start a fresh game in slot g (lane 0 only).
@@ -216,6 +209,7 @@ struct MctsSmem {
     cb_board next[kMctsWarps];
     Move pseudo[kMctsWarps][CB_MAX_MOVES];
     Move legal[kMctsWarps][CB_MAX_MOVES];
+    uint8_t mailbox[kMctsWarps][64];   // piece codes of the position under the exchange line
 };
 
 __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& sm, int g, int wl, int lane) {
@@ -333,8 +327,10 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         p.eval_idx[(size_t)g * CB_MAX_MOVES + i] = (uint16_t)cbchess::policy_index_hd(m, wtm);
     }
     if (lane < 16) reinterpret_cast<uint64_t*>(&p.eval_boards[g])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
+    __syncwarp();
+    const float leaf_q = mcts_material_q(p, board, sm.next[wl], sm.mailbox[wl], lane);   // `board` is dead after this
     if (lane == 0) {
-        p.eval_q[g] = p.material_on ? __fdiv_rn((float)static_pesto_cp_dev(board), 100.0f) : 0.0f;
+        p.eval_q[g] = leaf_q;
         p.eval_cnt[g] = (uint16_t)n_moves;
         p.path_n[g] = path_n;
         p.wants_eval[g] = 1;
@@ -482,21 +478,26 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
         for (uint32_t i = lane; i < root.n_children; i += 32) total += nodes[root.first_child + i].visits;
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
-        const cb_board rb = p.root[g];
-        const bool wtm = rb.w_to_move != 0;
+        const bool wtm = p.root[g].w_to_move != 0;
         const uint32_t n = total > 0 ? root.n_children : 0;
         for (uint32_t i = lane; i < n; i += 32) {
             const MNode ch = nodes[root.first_child + i];
             const uint32_t v = ch.visits > 65535u ? 65535u : ch.visits;
             reinterpret_cast<uint32_t*>(rec + 144)[i] = (uint32_t)(uint16_t)cbchess::policy_index_hd(ch.move, wtm) | (v << 16);
         }
-        if (lane < 16) reinterpret_cast<uint64_t*>(rec + 16)[lane] = reinterpret_cast<const uint64_t*>(&p.root[g])[lane];
+        if (lane < 16) {
+            const uint64_t w = reinterpret_cast<const uint64_t*>(&p.root[g])[lane];
+            reinterpret_cast<uint64_t*>(rec + 16)[lane] = w;
+            reinterpret_cast<uint64_t*>(&sm.board[wl])[lane] = w;
+        }
+        __syncwarp();
+        const float root_q = mcts_material_q(p, sm.board[wl], sm.next[wl], sm.mailbox[wl], lane);
         if (lane == 0) {
             reinterpret_cast<uint32_t*>(rec)[0] = (uint32_t)g;
             reinterpret_cast<uint32_t*>(rec)[1] = p.game_serial[g];
             reinterpret_cast<uint16_t*>(rec)[4] = (uint16_t)p.ply[g];
             reinterpret_cast<uint16_t*>(rec)[5] = (uint16_t)n;
-            reinterpret_cast<float*>(rec)[3] = p.material_on ? __fdiv_rn((float)static_pesto_cp_dev(rb), 100.0f) : 0.0f;
+            reinterpret_cast<float*>(rec)[3] = root_q;
         }
         __syncwarp();
     }

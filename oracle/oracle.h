@@ -68,6 +68,14 @@ uint64_t orc_perft(const orc_board* b, int depth);
 int      orc_random_positions(uint64_t seed, int n, int max_plies, orc_board* boards,
                               uint16_t* move_idx, uint32_t* move_off, orc_move* moves_raw);
 
+/* ---- principal-exchange quiescence line (qsearch.c; the "pe" dM search) ---- */
+/* MVV-LVA ordered captures + promotions, src/move_generation.rs:426-446.  *long_list = 1 when the list is longer
+ * than the 20 elements for which the reference's sort is known to keep ties in generation order. */
+int   orc_gen_captures_mvvlva(const orc_board* b, orc_move* out, int* long_list);
+int   orc_principal_exchange(const orc_board* b, int alpha, int beta, int max_depth, uint32_t* nodes,
+                             int* long_list);                       /* src/search/quiescence.rs:756-794; *nodes accumulates */
+float orc_forced_principal_exchange(const orc_board* b, uint32_t* nodes, int* long_list); /* :797-804 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ MAX_MOVES = 256
 
 def build(force=False):
     """Compile the C restatement with gcc (seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in ("codec.c", "chess.c", "oracle.h", "pesto_tables.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("codec.c", "chess.c", "qsearch.c", "oracle.h", "pesto_tables.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
@@ -75,6 +75,14 @@ def lib():
             ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_random_positions.restype = ctypes.c_int
+        ip = ctypes.POINTER(ctypes.c_int)
+        up = ctypes.POINTER(ctypes.c_uint32)
+        L.orc_gen_captures_mvvlva.argtypes = [bp, ctypes.POINTER(ctypes.c_uint16), ip]
+        L.orc_gen_captures_mvvlva.restype = ctypes.c_int
+        L.orc_principal_exchange.argtypes = [bp, ctypes.c_int, ctypes.c_int, ctypes.c_int, up, ip]
+        L.orc_principal_exchange.restype = ctypes.c_int
+        L.orc_forced_principal_exchange.argtypes = [bp, up, ip]
+        L.orc_forced_principal_exchange.restype = ctypes.c_float
         _lib = L
     return _lib
 
@@ -180,6 +188,38 @@ def random_positions(seed, n, max_plies=160):
     assert got == n
     total = int(off[n])
     return boards, idx[:total].copy(), off, raw[:total].copy()
+
+
+def captures_mvvlva(b):
+    """MVV-LVA ordered pseudo-legal captures + promotions -> (moves, list longer than the pinned 20)."""
+    buf = (ctypes.c_uint16 * MAX_MOVES)()
+    long_list = ctypes.c_int(0)
+    n = lib().orc_gen_captures_mvvlva(ctypes.byref(b), buf, ctypes.byref(long_list))
+    return [buf[i] for i in range(n)], bool(long_list.value)
+
+
+def principal_exchange(b, alpha=-100000, beta=100000, max_depth=20):
+    """-> (score_cp, nodes, long_list)."""
+    nodes = ctypes.c_uint32(0)
+    long_list = ctypes.c_int(0)
+    cp = lib().orc_principal_exchange(ctypes.byref(b), alpha, beta, max_depth, ctypes.byref(nodes), ctypes.byref(long_list))
+    return cp, nodes.value, bool(long_list.value)
+
+
+def forced_principal_exchange(b):
+    """-> (pawn units as f32, nodes)."""
+    nodes = ctypes.c_uint32(0)
+    long_list = ctypes.c_int(0)
+    s = lib().orc_forced_principal_exchange(ctypes.byref(b), ctypes.byref(nodes), ctypes.byref(long_list))
+    return float(s), nodes.value
+
+
+def pe_q(boards_u8):
+    """Principal-exchange material scalar of every board (pawn units, side to move)."""
+    q = np.zeros(boards_u8.shape[0], dtype=np.float32)
+    for i in range(boards_u8.shape[0]):
+        q[i] = forced_principal_exchange(array_to_board(boards_u8[i]))[0]
+    return q
 
 
 def static_q(boards_u8, clip=20.0):

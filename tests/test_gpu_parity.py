@@ -291,14 +291,16 @@ def test_resident_path_equals_host_path(cb, golden, positions):
 # ------------------------------------------------------------------ device-side tree operations
 @pytest.mark.parametrize("name,material,dtype,koth", [("6x128_A", False, "bf16", False), ("6x128_B", False, "bf16", False),
                                                       ("6x128_B", True, "bf16", False), ("6x128_B", False, "bf16", True),
-                                                      ("2x128_B", True, "fp32", False), ("10x256_B", False, "bf16", False)])
+                                                      ("2x128_B", True, "fp32", False), ("10x256_B", False, "bf16", False),
+                                                      ("6x128_B", "pe", "bf16", False), ("2x128_B", "pe", "fp32", True)])
 def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material, dtype, koth, tmp_path):
     """Self-play with select / expand / backup / move choice on the device (pipeline 3) must walk exactly the
     trees of the host driver: same evaluator outputs (they do not depend on batch composition), same chess
     rules (shared inline code), same explicitly rounded PUCT arithmetic, same RNG stream => identical counters."""
     g, blob = golden(name)
     ev = make_eval(cb, g, blob, dtype)
-    kw = dict(games=24, sims_per_move=20, max_plies=40, material_on=material, koth=koth, seed=11, max_sims=24 * 20 * 60)
+    kw = dict(games=24, sims_per_move=20, max_plies=40, material_on=bool(material), koth=koth, seed=11,
+              max_sims=24 * 20 * 60, qsearch="pe" if material == "pe" else 0)   # "pe": dM by the exchange line (warp form)
     host = ev.selfplay(threads=1, pipeline=1, sample_path=str(tmp_path / "host.bin"), **kw)
     dev = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "dev.bin"), **kw)
     for k in ("sims", "steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins",
@@ -313,6 +315,21 @@ def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material, dtype
     assert rh.shape == rd.shape and rh.shape[0] == host["samples"] > 0
     key = lambda r: r[np.lexsort(r.T[::-1])]
     assert np.array_equal(key(rh), key(rd))
+
+
+def test_principal_exchange_on_device(cb, golden):
+    """The warp form of the exchange line (one piece per lane) against the host form and the oracle, and the
+    material scalar of a self-play sample file against the oracle."""
+    g, blob = golden("2x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    a, _, _, _ = O.random_positions(20261019, 3000, 200)
+    b, _, _, _ = O.random_positions(5, 1100, 100)
+    boards = np.concatenate([a, b])
+    dev = ev.principal_exchange(boards)
+    assert np.array_equal(dev, cb.principal_exchange(boards))
+    assert np.array_equal(dev[:600], O.pe_q(boards[:600]))
+    assert np.array_equal(ev.principal_exchange(boards[:1]), dev[:1]) and ev.principal_exchange(boards[:0]).shape == (0,)
+    assert (dev != O.static_q(boards, clip=1e9)).mean() > 0.2      # the line does change dM on this corpus
 
 
 def test_model_match_on_device(cb, golden):

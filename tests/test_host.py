@@ -41,6 +41,37 @@ def test_product_legal_lists_equal_oracle(cb):
                                   O.boards_to_array([O.make_move(O.array_to_board(boards[i]), m)])[0])
 
 
+PE_FENS = [START, POS1, POS2, POS3, POS4, POS5,
+           "4k3/8/8/8/4n3/3P4/8/4K3 w - - 0 1", "4k3/8/8/3p4/2p5/8/8/3QK3 w - - 0 1",       # ext_qsearch_tests.rs:321,333
+           "4k3/8/8/8/8/8/8/r3K2R w K - 0 1", "1n2k3/2P5/8/8/8/8/8/4K3 w - - 0 1",          # :345,:561
+           "r3k3/8/8/1N6/8/8/8/4K3 w - - 0 1", "4k3/8/8/8/8/8/8/4K3 w - - 0 1",             # :368,:550
+           "rnbqkb1r/pppp1ppp/8/4p3/2B1N3/8/PPPP1PPP/R1BQK1NR b KQkq - 0 4",                # :421
+           "r1b2rk1/pp2nppp/2pBp3/q7/1nP4P/5BN1/P4P2/R2QK2R w KQ - 0 15",                   # :425
+           "7k/1p1b1Qp1/1r6/p4pq1/1b1Np2p/4P3/K1rNR1PP/3R4 w - - 0 36",                     # :402
+           "4k3/8/8/3pP3/8/8/8/4K3 w - d6 0 1",                                             # en passant is the only capture
+           "4r1k1/8/8/8/8/8/4R3/4K3 b - - 0 1", "4r2k/8/8/8/7b/8/4R3/4K3 w - - 0 1",        # pinned capturer
+           "3r2k1/8/8/8/8/8/3p4/4K3 w - - 0 1", "1r2k3/P7/8/8/8/8/8/4K3 w - - 0 1"]          # defended piece next to the king; promotion choices
+
+
+def test_principal_exchange_equals_the_oracle(cb):
+    """Product (key order, no list) against oracle/qsearch.c (list + stable sort): score and positions visited."""
+    a, _, _, _ = O.random_positions(20261019, 2500, 200)
+    b, _, _, _ = O.random_positions(99, 1500, 120)
+    boards = np.concatenate([a, b, np.stack([u8(f) for f in PE_FENS])])
+    q, nodes = cb.principal_exchange(boards, want_nodes=True)
+    first_illegal = deep = 0
+    for i in range(boards.shape[0]):
+        ob = O.array_to_board(boards[i])
+        want_q, want_nodes = O.forced_principal_exchange(ob)
+        assert q[i] == np.float32(want_q) and nodes[i] == want_nodes, i
+        caps, long_list = O.captures_mvvlva(ob)
+        assert not long_list
+        first_illegal += bool(caps) and caps[0] not in O.legal_moves(ob)
+        deep += want_nodes >= 4
+    assert first_illegal > 20 and deep > 200     # the corpus exercises the retry and real exchanges
+    assert cb.principal_exchange(boards[:0]).shape == (0,)
+
+
 @pytest.fixture(scope="module")
 def host_test_exe(cb):
     exe = os.path.join(REPO, "tests", "cpp", "_host_mirror_test")
