@@ -303,7 +303,7 @@ def main():
     # tree operations on the device (select / expand / backup / move choice as two kernels around the forward
     # kernel, no host work per simulation), and beside it the host-driven pool (two half-pools of 512 games,
     # each with its own evaluator handle) whose rate depends on the host cores available per GPU.
-    sp = sp_host = sp_koth = None
+    sp = sp_host = sp_koth = sp_two = sp_two_pe = None
     nthreads = max(1, (os.cpu_count() or 1) // world - 2)
     if args.selfplay_seconds > 0:
         barrier()
@@ -317,19 +317,30 @@ def main():
         sp_koth = ev.selfplay(games=args.selfplay_games, sims_per_move=800, material_on=False, koth=True, seed=201 + rank,
                               max_seconds=args.selfplay_seconds, pipeline=3)
         barrier()
+        # two pools of that many games each: one pool's tree kernel runs beside the other pool's forward kernel;
+        # vanilla, and with the material term from the principal-exchange q-search run on the device for every leaf
+        sp_two = ev.selfplay(games=2 * args.selfplay_games, sims_per_move=200, material_on=False, seed=301 + rank,
+                             max_seconds=args.selfplay_seconds, pipeline=4)
+        barrier()
+        sp_two_pe = ev.selfplay(games=2 * args.selfplay_games, sims_per_move=200, material_on=True, qsearch="pe",
+                                seed=401 + rank, max_seconds=args.selfplay_seconds, pipeline=4)
+        barrier()
     ev2.close()
 
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3, launch_ms, e2e_sync_s * 1e3, sp["seconds"] if sp else 0.0,
-                      sp_host["seconds"] if sp_host else 0.0, sp_koth["seconds"] if sp_koth else 0.0],
+                      sp_host["seconds"] if sp_host else 0.0, sp_koth["seconds"] if sp_koth else 0.0,
+                      sp_two["seconds"] if sp_two else 0.0, sp_two_pe["seconds"] if sp_two_pe else 0.0],
                      dtype=torch.float64, device="cuda")
     tot = torch.tensor([sp["sims"] if sp else 0, sp["nn_evals"] if sp else 0, sp_host["sims"] if sp_host else 0,
-                        sp_koth["sims"] if sp_koth else 0],
+                        sp_koth["sims"] if sp_koth else 0, sp_two["sims"] if sp_two else 0,
+                        sp_two_pe["sims"] if sp_two_pe else 0],
                        dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds, sp_host_seconds, sp_koth_seconds = [float(x) for x in t.tolist()]
+    (dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds, sp_host_seconds, sp_koth_seconds, sp_two_seconds,
+     sp_two_pe_seconds) = [float(x) for x in t.tolist()]
     value = world * B * K / (dev_ms * 1e-3)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     # off the hot path: the one exchange the multi-GPU design has (training-sample gather over NCCL)
@@ -378,6 +389,12 @@ def main():
                                 "forward_fraction": sp["eval_seconds"] / max(sp["seconds"], 1e-9),
                                 "host_driven_sims_per_s": float(tot[2].item()) / max(sp_host_seconds, 1e-9),
                                 "koth_800_sims_per_move_sims_per_s": float(tot[3].item()) / max(sp_koth_seconds, 1e-9),
+                                "two_pools_sims_per_s": float(tot[4].item()) / max(sp_two_seconds, 1e-9),
+                                "two_pools_material_pe_sims_per_s": float(tot[5].item()) / max(sp_two_pe_seconds, 1e-9),
+                                "two_pools_games_per_gpu": 2 * args.selfplay_games,
+                                "two_pools_mode": "cb_selfplay_run pipeline 4: two pools of games_per_gpu games alternate, "
+                                                  "the tree kernel of one beside the forward kernel of the other; "
+                                                  "material_pe: dM by the principal-exchange line on the device",
                                 "host_threads_per_gpu": nthreads}
         if gathered is not None:
             line["nccl_sample_gather_records"] = gathered

@@ -192,7 +192,9 @@ typedef struct cb_selfplay_config {
     const char* sample_path; /* nullable: append finished games as 5763-f32 records (src/training_data.rs:24-60) */
     int pipeline;         /* 0/1: lock step (select, evaluate, expand); 2: two half-pools, the tree work of one
                              half runs on the host while the other half's leaves are on the GPU; 3: tree
-                             operations on the device (cb_selfplay_device) */
+                             operations on the device (cb_selfplay_device); 4: the same with the games split in
+                             two pools that alternate, one pool's tree kernel running beside the other pool's
+                             forward kernel (needs an even number of games; same games, same trees as 3) */
     cb_handle* aux_handle; /* nullable, pipeline 2 only: a second evaluator with the same weights (own stream and
                              buffers) that serves the second half-pool, so one half's copies and synchronisation
                              overlap the other half's kernel (the reference's multi-instance use) */

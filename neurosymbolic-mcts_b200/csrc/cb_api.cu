@@ -451,21 +451,27 @@ int tower_r_units(const cb_handle* h, int B) {
 // One launch = the whole forward: planes, conv tower, policy head and value head.
 // `src` (default: h itself): the handle whose input block (boards, q) is evaluated — a match evaluates one
 // set of leaves with two models; `stream`: where to launch (default: h's own stream).
+// `board0`: evaluate the boards [board0, board0 + B) of the input block, results at the same offsets (`po` is passed
+// already offset); `unit_cap` > 0 bounds the grid (a two-pool self-play run leaves SMs to the other pool's tree kernel).
 int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bool use_q, const cb_handle* src = nullptr,
-                   cudaStream_t stream = nullptr) {
+                   cudaStream_t stream = nullptr, int board0 = 0, int unit_cap = 0) {
     if (!src) src = h;
     if (!stream) stream = h->stream;
     TowerRParams tp;
-    tp.boards = src->d_boards;
+    tp.boards = src->d_boards + board0;
     tp.maps = h->d_maps_r;
     tp.maps_half = h->d_maps_r_half;
     tp.layers = h->d_layers_r;
     tp.po = po;
     tp.vp = value_params(h, B, material_on, use_q, 0);
-    tp.vp.q = use_q ? src->d_q : nullptr;
+    tp.vp.q = use_q ? src->d_q + board0 : nullptr;
+    tp.vp.v_logit += board0;
+    tp.vp.v_final += board0;
+    tp.vp.k_out += board0;
     tp.num_layers = (int)h->convs.size() + 1;
     tp.num_boards = B;
     tp.num_units = tower_r_units(h, B);
+    if (unit_cap > 0 && tp.num_units > unit_cap && (long long)unit_cap * 8 >= B) tp.num_units = unit_cap;
     tp.res_scratch = h->d_res_scratch;
     tp.dbg_backbone = h->d_dbg_backbone;
     tp.trace = h->d_trace;
@@ -1474,8 +1480,12 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
     CB_CUDA(h, cudaSetDevice(h->device));
     const int G = cfg->games;
+    const int pools = cfg->pipeline == 4 ? 2 : 1;
+    if (pools == 2 && (G & 1)) return fail(h, CB_EINVAL, "two pools need an even number of games");
     int rc = ensure_capacity(h, G);
     if (rc) return rc;
+    if (pools == 2 && fused_kind(h) != 3)
+        return fail(h, CB_ESTATE, "two pools need the resident single-launch forward (128-channel nets, 16-bit mode)");
     memset(out, 0, sizeof(*out));
     if (!h->chess_tables_uploaded) {
         CB_CUDA(h, cudaMemcpyToSymbol(cbchess::d_chess_tables, &cbchess::host_tables(), sizeof(cbchess::Tables)));
@@ -1483,6 +1493,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     }
     MctsParams mp = {};
     mp.G = G;
+    mp.gn = G;
     mp.sims_per_move = cfg->sims_per_move;
     mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     mp.material_on = cfg->material_on;
@@ -1542,21 +1553,71 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     cudaMemsetAsync(mp.stats, 0, MS_COUNT * 8, h->stream);
     cudaMemsetAsync(h->d_boards, 0, (size_t)G * sizeof(cb_board), h->stream);
     mcts_init_kernel<<<(G + 127) / 128, 128, 0, h->stream>>>(mp);
-    const int grid = (G + kMctsWarps - 1) / kMctsWarps;
     // A simulation step = select, forward, expand.  In steady state the expand of step n and the select of
     // step n + 1 are one launch (mcts_step_kernel), so a step is two kernels; the run starts with a lone
     // select and ends with a lone expand, which completes the simulation in flight.
+    //
+    // Two pools (pipeline 4): the games are split in two halves that alternate — while the forward kernel of one
+    // half runs, the tree kernel of the other half runs beside it.  The forward kernel takes a whole SM per CTA
+    // (shared memory), so it is launched on ceil(Gp / 8) SMs (8 boards per CTA, its most efficient unit) and the
+    // tree kernel is launched as its PROGRAMMATIC DEPENDENT: it is scheduled once every forward CTA is resident
+    // and so lands on the SMs the forward leaves free.  One stream:
+    //     fwd(1) , step(0)* , fwd(0) , step(1)* , ...          * = programmatic dependent of the kernel before it
+    // step(p) reads the results of fwd(p), which completed before the forward kernel it runs beside started.
+    const int Gp = G / pools;
+    const int grid = (Gp + kMctsWarps - 1) / kMctsWarps;
+    unsigned int* pdl_done = nullptr;          // [2] wrapping counters of finished warps (mcts_step_kernel)
+    if ((rc = dalloc((void**)&pdl_done, 8))) { if (sample_file) fclose(sample_file); release(); return rc; }
+    cudaMemsetAsync(pdl_done, 0, 8, h->stream);
+    const int unit_cap = pools == 2 ? std::max(1, std::min(h->sm_count, (Gp + 7) / 8)) : 0;
+    auto pool_params = [&](int pool, bool beside_forward) {
+        MctsParams q = mp;
+        q.g0 = pool * Gp;
+        q.gn = Gp;
+        q.pdl_done = beside_forward ? pdl_done + pool : nullptr;
+        return q;
+    };
+    auto fwd = [&](int pool) -> int {
+        if (pools == 1) return enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
+        PolicyOut po = {};
+        po.move_idx = h->d_move_idx + (size_t)pool * Gp * CB_MAX_MOVES;
+        po.move_off = h->d_move_off;
+        po.priors = h->d_priors + (size_t)pool * Gp * CB_MAX_MOVES;
+        po.move_cnt = mp.eval_cnt + pool * Gp;
+        return launch_tower_r(h, Gp, po, cfg->material_on, true, nullptr, nullptr, pool * Gp, unit_cap);
+    };
+    // the tree kernel of `pool` beside the forward kernel launched just before it
+    auto step_beside = [&](int pool) -> int {
+        const MctsParams q = pool_params(pool, true);
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(grid);
+        lc.blockDim = dim3(32 * kMctsWarps);
+        lc.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        CB_CUDA(h, cudaLaunchKernelEx(&lc, mcts_step_kernel, q));
+        return CB_OK;
+    };
+    // one step of every pool; leaves the run in the state it found it (pool 0 evaluated, the others selected)
     auto fused = [&]() -> int {
-        int r = enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
-        if (r) return r;
-        mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        int r;
+        if (pools == 1) {
+            if ((r = fwd(0))) return r;
+            mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+            return CB_OK;
+        }
+        if ((r = fwd(1)) || (r = step_beside(0)) || (r = fwd(0)) || (r = step_beside(1))) return r;
         return CB_OK;
     };
     const long long target = cfg->max_sims > 0 ? (cfg->max_sims + G - 1) / G : 0;   // steps to run (0 = unbounded)
     long long done = 0;                        // completed steps; one more is always in flight
-    mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+    for (int pool = 0; pool < pools; ++pool) mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
+    if (pools == 2) rc = fwd(0);
     // one eager fused step (sets the kernels' attributes outside capture)
-    if (target == 0 || target > 1) {
+    if (!rc && (target == 0 || target > 1)) {
         rc = fused();
         done = 1;
     }
@@ -1583,7 +1644,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     }
     unsigned long long st[MS_COUNT] = {0};
     float ms_fwd = 0, ms_tree = 0;             // split of one steady-state step (CUDA events, measured once mid-run)
-    bool split_done = false;
+    bool split_done = pools == 2;              // (two pools: the kernels overlap, there is no split to report)
     const auto t_start = std::chrono::steady_clock::now();
     auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     for (;;) {
@@ -1599,9 +1660,9 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
             cudaEvent_t e[3];
             for (auto& x : e) cudaEventCreate(&x);
             cudaEventRecord(e[0], h->stream);
-            rc = enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
+            rc = fwd(0);
             cudaEventRecord(e[1], h->stream);
-            mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+            mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
             cudaEventRecord(e[2], h->stream);
             ce = cudaStreamSynchronize(h->stream);
             cudaEventElapsedTime(&ms_fwd, e[0], e[1]);
@@ -1619,10 +1680,15 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
             done += kStepsPerGraph;
         }
     }
-    // complete the simulation in flight
+    // complete the simulations in flight
     if (!rc && ce == cudaSuccess) {
-        rc = enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
-        if (!rc) mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        if (pools == 2) {
+            rc = fwd(1);
+            for (int pool = 0; pool < 2 && !rc; ++pool) mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
+        } else {
+            rc = fwd(0);
+            if (!rc) mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+        }
         if (!rc) ce = cudaMemcpyAsync(st, mp.stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream);
         if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
         if (!rc && ce == cudaSuccess && sample_file) rc = drain_samples(h, mp, ring_read, ring_host, pending, sample_file);
@@ -1700,6 +1766,7 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     CB_CUDA(h, cudaStreamSynchronize(curr->stream));
     MctsParams mp = {};
     mp.G = G;
+    mp.gn = G;
     mp.sims_per_move = cfg->sims_per_move;
     mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     mp.material_on = cfg->material_on;

@@ -340,7 +340,7 @@ int cb_principal_exchange(const cb_board* boards, int n, float* q, uint32_t* nod
 int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
     if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
     if (!cb_is_available(h)) return CB_ESTATE;
-    if (cfg->pipeline == 3) return cb_selfplay_device(h, cfg, out);
+    if (cfg->pipeline == 3 || cfg->pipeline == 4) return cb_selfplay_device(h, cfg, out);
     memset(out, 0, sizeof(*out));
     const int G = cfg->games;
     const int max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;

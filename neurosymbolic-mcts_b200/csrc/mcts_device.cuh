@@ -46,6 +46,11 @@ enum { MS_EVALS = 0, MS_TERMINAL, MS_MOVES, MS_GAMES, MS_SAMPLES, MS_WWINS, MS_B
 struct MctsParams {
     int G, sims_per_move, max_plies, material_on, koth;
     int qsearch;                  // dM: 0 stand pat, 1 principal exchange (host/qsearch.hpp)
+    int g0, gn;                   // the games [g0, g0 + gn) this launch works on (one pool of a two-pool run)
+    unsigned int* pdl_done;       // nullable.  Set when the launch is a programmatic dependent of the forward kernel of the
+                                  // OTHER pool: the last warp to finish (wrapping counter) waits for that kernel before it
+                                  // exits, so that stream order after this launch still implies the forward's completion —
+                                  // the other warps leave at once and free their SM for the blocks still queued
     float c_puct;
     double explore_base;
     uint32_t node_cap;              // nodes per arena
@@ -341,8 +346,8 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
 __global__ void __launch_bounds__(32 * kMctsWarps) mcts_select_kernel(const MctsParams p) {
     __shared__ MctsSmem sm;
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * kMctsWarps + wl;
-    if (g >= p.G) return;
+    const int g = p.g0 + blockIdx.x * kMctsWarps + wl;
+    if (g >= p.g0 + p.gn) return;
     mcts_select_body(p, sm, g, wl, lane);
 }
 
@@ -579,8 +584,8 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
 __global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const MctsParams p) {
     __shared__ MctsSmem sm;
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * kMctsWarps + wl;
-    if (g >= p.G) return;
+    const int g = p.g0 + blockIdx.x * kMctsWarps + wl;
+    if (g >= p.g0 + p.gn) return;
     mcts_expand_body(p, sm, g, wl, lane);
 }
 
@@ -588,11 +593,17 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const Mcts
 __global__ void __launch_bounds__(32 * kMctsWarps) mcts_step_kernel(const MctsParams p) {
     __shared__ MctsSmem sm;
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * kMctsWarps + wl;
-    if (g >= p.G) return;
+    const int g = p.g0 + blockIdx.x * kMctsWarps + wl;
+    if (g >= p.g0 + p.gn) return;
     mcts_expand_body(p, sm, g, wl, lane);
     __syncwarp();
     mcts_select_body(p, sm, g, wl, lane);
+    if (p.pdl_done) {
+        __syncwarp();
+        unsigned int last = 0;
+        if (lane == 0) last = atomicInc(p.pdl_done, (unsigned int)p.gn - 1u) == (unsigned int)p.gn - 1u;
+        if (__shfl_sync(0xffffffffu, last, 0)) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 }
 
 }  // namespace cb

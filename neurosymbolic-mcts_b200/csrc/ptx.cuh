@@ -268,5 +268,9 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// Programmatic dependent launch: let the dependents of this grid be scheduled / wait for the grids this one depends on.
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace ptx
 }  // namespace cb

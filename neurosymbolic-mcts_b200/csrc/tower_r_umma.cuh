@@ -365,6 +365,9 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
     constexpr int kTapOrder[9] = {4, 3, 5, 1, 0, 2, 7, 6, 8};
 
     if (threadIdx.x == 0) {
+        // this CTA is resident: a kernel launched as a programmatic dependent (the tree kernel of the other game
+        // pool, cb_selfplay_device with two pools) may now take the SMs this grid leaves free; no-op otherwise
+        ptx::grid_launch_dependents();
         for (int s = 0; s < kWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], CL2 ? 2 : 1); }
         for (int c = 0; c < 2; ++c) {
             ptx::mbar_init(&tmem_full[c], 1);

@@ -317,6 +317,28 @@ def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material, dtype
     assert np.array_equal(key(rh), key(rd))
 
 
+@pytest.mark.parametrize("material,qsearch", [(False, 0), (True, "pe")])
+def test_two_pool_self_play_walks_the_same_trees(cb, golden, material, qsearch, tmp_path):
+    """pipeline 4: the games split in two pools whose tree kernels run beside each other's forward kernel
+    (programmatic dependent launch, forward on a bounded grid with a board offset).  Games are independent and
+    the evaluator does not depend on batch composition, so every game must be the one pipeline 3 plays."""
+    g, blob = golden("6x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    kw = dict(games=48, sims_per_move=20, max_plies=40, material_on=material, qsearch=qsearch, seed=11, max_sims=48 * 20 * 60)
+    one = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "one.bin"), **kw)
+    two = ev.selfplay(pipeline=4, sample_path=str(tmp_path / "two.bin"), **kw)
+    for k in ("sims", "steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins",
+              "black_wins", "draws"):
+        assert one[k] == two[k], (k, one[k], two[k])
+    assert two["games_finished"] >= 48
+    ra = np.fromfile(tmp_path / "one.bin", dtype=np.float32).reshape(-1, 5763)
+    rb = np.fromfile(tmp_path / "two.bin", dtype=np.float32).reshape(-1, 5763)
+    key = lambda r: r[np.lexsort(r.T[::-1])]
+    assert ra.shape == rb.shape and np.array_equal(key(ra), key(rb))
+    with pytest.raises(cb.CaissaError):
+        ev.selfplay(pipeline=4, games=47, sims_per_move=4, max_sims=47 * 8)
+
+
 def test_principal_exchange_on_device(cb, golden):
     """The warp form of the exchange line (one piece per lane) against the host form and the oracle, and the
     material scalar of a self-play sample file against the oracle."""
