@@ -201,6 +201,10 @@ typedef struct cb_selfplay_config {
     int qsearch;          /* dM when material_on: 0 static PeSTO/100 (stand pat), 1 principal exchange
                              (QSearchVariant::PrincipalExchange; leaf input and the sample's material scalar,
                              src/bin/self_play.rs:315-329) */
+    int tier1_light;      /* 1: the light Tier-1 gates (the reference's gate at depth 1): a leaf where the side to
+                             move mates in one — or, with koth, steps onto the hill / faces a king already on it —
+                             is terminal (+1 / -1, src/mcts/tactical_mcts.rs:619-708) and a game whose root hits a
+                             gate is adjudicated (src/bin/self_play.rs:241-283) */
 } cb_selfplay_config;
 
 typedef struct cb_selfplay_stats {
@@ -244,6 +248,8 @@ typedef struct cb_match_config {
     double elo0, elo1, alpha, beta;   /* 0, 10, 0.05, 0.05 */
     double max_seconds;   /* wall-clock bound (0 = unlimited) */
     int qsearch;          /* as cb_selfplay_config.qsearch (src/bin/evaluate_models.rs:343-357) */
+    int tier1_light;      /* as cb_selfplay_config.tier1_light; a root that hits a gate is scored as the win it is (the
+                             reference's search returns the winning move there, src/mcts/tactical_mcts.rs:330-420) */
 } cb_match_config;
 
 typedef struct cb_match_stats {
@@ -262,6 +268,11 @@ typedef struct cb_match_stats {
  * Both are bit-identical. */
 int cb_principal_exchange(const cb_board* boards, int n, float* q, uint32_t* nodes);
 int cb_principal_exchange_device(cb_handle* h, const cb_board* boards, int n, float* q);
+/* Light Tier-1 gates of n boards on the calling host thread: out[i] = +1 (the side to move mates in one, or with
+ * koth has its king on / steps onto the hill), -1 (koth: the opponent's king is on the hill), 2 (no gate).
+ * mate_search(board, 1) of src/search/mate_search.rs:64-108 and koth_center_in_n(board, 1) of
+ * src/search/koth.rs:43-65, in the order of src/mcts/tactical_mcts.rs:619-708. */
+int cb_light_gates(const cb_board* boards, int n, int koth, int8_t* out);
 
 int cb_match_run(cb_handle* candidate, cb_handle* current, const cb_match_config* cfg, cb_match_stats* out);
 

@@ -34,7 +34,7 @@ class SelfplayConfig(ctypes.Structure):
                 ("c_puct", ctypes.c_float), ("explore_base", ctypes.c_float), ("seed", ctypes.c_uint64),
                 ("max_sims", ctypes.c_longlong), ("max_games", ctypes.c_longlong), ("max_seconds", ctypes.c_double),
                 ("sample_path", ctypes.c_char_p), ("pipeline", ctypes.c_int), ("aux_handle", ctypes.c_void_p),
-                ("qsearch", ctypes.c_int)]
+                ("qsearch", ctypes.c_int), ("tier1_light", ctypes.c_int)]
 
 
 class SelfplayStats(ctypes.Structure):
@@ -49,7 +49,7 @@ class MatchConfig(ctypes.Structure):
                 ("c_puct", ctypes.c_float), ("explore_base", ctypes.c_float), ("seed", ctypes.c_uint64),
                 ("use_sprt", ctypes.c_int), ("elo0", ctypes.c_double), ("elo1", ctypes.c_double),
                 ("alpha", ctypes.c_double), ("beta", ctypes.c_double), ("max_seconds", ctypes.c_double),
-                ("qsearch", ctypes.c_int)]
+                ("qsearch", ctypes.c_int), ("tier1_light", ctypes.c_int)]
 
 
 class MatchStats(ctypes.Structure):
@@ -78,6 +78,7 @@ SIGNATURES = {
     "cb_pst_eval_cp": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
     "cb_principal_exchange": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
     "cb_principal_exchange_device": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
+    "cb_light_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_stage_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_time_resident": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_time_conv_layers": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
@@ -291,24 +292,24 @@ class Evaluator:
 
     def selfplay(self, games=1024, sims_per_move=200, max_plies=200, material_on=False, koth=False, threads=0,
                  c_puct=1.414, explore_base=0.80, seed=1, max_sims=0, max_games=0, max_seconds=0.0, sample_path=None,
-                 pipeline=1, aux=None, qsearch=0):
+                 pipeline=1, aux=None, qsearch=0, tier1_light=False):
         """Run the self-play pool on this evaluator; returns the stats as a dict.  `aux`: a second Evaluator
         with the same weights that serves the second half-pool in pipeline mode 2.  `qsearch`: 0 stand-pat
         material, 1 principal exchange ("pe")."""
         cfg = SelfplayConfig(games, sims_per_move, max_plies, int(material_on), int(koth), threads, c_puct,
                              explore_base, seed, max_sims, max_games, max_seconds,
                              sample_path.encode() if sample_path else None, pipeline, aux._h if aux is not None else None,
-                             _QSEARCH[qsearch])
+                             _QSEARCH[qsearch], int(tier1_light))
         st = SelfplayStats()
         self._check(self._L.cb_selfplay_run(self._h, ctypes.byref(cfg), ctypes.byref(st)))
         return {n: getattr(st, n) for n, _ in SelfplayStats._fields_}
 
     def match(self, current, games=256, total_games=256, sims_per_move=200, max_plies=200, material_on=False, koth=False,
               c_puct=1.414, explore_base=0.80, seed=1, use_sprt=False, elo0=0.0, elo1=10.0, alpha=0.05, beta=0.05,
-              max_seconds=0.0, qsearch=0):
+              max_seconds=0.0, qsearch=0, tier1_light=False):
         """Evaluation match: this evaluator is the candidate, `current` the incumbent (cb_match_run)."""
         cfg = MatchConfig(games, total_games, sims_per_move, max_plies, int(material_on), int(koth), c_puct, explore_base,
-                          seed, int(use_sprt), elo0, elo1, alpha, beta, max_seconds, _QSEARCH[qsearch])
+                          seed, int(use_sprt), elo0, elo1, alpha, beta, max_seconds, _QSEARCH[qsearch], int(tier1_light))
         st = MatchStats()
         self._check(self._L.cb_match_run(self._h, current._h, ctypes.byref(cfg), ctypes.byref(st)))
         return {n: getattr(st, n) for n, _ in MatchStats._fields_}
@@ -335,6 +336,15 @@ def principal_exchange(boards, want_nodes=False):
     if rc:
         raise CaissaError("cb_principal_exchange failed")
     return (out, nodes) if want_nodes else out
+
+
+def light_gates(boards, koth=False):
+    """Light Tier-1 gates (cb_light_gates): int8 per board, +1 / -1 for the side to move, 2 = no gate."""
+    b = _boards_u8(boards)
+    out = np.empty(b.shape[0], dtype=np.int8)
+    if load_library().cb_light_gates(_ptr(b), b.shape[0], int(koth), _ptr(out)):
+        raise CaissaError("cb_light_gates failed")
+    return out
 
 
 def sprt_llr(wins, losses, draws, elo0=0.0, elo1=10.0):

@@ -1498,6 +1498,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     mp.material_on = cfg->material_on;
     mp.qsearch = cfg->qsearch;
+    mp.tier1_light = cfg->tier1_light;
     mp.koth = cfg->koth;
     mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
     mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
@@ -1771,6 +1772,7 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     mp.material_on = cfg->material_on;
     mp.qsearch = cfg->qsearch;
+    mp.tier1_light = cfg->tier1_light;
     mp.koth = cfg->koth;
     mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
     mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;

@@ -21,6 +21,7 @@
 
 #include "../../../include/caissa_b200.h"
 #include "qsearch.hpp"
+#include "gates.hpp"
 #include "chess.hpp"
 
 using namespace cbchess;
@@ -85,7 +86,7 @@ struct Game {
 };
 
 // One simulation, phase A: walk down with PUCT; stop at an unexpanded or terminal node.
-void select_leaf(Game& g, float c_puct, std::atomic<long long>& terminal_hits) {
+void select_leaf(Game& g, float c_puct, std::atomic<long long>& terminal_hits, bool tier1_light, bool koth) {
     g.path.clear();
     g.wants_eval = false;
     uint32_t cur = 0;
@@ -132,9 +133,16 @@ void select_leaf(Game& g, float c_puct, std::atomic<long long>& terminal_hits) {
         return;
     }
     g.leaf_n = gen_legal(board, g.leaf_moves);
-    if (g.leaf_n == 0) {  // mate / stalemate (MctsNode::new_child terminal test, src/mcts/node.rs:162-177)
+    // mate / stalemate (MctsNode::new_child terminal test, src/mcts/node.rs:162-177), else the light Tier-1 gates
+    // (gates.hpp); with the gates on, an opponent king on the hill is tested before anything else
+    // (src/mcts/tactical_mcts.rs:619-632)
+    int tv = 2;
+    if (tier1_light && koth && (board.pieces[(board.w_to_move ? 1 : 0) * 6 + KING] & kKothCenter)) tv = -1;
+    else if (g.leaf_n == 0) tv = in_check(board, board.w_to_move ? 0 : 1) ? -1 : 0;
+    else if (tier1_light) tv = cbchess::light_gates_hd(board, g.leaf_moves, g.leaf_n, koth);
+    if (tv != 2) {
         leaf.state = 2;
-        leaf.term_value = in_check(board, board.w_to_move ? 0 : 1) ? -1 : 0;
+        leaf.term_value = (int8_t)tv;
         float val = (float)leaf.term_value;
         for (int i = (int)g.path.size() - 1; i >= 0; --i) {
             val = -val;
@@ -337,6 +345,16 @@ int cb_principal_exchange(const cb_board* boards, int n, float* q, uint32_t* nod
     return 0;
 }
 
+int cb_light_gates(const cb_board* boards, int n, int koth, int8_t* out) {
+    if (n < 0 || (n > 0 && (!boards || !out))) return 1;
+    Move mv[kMaxMoves];
+    for (int i = 0; i < n; ++i) {
+        const int nm = gen_legal(boards[i], mv);
+        out[i] = (int8_t)cbchess::light_gates_hd(boards[i], mv, nm, koth != 0);
+    }
+    return 0;
+}
+
 int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
     if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
     if (!cb_is_available(h)) return CB_ESTATE;
@@ -437,11 +455,17 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
         int result = 2;  // 2 = continue
         Move tmp[kMaxMoves];
         if (cfg->koth && (nb.pieces[(white_moved ? 0 : 6) + KING] & kKothCenter)) result = white_moved ? 1 : -1;
-        else if (gen_legal(nb, tmp) == 0) result = in_check(nb, nb.w_to_move ? 0 : 1) ? (white_moved ? 1 : -1) : 0;
         else {
-            int reps = 0;
-            for (uint64_t k : g.history) reps += (k == g.history.back());
-            if (reps >= 3 || nb.halfmove >= 100 || g.ply > max_plies) result = 0;
+            const int n_legal = gen_legal(nb, tmp);
+            if (n_legal == 0) result = in_check(nb, nb.w_to_move ? 0 : 1) ? (white_moved ? 1 : -1) : 0;
+            else {
+                int reps = 0;
+                for (uint64_t k : g.history) reps += (k == g.history.back());
+                if (reps >= 3 || nb.halfmove >= 100 || g.ply > max_plies) result = 0;
+                // the game goes on: a position where the side to move wins at once is adjudicated before it is
+                // searched (Tier-1 pre-check of the self-play loop, src/bin/self_play.rs:241-283, at depth 1)
+                else if (cfg->tier1_light && cbchess::light_gates_hd(nb, tmp, n_legal, cfg->koth != 0) == 1) result = white_moved ? -1 : 1;
+            }
         }
         if (result != 2) {
             finish_game(g, result);
@@ -465,7 +489,7 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
         EvalJob& j = jobs[hf];
         const int g0 = hb[hf], g1 = hb[hf + 1];
         pool.run(g0, g1, [&](int b, int e) {
-            for (int i = b; i < e; ++i) select_leaf(games[i], c_puct, terminal_hits);
+            for (int i = b; i < e; ++i) select_leaf(games[i], c_puct, terminal_hits, cfg->tier1_light != 0, cfg->koth != 0);
         });
         int nb = 0;
         uint32_t off = 0;

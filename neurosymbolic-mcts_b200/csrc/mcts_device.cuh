@@ -19,6 +19,7 @@
 
 #include "host/chess_rules.hpp"
 #include "host/qsearch.hpp"
+#include "host/gates.hpp"
 
 namespace cb {
 
@@ -46,6 +47,7 @@ enum { MS_EVALS = 0, MS_TERMINAL, MS_MOVES, MS_GAMES, MS_SAMPLES, MS_WWINS, MS_B
 struct MctsParams {
     int G, sims_per_move, max_plies, material_on, koth;
     int qsearch;                  // dM: 0 stand pat, 1 principal exchange (host/qsearch.hpp)
+    int tier1_light;              // light Tier-1 gates at the leaves + adjudication at the root (host/gates.hpp)
     int g0, gn;                   // the games [g0, g0 + gn) this launch works on (one pool of a two-pool run)
     unsigned int* pdl_done;       // nullable.  Set when the launch is a programmatic dependent of the forward kernel of the
                                   // OTHER pool: the last warp to finish (wrapping counter) waits for that kernel before it
@@ -309,8 +311,13 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         return;
     }
     const int n_moves = mcts_gen_legal_warp(board, s_pseudo[wl], s_legal[wl], lane);
-    if (n_moves == 0) {   // mate / stalemate
-        const int tv = cbchess::in_check_hd(board, board.w_to_move ? 0 : 1) ? -1 : 0;
+    // mate / stalemate, else the light Tier-1 gates; with the gates on, an opponent king on the hill is tested
+    // before anything else (src/mcts/tactical_mcts.rs:619-632) — same order as the host driver
+    int tv = 2;
+    if (p.tier1_light && p.koth && (board.pieces[(board.w_to_move ? 1 : 0) * 6 + cbchess::KING] & cbchess::kKothCenter)) tv = -1;
+    else if (n_moves == 0) tv = cbchess::in_check_hd(board, board.w_to_move ? 0 : 1) ? -1 : 0;
+    else if (p.tier1_light) tv = cbchess::light_gates_warp(board, s_legal[wl], n_moves, p.koth != 0, lane);
+    if (tv != 2) {
         if (lane == 0) {
             leaf.state = 2;
             leaf.term_value = (int8_t)tv;
@@ -536,6 +543,9 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
     }
     // game end
     const int n_legal = mcts_gen_legal_warp(nb, s_pseudo[wl], s_legal[wl], lane);
+    // a root where the side to move wins at once is adjudicated (src/bin/self_play.rs:241-283 at depth 1; in a match
+    // the reference's search returns the winning move there, src/mcts/tactical_mcts.rs:330-357,400-420: same result)
+    const int gate = (p.tier1_light && n_legal > 0) ? cbchess::light_gates_warp(nb, s_legal[wl], n_legal, p.koth != 0, lane) : 2;
     if (lane == 0) {
         int result = 2;   // +1 white won, -1 black won, 0 draw, 2 continue
         if (p.koth && (nb.pieces[(white_moved ? 0 : 6) + cbchess::KING] & cbchess::kKothCenter)) result = white_moved ? 1 : -1;
@@ -546,6 +556,7 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
             int reps = 0;
             for (int i = 0; i < hn; ++i) reps += (hist[i] == hist[hn - 1]);
             if (reps >= 3 || nb.halfmove >= 100 || p.ply[g] > p.max_plies) result = 0;
+            else if (gate == 1) result = white_moved ? -1 : 1;
         }
         if (result != 2 && p.match_mode) {
             // result from the candidate's point of view, logged in finish order for the SPRT; next game or idle

@@ -75,6 +75,10 @@ int   orc_gen_captures_mvvlva(const orc_board* b, orc_move* out, int* long_list)
 int   orc_principal_exchange(const orc_board* b, int alpha, int beta, int max_depth, uint32_t* nodes,
                              int* long_list);                       /* src/search/quiescence.rs:756-794; *nodes accumulates */
 float orc_forced_principal_exchange(const orc_board* b, uint32_t* nodes, int* long_list); /* :797-804 */
+/* light Tier-1 gates = the reference's gate at depth 1 (qsearch.c) */
+int   orc_mate_in_1(const orc_board* b);            /* src/search/mate_search.rs:64-108, max_depth 1 */
+int   orc_koth_in_1(const orc_board* b);            /* src/search/koth.rs:43-65, max_n 1 */
+int   orc_light_gates(const orc_board* b, int koth); /* src/mcts/tactical_mcts.rs:619-708: -1, +1 or 2 (none) */
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,11 @@ def lib():
         L.orc_principal_exchange.restype = ctypes.c_int
         L.orc_forced_principal_exchange.argtypes = [bp, up, ip]
         L.orc_forced_principal_exchange.restype = ctypes.c_float
+        for name in ("orc_mate_in_1", "orc_koth_in_1"):
+            getattr(L, name).argtypes = [bp]
+            getattr(L, name).restype = ctypes.c_int
+        L.orc_light_gates.argtypes = [bp, ctypes.c_int]
+        L.orc_light_gates.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -212,6 +217,19 @@ def forced_principal_exchange(b):
     long_list = ctypes.c_int(0)
     s = lib().orc_forced_principal_exchange(ctypes.byref(b), ctypes.byref(nodes), ctypes.byref(long_list))
     return float(s), nodes.value
+
+
+def mate_in_1(b):
+    return bool(lib().orc_mate_in_1(ctypes.byref(b)))
+
+
+def koth_in_1(b):
+    return bool(lib().orc_koth_in_1(ctypes.byref(b)))
+
+
+def light_gates(b, koth=False):
+    """-1 / +1 for the side to move, 2 when no gate fires."""
+    return lib().orc_light_gates(ctypes.byref(b), int(koth))
 
 
 def pe_q(boards_u8):

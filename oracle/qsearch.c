@@ -185,3 +185,43 @@ float orc_forced_principal_exchange(const orc_board* b, uint32_t* nodes, int* lo
     const int cp = orc_principal_exchange(b, -100000, 100000, 20, nodes, long_list);
     return (float)cp / 100.0f;
 }
+
+/* ---- light Tier-1 gates: the reference's gate at depth 1 ----
+ *   mate in one     src/search/mate_search.rs:64-108 with max_depth = 1: a legal (checking) move after which the
+ *                   opponent is in check without a legal move (:129-200)
+ *   hill in one     src/search/koth.rs:43-65 with max_n = 1: own king on a centre square, or (:213-247) a legal king
+ *                   step onto one; false when the opponent's king already stands on one (:185-209)
+ *   leaf value      src/mcts/tactical_mcts.rs:619-708: opponent on the hill -> -1, hill in one -> +1, mate in one -> +1
+ * Pins: tests/unit/mate_search_tests.rs:26-33,346-351,448-474 and tests/unit/koth_tests.rs:19-37. */
+#define ORC_CENTER 0x0000001818000000ULL
+
+int orc_mate_in_1(const orc_board* b) {
+    orc_move mv[ORC_MAX_MOVES], reply[ORC_MAX_MOVES];
+    const int n = orc_gen_legal(b, mv);
+    for (int i = 0; i < n; ++i) {
+        orc_board nb;
+        orc_make_move(b, mv[i], &nb);
+        if (orc_in_check(&nb, nb.w_to_move ? 0 : 1) && orc_gen_legal(&nb, reply) == 0) return 1;
+    }
+    return 0;
+}
+
+int orc_koth_in_1(const orc_board* b) {
+    const int us = b->w_to_move ? 0 : 1;
+    const uint64_t k = b->pieces[us * 6 + K];
+    if (k & ORC_CENTER) return 1;
+    if (b->pieces[(1 - us) * 6 + K] & ORC_CENTER) return 0;
+    orc_move mv[ORC_MAX_MOVES];
+    const int n = orc_gen_legal(b, mv);
+    for (int i = 0; i < n; ++i)
+        if ((k >> ORC_FROM(mv[i]) & 1) && (ORC_CENTER >> ORC_TO(mv[i]) & 1)) return 1;
+    return 0;
+}
+
+int orc_light_gates(const orc_board* b, int koth) { /* -1 / +1 for the side to move, 2 = no gate */
+    if (koth) {
+        if (b->pieces[(b->w_to_move ? 1 : 0) * 6 + K] & ORC_CENTER) return -1;
+        if (orc_koth_in_1(b)) return 1;
+    }
+    return orc_mate_in_1(b) ? 1 : 2;
+}

@@ -292,7 +292,8 @@ def test_resident_path_equals_host_path(cb, golden, positions):
 @pytest.mark.parametrize("name,material,dtype,koth", [("6x128_A", False, "bf16", False), ("6x128_B", False, "bf16", False),
                                                       ("6x128_B", True, "bf16", False), ("6x128_B", False, "bf16", True),
                                                       ("2x128_B", True, "fp32", False), ("10x256_B", False, "bf16", False),
-                                                      ("6x128_B", "pe", "bf16", False), ("2x128_B", "pe", "fp32", True)])
+                                                      ("6x128_B", "pe", "bf16", False), ("2x128_B", "pe", "fp32", True),
+                                                      ("6x128_B", "gates", "bf16", False), ("6x128_B", "gates", "bf16", True)])
 def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material, dtype, koth, tmp_path):
     """Self-play with select / expand / backup / move choice on the device (pipeline 3) must walk exactly the
     trees of the host driver: same evaluator outputs (they do not depend on batch composition), same chess
@@ -300,7 +301,8 @@ def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material, dtype
     g, blob = golden(name)
     ev = make_eval(cb, g, blob, dtype)
     kw = dict(games=24, sims_per_move=20, max_plies=40, material_on=bool(material), koth=koth, seed=11,
-              max_sims=24 * 20 * 60, qsearch="pe" if material == "pe" else 0)   # "pe": dM by the exchange line (warp form)
+              max_sims=24 * 20 * 60, qsearch="pe" if material == "pe" else 0,   # "pe": dM by the exchange line (warp form)
+              tier1_light=material == "gates")                                  # "gates": light Tier-1 gates + adjudication
     host = ev.selfplay(threads=1, pipeline=1, sample_path=str(tmp_path / "host.bin"), **kw)
     dev = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "dev.bin"), **kw)
     for k in ("sims", "steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins",

@@ -72,6 +72,21 @@ def test_principal_exchange_equals_the_oracle(cb):
     assert cb.principal_exchange(boards[:0]).shape == (0,)
 
 
+def test_light_gates_equal_the_oracle(cb):
+    """cb_light_gates (legal list + early-exit reply search) against the oracle's plain statement, both rule sets."""
+    a, _, _, _ = O.random_positions(31337, 3000, 200)
+    boards = np.concatenate([a, np.stack([u8(f) for f in PE_FENS + [
+        "6k1/5ppp/8/8/8/8/8/4R1K1 w - - 0 1", "4r1k1/8/8/8/8/8/5PPP/6K1 b - - 0 1",
+        "r1bqkbnr/pppp1ppp/2n5/4p2Q/2B1P3/8/PPPP1PPP/RNB1K1NR w KQkq - 4 4", "k7/1R6/K7/8/8/8/8/8 b - - 0 1",
+        "8/8/8/8/8/2K5/8/k7 w - - 0 1", "8/8/8/8/3k4/8/8/K7 w - - 0 1", "8/8/8/2k5/8/2K5/8/8 w - - 0 1"]])])
+    for koth in (False, True):
+        got = cb.light_gates(boards, koth=koth)
+        want = np.array([O.light_gates(O.array_to_board(r), koth) for r in boards], dtype=np.int8)
+        assert np.array_equal(got, want)
+        assert (got == 1).sum() >= 5
+    assert (cb.light_gates(boards, koth=True) == -1).sum() >= 1
+
+
 @pytest.fixture(scope="module")
 def host_test_exe(cb):
     exe = os.path.join(REPO, "tests", "cpp", "_host_mirror_test")

@@ -123,3 +123,27 @@ def test_captures_are_exactly_the_pseudo_legal_captures_and_promotions():
             attacker = next(i % 6 for i in range(12) if b.pieces[i] >> (m & 63) & 1)
             keys.append(0 if victim is None else 10 * victim - attacker)
         assert keys == sorted(keys, reverse=True)
+
+
+# ------------------------------------------------------------------ light Tier-1 gates (depth 1)
+def test_mate_in_one_known_answers():  # tests/unit/mate_search_tests.rs:26-33,346-351,448-474
+    for fen in ("6k1/5ppp/8/8/8/8/8/4R1K1 w - - 0 1",                       # Re8#
+                "4r1k1/8/8/8/8/8/5PPP/6K1 b - - 0 1",                       # Re1#
+                "r1bqkbnr/pppp1ppp/2n5/4p2Q/2B1P3/8/PPPP1PPP/RNB1K1NR w KQkq - 4 4"):   # Qxf7#
+        assert O.mate_in_1(O.from_fen(fen)), fen
+    for fen in (START,
+                "r1bqk2r/pppp1ppp/2n2n2/2b1p3/2B1P3/5N2/PPPP1PPP/RNBQK2R w KQkq - 4 4",   # "no mate within depth 1"
+                "k7/1R6/K7/8/8/8/8/8 b - - 0 1",                            # stalemate
+                "7k/R7/5K2/8/8/8/8/8 w - - 0 1"):                           # a mate in TWO
+        assert not O.mate_in_1(O.from_fen(fen)), fen
+
+
+def test_hill_in_one_known_answers():  # tests/unit/koth_tests.rs:19-37,104-118
+    assert O.koth_in_1(O.from_fen("8/8/8/8/3K4/8/8/k7 w - - 0 1"))          # already there: Some(0)
+    assert O.koth_in_1(O.from_fen("8/8/8/8/8/2K5/8/k7 w - - 0 1"))          # Kc3-d4: Some(1)
+    assert not O.koth_in_1(O.from_fen("8/8/8/8/8/8/1K6/k7 w - - 0 1"))      # two steps away
+    assert not O.koth_in_1(O.from_fen("8/8/8/8/3k4/8/8/K7 w - - 0 1"))      # the opponent is already on the hill
+    assert not O.koth_in_1(O.from_fen("8/8/8/2k5/8/2K5/8/8 w - - 0 1"))     # d4 is covered by the other king
+    b = O.from_fen("8/8/8/8/3k4/8/8/K7 w - - 0 1")
+    assert O.light_gates(b, koth=True) == -1 and O.light_gates(b, koth=False) == 2
+    assert O.light_gates(O.from_fen("6k1/5ppp/8/8/8/8/8/4R1K1 w - - 0 1")) == 1
