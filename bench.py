@@ -66,11 +66,13 @@ def make_workload(args, rank):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled (NVML, every 5 ms) DURING the measured region."""
+    """SM clock and throttle reasons sampled (NVML, every millisecond) DURING the timed regions: the sampler thread
+    records only while `active` is set, which the bench does around the resident and the end-to-end loops."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop, self.t = index, [], False, None
         self.max_mhz = None
+        self.active = False
 
     def __enter__(self):
         try:
@@ -82,12 +84,13 @@ class ClockSampler:
 
             def run():
                 while not self.stop:
-                    try:
-                        self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
-                                          nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
-                    except Exception:
-                        pass
-                    time.sleep(0.005)
+                    if self.active:
+                        try:
+                            self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                              nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+                        except Exception:
+                            pass
+                    time.sleep(0.001)
             self.t = threading.Thread(target=run, daemon=True)
             self.t.start()
         except Exception:
@@ -247,12 +250,14 @@ def main():
     ev.stage_leaves(boards, q, idx, off)
     ev.time_resident(W, material_on=True, flush_l2=True)
     barrier()
-    with ClockSampler(local_rank) as clocks:
-        t_wall0 = time.perf_counter()
-        ms_each = ev.time_resident(K, material_on=True, flush_l2=True)
-        barrier()
-        wall = time.perf_counter() - t_wall0
-        clk = clocks.summary()
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    clocks.active = True
+    t_wall0 = time.perf_counter()
+    ms_each = ev.time_resident(K, material_on=True, flush_l2=True)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks.active = False
     dev_ms = float(ms_each.sum())
     pri, v, vf, kk = ev.read_resident()
     assert np.isfinite(pri).all() and np.isfinite(vf).all() and np.abs(vf).max() <= 1.0
@@ -274,11 +279,13 @@ def main():
     for _ in range(W):
         ev.eval_leaves(boards, q, idx, off)
     barrier()
+    clocks.active = True
     t0 = time.perf_counter()
     for _ in range(K):
         out = ev.eval_leaves(boards, q, idx, off)
     torch.cuda.synchronize()
     e2e_sync_s = time.perf_counter() - t0
+    clocks.active = False
     ev2 = cb.Evaluator(args.blocks, args.hidden, args.dtype, device=local_rank)
     ev2.load_weights(blob)
     for _ in range(W):
@@ -290,11 +297,16 @@ def main():
             e.eval_leaves(boards, q, idx, off)
     barrier()
     threads = [threading.Thread(target=pump, args=(e, n)) for e, n in zip((ev, ev2), counts)]
+    clocks.active = True
     t0 = time.perf_counter()
     [t.start() for t in threads]
     [t.join() for t in threads]
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks.active = False
+    clocks.__exit__()
+    clk = clocks.summary()
+    clk["regions"] = "resident loop + both end-to-end loops (the timed regions), NVML every 1 ms"
     barrier()
     h2d = int(boards.nbytes + q.nbytes + idx.nbytes + off.nbytes)
     d2h = int(out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes)
