@@ -335,7 +335,12 @@ __device__ __forceinline__ void value_phase(const TowerRParams& p, int et, int l
 // ring slot is refilled when both CTAs' MMAs have released it (commit multicast to both w_empty barriers).
 // Requires the two CTAs to walk the same stage sequence (same number of chains, one unit each): the host
 // checks.  Measured: +5 % SM clock, but the lock-step on a 4-stage ring costs 10 % more cycles: not the default.
-template <bool BF16, bool DBG, bool CL2>
+//
+// DEEP = true (launches whose units all have ONE chain, i.e. at most 4 boards per CTA: batches of up to 4 boards per
+// SM): the second chain's activation buffer is idle, so the weight ring grows from 4 to 8 stages into it (the four
+// extra stages sit right below the regular ones: one contiguous ring).  Such launches are bound by the latency of
+// the L2 -> SM weight stream (295 KB per layer through 64 KB in flight), which the deeper ring halves.
+template <bool BF16, bool DBG, bool CL2, bool DEEP = false>
 __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(const TowerRParams p) {
     const int dbg = DBG ? p.dbg : 0;
     long long* const trace = DBG ? p.trace : nullptr;
@@ -343,15 +348,16 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
     float* const dbg_backbone = DBG ? p.dbg_backbone : nullptr;
     using Cfg = TowerRCfg;
     constexpr int HID = 128;
-    constexpr int kWStages = Cfg::kWStages, kSE = 8;
+    constexpr int kWStages = DEEP ? 2 * Cfg::kWStages : Cfg::kWStages, kSE = 8;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* chain_base = smem;                                // [2][2 halves][kHalfBytes]
-    uint8_t* w_base = chain_base + 2 * Cfg::kChainBytes;
+    uint8_t* w_base = chain_base + 2 * Cfg::kChainBytes - (DEEP ? Cfg::kWStages * Cfg::kWBytes : 0);
     uint8_t* misc = w_base + kWStages * Cfg::kWBytes;
-    uint64_t* w_full = reinterpret_cast<uint64_t*>(misc);      // [4]
-    uint64_t* w_empty = w_full + kWStages;                     // [4]
-    uint64_t* tmem_full = w_empty + kWStages;                  // [2 chains]
+    static_assert(Cfg::kChainBytes >= Cfg::kWStages * Cfg::kWBytes, "the deep ring lives in the idle chain's buffer");
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(misc);      // [kWStages]
+    uint64_t* w_empty = w_full + kWStages;                     // [kWStages]
+    uint64_t* tmem_full = w_empty + kWStages;                  // [2 chains]   (20 barriers + the TMEM pointer < 256 B)
     uint64_t* chain_ready = tmem_full + 2;                     // [2 chains] buffer written + TMEM drained
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(chain_ready + 2);
     float* s_part = reinterpret_cast<float*>(misc + 256);      // [kParts][4 boards][128 ch]
