@@ -79,6 +79,7 @@ SIGNATURES = {
     "cb_principal_exchange": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
     "cb_principal_exchange_device": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
     "cb_light_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
+    "cb_debug_device_legal_moves": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_stage_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_time_resident": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_time_conv_layers": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
@@ -189,6 +190,14 @@ class Evaluator:
         out = np.empty(b.shape[0], dtype=np.int32)
         self._check(self._L.cb_pst_eval_cp(self._h, _ptr(b), b.shape[0], _ptr(out)))
         return out
+
+    def debug_device_legal_moves(self, boards):
+        """The tree kernels' legal-move lists: (moves uint16 [n,256], counts int32 [n])."""
+        b = _boards_u8(boards)
+        moves = np.zeros((b.shape[0], 256), dtype=np.uint16)
+        counts = np.zeros(b.shape[0], dtype=np.int32)
+        self._check(self._L.cb_debug_device_legal_moves(self._h, _ptr(b), b.shape[0], _ptr(moves), _ptr(counts)))
+        return moves, counts
 
     def principal_exchange(self, boards):
         """Principal-exchange material balance of every board, on the device (pawn units, f32)."""

@@ -1215,6 +1215,48 @@ int cb_pst_eval_cp(cb_handle* h, const cb_board* boards, int B, int32_t* cp) {
     return CB_OK;
 }
 
+// One warp per board: the tree kernels' legal-move generator (debug / test hook).
+__global__ void __launch_bounds__(256) device_legal_moves_kernel(const cb_board* __restrict__ boards, int n, uint16_t* __restrict__ moves,
+                                                                 int32_t* __restrict__ counts) {
+    __shared__ cb_board s_b[8];
+    __shared__ cbchess::Move s_pseudo[8][CB_MAX_MOVES], s_legal[8][CB_MAX_MOVES];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + wl;
+    if (i >= n) return;
+    if (lane < 16) reinterpret_cast<uint64_t*>(&s_b[wl])[lane] = reinterpret_cast<const uint64_t*>(&boards[i])[lane];
+    __syncwarp();
+    const int cnt = mcts_gen_legal_warp(s_b[wl], s_pseudo[wl], s_legal[wl], lane);
+    for (int j = lane; j < cnt; j += 32) moves[(size_t)i * CB_MAX_MOVES + j] = s_legal[wl][j];
+    if (lane == 0) counts[i] = cnt;
+}
+
+int cb_debug_device_legal_moves(cb_handle* h, const cb_board* boards, int n, uint16_t* moves, int32_t* counts) {
+    if (!h || n < 0 || (n > 0 && (!boards || !moves || !counts))) return CB_EINVAL;
+    if (n == 0) return CB_OK;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->chess_tables_uploaded) {
+        CB_CUDA(h, cudaMemcpyToSymbol(cbchess::d_chess_tables, &cbchess::host_tables(), sizeof(cbchess::Tables)));
+        h->chess_tables_uploaded = true;
+    }
+    int rc = upload_leaves(h, boards, nullptr, n, nullptr, nullptr);
+    if (rc) return rc;
+    uint16_t* d_moves = nullptr;
+    int32_t* d_counts = nullptr;
+    CB_CUDA(h, cudaMalloc(&d_moves, (size_t)n * CB_MAX_MOVES * 2));
+    cudaError_t ce = cudaMalloc(&d_counts, (size_t)n * 4);
+    if (ce == cudaSuccess) {
+        device_legal_moves_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(h->d_boards, n, d_moves, d_counts);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(moves, d_moves, (size_t)n * CB_MAX_MOVES * 2, cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(counts, d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+    cudaFree(d_moves);
+    cudaFree(d_counts);
+    CB_CUDA(h, ce);
+    return CB_OK;
+}
+
 // One warp per board: the principal-exchange line of host/qsearch.hpp.
 __global__ void __launch_bounds__(256) principal_exchange_kernel(const cb_board* __restrict__ boards, int n, float* __restrict__ q) {
     __shared__ cb_board s_b[8], s_nb[8];

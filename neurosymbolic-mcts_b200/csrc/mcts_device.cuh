@@ -178,13 +178,94 @@ __device__ __forceinline__ void mcts_backup(MNode* nodes, const uint32_t* path, 
     __syncwarp();
 }
 
-// Legal moves of `board` in generation order: lane 0 generates the pseudo-legal list, the lanes test
+// cbchess::gen_pseudo with one own piece per lane (a side has at most 16): the same list in the same order.
+// Lane k takes the k-th piece in generation order (pawns, knights, bishops, rooks, queens, king; ascending squares),
+// counts its captures / promotions and its quiet moves, two warp scans give every lane its place in the capture
+// block and in the quiet block, and the castling moves (five squares tested for attack on five lanes) close the list.
+__device__ __forceinline__ int gen_pseudo_warp(const cb_board& b, Move* out, int lane) {
+    using namespace cbchess;
+    const Tables& T = tables();
+    const int us = b.w_to_move ? 0 : 1, them = 1 - us;
+    const uint64_t opp = b.occ[them], occ = b.occ[0] | b.occ[1];
+    const uint64_t* pc = &b.pieces[us * 6];
+    const int fwd = us == 0 ? 8 : -8, promo_rank = us == 0 ? 7 : 0, start_rank = us == 0 ? 1 : 6;
+    int pt = -1, from = 0;
+    {
+        int k = lane;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const int c = __popcll(pc[t]);
+            if (pt < 0) {
+                if (k < c) { pt = t; from = nth_set_bit(pc[t], k); }
+                else k -= c;
+            }
+        }
+    }
+    uint64_t caps = 0, quiets = 0;
+    int ncap = 0, nquiet = 0;
+    bool ep = false, promo_push = false, one_ok = false, two_ok = false;
+    if (pt == PAWN) {
+        const int one = from + fwd;
+        const bool promo = (one >> 3) == promo_rank, one_empty = !(occ >> one & 1);
+        caps = T.pawn[us][from] & opp;
+        ep = b.en_passant != 0xFF && (T.pawn[us][from] >> b.en_passant & 1);
+        promo_push = promo && one_empty;
+        ncap = __popcll(caps) * (promo ? 4 : 1) + (ep ? 1 : 0) + (promo_push ? 4 : 0);
+        one_ok = !promo && one_empty;
+        two_ok = one_ok && (from >> 3) == start_rank && !(occ >> (one + fwd) & 1);
+        nquiet = (one_ok ? 1 : 0) + (two_ok ? 1 : 0);
+    } else if (pt >= 0) {
+        const uint64_t att = pt == KNIGHT ? T.knight[from] : pt == KING ? T.king[from] : pt == BISHOP ? bishop_att(from, occ)
+                           : pt == ROOK ? rook_att(from, occ) : (rook_att(from, occ) | bishop_att(from, occ));
+        caps = att & opp;
+        quiets = att & ~occ;
+        ncap = __popcll(caps);
+        nquiet = __popcll(quiets);
+    }
+    int cap_end = ncap, quiet_end = nquiet;   // inclusive scans over the lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, cap_end, d), q = __shfl_up_sync(0xffffffffu, quiet_end, d);
+        if (lane >= d) { cap_end += a; quiet_end += q; }
+    }
+    const int total_caps = __shfl_sync(0xffffffffu, cap_end, 31), total_quiets = __shfl_sync(0xffffffffu, quiet_end, 31);
+    int n = cap_end - ncap;
+    if (pt == PAWN) {
+        for (uint64_t t = caps; t; t &= t - 1) n = add_pawn(out, n, from, lsb(t), promo_rank);
+        if (ep) out[n++] = make_mv(from, b.en_passant, 0);
+        if (promo_push) n = add_pawn(out, n, from, from + fwd, promo_rank);
+        n = total_caps + quiet_end - nquiet;
+        if (one_ok) out[n++] = make_mv(from, from + fwd, 0);
+        if (two_ok) out[n++] = make_mv(from, from + 2 * fwd, 0);
+    } else if (pt >= 0) {
+        for (uint64_t t = caps; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
+        n = total_caps + quiet_end - nquiet;
+        for (uint64_t t = quiets; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
+    }
+    int total = total_caps + total_quiets;
+    const int ksq = us == 0 ? 4 : 60, ks = us == 0 ? WK : BK, qs = us == 0 ? WQ : BQ;
+    if ((pc[KING] >> ksq & 1) && (b.castling & (ks | qs))) {          // uniform
+        const bool att = lane < 5 && attacked(b, ksq - 2 + lane, them);
+        const uint32_t am = __ballot_sync(0xffffffffu, att);           // bit i: square ksq - 2 + i is attacked
+        if (!(am >> 2 & 1)) {
+            if ((b.castling & ks) && (pc[ROOK] >> (ksq + 3) & 1) && !(occ & (3ull << (ksq + 1))) && !(am >> 3 & 3)) {
+                if (lane == 0) out[total] = make_mv(ksq, ksq + 2, 0);
+                ++total;
+            }
+            if ((b.castling & qs) && (pc[ROOK] >> (ksq - 4) & 1) && !(occ & (7ull << (ksq - 3))) && !(am & 3)) {
+                if (lane == 0) out[total] = make_mv(ksq, ksq - 2, 0);
+                ++total;
+            }
+        }
+    }
+    __syncwarp();
+    return total;
+}
+
+// Legal moves of `board` in generation order: the warp generates the pseudo-legal list, the lanes test
 // legality in parallel, a ballot compacts in order.  Returns the count (uniform); moves in `legal`.
 __device__ __forceinline__ int mcts_gen_legal_warp(const cb_board& board, Move* pseudo, Move* legal, int lane) {
-    int np = 0;
-    if (lane == 0) np = cbchess::gen_pseudo(board, pseudo);
-    np = __shfl_sync(0xffffffffu, np, 0);
-    __syncwarp();
+    const int np = gen_pseudo_warp(board, pseudo, lane);
     const int us = board.w_to_move ? 0 : 1;
     int n = 0;
     for (int base = 0; base < np; base += 32) {

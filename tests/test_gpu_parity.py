@@ -341,6 +341,23 @@ def test_two_pool_self_play_walks_the_same_trees(cb, golden, material, qsearch, 
         ev.selfplay(pipeline=4, games=47, sims_per_move=4, max_sims=47 * 8)
 
 
+def test_device_move_generator_equals_the_host_list_move_for_move(cb, golden):
+    """The warp form of the move generator (one piece per lane, scans for the order) against the host list —
+    same moves in the same order, which is what keeps device trees identical to the host driver's."""
+    g, blob = golden("2x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    a, _, _, _ = O.random_positions(20261019, 3000, 200)
+    fens = ["r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1",      # castling both ways
+            "r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1",           # promotions, captures
+            "r3k2r/8/8/8/8/8/8/R3K2R b KQkq - 0 1", "r3k2r/8/8/8/8/5n2/8/R3K2R w KQkq - 0 1",   # castling through check
+            "4k3/8/8/3pP3/8/8/8/4K3 w - d6 0 1", "8/P7/8/8/8/8/7p/K6k b - - 0 1", "4k3/8/8/8/8/8/8/4K3 w - - 0 1"]
+    boards = np.concatenate([a, O.boards_to_array([O.from_fen(f) for f in fens])])
+    moves, counts = ev.debug_device_legal_moves(boards)
+    for i in range(boards.shape[0]):
+        want, _ = cb.chess_legal_moves(boards[i])
+        assert counts[i] == len(want) and np.array_equal(moves[i, :counts[i]], want), i
+
+
 def test_principal_exchange_on_device(cb, golden):
     """The warp form of the exchange line (one piece per lane) against the host form and the oracle, and the
     material scalar of a self-play sample file against the oracle."""
