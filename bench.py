@@ -15,10 +15,15 @@ initialisation law with live heads (oracle/weights.py variant B); both synthetic
            library), L2 flushed (256 MiB rewrite) between steps; max over ranks.
   e2e      same metric through the public C-ABI call cb_eval_leaves with HOST buffers: H2D of
            boards/q/CSR and D2H of priors/values inside the timed region, every step.
-  roofline the dominant kernel (3x3 conv HID->HID, tcgen05): algorithmic FLOPs per launch /
-           mean CUDA-event duration of its launches, against the measured bf16 peak.
+  roofline the dominant kernel — for 128-channel nets the ONE kernel of the forward (planes, 14 tcgen05
+           convs, both heads) — algorithmic FLOPs per launch / mean CUDA-event duration of its launches,
+           against the measured bf16 peak.
   cpu_baseline  the reference's own traced TorchScript module (oracle/_ref, built from the
            reference sources) on the host cores, bounded sample; "port" if _ref is absent.
+
+oracle/ appears here in two roles only: as the generator of the synthetic inputs (seeded positions and
+random-init weights, built before any timed region) and as the CPU baseline / --impl reference leg.  The
+measured path is libcaissa_b200.so alone.
 
 N > 1: one process per GPU (torchrun), each rank evaluates its own independent batch — the path
 shards by position with no collective — so scaling is "weak".
