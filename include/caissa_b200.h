@@ -148,6 +148,8 @@ int cb_debug_backbone(cb_handle* h, int B, float* out);
 /* The device tree kernels' legal-move generator (one warp per board) on n boards: moves[i*256 ..] in generation
  * order and counts[i] — must equal cb_chess_legal_moves move for move (tests). */
 int cb_debug_device_legal_moves(cb_handle* h, const cb_board* boards, int n, uint16_t* moves, int32_t* counts);
+/* The device tree kernels' light Tier-1 gates (warp form) on n boards — must equal cb_light_gates (tests). */
+int cb_debug_device_light_gates(cb_handle* h, const cb_board* boards, int n, int koth, int8_t* out);
 /* Same for activation ring buffer `buf` (0..2); with cb_debug_set_layer_limit(n) the tower stops
  * after n convolution launches so individual layers can be compared across arithmetic modes. */
 int cb_debug_act(cb_handle* h, int B, int buf, float* out);

@@ -80,6 +80,7 @@ SIGNATURES = {
     "cb_principal_exchange_device": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
     "cb_light_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_debug_device_legal_moves": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP, _VP]),
+    "cb_debug_device_light_gates": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_stage_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_time_resident": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_time_conv_layers": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
@@ -198,6 +199,13 @@ class Evaluator:
         counts = np.zeros(b.shape[0], dtype=np.int32)
         self._check(self._L.cb_debug_device_legal_moves(self._h, _ptr(b), b.shape[0], _ptr(moves), _ptr(counts)))
         return moves, counts
+
+    def debug_device_light_gates(self, boards, koth=False):
+        """The tree kernels' light gates (warp form): int8 per board (+1, -1, 2 = none)."""
+        b = _boards_u8(boards)
+        out = np.zeros(b.shape[0], dtype=np.int8)
+        self._check(self._L.cb_debug_device_light_gates(self._h, _ptr(b), b.shape[0], int(koth), _ptr(out)))
+        return out
 
     def principal_exchange(self, boards):
         """Principal-exchange material balance of every board, on the device (pawn units, f32)."""

@@ -1257,6 +1257,38 @@ int cb_debug_device_legal_moves(cb_handle* h, const cb_board* boards, int n, uin
     return CB_OK;
 }
 
+// One warp per board: the tree kernels' light gates (debug / test hook).
+__global__ void __launch_bounds__(256) device_light_gates_kernel(const cb_board* __restrict__ boards, int n, int koth, int8_t* __restrict__ out) {
+    __shared__ cb_board s_b[8], s_nb[8];
+    __shared__ cbchess::Move s_pseudo[8][CB_MAX_MOVES], s_legal[8][CB_MAX_MOVES];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + wl;
+    if (i >= n) return;
+    if (lane < 16) reinterpret_cast<uint64_t*>(&s_b[wl])[lane] = reinterpret_cast<const uint64_t*>(&boards[i])[lane];
+    __syncwarp();
+    const int cnt = mcts_gen_legal_warp(s_b[wl], s_pseudo[wl], s_legal[wl], lane);
+    const int tv = light_gates_warp(s_b[wl], s_legal[wl], cnt, koth != 0, s_nb[wl], s_pseudo[wl], lane);
+    if (lane == 0) out[i] = (int8_t)tv;
+}
+
+int cb_debug_device_light_gates(cb_handle* h, const cb_board* boards, int n, int koth, int8_t* out) {
+    if (!h || n < 0 || (n > 0 && (!boards || !out))) return CB_EINVAL;
+    if (n == 0) return CB_OK;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->chess_tables_uploaded) {
+        CB_CUDA(h, cudaMemcpyToSymbol(cbchess::d_chess_tables, &cbchess::host_tables(), sizeof(cbchess::Tables)));
+        h->chess_tables_uploaded = true;
+    }
+    int rc = upload_leaves(h, boards, nullptr, n, nullptr, nullptr);
+    if (rc) return rc;
+    if ((rc = ensure_scratch(h, (size_t)n))) return rc;
+    device_light_gates_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(h->d_boards, n, koth, (int8_t*)h->d_scratch);
+    CB_CUDA(h, cudaGetLastError());
+    CB_CUDA(h, cudaMemcpyAsync(out, h->d_scratch, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+
 // One warp per board: the principal-exchange line of host/qsearch.hpp.
 __global__ void __launch_bounds__(256) principal_exchange_kernel(const cb_board* __restrict__ boards, int n, float* __restrict__ q) {
     __shared__ cb_board s_b[8], s_nb[8];

@@ -7,7 +7,8 @@
 // value +1 for the side to move (src/mcts/tactical_mcts.rs:636-647,695-707); the self-play driver adjudicates a game
 // whose root position hits a gate (src/bin/self_play.rs:241-283).
 //
-// One inline host+device statement (scalar forms) plus warp forms for the tree kernels.  Product code: it does not
+// One inline host+device statement (scalar forms); the warp form of the tree kernels is light_gates_warp in
+// mcts_device.cuh.  Product code: it does not
 // use oracle/; tests/ check it against oracle/qsearch.c's independent statement and the reference's known answers.
 #pragma once
 #include "chess_rules.hpp"
@@ -71,27 +72,5 @@ CB_HD int light_gates_hd(const cb_board& b, const Move* legal, int n, bool koth)
     }
     return mate_in_1_hd(b, legal, n) ? 1 : 2;
 }
-
-#if defined(__CUDACC__)
-// Warp form: one legal move per lane.  All lanes must call; all lanes return the same value.
-__device__ __forceinline__ int light_gates_warp(const cb_board& b, const Move* legal, int n, bool koth, int lane) {
-    const int us = b.w_to_move ? 0 : 1;
-    if (koth) {
-        if (b.pieces[(1 - us) * 6 + KING] & kKothCenter) return -1;
-        const uint64_t k = b.pieces[us * 6 + KING];
-        if (k & kKothCenter) return 1;
-        const int ks = k ? lsb(k) : -1;
-        bool step = false;
-        for (int i = lane; i < n; i += 32) step |= mv_from(legal[i]) == ks && (kKothCenter >> mv_to(legal[i]) & 1);
-        if (__any_sync(0xffffffffu, step)) return 1;
-    }
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const bool hit = i < n && move_mates_hd(b, legal[i]);
-        if (__any_sync(0xffffffffu, hit)) return 1;
-    }
-    return 2;
-}
-#endif
 
 }  // namespace cbchess

@@ -286,6 +286,87 @@ __device__ __forceinline__ int mcts_gen_legal_warp(const cb_board& board, Move* 
     return n;
 }
 
+// Warp form of cbchess::light_gates_hd (host/gates.hpp): the value of a gate hit for the side to move of `b`, or 2.
+// `legal[0..n)` are the legal moves of `b`; `nb` and `pseudo` are shared scratch.  All lanes call and return alike.
+//  * Which moves give check is decided without making them: a knight / pawn checks from the squares that attack the
+//    king square, a slider from the squares a rook / bishop standing on the king square would see.  Moves that can
+//    uncover a line (the mover stands on a rank, file or diagonal of the enemy king), en passant, castling and
+//    promotions take the exact test (make the move, test the king).
+//  * Every checking move is then examined by the whole warp: the king's steps on eight lanes first (the usual way
+//    out), and only when none is legal the full reply list (warp generator, one reply per lane).
+__device__ __forceinline__ int light_gates_warp(const cb_board& b, const Move* legal, int n, bool koth, cb_board& nb, Move* pseudo,
+                                                int lane) {
+    using namespace cbchess;
+    const Tables& T = tables();
+    const int us = b.w_to_move ? 0 : 1, them = 1 - us;
+    if (koth) {
+        if (b.pieces[them * 6 + KING] & kKothCenter) return -1;
+        const uint64_t k = b.pieces[us * 6 + KING];
+        if (k & kKothCenter) return 1;
+        const int ks = k ? lsb(k) : -1;
+        bool step = false;
+        for (int i = lane; i < n; i += 32) step |= mv_from(legal[i]) == ks && (kKothCenter >> mv_to(legal[i]) & 1);
+        if (__any_sync(0xffffffffu, step)) return 1;
+    }
+    const uint64_t ek = b.pieces[them * 6 + KING];
+    if (!ek) return 2;
+    const int eks = lsb(ek);
+    const uint64_t occ = b.occ[0] | b.occ[1];
+    const uint64_t rvis = rook_att(eks, occ), bvis = bishop_att(eks, occ);          // checking squares of the sliders
+    const uint64_t klines = rook_att(eks, 0ull) | bishop_att(eks, 0ull);            // every square aligned with that king
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool chk = false;
+        if (i < n) {
+            const Move m = legal[i];
+            const int from = mv_from(m), to = mv_to(m);
+            const int pt = piece_on(b, us, 1ull << from);
+            const bool exact = mv_promo(m) != 0 || (klines >> from & 1) || (pt == PAWN && to == b.en_passant) ||
+                               (pt == KING && (to - from == 2 || from - to == 2));
+            if (exact) {
+                cb_board t;
+                make_move_hd(b, m, &t);
+                chk = in_check_hd(t, them);
+            } else {
+                chk = pt == PAWN ? (T.pawn[us][to] & ek) != 0 : pt == KNIGHT ? (T.knight[to] & ek) != 0
+                    : pt == BISHOP ? (bvis >> to & 1) != 0 : pt == ROOK ? (rvis >> to & 1) != 0
+                    : pt == QUEEN ? ((rvis | bvis) >> to & 1) != 0 : false;
+            }
+        }
+        for (uint32_t cm = __ballot_sync(0xffffffffu, chk); cm; cm &= cm - 1) {
+            const Move m = legal[base + __ffs(cm) - 1];
+            __syncwarp();
+            if (lane == 0) make_move_hd(b, m, &nb);
+            __syncwarp();
+            // the checked king's steps
+            const uint64_t k2 = nb.pieces[them * 6 + KING];
+            const int ks2 = lsb(k2);
+            const uint64_t steps = T.king[ks2] & ~nb.occ[them];
+            bool out = false;
+            if (lane < __popcll(steps)) {
+                cb_board t;
+                make_move_hd(nb, make_mv(ks2, nth_set_bit(steps, lane), 0), &t);
+                out = !in_check_hd(t, them);
+            }
+            if (__any_sync(0xffffffffu, out)) continue;
+            // captures of the checker and interpositions
+            const int np = gen_pseudo_warp(nb, pseudo, lane);
+            bool reply = false;
+            for (int rb = 0; rb < np && !reply; rb += 32) {
+                bool ok = false;
+                if (rb + lane < np) {
+                    cb_board t;
+                    make_move_hd(nb, pseudo[rb + lane], &t);
+                    ok = !in_check_hd(t, them);
+                }
+                reply = __any_sync(0xffffffffu, ok);
+            }
+            if (!reply) return 1;
+        }
+    }
+    return 2;
+}
+
 // Phase A of a simulation for every game: walk down with PUCT, stop at an unexpanded or terminal node.
 // best still equals first_child because no child was selected by the scan (n_children == 0 cannot reach here; NaN
 // scores could): fall back to loading the node.
@@ -397,7 +478,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     int tv = 2;
     if (p.tier1_light && p.koth && (board.pieces[(board.w_to_move ? 1 : 0) * 6 + cbchess::KING] & cbchess::kKothCenter)) tv = -1;
     else if (n_moves == 0) tv = cbchess::in_check_hd(board, board.w_to_move ? 0 : 1) ? -1 : 0;
-    else if (p.tier1_light) tv = cbchess::light_gates_warp(board, s_legal[wl], n_moves, p.koth != 0, lane);
+    else if (p.tier1_light) tv = light_gates_warp(board, s_legal[wl], n_moves, p.koth != 0, sm.next[wl], s_pseudo[wl], lane);
     if (tv != 2) {
         if (lane == 0) {
             leaf.state = 2;
@@ -626,7 +707,7 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
     const int n_legal = mcts_gen_legal_warp(nb, s_pseudo[wl], s_legal[wl], lane);
     // a root where the side to move wins at once is adjudicated (src/bin/self_play.rs:241-283 at depth 1; in a match
     // the reference's search returns the winning move there, src/mcts/tactical_mcts.rs:330-357,400-420: same result)
-    const int gate = (p.tier1_light && n_legal > 0) ? cbchess::light_gates_warp(nb, s_legal[wl], n_legal, p.koth != 0, lane) : 2;
+    const int gate = (p.tier1_light && n_legal > 0) ? light_gates_warp(nb, s_legal[wl], n_legal, p.koth != 0, sm.board[wl], s_pseudo[wl], lane) : 2;
     if (lane == 0) {
         int result = 2;   // +1 white won, -1 black won, 0 draw, 2 continue
         if (p.koth && (nb.pieces[(white_moved ? 0 : 6) + cbchess::KING] & cbchess::kKothCenter)) result = white_moved ? 1 : -1;

@@ -358,6 +358,28 @@ def test_device_move_generator_equals_the_host_list_move_for_move(cb, golden):
         assert counts[i] == len(want) and np.array_equal(moves[i, :counts[i]], want), i
 
 
+def test_device_light_gates_equal_the_host_form(cb, golden):
+    """The warp form decides "gives check" from attack sets (exact test only for moves that can uncover a line, en
+    passant, castling, promotions); the host form makes every move.  Same answers, both rule sets."""
+    g, blob = golden("2x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    a, _, _, _ = O.random_positions(31337, 4000, 200)
+    fens = ["6k1/5ppp/8/8/8/8/8/4R1K1 w - - 0 1", "4r1k1/8/8/8/8/8/5PPP/6K1 b - - 0 1",
+            "r1bqkbnr/pppp1ppp/2n5/4p2Q/2B1P3/8/PPPP1PPP/RNB1K1NR w KQkq - 4 4", "k7/1R6/K7/8/8/8/8/8 b - - 0 1",
+            "6k1/5ppp/8/8/8/8/5PPP/3R2K1 w - - 0 1",                       # Rd8#
+            "5rk1/5ppp/8/8/8/8/1B6/K5R1 w - - 0 1",                        # Rxg7+ is not mate; discovered lines
+            "7k/5P2/6K1/8/8/8/8/8 w - - 0 1",                              # f8=Q# / f8=R#: promotion mates
+            "4k3/8/8/8/8/8/8/R3K2R w KQ - 0 1",                            # castling gives no mate here
+            "7k/6pp/8/3B4/8/8/6PP/5R1K w - - 0 1",                         # Rf8#
+            "8/8/8/8/8/2K5/8/k7 w - - 0 1", "8/8/8/8/3k4/8/8/K7 w - - 0 1"]
+    boards = np.concatenate([a, O.boards_to_array([O.from_fen(f) for f in fens])])
+    for koth in (False, True):
+        got = ev.debug_device_light_gates(boards, koth=koth)
+        want = cb.light_gates(boards, koth=koth)
+        assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
+        assert (got == 1).sum() >= 8
+
+
 def test_principal_exchange_on_device(cb, golden):
     """The warp form of the exchange line (one piece per lane) against the host form and the oracle, and the
     material scalar of a self-play sample file against the oracle."""
