@@ -10,7 +10,7 @@ from oracle import pyoracle, weights as W  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-blocks, hidden = 6, 128
+blocks, hidden = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (6, 128)
 boards, idx, off, _ = pyoracle.random_positions(20261019, B)
 q = pyoracle.static_q(boards)
 ev = cb.Evaluator(blocks, hidden, "bf16")
