@@ -4,6 +4,7 @@ Every literal below is transcribed from a reference test (file:line given per ca
 tests/unit/board_encoding_tests.rs, tests/unit/tensor_extended_tests.rs, src/tensor.rs:215-246,
 tests/unit/pesto_qsearch_tests.rs:14-80, cuda/test/test_nn_ops.cu:619-645.
 """
+import os
 import numpy as np
 import pytest
 
@@ -173,3 +174,34 @@ def test_value_fuse_matches_f64_tanh():  # src/mcts/tactical_mcts.rs:762-765, :7
     import math
     assert O.value_fuse(0.3, 0.4, 1.5, True) == math.tanh(float(np.float32(0.3)) + float(np.float32(0.4)) * 1.5)
     assert O.value_fuse(0.3, 0.4, 1.5, False) == math.tanh(float(np.float32(0.3)))
+
+
+# ------------------------------------------------------------------ independent statement of the 73-plane layout
+@pytest.mark.skipif(not os.path.isdir("/root/reference/python"), reason="reference checkout not present (GPU box)")
+def test_policy_index_commutes_with_the_reference_mirror_table():
+    """python/augmentation.py states the policy layout a second time (direction order, knight order, underpromotion
+    offsets) as permutation tables.  move_to_index must commute with the file mirror: index(mirror(move)) ==
+    HFLIP_POLICY[index(move)] for every move kind.  (The quarter-turn table of that file is not used as a pin: its
+    direction map (+2) and its square map (file -> rank) turn in opposite senses, e.g. a1-b1 lands on h1-h2 by the
+    square table but is sent to the "south" plane by the direction table.)"""
+    import sys
+    sys.path.insert(0, "/root/reference/python")
+    try:
+        import augmentation as aug
+    finally:
+        sys.path.remove("/root/reference/python")
+    hflip = lambda s: (s // 8) * 8 + (7 - s % 8)
+    assert [hflip(s) for s in range(64)] == aug.HFLIP_SQ.tolist()
+    checked = set()
+    for frm in range(64):
+        for to in range(64):
+            for promo in (0, 1, 2, 3, 4):
+                if promo and not (frm // 8 == 6 and to // 8 == 7 and abs(to % 8 - frm % 8) <= 1):
+                    continue
+                idx = O.move_to_index(frm, to, promo)
+                if idx < 0:
+                    continue
+                assert O.move_to_index(hflip(frm), hflip(to), promo) == aug.HFLIP_POLICY[idx]
+                checked.add(idx)
+    # every queen-slide / knight entry reachable from some square, and all nine underpromotion planes
+    assert len(checked) >= 1792 + 64 and {i % 73 for i in checked} == set(range(73))
