@@ -1,0 +1,45 @@
+"""The bench.py line format the driver depends on, checked on the committed lines (profiles/r01_bench_v13*.json are
+verbatim stdout of `python bench.py` on 1 / 4 / 8 B200s) and on a live `--impl reference` run of one small step."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REQUIRED = {"metric": str, "value": float, "unit": str, "n_gpus": int, "steps": int, "warmup": int, "ms_per_step": float,
+            "higher_is_better": bool, "scaling": str, "dtype": str, "data": str, "config": dict, "e2e": dict,
+            "gpu_launches": int, "clocks": dict, "roofline": dict}
+
+
+@pytest.mark.parametrize("name,n", [("r01_bench_v13.json", 1), ("r01_bench_v13_n4.json", 4), ("r01_bench_v13_n8.json", 8)])
+def test_committed_lines_follow_the_contract(name, n):
+    d = json.load(open(os.path.join(REPO, "profiles", name)))
+    for k, t in REQUIRED.items():
+        assert isinstance(d[k], t), (k, type(d[k]))
+    assert d["vs_baseline"] is None and d["n_gpus"] == n and d["scaling"] == "weak" and d["higher_is_better"] is True
+    assert d["metric"] == json.load(open(os.path.join(REPO, "BASELINE.json")))["metric"].split(";")[0]
+    assert "workload" in d["config"] and "model" not in d["config"]
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    assert d["gpu_launches"] == d["steps"] * n            # one kernel per forward per GPU
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+    if n == 1:
+        c = d["cpu_baseline"]
+        assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == d["unit"] and c["sample"]
+
+
+def test_reference_arm_prints_one_line():
+    p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--batch", "64"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["unit"] == "evals/s"
