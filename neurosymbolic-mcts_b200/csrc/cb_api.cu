@@ -884,11 +884,12 @@ void cbsp_write_sample(FILE* f, const cb_board& b, float material, const std::pa
 namespace {
 
 // Copy the records appended since the last drain, rebuild the games and write the finished ones.
+// Records [ring_read, cursor) of the device-side sample log -> finished games in the sample file.  `cursor` was read
+// after the kernels that wrote those records completed; the copies run on `cs` (nullptr: the handle's stream), so the
+// caller may already have the next graph replay running on the handle's stream (it appends beyond `cursor`).
 int drain_samples(cb_handle* h, const MctsParams& mp, unsigned long long& ring_read, std::vector<uint8_t>& host,
-                  std::vector<std::vector<DevSample>>& pending, FILE* f) {
-    unsigned long long cursor = 0;
-    CB_CUDA(h, cudaMemcpyAsync(&cursor, mp.ring_cursor, 8, cudaMemcpyDeviceToHost, h->stream));
-    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+                  std::vector<std::vector<DevSample>>& pending, FILE* f, unsigned long long cursor, cudaStream_t cs) {
+    if (!cs) cs = h->stream;
     if (cursor == ring_read) return CB_OK;
     if (cursor - ring_read > mp.ring_slots) return fail(h, CB_ESTATE, "sample ring overflow");
     const size_t n = (size_t)(cursor - ring_read);
@@ -896,11 +897,11 @@ int drain_samples(cb_handle* h, const MctsParams& mp, unsigned long long& ring_r
     const size_t first = (size_t)(ring_read % mp.ring_slots);
     const size_t run = n < mp.ring_slots - first ? n : mp.ring_slots - first;
     CB_CUDA(h, cudaMemcpyAsync(host.data(), mp.sample_ring + first * kSampleSlotBytes, run * kSampleSlotBytes,
-                               cudaMemcpyDeviceToHost, h->stream));
+                               cudaMemcpyDeviceToHost, cs));
     if (run < n)
         CB_CUDA(h, cudaMemcpyAsync(host.data() + run * kSampleSlotBytes, mp.sample_ring, (n - run) * kSampleSlotBytes,
-                                   cudaMemcpyDeviceToHost, h->stream));
-    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+                                   cudaMemcpyDeviceToHost, cs));
+    CB_CUDA(h, cudaStreamSynchronize(cs));
     std::vector<float> rec;
     for (size_t i = 0; i < n; ++i) {
         const uint8_t* r = host.data() + i * kSampleSlotBytes;
@@ -1730,11 +1731,17 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     bool split_done = pools == 2;              // (two pools: the kernels overlap, there is no split to report)
     const auto t_start = std::chrono::steady_clock::now();
     auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    // The sample log is drained while the NEXT graph replay runs: the cursor is read with the counters (those records
+    // are complete), the replay is launched, then the ring is copied on a second stream and the finished games are
+    // written.  The ring holds four replays' worth of records, the drain is at most one replay behind.
+    cudaStream_t copy_stream = nullptr;
+    if (sample_file) cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+    unsigned long long cursor = 0;
     for (;;) {
         ce = cudaMemcpyAsync(st, mp.stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream);
+        if (ce == cudaSuccess && sample_file) ce = cudaMemcpyAsync(&cursor, mp.ring_cursor, 8, cudaMemcpyDeviceToHost, h->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
         if (ce != cudaSuccess) break;
-        if (sample_file && (rc = drain_samples(h, mp, ring_read, ring_host, pending, sample_file))) break;
         // the step in flight is completed after the loop: stop once `done + 1` steps suffice
         if (target > 0 && done + 1 >= target) break;
         if (cfg->max_games > 0 && (long long)st[MS_GAMES] >= cfg->max_games) break;
@@ -1762,7 +1769,9 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
             if ((ce = cudaGraphLaunch(gexec, h->stream)) != cudaSuccess) break;
             done += kStepsPerGraph;
         }
+        if (sample_file && (rc = drain_samples(h, mp, ring_read, ring_host, pending, sample_file, cursor, copy_stream))) break;
     }
+    if (rc || ce != cudaSuccess) cudaStreamSynchronize(h->stream);     // nothing in flight while the buffers go away
     // complete the simulations in flight
     if (!rc && ce == cudaSuccess) {
         if (pools == 2) {
@@ -1773,11 +1782,13 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
             if (!rc) mcts_expand_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
         }
         if (!rc) ce = cudaMemcpyAsync(st, mp.stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream);
+        if (!rc && ce == cudaSuccess && sample_file) ce = cudaMemcpyAsync(&cursor, mp.ring_cursor, 8, cudaMemcpyDeviceToHost, h->stream);
         if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
-        if (!rc && ce == cudaSuccess && sample_file) rc = drain_samples(h, mp, ring_read, ring_host, pending, sample_file);
+        if (!rc && ce == cudaSuccess && sample_file) rc = drain_samples(h, mp, ring_read, ring_host, pending, sample_file, cursor, nullptr);
     }
     const long long steps = done + 1;
     const double secs = elapsed();
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     cudaGraphExecDestroy(gexec);
     if (sample_file) fclose(sample_file);
     release();
