@@ -240,6 +240,28 @@ class Evaluator:
                                            _ptr(pri), _ptr(v), _ptr(vf), _ptr(k)))
         return pri, v, vf, k
 
+    def prepared_eval_leaves(self, boards, q, move_idx, move_off, material_on=True):
+        """cb_eval_leaves on fixed host buffers: returns run() -> (priors, v_logit, v_final, k), which calls the C ABI
+        with argument pointers and output arrays made once (what a host that reuses its request buffers does; the
+        per-call cost of the numpy / ctypes marshalling above is ~20 us).  Every run() still copies the inputs host ->
+        device and the results device -> host inside cb_eval_leaves."""
+        b = _boards_u8(boards)
+        B = b.shape[0]
+        qa = None if q is None else np.ascontiguousarray(q, dtype=np.float32)
+        mi = np.ascontiguousarray(move_idx, dtype=np.uint16)
+        mo = np.ascontiguousarray(move_off, dtype=np.uint32)
+        assert mo.size == B + 1
+        outs = (np.empty(int(mo[B]), dtype=np.float32), np.empty(B, dtype=np.float32), np.empty(B, dtype=np.float32),
+                np.empty(B, dtype=np.float32))
+        keep = (b, qa, mi, mo)                                    # the pointers below borrow these arrays
+        args = (self._h, _ptr(b), _ptr(qa), B, int(material_on), _ptr(mi), _ptr(mo)) + tuple(_ptr(o) for o in outs)
+        fn, check = self._L.cb_eval_leaves, self._check
+
+        def run(_keep=keep):
+            check(fn(*args))
+            return outs
+        return run
+
     def stage_leaves(self, boards, q, move_idx, move_off):
         b = _boards_u8(boards)
         qa = None if q is None else np.ascontiguousarray(q, dtype=np.float32)

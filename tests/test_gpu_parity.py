@@ -167,6 +167,17 @@ def test_edge_cases(cb, golden):
     np.testing.assert_allclose(pri2, [0.5, 0.5], rtol=1e-6)
 
 
+def test_prepared_eval_leaves_equals_eval_leaves(cb, golden):
+    g, blob = golden("2x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    want = ev.eval_leaves(g["boards"], g["q"], g["move_idx"], g["move_off"])
+    run = ev.prepared_eval_leaves(g["boards"], g["q"], g["move_idx"], g["move_off"])
+    for _ in range(2):
+        got = run()
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+
+
 def test_errors_are_codes_not_aborts(cb):
     ev = cb.Evaluator(2, 128, "bf16")
     with pytest.raises(cb.CaissaError, match="not loaded"):
