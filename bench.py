@@ -333,7 +333,7 @@ def main():
     # tree operations on the device (select / expand / backup / move choice as two kernels around the forward
     # kernel, no host work per simulation), and beside it the host-driven pool (two half-pools of 512 games,
     # each with its own evaluator handle) whose rate depends on the host cores available per GPU.
-    sp = sp_host = sp_koth = sp_two = sp_two_pe = None
+    sp = sp_host = sp_koth = sp_two = sp_two_pe = sp_rec = None
     nthreads = max(1, (os.cpu_count() or 1) // world - 2)
     if args.selfplay_seconds > 0:
         barrier()
@@ -355,22 +355,29 @@ def main():
         sp_two_pe = ev.selfplay(games=2 * args.selfplay_games, sims_per_move=200, material_on=True, qsearch="pe",
                                 seed=401 + rank, max_seconds=args.selfplay_seconds, pipeline=4)
         barrier()
+        # the one-pool run again with the training samples produced: every finished game is assembled on the host into
+        # the reference's 5763-f32 records and written out (to /dev/null: record building and write calls, no storage)
+        sp_rec = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=501 + rank,
+                             max_seconds=args.selfplay_seconds, pipeline=3, sample_path="/dev/null")
+        barrier()
     ev2.close()
 
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3, launch_ms, e2e_sync_s * 1e3, sp["seconds"] if sp else 0.0,
                       sp_host["seconds"] if sp_host else 0.0, sp_koth["seconds"] if sp_koth else 0.0,
-                      sp_two["seconds"] if sp_two else 0.0, sp_two_pe["seconds"] if sp_two_pe else 0.0],
+                      sp_two["seconds"] if sp_two else 0.0, sp_two_pe["seconds"] if sp_two_pe else 0.0,
+                      sp_rec["seconds"] if sp_rec else 0.0],
                      dtype=torch.float64, device="cuda")
     tot = torch.tensor([sp["sims"] if sp else 0, sp["nn_evals"] if sp else 0, sp_host["sims"] if sp_host else 0,
                         sp_koth["sims"] if sp_koth else 0, sp_two["sims"] if sp_two else 0,
-                        sp_two_pe["sims"] if sp_two_pe else 0],
+                        sp_two_pe["sims"] if sp_two_pe else 0, sp_rec["sims"] if sp_rec else 0,
+                        sp_rec["samples"] if sp_rec else 0],
                        dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     (dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds, sp_host_seconds, sp_koth_seconds, sp_two_seconds,
-     sp_two_pe_seconds) = [float(x) for x in t.tolist()]
+     sp_two_pe_seconds, sp_rec_seconds) = [float(x) for x in t.tolist()]
     value = world * B * K / (dev_ms * 1e-3)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     # off the hot path: the one exchange the multi-GPU design has (training-sample gather over NCCL)
@@ -421,6 +428,8 @@ def main():
                                 "koth_800_sims_per_move_sims_per_s": float(tot[3].item()) / max(sp_koth_seconds, 1e-9),
                                 "two_pools_sims_per_s": float(tot[4].item()) / max(sp_two_seconds, 1e-9),
                                 "two_pools_material_pe_sims_per_s": float(tot[5].item()) / max(sp_two_pe_seconds, 1e-9),
+                                "with_sample_records_sims_per_s": float(tot[6].item()) / max(sp_rec_seconds, 1e-9),
+                                "sample_records_per_s": float(tot[7].item()) / max(sp_rec_seconds, 1e-9),
                                 "two_pools_games_per_gpu": 2 * args.selfplay_games,
                                 "two_pools_mode": "cb_selfplay_run pipeline 4: two pools of games_per_gpu games alternate, "
                                                   "the tree kernel of one beside the forward kernel of the other; "
