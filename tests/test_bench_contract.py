@@ -13,7 +13,7 @@ REQUIRED = {"metric": str, "value": float, "unit": str, "n_gpus": int, "steps": 
             "gpu_launches": int, "clocks": dict, "roofline": dict}
 
 
-@pytest.mark.parametrize("name,n", [("r01_bench_v15.json", 1), ("r01_bench_v15_n8.json", 8), ("r01_bench_v14.json", 1), ("r01_bench_v13.json", 1), ("r01_bench_v13_n2.json", 2), ("r01_bench_v13_n4.json", 4),
+@pytest.mark.parametrize("name,n", [("r01_bench_v15.json", 1), ("r01_bench_v15_n8.json", 8), ("r01_bench_v16_n2.json", 2), ("r01_bench_v14.json", 1), ("r01_bench_v13.json", 1), ("r01_bench_v13_n2.json", 2), ("r01_bench_v13_n4.json", 4),
                                     ("r01_bench_v13_n8.json", 8)])
 def test_committed_lines_follow_the_contract(name, n):
     d = json.load(open(os.path.join(REPO, "profiles", name)))
