@@ -88,3 +88,27 @@ def test_the_reference_loader_reads_the_file(tmp_path):
     assert np.isclose(flat, rec[3, 1088]).any() and np.isclose(flat, rec[3, 1090]).any()     # material and value target
     pol = [t for t in tensors if t.size == 4672][0]
     assert np.array_equal(pol.reshape(-1), rec[3, 1091:])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_PY), reason="reference checkout not present (GPU box)")
+def test_the_reference_replay_buffer_samples_the_file(tmp_path):
+    """python/replay_buffer.py (the training loop's data source, python/orchestrate.py), imported in place: add the
+    game file, draw a batch, and find every drawn row among our records field for field."""
+    import shutil
+    games = tmp_path / "games"
+    games.mkdir()
+    shutil.copy(FIXTURE, games / "game_000.bin")
+    sys.path.insert(0, REF_PY)
+    try:
+        import replay_buffer as ref_rb
+    finally:
+        sys.path.remove(REF_PY)
+    rec = records()
+    rb = ref_rb.ReplayBuffer(1000, str(tmp_path / "buffer"))
+    assert rb.add_games(str(games)) == rec.shape[0] == rb.total_positions()
+    np.random.seed(0)
+    boards, scalars, values, policies = rb.sample_batch(32)
+    assert boards.shape == (32, 17, 8, 8) and scalars.shape == (32, 2) and values.shape == (32, 1) and policies.shape == (32, 4672)
+    for i in range(32):
+        row = np.concatenate([boards[i].reshape(-1), scalars[i], values[i], policies[i]])
+        assert (rec == row).all(axis=1).any()
