@@ -41,6 +41,9 @@ def test_weight_count_matches_reference_blob(cb):
     L = cb.load_library()
     from oracle import weights as W
     assert L.cb_weight_count(6, 128) == 1982672 == W.blob_size(6, 128)   # 7,930,688 B (BENCHMARKS.md:203)
+    # = the model's 1,979,086 trainable parameters (python/test_architectures.py:262-266) + the running mean / variance of
+    #   its BatchNorm layers (14 of 128 channels, v_bn of 1), which the export carries and the parameter count does not
+    assert L.cb_weight_count(6, 128) - 2 * (14 * 128 + 1) == 1979086
     assert L.cb_weight_count(10, 256) == W.blob_size(10, 256)
     assert L.cb_version().startswith(b"caissa_b200")
 
