@@ -80,6 +80,53 @@ int   orc_mate_in_1(const orc_board* b);            /* src/search/mate_search.rs
 int   orc_koth_in_1(const orc_board* b);            /* src/search/koth.rs:43-65, max_n 1 */
 int   orc_light_gates(const orc_board* b, int koth); /* src/mcts/tactical_mcts.rs:619-708: -1, +1 or 2 (none) */
 
+/* ---- tree operations (mcts.c): generation order, tactical-first selection, f64 PUCT, backup, reuse, game loop ---- */
+/* gen_pseudo_legal_moves in the reference's order, src/move_generation.rs:287-328: captures (pawns, knights, bishops,
+ * rooks, queens, king) ++ promotions, then quiets; *n_captures = length of the first (capture + promotion) list */
+int    orc_gen_pseudo_ref(const orc_board* b, orc_move* out, int* n_captures);
+/* legal moves in child order (src/mcts/tactical_mcts.rs:813-836); *n_tactical (nullable) = how many come from the capture list */
+int    orc_gen_legal_ref(const orc_board* b, orc_move* out, int* n_tactical);
+double orc_tactical_score(const orc_board* b, orc_move m);       /* calculate_mvv_lva, src/mcts/tactical.rs:179-216 */
+void   orc_tactical_order(const orc_board* b, const orc_move* moves, int n_tactical, int* order); /* :155-177 */
+
+/* Evaluator callback: priors of `moves` (child order; src/tensor.rs:184-213) and the fused leaf value
+ * tanh(v_logit + k*q) / tanh(v_logit) (src/mcts/tactical_mcts.rs:762-765,787-790). */
+typedef void (*orc_eval_fn)(void* user, const orc_board* b, const orc_move* moves, int n, float q, int material_on,
+                            float* priors, double* value);
+typedef struct {
+    int sims;             /* max_iterations */
+    int material_on;      /* enable_material_value */
+    int qsearch;          /* dM: 0 static PeSTO / 100, 1 principal exchange */
+    int koth;
+    int tier1_light;      /* Tier-1 gates at depth 1 */
+    int shuffle;          /* permute every expansion's child order (the reference's randomize_move_order is dead code in its
+                             search loop: selection.rs:82-104 returns before shuffling, the children already exist) */
+    int max_plies;        /* game loop: 200 */
+    double c_puct;        /* 1.414 */
+    double explore_base;  /* 0.80 */
+} orc_mcts_config;
+typedef struct orc_tree orc_tree;
+orc_tree* orc_mcts_new(const orc_board* root, uint64_t seed);
+void      orc_mcts_free(orc_tree* t);
+int       orc_mcts_search(orc_tree* t, const orc_mcts_config* cfg, orc_eval_fn eval, void* user); /* returns iterations run */
+int       orc_mcts_root_children(const orc_tree* t, orc_move* moves, uint32_t* visits, double* total_value);
+void      orc_mcts_root_stats(const orc_tree* t, uint32_t* visits, double* total_value, long* evals, long* terminal_hits, long* tactical);
+orc_move  orc_mcts_best_move(const orc_tree* t);                  /* select_best_move_from_root; 0 = None */
+int       orc_mcts_advance(orc_tree* t, orc_move played);         /* reuse_subtree */
+void      orc_eval_mock(void* user /* const float[2]: v_logit, k */, const orc_board* b, const orc_move* moves, int n, float q,
+                        int material_on, float* priors, double* value); /* InferenceServer::new_mock_biased */
+typedef struct {
+    orc_board board;
+    int n;
+    uint16_t idx[ORC_MAX_MOVES];
+    float prob[ORC_MAX_MOVES];
+    float material, value_target;
+    int w_to_move;
+} orc_game_sample;
+/* play_game, src/bin/self_play.rs:191-445; returns the number of samples (moves played) */
+int orc_play_game(const orc_board* start, const orc_mcts_config* cfg, uint64_t seed, orc_eval_fn eval, void* user,
+                  orc_game_sample* samples, int max_samples, int* result_white, int* plies);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ MAX_MOVES = 256
 
 def build(force=False):
     """Compile the C restatement with gcc (seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in ("codec.c", "chess.c", "qsearch.c", "oracle.h", "pesto_tables.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("codec.c", "chess.c", "qsearch.c", "mcts.c", "oracle.h", "pesto_tables.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
@@ -88,8 +88,48 @@ def lib():
             getattr(L, name).restype = ctypes.c_int
         L.orc_light_gates.argtypes = [bp, ctypes.c_int]
         L.orc_light_gates.restype = ctypes.c_int
+        # tree operations (mcts.c)
+        L.orc_gen_pseudo_ref.argtypes = [bp, ctypes.POINTER(ctypes.c_uint16), ip]
+        L.orc_gen_pseudo_ref.restype = ctypes.c_int
+        L.orc_gen_legal_ref.argtypes = [bp, ctypes.POINTER(ctypes.c_uint16), ip]
+        L.orc_gen_legal_ref.restype = ctypes.c_int
+        L.orc_tactical_score.argtypes = [bp, ctypes.c_uint16]
+        L.orc_tactical_score.restype = ctypes.c_double
+        L.orc_tactical_order.argtypes = [bp, ctypes.POINTER(ctypes.c_uint16), ctypes.c_int, ip]
+        L.orc_mcts_new.argtypes = [bp, ctypes.c_uint64]
+        L.orc_mcts_new.restype = ctypes.c_void_p
+        L.orc_mcts_free.argtypes = [ctypes.c_void_p]
+        L.orc_mcts_search.argtypes = [ctypes.c_void_p, ctypes.POINTER(MctsConfig), ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_mcts_search.restype = ctypes.c_int
+        L.orc_mcts_root_children.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint16), up, ctypes.POINTER(ctypes.c_double)]
+        L.orc_mcts_root_children.restype = ctypes.c_int
+        lp = ctypes.POINTER(ctypes.c_long)
+        L.orc_mcts_root_stats.argtypes = [ctypes.c_void_p, up, ctypes.POINTER(ctypes.c_double), lp, lp, lp]
+        L.orc_mcts_best_move.argtypes = [ctypes.c_void_p]
+        L.orc_mcts_best_move.restype = ctypes.c_uint16
+        L.orc_mcts_advance.argtypes = [ctypes.c_void_p, ctypes.c_uint16]
+        L.orc_mcts_advance.restype = ctypes.c_int
+        L.orc_play_game.argtypes = [bp, ctypes.POINTER(MctsConfig), ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.POINTER(GameSample), ctypes.c_int, ip, ip]
+        L.orc_play_game.restype = ctypes.c_int
         _lib = L
     return _lib
+
+
+class MctsConfig(ctypes.Structure):
+    _fields_ = [("sims", ctypes.c_int), ("material_on", ctypes.c_int), ("qsearch", ctypes.c_int), ("koth", ctypes.c_int),
+                ("tier1_light", ctypes.c_int), ("shuffle", ctypes.c_int), ("max_plies", ctypes.c_int),
+                ("c_puct", ctypes.c_double), ("explore_base", ctypes.c_double)]
+
+
+class GameSample(ctypes.Structure):
+    _fields_ = [("board", Board), ("n", ctypes.c_int), ("idx", ctypes.c_uint16 * MAX_MOVES),
+                ("prob", ctypes.c_float * MAX_MOVES), ("material", ctypes.c_float), ("value_target", ctypes.c_float),
+                ("w_to_move", ctypes.c_int)]
+
+
+EVAL_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(Board), ctypes.POINTER(ctypes.c_uint16), ctypes.c_int,
+                           ctypes.c_float, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double))
 
 
 # ---------------------------------------------------------------- helpers
@@ -246,3 +286,99 @@ def static_q(boards_u8, clip=20.0):
     for i in range(boards_u8.shape[0]):
         q[i] = pst_eval_cp(array_to_board(boards_u8[i])) / 100.0
     return np.clip(q, -clip, clip).astype(np.float32)
+
+
+# ---------------------------------------------------------------- tree operations (mcts.c)
+def mcts_config(sims=200, material_on=False, qsearch=0, koth=False, tier1_light=False, shuffle=False, max_plies=200,
+                c_puct=1.414, explore_base=0.80):
+    return MctsConfig(int(sims), int(bool(material_on)), 1 if qsearch in (1, "pe") else 0, int(koth), int(tier1_light),
+                      int(shuffle), int(max_plies), float(c_puct), float(explore_base))
+
+
+def gen_legal_ref(b):
+    """Legal moves in the reference's child order -> (moves, n_tactical)."""
+    buf = (ctypes.c_uint16 * MAX_MOVES)()
+    nt = ctypes.c_int(0)
+    n = lib().orc_gen_legal_ref(ctypes.byref(b), buf, ctypes.byref(nt))
+    return [buf[i] for i in range(n)], nt.value
+
+
+def tactical_moves(b):
+    """identify_tactical_moves: [(move, score)] in visiting order."""
+    moves, nt = gen_legal_ref(b)
+    arr = (ctypes.c_uint16 * max(1, len(moves)))(*moves)
+    order = (ctypes.c_int * max(1, nt))()
+    lib().orc_tactical_order(ctypes.byref(b), arr, nt, order)
+    return [(moves[order[i]], lib().orc_tactical_score(ctypes.byref(b), moves[order[i]])) for i in range(nt)]
+
+
+def _evaluator(evaluator):
+    """evaluator: ('mock', v_logit[, k]) -> C mock; or a Python callable (board, moves, q, material_on) -> (priors, value)."""
+    if isinstance(evaluator, tuple) and evaluator[0] == "mock":
+        user = (ctypes.c_float * 2)(float(evaluator[1]), float(evaluator[2]) if len(evaluator) > 2 else 0.5)
+        fn = ctypes.cast(lib().orc_eval_mock, ctypes.c_void_p)
+        return fn, ctypes.cast(user, ctypes.c_void_p), user
+
+    def trampoline(_user, bptr, mptr, n, q, material_on, priors, value):
+        pri, val = evaluator(bptr.contents, [mptr[i] for i in range(n)], float(q), bool(material_on))
+        for i in range(n):
+            priors[i] = pri[i]
+        value[0] = float(val)
+    cb = EVAL_FN(trampoline)
+    return ctypes.cast(cb, ctypes.c_void_p), None, cb
+
+
+class Tree:
+    """One search tree of the restated reference search (tactical_mcts_search_for_training_with_reuse)."""
+
+    def __init__(self, board, seed=1):
+        self.h = lib().orc_mcts_new(ctypes.byref(board), seed)
+
+    def search(self, cfg, evaluator):
+        fn, user, keep = _evaluator(evaluator)
+        return lib().orc_mcts_search(self.h, ctypes.byref(cfg), fn, user)
+
+    def root_children(self):
+        mv_ = (ctypes.c_uint16 * MAX_MOVES)()
+        vis = (ctypes.c_uint32 * MAX_MOVES)()
+        tv = (ctypes.c_double * MAX_MOVES)()
+        n = lib().orc_mcts_root_children(self.h, mv_, vis, tv)
+        return [(mv_[i], vis[i], tv[i]) for i in range(n)]
+
+    def root_stats(self):
+        v = ctypes.c_uint32(0)
+        tv = ctypes.c_double(0)
+        e, th, tc = ctypes.c_long(0), ctypes.c_long(0), ctypes.c_long(0)
+        lib().orc_mcts_root_stats(self.h, ctypes.byref(v), ctypes.byref(tv), ctypes.byref(e), ctypes.byref(th), ctypes.byref(tc))
+        return dict(visits=v.value, total_value=tv.value, evals=e.value, terminal_hits=th.value, tactical=tc.value)
+
+    def best_move(self):
+        return lib().orc_mcts_best_move(self.h)
+
+    def advance(self, move):
+        return bool(lib().orc_mcts_advance(self.h, move))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_mcts_free(self.h)
+            self.h = None
+
+
+def play_game(start, cfg, seed, evaluator, max_samples=512):
+    """-> (samples list of dict, result_white, plies)."""
+    fn, user, keep = _evaluator(evaluator)
+    buf = (GameSample * max_samples)()
+    res, plies = ctypes.c_int(0), ctypes.c_int(0)
+    n = lib().orc_play_game(ctypes.byref(start), ctypes.byref(cfg), seed, fn, user, buf, max_samples, ctypes.byref(res),
+                            ctypes.byref(plies))
+    out = []
+    for i in range(min(n, max_samples)):
+        s = buf[i]
+        out.append(dict(board=np.frombuffer(bytes(s.board), dtype=np.uint8).copy(), idx=np.array(s.idx[:s.n], dtype=np.uint16),
+                        prob=np.array(s.prob[:s.n], dtype=np.float32), material=s.material, z=s.value_target))
+    return out, res.value, plies.value
+
+
+def uci(m):
+    s_ = lambda q_: "abcdefgh"[q_ & 7] + str((q_ >> 3) + 1)
+    return s_(m & 63) + s_((m >> 6) & 63) + ["", "n", "b", "r", "q"][(m >> 12) & 7]
