@@ -189,8 +189,8 @@ typedef struct cb_selfplay_config {
     int material_on;      /* 1: V = tanh(v + k*q), q chosen by `qsearch`; 0: vanilla (config 5) */
     int koth;             /* King-of-the-Hill game-end rule */
     int threads;          /* host threads for tree operations (0 = hardware concurrency) */
-    float c_puct;         /* 1.414 (TacticalMctsConfig::default) */
-    float explore_base;   /* 0.80 */
+    double c_puct;        /* 1.414 (exploration_constant, f64 like the reference; 0 = that default) */
+    double explore_base;  /* 0.80 (0 = that default) */
     uint64_t seed;
     long long max_sims;   /* stop after this many simulations in total (0 = unlimited) */
     long long max_games;  /* stop after this many finished games (0 = unlimited) */
@@ -211,6 +211,16 @@ typedef struct cb_selfplay_config {
                              move mates in one — or, with koth, steps onto the hill / faces a king already on it —
                              is terminal (+1 / -1, src/mcts/tactical_mcts.rs:619-708) and a game whose root hits a
                              gate is adjudicated (src/bin/self_play.rs:241-283) */
+    int shuffle_children; /* 1: permute the child order of every expansion with the game's random stream.  The reference sets
+                             randomize_move_order for self-play (src/bin/self_play.rs:224), but its shuffle never executes:
+                             ensure_node_expanded (src/mcts/selection.rs:82-104) returns when the node already has children,
+                             and the search loop only selects below nodes that evaluate_and_expand_node
+                             (src/mcts/tactical_mcts.rs:813-836, no shuffle) has expanded.  0 is therefore what the reference
+                             runs; 1 is the behaviour its flag describes */
+    int mock_eval;        /* 1 (device pipelines only): replace the network by the reference's mock evaluator
+                             (InferenceServer::new_mock_biased, src/mcts/inference_server.rs:103-122): uniform priors,
+                             v_logit = mock_v_logit, k = mock_k */
+    float mock_v_logit, mock_k;
 } cb_selfplay_config;
 
 typedef struct cb_selfplay_stats {
@@ -218,9 +228,29 @@ typedef struct cb_selfplay_stats {
     long long white_wins, black_wins, draws;
     double seconds, eval_seconds, tree_seconds;
     double mean_batch;
+    long long overflow;   /* device pipelines: leaves left unexpanded because a game's node arena was full (0 in a sound run) */
 } cb_selfplay_stats;
 
 int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out);
+
+/* ---- search hooks for the parity tests (tests compare them with oracle/mcts.c) ----
+ * Evaluator callback of the host hooks: the leaf, its legal moves in child order (packed moves and policy indices) and dM;
+ * writes the priors of those moves and the fused value. */
+typedef void (*cb_eval_callback)(void* user, const cb_board* b, const uint16_t* moves, const uint16_t* policy_idx, int n, float q,
+                                 int material_on, float* priors, float* v_final);
+/* One move's search (cfg->sims_per_move simulations, src/mcts/tactical_mcts.rs:981-1075 on a fresh root) from each of n
+ * positions with the HOST driver's tree code and the caller's evaluator — runs without a GPU.  Outputs per position i:
+ * counts[i] root children, moves / visits / value_sums[i * CB_MAX_MOVES + c], root_visits[i]. */
+int cb_debug_host_search(const cb_selfplay_config* cfg, const cb_board* boards, int n, cb_eval_callback eval, void* user,
+                         uint16_t* moves, uint32_t* visits, double* value_sums, int32_t* counts, uint32_t* root_visits);
+/* One whole game of the host driver (search, move choice, tree reuse, game end: src/bin/self_play.rs:191-445) from `start`
+ * with the game's random stream seeded by `seed`; returns the number of samples, written like the training records. */
+int cb_debug_host_game(const cb_selfplay_config* cfg, const cb_board* start, uint64_t seed, cb_eval_callback eval, void* user,
+                       cb_board* sample_boards, uint16_t* sample_idx, float* sample_prob, int32_t* sample_n, float* sample_material,
+                       int max_samples, int* result_white, int* plies);
+/* The same one-move search with the DEVICE tree kernels and the handle's network (or cfg->mock_eval) as evaluator. */
+int cb_debug_device_search(cb_handle* h, const cb_selfplay_config* cfg, const cb_board* boards, int n,
+                           uint16_t* moves, uint32_t* visits, double* value_sums, int32_t* counts, uint32_t* root_visits);
 /* The same pool with the tree operations on the device (cb_selfplay_run dispatches here
  * for pipeline = 3): select (src/mcts/selection.rs:65-73,254-273), expand (:82-104), backup
  * (src/mcts/node.rs:403-424), move choice / tree reuse / game end (src/bin/self_play.rs:300-388) run as two
@@ -247,8 +277,8 @@ typedef struct cb_match_config {
     int max_plies;        /* 200 */
     int material_on;
     int koth;
-    float c_puct;         /* 1.414 */
-    float explore_base;   /* 0.80 */
+    double c_puct;        /* 1.414 (0 = that default) */
+    double explore_base;  /* 0.90, DEFAULT_EXPLORE_BASE of src/bin/evaluate_models.rs:85 (0 = that default) */
     uint64_t seed;
     int use_sprt;
     double elo0, elo1, alpha, beta;   /* 0, 10, 0.05, 0.05 */

@@ -31,22 +31,24 @@ class CbTiming(ctypes.Structure):
 class SelfplayConfig(ctypes.Structure):
     _fields_ = [("games", ctypes.c_int), ("sims_per_move", ctypes.c_int), ("max_plies", ctypes.c_int),
                 ("material_on", ctypes.c_int), ("koth", ctypes.c_int), ("threads", ctypes.c_int),
-                ("c_puct", ctypes.c_float), ("explore_base", ctypes.c_float), ("seed", ctypes.c_uint64),
+                ("c_puct", ctypes.c_double), ("explore_base", ctypes.c_double), ("seed", ctypes.c_uint64),
                 ("max_sims", ctypes.c_longlong), ("max_games", ctypes.c_longlong), ("max_seconds", ctypes.c_double),
                 ("sample_path", ctypes.c_char_p), ("pipeline", ctypes.c_int), ("aux_handle", ctypes.c_void_p),
-                ("qsearch", ctypes.c_int), ("tier1_light", ctypes.c_int)]
+                ("qsearch", ctypes.c_int), ("tier1_light", ctypes.c_int), ("shuffle_children", ctypes.c_int),
+                ("mock_eval", ctypes.c_int), ("mock_v_logit", ctypes.c_float), ("mock_k", ctypes.c_float)]
 
 
 class SelfplayStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_longlong) for n in ("sims", "nn_evals", "terminal_hits", "moves", "games_finished",
                                                  "samples", "steps", "white_wins", "black_wins", "draws")] + \
-               [(n, ctypes.c_double) for n in ("seconds", "eval_seconds", "tree_seconds", "mean_batch")]
+               [(n, ctypes.c_double) for n in ("seconds", "eval_seconds", "tree_seconds", "mean_batch")] + \
+               [("overflow", ctypes.c_longlong)]
 
 
 class MatchConfig(ctypes.Structure):
     _fields_ = [("games", ctypes.c_int), ("total_games", ctypes.c_int), ("sims_per_move", ctypes.c_int),
                 ("max_plies", ctypes.c_int), ("material_on", ctypes.c_int), ("koth", ctypes.c_int),
-                ("c_puct", ctypes.c_float), ("explore_base", ctypes.c_float), ("seed", ctypes.c_uint64),
+                ("c_puct", ctypes.c_double), ("explore_base", ctypes.c_double), ("seed", ctypes.c_uint64),
                 ("use_sprt", ctypes.c_int), ("elo0", ctypes.c_double), ("elo1", ctypes.c_double),
                 ("alpha", ctypes.c_double), ("beta", ctypes.c_double), ("max_seconds", ctypes.c_double),
                 ("qsearch", ctypes.c_int), ("tier1_light", ctypes.c_int)]
@@ -59,6 +61,88 @@ class MatchStats(ctypes.Structure):
 
 class CaissaError(RuntimeError):
     pass
+
+
+def selfplay_config(games=1024, sims_per_move=200, max_plies=200, material_on=False, koth=False, threads=0, c_puct=1.414,
+                    explore_base=0.80, seed=1, max_sims=0, max_games=0, max_seconds=0.0, sample_path=None, pipeline=1, aux=None,
+                    qsearch=0, tier1_light=False, shuffle_children=False, mock=None):
+    return SelfplayConfig(games, sims_per_move, max_plies, int(bool(material_on)), int(koth), threads, c_puct, explore_base, seed,
+                          max_sims, max_games, max_seconds, sample_path.encode() if sample_path else None, pipeline,
+                          aux._h if aux is not None else None, _QSEARCH[qsearch], int(tier1_light), int(shuffle_children),
+                          int(mock is not None), float(mock[0]) if mock else 0.0, float(mock[1]) if mock else 0.5)
+
+
+class _SearchOut:
+    """Output buffers of the cb_debug_*_search hooks."""
+
+    def __init__(self, n):
+        self.n = n
+        self.moves = np.zeros((n, MAX_MOVES), dtype=np.uint16)
+        self.visits = np.zeros((n, MAX_MOVES), dtype=np.uint32)
+        self.sums = np.zeros((n, MAX_MOVES), dtype=np.float64)
+        self.counts = np.zeros(n, dtype=np.int32)
+        self.root_visits = np.zeros(n, dtype=np.uint32)
+
+    def ptrs(self):
+        return (self.moves.ctypes.data, self.visits.ctypes.data, self.sums.ctypes.data, self.counts.ctypes.data,
+                self.root_visits.ctypes.data)
+
+    def unpack(self):
+        kids = [[(int(self.moves[i, c]), int(self.visits[i, c]), float(self.sums[i, c])) for c in range(self.counts[i])]
+                for i in range(self.n)]
+        return kids, self.root_visits.copy()
+
+
+EVAL_CALLBACK = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint16),
+                                 ctypes.POINTER(ctypes.c_uint16), ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                 ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float))
+
+
+def _eval_callback(evaluator):
+    """evaluator(board_bytes[128] as np.uint8, moves, policy_idx, q, material_on) -> (priors, v_final)"""
+    def tramp(_user, bptr, mptr, iptr, n, q, material_on, priors, v_final):
+        board = np.frombuffer(ctypes.string_at(bptr, 128), dtype=np.uint8)
+        pri, val = evaluator(board, [mptr[i] for i in range(n)], [iptr[i] for i in range(n)], float(q), bool(material_on))
+        for i in range(n):
+            priors[i] = pri[i]
+        v_final[0] = float(val)
+    return EVAL_CALLBACK(tramp)
+
+
+def debug_host_search(boards, evaluator, **kw):
+    """One move's search with the HOST driver's tree code and a Python evaluator (no GPU needed) ->
+    list of [(move, visits, value_sum)], root visit counts (cb_debug_host_search)."""
+    L = load_library()
+    boards = np.ascontiguousarray(boards, dtype=np.uint8).reshape(-1, 128)
+    n = boards.shape[0]
+    cfg = selfplay_config(games=n, **kw)
+    out = _SearchOut(n)
+    cb = _eval_callback(evaluator)
+    rc = L.cb_debug_host_search(ctypes.byref(cfg), boards.ctypes.data, n, cb, None, *out.ptrs())
+    if rc != 0:
+        raise CaissaError("cb_debug_host_search failed: %d" % rc)
+    return out.unpack()
+
+
+def debug_host_game(start, seed, evaluator, max_samples=512, **kw):
+    """One whole game of the host driver with a Python evaluator -> (samples, result_white, plies)."""
+    L = load_library()
+    start = np.ascontiguousarray(start, dtype=np.uint8).reshape(128)
+    cfg = selfplay_config(games=1, **kw)
+    sb = np.zeros((max_samples, 128), dtype=np.uint8)
+    idx = np.zeros((max_samples, MAX_MOVES), dtype=np.uint16)
+    prob = np.zeros((max_samples, MAX_MOVES), dtype=np.float32)
+    cnt = np.zeros(max_samples, dtype=np.int32)
+    mat = np.zeros(max_samples, dtype=np.float32)
+    res, plies = ctypes.c_int(0), ctypes.c_int(0)
+    cb = _eval_callback(evaluator)
+    n = L.cb_debug_host_game(ctypes.byref(cfg), start.ctypes.data, ctypes.c_uint64(seed), cb, None, sb.ctypes.data, idx.ctypes.data,
+                             prob.ctypes.data, cnt.ctypes.data, mat.ctypes.data, max_samples, ctypes.byref(res), ctypes.byref(plies))
+    if n < 0:
+        raise CaissaError("cb_debug_host_game failed: %d" % n)
+    samples = [dict(board=sb[i].copy(), idx=idx[i, :cnt[i]].copy(), prob=prob[i, :cnt[i]].copy(), material=float(mat[i]))
+               for i in range(min(n, max_samples))]
+    return samples, res.value, plies.value
 
 
 _lib = None
@@ -103,6 +187,12 @@ SIGNATURES = {
     "cb_sprt_decision": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_double, ctypes.c_double,
                                         ctypes.c_double, ctypes.c_double]),
     "cb_selfplay_device": (ctypes.c_int, [_VP, ctypes.POINTER(SelfplayConfig), ctypes.POINTER(SelfplayStats)]),
+    "cb_debug_host_search": (ctypes.c_int, [ctypes.POINTER(SelfplayConfig), _VP, ctypes.c_int, EVAL_CALLBACK, _VP,
+                                            _VP, _VP, _VP, _VP, _VP]),
+    "cb_debug_host_game": (ctypes.c_int, [ctypes.POINTER(SelfplayConfig), _VP, ctypes.c_uint64, EVAL_CALLBACK, _VP,
+                                          _VP, _VP, _VP, _VP, _VP, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                          ctypes.POINTER(ctypes.c_int)]),
+    "cb_debug_device_search": (ctypes.c_int, [_VP, ctypes.POINTER(SelfplayConfig), _VP, ctypes.c_int, _VP, _VP, _VP, _VP, _VP]),
     "cb_launches_per_forward": (ctypes.c_int, [_VP]),
     "cb_get_timing": (ctypes.c_int, [_VP, ctypes.POINTER(CbTiming)]),
     "cb_reset_timing": (None, [_VP]),
@@ -331,20 +421,31 @@ class Evaluator:
 
     def selfplay(self, games=1024, sims_per_move=200, max_plies=200, material_on=False, koth=False, threads=0,
                  c_puct=1.414, explore_base=0.80, seed=1, max_sims=0, max_games=0, max_seconds=0.0, sample_path=None,
-                 pipeline=1, aux=None, qsearch=0, tier1_light=False):
+                 pipeline=1, aux=None, qsearch=0, tier1_light=False, shuffle_children=False, mock=None):
         """Run the self-play pool on this evaluator; returns the stats as a dict.  `aux`: a second Evaluator
         with the same weights that serves the second half-pool in pipeline mode 2.  `qsearch`: 0 stand-pat
-        material, 1 principal exchange ("pe")."""
-        cfg = SelfplayConfig(games, sims_per_move, max_plies, int(material_on), int(koth), threads, c_puct,
-                             explore_base, seed, max_sims, max_games, max_seconds,
-                             sample_path.encode() if sample_path else None, pipeline, aux._h if aux is not None else None,
-                             _QSEARCH[qsearch], int(tier1_light))
+        material, 1 principal exchange ("pe").  `mock`: (v_logit, k) replaces the network by the reference's mock
+        evaluator (device pipelines)."""
+        cfg = selfplay_config(games=games, sims_per_move=sims_per_move, max_plies=max_plies, material_on=material_on, koth=koth,
+                              threads=threads, c_puct=c_puct, explore_base=explore_base, seed=seed, max_sims=max_sims,
+                              max_games=max_games, max_seconds=max_seconds, sample_path=sample_path, pipeline=pipeline,
+                              aux=aux, qsearch=qsearch, tier1_light=tier1_light, shuffle_children=shuffle_children, mock=mock)
         st = SelfplayStats()
         self._check(self._L.cb_selfplay_run(self._h, ctypes.byref(cfg), ctypes.byref(st)))
         return {n: getattr(st, n) for n, _ in SelfplayStats._fields_}
 
+    def debug_device_search(self, boards, **kw):
+        """One move's search with the device tree kernels from every position -> list of [(move, visits, value_sum)],
+        root visit counts (cb_debug_device_search)."""
+        boards = np.ascontiguousarray(boards, dtype=np.uint8).reshape(-1, 128)
+        n = boards.shape[0]
+        cfg = selfplay_config(games=n, pipeline=3, **kw)
+        out = _SearchOut(n)
+        self._check(self._L.cb_debug_device_search(self._h, ctypes.byref(cfg), boards.ctypes.data, n, *out.ptrs()))
+        return out.unpack()
+
     def match(self, current, games=256, total_games=256, sims_per_move=200, max_plies=200, material_on=False, koth=False,
-              c_puct=1.414, explore_base=0.80, seed=1, use_sprt=False, elo0=0.0, elo1=10.0, alpha=0.05, beta=0.05,
+              c_puct=1.414, explore_base=0.90, seed=1, use_sprt=False, elo0=0.0, elo1=10.0, alpha=0.05, beta=0.05,
               max_seconds=0.0, qsearch=0, tier1_light=False):
         """Evaluation match: this evaluator is the candidate, `current` the incumbent (cb_match_run)."""
         cfg = MatchConfig(games, total_games, sims_per_move, max_plies, int(material_on), int(koth), c_puct, explore_base,

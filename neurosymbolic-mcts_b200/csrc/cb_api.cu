@@ -1558,12 +1558,46 @@ int cb_debug_set_layer_limit(cb_handle* h, int n_conv_launches) {
 // and drains the sample log while the GPU idles (~30 us): 8 steps per replay cost 2 % of the run, 32 cost 0.5 %.
 constexpr int kSelfplayStepsPerGraph = 32;
 
-int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
+// Per-game tree state of the device drivers.
+static int mcts_alloc(cb_handle* h, MctsParams& mp, int G, std::vector<void*>& owned) {
+    auto dalloc = [&](void** ptr, size_t bytes) -> int {
+        CB_CUDA(h, cudaMalloc(ptr, bytes));
+        owned.push_back(*ptr);
+        return CB_OK;
+    };
+    int rc;
+    if ((rc = dalloc((void**)&mp.root, (size_t)G * sizeof(cb_board))) ||
+        (rc = dalloc((void**)&mp.nodes, (size_t)G * 2 * mp.node_cap * sizeof(MNode))) ||
+        (rc = dalloc((void**)&mp.n_nodes, (size_t)G * 4)) || (rc = dalloc((void**)&mp.arena, (size_t)G)) ||
+        (rc = dalloc((void**)&mp.history, (size_t)G * kMctsHist * 8)) || (rc = dalloc((void**)&mp.hist_n, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.rng, (size_t)G * 8)) || (rc = dalloc((void**)&mp.ply, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.sims_done, (size_t)G * 4)) || (rc = dalloc((void**)&mp.samples_in_game, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.path, (size_t)G * kMctsMaxDepth * 4)) || (rc = dalloc((void**)&mp.path_n, (size_t)G * 4)) ||
+        (rc = dalloc((void**)&mp.wants_eval, (size_t)G)) || (rc = dalloc((void**)&mp.leaf_moves, (size_t)G * CB_MAX_MOVES * 2)) ||
+        (rc = dalloc((void**)&mp.leaf_trank, (size_t)G * CB_MAX_MOVES)) || (rc = dalloc((void**)&mp.leaf_ntact, (size_t)G)) ||
+        (rc = dalloc((void**)&mp.idle, (size_t)G)) ||
+        (rc = dalloc((void**)&mp.eval_cnt, (size_t)G * 2)) || (rc = dalloc((void**)&mp.stats, MS_COUNT * 8)))
+        return rc;
+    CB_CUDA(h, cudaMemsetAsync(mp.idle, 0, (size_t)G, h->stream));
+    return CB_OK;
+}
+
+// cb_debug_device_search: start positions and where the root children go.
+struct DeviceSearchIO {
+    const cb_board* boards;
+    uint16_t* moves;
+    uint32_t* visits;
+    double* value_sums;
+    int32_t* counts;
+    uint32_t* root_visits;
+};
+
+static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out, const DeviceSearchIO* dbg) {
     if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
     if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
     CB_CUDA(h, cudaSetDevice(h->device));
     const int G = cfg->games;
-    const int pools = cfg->pipeline == 4 ? 2 : 1;
+    const int pools = (!dbg && cfg->pipeline == 4) ? 2 : 1;
     if (pools == 2 && (G & 1)) return fail(h, CB_EINVAL, "two pools need an even number of games");
     int rc = ensure_capacity(h, G);
     if (rc) return rc;
@@ -1583,8 +1617,11 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     mp.qsearch = cfg->qsearch;
     mp.tier1_light = cfg->tier1_light;
     mp.koth = cfg->koth;
-    mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
+    mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414;
     mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
+    mp.shuffle = cfg->shuffle_children;
+    mp.mock_eval = cfg->mock_eval;
+    mp.search_only = dbg ? 1 : 0;
     {   // a move adds sims_per_move expansions of ~35 (at most 218) children to the subtree kept from the last move
         const long long want = (long long)cfg->sims_per_move * 160;
         mp.node_cap = (uint32_t)(want < 32768 ? 32768 : want > 262144 ? 262144 : want);
@@ -1597,15 +1634,7 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         return CB_OK;
     };
     auto release = [&] { for (void* q : owned) cudaFree(q); };
-    if ((rc = dalloc((void**)&mp.root, (size_t)G * sizeof(cb_board))) ||
-        (rc = dalloc((void**)&mp.nodes, (size_t)G * 2 * mp.node_cap * sizeof(MNode))) ||
-        (rc = dalloc((void**)&mp.n_nodes, (size_t)G * 4)) || (rc = dalloc((void**)&mp.arena, (size_t)G)) ||
-        (rc = dalloc((void**)&mp.history, (size_t)G * kMctsHist * 8)) || (rc = dalloc((void**)&mp.hist_n, (size_t)G * 4)) ||
-        (rc = dalloc((void**)&mp.rng, (size_t)G * 8)) || (rc = dalloc((void**)&mp.ply, (size_t)G * 4)) ||
-        (rc = dalloc((void**)&mp.sims_done, (size_t)G * 4)) || (rc = dalloc((void**)&mp.samples_in_game, (size_t)G * 4)) ||
-        (rc = dalloc((void**)&mp.path, (size_t)G * kMctsMaxDepth * 4)) || (rc = dalloc((void**)&mp.path_n, (size_t)G * 4)) ||
-        (rc = dalloc((void**)&mp.wants_eval, (size_t)G)) || (rc = dalloc((void**)&mp.leaf_moves, (size_t)G * CB_MAX_MOVES * 2)) ||
-        (rc = dalloc((void**)&mp.eval_cnt, (size_t)G * 2)) || (rc = dalloc((void**)&mp.stats, MS_COUNT * 8))) {
+    if ((rc = mcts_alloc(h, mp, G, owned))) {
         release();
         return rc;
     }
@@ -1633,6 +1662,13 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         cudaMemsetAsync(mp.ring_cursor, 0, 8, h->stream);
         cudaMemsetAsync(mp.game_serial, 0, (size_t)G * 4, h->stream);
         pending.resize(G);
+    }
+    if (cfg->mock_eval && pools == 2) { if (sample_file) fclose(sample_file); release(); return fail(h, CB_EINVAL, "the mock evaluator runs with one pool"); }
+    if (dbg) {
+        cb_board* d_start = nullptr;
+        if ((rc = dalloc((void**)&d_start, (size_t)G * sizeof(cb_board)))) { release(); return rc; }
+        CB_CUDA(h, cudaMemcpyAsync(d_start, dbg->boards, (size_t)G * sizeof(cb_board), cudaMemcpyHostToDevice, h->stream));
+        mp.start_boards = d_start;
     }
     cudaMemsetAsync(mp.stats, 0, MS_COUNT * 8, h->stream);
     cudaMemsetAsync(h->d_boards, 0, (size_t)G * sizeof(cb_board), h->stream);
@@ -1662,6 +1698,10 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         return q;
     };
     auto fwd = [&](int pool) -> int {
+        if (cfg->mock_eval) {   // the reference's mock server in place of the network (tests)
+            mcts_mock_eval_kernel<<<(G + 3) / 4, 128, 0, h->stream>>>(pool_params(0, false), cfg->mock_v_logit, cfg->mock_k, h->d_priors, h->d_vfinal);
+            return CB_OK;
+        }
         if (pools == 1) return enqueue_forward(h, G, false, true, cfg->material_on, true, mp.eval_cnt);
         PolicyOut po = {};
         po.move_idx = h->d_move_idx + (size_t)pool * Gp * CB_MAX_MOVES;
@@ -1696,6 +1736,41 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
         if ((r = fwd(1)) || (r = step_beside(0)) || (r = fwd(0)) || (r = step_beside(1))) return r;
         return CB_OK;
     };
+    if (dbg) {
+        // one move's search for every position: a fresh root asks for its policy first (one step that is no simulation),
+        // then sims_per_move simulations; games that are done go idle.  Eager launches, then the root children are read.
+        mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+        for (int i = 0; i <= cfg->sims_per_move && !rc; ++i) rc = fused();
+        cudaError_t e2 = cudaStreamSynchronize(h->stream);
+        std::vector<MNode> kids(CB_MAX_MOVES);
+        std::vector<uint8_t> arena(G);
+        unsigned long long st2[MS_COUNT] = {0};
+        if (!rc && e2 == cudaSuccess) e2 = cudaMemcpy(arena.data(), mp.arena, (size_t)G, cudaMemcpyDeviceToHost);
+        if (!rc && e2 == cudaSuccess) e2 = cudaMemcpy(st2, mp.stats, sizeof(st2), cudaMemcpyDeviceToHost);
+        for (int g = 0; g < G && !rc && e2 == cudaSuccess; ++g) {
+            const MNode* base = mp.nodes + ((size_t)g * 2 + arena[g]) * mp.node_cap;
+            MNode root;
+            e2 = cudaMemcpy(&root, base, sizeof(MNode), cudaMemcpyDeviceToHost);
+            if (e2 != cudaSuccess) break;
+            const int nc = root.state == 1 ? root.n_children : 0;
+            dbg->counts[g] = nc;
+            if (dbg->root_visits) dbg->root_visits[g] = root.visits;
+            if (nc > 0) e2 = cudaMemcpy(kids.data(), base + root.first_child, (size_t)nc * sizeof(MNode), cudaMemcpyDeviceToHost);
+            for (int c = 0; c < nc; ++c) {
+                if (dbg->moves) dbg->moves[(size_t)g * CB_MAX_MOVES + c] = kids[c].move;
+                if (dbg->visits) dbg->visits[(size_t)g * CB_MAX_MOVES + c] = kids[c].visits;
+                if (dbg->value_sums) dbg->value_sums[(size_t)g * CB_MAX_MOVES + c] = kids[c].value_sum;
+            }
+        }
+        release();
+        if (rc) return rc;
+        if (e2 != cudaSuccess) return fail(h, CB_ECUDA, std::string("device search: ") + cudaGetErrorString(e2));
+        out->nn_evals = (long long)st2[MS_EVALS];
+        out->terminal_hits = (long long)st2[MS_TERMINAL];
+        out->overflow = (long long)st2[MS_OVERFLOW];
+        out->steps = cfg->sims_per_move + 1;
+        return CB_OK;
+    }
     const long long target = cfg->max_sims > 0 ? (cfg->max_sims + G - 1) / G : 0;   // steps to run (0 = unbounded)
     long long done = 0;                        // completed steps; one more is always in flight
     for (int pool = 0; pool < pools; ++pool) mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
@@ -1804,12 +1879,29 @@ int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_
     out->white_wins = (long long)st[MS_WWINS];
     out->black_wins = (long long)st[MS_BWINS];
     out->draws = (long long)st[MS_DRAWS];
+    out->overflow = (long long)st[MS_OVERFLOW];
     out->seconds = secs;
     const double tot = (double)ms_fwd + ms_tree;
     out->eval_seconds = tot > 0 ? secs * ms_fwd / tot : 0.0;
     out->tree_seconds = tot > 0 ? secs * ms_tree / tot : 0.0;
     out->mean_batch = steps ? (double)out->nn_evals / (double)steps : 0.0;
     return CB_OK;
+}
+
+int cb_selfplay_device(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
+    return selfplay_device_impl(h, cfg, out, nullptr);
+}
+
+int cb_debug_device_search(cb_handle* h, const cb_selfplay_config* cfg, const cb_board* boards, int n,
+                           uint16_t* moves, uint32_t* visits, double* value_sums, int32_t* counts, uint32_t* root_visits) {
+    if (!h || !cfg || !boards || n <= 0 || !counts) return CB_EINVAL;
+    cb_selfplay_config c = *cfg;
+    c.games = n;
+    c.pipeline = 3;
+    c.sample_path = nullptr;
+    cb_selfplay_stats st;
+    const DeviceSearchIO io = {boards, moves, visits, value_sums, counts, root_visits};
+    return selfplay_device_impl(h, &c, &st, &io);
 }
 
 // ------------------------------------------------------------------ SPRT (src/mcts/sprt.rs)
@@ -1867,8 +1959,8 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     mp.qsearch = cfg->qsearch;
     mp.tier1_light = cfg->tier1_light;
     mp.koth = cfg->koth;
-    mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
-    mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
+    mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414;
+    mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.90;   // DEFAULT_EXPLORE_BASE, src/bin/evaluate_models.rs:85
     {   // fresh tree every move: sims_per_move expansions of ~35 (at most 218) children
         const long long want = (long long)cfg->sims_per_move * 64;
         mp.node_cap = (uint32_t)(want < 8192 ? 8192 : want > 65536 ? 65536 : want);
@@ -1884,16 +1976,8 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
         return CB_OK;
     };
     auto release = [&] { for (void* q : owned) cudaFree(q); };
-    if ((rc = dalloc((void**)&mp.root, (size_t)G * sizeof(cb_board))) ||
-        (rc = dalloc((void**)&mp.nodes, (size_t)G * 2 * mp.node_cap * sizeof(MNode))) ||
-        (rc = dalloc((void**)&mp.n_nodes, (size_t)G * 4)) || (rc = dalloc((void**)&mp.arena, (size_t)G)) ||
-        (rc = dalloc((void**)&mp.history, (size_t)G * kMctsHist * 8)) || (rc = dalloc((void**)&mp.hist_n, (size_t)G * 4)) ||
-        (rc = dalloc((void**)&mp.rng, (size_t)G * 8)) || (rc = dalloc((void**)&mp.ply, (size_t)G * 4)) ||
-        (rc = dalloc((void**)&mp.sims_done, (size_t)G * 4)) || (rc = dalloc((void**)&mp.samples_in_game, (size_t)G * 4)) ||
-        (rc = dalloc((void**)&mp.path, (size_t)G * kMctsMaxDepth * 4)) || (rc = dalloc((void**)&mp.path_n, (size_t)G * 4)) ||
-        (rc = dalloc((void**)&mp.wants_eval, (size_t)G)) || (rc = dalloc((void**)&mp.leaf_moves, (size_t)G * CB_MAX_MOVES * 2)) ||
-        (rc = dalloc((void**)&mp.eval_cnt, (size_t)G * 2)) || (rc = dalloc((void**)&mp.stats, MS_COUNT * 8)) ||
-        (rc = dalloc((void**)&mp.cand_white, (size_t)G)) || (rc = dalloc((void**)&mp.idle, (size_t)G)) ||
+    if ((rc = mcts_alloc(h, mp, G, owned)) ||
+        (rc = dalloc((void**)&mp.cand_white, (size_t)G)) ||
         (rc = dalloc((void**)&mp.games_started, 8)) || (rc = dalloc((void**)&mp.result_cursor, 8)) ||
         (rc = dalloc((void**)&mp.result_log, (size_t)mp.result_cap * 4))) {
         release();

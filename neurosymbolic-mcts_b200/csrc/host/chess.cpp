@@ -34,7 +34,7 @@ void startpos(cb_board* b) {
 
 bool in_check(const cb_board& b, int color) { return in_check_hd(b, color); }
 void make_move(const cb_board& b, Move m, cb_board* out) { make_move_hd(b, m, out); }
-int gen_legal(const cb_board& b, Move* out) { return gen_legal_hd(b, out); }
+int gen_legal(const cb_board& b, Move* out, int* n_tactical) { return gen_legal_hd(b, out, n_tactical); }
 int policy_index(Move m, bool white_to_move) { return policy_index_hd(m, white_to_move); }
 uint64_t position_key(const cb_board& b) { return position_key_hd(b); }
 

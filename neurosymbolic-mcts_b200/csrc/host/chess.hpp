@@ -31,7 +31,7 @@ constexpr uint64_t kKothCenter = 0x0000001818000000ull;  // d4 e4 d5 e5 (src/boa
 
 void startpos(cb_board* b);
 bool in_check(const cb_board& b, int color);
-int gen_legal(const cb_board& b, Move* out);            // captures / promotions first
+int gen_legal(const cb_board& b, Move* out, int* n_tactical = nullptr);   // the reference's generation order; see chess_rules.hpp
 void make_move(const cb_board& b, Move m, cb_board* out);
 uint64_t perft(const cb_board& b, int depth);
 int policy_index(Move m, bool white_to_move);           // move_to_index(flip-if-black(m)); -1 if malformed

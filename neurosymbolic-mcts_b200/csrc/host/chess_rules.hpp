@@ -1,6 +1,6 @@
 // chess_rules.hpp — the bitboard chess rules of chess.hpp as inline host+device code, so that the
 // host self-play driver (selfplay.cpp) and the device-side tree kernels (mcts_device.cuh) run the SAME
-// move generator: identical legal sets in identical order (captures / promotions first), identical
+// move generator: identical legal sets in identical order (the reference's generation order), identical
 // make-move side effects (src/make_move.rs:99-185), identical policy indices (src/tensor.rs:82-178).
 // Attack tables (6 KB) are a static object on the host and a global-memory object on the device (L1-resident;
 // the warp forms index them with a different square in every lane, which the constant cache would serialise).
@@ -126,31 +126,56 @@ CB_HD int add_pawn(Move* out, int n, int from, int to, int promo_rank) {
     return n;
 }
 
-// Pseudo-legal moves, captures and promotions first (src/move_generation.rs:323-328).
-CB_HD int gen_pseudo(const cb_board& b, Move* out) {
+// Target order of one knight / king, as square deltas: the reference's tables list them this way
+// (init_knight_moves src/magic_bitboard.rs:160-189, init_king_moves :120-149), and a piece's moves are generated in
+// table order.  A delta is valid when the target is in the piece's attack set (a wrapped delta never is).
+CB_HD int knight_delta(int i) { return i == 0 ? 15 : i == 1 ? 17 : i == 2 ? 6 : i == 3 ? 10 : i == 4 ? -10 : i == 5 ? -6 : i == 6 ? -17 : -15; }
+CB_HD int king_delta(int i) { return i == 0 ? -1 : i == 1 ? 7 : i == 2 ? 8 : i == 3 ? 9 : i == 4 ? 1 : i == 5 ? -7 : i == 6 ? -8 : -9; }
+CB_HD uint64_t step_targets_bit(uint64_t att, int from, int d) {
+    const int to = from + d;
+    return (to >= 0 && to < 64) ? (att & (1ull << to)) : 0ull;
+}
+
+// Pseudo-legal moves in the reference's generation order (gen_pseudo_legal_moves, src/move_generation.rs:287-328):
+//   capture list  pawn captures incl. en passant (per pawn from the lowest square, the a-file side target first), knights
+//                 (table order), bishops, rooks (attack-set bits ascending), queens (rook set, then bishop set), king
+//                 (table order), then every promotion (per pawn: capturing ones first; Q, R, N, B)
+//   quiet list    pawns (the DOUBLE push before the single one, src/magic_bitboard.rs:248-265), knights, bishops, rooks,
+//                 queens, then the king: castling (king side, queen side) before its steps
+// Children of a tree node are created in this order (src/mcts/tactical_mcts.rs:813-836), which decides PUCT ties, the
+// root's force-visit order and the order of the tactical phase.  *n_caps (nullable) = length of the capture list.
+CB_HD int gen_pseudo(const cb_board& b, Move* out, int* n_caps = nullptr) {
     const Tables& T = tables();
     int n = 0;
     const int us = b.w_to_move ? 0 : 1, them = 1 - us;
     const uint64_t own = b.occ[us], opp = b.occ[them], occ = own | opp;
     const uint64_t* pc = &b.pieces[us * 6];
-    const int fwd = us == 0 ? 8 : -8, promo_rank = us == 0 ? 7 : 0, start_rank = us == 0 ? 1 : 6;
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool caps = pass == 0;
+    const int fwd = us == 0 ? 8 : -8, promo_from_rank = us == 0 ? 6 : 1, start_rank = us == 0 ? 1 : 6;
+    const uint64_t ep = b.en_passant != 0xFF ? 1ull << b.en_passant : 0ull;
+    for (int pass = 0; pass < 3; ++pass) {   // 0 captures, 1 promotions, 2 quiets
         for (uint64_t bb = pc[PAWN]; bb; bb &= bb - 1) {
             const int from = lsb(bb), one = from + fwd;
-            if (caps) {
-                for (uint64_t t = T.pawn[us][from] & opp; t; t &= t - 1) n = add_pawn(out, n, from, lsb(t), promo_rank);
-                if (b.en_passant != 0xFF && (T.pawn[us][from] >> b.en_passant & 1)) out[n++] = make_mv(from, b.en_passant, 0);
-                if ((one >> 3) == promo_rank && !(occ >> one & 1)) n = add_pawn(out, n, from, one, promo_rank);
-            } else if ((one >> 3) != promo_rank && !(occ >> one & 1)) {
-                out[n++] = make_mv(from, one, 0);
+            const bool promo = (from >> 3) == promo_from_rank;
+            if (pass == 0 && !promo) {
+                for (uint64_t t = T.pawn[us][from] & (opp | ep); t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
+            } else if (pass == 1 && promo) {
+                for (uint64_t t = T.pawn[us][from] & (opp | ep); t; t &= t - 1) n = add_pawn(out, n, from, lsb(t), one >> 3);
+                if (!(occ >> one & 1)) n = add_pawn(out, n, from, one, one >> 3);
+            } else if (pass == 2 && !promo && !(occ >> one & 1)) {
                 if ((from >> 3) == start_rank && !(occ >> (one + fwd) & 1)) out[n++] = make_mv(from, one + fwd, 0);
+                out[n++] = make_mv(from, one, 0);
             }
         }
-        const uint64_t mask = caps ? opp : ~occ;
+        if (pass == 1) {
+            if (n_caps) *n_caps = n;
+            continue;
+        }
+        const uint64_t mask = pass == 0 ? opp : ~occ;
         for (uint64_t bb = pc[KNIGHT]; bb; bb &= bb - 1) {
             const int from = lsb(bb);
-            for (uint64_t t = T.knight[from] & mask; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
+            const uint64_t att = T.knight[from] & mask;
+            for (int i = 0; i < 8; ++i)
+                if (step_targets_bit(att, from, knight_delta(i))) out[n++] = make_mv(from, from + knight_delta(i), 0);
         }
         for (uint64_t bb = pc[BISHOP]; bb; bb &= bb - 1) {
             const int from = lsb(bb);
@@ -162,14 +187,10 @@ CB_HD int gen_pseudo(const cb_board& b, Move* out) {
         }
         for (uint64_t bb = pc[QUEEN]; bb; bb &= bb - 1) {
             const int from = lsb(bb);
-            for (uint64_t t = (rook_att(from, occ) | bishop_att(from, occ)) & mask; t; t &= t - 1)
-                out[n++] = make_mv(from, lsb(t), 0);
+            for (uint64_t t = rook_att(from, occ) & mask; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
+            for (uint64_t t = bishop_att(from, occ) & mask; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
         }
-        for (uint64_t bb = pc[KING]; bb; bb &= bb - 1) {
-            const int from = lsb(bb);
-            for (uint64_t t = T.king[from] & mask; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
-        }
-        if (!caps) {
+        if (pass == 2) {
             const int ksq = us == 0 ? 4 : 60;
             if ((pc[KING] >> ksq & 1) && !attacked(b, ksq, them)) {
                 const int ks = us == 0 ? WK : BK, qs = us == 0 ? WQ : BQ;
@@ -180,6 +201,12 @@ CB_HD int gen_pseudo(const cb_board& b, Move* out) {
                     !attacked(b, ksq - 1, them) && !attacked(b, ksq - 2, them))
                     out[n++] = make_mv(ksq, ksq - 2, 0);
             }
+        }
+        for (uint64_t bb = pc[KING]; bb; bb &= bb - 1) {
+            const int from = lsb(bb);
+            const uint64_t att = T.king[from] & mask;
+            for (int i = 0; i < 8; ++i)
+                if (step_targets_bit(att, from, king_delta(i))) out[n++] = make_mv(from, from + king_delta(i), 0);
         }
     }
     return n;
@@ -226,18 +253,47 @@ CB_HD void make_move_hd(const cb_board& src, Move m, cb_board* out) {
 }
 
 // Legal moves in generation order: a pseudo-legal move stays if the mover's king is not attacked after
-// it (src/make_move.rs:24, src/board.rs:352).
-CB_HD int gen_legal_hd(const cb_board& b, Move* out) {
+// it (src/make_move.rs:24, src/board.rs:352).  *n_tactical (nullable) = how many of them come from the capture list:
+// the candidates of the tactical phase (src/mcts/tactical.rs:155-177).
+CB_HD int gen_legal_hd(const cb_board& b, Move* out, int* n_tactical = nullptr) {
     Move tmp[kMaxMoves];
-    const int np = gen_pseudo(b, tmp);
+    int ncap = 0;
+    const int np = gen_pseudo(b, tmp, &ncap);
     const int us = b.w_to_move ? 0 : 1;
-    int n = 0;
+    int n = 0, nt = 0;
     for (int i = 0; i < np; ++i) {
         cb_board nb;
         make_move_hd(b, tmp[i], &nb);
-        if (!in_check_hd(nb, us)) out[n++] = tmp[i];
+        if (!in_check_hd(nb, us)) {
+            out[n++] = tmp[i];
+            if (i < ncap) ++nt;
+        }
     }
+    if (n_tactical) *n_tactical = nt;
     return n;
+}
+
+// calculate_mvv_lva of the tactical phase (src/mcts/tactical.rs:179-216) as an integer: 10 * victim - attacker + promoted
+// piece with P1 N3 B3 R5 Q9 K0 (the en-passant target square is empty: victim 0).  Range [-9, 98].
+CB_HD int tactical_score_hd(const cb_board& b, Move m) {
+    const int us = b.w_to_move ? 0 : 1;
+    const int val[6] = {1, 3, 3, 5, 9, 0};
+    const int victim = piece_on(b, 1 - us, 1ull << mv_to(m)), attacker = piece_on(b, us, 1ull << mv_from(m));
+    int s = (victim >= 0 ? 10 * val[victim] : 0) - (attacker >= 0 ? val[attacker] : 0);
+    if (mv_promo(m)) s += val[mv_promo(m)];
+    return s;
+}
+
+// Rank of every tactical child in the order the reference visits them (stable descending sort by score,
+// src/mcts/tactical.rs:166-172): rank[i] for the first n_tactical moves of a legal list in generation order.
+CB_HD void tactical_ranks_hd(const cb_board& b, const Move* legal, int n_tactical, uint8_t* rank) {
+    int sc[kMaxMoves];
+    for (int i = 0; i < n_tactical; ++i) sc[i] = tactical_score_hd(b, legal[i]);
+    for (int i = 0; i < n_tactical; ++i) {
+        int r = 0;
+        for (int j = 0; j < n_tactical; ++j) r += sc[j] > sc[i] || (sc[j] == sc[i] && j < i);
+        rank[i] = (uint8_t)r;
+    }
 }
 
 CB_HD int policy_index_hd(Move m, bool white_to_move) {

@@ -28,16 +28,25 @@ using namespace cbchess;
 
 namespace {
 
+// Same 32-byte node as the device arenas (mcts_device.cuh: MNode).
 struct Node {
+    double value_sum = 0.0;   // total_value (f64 as the reference): from the point of view of the player who moved INTO this node
     uint32_t first_child = 0;
     uint32_t visits = 0;
-    float value_sum = 0.0f;   // from the point of view of the player who moved INTO this node
     float prior = 0.0f;
     uint16_t n_children = 0;
     Move move = 0;
-    uint8_t state = 0;        // 0 unexpanded, 1 expanded, 2 terminal
-    int8_t term_value = 0;    // value for the side to move at a terminal node (-1 mated, 0 stalemate)
+    uint8_t state = 0;        // 0 unexpanded, 1 expanded, 2 terminal or resolved by a gate
+    int8_t term_value = 0;    // terminal_or_mate_value for the side to move at a state-2 node
+    uint8_t n_tact = 0;       // as a parent: children from the capture list
+    uint8_t t_done = 0;       // as a parent: how many of them have been visited
+    uint8_t trank = 0xFF;     // as a child: place in the parent's tactical order
+    uint8_t term_dist = 0;    // terminal_distance of a state-2 node
+    uint16_t pad = 0;
 };
+static_assert(sizeof(Node) == 32, "node layout");
+
+constexpr uint8_t kMateIn1Dist = (uint8_t)1000001u;   // `mate_result.0.unsigned_abs() as u8`, src/mcts/tactical_mcts.rs:701
 
 struct Sample {
     cb_board board;
@@ -56,6 +65,12 @@ float material_q(const cb_board& b, int qsearch) {
     return (float)(qsearch == 1 ? cbchess::principal_exchange_cp(b) : cbchess::pesto_cp(b)) / 100.0f;
 }
 
+// What the search needs of cb_selfplay_config / cb_match_config.
+struct SearchCfg {
+    int sims = 200, material_on = 0, qsearch = 0, koth = 0, tier1_light = 0, shuffle = 0, max_plies = 200;
+    double c_puct = 1.414, explore_base = 0.80;
+};
+
 struct Game {
     cb_board root_board;
     std::vector<Node> nodes;        // nodes[0] = root
@@ -69,11 +84,14 @@ struct Game {
     cb_board leaf_board;
     Move leaf_moves[kMaxMoves];
     uint16_t leaf_idx[kMaxMoves];
-    int leaf_n = 0;
+    uint8_t leaf_trank[kMaxMoves];
+    int leaf_n = 0, leaf_ntact = 0;
+    float leaf_q = 0.0f;
     bool wants_eval = false;
 
-    void reset(uint64_t seed) {
-        startpos(&root_board);
+    void reset(uint64_t seed, const cb_board* start = nullptr) {
+        if (start) root_board = *start;
+        else startpos(&root_board);
         nodes.clear();
         nodes.emplace_back();
         history.clear();
@@ -85,8 +103,41 @@ struct Game {
     }
 };
 
-// One simulation, phase A: walk down with PUCT; stop at an unexpanded or terminal node.
-void select_leaf(Game& g, float c_puct, std::atomic<long long>& terminal_hits, bool tier1_light, bool koth) {
+void backup(Game& g, double val) {   // src/mcts/node.rs:403-424: the sign flips every ply
+    for (int i = (int)g.path.size() - 1; i >= 0; --i) {
+        val = -val;
+        Node& n = g.nodes[g.path[i]];
+        n.value_sum += val;
+        n.visits++;
+    }
+}
+
+// should_early_terminate, src/mcts/tactical_mcts.rs:524-560 (only with the gates on)
+bool early_terminate(const Game& g) {
+    const Node& root = g.nodes[0];
+    if (root.state != 1) return false;
+    bool win1 = false, forced = false, all_visited = true, all_losing = root.n_children > 0;
+    for (uint32_t i = 0; i < root.n_children; ++i) {
+        const Node& ch = g.nodes[root.first_child + i];
+        const bool term = ch.state == 2;
+        if (term && ch.term_value < 0) win1 = true;
+        if (ch.visits > 0 && ch.value_sum / (double)ch.visits > 0.99) forced = true;
+        if (ch.visits == 0) all_visited = false;
+        if (!(term && ch.term_value > 0)) all_losing = false;
+    }
+    if (win1) return true;
+    if (forced && all_visited) return true;
+    return all_visited && all_losing;
+}
+
+void sim_done(Game& g, const SearchCfg& c) {
+    if (c.tier1_light && early_terminate(g)) g.sims_done = c.sims;
+    else g.sims_done++;
+}
+
+// One simulation, phase A: walk down — tactical phase (src/mcts/selection.rs:37-63,107-149), every root child once
+// (:65-73), PUCT in f64 with the proven-loss rules (:152-273) — and stop at an unexpanded or decided node.
+void select_leaf(Game& g, const SearchCfg& c, std::atomic<long long>& terminal_hits) {
     g.path.clear();
     g.wants_eval = false;
     uint32_t cur = 0;
@@ -96,22 +147,34 @@ void select_leaf(Game& g, float c_puct, std::atomic<long long>& terminal_hits, b
     for (;;) {
         Node& n = g.nodes[cur];
         if (n.state != 1) break;
-        uint32_t best = n.first_child;
-        bool forced = false;
-        if (depth == 0) {  // every root child gets one visit first (src/mcts/selection.rs:65-73)
+        uint32_t best = 0xFFFFFFFFu;
+        if (n.t_done < n.n_tact) {
             for (uint32_t i = 0; i < n.n_children; ++i)
-                if (g.nodes[n.first_child + i].visits == 0) { best = n.first_child + i; forced = true; break; }
-        }
-        if (!forced) {
-            const float sq = sqrtf((float)(n.visits > 1 ? n.visits : 1));
-            float best_u = -1e30f;
-            for (uint32_t i = 0; i < n.n_children; ++i) {
-                const Node& ch = g.nodes[n.first_child + i];
-                const float q = ch.visits ? ch.value_sum / (float)ch.visits : 0.0f;
-                const float u = q + c_puct * ch.prior * sq / (1.0f + (float)ch.visits);
-                if (u > best_u) { best_u = u; best = n.first_child + i; }
+                if (g.nodes[n.first_child + i].trank == n.t_done) { best = n.first_child + i; break; }
+            n.t_done++;
+        } else {
+            if (depth == 0)
+                for (uint32_t i = 0; i < n.n_children; ++i)
+                    if (g.nodes[n.first_child + i].visits == 0) { best = n.first_child + i; break; }
+            if (best == 0xFFFFFFFFu) {
+                const double sq = sqrt((double)(n.visits > 1 ? n.visits : 1));
+                double best_u = -INFINITY;
+                uint32_t losing = 0xFFFFFFFFu;
+                int losing_dist = -1;
+                for (uint32_t i = 0; i < n.n_children; ++i) {
+                    const Node& ch = g.nodes[n.first_child + i];
+                    if (ch.state == 2 && ch.term_value > 0) {
+                        if ((int)ch.term_dist > losing_dist) { losing_dist = ch.term_dist; losing = n.first_child + i; }
+                        continue;
+                    }
+                    const double q = ch.visits ? ch.value_sum / (double)ch.visits : 0.0;
+                    const double u = q + c.c_puct * (double)ch.prior * sq / (1.0 + (double)ch.visits);
+                    if (u > best_u) { best_u = u; best = n.first_child + i; }
+                }
+                if (best == 0xFFFFFFFFu) best = losing;
             }
         }
+        if (best == 0xFFFFFFFFu) break;
         cb_board nb;
         make_move(board, g.nodes[best].move, &nb);
         board = nb;
@@ -120,67 +183,73 @@ void select_leaf(Game& g, float c_puct, std::atomic<long long>& terminal_hits, b
         ++depth;
     }
     Node& leaf = g.nodes[cur];
-    if (leaf.state == 2) {  // terminal: back its value up again
-        float val = (float)leaf.term_value;
-        for (int i = (int)g.path.size() - 1; i >= 0; --i) {
-            val = -val;
-            Node& n = g.nodes[g.path[i]];
-            n.value_sum += val;
-            n.visits++;
-        }
+    if (leaf.state != 0) {  // decided: back its value up again
+        backup(g, leaf.state == 2 ? (double)leaf.term_value : 0.0);
         terminal_hits.fetch_add(1, std::memory_order_relaxed);
-        g.sims_done++;
+        sim_done(g, c);
         return;
     }
-    g.leaf_n = gen_legal(board, g.leaf_moves);
+    g.leaf_n = gen_legal(board, g.leaf_moves, &g.leaf_ntact);
     // mate / stalemate (MctsNode::new_child terminal test, src/mcts/node.rs:162-177), else the light Tier-1 gates
     // (gates.hpp); with the gates on, an opponent king on the hill is tested before anything else
-    // (src/mcts/tactical_mcts.rs:619-632)
-    int tv = 2;
-    if (tier1_light && koth && (board.pieces[(board.w_to_move ? 1 : 0) * 6 + KING] & kKothCenter)) tv = -1;
-    else if (g.leaf_n == 0) tv = in_check(board, board.w_to_move ? 0 : 1) ? -1 : 0;
-    else if (tier1_light) tv = cbchess::light_gates_hd(board, g.leaf_moves, g.leaf_n, koth);
+    // (src/mcts/tactical_mcts.rs:619-632).  The root itself is never gated (the game loop adjudicates it first).
+    int tv = 2, td = 0;
+    const int us = board.w_to_move ? 0 : 1;
+    if (g.leaf_n == 0) tv = in_check(board, us) ? -1 : 0;
+    else if (c.tier1_light && cur != 0) {
+        if (c.koth && (board.pieces[(1 - us) * 6 + KING] & kKothCenter)) tv = -1;
+        else if (c.koth && cbchess::koth_in_1_hd(board, g.leaf_moves, g.leaf_n)) {
+            tv = 1;
+            td = (board.pieces[us * 6 + KING] & kKothCenter) ? 0 : 1;
+        } else if (cbchess::mate_in_1_hd(board, g.leaf_moves, g.leaf_n)) {
+            tv = 1;
+            td = kMateIn1Dist;
+        }
+    }
     if (tv != 2) {
         leaf.state = 2;
         leaf.term_value = (int8_t)tv;
-        float val = (float)leaf.term_value;
-        for (int i = (int)g.path.size() - 1; i >= 0; --i) {
-            val = -val;
-            Node& n = g.nodes[g.path[i]];
-            n.value_sum += val;
-            n.visits++;
-        }
+        leaf.term_dist = (uint8_t)td;
+        backup(g, (double)tv);
         terminal_hits.fetch_add(1, std::memory_order_relaxed);
-        g.sims_done++;
+        sim_done(g, c);
         return;
     }
+    for (int i = 0; i < g.leaf_n; ++i) g.leaf_trank[i] = 0xFF;
+    cbchess::tactical_ranks_hd(board, g.leaf_moves, g.leaf_ntact, g.leaf_trank);
+    if (c.shuffle)   // SliceRandom::shuffle: for i in (1..len).rev() swap(i, uniform(0..=i))
+        for (int i = g.leaf_n - 1; i >= 1; --i) {
+            const int j = (int)(g.rng.next() % (uint64_t)(i + 1));
+            std::swap(g.leaf_moves[i], g.leaf_moves[j]);
+            std::swap(g.leaf_trank[i], g.leaf_trank[j]);
+        }
     for (int i = 0; i < g.leaf_n; ++i) g.leaf_idx[i] = (uint16_t)policy_index(g.leaf_moves[i], board.w_to_move != 0);
     g.leaf_board = board;
+    // a root asks for its policy only, with dM = 0 (src/mcts/selection.rs:315-332)
+    g.leaf_q = (cur == 0 || !c.material_on) ? 0.0f : material_q(board, c.qsearch);
     g.wants_eval = true;
 }
 
 // Phase C: expand the evaluated leaf with its priors and back the value up.
-void expand_and_backup(Game& g, const float* priors, float v_final) {
+void expand_and_backup(Game& g, const SearchCfg& c, const float* priors, float v_final) {
     const uint32_t cur = g.path.back();
     const uint32_t first = (uint32_t)g.nodes.size();
     g.nodes.resize(g.nodes.size() + g.leaf_n);
     Node& leaf = g.nodes[cur];
     leaf.first_child = first;
     leaf.n_children = (uint16_t)g.leaf_n;
+    leaf.n_tact = (uint8_t)g.leaf_ntact;
+    leaf.t_done = 0;
     leaf.state = 1;
     for (int i = 0; i < g.leaf_n; ++i) {
         Node& ch = g.nodes[first + i];
         ch.move = g.leaf_moves[i];
         ch.prior = priors[i];
+        ch.trank = g.leaf_trank[i];
     }
-    float val = v_final;  // side-to-move perspective at the leaf
-    for (int i = (int)g.path.size() - 1; i >= 0; --i) {
-        val = -val;  // sign flips every ply (src/mcts/node.rs:403-424)
-        Node& n = g.nodes[g.path[i]];
-        n.value_sum += val;
-        n.visits++;
-    }
-    g.sims_done++;
+    if (cur == 0) return;   // the root only asked for its priors: no value, no simulation
+    backup(g, (double)v_final);  // side-to-move perspective at the leaf
+    sim_done(g, c);
 }
 
 // Keep the subtree under `child` as the new tree (tree reuse, src/bin/self_play.rs:358-363).
@@ -203,6 +272,72 @@ void reroot(Game& g, uint32_t child) {
         }
     }
     g.nodes.swap(fresh);
+}
+
+// After the move's simulations: record the sample, choose and play a move (src/bin/self_play.rs:300-363), detect the end
+// of the game (:365-388).  Returns 2 when the game goes on, else the result for white (+1, 0, -1).
+int play_move(Game& g, const SearchCfg& c) {
+    Node& root = g.nodes[0];
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < root.n_children; ++i) total += g.nodes[root.first_child + i].visits;
+    Sample s;
+    s.board = g.root_board;
+    s.material = material_q(g.root_board, c.qsearch);   // computed whatever material_on says (:315-329)
+    if (total > 0)
+        for (uint32_t i = 0; i < root.n_children; ++i) {
+            const Node& ch = g.nodes[root.first_child + i];
+            s.policy.emplace_back((uint16_t)policy_index(ch.move, g.root_board.w_to_move != 0), (float)ch.visits / (float)total);
+        }
+    g.samples.push_back(std::move(s));
+    // proportional to (visits-1) with probability explore_base^(move-1), else greedy: the LAST most-visited child
+    // (Iterator::max_by_key, :648-650)
+    const int move_number = g.ply / 2 + 1;
+    uint32_t pick = root.first_child;
+    uint32_t best_v = 0;
+    for (uint32_t i = 0; i < root.n_children; ++i)
+        if (g.nodes[root.first_child + i].visits >= best_v) { best_v = g.nodes[root.first_child + i].visits; pick = root.first_child + i; }
+    if (g.rng.uniform() < pow(c.explore_base, move_number - 1)) {
+        uint32_t tot1 = 0;
+        for (uint32_t i = 0; i < root.n_children; ++i) {
+            const uint32_t v = g.nodes[root.first_child + i].visits;
+            tot1 += v > 0 ? v - 1 : 0;
+        }
+        if (tot1 > 0) {
+            const uint32_t thr = (uint32_t)(g.rng.next() % tot1);
+            uint32_t cum = 0;
+            for (uint32_t i = 0; i < root.n_children; ++i) {
+                const uint32_t v = g.nodes[root.first_child + i].visits;
+                cum += v > 0 ? v - 1 : 0;
+                if (cum > thr) { pick = root.first_child + i; break; }
+            }
+        }
+    }
+    const Move mv = g.nodes[pick].move;
+    const bool white_moved = g.root_board.w_to_move != 0;
+    cb_board nb;
+    make_move(g.root_board, mv, &nb);
+    if (nb.halfmove == 0) g.history.clear();
+    g.root_board = nb;
+    g.history.push_back(position_key(nb));
+    g.ply++;
+    g.sims_done = 0;
+    reroot(g, pick);
+    int result = 2;
+    Move tmp[kMaxMoves];
+    if (c.koth && (nb.pieces[(white_moved ? 0 : 6) + KING] & kKothCenter)) result = white_moved ? 1 : -1;
+    else {
+        const int n_legal = gen_legal(nb, tmp);
+        if (n_legal == 0) result = in_check(nb, nb.w_to_move ? 0 : 1) ? (white_moved ? 1 : -1) : 0;
+        else {
+            int reps = 0;
+            for (uint64_t k : g.history) reps += (k == g.history.back());
+            if (reps >= 3 || nb.halfmove >= 100 || g.ply > c.max_plies) result = 0;
+            // the game goes on: a position where the side to move wins at once is adjudicated before it is
+            // searched (Tier-1 pre-check of the self-play loop, src/bin/self_play.rs:241-283, at depth 1)
+            else if (c.tier1_light && cbchess::light_gates_hd(nb, tmp, n_legal, c.koth != 0) == 1) result = white_moved ? -1 : 1;
+        }
+    }
+    return result;
 }
 
 // Worker pool for the per-step tree work.  Dedicated spinning threads: a step's phases last
@@ -311,6 +446,41 @@ double now_s() {
 
 }  // namespace
 
+namespace {
+
+SearchCfg search_cfg(const cb_selfplay_config* cfg) {
+    SearchCfg c;
+    c.sims = cfg->sims_per_move;
+    c.material_on = cfg->material_on;
+    c.qsearch = cfg->qsearch;
+    c.koth = cfg->koth;
+    c.tier1_light = cfg->tier1_light;
+    c.shuffle = cfg->shuffle_children;
+    c.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
+    c.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414;
+    c.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
+    return c;
+}
+
+// One move's search of the host driver with a caller-supplied evaluator.
+void search_with_callback(Game& g, const SearchCfg& sc, cb_eval_callback eval, void* user) {
+    std::atomic<long long> terminal_hits(0);
+    float priors[kMaxMoves];
+    const Node& root = g.nodes[0];
+    if (root.state == 2) return;
+    while (g.sims_done < sc.sims) {
+        select_leaf(g, sc, terminal_hits);
+        if (g.nodes[0].state == 2) return;   // the root itself is mate / stalemate: nothing to search
+        if (g.wants_eval) {
+            float v = 0.0f;
+            eval(user, &g.leaf_board, g.leaf_moves, g.leaf_idx, g.leaf_n, g.leaf_q, sc.material_on, priors, &v);
+            expand_and_backup(g, sc, priors, v);
+        }
+    }
+}
+
+}  // namespace
+
 extern "C" {
 
 int cb_chess_startpos(cb_board* out) {
@@ -355,15 +525,70 @@ int cb_light_gates(const cb_board* boards, int n, int koth, int8_t* out) {
     return 0;
 }
 
+int cb_debug_host_search(const cb_selfplay_config* cfg, const cb_board* boards, int n, cb_eval_callback eval, void* user,
+                         uint16_t* moves, uint32_t* visits, double* value_sums, int32_t* counts, uint32_t* root_visits) {
+    if (!cfg || !boards || n < 0 || !eval || !counts) return CB_EINVAL;
+    const SearchCfg sc = search_cfg(cfg);
+    for (int i = 0; i < n; ++i) {
+        Game g;
+        g.reset(cfg->seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * (uint64_t)(i + 1), &boards[i]);
+        search_with_callback(g, sc, eval, user);
+        const Node& root = g.nodes[0];
+        const int nc = root.state == 1 ? root.n_children : 0;
+        counts[i] = nc;
+        if (root_visits) root_visits[i] = root.visits;
+        for (int c = 0; c < nc; ++c) {
+            const Node& ch = g.nodes[root.first_child + c];
+            if (moves) moves[(size_t)i * kMaxMoves + c] = ch.move;
+            if (visits) visits[(size_t)i * kMaxMoves + c] = ch.visits;
+            if (value_sums) value_sums[(size_t)i * kMaxMoves + c] = ch.value_sum;
+        }
+    }
+    return CB_OK;
+}
+
+int cb_debug_host_game(const cb_selfplay_config* cfg, const cb_board* start, uint64_t seed, cb_eval_callback eval, void* user,
+                       cb_board* sample_boards, uint16_t* sample_idx, float* sample_prob, int32_t* sample_n, float* sample_material,
+                       int max_samples, int* result_white, int* plies) {
+    if (!cfg || !start || !eval) return CB_EINVAL;
+    const SearchCfg sc = search_cfg(cfg);
+    Game g;
+    g.reset(seed, start);
+    int result = 2;
+    Move tmp[kMaxMoves];
+    // the game loop's own pre-check of the start position (src/bin/self_play.rs:241-283 at depth 1)
+    const int n0 = gen_legal(g.root_board, tmp);
+    if (n0 == 0) result = in_check(g.root_board, g.root_board.w_to_move ? 0 : 1) ? (g.root_board.w_to_move ? -1 : 1) : 0;
+    else if (sc.tier1_light && cbchess::light_gates_hd(g.root_board, tmp, n0, sc.koth != 0) == 1) result = g.root_board.w_to_move ? 1 : -1;
+    while (result == 2) {
+        search_with_callback(g, sc, eval, user);
+        result = play_move(g, sc);
+    }
+    const int ns = (int)g.samples.size();
+    // a game that was adjudicated at its start has no samples; otherwise the sample of the last move was recorded
+    for (int i = 0; i < ns && i < max_samples; ++i) {
+        const Sample& s = g.samples[i];
+        if (sample_boards) sample_boards[i] = s.board;
+        if (sample_n) sample_n[i] = (int32_t)s.policy.size();
+        if (sample_material) sample_material[i] = s.material;
+        for (size_t k2 = 0; k2 < s.policy.size(); ++k2) {
+            if (sample_idx) sample_idx[(size_t)i * kMaxMoves + k2] = s.policy[k2].first;
+            if (sample_prob) sample_prob[(size_t)i * kMaxMoves + k2] = s.policy[k2].second;
+        }
+    }
+    if (result_white) *result_white = result;
+    if (plies) *plies = g.ply;
+    return ns;
+}
+
 int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out) {
     if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
     if (!cb_is_available(h)) return CB_ESTATE;
     if (cfg->pipeline == 3 || cfg->pipeline == 4) return cb_selfplay_device(h, cfg, out);
     memset(out, 0, sizeof(*out));
+    if (cfg->mock_eval) return CB_EINVAL;   // the mock evaluator exists on the device path only
     const int G = cfg->games;
-    const int max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
-    const float c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414f;
-    const double explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
+    const SearchCfg sc = search_cfg(cfg);
     // the workers spin between phases: keep two cores for the driving thread and the CUDA runtime
     int nthreads = cfg->threads > 0 ? cfg->threads : (int)std::thread::hardware_concurrency() - 2;
     if (nthreads < 1) nthreads = 1;
@@ -400,73 +625,14 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
     };
 
     // After sims_per_move simulations: record the sample, choose and play a move, detect game end.
-    auto play_move = [&](Game& g, int gi) {
+    auto play = [&](Game& g, int gi) {
         Node& root = g.nodes[0];
         if (root.state != 1 || root.n_children == 0) {  // cannot happen for a live game; restart defensively
             g.reset(g.rng.next());
             return;
         }
-        uint32_t total = 0;
-        for (uint32_t i = 0; i < root.n_children; ++i) total += g.nodes[root.first_child + i].visits;
-        Sample s;
-        s.board = g.root_board;
-        s.material = cfg->material_on ? material_q(g.root_board, cfg->qsearch) : 0.0f;
-        if (total > 0)
-            for (uint32_t i = 0; i < root.n_children; ++i) {
-                const Node& ch = g.nodes[root.first_child + i];
-                s.policy.emplace_back((uint16_t)policy_index(ch.move, g.root_board.w_to_move != 0),
-                                      (float)ch.visits / (float)total);
-            }
-        g.samples.push_back(std::move(s));
-        // proportional to (visits-1) with probability explore_base^(move-1), else greedy
-        const int move_number = g.ply / 2 + 1;
-        uint32_t pick = root.first_child;
-        uint32_t best_v = 0;
-        for (uint32_t i = 0; i < root.n_children; ++i)
-            if (g.nodes[root.first_child + i].visits > best_v) { best_v = g.nodes[root.first_child + i].visits; pick = root.first_child + i; }
-        if (g.rng.uniform() < pow(explore_base, move_number - 1)) {
-            uint32_t tot1 = 0;
-            for (uint32_t i = 0; i < root.n_children; ++i) {
-                const uint32_t v = g.nodes[root.first_child + i].visits;
-                tot1 += v > 0 ? v - 1 : 0;
-            }
-            if (tot1 > 0) {
-                const uint32_t thr = (uint32_t)(g.rng.next() % tot1);
-                uint32_t cum = 0;
-                for (uint32_t i = 0; i < root.n_children; ++i) {
-                    const uint32_t v = g.nodes[root.first_child + i].visits;
-                    cum += v > 0 ? v - 1 : 0;
-                    if (cum > thr) { pick = root.first_child + i; break; }
-                }
-            }
-        }
-        const Move mv = g.nodes[pick].move;
-        const bool white_moved = g.root_board.w_to_move != 0;
-        cb_board nb;
-        make_move(g.root_board, mv, &nb);
-        if (nb.halfmove == 0) g.history.clear();
-        g.root_board = nb;
-        g.history.push_back(position_key(nb));
-        g.ply++;
-        g.sims_done = 0;
+        const int result = play_move(g, sc);
         moves_played++;
-        reroot(g, pick);
-        // game end (src/bin/self_play.rs:358-388)
-        int result = 2;  // 2 = continue
-        Move tmp[kMaxMoves];
-        if (cfg->koth && (nb.pieces[(white_moved ? 0 : 6) + KING] & kKothCenter)) result = white_moved ? 1 : -1;
-        else {
-            const int n_legal = gen_legal(nb, tmp);
-            if (n_legal == 0) result = in_check(nb, nb.w_to_move ? 0 : 1) ? (white_moved ? 1 : -1) : 0;
-            else {
-                int reps = 0;
-                for (uint64_t k : g.history) reps += (k == g.history.back());
-                if (reps >= 3 || nb.halfmove >= 100 || g.ply > max_plies) result = 0;
-                // the game goes on: a position where the side to move wins at once is adjudicated before it is
-                // searched (Tier-1 pre-check of the self-play loop, src/bin/self_play.rs:241-283, at depth 1)
-                else if (cfg->tier1_light && cbchess::light_gates_hd(nb, tmp, n_legal, cfg->koth != 0) == 1) result = white_moved ? -1 : 1;
-            }
-        }
         if (result != 2) {
             finish_game(g, result);
             g.reset(g.rng.next() ^ ((uint64_t)gi << 32));
@@ -489,7 +655,7 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
         EvalJob& j = jobs[hf];
         const int g0 = hb[hf], g1 = hb[hf + 1];
         pool.run(g0, g1, [&](int b, int e) {
-            for (int i = b; i < e; ++i) select_leaf(games[i], c_puct, terminal_hits, cfg->tier1_light != 0, cfg->koth != 0);
+            for (int i = b; i < e; ++i) select_leaf(games[i], sc, terminal_hits);
         });
         int nb = 0;
         uint32_t off = 0;
@@ -497,7 +663,7 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
             Game& g = games[i];
             if (!g.wants_eval) continue;
             j.boards[nb] = g.leaf_board;
-            j.q[nb] = cfg->material_on ? material_q(g.leaf_board, cfg->qsearch) : 0.0f;
+            j.q[nb] = g.leaf_q;
             j.move_off[nb] = off;
             memcpy(&j.move_idx[off], g.leaf_idx, sizeof(uint16_t) * g.leaf_n);
             off += (uint32_t)g.leaf_n;
@@ -516,9 +682,9 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
                 Game& g = games[i];
                 if (g.wants_eval) {
                     const int s = j.game_slot[i - g0];
-                    expand_and_backup(g, &j.priors[j.move_off[s]], j.v_final[s]);
+                    expand_and_backup(g, sc, &j.priors[j.move_off[s]], j.v_final[s]);
                 }
-                if (g.sims_done >= cfg->sims_per_move) play_move(g, i);
+                if (g.sims_done >= cfg->sims_per_move) play(g, i);
             }
         });
         sims += g1 - g0;

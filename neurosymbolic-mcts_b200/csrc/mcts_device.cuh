@@ -1,18 +1,26 @@
 // mcts_device.cuh — the tree operations of the self-play pool ON THE DEVICE: one warp
-// per game walks its tree with PUCT, generates the leaf's legal moves and writes the leaf straight into the
+// per game walks its tree, generates the leaf's legal moves and writes the leaf straight into the
 // evaluator's input block; after the forward kernel a second kernel expands the leaf with the priors,
 // backs the value up and — when the simulation budget of the move is spent — picks and plays the move,
 // re-roots the tree and detects the end of the game.  No host work and no PCIe traffic per simulation.
 //
-// Semantics are those of the host driver (host/selfplay.cpp), statement for statement, which follow
-//   selection        src/mcts/selection.rs:65-73 (every root child once), :254-273 (PUCT, sqrt(max(N,1)), Q = 0 unvisited)
-//   expansion        src/mcts/selection.rs:82-104, terminal test src/mcts/node.rs:162-177
-//   backup           src/mcts/node.rs:403-424 (sign flips every ply)
-//   move choice      src/bin/self_play.rs:300-356 (proportional to visits-1 with probability 0.8^(move-1), else greedy)
+// Semantics are the reference's search, statement for statement (the host driver host/selfplay.cpp is the scalar twin,
+// oracle/mcts.c the independent restatement the tests compare both with):
+//   child order      generation order, src/move_generation.rs:287-328 (host/chess_rules.hpp)
+//   selection        src/mcts/selection.rs:37-63,107-149 (tactical phase: every capture / promotion child once, MVV-LVA
+//                    order, in every mode), :65-73 (every root child once), :152-273 (PUCT in f64, sqrt(max(N,1)), Q = 0
+//                    unvisited, first maximum wins; proven losses skipped, longest delay when every move loses)
+//   priors           a fresh root is expanded without an evaluation and asks for its policy before its first PUCT step
+//                    (:281-345): here the root of a new game is evaluated once for its priors only (no backup)
+//   expansion        src/mcts/tactical_mcts.rs:813-836; terminal test src/mcts/node.rs:162-177 (made when the child is first
+//                    reached instead of at creation: same values, same visit counts)
+//   backup           src/mcts/node.rs:403-424 (f64 sums, sign flips every ply)
+//   early stop       src/mcts/tactical_mcts.rs:524-560 (with the gates on)
+//   move choice      src/bin/self_play.rs:300-356,628-650 (proportional to visits-1 with probability 0.8^(move-1), else the
+//                    LAST most-visited child)
 //   tree reuse / game end  src/bin/self_play.rs:358-388
-// and the chess rules are the same inline code (host/chess_rules.hpp).  All floating-point steps use
-// explicitly rounded single operations (no FMA contraction), so for identical evaluator outputs the
-// device trees are bit-identical to the host driver's (tests/test_gpu_parity.py).
+// All floating-point steps are explicitly rounded single operations (no FMA contraction), so for identical evaluator
+// outputs the device trees are bit-identical to the host driver's and the oracle's (tests/test_gpu_parity.py).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,17 +34,23 @@ namespace cb {
 using cbchess::Move;
 
 struct MNode {
+    double value_sum;      // total_value (src/mcts/node.rs:63): from the point of view of the player who moved INTO this node
     uint32_t first_child;
     uint32_t visits;
-    float value_sum;   // from the point of view of the player who moved INTO this node
-    float prior;
+    float prior;           // move_priorities[move] of the parent (f32 from the evaluator; the reference widens it to f64)
     uint16_t n_children;
     uint16_t move;
-    uint8_t state;     // 0 unexpanded, 1 expanded, 2 terminal
-    int8_t term_value; // value for the side to move at a terminal node (-1 mated, 0 stalemate)
+    uint8_t state;         // 0 unexpanded, 1 expanded, 2 terminal or resolved by a gate
+    int8_t term_value;     // terminal_or_mate_value for the side to move at a state-2 node (-1, 0, +1)
+    uint8_t n_tact;        // as a parent: children that come from the capture list (the tactical phase's candidates)
+    uint8_t t_done;        // as a parent: how many of them have been visited (tactical_moves_explored)
+    uint8_t trank;         // as a child: place in the parent's tactical order (MVV-LVA, stable); 0xFF = not tactical
+    uint8_t term_dist;     // terminal_distance of a state-2 node
     uint16_t pad;
 };
-static_assert(sizeof(MNode) == 24, "node layout");
+static_assert(sizeof(MNode) == 32, "node layout");
+
+constexpr uint8_t kMateIn1Dist = (uint8_t)1000001u;   // `mate_result.0.unsigned_abs() as u8` for 1_000_000 + 1 (tactical_mcts.rs:701)
 
 constexpr int kMctsHist = 128;      // position keys since the last irreversible move (halfmove clock <= 100)
 constexpr int kMctsMaxDepth = 512;  // longest root-to-leaf path kept
@@ -53,8 +67,11 @@ struct MctsParams {
                                   // OTHER pool: the last warp to finish (wrapping counter) waits for that kernel before it
                                   // exits, so that stream order after this launch still implies the forward's completion —
                                   // the other warps leave at once and free their SM for the blocks still queued
-    float c_puct;
+    double c_puct;                // 1.414 (f64 like the reference's exploration_constant)
     double explore_base;
+    int shuffle;                  // permute every expansion's child order (see cb_selfplay_config.shuffle_children)
+    int search_only;              // debug search (cb_debug_device_search): a game stops once its budget is spent, no move is played
+    int mock_eval;                // the evaluator is mcts_mock_eval_kernel (InferenceServer::new_mock_biased), not the network
     uint32_t node_cap;              // nodes per arena
     // per-game state
     cb_board* root;                 // [G]
@@ -72,6 +89,8 @@ struct MctsParams {
     int* path_n;                    // [G]
     uint8_t* wants_eval;            // [G]
     uint16_t* leaf_moves;           // [G][CB_MAX_MOVES]
+    uint8_t* leaf_trank;            // [G][CB_MAX_MOVES] tactical rank of every leaf move (0xFF: not tactical)
+    uint8_t* leaf_ntact;            // [G]
     // evaluator input / output block (slot = game)
     cb_board* eval_boards;          // [G]
     float* eval_q;                  // [G]
@@ -81,6 +100,7 @@ struct MctsParams {
     const float* v_final;           // [G]
     unsigned long long* stats;      // [MS_COUNT]
     uint64_t seed;
+    const cb_board* start_boards;   // nullable: the position a game in slot g starts from (debug search); else the start position
     // optional training-sample log (nullptr: off): ring of kSampleSlotBytes records appended in program order
     // per game — one per move played (board, material, visit counts of the root's children) and one per
     // finished game (the result); the host drains it between graph replays
@@ -115,8 +135,10 @@ __device__ __forceinline__ uint64_t rng_next(uint64_t& s) {
 __device__ __forceinline__ double rng_uniform(uint64_t& s) { return (double)(rng_next(s) >> 11) * (1.0 / 9007199254740992.0); }
 
 // dM of the position in `b` (shared memory; overwritten when the exchange line runs) in pawn units.  All lanes.
-__device__ __forceinline__ float mcts_material_q(const MctsParams& p, cb_board& b, cb_board& scratch, uint8_t* mailbox, int lane) {
-    if (!p.material_on) return 0.0f;
+// `always`: the material scalar of a training sample is computed whatever material_on says (src/bin/self_play.rs:315-329).
+__device__ __forceinline__ float mcts_material_q(const MctsParams& p, cb_board& b, cb_board& scratch, uint8_t* mailbox, int lane,
+                                                 bool always = false) {
+    if (!p.material_on && !always) return 0.0f;
     const int cp = p.qsearch == 1 ? cbchess::principal_exchange_cp_warp(b, scratch, mailbox, lane) : cbchess::pesto_cp_warp(b, mailbox, lane);
     return __fdiv_rn((float)cp, 100.0f);
 }
@@ -125,6 +147,8 @@ __device__ __forceinline__ float mcts_material_q(const MctsParams& p, cb_board& 
 __device__ __forceinline__ void mcts_reset_game(const MctsParams& p, int g, uint64_t seed) {
     cb_board b;
     memset(&b, 0, sizeof(b));
+    if (p.start_boards) b = p.start_boards[g];
+    else {
     const uint64_t back[6] = {0, 0x42, 0x24, 0x81, 0x08, 0x10};
     b.pieces[cbchess::PAWN] = 0xFF00ull;
     b.pieces[6 + cbchess::PAWN] = 0xFFull << 48;
@@ -137,6 +161,7 @@ __device__ __forceinline__ void mcts_reset_game(const MctsParams& p, int g, uint
     b.w_to_move = 1;
     b.en_passant = 0xFF;
     b.castling = cbchess::WK | cbchess::WQ | cbchess::BK | cbchess::BQ;
+    }
     p.root[g] = b;
     p.arena[g] = 0;
     MNode z;
@@ -166,29 +191,72 @@ __global__ void mcts_init_kernel(const MctsParams p) {
 
 // Value backed up along the stored path, sign flipping every ply (src/mcts/node.rs:403-424).  The updates of
 // the path's nodes are independent, so the lanes take one node each (their memory round trips overlap); the
-// arithmetic per node is the host's: value_sum += +-val, visits += 1.  All lanes call this.
-__device__ __forceinline__ void mcts_backup(MNode* nodes, const uint32_t* path, int n, float val, int lane) {
+// arithmetic per node is the reference's: total_value += +-value (f64), visits += 1.  All lanes call this.
+__device__ __forceinline__ void mcts_backup(MNode* nodes, const uint32_t* path, int n, double val, int lane) {
     for (int i = n - 1 - lane; i >= 0; i -= 32) {
         // node at path index i gets val negated (n - i) times
-        const float v = ((n - i) & 1) ? -val : val;
+        const double v = ((n - i) & 1) ? -val : val;
         MNode& nd = nodes[path[i]];
-        nd.value_sum = __fadd_rn(nd.value_sum, v);
+        nd.value_sum = __dadd_rn(nd.value_sum, v);
         nd.visits++;
     }
     __syncwarp();
 }
 
+// should_early_terminate (src/mcts/tactical_mcts.rs:524-560; only with the gates on): a root child that is a decided
+// win, a visited child with Q > 0.99 once every child is visited, or every child a proven loss.  All lanes; uniform.
+__device__ __forceinline__ bool mcts_early_terminate(const MNode* nodes, int lane) {
+    const MNode root = nodes[0];
+    if (root.state != 1) return false;
+    bool win1 = false, forced = false, unvisited = false, not_losing = false;
+    for (uint32_t i = lane; i < root.n_children; i += 32) {
+        const MNode ch = nodes[root.first_child + i];
+        const bool term = ch.state == 2;
+        win1 |= term && ch.term_value < 0;
+        forced |= ch.visits > 0 && __ddiv_rn(ch.value_sum, (double)ch.visits) > 0.99;
+        unvisited |= ch.visits == 0;
+        not_losing |= !(term && ch.term_value > 0);
+    }
+    win1 = __any_sync(0xffffffffu, win1);
+    forced = __any_sync(0xffffffffu, forced);
+    unvisited = __any_sync(0xffffffffu, unvisited);
+    not_losing = __any_sync(0xffffffffu, not_losing);
+    if (win1) return true;
+    if (forced && !unvisited) return true;
+    return !unvisited && !not_losing && root.n_children > 0;
+}
+
+// A simulation is complete: count it, and with the gates on test the early stop (the move is then played at once).
+__device__ __forceinline__ void mcts_sim_done(const MctsParams& p, const MNode* nodes, int g, int lane) {
+    __syncwarp();
+    const bool stop = p.tier1_light && mcts_early_terminate(nodes, lane);
+    if (lane == 0) p.sims_done[g] = stop ? p.sims_per_move : p.sims_done[g] + 1;
+    __syncwarp();
+}
+
 // cbchess::gen_pseudo with one own piece per lane (a side has at most 16): the same list in the same order.
-// Lane k takes the k-th piece in generation order (pawns, knights, bishops, rooks, queens, king; ascending squares),
-// counts its captures / promotions and its quiet moves, two warp scans give every lane its place in the capture
-// block and in the quiet block, and the castling moves (five squares tested for attack on five lanes) close the list.
-__device__ __forceinline__ int gen_pseudo_warp(const cb_board& b, Move* out, int lane) {
+// Lane k takes the k-th piece in generation order (pawns, knights, bishops, rooks, queens, king; ascending squares) and
+// counts its captures, its promotions and its quiet moves; three warp scans give every lane its place in the capture
+// block, the promotion block and the quiet block.  The castling moves (five squares tested for attack on five lanes)
+// open the king's quiet moves.  Returns the list length; *n_caps = length of the capture list (captures + promotions).
+__device__ __forceinline__ int gen_pseudo_warp(const cb_board& b, Move* out, int lane, int* n_caps = nullptr) {
     using namespace cbchess;
     const Tables& T = tables();
     const int us = b.w_to_move ? 0 : 1, them = 1 - us;
     const uint64_t opp = b.occ[them], occ = b.occ[0] | b.occ[1];
     const uint64_t* pc = &b.pieces[us * 6];
-    const int fwd = us == 0 ? 8 : -8, promo_rank = us == 0 ? 7 : 0, start_rank = us == 0 ? 1 : 6;
+    const int fwd = us == 0 ? 8 : -8, promo_from_rank = us == 0 ? 6 : 1, start_rank = us == 0 ? 1 : 6;
+    // castling first: uniform, needed by the king's lane count
+    bool castle_k = false, castle_q = false;
+    const int ksq = us == 0 ? 4 : 60, ks = us == 0 ? WK : BK, qs = us == 0 ? WQ : BQ;
+    if ((pc[KING] >> ksq & 1) && (b.castling & (ks | qs))) {          // uniform
+        const bool att = lane < 5 && attacked(b, ksq - 2 + lane, them);
+        const uint32_t am = __ballot_sync(0xffffffffu, att);           // bit i: square ksq - 2 + i is attacked
+        if (!(am >> 2 & 1)) {
+            castle_k = (b.castling & ks) && (pc[ROOK] >> (ksq + 3) & 1) && !(occ & (3ull << (ksq + 1))) && !(am >> 3 & 3);
+            castle_q = (b.castling & qs) && (pc[ROOK] >> (ksq - 4) & 1) && !(occ & (7ull << (ksq - 3))) && !(am & 3);
+        }
+    }
     int pt = -1, from = 0;
     {
         int k = lane;
@@ -201,73 +269,87 @@ __device__ __forceinline__ int gen_pseudo_warp(const cb_board& b, Move* out, int
             }
         }
     }
-    uint64_t caps = 0, quiets = 0;
-    int ncap = 0, nquiet = 0;
-    bool ep = false, promo_push = false, one_ok = false, two_ok = false;
+    uint64_t caps = 0, quiets = 0, caps2 = 0, quiets2 = 0;   // (queen: rook set, then bishop set)
+    int ncap = 0, nprom = 0, nquiet = 0;
+    bool promo = false, one_ok = false, two_ok = false;
     if (pt == PAWN) {
         const int one = from + fwd;
-        const bool promo = (one >> 3) == promo_rank, one_empty = !(occ >> one & 1);
-        caps = T.pawn[us][from] & opp;
-        ep = b.en_passant != 0xFF && (T.pawn[us][from] >> b.en_passant & 1);
-        promo_push = promo && one_empty;
-        ncap = __popcll(caps) * (promo ? 4 : 1) + (ep ? 1 : 0) + (promo_push ? 4 : 0);
-        one_ok = !promo && one_empty;
-        two_ok = one_ok && (from >> 3) == start_rank && !(occ >> (one + fwd) & 1);
-        nquiet = (one_ok ? 1 : 0) + (two_ok ? 1 : 0);
+        promo = (from >> 3) == promo_from_rank;
+        const bool one_empty = !(occ >> one & 1);
+        caps = T.pawn[us][from] & (opp | (b.en_passant != 0xFF ? 1ull << b.en_passant : 0ull));
+        if (promo) nprom = 4 * (__popcll(caps) + (one_empty ? 1 : 0));
+        else {
+            ncap = __popcll(caps);
+            one_ok = one_empty;
+            two_ok = one_ok && (from >> 3) == start_rank && !(occ >> (one + fwd) & 1);
+            nquiet = (one_ok ? 1 : 0) + (two_ok ? 1 : 0);
+        }
+    } else if (pt == QUEEN) {
+        const uint64_t ra = rook_att(from, occ), ba = bishop_att(from, occ);
+        caps = ra & opp; caps2 = ba & opp;
+        quiets = ra & ~occ; quiets2 = ba & ~occ;
+        ncap = __popcll(caps) + __popcll(caps2);
+        nquiet = __popcll(quiets) + __popcll(quiets2);
     } else if (pt >= 0) {
         const uint64_t att = pt == KNIGHT ? T.knight[from] : pt == KING ? T.king[from] : pt == BISHOP ? bishop_att(from, occ)
-                           : pt == ROOK ? rook_att(from, occ) : (rook_att(from, occ) | bishop_att(from, occ));
+                                                                                                      : rook_att(from, occ);
         caps = att & opp;
         quiets = att & ~occ;
         ncap = __popcll(caps);
-        nquiet = __popcll(quiets);
+        nquiet = __popcll(quiets) + (pt == KING ? (castle_k ? 1 : 0) + (castle_q ? 1 : 0) : 0);
     }
-    int cap_end = ncap, quiet_end = nquiet;   // inclusive scans over the lanes
+    int cap_end = ncap, prom_end = nprom, quiet_end = nquiet;   // inclusive scans over the lanes
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, cap_end, d), q = __shfl_up_sync(0xffffffffu, quiet_end, d);
-        if (lane >= d) { cap_end += a; quiet_end += q; }
+        const int a = __shfl_up_sync(0xffffffffu, cap_end, d), pr = __shfl_up_sync(0xffffffffu, prom_end, d),
+                  q = __shfl_up_sync(0xffffffffu, quiet_end, d);
+        if (lane >= d) { cap_end += a; prom_end += pr; quiet_end += q; }
     }
-    const int total_caps = __shfl_sync(0xffffffffu, cap_end, 31), total_quiets = __shfl_sync(0xffffffffu, quiet_end, 31);
-    int n = cap_end - ncap;
+    const int total_caps = __shfl_sync(0xffffffffu, cap_end, 31), total_proms = __shfl_sync(0xffffffffu, prom_end, 31),
+              total_quiets = __shfl_sync(0xffffffffu, quiet_end, 31);
+    int n = cap_end - ncap;                                        // this lane's first capture slot
+    int nq = total_caps + total_proms + quiet_end - nquiet;        // ... first quiet slot
     if (pt == PAWN) {
-        for (uint64_t t = caps; t; t &= t - 1) n = add_pawn(out, n, from, lsb(t), promo_rank);
-        if (ep) out[n++] = make_mv(from, b.en_passant, 0);
-        if (promo_push) n = add_pawn(out, n, from, from + fwd, promo_rank);
-        n = total_caps + quiet_end - nquiet;
-        if (one_ok) out[n++] = make_mv(from, from + fwd, 0);
-        if (two_ok) out[n++] = make_mv(from, from + 2 * fwd, 0);
+        if (promo) {
+            int np = total_caps + prom_end - nprom;
+            const int one = from + fwd;
+            for (uint64_t t = caps; t; t &= t - 1) np = add_pawn(out, np, from, lsb(t), one >> 3);
+            if (!(occ >> one & 1)) np = add_pawn(out, np, from, one, one >> 3);
+        } else {
+            for (uint64_t t = caps; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
+            if (two_ok) out[nq++] = make_mv(from, from + 2 * fwd, 0);
+            if (one_ok) out[nq++] = make_mv(from, from + fwd, 0);
+        }
+    } else if (pt == KNIGHT || pt == KING) {
+        if (pt == KING) {
+            if (castle_k) out[nq++] = make_mv(ksq, ksq + 2, 0);
+            if (castle_q) out[nq++] = make_mv(ksq, ksq - 2, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int d = pt == KNIGHT ? knight_delta(i) : king_delta(i);
+            if (step_targets_bit(caps, from, d)) out[n++] = make_mv(from, from + d, 0);
+            else if (step_targets_bit(quiets, from, d)) out[nq++] = make_mv(from, from + d, 0);
+        }
     } else if (pt >= 0) {
         for (uint64_t t = caps; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
-        n = total_caps + quiet_end - nquiet;
-        for (uint64_t t = quiets; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
+        for (uint64_t t = caps2; t; t &= t - 1) out[n++] = make_mv(from, lsb(t), 0);
+        for (uint64_t t = quiets; t; t &= t - 1) out[nq++] = make_mv(from, lsb(t), 0);
+        for (uint64_t t = quiets2; t; t &= t - 1) out[nq++] = make_mv(from, lsb(t), 0);
     }
-    int total = total_caps + total_quiets;
-    const int ksq = us == 0 ? 4 : 60, ks = us == 0 ? WK : BK, qs = us == 0 ? WQ : BQ;
-    if ((pc[KING] >> ksq & 1) && (b.castling & (ks | qs))) {          // uniform
-        const bool att = lane < 5 && attacked(b, ksq - 2 + lane, them);
-        const uint32_t am = __ballot_sync(0xffffffffu, att);           // bit i: square ksq - 2 + i is attacked
-        if (!(am >> 2 & 1)) {
-            if ((b.castling & ks) && (pc[ROOK] >> (ksq + 3) & 1) && !(occ & (3ull << (ksq + 1))) && !(am >> 3 & 3)) {
-                if (lane == 0) out[total] = make_mv(ksq, ksq + 2, 0);
-                ++total;
-            }
-            if ((b.castling & qs) && (pc[ROOK] >> (ksq - 4) & 1) && !(occ & (7ull << (ksq - 3))) && !(am & 3)) {
-                if (lane == 0) out[total] = make_mv(ksq, ksq - 2, 0);
-                ++total;
-            }
-        }
-    }
+    if (n_caps) *n_caps = total_caps + total_proms;
     __syncwarp();
-    return total;
+    return total_caps + total_proms + total_quiets;
 }
 
 // Legal moves of `board` in generation order: the warp generates the pseudo-legal list, the lanes test
-// legality in parallel, a ballot compacts in order.  Returns the count (uniform); moves in `legal`.
-__device__ __forceinline__ int mcts_gen_legal_warp(const cb_board& board, Move* pseudo, Move* legal, int lane) {
-    const int np = gen_pseudo_warp(board, pseudo, lane);
+// legality in parallel, a ballot compacts in order.  Returns the count (uniform); moves in `legal`; *n_tactical = how
+// many of them come from the capture list (the candidates of the tactical phase).
+__device__ __forceinline__ int mcts_gen_legal_warp(const cb_board& board, Move* pseudo, Move* legal, int lane, int* n_tactical = nullptr) {
+    int ncap = 0;
+    const int np = gen_pseudo_warp(board, pseudo, lane, &ncap);
     const int us = board.w_to_move ? 0 : 1;
-    int n = 0;
+    int n = 0, nt = 0;
     for (int base = 0; base < np; base += 32) {
         const int i = base + lane;
         bool ok = false;
@@ -281,7 +363,9 @@ __device__ __forceinline__ int mcts_gen_legal_warp(const cb_board& board, Move* 
         const uint32_t mask = __ballot_sync(0xffffffffu, ok);
         if (ok) legal[n + __popc(mask & ((1u << lane) - 1u))] = m;
         n += __popc(mask);
+        nt += __popc(__ballot_sync(0xffffffffu, ok && i < ncap));
     }
+    if (n_tactical) *n_tactical = nt;
     __syncwarp();
     return n;
 }
@@ -294,20 +378,25 @@ __device__ __forceinline__ int mcts_gen_legal_warp(const cb_board& board, Move* 
 //    promotions take the exact test (make the move, test the king).
 //  * Every checking move is then examined by the whole warp: the king's steps on eight lanes first (the usual way
 //    out), and only when none is legal the full reply list (warp generator, one reply per lane).
+// *dist (nullable) = terminal_distance of a hit (src/mcts/tactical_mcts.rs:624,641,701): 0 king already on the hill,
+// 1 hill in one, kMateIn1Dist for the mate.
 __device__ __forceinline__ int light_gates_warp(const cb_board& b, const Move* legal, int n, bool koth, cb_board& nb, Move* pseudo,
-                                                int lane) {
+                                                int lane, int* dist = nullptr) {
     using namespace cbchess;
     const Tables& T = tables();
     const int us = b.w_to_move ? 0 : 1, them = 1 - us;
     if (koth) {
+        if (dist) *dist = 0;
         if (b.pieces[them * 6 + KING] & kKothCenter) return -1;
         const uint64_t k = b.pieces[us * 6 + KING];
         if (k & kKothCenter) return 1;
+        if (dist) *dist = 1;
         const int ks = k ? lsb(k) : -1;
         bool step = false;
         for (int i = lane; i < n; i += 32) step |= mv_from(legal[i]) == ks && (kKothCenter >> mv_to(legal[i]) & 1);
         if (__any_sync(0xffffffffu, step)) return 1;
     }
+    if (dist) *dist = kMateIn1Dist;
     const uint64_t ek = b.pieces[them * 6 + KING];
     if (!ek) return 2;
     const int eks = lsb(ek);
@@ -367,11 +456,8 @@ __device__ __forceinline__ int light_gates_warp(const cb_board& b, const Move* l
     return 2;
 }
 
-// Phase A of a simulation for every game: walk down with PUCT, stop at an unexpanded or terminal node.
-// best still equals first_child because no child was selected by the scan (n_children == 0 cannot reach here; NaN
-// scores could): fall back to loading the node.
-__device__ __forceinline__ bool bi_invalid(uint32_t best, const MNode& n) { return n.n_children == 0 || best < n.first_child; }
-
+// Phase A of a simulation for every game: walk down (tactical phase, root force-visit, PUCT), stop at an unexpanded or
+// decided node.
 // Per-warp shared scratch of the tree kernels.
 struct MctsSmem {
     cb_board board[kMctsWarps];
@@ -381,10 +467,23 @@ struct MctsSmem {
     uint8_t mailbox[kMctsWarps][64];   // piece codes of the position under the exchange line
 };
 
+// The part of a child node the walk needs, packed for one round of shuffles.
+struct MChildLite {
+    uint32_t first_child, visits, pk /* n_children | move << 16 */, st /* state | term_value << 8 | n_tact << 16 | t_done << 24 */;
+};
+__device__ __forceinline__ MChildLite lite_of(const MNode& n) {
+    MChildLite l;
+    l.first_child = n.first_child;
+    l.visits = n.visits;
+    l.pk = (uint32_t)n.n_children | ((uint32_t)n.move << 16);
+    l.st = (uint32_t)n.state | ((uint32_t)(uint8_t)n.term_value << 8) | ((uint32_t)n.n_tact << 16) | ((uint32_t)n.t_done << 24);
+    return l;
+}
+
 __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& sm, int g, int wl, int lane) {
     Move (&s_pseudo)[kMctsWarps][CB_MAX_MOVES] = sm.pseudo;
     Move (&s_legal)[kMctsWarps][CB_MAX_MOVES] = sm.legal;
-    if (p.match_mode && p.idle[g]) {
+    if ((p.match_mode || p.search_only) && p.idle[g]) {
         if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; }
         return;
     }
@@ -398,57 +497,88 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     if (lane == 0) path[0] = 0;
     // The node at the top of each level comes from the lane that scanned it as a child one level up (one
     // dependent memory round trip per level instead of two).
-    MNode n = nodes[0];
+    MChildLite n = lite_of(nodes[0]);
     for (;;) {
-        if (n.state != 1 || depth >= kMctsMaxDepth - 1) break;
-        uint32_t best = n.first_child;
-        bool forced = false;
-        MNode bch;                       // the best child seen by this lane
-        bch.first_child = 0; bch.visits = 0; bch.n_children = 0; bch.move = 0; bch.state = 0; bch.term_value = 0;
-        if (depth == 0) {   // every root child gets one visit first
-            for (uint32_t base = 0; base < n.n_children && !forced; base += 32) {
-                const uint32_t i = base + lane;
-                const bool z = i < n.n_children && nodes[n.first_child + i].visits == 0;
-                const uint32_t mask = __ballot_sync(0xffffffffu, z);
-                if (mask) { best = n.first_child + base + (__ffs(mask) - 1); forced = true; }
-            }
-        }
-        if (!forced) {
-            const float sq = sqrtf((float)(n.visits > 1 ? n.visits : 1));
-            float bu = -1e30f;
-            uint32_t bi = 0xFFFFFFFFu;
-            for (uint32_t i = lane; i < n.n_children; i += 32) {
+        const uint32_t n_children = n.pk & 0xFFFFu, n_state = n.st & 0xFFu, n_tact = (n.st >> 16) & 0xFFu, t_done = n.st >> 24;
+        if (n_state != 1 || depth >= kMctsMaxDepth - 1) break;
+        uint32_t bi = 0xFFFFFFFFu;       // index of the chosen child
+        MChildLite bch = {0, 0, 0, 0};   // ... as seen by the lane that scanned it
+        if (t_done < n_tact) {
+            // tactical phase (selection.rs:107-149): the next capture-list child in MVV-LVA order, whatever its statistics
+            for (uint32_t i = lane; i < n_children; i += 32) {
                 const MNode ch = nodes[n.first_child + i];
-                const float q = ch.visits ? __fdiv_rn(ch.value_sum, (float)ch.visits) : 0.0f;
-                const float u = __fadd_rn(q, __fdiv_rn(__fmul_rn(__fmul_rn(p.c_puct, ch.prior), sq), __fadd_rn(1.0f, (float)ch.visits)));
-                if (u > bu) { bu = u; bi = i; bch = ch; }
+                if (ch.trank == t_done) { bi = i; bch = lite_of(ch); }
             }
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                const float ou = __shfl_xor_sync(0xffffffffu, bu, d);
-                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, d);
-                if (ou > bu || (ou == bu && oi < bi)) { bu = ou; bi = oi; }
-            }
-            if (bi != 0xFFFFFFFFu) best = n.first_child + bi;
-        }
-        MNode nxt;
-        if (forced || bi_invalid(best, n)) {
-            nxt = nodes[best];
+            bi = __reduce_min_sync(0xffffffffu, bi);
+            if (lane == 0) nodes[cur].t_done = (uint8_t)(t_done + 1);
         } else {
-            const int owner = static_cast<int>((best - n.first_child) & 31u);   // child i was scanned by lane i & 31
-            nxt.first_child = __shfl_sync(0xffffffffu, bch.first_child, owner);
-            nxt.visits = __shfl_sync(0xffffffffu, bch.visits, owner);
-            const uint32_t pk = __shfl_sync(0xffffffffu, (uint32_t)bch.n_children | ((uint32_t)bch.move << 16), owner);
-            const uint32_t st = __shfl_sync(0xffffffffu, (uint32_t)bch.state | ((uint32_t)(uint8_t)bch.term_value << 8), owner);
-            nxt.n_children = (uint16_t)(pk & 0xFFFFu);
-            nxt.move = (uint16_t)(pk >> 16);
-            nxt.state = (uint8_t)(st & 0xFFu);
-            nxt.term_value = (int8_t)(st >> 8);
-            nxt.value_sum = 0.0f; nxt.prior = 0.0f; nxt.pad = 0;
+            bool forced = false;
+            if (depth == 0) {   // every root child gets one visit first (selection.rs:65-73)
+                for (uint32_t base = 0; base < n_children && !forced; base += 32) {
+                    const uint32_t i = base + lane;
+                    MNode ch;
+                    ch.visits = 1;
+                    if (i < n_children) ch = nodes[n.first_child + i];
+                    const uint32_t mask = __ballot_sync(0xffffffffu, i < n_children && ch.visits == 0);
+                    if (mask) {
+                        bi = base + (__ffs(mask) - 1);
+                        if (i == bi) bch = lite_of(ch);
+                        forced = true;
+                    }
+                }
+            }
+            if (!forced) {
+                // PUCT (selection.rs:152-273), f64: Q + c * P * sqrt(max(N, 1)) / (1 + n), first maximum; a child whose side
+                // to move has a decided win is skipped, and when every child is one the longest delay is taken
+                const double sq = sqrt((double)(n.visits > 1 ? n.visits : 1));
+                double bu = -INFINITY;
+                uint32_t li = 0xFFFFFFFFu;      // least-bad losing child of this lane
+                int ld = -1;
+                MChildLite lch = {0, 0, 0, 0};
+                for (uint32_t i = lane; i < n_children; i += 32) {
+                    const MNode ch = nodes[n.first_child + i];
+                    if (ch.state == 2 && ch.term_value > 0) {
+                        if ((int)ch.term_dist > ld) { ld = ch.term_dist; li = i; lch = lite_of(ch); }
+                        continue;
+                    }
+                    const double q = ch.visits ? __ddiv_rn(ch.value_sum, (double)ch.visits) : 0.0;
+                    const double u = __dadd_rn(q, __ddiv_rn(__dmul_rn(__dmul_rn(p.c_puct, (double)ch.prior), sq),
+                                                            __dadd_rn(1.0, (double)ch.visits)));
+                    if (u > bu) { bu = u; bi = i; bch = lite_of(ch); }
+                }
+                double wu = bu;
+                uint32_t wi = bi;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const double ou = __shfl_xor_sync(0xffffffffu, wu, d);
+                    const uint32_t oi = __shfl_xor_sync(0xffffffffu, wi, d);
+                    if (oi != 0xFFFFFFFFu && (wi == 0xFFFFFFFFu || ou > wu || (ou == wu && oi < wi))) { wu = ou; wi = oi; }
+                }
+                if (wi == 0xFFFFFFFFu) {   // every child is a proven loss: first child with the largest distance
+                    int wd = ld;
+                    wi = li;
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) {
+                        const int od = __shfl_xor_sync(0xffffffffu, wd, d);
+                        const uint32_t oi = __shfl_xor_sync(0xffffffffu, wi, d);
+                        if (oi != 0xFFFFFFFFu && (wi == 0xFFFFFFFFu || od > wd || (od == wd && oi < wi))) { wd = od; wi = oi; }
+                    }
+                    bch = lch;                 // (the lane that owns the winner holds it as its own best)
+                }
+                bi = wi;
+            }
         }
+        if (bi == 0xFFFFFFFFu) break;             // no child (cannot happen for an expanded node)
+        const uint32_t best = n.first_child + bi;
+        const int owner = static_cast<int>(bi & 31u);   // child i was scanned by lane i & 31
+        MChildLite nxt;
+        nxt.first_child = __shfl_sync(0xffffffffu, bch.first_child, owner);
+        nxt.visits = __shfl_sync(0xffffffffu, bch.visits, owner);
+        nxt.pk = __shfl_sync(0xffffffffu, bch.pk, owner);
+        nxt.st = __shfl_sync(0xffffffffu, bch.st, owner);
         if (lane == 0) {
             cb_board nb;
-            cbchess::make_move_hd(board, nxt.move, &nb);
+            cbchess::make_move_hd(board, (Move)(nxt.pk >> 16), &nb);
             board = nb;
             path[depth + 1] = best;
         }
@@ -459,41 +589,78 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     }
     const int path_n = depth + 1;
     MNode& leaf = nodes[cur];
-    const uint8_t leaf_state = n.state;
-    const int8_t leaf_term = n.term_value;
-    if (leaf_state == 2 || leaf_state == 1) {   // terminal (or the depth cap): back its value up again
+    const uint8_t leaf_state = (uint8_t)(n.st & 0xFFu);
+    const int8_t leaf_term = (int8_t)((n.st >> 8) & 0xFFu);
+    if (leaf_state == 2 || leaf_state == 1) {   // decided (or the depth cap): back its value up again
         __syncwarp();
-        mcts_backup(nodes, path, path_n, leaf_state == 2 ? (float)leaf_term : 0.0f, lane);
+        mcts_backup(nodes, path, path_n, leaf_state == 2 ? (double)leaf_term : 0.0, lane);
         if (lane == 0) {
             atomicAdd(&p.stats[MS_TERMINAL], 1ull);
-            p.sims_done[g]++;
             p.wants_eval[g] = 0;
             p.eval_cnt[g] = 0;
         }
+        mcts_sim_done(p, nodes, g, lane);
         return;
     }
-    const int n_moves = mcts_gen_legal_warp(board, s_pseudo[wl], s_legal[wl], lane);
-    // mate / stalemate, else the light Tier-1 gates; with the gates on, an opponent king on the hill is tested
-    // before anything else (src/mcts/tactical_mcts.rs:619-632) — same order as the host driver
-    int tv = 2;
-    if (p.tier1_light && p.koth && (board.pieces[(board.w_to_move ? 1 : 0) * 6 + cbchess::KING] & cbchess::kKothCenter)) tv = -1;
-    else if (n_moves == 0) tv = cbchess::in_check_hd(board, board.w_to_move ? 0 : 1) ? -1 : 0;
-    else if (p.tier1_light) tv = light_gates_warp(board, s_legal[wl], n_moves, p.koth != 0, sm.next[wl], s_pseudo[wl], lane);
+    int n_tact = 0;
+    const int n_moves = mcts_gen_legal_warp(board, s_pseudo[wl], s_legal[wl], lane, &n_tact);
+    // mate / stalemate (MctsNode::new_child, src/mcts/node.rs:162-177), else the light Tier-1 gates; with the gates on, an
+    // opponent king on the hill is tested before anything else (src/mcts/tactical_mcts.rs:619-632).  The root itself is
+    // never gated: the game loop adjudicates it before the search (src/bin/self_play.rs:241-283)
+    int tv = 2, td = 0;
+    const int us = board.w_to_move ? 0 : 1;
+    if (n_moves == 0) tv = cbchess::in_check_hd(board, us) ? -1 : 0;
+    else if (p.tier1_light && cur != 0) {
+        if (p.koth && (board.pieces[(1 - us) * 6 + cbchess::KING] & cbchess::kKothCenter)) tv = -1;
+        else {
+            tv = light_gates_warp(board, s_legal[wl], n_moves, p.koth != 0, sm.next[wl], s_pseudo[wl], lane, &td);
+        }
+    }
     if (tv != 2) {
         if (lane == 0) {
             leaf.state = 2;
             leaf.term_value = (int8_t)tv;
+            leaf.term_dist = (uint8_t)td;
         }
         __syncwarp();
-        mcts_backup(nodes, path, path_n, (float)tv, lane);
+        mcts_backup(nodes, path, path_n, (double)tv, lane);
         if (lane == 0) {
             atomicAdd(&p.stats[MS_TERMINAL], 1ull);
-            p.sims_done[g]++;
             p.wants_eval[g] = 0;
             p.eval_cnt[g] = 0;
         }
+        mcts_sim_done(p, nodes, g, lane);
         return;
     }
+    // tactical ranks of the capture-list moves (src/mcts/tactical.rs:155-177): stable descending MVV-LVA
+    uint8_t* trank = p.leaf_trank + (size_t)g * CB_MAX_MOVES;
+    for (int base = 0; base < n_moves; base += 32) {
+        const int i = base + lane;
+        if (i < n_moves) {
+            uint8_t r = 0xFF;
+            if (i < n_tact) {
+                const int si = cbchess::tactical_score_hd(board, s_legal[wl][i]);
+                int rk = 0;
+                for (int j = 0; j < n_tact; ++j) {
+                    const int sj = cbchess::tactical_score_hd(board, s_legal[wl][j]);
+                    rk += sj > si || (sj == si && j < i);
+                }
+                r = (uint8_t)rk;
+            }
+            trank[i] = r;
+        }
+    }
+    __syncwarp();
+    if (p.shuffle && lane == 0) {   // SliceRandom::shuffle: for i in (1..len).rev() swap(i, uniform(0..=i))
+        uint64_t rs = p.rng[g];
+        for (int i = n_moves - 1; i >= 1; --i) {
+            const int j = (int)(rng_next(rs) % (uint64_t)(i + 1));
+            const Move tm = s_legal[wl][i]; s_legal[wl][i] = s_legal[wl][j]; s_legal[wl][j] = tm;
+            const uint8_t tr = trank[i]; trank[i] = trank[j]; trank[j] = tr;
+        }
+        p.rng[g] = rs;
+    }
+    __syncwarp();
     const bool wtm = board.w_to_move != 0;
     for (int i = lane; i < n_moves; i += 32) {
         const Move m = s_legal[wl][i];
@@ -502,10 +669,12 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     }
     if (lane < 16) reinterpret_cast<uint64_t*>(&p.eval_boards[g])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
     __syncwarp();
-    const float leaf_q = mcts_material_q(p, board, sm.next[wl], sm.mailbox[wl], lane);   // `board` is dead after this
+    // a root asks for its policy only, with dM = 0 (selection.rs:315-332)
+    const float leaf_q = cur == 0 ? 0.0f : mcts_material_q(p, board, sm.next[wl], sm.mailbox[wl], lane);   // `board` is dead after this
     if (lane == 0) {
         p.eval_q[g] = leaf_q;
         p.eval_cnt[g] = (uint16_t)n_moves;
+        p.leaf_ntact[g] = (uint8_t)n_tact;
         p.path_n[g] = path_n;
         p.wants_eval[g] = 1;
         atomicAdd(&p.stats[MS_EVALS], 1ull);
@@ -560,7 +729,7 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
     Move (&s_pseudo)[kMctsWarps][CB_MAX_MOVES] = sm.pseudo;
     Move (&s_legal)[kMctsWarps][CB_MAX_MOVES] = sm.legal;
     MNode* nodes = p.nodes + ((size_t)g * 2 + p.arena[g]) * p.node_cap;
-    if (p.match_mode && p.idle[g]) return;
+    if ((p.match_mode || p.search_only) && p.idle[g]) return;
     // whose search is this?  (match mode: the model of the side to move at the root)
     const bool second = p.match_mode && ((p.root[g].w_to_move != 0) != (p.cand_white[g] != 0));
     const float* priors = second ? p.priors_b : p.priors;
@@ -574,16 +743,20 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
         if (first + (uint32_t)n <= p.node_cap) {
             for (int i = lane; i < n; i += 32) {
                 MNode ch;
-                ch.first_child = 0; ch.visits = 0; ch.value_sum = 0.0f;
+                ch.value_sum = 0.0; ch.first_child = 0; ch.visits = 0;
                 ch.prior = priors[(size_t)g * CB_MAX_MOVES + i];
                 ch.n_children = 0;
                 ch.move = p.leaf_moves[(size_t)g * CB_MAX_MOVES + i];
-                ch.state = 0; ch.term_value = 0; ch.pad = 0;
+                ch.state = 0; ch.term_value = 0; ch.n_tact = 0; ch.t_done = 0;
+                ch.trank = p.leaf_trank[(size_t)g * CB_MAX_MOVES + i];
+                ch.term_dist = 0; ch.pad = 0;
                 nodes[first + i] = ch;
             }
             if (lane == 0) {
                 nodes[cur].first_child = first;
                 nodes[cur].n_children = (uint16_t)n;
+                nodes[cur].n_tact = p.leaf_ntact[g];
+                nodes[cur].t_done = 0;
                 nodes[cur].state = 1;
                 p.n_nodes[g] = first + (uint32_t)n;
             }
@@ -591,11 +764,17 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
             atomicAdd(&p.stats[MS_OVERFLOW], 1ull);   // arena full: the leaf stays unexpanded (evaluated again later)
         }
         __syncwarp();
-        mcts_backup(nodes, path, path_n, v_final[g], lane);
-        if (lane == 0) p.sims_done[g]++;
+        if (cur != 0) {    // (the root only asked for its priors: no value, no simulation)
+            mcts_backup(nodes, path, path_n, (double)v_final[g], lane);
+            mcts_sim_done(p, nodes, g, lane);
+        }
         __syncwarp();
     }
     if (p.sims_done[g] < p.sims_per_move) return;
+    if (p.search_only) {   // debug search: the tree stays as it is for the host to read
+        if (lane == 0) p.idle[g] = 1;
+        return;
+    }
 
     // ------------------------------------------------------------------ play a move
     const MNode root = nodes[0];
@@ -618,10 +797,10 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
         }
     }
     if (lane == 0 && !forced_win) {
-        uint32_t best_v = 0;
+        uint32_t best_v = 0;     // select_greedy: Iterator::max_by_key keeps the LAST maximum (src/bin/self_play.rs:648-650)
         for (uint32_t i = 0; i < root.n_children; ++i) {
             const uint32_t v = nodes[root.first_child + i].visits;
-            if (v > best_v) { best_v = v; pick = root.first_child + i; }
+            if (v >= best_v) { best_v = v; pick = root.first_child + i; }
         }
         const int move_number = p.ply[g] / 2 + 1;
         if (rng_uniform(rs) < pow(p.explore_base, (double)(move_number - 1))) {
@@ -665,7 +844,7 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
             reinterpret_cast<uint64_t*>(&sm.board[wl])[lane] = w;
         }
         __syncwarp();
-        const float root_q = mcts_material_q(p, sm.board[wl], sm.next[wl], sm.mailbox[wl], lane);
+        const float root_q = mcts_material_q(p, sm.board[wl], sm.next[wl], sm.mailbox[wl], lane, true);
         if (lane == 0) {
             reinterpret_cast<uint32_t*>(rec)[0] = (uint32_t)g;
             reinterpret_cast<uint32_t*>(rec)[1] = p.game_serial[g];
@@ -777,6 +956,18 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_step_kernel(const MctsPa
         if (lane == 0) last = atomicInc(p.pdl_done, (unsigned int)p.gn - 1u) == (unsigned int)p.gn - 1u;
         if (__shfl_sync(0xffffffffu, last, 0)) asm volatile("griddepcontrol.wait;" ::: "memory");
     }
+}
+
+// The reference's mock evaluator (InferenceServer::new_mock_biased, src/mcts/inference_server.rs:103-122) in place of
+// the network: an all-zero policy, i.e. the uniform fallback 1 / len of policy_to_move_priors (src/tensor.rs:202-211),
+// a constant v_logit and k; the value is fused like the network's (tanhf(v + k * dM), or tanhf(v) without material).
+__global__ void mcts_mock_eval_kernel(const MctsParams p, float v_logit, float k, float* priors, float* v_final) {
+    const int g = p.g0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (g >= p.g0 + p.gn || !p.wants_eval[g]) return;
+    const int n = p.eval_cnt[g];
+    const float u = __fdiv_rn(1.0f, (float)n);
+    for (int i = lane; i < n; i += 32) priors[(size_t)g * CB_MAX_MOVES + i] = u;
+    if (lane == 0) v_final[g] = tanhf(p.material_on ? __fadd_rn(v_logit, __fmul_rn(k, p.eval_q[g])) : v_logit);
 }
 
 }  // namespace cb
