@@ -319,7 +319,8 @@ def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material, dtype
     for k in ("sims", "steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins",
               "black_wins", "draws"):
         assert host[k] == dev[k], (k, host[k], dev[k])
-    assert dev["moves"] > 24 * 40 and dev["games_finished"] >= 24
+    assert dev["moves"] > 24 * 40 and dev["games_finished"] >= 24 and dev["overflow"] == 0
+    # every step of a game is an evaluation (a simulation's leaf, or the policy request of a new game's root) or a decided leaf
     assert dev["sims"] == dev["nn_evals"] + dev["terminal_hits"]
     # the training samples too (5763-f32 records, src/training_data.rs:20-60); games that end in the same step
     # may be written in a different order
@@ -328,6 +329,96 @@ def test_device_tree_ops_equal_the_host_driver(cb, golden, name, material, dtype
     assert rh.shape == rd.shape and rh.shape[0] == host["samples"] > 0
     key = lambda r: r[np.lexsort(r.T[::-1])]
     assert np.array_equal(key(rh), key(rd))
+
+
+SEARCH_FENS = ["r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1",
+               "r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1",
+               "8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1",
+               "rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8",
+               "r1b2bnr/p2q1p1p/3kP1p1/2p5/p7/N4N2/PP1PPPPP/R1BK1B1R w - - 0 10",
+               "4k3/8/8/3pP3/8/8/8/4K3 w - d6 0 1", "1n2k3/P1P5/8/8/8/8/8/4K3 w - - 0 1", "8/8/8/8/8/3k4/8/4K3 w - - 0 1",
+               "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1"]
+
+
+def search_corpus(n_random, koth=None):
+    """Positions for the one-move searches; with the gates on, roots the game loop would adjudicate are left out
+    (src/bin/self_play.rs:241-283; see tests/test_host_search.py)."""
+    boards, _, _, _ = O.random_positions(99, n_random, 160)
+    boards = np.concatenate([O.boards_to_array([O.from_fen(f) for f in SEARCH_FENS]), boards])
+    if koth is not None:
+        boards = boards[[i for i in range(boards.shape[0]) if O.light_gates(O.array_to_board(boards[i]), koth=koth) == 2]]
+    return boards
+
+
+@pytest.mark.parametrize("mock,mode", [((0.0, 0.5), dict()), ((20.0, 0.5), dict()), ((-20.0, 0.5), dict(koth=True)),
+                                       ((0.0, 0.5), dict(koth=True, tier1_light=True)), ((0.0, 0.5), dict(tier1_light=True)),
+                                       ((0.0, 0.5), dict(shuffle_children=True))],
+                         ids=["uniform", "biased+", "biased-koth", "uniform-koth-gates", "uniform-gates", "uniform-shuffle"])
+def test_device_search_equals_the_oracle_with_the_mock_evaluator(cb, golden, mock, mode):
+    """The device tree kernels against oracle/mcts.c with the reference's mock evaluator (InferenceServer::new_mock_biased:
+    uniform priors, constant v_logit — 0 and a saturated +-20 give exact values on both sides): ties everywhere, so child
+    order, the tactical phase, the root's force-visit and the first-maximum rule decide every visit count.  200 simulations
+    from each of >= 64 positions; visit counts AND f64 value sums must be identical."""
+    g, blob = golden("2x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    boards = search_corpus(72, koth=mode.get("koth", False) if mode.get("tier1_light") else None)
+    assert boards.shape[0] >= 64
+    kids, root_visits = ev.debug_device_search(boards, sims_per_move=200, seed=3, mock=mock, **mode)
+    okw = dict(mode)
+    okw["shuffle"] = okw.pop("shuffle_children", False)
+    cfg = O.mcts_config(sims=200, **okw)
+    for i in range(boards.shape[0]):
+        seed = (3 * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019 * (i + 1)) % (1 << 64)
+        t = O.Tree(O.array_to_board(boards[i]), seed)
+        t.search(cfg, ("mock", mock[0], mock[1]))
+        want = t.root_children()
+        assert [(m, v) for m, v, _ in kids[i]] == [(m, v) for m, v, _ in want], (i, mode)
+        assert [s for _, _, s in kids[i]] == [s for _, _, s in want], (i, mode)
+        assert root_visits[i] == t.root_stats()["visits"]
+
+
+@pytest.mark.parametrize("material", [False, "pe"])
+def test_device_search_equals_the_oracle_with_the_network(cb, golden, material):
+    """The same comparison with the golden 6x128 network as evaluator: the oracle's callback evaluates each leaf through
+    cb_eval_leaves (one board per call; the forward is bit-identical whatever the batch), so both searches see the same
+    priors and values and must build the same tree — 64 positions x 200 simulations."""
+    g, blob = golden("6x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    boards = search_corpus(56)[:64]
+    mode = dict(material_on=bool(material), qsearch="pe" if material else 0)
+    kids, root_visits = ev.debug_device_search(boards, sims_per_move=200, seed=3, **mode)
+
+    def net(b, moves, q, material_on):
+        bu = np.frombuffer(bytes(b), dtype=np.uint8)[None]
+        idx = np.array([O.move_to_index_stm(m, b.w_to_move) for m in moves], dtype=np.uint16)
+        pri, _, vf, _ = ev.eval_leaves(bu, np.array([q], dtype=np.float32), idx, np.array([0, len(moves)], dtype=np.uint32),
+                                       material_on=material_on)
+        return pri, float(vf[0])
+    cfg = O.mcts_config(sims=200, **mode)
+    tactical = 0
+    for i in range(boards.shape[0]):
+        t = O.Tree(O.array_to_board(boards[i]), 1)
+        t.search(cfg, net)
+        want = t.root_children()
+        assert [(m, v) for m, v, _ in kids[i]] == [(m, v) for m, v, _ in want], i
+        assert [s for _, _, s in kids[i]] == [s for _, _, s in want], i
+        tactical += t.root_stats()["tactical"]
+    assert tactical > 500          # the tactical phase did steer leaves
+
+
+def test_device_search_equals_the_host_driver_hook(cb, golden):
+    """cb_debug_host_search with the network behind its callback == cb_debug_device_search (three-way closure)."""
+    g, blob = golden("6x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    boards = search_corpus(24)[:32]
+    kids, _ = ev.debug_device_search(boards, sims_per_move=64, seed=3, material_on=True, qsearch="pe", tier1_light=False)
+
+    def net(board, moves, idx, q, material_on):
+        pri, _, vf, _ = ev.eval_leaves(board[None], np.array([q], dtype=np.float32), np.array(idx, dtype=np.uint16),
+                                       np.array([0, len(moves)], dtype=np.uint32), material_on=material_on)
+        return pri, float(vf[0])
+    hk, _ = cb.debug_host_search(boards, net, sims_per_move=64, seed=3, material_on=True, qsearch="pe")
+    assert hk == kids
 
 
 @pytest.mark.parametrize("material,qsearch", [(False, 0), (True, "pe")])
