@@ -113,6 +113,16 @@ int cb_eval_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, 
                    const uint16_t* move_idx, const uint32_t* move_off,
                    float* priors, float* v_logit, float* v_final, float* k);
 
+/* The same call in two halves, so that ONE host thread can keep several handles busy (the reference's multi-instance use,
+ * SURVEY.md §3.4): submit copies the request into the handle's pinned staging block (the caller's buffers are free again
+ * on return), enqueues the host->device copy, the forward and the device->host copy on the handle's stream and returns
+ * without synchronising; wait blocks until that batch is done and copies the results out.  One batch in flight per handle;
+ * cb_eval_leaves == submit + wait, bit for bit.  With two handles: submit(a), submit(b), wait(a), submit(a), wait(b), ... —
+ * b's copies overlap a's kernel. */
+int cb_eval_leaves_submit(cb_handle* h, const cb_board* boards, const float* q, int B, int material_on,
+                          const uint16_t* move_idx, const uint32_t* move_off);
+int cb_eval_leaves_wait(cb_handle* h, float* priors, float* v_logit, float* v_final, float* k);
+
 /* Bit-exactness hook for board_to_planes (src/tensor.rs:21-77): planes[B*1088]
  * f32, NCHW, exactly the reference's Vec<f32>. */
 int cb_encode(cb_handle* h, const cb_board* boards, int B, float* planes);

@@ -158,6 +158,8 @@ SIGNATURES = {
     "cb_is_available": (ctypes.c_int, [_VP]),
     "cb_predict_batch": (ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_int, _VP, _VP, _VP]),
     "cb_eval_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "cb_eval_leaves_submit": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    "cb_eval_leaves_wait": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "cb_encode": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
     "cb_pst_eval_cp": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
     "cb_principal_exchange": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
@@ -351,6 +353,30 @@ class Evaluator:
             check(fn(*args))
             return outs
         return run
+
+    def prepared_submit_wait(self, boards, q, move_idx, move_off, material_on=True):
+        """cb_eval_leaves_submit / cb_eval_leaves_wait on fixed host buffers -> (submit(), wait() -> outputs): the two
+        halves of prepared_eval_leaves, for a single host thread that keeps several handles busy."""
+        b = _boards_u8(boards)
+        B = b.shape[0]
+        qa = None if q is None else np.ascontiguousarray(q, dtype=np.float32)
+        mi = np.ascontiguousarray(move_idx, dtype=np.uint16)
+        mo = np.ascontiguousarray(move_off, dtype=np.uint32)
+        assert mo.size == B + 1
+        outs = (np.empty(int(mo[B]), dtype=np.float32), np.empty(B, dtype=np.float32), np.empty(B, dtype=np.float32),
+                np.empty(B, dtype=np.float32))
+        keep = (b, qa, mi, mo)
+        sargs = (self._h, _ptr(b), _ptr(qa), B, int(material_on), _ptr(mi), _ptr(mo))
+        wargs = (self._h,) + tuple(_ptr(o) for o in outs)
+        fs, fw, check = self._L.cb_eval_leaves_submit, self._L.cb_eval_leaves_wait, self._check
+
+        def submit(_keep=keep):
+            check(fs(*sargs))
+
+        def wait():
+            check(fw(*wargs))
+            return outs
+        return submit, wait
 
     def stage_leaves(self, boards, q, move_idx, move_off):
         b = _boards_u8(boards)

@@ -22,7 +22,6 @@
 #include "kernels_simt.cuh"
 #include "policy_umma.cuh"
 #include "tower_umma.cuh"
-#include "tower_t_umma.cuh"
 #include "tower_r_umma.cuh"
 #include "mcts_device.cuh"
 
@@ -105,13 +104,7 @@ struct cb_handle {
     cb::TowerLayer* d_layers = nullptr;
     bool tower_ready = false;
     bool use_fused = true;
-    // transposed (quad-layout) fused tower for the 128-channel net
-    CUtensorMap tm_x0_q, tm_act_ld_q[3], tm_act_st_q[3];
-    CUtensorMap* d_maps_q = nullptr;
-    cb::TowerTLayer* d_layers_q = nullptr;
-    bool tower_q_ready = false;
-    bool use_quad = true;
-    long long* d_trace = nullptr;   // debug timeline of CTA 0 of the transposed tower (cb_debug_tower_trace)
+    long long* d_trace = nullptr;   // debug timeline of CTA 0 of the resident tower (cb_debug_tower_trace)
     // smem-resident fused tower for the 128-channel net (tower_r_umma.cuh)
     void* p_w16r = nullptr;              // p_head weights padded to [128][HID] 16-bit (rows 73.. zero)
     float* p_bias_r = nullptr;           // p_head bias padded to 128
@@ -135,11 +128,16 @@ struct cb_handle {
     float* h_priors = nullptr;
     float* h_small = nullptr;   // v_logit | v_final | k, 3*cap
 
+    // cb_eval_leaves_submit / _wait: the batch in flight (-1: none)
+    int pending_B = -1;
+    size_t pending_priors = 0;
+
     // resident state
     int staged_B = 0;
     size_t staged_moves = 0;
 
     std::map<uint64_t, cudaGraphExec_t> graphs;
+    std::map<uint64_t, int> graph_seen;          // how often a forward shape was requested (run_forward)
     cb_timing timing = {};
     bool use_graphs = true;
     int layer_limit = 0;  // debug: stop the tower after this many conv launches (0 = all)
@@ -282,11 +280,6 @@ int ensure_capacity(cb_handle* h, int B) {
             if ((rc = make_act_map(h, &h->tm_act_st[i], h->d_act[i], h->hid, cap, 8))) return rc;
         }
         if (h->hid == 128) {
-            if ((rc = make_act_map(h, &h->tm_x0_q, h->d_x0, 64, cap, 10, 4))) return rc;
-            for (int i = 0; i < 3; ++i) {
-                if ((rc = make_act_map(h, &h->tm_act_ld_q[i], h->d_act[i], h->hid, cap, 10, 4))) return rc;
-                if ((rc = make_act_map(h, &h->tm_act_st_q[i], h->d_act[i], h->hid, cap, 8, 4))) return rc;
-            }
             free_dev(h->d_res_scratch);
             h->d_res_scratch = nullptr;
             CB_CUDA(h, cudaMalloc(&h->d_res_scratch, (size_t)h->sm_count * TowerRCfg::kScratchPerCta * sizeof(uint4)));
@@ -332,44 +325,7 @@ int build_tower_tables(cb_handle* h) {
     CB_CUDA(h, cudaMemcpy(h->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     CB_CUDA(h, cudaMemcpy(h->d_layers, ly.data(), ly.size() * sizeof(TowerLayer), cudaMemcpyHostToDevice));
     h->tower_ready = true;
-    h->tower_q_ready = false;
     if (h->hid == 128) {
-        // map table: 0 x0 (quad ld) | 1..3 act quad ld | 4..6 act quad st (also residual loads) |
-        //            7 act[1] pair st (p_conv output, read by the policy kernel) | 8.. weights
-        std::vector<CUtensorMap> mq(8 + nl);
-        mq[0] = h->tm_x0_q;
-        for (int i = 0; i < 3; ++i) { mq[1 + i] = h->tm_act_ld_q[i]; mq[4 + i] = h->tm_act_st_q[i]; }
-        mq[7] = h->tm_act_st[1];
-        for (int l = 0; l < nl; ++l) mq[8 + l] = h->convs[l].tm_w;
-        std::vector<TowerTLayer> lq(nl);
-        memset(lq.data(), 0, sizeof(TowerTLayer) * nl);
-        int c2 = 0;
-        lq[0].in_map = 0; lq[0].w_map = 8; lq[0].out_map = 4 + 0; lq[0].kc_in = 1; lq[0].mode = MODE_RELU;
-        lq[0].bias = h->convs[0].bias;
-        for (int i = 0; i < h->blocks; ++i) {
-            const int nxt = c2 == 0 ? 2 : 0;
-            TowerTLayer& a = lq[1 + 2 * i];
-            a.in_map = 1 + c2; a.w_map = 8 + 1 + 2 * i; a.out_map = 4 + 1; a.kc_in = 2; a.mode = MODE_RELU;
-            a.bias = h->convs[1 + 2 * i].bias;
-            TowerTLayer& b = lq[2 + 2 * i];
-            b.in_map = 1 + 1; b.w_map = 8 + 2 + 2 * i; b.out_map = 4 + nxt; b.res_map = 4 + c2; b.kc_in = 2;
-            b.mode = MODE_SE_RES;
-            b.bias = h->convs[2 + 2 * i].bias;
-            b.se_w1 = h->se_w1[i]; b.se_w2 = h->se_w2[i];
-            if (i == h->blocks - 1) { b.v_w = h->v_w; b.v_pre = h->d_vpre; }
-            c2 = nxt;
-        }
-        TowerTLayer& pq = lq[nl - 1];
-        pq.in_map = 1 + c2; pq.w_map = 8 + nl - 1; pq.out_map = 7; pq.out_pair = 1; pq.kc_in = 2; pq.mode = MODE_RELU;
-        pq.bias = h->convs[nl - 1].bias;
-        free_dev(h->d_maps_q); free_dev(h->d_layers_q);
-        h->d_maps_q = nullptr; h->d_layers_q = nullptr;
-        CB_CUDA(h, cudaMalloc(&h->d_maps_q, mq.size() * sizeof(CUtensorMap)));
-        CB_CUDA(h, cudaMalloc(&h->d_layers_q, lq.size() * sizeof(TowerTLayer)));
-        CB_CUDA(h, cudaMemcpy(h->d_maps_q, mq.data(), mq.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-        CB_CUDA(h, cudaMemcpy(h->d_layers_q, lq.data(), lq.size() * sizeof(TowerTLayer), cudaMemcpyHostToDevice));
-        h->tower_q_ready = true;
-
         // resident tower: map table = weights of the nl conv layers, then the padded p_head; the layer table
         // ends with the policy head as a one-tap layer
         h->tower_r_ready = false;
@@ -410,12 +366,11 @@ int build_tower_tables(cb_handle* h) {
     return CB_OK;
 }
 
-// Which fused tower runs for this handle right now (0 none / per-layer, 1 pair-layout, 2 quad-layout
-// transposed, 3 smem-resident transposed).
+// Which tower runs for this handle right now: 0 per-layer launches, 1 the pair-layout fused tower (256-channel nets;
+// 128-channel ones with CB_TOWER_PAIR=1), 3 the shared-memory-resident single-launch forward (128-channel nets).
 int fused_kind(const cb_handle* h) {
     if (h->dtype == CB_DTYPE_FP32 || !h->use_fused || h->layer_limit != 0) return 0;
     if (h->hid == 128 && h->use_resident && h->tower_r_ready) return 3;
-    if (h->hid == 128 && h->use_quad && h->tower_q_ready) return 2;
     return h->tower_ready ? 1 : 0;
 }
 
@@ -432,7 +387,7 @@ ValueParams value_params(const cb_handle* h, int B, int material_on, bool use_q,
     vp.out_b = h->out_b;
     vp.k = h->k;
     vp.material_on = material_on;
-    vp.pair_layout = pair_layout;   // layout of v_pre rows: the quad / resident towers emit plain order
+    vp.pair_layout = pair_layout;   // layout of v_pre rows: the resident tower emits plain order
     vp.B = B;
     vp.v_logit = h->d_vlogit;
     vp.v_final = h->d_vfinal;
@@ -527,28 +482,6 @@ int launch_tower_r_staged(cb_handle* h, int B) {
     return launch_tower_r(h, B, po, 1, true);
 }
 
-int launch_tower_q(cb_handle* h, int B) {
-    TowerTParams tp;
-    tp.maps = h->d_maps_q;
-    tp.layers = h->d_layers_q;
-    tp.num_layers = (int)h->convs.size();
-    tp.num_quads = (B + 3) / 4;
-    tp.num_boards = B;
-    tp.trace = h->d_trace;
-    const int units = (tp.num_quads + 1) / 2;
-    const int grid = units < h->sm_count ? units : h->sm_count;
-    if (h->dtype == CB_DTYPE_BF16) {
-        auto kern = tower_t_umma_kernel<true>;
-        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerTCfg::kSmemBytes));
-        kern<<<grid, TowerTCfg::kThreads, TowerTCfg::kSmemBytes, h->stream>>>(tp);
-    } else {
-        auto kern = tower_t_umma_kernel<false>;
-        CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerTCfg::kSmemBytes));
-        kern<<<grid, TowerTCfg::kThreads, TowerTCfg::kSmemBytes, h->stream>>>(tp);
-    }
-    CB_CUDA(h, cudaGetLastError());
-    return CB_OK;
-}
 
 template <int HID, bool BF16>
 int launch_tower_t(cb_handle* h, int B) {
@@ -768,7 +701,7 @@ int enqueue_tower(cb_handle* h, int B, std::vector<cudaEvent_t>* ev) {
 int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int material_on, bool use_q,
                     const uint16_t* move_cnt = nullptr) {
     const int kind = fused_kind(h);
-    const int glog = kind == 2 ? 2 : 1;                       // boards interleaved per activation group
+    const int glog = 1;                                       // boards interleaved per activation group (pairs)
     const int Bpad = (B + (1 << glog) - 1) & ~((1 << glog) - 1);
     if (kind == 3) {
         // the resident tower encodes the planes itself
@@ -790,9 +723,7 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     }
     int rc;
     if (kind == 3) return launch_tower_r(h, B, po, material_on, use_q);   // heads included
-    if (kind == 2)
-        rc = launch_tower_q(h, B);
-    else if (kind == 1)
+    if (kind == 1)
         rc = launch_tower(h, B);
     else
         rc = enqueue_tower(h, B, nullptr);
@@ -800,7 +731,7 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     // the two heads are independent: fork the value head onto the side stream
     CB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     CB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-    const ValueParams vp = value_params(h, B, material_on, use_q, h->dtype == CB_DTYPE_FP32 ? 0 : (kind >= 2 ? 0 : 1));
+    const ValueParams vp = value_params(h, B, material_on, use_q, h->dtype == CB_DTYPE_FP32 ? 0 : (kind == 3 ? 0 : 1));
     value_head_kernel<<<(B + kValueBoardsPerCta - 1) / kValueBoardsPerCta, 256, 0, h->stream2>>>(vp);
     CB_CUDA(h, cudaGetLastError());
     CB_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
@@ -809,20 +740,22 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     return CB_OK;
 }
 
-// Replay (capturing on first use) the forward graph for this shape.
+// Replay the forward graph for this shape.  A shape is launched eagerly the first two times it is seen (which also sets
+// the kernels' attributes outside capture) and captured on the third; at most kMaxForwardGraphs shapes are kept — the
+// host-driven pools submit a different batch size almost every step, and those ragged sizes simply stay eager.
+constexpr size_t kMaxForwardGraphs = 24;
 int run_forward(cb_handle* h, int B, bool full_policy, bool csr, int material_on, bool use_q) {
     if (!h->use_graphs) return enqueue_forward(h, B, full_policy, csr, material_on, use_q);
     const uint64_t key = (uint64_t)B | ((uint64_t)full_policy << 32) | ((uint64_t)csr << 33) |
                          ((uint64_t)(material_on != 0) << 34) | ((uint64_t)use_q << 35);
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
-        // first call of each kernel sets its smem attribute outside capture
-        int rc = enqueue_forward(h, B, full_policy, csr, material_on, use_q);
-        if (rc) return rc;
-        CB_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->graph_seen.size() > 4096) h->graph_seen.clear();
+        if (++h->graph_seen[key] < 3 || h->graphs.size() >= kMaxForwardGraphs)
+            return enqueue_forward(h, B, full_policy, csr, material_on, use_q);
         cudaGraph_t g = nullptr;
         CB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        rc = enqueue_forward(h, B, full_policy, csr, material_on, use_q);
+        const int rc = enqueue_forward(h, B, full_policy, csr, material_on, use_q);
         cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
         if (rc) {
             if (g) cudaGraphDestroy(g);
@@ -961,10 +894,8 @@ int cb_create(cb_handle** out, int device, int num_blocks, int hidden, int dtype
     h->use_graphs = !(ng && ng[0] == '1');
     const char* nf = getenv("CB_NO_FUSE");
     h->use_fused = !(nf && nf[0] == '1');
-    const char* tp = getenv("CB_TOWER_PAIR");
-    h->use_quad = !(tp && tp[0] == '1');
-    const char* tq = getenv("CB_TOWER_QUAD");   // force the global-round-trip towers (debug / comparison)
-    h->use_resident = h->use_quad && !(tq && tq[0] == '1');
+    const char* tp = getenv("CB_TOWER_PAIR");   // 128-channel nets on the global-round-trip tower of the 256-channel ones (comparison)
+    h->use_resident = !(tp && tp[0] == '1');
     // 2-CTA clusters sharing the weight stream (TMA multicast): measured, not the default — it saves power
     // (+5 % SM clock under the 1000 W cap) but the lock-step of the two CTAs on a 4-stage ring costs 10 % more
     // cycles (sustained 195.9 us vs 188.1 us per forward at batch 1024).  CB_CLUSTER=1 turns it on.
@@ -1011,7 +942,6 @@ void cb_destroy(cb_handle* h) {
     free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
     free_dev(h->p_w16); free_dev(h->p_w16r); free_dev(h->p_bias_r);
     free_dev(h->d_maps); free_dev(h->d_layers);
-    free_dev(h->d_maps_q); free_dev(h->d_layers_q);
     free_dev(h->d_maps_r); free_dev(h->d_layers_r); free_dev(h->d_res_scratch); free_dev(h->d_maps_r_half);
     free_dev(h->d_flush);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1322,7 +1252,8 @@ int cb_principal_exchange_device(cb_handle* h, const cb_board* boards, int n, fl
 }
 
 // Device -> host read-back of the per-position scalars and (n_priors > 0) the gathered priors.
-static int read_results(cb_handle* h, int B, size_t n_priors, float* priors, float* v_logit, float* v_final, float* k) {
+// Device -> pinned copies of a batch's results, enqueued behind the forward; ev3 marks their completion.
+static int enqueue_results(cb_handle* h, int B, size_t n_priors) {
     float* s = h->h_small;
     if (n_priors && (size_t)B * 4 >= (size_t)h->cap * 3) {
         CB_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_pri_off + n_priors * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1334,12 +1265,23 @@ static int read_results(cb_handle* h, int B, size_t n_priors, float* priors, flo
             CB_CUDA(h, cudaMemcpyAsync(h->h_priors, h->d_priors, n_priors * 4, cudaMemcpyDeviceToHost, h->stream));
     }
     CB_CUDA(h, cudaEventRecord(h->ev3, h->stream));
-    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+
+// Pinned -> caller buffers once ev3 has passed.
+static int finish_results(cb_handle* h, int B, size_t n_priors, float* priors, float* v_logit, float* v_final, float* k) {
+    float* s = h->h_small;
+    CB_CUDA(h, cudaEventSynchronize(h->ev3));
     if (v_logit) memcpy(v_logit, s, (size_t)B * 4);
     if (v_final) memcpy(v_final, s + h->cap, (size_t)B * 4);
     if (k) memcpy(k, s + 2 * (size_t)h->cap, (size_t)B * 4);
     if (n_priors && priors) memcpy(priors, h->h_priors, n_priors * 4);
     return CB_OK;
+}
+
+static int read_results(cb_handle* h, int B, size_t n_priors, float* priors, float* v_logit, float* v_final, float* k) {
+    const int rc = enqueue_results(h, B, n_priors);
+    return rc ? rc : finish_results(h, B, n_priors, priors, v_logit, v_final, k);
 }
 
 static void account(cb_handle* h, int B) {
@@ -1381,23 +1323,52 @@ int cb_predict_batch(cb_handle* h, const cb_board* boards, const float* q, const
     return CB_OK;
 }
 
+int cb_eval_leaves_submit(cb_handle* h, const cb_board* boards, const float* q, int B, int material_on,
+                          const uint16_t* move_idx, const uint32_t* move_off) {
+    if (!h || !boards || B < 0) return CB_EINVAL;
+    if ((move_idx == nullptr) != (move_off == nullptr)) return CB_EINVAL;
+    if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
+    if (h->pending_B >= 0) return fail(h, CB_ESTATE, "a submitted batch is still waiting for cb_eval_leaves_wait");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    h->pending_B = 0;
+    h->pending_priors = 0;
+    if (B == 0) return CB_OK;
+    CB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    int rc = upload_leaves(h, boards, q, B, move_idx, move_off);   // the caller's buffers are free again on return
+    if (!rc) {
+        CB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        rc = run_forward(h, B, false, move_off != nullptr, material_on, q != nullptr);
+    }
+    if (!rc) {
+        CB_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+        rc = enqueue_results(h, B, h->staged_moves);
+    }
+    if (rc) { h->pending_B = -1; return rc; }
+    h->pending_B = B;
+    h->pending_priors = h->staged_moves;
+    return CB_OK;
+}
+
+int cb_eval_leaves_wait(cb_handle* h, float* priors, float* v_logit, float* v_final, float* k) {
+    if (!h) return CB_EINVAL;
+    if (h->pending_B < 0) return fail(h, CB_ESTATE, "no submitted batch to wait for");
+    const int B = h->pending_B;
+    const size_t n = h->pending_priors;
+    h->pending_B = -1;
+    if (B == 0) return CB_OK;
+    if (n && !priors) return fail(h, CB_EINVAL, "the submitted batch has legal-move lists: priors must not be null");
+    const int rc = finish_results(h, B, n, priors, v_logit, v_final, k);
+    if (rc) return rc;
+    account(h, B);
+    return CB_OK;
+}
+
 int cb_eval_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, int material_on,
                    const uint16_t* move_idx, const uint32_t* move_off, float* priors, float* v_logit,
                    float* v_final, float* k) {
-    if (!h || !boards || B < 0) return CB_EINVAL;
-    if ((move_idx == nullptr) != (move_off == nullptr) || (move_off && !priors)) return CB_EINVAL;
-    if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
-    if (B == 0) return CB_OK;
-    CB_CUDA(h, cudaSetDevice(h->device));
-    CB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    int rc = upload_leaves(h, boards, q, B, move_idx, move_off);
-    if (rc) return rc;
-    CB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-    if ((rc = run_forward(h, B, false, move_off != nullptr, material_on, q != nullptr))) return rc;
-    CB_CUDA(h, cudaEventRecord(h->ev2, h->stream));
-    if ((rc = read_results(h, B, h->staged_moves, priors, v_logit, v_final, k))) return rc;
-    account(h, B);
-    return CB_OK;
+    if (move_off && !priors) return CB_EINVAL;
+    const int rc = cb_eval_leaves_submit(h, boards, q, B, material_on, move_idx, move_off);
+    return rc ? rc : cb_eval_leaves_wait(h, priors, v_logit, v_final, k);
 }
 
 int cb_stage_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, const uint16_t* move_idx,
@@ -1481,7 +1452,6 @@ int cb_time_tower(cb_handle* h, int iters, float* ms_each, int* n_launches) {
     for (int i = 0; i < iters && !rc; ++i) {
         CB_CUDA(h, cudaEventRecord(ev[2 * i], h->stream));
         rc = kind == 3   ? launch_tower_r_staged(h, h->staged_B)
-             : kind == 2 ? launch_tower_q(h, h->staged_B)
              : kind == 1 ? launch_tower(h, h->staged_B)
                          : enqueue_tower(h, h->staged_B, nullptr);
         CB_CUDA(h, cudaEventRecord(ev[2 * i + 1], h->stream));
@@ -1506,14 +1476,14 @@ int cb_read_resident(cb_handle* h, float* priors, float* v_logit, float* v_final
 int cb_debug_tower_trace(cb_handle* h, long long* out, int max_items) {
     if (!h || !out || max_items <= 0) return CB_EINVAL;
     const int kind = fused_kind(h);
-    if (!h->staged_B || kind < 2) return fail(h, CB_ESTATE, "needs staged leaves and a transposed tower");
+    if (!h->staged_B || kind != 3) return fail(h, CB_ESTATE, "needs staged leaves and the resident tower");
     CB_CUDA(h, cudaSetDevice(h->device));
-    const int items = 2 * ((int)h->convs.size() + (kind == 3 ? 1 : 0));   // the resident tower's last "layer" is the policy head
+    const int items = 2 * ((int)h->convs.size() + 1);   // the resident tower's last "layer" is the policy head
     const int n = items < max_items ? items : max_items;
     drop_graphs(h);
     CB_CUDA(h, cudaMalloc(&h->d_trace, (size_t)items * 8 * sizeof(long long)));
     CB_CUDA(h, cudaMemsetAsync(h->d_trace, 0, (size_t)items * 8 * sizeof(long long), h->stream));
-    int rc = kind == 3 ? launch_tower_r_staged(h, h->staged_B) : launch_tower_q(h, h->staged_B);
+    int rc = launch_tower_r_staged(h, h->staged_B);
     cudaError_t e = cudaMemcpyAsync(out, h->d_trace, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
     cudaError_t e2 = cudaStreamSynchronize(h->stream);
     cudaFree(h->d_trace);

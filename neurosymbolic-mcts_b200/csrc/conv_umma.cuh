@@ -97,6 +97,26 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
     }
 }
 
+// One activation value <-> its 16-bit storage form.
+template <bool BF16>
+__device__ __forceinline__ uint16_t to16bits(float v) {
+    if constexpr (BF16) {
+        __nv_bfloat16 b = __float2bfloat16_rn(v);
+        return *reinterpret_cast<uint16_t*>(&b);
+    } else {
+        __half h = __float2half_rn(v);
+        return *reinterpret_cast<uint16_t*>(&h);
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ float from16bits(uint16_t u) {
+    if constexpr (BF16) {
+        return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+    } else {
+        return __half2float(*reinterpret_cast<__half*>(&u));
+    }
+}
+
 // Per-board column sums inside one warp.  Lane bit 3 is the board (b2) of the lane's
 // pixel row, so the butterfly runs over lane bits 4, 2, 1, 0 only: 32 per-thread values
 // shrink to 2, summed over the 16 lanes that share the board bit.  On return v[0], v[1]

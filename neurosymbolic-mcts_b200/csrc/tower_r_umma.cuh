@@ -39,7 +39,7 @@
 // MMA: buffer written, accumulator preset).  All waits are bounded (a protocol bug traps).
 #pragma once
 #include "kernels_simt.cuh"
-#include "tower_t_umma.cuh"
+#include "tower_umma.cuh"
 
 namespace cb {
 

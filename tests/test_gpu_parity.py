@@ -111,6 +111,34 @@ def test_tensor_core_modes_match_reference(cb, golden, name, dtype):
     assert np.abs(bb - g["backbone"]).max() <= (0.03 if dtype == "bf16" else 0.005) * max(scale, 1.0)
 
 
+@pytest.mark.parametrize("env,name,dtype", [({"CB_NO_FUSE": "1"}, "6x128_B", "bf16"), ({"CB_NO_FUSE": "1"}, "10x256_B", "fp16"),
+                                            ({"CB_TOWER_PAIR": "1"}, "6x128_B", "bf16"), ({"CB_TOWER_PAIR": "1"}, "2x128_B", "fp16"),
+                                            ({"CB_CLUSTER": "1"}, "6x128_B", "bf16"), ({"CB_SIMT_POLICY": "1"}, "10x256_B", "fp16"),
+                                            ({"CB_NO_GRAPH": "1"}, "6x128_B", "fp16"), ({"CB_NO_DEEP_RING": "1"}, "2x128_B", "bf16")],
+                         ids=lambda x: "+".join(x) if isinstance(x, dict) else x)
+def test_every_kernel_path_in_the_library_matches_reference(cb, golden, monkeypatch, env, name, dtype):
+    """The switches that select the other kernels the library ships — one launch per layer (CB_NO_FUSE), the pair-layout
+    global-round-trip tower on a 128-channel net (CB_TOWER_PAIR; it is the 256-channel nets' default), the 2-CTA weight
+    multicast of the resident kernel (CB_CLUSTER), the SIMT policy head (CB_SIMT_POLICY), eager launches (CB_NO_GRAPH),
+    the 4-stage ring for small batches (CB_NO_DEEP_RING): each must meet the same bars as the default path."""
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    g, blob = golden(name)
+    ev = make_eval(cb, g, blob, dtype)
+    q = g["q"]
+    pol, v, k = ev.predict_batch(g["boards"], q, None)
+    nf = g["log_policy_full"].shape[0]
+    ref = np.tanh(g["v_logit"].astype(np.float64) + g["k"].astype(np.float64) * q)
+    got = np.tanh(v.astype(np.float64) + k.astype(np.float64) * q)
+    assert np.abs(got - ref).max() <= TOL_V_16
+    assert kl(np.exp(g["log_policy_full"]), pol[:nf]).max() <= TOL_KL
+    pri, v2, vf, _ = ev.eval_leaves(g["boards"], q, g["move_idx"], g["move_off"], material_on=True)
+    assert np.abs(pri - g["priors"]).max() <= 2e-3 and np.abs(v2 - v).max() <= 1e-3
+    # small batches too (the deep-ring / single-chain launch shapes of the resident kernel)
+    pri1, v1, _, _ = ev.eval_leaves(g["boards"][:3], q[:3], g["move_idx"][:g["move_off"][3]], g["move_off"][:4], material_on=True)
+    assert np.abs(v1 - v[:3]).max() <= 1e-3 and np.abs(pri1 - pri[:g["move_off"][3]]).max() <= 1e-3
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_fused_leaf_eval_matches_reference(cb, golden, dtype):
     g, blob = golden("6x128_B")
@@ -297,6 +325,37 @@ def test_resident_path_equals_host_path(cb, golden, positions):
     tower_ms, launches = ev.time_tower(3)
     assert launches == 1 and tower_ms.min() > 0            # the fused persistent tower kernel
     assert ev.launches_per_forward() == 1                  # planes, tower and both heads in one launch
+
+
+def test_submit_wait_equals_eval_leaves(cb, golden, positions):
+    """cb_eval_leaves_submit + cb_eval_leaves_wait == cb_eval_leaves bit for bit; one host thread drives two handles with
+    their batches interleaved (the second handle's copies run under the first one's kernel)."""
+    g, blob = golden("6x128_B")
+    a, b = make_eval(cb, g, blob, "bf16"), make_eval(cb, g, blob, "bf16")
+    boards, idx, off, _ = positions
+    q = O.static_q(boards)
+    cuts = [(0, 700), (700, 1724), (1724, 1725), (1725, 2048)]
+    want = [a.eval_leaves(boards[s:e], q[s:e], idx[off[s]:off[e]], off[s:e + 1] - off[s]) for s, e in cuts]
+    pairs = [(a if i % 2 == 0 else b).prepared_submit_wait(boards[s:e], q[s:e], idx[off[s]:off[e]], off[s:e + 1] - off[s])
+             for i, (s, e) in enumerate(cuts)]
+    pairs[0][0]()
+    pairs[1][0]()
+    got = [None] * 4
+    got[0] = [x.copy() for x in pairs[0][1]()]
+    pairs[2][0]()
+    got[1] = [x.copy() for x in pairs[1][1]()]
+    pairs[3][0]()
+    got[2] = [x.copy() for x in pairs[2][1]()]
+    got[3] = [x.copy() for x in pairs[3][1]()]
+    for w, gt in zip(want, got):
+        for x, y in zip(w, gt):
+            assert np.array_equal(x, y)
+    with pytest.raises(cb.CaissaError):
+        pairs[0][1]()                                  # nothing in flight
+    pairs[0][0]()
+    with pytest.raises(cb.CaissaError):
+        pairs[0][0]()                                  # one batch per handle
+    pairs[0][1]()
 
 
 # ------------------------------------------------------------------ device-side tree operations
