@@ -13,8 +13,11 @@ initialisation law with live heads (oracle/weights.py variant B); both synthetic
   value    whole-job evals/s with inputs already resident in HBM: K replays of the captured
            forward graph, each timed with CUDA events on the launching stream (inside the
            library), L2 flushed (256 MiB rewrite) between steps; max over ranks.
-  e2e      same metric through the public C-ABI call cb_eval_leaves with HOST buffers: H2D of
-           boards/q/CSR and D2H of priors/values inside the timed region, every step.
+           value_sustained: the same forward replayed back to back for >= 2 s without the flush
+           (the kernel is power-capped: the flush lets the clock recover, a busy pool does not).
+  e2e      same metric through the public C ABI with HOST buffers: H2D of boards/q/CSR and D2H
+           of priors/values inside the timed region, every step.  ONE host thread keeps two
+           handles busy with cb_eval_leaves_submit / cb_eval_leaves_wait.
   roofline the dominant kernel — for 128-channel nets the ONE kernel of the forward (planes, 14 tcgen05
            convs, both heads) — algorithmic FLOPs per launch / mean CUDA-event duration of its launches,
            against the measured bf16 peak.
@@ -54,6 +57,26 @@ def tower_flops_per_position(blocks, hidden):
     return 2 * 9 * 64 * (17 * hidden + (2 * blocks + 1) * hidden * hidden)
 
 
+def workload_label(blocks, hidden, batch):
+    """Which BASELINE.json config the arguments describe."""
+    if (blocks, hidden) == (6, 128):
+        return "configs[1]: batched leaf eval sweep, OracleNet 6x128, batch %d, one batch per GPU" % batch
+    if (blocks, hidden) == (10, 256):
+        return "configs[3]: scaled OracleNet 10x256 leaf eval, batch %d, one batch per GPU" % batch
+    return "OracleNet %dx%d leaf eval, batch %d, one batch per GPU (not a BASELINE.json config)" % (blocks, hidden, batch)
+
+
+def measured_traffic(blocks, hidden, batch, dtype):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of THIS configuration, or None."""
+    tp = os.path.join(REPO, "profiles", "roofline_traffic.json")
+    if not os.path.exists(tp):
+        return None
+    rows = json.load(open(tp))
+    key = "%dx%d_b%d_%s" % (blocks, hidden, batch, dtype)
+    row = rows.get(key) if isinstance(rows, dict) else None
+    return row.get("dram_bytes_per_launch") if row else None
+
+
 def load_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -64,10 +87,10 @@ def load_peaks():
 
 def make_workload(args, rank):
     from oracle import pyoracle, weights as W
-    boards, idx, off, _ = pyoracle.random_positions(20261019 + 7919 * rank, args.batch, 160)
+    boards, idx, off, raw = pyoracle.random_positions(20261019 + 7919 * rank, args.batch, 160)
     q = pyoracle.static_q(boards)
     blob = W.flatten(W.make_weights(args.blocks, args.hidden, WEIGHT_SEED, "B"), args.blocks, args.hidden)
-    return boards, q, idx, off, blob
+    return boards, q, idx, off, blob, raw
 
 
 class ClockSampler:
@@ -133,7 +156,7 @@ def cpu_reference_module(blocks, hidden):
     return None, "port"
 
 
-def time_cpu_path(args, boards, q, idx, off, blob, budget_s, steps, warmup):
+def time_cpu_path(args, boards, q, idx, off, blob, budget_s, steps, warmup, moves_raw=None):
     """Reference CPU implementation of the path on a bounded sample: encode (C restatement of
     board_to_planes) -> traced OracleNet on libtorch CPU -> exp -> priors (C restatement)."""
     import torch
@@ -153,11 +176,8 @@ def time_cpu_path(args, boards, q, idx, off, blob, budget_s, steps, warmup):
         else:
             logp, v, k = net.forward(blob, args.blocks, args.hidden, planes, q[:n])
             probs = np.exp(logp)
-        for i in range(n):
-            m = idx[off[i]:off[i + 1]]
-            p = probs[i][m]
-            s = p.sum()
-            p = p / s if s > 0 else np.full(len(m), 1.0 / max(len(m), 1), dtype=np.float32)
+        for i in range(n):   # policy_to_move_priors: the C restatement (src/tensor.rs:184-213)
+            pyoracle.policy_to_move_priors(probs[i], moves_raw[off[i]:off[i + 1]], raw[i].w_to_move)
         return n
 
     n = min(256, args.batch)
@@ -188,6 +208,41 @@ def emit(line):
     os.write(_JSON_FD if _JSON_FD is not None else 1, data)
 
 
+def resident_rate(ev, boards, q, idx, off, B, iters, warmup=3):
+    """Flushed-L2 resident rate of one batch size: median CUDA-event time of `iters` replays -> (evals/s, us)."""
+    ev.stage_leaves(boards[:B], q[:B], idx[:off[B]], off[:B + 1])
+    ev.time_resident(warmup, material_on=True, flush_l2=True)
+    ms = ev.time_resident(iters, material_on=True, flush_l2=True)
+    med = float(np.median(ms))
+    return B / (med * 1e-3), med * 1e3
+
+
+def config4_record(cb, local_rank, peaks):
+    """BASELINE.json configs[3] on this GPU: OracleNet 10x256, batch 2048.  fp16 operands: on random-init weights the 21
+    bf16 layers of this net land at 1.2e-2 against the 1e-2 value bar, fp16 (same tensor rate) meets it — DESIGN.md §5."""
+    from oracle import pyoracle, weights as W
+    blocks, hidden, B, dtype = 10, 256, 2048, "fp16"
+    boards, idx, off, _ = pyoracle.random_positions(4242, B, 160)
+    q = pyoracle.static_q(boards)
+    blob = W.flatten(W.make_weights(blocks, hidden, WEIGHT_SEED, "B"), blocks, hidden)
+    ev = cb.Evaluator(blocks, hidden, dtype, device=local_rank)
+    ev.load_weights(blob)
+    rate, us = resident_rate(ev, boards, q, idx, off, B, 12)
+    ev.time_tower(2)
+    tower_ms, n_tower = ev.time_tower(8)
+    sus_ms, sus_n = ev.time_sustained(1.0)
+    launches = ev.launches_per_forward()
+    ev.close()
+    sustained, burst, _ = peaks
+    tower_tf = tower_flops_per_position(blocks, hidden) * B / (float(tower_ms.mean()) * 1e-3) / 1e12
+    return {"workload": workload_label(blocks, hidden, B), "dtype": dtype, "value": rate, "unit": UNIT, "us_per_forward": us,
+            "value_sustained": B * sus_n / (sus_ms * 1e-3), "gpu_launches_per_forward": launches,
+            "roofline": {"bound": "tensor", "kernel": "tower_umma_kernel<256> (conv tower, %d launch/step)" % n_tower,
+                         "achieved": tower_tf, "peak": burst, "unit": "TFLOP/s", "frac": tower_tf / burst,
+                         "traffic": measured_traffic(blocks, hidden, B, dtype)},
+            "parity": "tests/test_gpu_parity.py::test_tensor_core_modes_match_reference[10x256_B-fp16]: |dV| <= 1e-2, KL <= 1e-4"}
+
+
 def main():
     global _JSON_FD
     sys.stdout.flush()
@@ -203,7 +258,8 @@ def main():
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--selfplay-seconds", type=float, default=3.0, help="seconds per self-play pool shape (two are run); 0 disables the section")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 10x256 batch-2048 sub-record (N = 1 only)")
+    ap.add_argument("--selfplay-seconds", type=float, default=3.0, help="seconds per self-play pool shape; 0 disables the section")
     ap.add_argument("--selfplay-games", type=int, default=1024)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -211,9 +267,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = "configs[1]: batched leaf eval, OracleNet %dx%d, batch %d, one batch per GPU" % (
-        args.blocks, args.hidden, args.batch)
-    config = {"workload": workload, "batch_per_gpu": args.batch, "blocks": args.blocks, "hidden": args.hidden,
+    config = {"workload": workload_label(args.blocks, args.hidden, args.batch), "batch_per_gpu": args.batch,
+              "blocks": args.blocks, "hidden": args.hidden,
               "positions": "seeded random legal playouts (oracle chess substrate), material dM = static PeSTO/100",
               "weights": "reference init law, heads de-zeroed (variant B, numpy seed %d)" % WEIGHT_SEED,
               "l2": "flushed (256 MiB rewrite) between timed steps", "material_on": True}
@@ -221,8 +276,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        boards, q, idx, off, blob = make_workload(args, 0)
-        cpu, ms = time_cpu_path(args, boards, q, idx, off, blob, 150.0, args.steps, args.warmup)
+        boards, q, idx, off, blob, raw = make_workload(args, 0)
+        cpu, ms = time_cpu_path(args, boards, q, idx, off, blob, 150.0, args.steps, args.warmup, raw)
         line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -247,12 +302,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    boards, q, idx, off, blob = make_workload(args, rank)
+    boards, q, idx, off, blob, raw = make_workload(args, rank)
     ev = cb.Evaluator(args.blocks, args.hidden, args.dtype, device=local_rank)
     ev.load_weights(blob)
     B, K, W = args.batch, args.steps, args.warmup
+    peaks = load_peaks()
 
-    # ---- device-resident throughput (value)
+    # ---- device-resident throughput (value): exactly K timed steps
     ev.stage_leaves(boards, q, idx, off)
     ev.time_resident(W, material_on=True, flush_l2=True)
     barrier()
@@ -268,6 +324,13 @@ def main():
     pri, v, vf, kk = ev.read_resident()
     assert np.isfinite(pri).all() and np.isfinite(vf).all() and np.abs(vf).max() <= 1.0
 
+    # ---- sustained: the same forward back to back for >= 2 s (no flush, no pause: the power-capped rate)
+    barrier()
+    clocks.active = True
+    sus_ms, sus_n = ev.time_sustained(2.0)
+    clocks.active = False
+    barrier()
+
     # ---- roofline of the dominant kernel: the fused persistent conv tower (one launch per step)
     ev.time_tower(3)
     tower_ms, n_tower = ev.time_tower(max(K // 2, 5))
@@ -278,12 +341,11 @@ def main():
     else:
         flops_launch = tower_flops_per_position(args.blocks, args.hidden) * B
 
-    # ---- end to end through the public C ABI with host buffers: every step copies boards / q / CSR
-    # host->device and priors / values device->host inside the timed region.  Two evaluator handles
-    # (independent streams, the ABI's documented multi-handle use) are driven by two host threads so
-    # one handle's copies overlap the other's kernels; the single-handle synchronous rate is kept too.
-    # (host buffers and argument pointers are set up once, as a host that reuses its request buffers would;
-    #  every call still copies inputs H2D and results D2H inside cb_eval_leaves)
+    # ---- end to end through the public C ABI with host buffers: every step copies boards / q / CSR host->device and
+    # priors / values device->host inside the timed region.  ONE host thread drives two evaluator handles (independent
+    # streams, the ABI's documented multi-handle use) with cb_eval_leaves_submit / _wait, so one handle's copies run
+    # under the other's kernel; the single-handle synchronous rate is kept too.  (Host buffers and argument pointers
+    # are set up once, as a host that reuses its request buffers would.)
     run1 = ev.prepared_eval_leaves(boards, q, idx, off)
     for _ in range(W):
         run1()
@@ -297,115 +359,191 @@ def main():
     clocks.active = False
     ev2 = cb.Evaluator(args.blocks, args.hidden, args.dtype, device=local_rank)
     ev2.load_weights(blob)
-    run2 = ev2.prepared_eval_leaves(boards, q, idx, off)
-    for _ in range(W):
-        run2()
-    counts = [K - K // 2, K // 2]
+    sub = [ev.prepared_submit_wait(boards, q, idx, off), ev2.prepared_submit_wait(boards, q, idx, off)]
 
-    def pump(e, n):
-        run = run1 if e is ev else run2
-        for _ in range(n):
-            run()
+    def pipelined(n):
+        """n batches through the two handles from this one thread, at most one batch in flight per handle."""
+        sub[0][0]()
+        for i in range(1, n):
+            sub[i & 1][0]()
+            sub[(i - 1) & 1][1]()
+        return sub[(n - 1) & 1][1]()
+    pipelined(max(W, 4))
     barrier()
-    threads = [threading.Thread(target=pump, args=(e, n)) for e, n in zip((ev, ev2), counts)]
     clocks.active = True
     t0 = time.perf_counter()
-    [t.start() for t in threads]
-    [t.join() for t in threads]
+    out = pipelined(K)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the same loop for >= 0.5 s whatever --steps says (a short K leaves a timed region of a few ms)
+    n_long = max(K, int(0.5 / max(e2e_s / K, 1e-6)))
+    t0 = time.perf_counter()
+    pipelined(n_long)
+    torch.cuda.synchronize()
+    e2e_long_s = time.perf_counter() - t0
     clocks.active = False
     in_region = len(clocks.rows)
-    if in_region < 5:
-        # short timed regions (few steps): top the sample up under the same load, outside the timing
-        clocks.active = True
-        ev.time_resident(max(200, K), material_on=True, flush_l2=True)
-        clocks.active = False
     clocks.__exit__()
     clk = clocks.summary()
-    clk["regions"] = ("NVML every 5 ms during the resident loop and both end-to-end loops (the timed regions): %d samples; "
-                      "%d more under an untimed replay of the resident loop" % (in_region, len(clocks.rows) - in_region))
+    clk["regions"] = ("NVML every 5 ms during the resident loop, the sustained loop and the end-to-end loops (the timed "
+                      "regions): %d samples" % in_region)
     barrier()
     h2d = int(boards.nbytes + q.nbytes + idx.nbytes + off.nbytes)
     d2h = int(out[0].nbytes + out[1].nbytes + out[2].nbytes + out[3].nbytes)
 
-    # ---- self-play pool on this GPU (config 3 shape: 200 sims/move, 1024 concurrent games, vanilla mode):
-    # tree operations on the device (select / expand / backup / move choice as two kernels around the forward
-    # kernel, no host work per simulation), and beside it the host-driven pool (two half-pools of 512 games,
-    # each with its own evaluator handle) whose rate depends on the host cores available per GPU.
+    # ---- batch sweep (config 2's small end: the reference's server batches <= 16 by default) and config 4, rank 0 of N = 1
+    sweep = cfg4 = None
+    if world == 1:
+        sweep = {}
+        for b_ in (1, 16, 128, 256):
+            if b_ <= B:
+                rate, us = resident_rate(ev, boards, q, idx, off, b_, 30)
+                sweep[str(b_)] = {"evals_per_s": rate, "us_per_forward": us}
+        ev.stage_leaves(boards, q, idx, off)
+        if not args.no_config4 and (args.blocks, args.hidden) == (6, 128):
+            cfg4 = config4_record(cb, local_rank, peaks)
+
+    # ---- self-play pool on this GPU (config 3 shape: 200 sims/move, 1024 concurrent games, vanilla mode): the
+    # reference's search (tactical-first phase, f64 PUCT, tree reuse) with the tree operations on the device, and beside
+    # it the host-driven pool (two half-pools, each with its own evaluator handle).
     sp = sp_host = sp_koth = sp_two = sp_two_pe = sp_rec = None
     nthreads = max(1, (os.cpu_count() or 1) // world - 2)
+    rec_path = "/dev/shm/caissa_bench_samples_r%d.bin" % rank
     if args.selfplay_seconds > 0:
+        T = args.selfplay_seconds
         barrier()
-        sp = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=1 + rank,
-                         max_seconds=args.selfplay_seconds, pipeline=3)
+        sp = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=1 + rank, max_seconds=T, pipeline=3)
         barrier()
         sp_host = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=101 + rank,
-                              max_seconds=args.selfplay_seconds, threads=nthreads, pipeline=2, aux=ev2)
+                              max_seconds=T, threads=nthreads, pipeline=2, aux=ev2)
         barrier()
         # config 5 shape: King-of-the-Hill rules, 800 simulations per move
         sp_koth = ev.selfplay(games=args.selfplay_games, sims_per_move=800, material_on=False, koth=True, seed=201 + rank,
-                              max_seconds=args.selfplay_seconds, pipeline=3)
+                              max_seconds=T, pipeline=3)
         barrier()
         # two pools of that many games each: one pool's tree kernel runs beside the other pool's forward kernel;
         # vanilla, and with the material term from the principal-exchange q-search run on the device for every leaf
         sp_two = ev.selfplay(games=2 * args.selfplay_games, sims_per_move=200, material_on=False, seed=301 + rank,
-                             max_seconds=args.selfplay_seconds, pipeline=4)
+                             max_seconds=T, pipeline=4)
         barrier()
         sp_two_pe = ev.selfplay(games=2 * args.selfplay_games, sims_per_move=200, material_on=True, qsearch="pe",
-                                seed=401 + rank, max_seconds=args.selfplay_seconds, pipeline=4)
+                                seed=401 + rank, max_seconds=T, pipeline=4)
         barrier()
         # the one-pool run again with the training samples produced: every finished game is assembled on the host into
-        # the reference's 5763-f32 records and written out (to /dev/null: record building and write calls, no storage)
+        # the reference's 5763-f32 records and written to a file (tmpfs) — the records the NCCL gather below moves
+        if os.path.exists(rec_path):
+            os.remove(rec_path)
         sp_rec = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=501 + rank,
-                             max_seconds=args.selfplay_seconds, pipeline=3, sample_path="/dev/null")
+                             max_seconds=T, pipeline=3, sample_path=rec_path)
         barrier()
+
+    # ---- off the hot path: the exchanges the multi-GPU design has (NCCL over NVLink), with REAL data: the sample records
+    # this rank's self-play just wrote are gathered (all ranks -> every rank), checked bit for bit on rank 0, then gathered
+    # again on a side thread WHILE a self-play pool runs (the cost of the exchange to the hot path); a new weight blob is
+    # broadcast from rank 0, loaded by every rank's evaluator and spot-checked against rank 0's outputs.
+    nccl = None
+    if world > 1 and sp_rec is not None:
+        import zlib
+        from caissa_b200 import distributed as D
+        local = np.fromfile(rec_path, dtype=np.float32).reshape(-1, D.RECORD_FLOATS) if os.path.exists(rec_path) else \
+            np.zeros((0, D.RECORD_FLOATS), dtype=np.float32)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        allrec = D.gather_samples(local)
+        torch.cuda.synchronize()
+        gather_s = time.perf_counter() - t0
+        sums = [None] * world
+        dist.all_gather_object(sums, (int(local.shape[0]), zlib.crc32(local.tobytes())))
+        ok = True
+        if rank == 0:
+            lo = 0
+            for n_r, crc in sums:
+                ok = ok and zlib.crc32(allrec[lo:lo + n_r].tobytes()) == crc
+                lo += n_r
+            ok = ok and lo == allrec.shape[0]
+        # the gather under load: a side thread gathers this rank's records in a FIXED number of flushes (the same on every
+        # rank: collectives must pair up) spread over the run of a self-play pool
+        n_flush = max(1, int(args.selfplay_seconds * 25))
+        flushes = [0]
+
+        def gather_loop():
+            torch.cuda.set_device(local_rank)
+            chunk = local[:max(1, min(local.shape[0], 256))]
+            for _ in range(n_flush):          # 25 flushes/s x 256 records/rank: above the produced rate
+                D.gather_samples(chunk)
+                flushes[0] += 1
+                time.sleep(0.02)
+        dist.barrier()
+        th = threading.Thread(target=gather_loop)
+        th.start()
+        sp_g = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=1 + rank,
+                           max_seconds=args.selfplay_seconds, pipeline=3)
+        th.join()
+        # weight refresh: rank 0 draws a new blob, NCCL broadcast, every rank loads it and evaluates the same 8 positions
+        from oracle import weights as Wt
+        new_blob = Wt.flatten(Wt.make_weights(args.blocks, args.hidden, WEIGHT_SEED + 1, "B"), args.blocks, args.hidden) \
+            if rank == 0 else None
+        t0 = time.perf_counter()
+        got = D.broadcast_weights(new_blob, ev.weight_count())
+        bcast_s = time.perf_counter() - t0
+        ev2.load_weights(got)
+        b0, q0, i0, o0, _, _ = make_workload(argparse.Namespace(batch=8, blocks=args.blocks, hidden=args.hidden), 0)
+        _, v0, _, _ = ev2.eval_leaves(b0, q0, i0, o0)
+        vs = [None] * world
+        dist.all_gather_object(vs, v0.tobytes())
+        nccl = {"gather_records": int(allrec.shape[0]), "gather_seconds": gather_s,
+                "gather_GBps": allrec.nbytes / gather_s / 1e9, "gather_bit_equal_on_rank0": bool(ok),
+                "records_per_s_produced": None, "selfplay_seconds_with_gather": sp_g["seconds"], "selfplay_sims_with_gather": sp_g["sims"],
+                "gather_flushes_during_selfplay": int(flushes[0]),
+                "weights_broadcast_floats": int(got.size), "weights_broadcast_seconds": bcast_s,
+                "weights_spot_check_identical_on_all_ranks": all(x == vs[0] for x in vs)}
     ev2.close()
 
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3, launch_ms, e2e_sync_s * 1e3, sp["seconds"] if sp else 0.0,
                       sp_host["seconds"] if sp_host else 0.0, sp_koth["seconds"] if sp_koth else 0.0,
                       sp_two["seconds"] if sp_two else 0.0, sp_two_pe["seconds"] if sp_two_pe else 0.0,
-                      sp_rec["seconds"] if sp_rec else 0.0],
+                      sp_rec["seconds"] if sp_rec else 0.0, sus_ms / max(sus_n, 1), e2e_long_s * 1e3 / n_long,
+                      nccl["selfplay_seconds_with_gather"] if nccl else 0.0],
                      dtype=torch.float64, device="cuda")
     tot = torch.tensor([sp["sims"] if sp else 0, sp["nn_evals"] if sp else 0, sp_host["sims"] if sp_host else 0,
                         sp_koth["sims"] if sp_koth else 0, sp_two["sims"] if sp_two else 0,
                         sp_two_pe["sims"] if sp_two_pe else 0, sp_rec["sims"] if sp_rec else 0,
-                        sp_rec["samples"] if sp_rec else 0],
+                        sp_rec["samples"] if sp_rec else 0, nccl["selfplay_sims_with_gather"] if nccl else 0,
+                        sum(x["overflow"] for x in (sp, sp_koth, sp_two, sp_two_pe, sp_rec) if x)],
                        dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     (dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds, sp_host_seconds, sp_koth_seconds, sp_two_seconds,
-     sp_two_pe_seconds, sp_rec_seconds) = [float(x) for x in t.tolist()]
+     sp_two_pe_seconds, sp_rec_seconds, sus_ms_per_launch, e2e_long_ms_per_step, sp_g_seconds) = [float(x) for x in t.tolist()]
     value = world * B * K / (dev_ms * 1e-3)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
-    # off the hot path: the one exchange the multi-GPU design has (training-sample gather over NCCL)
-    gathered = None
-    if world > 1:
-        from caissa_b200 import distributed as D
-        rec = np.zeros((4, D.RECORD_FLOATS), dtype=np.float32) + rank
-        gathered = int(D.gather_samples(rec).shape[0])
 
     if rank == 0:
-        sustained, burst, how = load_peaks()
+        sustained, burst, how = peaks
         achieved = flops_launch / (launch_ms * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(REPO, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        value_sustained = world * B / (sus_ms_per_launch * 1e-3)
+        sus_tf = value_sustained / world * FLOPS_PER_EVAL.get((args.blocks, args.hidden), 0) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config,
+            "value_sustained": value_sustained,
+            "sustained": {"seconds": 2.0, "launches": sus_n, "us_per_forward": sus_ms_per_launch * 1e3,
+                          "whole_path_tflops": sus_tf, "peak": sustained, "frac": sus_tf / sustained,
+                          "note": "the staged forward replayed back to back, no L2 flush, no pause: the power-capped rate; "
+                                  "denominator = bf16_tflops_sustained of MEASURED_PEAKS.json"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K,
-                    "api": "cb_eval_leaves with host buffers, 2 handles x 2 host threads per GPU",
+                    "api": "cb_eval_leaves_submit / cb_eval_leaves_wait with host buffers, 2 handles driven by ONE host thread per GPU",
+                    "sustained_value": world * B / (e2e_long_ms_per_step * 1e-3), "sustained_steps": n_long,
                     "single_handle_sync_value": world * B * K / (e2e_sync_ms * 1e-3)},
             "gpu_launches": int(ev.launches_per_forward() * K * world),
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
-                         "frac": achieved / burst, "traffic": traffic,
+                         "frac": achieved / burst, "traffic": measured_traffic(args.blocks, args.hidden, B, args.dtype),
                          "kernel": ("tower_r_umma_kernel<%s> (whole forward: planes, conv tower, policy and value heads; "
                                     "%d launch/step)" % (args.dtype, n_tower)) if single_launch else
                                    ("tower_umma_kernel<%d> (whole conv tower, %d launch/step)" % (args.hidden, n_tower)),
@@ -416,12 +554,18 @@ def main():
             "whole_path_tflops": value / world * FLOPS_PER_EVAL.get((args.blocks, args.hidden), 0) / 1e12,
             "wall_s_timed_region": wall,
         }
+        if sweep:
+            line["batch_sweep"] = sweep
+        if cfg4:
+            line["config4"] = cfg4
         if sp:
             line["selfplay"] = {"sims_per_s": float(tot[0].item()) / sp_seconds,
                                 "nn_evals_per_s": float(tot[1].item()) / sp_seconds,
-                                "games_per_gpu": args.selfplay_games, "sims_per_move": 200, "mode": "vanilla (config 5 rules: "
-                                "Tier 1 off, material off), one leaf in flight per game; tree operations on the device "
-                                "(cb_selfplay_run pipeline 3: select, forward, expand/play kernels in one CUDA graph)",
+                                "games_per_gpu": args.selfplay_games, "sims_per_move": 200,
+                                "mode": "vanilla (config 5 rules: Tier 1 off, material off), one leaf in flight per game; the "
+                                        "reference's search — tactical-first phase, root force-visit, f64 PUCT, tree reuse — with "
+                                        "the tree operations on the device (cb_selfplay_run pipeline 3: select, forward, "
+                                        "expand/play kernels in one CUDA graph); trees bit-equal to oracle/mcts.c (tests)",
                                 "seconds": sp_seconds, "mean_batch": sp["mean_batch"],
                                 "forward_fraction": sp["eval_seconds"] / max(sp["seconds"], 1e-9),
                                 "host_driven_sims_per_s": float(tot[2].item()) / max(sp_host_seconds, 1e-9),
@@ -430,17 +574,25 @@ def main():
                                 "two_pools_material_pe_sims_per_s": float(tot[5].item()) / max(sp_two_pe_seconds, 1e-9),
                                 "with_sample_records_sims_per_s": float(tot[6].item()) / max(sp_rec_seconds, 1e-9),
                                 "sample_records_per_s": float(tot[7].item()) / max(sp_rec_seconds, 1e-9),
+                                "arena_overflows": int(tot[9].item()),
                                 "two_pools_games_per_gpu": 2 * args.selfplay_games,
                                 "two_pools_mode": "cb_selfplay_run pipeline 4: two pools of games_per_gpu games alternate, "
                                                   "the tree kernel of one beside the forward kernel of the other; "
                                                   "material_pe: dM by the principal-exchange line on the device",
                                 "host_threads_per_gpu": nthreads}
-        if gathered is not None:
-            line["nccl_sample_gather_records"] = gathered
+        if nccl:
+            nccl["records_per_s_produced"] = float(tot[7].item()) / max(sp_rec_seconds, 1e-9)
+            nccl["sims_per_s_with_gather_running"] = float(tot[8].item()) / max(sp_g_seconds, 1e-9)
+            nccl["sims_per_s_without"] = float(tot[0].item()) / sp_seconds
+            for k_ in ("selfplay_seconds_with_gather", "selfplay_sims_with_gather"):
+                nccl.pop(k_)
+            line["nccl_exchange"] = nccl
         if world == 1 and not args.no_cpu_baseline:
-            cpu, _ = time_cpu_path(args, boards, q, idx, off, blob, 20.0, 3, 1)
+            cpu, _ = time_cpu_path(args, boards, q, idx, off, blob, 20.0, 3, 1, raw)
             line["cpu_baseline"] = cpu
         emit(line)
+    if os.path.exists(rec_path):
+        os.remove(rec_path)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

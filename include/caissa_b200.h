@@ -143,6 +143,9 @@ int cb_pst_eval_cp(cb_handle* h, const cb_board* boards, int B, int32_t* cp);
 int cb_stage_leaves(cb_handle* h, const cb_board* boards, const float* q, int B,
                     const uint16_t* move_idx, const uint32_t* move_off);
 int cb_time_resident(cb_handle* h, int material_on, int iters, int flush_l2, float* ms_each);
+/* The staged forward replayed back to back (no flush, no pause) for at least `seconds`: the SUSTAINED rate, i.e. under the
+ * board's power cap.  Device time of all launches (CUDA events around chunks of 256) and their number. */
+int cb_time_sustained(cb_handle* h, int material_on, double seconds, float* ms_total, int* launches);
 int cb_time_conv_layers(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches);
 /* per_layer_ms[2*blocks+2] (nullable): mean event time of every conv launch, start conv first. */
 int cb_time_conv_layers_detail(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches,

@@ -169,6 +169,8 @@ SIGNATURES = {
     "cb_debug_device_light_gates": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_stage_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_time_resident": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
+    "cb_time_sustained": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_float),
+                                         ctypes.POINTER(ctypes.c_int)]),
     "cb_time_conv_layers": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
     "cb_time_conv_layers_detail": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP]),
     "cb_time_tower": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
@@ -390,6 +392,12 @@ class Evaluator:
         ms = np.zeros(iters, dtype=np.float32)
         self._check(self._L.cb_time_resident(self._h, int(material_on), iters, int(flush_l2), _ptr(ms)))
         return ms
+
+    def time_sustained(self, seconds, material_on=True):
+        """-> (total device ms, launches) of back-to-back replays of the staged forward for >= seconds."""
+        ms, n = ctypes.c_float(0), ctypes.c_int(0)
+        self._check(self._L.cb_time_sustained(self._h, int(material_on), float(seconds), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     def time_conv_layers(self, iters):
         ms = ctypes.c_float(0)

@@ -1407,6 +1407,38 @@ int cb_time_resident(cb_handle* h, int material_on, int iters, int flush_l2, flo
     return CB_OK;
 }
 
+int cb_time_sustained(cb_handle* h, int material_on, double seconds, float* ms_total, int* launches) {
+    if (!h || seconds <= 0 || !ms_total || !launches) return CB_EINVAL;
+    if (!h->staged_B) return fail(h, CB_ESTATE, "nothing staged: call cb_stage_leaves first");
+    CB_CUDA(h, cudaSetDevice(h->device));
+    constexpr int kChunk = 256;
+    cudaEvent_t e0, e1;
+    CB_CUDA(h, cudaEventCreate(&e0));
+    CB_CUDA(h, cudaEventCreate(&e1));
+    double total = 0.0;
+    int n = 0, rc = CB_OK;
+    cudaError_t se = cudaSuccess;
+    const auto t0 = std::chrono::steady_clock::now();
+    do {
+        cudaEventRecord(e0, h->stream);
+        for (int i = 0; i < kChunk && !rc; ++i) rc = run_forward(h, h->staged_B, false, h->staged_moves > 0, material_on, true);
+        cudaEventRecord(e1, h->stream);
+        se = cudaStreamSynchronize(h->stream);
+        if (rc || se != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total += ms;
+        n += kChunk;
+    } while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < seconds);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    CB_CUDA(h, se);
+    *ms_total = (float)total;
+    *launches = n;
+    return CB_OK;
+}
+
 int cb_time_conv_layers(cb_handle* h, int iters, float* conv_ms_total, int* n_conv_launches) {
     return cb_time_conv_layers_detail(h, iters, conv_ms_total, n_conv_launches, nullptr);
 }
