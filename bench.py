@@ -324,14 +324,7 @@ def main():
     pri, v, vf, kk = ev.read_resident()
     assert np.isfinite(pri).all() and np.isfinite(vf).all() and np.abs(vf).max() <= 1.0
 
-    # ---- sustained: the same forward back to back for >= 2 s (no flush, no pause: the power-capped rate)
-    barrier()
-    clocks.active = True
-    sus_ms, sus_n = ev.time_sustained(2.0)
-    clocks.active = False
-    barrier()
-
-    # ---- roofline of the dominant kernel: the fused persistent conv tower (one launch per step)
+    # ---- roofline of the dominant kernel: the fused persistent conv tower (one launch per step), timed alone like `value`
     ev.time_tower(3)
     tower_ms, n_tower = ev.time_tower(max(K // 2, 5))
     launch_ms = float(tower_ms.mean())
@@ -340,6 +333,14 @@ def main():
         flops_launch = FLOPS_PER_EVAL[(args.blocks, args.hidden)] * B
     else:
         flops_launch = tower_flops_per_position(args.blocks, args.hidden) * B
+
+    # ---- sustained: the same forward back to back for >= 2 s (no flush, no pause: the power-capped rate)
+    barrier()
+    clocks.active = True
+    sus_ms, sus_n = ev.time_sustained(2.0)
+    clocks.active = False
+    barrier()
+    time.sleep(0.5)                                    # let the board cool before the next timed region
 
     # ---- end to end through the public C ABI with host buffers: every step copies boards / q / CSR host->device and
     # priors / values device->host inside the timed region.  ONE host thread drives two evaluator handles (independent
@@ -450,7 +451,7 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
-        allrec = D.gather_samples(local)
+        allrec = D.gather_samples(local, dst=0)
         torch.cuda.synchronize()
         gather_s = time.perf_counter() - t0
         sums = [None] * world
@@ -469,9 +470,9 @@ def main():
 
         def gather_loop():
             torch.cuda.set_device(local_rank)
-            chunk = local[:max(1, min(local.shape[0], 256))]
-            for _ in range(n_flush):          # 25 flushes/s x 256 records/rank: above the produced rate
-                D.gather_samples(chunk)
+            chunk = local[:max(1, min(local.shape[0], 512))]
+            for _ in range(n_flush):          # 25 flushes/s x 512 records/rank (12.8 k records/s/rank): above the produced rate
+                D.gather_samples(chunk, dst=0)
                 flushes[0] += 1
                 time.sleep(0.02)
         dist.barrier()
@@ -492,8 +493,10 @@ def main():
         _, v0, _, _ = ev2.eval_leaves(b0, q0, i0, o0)
         vs = [None] * world
         dist.all_gather_object(vs, v0.tobytes())
-        nccl = {"gather_records": int(allrec.shape[0]), "gather_seconds": gather_s,
-                "gather_GBps": allrec.nbytes / gather_s / 1e9, "gather_bit_equal_on_rank0": bool(ok),
+        n_all = int(sum(n_r for n_r, _ in sums))
+        nccl = {"gather_records": n_all, "gather_seconds": gather_s,
+                "gather_GBps": n_all * D.RECORD_FLOATS * 4 / gather_s / 1e9, "gather_bit_equal_on_rank0": bool(ok),
+                "gather": "every rank's finished-game records of the run above -> rank 0 (NCCL gather), device staging included",
                 "records_per_s_produced": None, "selfplay_seconds_with_gather": sp_g["seconds"], "selfplay_sims_with_gather": sp_g["sims"],
                 "gather_flushes_during_selfplay": int(flushes[0]),
                 "weights_broadcast_floats": int(got.size), "weights_broadcast_seconds": bcast_s,

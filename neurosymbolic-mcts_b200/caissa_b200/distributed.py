@@ -27,23 +27,33 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_samples(local):
-    """local: float32 [n_local, 5763] (n_local may differ per rank, may be 0) -> float32 [sum n, 5763],
-    rank-major order, identical on every rank."""
+def gather_samples(local, dst=None):
+    """local: float32 [n_local, 5763] (n_local may differ per rank, may be 0) -> float32 [sum n, 5763] in rank-major
+    order.  dst=None: all-gather, identical result on every rank.  dst=r: gathered on rank r only (the trainer's rank;
+    the reference writes one file per generation, src/training_data.rs:24-60) — the other ranks return an empty array and
+    only send, so the exchange costs a rank its own records once."""
     local = np.ascontiguousarray(local, dtype=np.float32).reshape(-1, RECORD_FLOATS)
     dev = _device()
-    world = dist.get_world_size()
+    world, rank = dist.get_world_size(), dist.get_rank()
     counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    counts[dist.get_rank()] = local.shape[0]
+    counts[rank] = local.shape[0]
     dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    counts = counts.cpu()
     n_max = int(counts.max().item())
     if n_max == 0:
         return np.zeros((0, RECORD_FLOATS), dtype=np.float32)
     block = torch.zeros((n_max, RECORD_FLOATS), dtype=torch.float32, device=dev)
     if local.shape[0]:
         block[:local.shape[0]] = torch.from_numpy(local).to(dev)
-    out = torch.empty((world, n_max, RECORD_FLOATS), dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(out, block) if dev.type == "cuda" else dist.all_gather(list(out.unbind(0)), block)
+    if dst is None:
+        out = torch.empty((world, n_max, RECORD_FLOATS), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(out, block) if dev.type == "cuda" else dist.all_gather(list(out.unbind(0)), block)
+    else:
+        parts = [torch.empty_like(block) for _ in range(world)] if rank == dst else None
+        dist.gather(block, parts, dst=dst)
+        if rank != dst:
+            return np.zeros((0, RECORD_FLOATS), dtype=np.float32)
+        out = torch.stack(parts, 0)
     out = out.cpu().numpy()
     return np.concatenate([out[r, :int(counts[r].item())] for r in range(world)], axis=0)
 

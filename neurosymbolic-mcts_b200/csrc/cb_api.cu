@@ -1624,9 +1624,12 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     mp.shuffle = cfg->shuffle_children;
     mp.mock_eval = cfg->mock_eval;
     mp.search_only = dbg ? 1 : 0;
-    {   // a move adds sims_per_move expansions of ~35 (at most 218) children to the subtree kept from the last move
-        const long long want = (long long)cfg->sims_per_move * 160;
-        mp.node_cap = (uint32_t)(want < 32768 ? 32768 : want > 262144 ? 262144 : want);
+    {   // a move adds sims_per_move expansions of ~35 (at most 218) children to the subtree kept from the last move; when
+        // the played child holds a share s of the visits the tree settles near new / (1 - s) nodes, so leave room for
+        // s ~ 0.9 (32-byte nodes: 1024 games x 2 arenas x 65536 nodes = 4.3 GB).  A full arena is counted
+        // (cb_selfplay_stats.overflow): the leaf then stays unexpanded and is evaluated again later.
+        const long long want = (long long)cfg->sims_per_move * 400;
+        mp.node_cap = (uint32_t)(want < 65536 ? 65536 : want > 524288 ? 524288 : want);
     }
     mp.seed = cfg->seed;
     std::vector<void*> owned;

@@ -20,9 +20,10 @@ def _worker(rank, world, port, out_dir):
     n_local = [3, 0, 5][rank % 3] if world > 1 else 3
     local = rng.random((n_local, D.RECORD_FLOATS), dtype=np.float32) + rank
     allrec = D.gather_samples(local)
+    on0 = D.gather_samples(local, dst=0)
     blob = D.broadcast_weights(np.arange(1000, dtype=np.float32) if rank == 0 else None, 1000)
     lo, hi = D.shard_range(1024 + 1, rank, world)
-    np.savez(os.path.join(out_dir, "r%d.npz" % rank), local=local, allrec=allrec, blob=blob, lo=lo, hi=hi)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), local=local, allrec=allrec, on0=on0, blob=blob, lo=lo, hi=hi)
     dist.destroy_process_group()
 
 
@@ -34,5 +35,6 @@ def test_two_rank_gloo_sample_gather_and_weight_broadcast(tmp_path):
     for i in range(world):
         assert np.array_equal(r[i]["allrec"], want)                 # rank-major, ragged counts (3 and 0)
         assert np.array_equal(r[i]["blob"], np.arange(1000, dtype=np.float32))
+        assert np.array_equal(r[i]["on0"], want) if i == 0 else r[i]["on0"].shape[0] == 0   # gather to the trainer's rank
     # the shards of the independent units tile [0, n) exactly
     assert r[0]["lo"] == 0 and r[0]["hi"] == r[1]["lo"] and r[1]["hi"] == 1025
