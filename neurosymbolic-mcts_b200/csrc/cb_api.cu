@@ -23,6 +23,7 @@
 #include "policy_umma.cuh"
 #include "tower_umma.cuh"
 #include "tower_r_umma.cuh"
+#include "tower_r2_umma.cuh"
 #include "mcts_device.cuh"
 
 namespace {
@@ -44,6 +45,7 @@ struct ConvLayer {
     float* bias = nullptr;
     CUtensorMap tm_w;
     CUtensorMap tm_w_half;   // 64-row box (cluster mode of the resident tower)
+    CUtensorMap tm_w128;     // 128-row box: one CTA's share of a stage in the resident kernels (all of it for 128 channels)
 };
 
 }  // namespace
@@ -215,6 +217,10 @@ int make_weight_map(cb_handle* h, ConvLayer& L) {
     r = h->encode_tiled(&L.tm_w_half, dt, 2, L.w16, dims, strides, box_half, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(half weights) failed: " + std::to_string((int)r));
+    const cuuint32_t box128[2] = {64, 128};
+    r = h->encode_tiled(&L.tm_w128, dt, 2, L.w16, dims, strides, box128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(128-row weights) failed: " + std::to_string((int)r));
     return CB_OK;
 }
 
@@ -279,7 +285,7 @@ int ensure_capacity(cb_handle* h, int B) {
             if ((rc = make_act_map(h, &h->tm_act_ld[i], h->d_act[i], h->hid, cap, 10))) return rc;
             if ((rc = make_act_map(h, &h->tm_act_st[i], h->d_act[i], h->hid, cap, 8))) return rc;
         }
-        if (h->hid == 128) {
+        if (h->hid == 128 || h->hid == 256) {
             free_dev(h->d_res_scratch);
             h->d_res_scratch = nullptr;
             CB_CUDA(h, cudaMalloc(&h->d_res_scratch, (size_t)h->sm_count * TowerRCfg::kScratchPerCta * sizeof(uint4)));
@@ -325,24 +331,25 @@ int build_tower_tables(cb_handle* h) {
     CB_CUDA(h, cudaMemcpy(h->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     CB_CUDA(h, cudaMemcpy(h->d_layers, ly.data(), ly.size() * sizeof(TowerLayer), cudaMemcpyHostToDevice));
     h->tower_ready = true;
-    if (h->hid == 128) {
-        // resident tower: map table = weights of the nl conv layers, then the padded p_head; the layer table
-        // ends with the policy head as a one-tap layer
+    if (h->hid == 128 || h->hid == 256) {
+        // resident towers (tower_r_umma.cuh for 128 channels, tower_r2_umma.cuh on CTA pairs for 256): map table = weights
+        // of the nl conv layers (128-row boxes), then the padded p_head; the layer table ends with the policy head as a
+        // one-tap layer
         h->tower_r_ready = false;
         std::vector<CUtensorMap> mr(nl + 1);
-        for (int l = 0; l < nl; ++l) mr[l] = h->convs[l].tm_w;
+        for (int l = 0; l < nl; ++l) mr[l] = h->convs[l].tm_w128;
         mr[nl] = h->tm_pwr;
         std::vector<TowerRLayer> lr(nl + 1);
         memset(lr.data(), 0, sizeof(TowerRLayer) * (nl + 1));
         for (int l = 0; l < nl; ++l) {
             lr[l].w_map = l;
-            lr[l].kc_in = l == 0 ? 1 : 2;
+            lr[l].kc_in = l == 0 ? 1 : h->hid / 64;
             lr[l].mode = (l >= 1 && l < nl - 1 && (l & 1) == 0) ? MODE_SE_RES : MODE_RELU;
             lr[l].bias = h->convs[l].bias;
             lr[l].ntaps = 9;
         }
-        lr[nl].w_map = nl; lr[nl].kc_in = 2; lr[nl].mode = MODE_POLICY; lr[nl].bias = h->p_bias_r;
-        lr[nl].ntaps = 1; lr[nl].w_row_off = -4 * 128;
+        lr[nl].w_map = nl; lr[nl].kc_in = h->hid / 64; lr[nl].mode = MODE_POLICY; lr[nl].bias = h->p_bias_r;
+        lr[nl].ntaps = 1; lr[nl].w_row_off = -4 * h->hid;
         lr[0].save_res = 1;
         for (int i = 0; i < h->blocks; ++i) {
             TowerRLayer& b = lr[2 + 2 * i];
@@ -367,10 +374,12 @@ int build_tower_tables(cb_handle* h) {
 }
 
 // Which tower runs for this handle right now: 0 per-layer launches, 1 the pair-layout fused tower (256-channel nets;
-// 128-channel ones with CB_TOWER_PAIR=1), 3 the shared-memory-resident single-launch forward (128-channel nets).
+// 128-channel ones with CB_TOWER_PAIR=1; 256-channel ones with it too), 3 the shared-memory-resident single-launch forward
+// (128-channel nets), 4 the resident forward on CTA pairs (256-channel nets: tower + policy head, then value_head_kernel).
 int fused_kind(const cb_handle* h) {
     if (h->dtype == CB_DTYPE_FP32 || !h->use_fused || h->layer_limit != 0) return 0;
     if (h->hid == 128 && h->use_resident && h->tower_r_ready) return 3;
+    if (h->hid == 256 && h->use_resident && h->tower_r_ready) return 4;
     return h->tower_ready ? 1 : 0;
 }
 
@@ -469,6 +478,63 @@ int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bo
     }
     CB_CUDA(h, cudaGetLastError());
     return CB_OK;
+}
+
+// 256-channel nets: the resident forward on CTA pairs (tower, p_conv, policy head) followed by the value head's FC layers.
+int launch_tower_r2(cb_handle* h, int B, const PolicyOut& po, int material_on, bool use_q) {
+    TowerR2Params tp = {};
+    tp.boards = h->d_boards;
+    tp.maps = h->d_maps_r;
+    tp.layers = h->d_layers_r;
+    tp.po = po;
+    tp.v_pre = h->d_vpre;
+    tp.num_layers = (int)h->convs.size() + 1;
+    tp.num_boards = B;
+    tp.res_scratch = h->d_res_scratch;
+    tp.dbg_backbone = h->d_dbg_backbone;
+    const int max_pairs = h->sm_count / 2;
+    {   // units of 8 boards (two chains that hide each other's epilogue) in rounds over the pairs; when the last round would
+        // occupy at most half of the pairs, its units are cut into single chains of 4 boards on twice as many pairs
+        const int units8 = (B + 7) / 8, rounds = units8 / max_pairs, last = units8 - rounds * max_pairs;
+        if (last > 0 && last * 2 <= max_pairs) {
+            tp.full_units = rounds * max_pairs;
+            tp.num_units = tp.full_units + (B - tp.full_units * 8 + 3) / 4;
+        } else {
+            tp.full_units = units8;
+            tp.num_units = units8;
+        }
+    }
+    const int pairs = tp.num_units < max_pairs ? tp.num_units : max_pairs;
+    CB_CUDA(h, cudaMemsetAsync(h->d_vpre, 0, (size_t)B * 64 * 4, h->stream));
+    void (*kern)(const TowerR2Params) = h->dtype == CB_DTYPE_BF16 ? tower_r2_umma_kernel<true> : tower_r2_umma_kernel<false>;
+    CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerR2Cfg::kSmemBytes));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(2 * pairs);
+    lc.blockDim = dim3(TowerR2Cfg::kThreads);
+    lc.dynamicSmemBytes = TowerR2Cfg::kSmemBytes;
+    lc.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    CB_CUDA(h, cudaLaunchKernelEx(&lc, kern, tp));
+    const ValueParams vp = value_params(h, B, material_on, use_q, 0);
+    value_head_kernel<<<(B + kValueBoardsPerCta - 1) / kValueBoardsPerCta, 256, 0, h->stream>>>(vp);
+    CB_CUDA(h, cudaGetLastError());
+    return CB_OK;
+}
+
+int launch_tower_r2_staged(cb_handle* h, int B) {
+    PolicyOut po = {};
+    if (h->staged_moves > 0) {
+        po.move_idx = h->d_move_idx;
+        po.move_off = h->d_move_off;
+        po.priors = h->d_priors;
+    }
+    return launch_tower_r2(h, B, po, 1, true);
 }
 
 // The same launch with the outputs of the fast path (priors of the staged legal moves, material on).
@@ -703,8 +769,8 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     const int kind = fused_kind(h);
     const int glog = 1;                                       // boards interleaved per activation group (pairs)
     const int Bpad = (B + (1 << glog) - 1) & ~((1 << glog) - 1);
-    if (kind == 3) {
-        // the resident tower encodes the planes itself
+    if (kind == 3 || kind == 4) {
+        // the resident towers encode the planes themselves
     } else if (h->dtype == CB_DTYPE_FP32) {
         encode_nhwc_f32_kernel<<<(B * 64 + 255) / 256, 256, 0, h->stream>>>(h->d_boards, B, (float*)h->d_x0);
     } else if (h->dtype == CB_DTYPE_BF16) {
@@ -723,6 +789,7 @@ int enqueue_forward(cb_handle* h, int B, bool full_policy, bool csr, int materia
     }
     int rc;
     if (kind == 3) return launch_tower_r(h, B, po, material_on, use_q);   // heads included
+    if (kind == 4) return launch_tower_r2(h, B, po, material_on, use_q);  // policy head included, value FCs follow
     if (kind == 1)
         rc = launch_tower(h, B);
     else
@@ -962,6 +1029,7 @@ int cb_launches_per_forward(const cb_handle* h) {
     if (!h) return 0;
     const int convs = 2 * h->blocks + 2;
     if (fused_kind(h) == 3) return 1;                          // resident tower: planes, convs and both heads in one launch
+    if (fused_kind(h) == 4) return 2;                          // resident pair tower with the policy head, then the value FCs
     if (h->dtype != CB_DTYPE_FP32 && h->use_fused) return 4;  // encode, fused tower, policy, value
     return 1 + convs + (h->dtype == CB_DTYPE_FP32 ? h->blocks : 0) + 2;
 }
@@ -1069,15 +1137,15 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(policy weights) failed");
-            if (H == 128) {
-                // resident tower: p_head as a one-tap "layer": weights [128][H] (73 real rows), bias padded to 128
-                std::vector<uint16_t> wr((size_t)128 * H, 0);
+            if (H == 128 || H == 256) {
+                // resident towers: p_head as a one-tap "layer": weights [H][H] (73 real rows), bias padded to H
+                std::vector<uint16_t> wr((size_t)H * H, 0);
                 memcpy(wr.data(), w16.data(), (size_t)73 * H * 2);
                 if ((rc = upload(wr.data(), wr.size() * 2, &h->p_w16r))) return rc;
-                std::vector<float> br(128, 0.0f);
+                std::vector<float> br(H, 0.0f);
                 memcpy(br.data(), pb, 73 * 4);
-                if ((rc = upload(br.data(), 128 * 4, (void**)&h->p_bias_r))) return rc;
-                const cuuint64_t dims_r[2] = {(cuuint64_t)H, 128};
+                if ((rc = upload(br.data(), (size_t)H * 4, (void**)&h->p_bias_r))) return rc;
+                const cuuint64_t dims_r[2] = {(cuuint64_t)H, (cuuint64_t)H};
                 const cuuint32_t box_r[2] = {64, 128};
                 if (h->encode_tiled(&h->tm_pwr, dt, 2, h->p_w16r, dims_r, strides, box_r, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1484,6 +1552,7 @@ int cb_time_tower(cb_handle* h, int iters, float* ms_each, int* n_launches) {
     for (int i = 0; i < iters && !rc; ++i) {
         CB_CUDA(h, cudaEventRecord(ev[2 * i], h->stream));
         rc = kind == 3   ? launch_tower_r_staged(h, h->staged_B)
+             : kind == 4 ? launch_tower_r2_staged(h, h->staged_B)
              : kind == 1 ? launch_tower(h, h->staged_B)
                          : enqueue_tower(h, h->staged_B, nullptr);
         CB_CUDA(h, cudaEventRecord(ev[2 * i + 1], h->stream));
@@ -2079,7 +2148,7 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
 
 int cb_debug_backbone(cb_handle* h, int B, float* out) {
     if (!h) return CB_EINVAL;
-    if (fused_kind(h) == 3) {
+    if (fused_kind(h) == 3 || fused_kind(h) == 4) {
         // the resident tower never writes the backbone to global memory: rerun it on the boards of the
         // last call with the debug dump enabled
         if (!out || B <= 0 || B > h->cap) return CB_EINVAL;
@@ -2088,7 +2157,7 @@ int cb_debug_backbone(cb_handle* h, int B, float* out) {
         int rc = ensure_scratch(h, total);
         if (rc) return rc;
         h->d_dbg_backbone = h->d_scratch;
-        rc = launch_tower_r_staged(h, B);
+        rc = fused_kind(h) == 4 ? launch_tower_r2_staged(h, B) : launch_tower_r_staged(h, B);
         h->d_dbg_backbone = nullptr;
         if (rc) return rc;
         CB_CUDA(h, cudaMemcpyAsync(out, h->d_scratch, total * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -2107,7 +2176,7 @@ int cb_debug_act(cb_handle* h, int B, int buf, float* out) {
     const void* src = h->d_act[buf];
     const int grid = (total + 255) / 256;
     // buffer 1 ends a forward holding p_conv's output, always in pair layout; the others follow the tower
-    const int lay = (fused_kind(h) == 2 && buf != 1) ? 2 : 1;
+    const int lay = 1;
     if (h->dtype == CB_DTYPE_FP32)
         act_to_nchw_f32_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)src, h->hid, total, 0, h->d_scratch);
     else if (h->dtype == CB_DTYPE_BF16)

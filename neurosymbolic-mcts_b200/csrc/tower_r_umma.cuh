@@ -180,7 +180,7 @@ __device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 12
 //   (src/neural_net.rs:279-284) and / or the legal moves gathered and renormalised in list order with
 //   the uniform fallback (src/tensor.rs:184-213);  value head BN(1)+ReLU, cat q, FC 65->256, FC 256->1,
 //   k, tanh fusion (python/model.py:128-132,109-110; src/mcts/tactical_mcts.rs:762-765,787-790).
-__device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board, int bs, int nb, int tix, int lane, int quadl,
+__device__ __forceinline__ void heads_epilogue(const PolicyOut& po, int board, int bs, int nb, int tix, int lane, int quadl,
                                                uint32_t tcol, float* lg, float* s_red, float* s_g) {
     const int bar = 2 + bs;
     float mx = -INFINITY;
@@ -215,30 +215,30 @@ __device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board,
     if (lane == 0) s_red[4 + quadl] = se;
     team_bar(bar);
     const float lse = bmax + __logf((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
-    if (p.po.probs) {
-        float* o = p.po.probs + static_cast<size_t>(board) * CB_POLICY_SIZE;
+    if (po.probs) {
+        float* o = po.probs + static_cast<size_t>(board) * CB_POLICY_SIZE;
         for (int i = tix; i < CB_POLICY_SIZE; i += 128) o[i] = __expf(lg[i] - lse);
     }
-    if (p.po.move_idx) {
+    if (po.move_idx) {
         uint32_t lo;
         int n;
-        if (p.po.move_cnt) {
+        if (po.move_cnt) {
             lo = static_cast<uint32_t>(board) * CB_MAX_MOVES;
-            n = p.po.move_cnt[board];
+            n = po.move_cnt[board];
         } else {
-            lo = p.po.move_off[board];
-            n = static_cast<int>(p.po.move_off[board + 1] - lo);
+            lo = po.move_off[board];
+            n = static_cast<int>(po.move_off[board + 1] - lo);
         }
         // gathered values -> registers (n <= 256 = 2 per thread), total via an ordered sequential sum by one
         // thread, exactly the reference's loop (src/tensor.rs:186-201)
         float g0 = 0.0f, g1 = 0.0f;
         if (tix < n) {
-            const int idx = p.po.move_idx[lo + tix];
+            const int idx = po.move_idx[lo + tix];
             g0 = idx < CB_POLICY_SIZE ? __expf(lg[idx] - lse) : 0.0f;
             s_g[tix] = g0;
         }
         if (tix + 128 < n) {
-            const int idx = p.po.move_idx[lo + tix + 128];
+            const int idx = po.move_idx[lo + tix + 128];
             g1 = idx < CB_POLICY_SIZE ? __expf(lg[idx] - lse) : 0.0f;
             s_g[tix + 128] = g1;
         }
@@ -256,8 +256,8 @@ __device__ __forceinline__ void heads_epilogue(const TowerRParams& p, int board,
         }
         team_bar(bar);
         const float total = s_red[8];
-        if (tix < n) p.po.priors[lo + tix] = total > 0.0f ? g0 / total : 1.0f / static_cast<float>(n);
-        if (tix + 128 < n) p.po.priors[lo + tix + 128] = total > 0.0f ? g1 / total : 1.0f / static_cast<float>(n);
+        if (tix < n) po.priors[lo + tix] = total > 0.0f ? g0 / total : 1.0f / static_cast<float>(n);
+        if (tix + 128 < n) po.priors[lo + tix + 128] = total > 0.0f ? g1 / total : 1.0f / static_cast<float>(n);
     }
 }
 
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quadl * 32) << 16) + c * 256 + bs * 8;
                     if (mode == MODE_POLICY) {
                         if (active)
-                            heads_epilogue(p, cb0 + bs, bs, nb, ch, lane, quadl, tcol,
+                            heads_epilogue(p.po, cb0 + bs, bs, nb, ch, lane, quadl, tcol,
                                            reinterpret_cast<float*>(buf) + bs * CB_POLICY_SIZE, s_part + 512 + bs * 32,
                                            s_vpart + bs * 256);
                         if (et == 0) trace_stamp(trace, L * 2 + c, 5);

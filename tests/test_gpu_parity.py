@@ -97,10 +97,9 @@ def test_tensor_core_modes_match_reference(cb, golden, name, dtype):
     dv, dl = np.abs(v_final - v_final_ref).max(), np.abs(v - g["v_logit"]).max()
     klm = kl(np.exp(g["log_policy_full"]), pol[:nf]).max()
     print("%s %s: max|dV_final|=%.3e max|dv_logit|=%.3e max KL=%.3e" % (name, dtype, dv, dl, klm))
-    # 21 bf16 layers of the 10x256 net accumulate slightly more rounding than the 1e-2 bar on
-    # these random weights (measured 1.2e-2); fp16 operands meet 1e-2 on the same net.
-    tol = 2e-2 if (name == "10x256_B" and dtype == "bf16") else TOL_V_16
-    assert dv <= tol, "value tolerance (north star: <= 1e-2 in 16-bit modes)"
+    # (the 10x256 net meets the bar in bf16 too since the pair kernel keeps the skip path in fp16: 9.2e-3; it was 1.2e-2
+    #  with bf16-stored block inputs)
+    assert dv <= TOL_V_16, "value tolerance (north star: <= 1e-2 in 16-bit modes)"
     assert klm <= TOL_KL
     assert np.abs(k - g["k"]).max() <= 1e-6
     if str(g["variant"]) == "A":      # zero heads: exactly uniform policy, zero logit
