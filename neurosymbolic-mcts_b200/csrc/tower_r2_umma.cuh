@@ -196,6 +196,10 @@ __global__ void __launch_bounds__(TowerR2Cfg::kThreads, 1) tower_r2_umma_kernel(
 
     // first board of a unit; chains of a unit that hold at least one board.  When the last round of 8-board units would
     // leave more than half of the pairs idle, the host cuts those units in two: twice as many pairs each run one chain
+    // (its epilogue is then not hidden: 0.79 of a full unit's time for half the boards, still a gain of 5 % at batch 2048.
+    // Measured and dropped: running such a chain as two sub-chains of one board per CTA — N = 128 MMAs over every other
+    // 9-row group, 8-row-group stride 18 rows — so that the epilogues hide again: the N = 128 MMAs of a pair are bound by
+    // the shared-memory port (4 KB of weights re-read per 64 cycles) and the launch got 1.8 % slower, not 4 % faster)
     auto unit_b0 = [&](int unit) { return unit < p.full_units ? unit * 8 : p.full_units * 8 + (unit - p.full_units) * 4; };
     auto chain_live = [&](int unit, int c) { return (c == 0 || unit < p.full_units) && unit_b0(unit) + c * 4 < p.num_boards; };
 

@@ -263,6 +263,36 @@ def test_full_size_properties(cb, golden, positions, B):
     assert kl(np.exp(logp), pol).max() <= TOL_KL
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_pair_kernel_batch_shapes_are_bit_identical(cb, golden, positions, dtype):
+    """The 256-channel forward on CTA pairs (tower_r2_umma.cuh): full units (two chains of 4 boards), tail units (one
+    chain), ragged ends, several rounds per pair — every position must get exactly the result it gets inside the big
+    batch, and the big batch must meet the parity bar on the golden boards."""
+    g, blob = golden("10x256_B")
+    ev = make_eval(cb, g, blob, dtype)
+    boards, idx, off, _ = positions
+    Bmax = 1400                                   # 175 units of 8 on 74 pairs: 2 full rounds + 27 units cut into 54 single chains
+    q = O.static_q(boards[:Bmax])
+    pri, v, vf, k = ev.eval_leaves(boards[:Bmax], q, idx[:off[Bmax]], off[:Bmax + 1])
+    assert np.isfinite(pri).all() and np.isfinite(v).all() and np.abs(v).max() > 0.05
+    for B in (1, 2, 3, 4, 5, 7, 8, 9, 16, 37, 296, 297, 300, 592, 593, 640, 1184, 1185):
+        p_b, v_b, vf_b, _ = ev.eval_leaves(boards[:B], q[:B], idx[:off[B]], off[:B + 1])
+        assert np.array_equal(v_b, v[:B]), "v_logit differs at batch %d" % B
+        assert np.array_equal(vf_b, vf[:B]), "v_final differs at batch %d" % B
+        assert np.array_equal(p_b, pri[:off[B]]), "priors differ at batch %d" % B
+    # the golden boards inside a batch large enough for full units
+    n = g["boards"].shape[0]
+    big = np.concatenate([boards[:800], g["boards"]])
+    pol, vg, kg = ev.predict_batch(big, np.concatenate([q[:800], g["q"]]), None)
+    ref = np.tanh(g["v_logit"].astype(np.float64) + g["k"].astype(np.float64) * g["q"])
+    got = np.tanh(vg[800:].astype(np.float64) + kg[800:].astype(np.float64) * g["q"])
+    assert np.abs(got - ref).max() <= TOL_V_16
+    nf = g["log_policy_full"].shape[0]
+    assert kl(np.exp(g["log_policy_full"]), pol[800:800 + nf]).max() <= TOL_KL
+    small, vs, _ = ev.predict_batch(g["boards"], g["q"], None)
+    assert np.array_equal(vs, vg[800:]) and np.array_equal(small, pol[800:])
+
+
 def test_ragged_batch_sizes_are_bit_identical_to_the_full_batch(cb, golden, positions):
     """Every way the resident tower splits a batch into units / chains (1..4 boards per chain, with and
     without y-halo rows, one or several units per SM) must give each position exactly the result it gets
