@@ -261,6 +261,7 @@ def main():
     ap.add_argument("--no-config4", action="store_true", help="skip the 10x256 batch-2048 sub-record (N = 1 only)")
     ap.add_argument("--selfplay-seconds", type=float, default=3.0, help="seconds per self-play pool shape; 0 disables the section")
     ap.add_argument("--selfplay-games", type=int, default=1024)
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the back-to-back replay loop")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -337,7 +338,7 @@ def main():
     # ---- sustained: the same forward back to back for >= 2 s (no flush, no pause: the power-capped rate)
     barrier()
     clocks.active = True
-    sus_ms, sus_n = ev.time_sustained(2.0)
+    sus_ms, sus_n = ev.time_sustained(args.sustained_seconds)
     clocks.active = False
     barrier()
     time.sleep(0.5)                                    # let the board cool before the next timed region
@@ -534,7 +535,7 @@ def main():
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config,
             "value_sustained": value_sustained,
-            "sustained": {"seconds": 2.0, "launches": sus_n, "us_per_forward": sus_ms_per_launch * 1e3,
+            "sustained": {"seconds": args.sustained_seconds, "launches": sus_n, "us_per_forward": sus_ms_per_launch * 1e3,
                           "whole_path_tflops": sus_tf, "peak": sustained, "frac": sus_tf / sustained,
                           "note": "the staged forward replayed back to back, no L2 flush, no pause: the power-capped rate; "
                                   "denominator = bf16_tflops_sustained of MEASURED_PEAKS.json"},

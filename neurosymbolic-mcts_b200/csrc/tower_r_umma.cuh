@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     }
                     if (!data) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) row1[i] = make_uint4(0, 0, 0, 0);
+                        for (int i = 0; i < 8; ++i) row1[i ^ (r & 7)] = make_uint4(0, 0, 0, 0);   // (rotated: no bank conflicts)
                     }
                 }
                 // accumulator preset: the folded-BN bias of the first layer (every MMA accumulates)
