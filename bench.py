@@ -402,6 +402,18 @@ def main():
                 rate, us = resident_rate(ev, boards, q, idx, off, b_, 30)
                 sweep[str(b_)] = {"evals_per_s": rate, "us_per_forward": us}
         ev.stage_leaves(boards, q, idx, off)
+        # the other arithmetic modes of the same net and batch: fp16 operands (same kernel), and the exact mode that meets the
+        # north star's fp32 tolerance (fp32 FMA on CUDA cores: a validation mode)
+        modes = {}
+        for dt in ("fp16", "fp32"):
+            if dt != args.dtype:
+                evm = cb.Evaluator(args.blocks, args.hidden, dt, device=local_rank)
+                evm.load_weights(blob)
+                rate, us = resident_rate(evm, boards, q, idx, off, B, 10 if dt == "fp16" else 3, warmup=1)
+                modes[dt] = {"evals_per_s": rate, "us_per_forward": us,
+                             "parity_bar": "|dV| <= 1e-2, KL <= 1e-4" if dt == "fp16" else "|dV| <= 1e-3, KL <= 1e-4 (measured 4e-7)"}
+                evm.close()
+        sweep["modes_at_batch_%d" % B] = modes
         if not args.no_config4 and (args.blocks, args.hidden) == (6, 128):
             cfg4 = config4_record(cb, local_rank, peaks)
 
@@ -449,6 +461,12 @@ def main():
         from caissa_b200 import distributed as D
         local = np.fromfile(rec_path, dtype=np.float32).reshape(-1, D.RECORD_FLOATS) if os.path.exists(rec_path) else \
             np.zeros((0, D.RECORD_FLOATS), dtype=np.float32)
+        ns = [None] * world
+        dist.all_gather_object(ns, int(local.shape[0]))
+        D.gather_samples(local[:min(8, local.shape[0])], dst=0)          # communicator and kernels warm
+        D._pinned("in", (max(ns), D.RECORD_FLOATS))                       # staging buffers exist before the timed gather
+        if rank == 0:
+            D._pinned("out", (sum(ns), D.RECORD_FLOATS))
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
@@ -479,8 +497,12 @@ def main():
         dist.barrier()
         th = threading.Thread(target=gather_loop)
         th.start()
-        sp_g = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=False, seed=1 + rank,
-                           max_seconds=args.selfplay_seconds, pipeline=3)
+        # (two pools: the forward kernel of a pool runs on 128 SMs, so the tree kernel of the other pool AND the NCCL kernels
+        #  find free SMs.  A one-pool forward is one wave of 148 single-SM CTAs: any other kernel holding an SM — an NCCL
+        #  kernel waiting for its peer does for hundreds of microseconds — pushes one CTA into a second wave and doubles the
+        #  step, which at 8 ranks cost 43 % of the sims/s when measured that way.)
+        sp_g = ev.selfplay(games=2 * args.selfplay_games, sims_per_move=200, material_on=False, seed=301 + rank,
+                           max_seconds=args.selfplay_seconds, pipeline=4)
         th.join()
         # weight refresh: rank 0 draws a new blob, NCCL broadcast, every rank loads it and evaluates the same 8 positions
         from oracle import weights as Wt
@@ -589,7 +611,8 @@ def main():
         if nccl:
             nccl["records_per_s_produced"] = float(tot[7].item()) / max(sp_rec_seconds, 1e-9)
             nccl["sims_per_s_with_gather_running"] = float(tot[8].item()) / max(sp_g_seconds, 1e-9)
-            nccl["sims_per_s_without"] = float(tot[0].item()) / sp_seconds
+            nccl["sims_per_s_without"] = float(tot[4].item()) / max(sp_two_seconds, 1e-9)
+            nccl["pool"] = "two pools of %d games (pipeline 4)" % args.selfplay_games
             for k_ in ("selfplay_seconds_with_gather", "selfplay_sims_with_gather"):
                 nccl.pop(k_)
             line["nccl_exchange"] = nccl
