@@ -519,7 +519,8 @@ def main():
         n_all = int(sum(n_r for n_r, _ in sums))
         nccl = {"gather_records": n_all, "gather_seconds": gather_s,
                 "gather_GBps": n_all * D.RECORD_FLOATS * 4 / gather_s / 1e9, "gather_bit_equal_on_rank0": bool(ok),
-                "gather": "every rank's finished-game records of the run above -> rank 0 (NCCL gather), device staging included",
+                "gather": "every rank's finished-game records of the run above -> rank 0 (one NCCL all-gather, host copy on "
+                          "rank 0 only), device staging included",
                 "records_per_s_produced": None, "selfplay_seconds_with_gather": sp_g["seconds"], "selfplay_sims_with_gather": sp_g["sims"],
                 "gather_flushes_during_selfplay": int(flushes[0]),
                 "weights_broadcast_floats": int(got.size), "weights_broadcast_seconds": bcast_s,

@@ -40,11 +40,13 @@ def _pinned(name, shape):
     return t[:n].view(*shape)
 
 
-def gather_samples(local, dst=None):
+def gather_samples(local, dst=None, transport="all_gather"):
     """local: float32 [n_local, 5763] (n_local may differ per rank, may be 0) -> float32 [sum n, 5763] in rank-major
-    order.  dst=None: all-gather, identical result on every rank.  dst=r: gathered on rank r only (the trainer's rank;
-    the reference writes one file per generation, src/training_data.rs:24-60) — the other ranks return an empty array and
-    only send, so the exchange costs a rank its own records once."""
+    order.  dst=None: identical result on every rank.  dst=r: only rank r (the trainer's rank; the reference writes one file
+    per generation, src/training_data.rs:24-60) copies the gathered records to the host, the others return an empty array.
+    transport: "all_gather" (default) is ONE NCCL collective kernel; "gather" is NCCL's send / receive form.  Measured beside
+    a two-pool self-play run (tools/exchange_probe.py, 2 x B200, 25 flushes/s of 512 records per rank): all_gather costs the
+    pool 0.3 % of its sims/s, gather 13 % — the send / receive kernels hold SMs while they wait for their peer."""
     local = np.ascontiguousarray(local, dtype=np.float32).reshape(-1, RECORD_FLOATS)
     dev = _device()
     cuda = dev.type == "cuda"
@@ -64,15 +66,17 @@ def gather_samples(local, dst=None):
             block[:local.shape[0]].copy_(stage, non_blocking=True)
         else:
             block[:local.shape[0]] = torch.from_numpy(local)
-    if dst is None:
+    if dst is None or transport == "all_gather":
         parts = torch.empty((world, n_max, RECORD_FLOATS), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(parts, block) if cuda else dist.all_gather(list(parts.unbind(0)), block)
         parts = list(parts.unbind(0))
     else:
         parts = [torch.empty_like(block) for _ in range(world)] if rank == dst else None
         dist.gather(block, parts, dst=dst)
-        if rank != dst:
-            return np.zeros((0, RECORD_FLOATS), dtype=np.float32)
+    if dst is not None and rank != dst:
+        if cuda:
+            torch.cuda.current_stream().synchronize()
+        return np.zeros((0, RECORD_FLOATS), dtype=np.float32)
     out = _pinned("out", (total, RECORD_FLOATS)) if cuda else torch.empty((total, RECORD_FLOATS), dtype=torch.float32)
     lo = 0
     for r in range(world):

@@ -21,6 +21,7 @@ def _worker(rank, world, port, out_dir):
     local = rng.random((n_local, D.RECORD_FLOATS), dtype=np.float32) + rank
     allrec = D.gather_samples(local)
     on0 = D.gather_samples(local, dst=0)
+    assert np.array_equal(D.gather_samples(local, dst=0, transport="gather"), on0)
     blob = D.broadcast_weights(np.arange(1000, dtype=np.float32) if rank == 0 else None, 1000)
     lo, hi = D.shard_range(1024 + 1, rank, world)
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), local=local, allrec=allrec, on0=on0, blob=blob, lo=lo, hi=hi)
