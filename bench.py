@@ -296,6 +296,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the only NCCL traffic is the off-path exchange: keep its kernels to a few SMs (the pools need the rest)
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -484,16 +486,18 @@ def main():
             ok = ok and lo == allrec.shape[0]
         # the gather under load: a side thread gathers this rank's records in a FIXED number of flushes (the same on every
         # rank: collectives must pair up) spread over the run of a self-play pool
-        n_flush = max(1, int(args.selfplay_seconds * 25))
+        # Small frequent flushes: the cost to the pool grows with the length of each NCCL kernel, not with the bytes per
+        # second (tools/exchange_probe.py, 4 x B200: 100 x 128 records/s costs 0.6 %, 25 x 512 costs 2.9 %, 5 x 2560 more).
+        n_flush = max(1, int(args.selfplay_seconds * 100))
         flushes = [0]
 
         def gather_loop():
             torch.cuda.set_device(local_rank)
-            chunk = local[:max(1, min(local.shape[0], 512))]
-            for _ in range(n_flush):          # 25 flushes/s x 512 records/rank (12.8 k records/s/rank): above the produced rate
+            chunk = local[:max(1, min(local.shape[0], 128))]
+            for _ in range(n_flush):          # 100 flushes/s x 128 records/rank (12.8 k records/s/rank): above the produced rate
                 D.gather_samples(chunk, dst=0)
                 flushes[0] += 1
-                time.sleep(0.02)
+                time.sleep(0.007)
         dist.barrier()
         th = threading.Thread(target=gather_loop)
         th.start()

@@ -48,12 +48,13 @@ def run(pipeline, games, rate, chunk, dst):
 
 
 D.gather_samples(records[:8], dst=0)
-for pipeline, games in ((3, 1024), (4, 2048)):
+FAST = os.environ.get("PROBE_FAST") == "1"
+for pipeline, games in (((4, 2048),) if FAST else ((3, 1024), (4, 2048))):
     base = run(pipeline, games, 0, 0, 0)
-    for rate, chunk in ((25, 512), (5, 2560), (1, 12800)):
-        for dst in (0, None):
+    for rate, chunk in (((25, 64), (100, 128), (25, 512)) if FAST else ((25, 512), (5, 2560), (1, 12800))):
+        for dst in ((None,) if FAST else (0, None)):
             v = run(pipeline, games, rate, chunk, dst)
             if rank == 0:
-                print("pipeline %d: %2d flushes/s x %5d records/rank (%s): %.2f M sims/s (%.1f %% of %.2f M)" % (
-                    pipeline, rate, chunk, "gather to rank 0" if dst == 0 else "all-gather", v / 1e6, 100 * v / base, base / 1e6), flush=True)
+                print("NCCL_MAX_CTAS=%s pipeline %d: %2d flushes/s x %5d records/rank (%s): %.2f M sims/s (%.1f %% of %.2f M)" % (
+                    os.environ.get("NCCL_MAX_CTAS", "-"), pipeline, rate, chunk, "gather to rank 0" if dst == 0 else "all-gather", v / 1e6, 100 * v / base, base / 1e6), flush=True)
 dist.destroy_process_group()
