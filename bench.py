@@ -226,15 +226,18 @@ def config4_record(cb, local_rank, peaks):
     blob = W.flatten(W.make_weights(blocks, hidden, WEIGHT_SEED, "B"), blocks, hidden)
     ev = cb.Evaluator(blocks, hidden, dtype, device=local_rank)
     ev.load_weights(blob)
-    rate, us = resident_rate(ev, boards, q, idx, off, B, 12)
+    rate, us = resident_rate(ev, boards, q, idx, off, B, 40)
     ev.time_tower(2)
-    tower_ms, n_tower = ev.time_tower(8)
+    tower_ms, n_tower = ev.time_tower(16)
     sus_ms, sus_n = ev.time_sustained(1.0)
     launches = ev.launches_per_forward()
     ev.close()
     sustained, burst, _ = peaks
     tower_tf = tower_flops_per_position(blocks, hidden) * B / (float(tower_ms.mean()) * 1e-3) / 1e12
     return {"workload": workload_label(blocks, hidden, B), "dtype": dtype, "value": rate, "unit": UNIT, "us_per_forward": us,
+            "timing": "value: median of 40 flushed steps (CUDA events); roofline: mean of 16 tower launches; value_sustained: "
+                      "back-to-back replays for 1 s.  Short regions run at up to 1.965 GHz, long ones at ~1.79 GHz under the "
+                      "power cap: `python bench.py --blocks 10 --hidden 256 --batch 2048` gives the 200-step figures",
             "value_sustained": B * sus_n / (sus_ms * 1e-3), "gpu_launches_per_forward": launches,
             "roofline": {"bound": "tensor", "kernel": "tower_r2_umma_kernel<bf16> (planes, conv tower, policy head on CTA pairs, "
                                                     "cta_group::2; %d launch/step)" % n_tower,
