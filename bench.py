@@ -231,6 +231,8 @@ def config4_record(cb, local_rank, peaks):
     tower_ms, n_tower = ev.time_tower(16)
     sus_ms, sus_n = ev.time_sustained(1.0)
     launches = ev.launches_per_forward()
+    # config 4's other half: self-play with this net (1024 concurrent games, 200 sims/move, tree operations on the device)
+    sp = ev.selfplay(games=1024, sims_per_move=200, material_on=False, seed=77, max_seconds=1.5, pipeline=3)
     ev.close()
     sustained, burst, _ = peaks
     tower_tf = tower_flops_per_position(blocks, hidden) * B / (float(tower_ms.mean()) * 1e-3) / 1e12
@@ -239,6 +241,7 @@ def config4_record(cb, local_rank, peaks):
                       "back-to-back replays for 1 s.  Short regions run at up to 1.965 GHz, long ones at ~1.79 GHz under the "
                       "power cap: `python bench.py --blocks 10 --hidden 256 --batch 2048` gives the 200-step figures",
             "value_sustained": B * sus_n / (sus_ms * 1e-3), "gpu_launches_per_forward": launches,
+            "selfplay_sims_per_s": sp["sims"] / sp["seconds"], "selfplay_games": 1024,
             "roofline": {"bound": "tensor", "kernel": "tower_r2_umma_kernel<bf16> (planes, conv tower, policy head on CTA pairs, "
                                                     "cta_group::2; %d launch/step)" % n_tower,
                          "achieved": tower_tf, "peak": burst, "unit": "TFLOP/s", "frac": tower_tf / burst,

@@ -13,7 +13,7 @@ REQUIRED = {"metric": str, "value": float, "unit": str, "n_gpus": int, "steps": 
             "gpu_launches": int, "clocks": dict, "roofline": dict}
 
 
-@pytest.mark.parametrize("name,n", [("r01_bench_v15.json", 1), ("r01_bench_v15_n8.json", 8), ("r01_bench_v16_n2.json", 2), ("r01_bench_v14.json", 1), ("r01_bench_v13.json", 1), ("r01_bench_v13_n2.json", 2), ("r01_bench_v13_n4.json", 4),
+@pytest.mark.parametrize("name,n", [("r02_bench_v6.json", 1), ("r02_bench_v5_n2.json", 2), ("r02_bench_v5_n8.json", 8), ("r01_bench_v15.json", 1), ("r01_bench_v15_n8.json", 8), ("r01_bench_v16_n2.json", 2), ("r01_bench_v14.json", 1), ("r01_bench_v13.json", 1), ("r01_bench_v13_n2.json", 2), ("r01_bench_v13_n4.json", 4),
                                     ("r01_bench_v13_n8.json", 8)])
 def test_committed_lines_follow_the_contract(name, n):
     d = json.load(open(os.path.join(REPO, "profiles", name)))
@@ -30,6 +30,16 @@ def test_committed_lines_follow_the_contract(name, n):
     assert d["gpu_launches"] == d["steps"] * n            # one kernel per forward per GPU
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+    if name.startswith("r02"):          # round 2 additions
+        assert d["value_sustained"] > 0 and d["sustained"]["frac"] > 0.5
+        assert "submit" in d["e2e"]["api"] and d["e2e"]["sustained_value"] > 0
+        if n == 1:
+            assert set(d["batch_sweep"]) >= {"1", "16", "128", "256"}
+            c4 = d["config4"]
+            assert c4["dtype"] == "bf16" and "configs[3]" in c4["workload"] and c4["roofline"]["traffic"] > 0
+        else:
+            x = d["nccl_exchange"]
+            assert x["gather_bit_equal_on_rank0"] and x["weights_spot_check_identical_on_all_ranks"] and x["gather_records"] > 1000
     if n == 1:
         c = d["cpu_baseline"]
         assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == d["unit"] and c["sample"]

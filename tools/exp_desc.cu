@@ -266,6 +266,7 @@ int main() {
     };
     timeit(1, 256, 1, 8); timeit(1, 256, 4, 8); timeit(1, 256, 0, 9); timeit(1, 256, 1, 9); timeit(1, 224, 1, 9); timeit(1, 192, 1, 9);
     timeit(1, 128, 1, 9); timeit(1, 256, 0, 16); timeit(1, 256, 1, 16); timeit(1, 128, 1, 8);
+    timeit(1, 64, 1, 9); timeit(1, 64, 1, 8); timeit(1, 32, 1, 8); timeit(1, 16, 1, 8);   // small-batch chains: is there a floor per MMA?
     auto timeld = [&](int ld_mode, int gap, int warps) {
         // single accumulator MMA chain (mode 3 uses tmem columns [0,256)); loaders read columns [256,512)
         Params p{dA, dB, dD, 0, 8, 0, 256, 0, dC, 3, 500, ld_mode, 1000, gap};
