@@ -450,13 +450,15 @@ int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bo
     const int n_lo = B / tp.num_units, n_hi = (B + tp.num_units - 1) / tp.num_units;
     const bool cl2 = h->use_cluster && !debug && tp.num_units == grid && (grid & 1) == 0 && (n_lo >= 5 || n_hi <= 4);
     // every unit a single chain (at most 4 boards per CTA): the deep weight ring (latency-bound small batches)
-    const bool deep = !cl2 && !debug && n_hi <= 4 && !getenv("CB_NO_DEEP_RING");
+    const bool deep = !cl2 && n_hi <= 4 && !getenv("CB_NO_DEEP_RING");
     void (*kern)(const TowerRParams);
     if (h->dtype == CB_DTYPE_BF16)
-        kern = cl2 ? tower_r_umma_kernel<true, false, true> : debug ? tower_r_umma_kernel<true, true, false>
+        kern = cl2 ? tower_r_umma_kernel<true, false, true>
+             : debug ? (deep ? tower_r_umma_kernel<true, true, false, true> : tower_r_umma_kernel<true, true, false>)
              : deep ? tower_r_umma_kernel<true, false, false, true> : tower_r_umma_kernel<true, false, false>;
     else
-        kern = cl2 ? tower_r_umma_kernel<false, false, true> : debug ? tower_r_umma_kernel<false, true, false>
+        kern = cl2 ? tower_r_umma_kernel<false, false, true>
+             : debug ? (deep ? tower_r_umma_kernel<false, true, false, true> : tower_r_umma_kernel<false, true, false>)
              : deep ? tower_r_umma_kernel<false, false, false, true> : tower_r_umma_kernel<false, false, false>;
     CB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TowerRCfg::kSmemBytes));
     if (cl2) {

@@ -169,6 +169,8 @@ __device__ __forceinline__ void trace_stamp(long long* trace, int item, int slot
 
 template <bool V>
 struct BoolC { static constexpr bool v = V; };
+template <int V>
+struct IntC { static constexpr int v = V; };
 
 
 __device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
@@ -286,7 +288,7 @@ __device__ __forceinline__ void value_phase(const TowerRParams& p, int et, int l
     const float fb = half ? 0.0f : __ldg(p.vp.fc_b + j);
     float h[8] = {fb, fb, fb, fb, fb, fb, fb, fb};
     const int e0 = half ? 33 : 0;
-#pragma unroll 11
+#pragma unroll
     for (int i = 0; i < 33; ++i) {
         const int e = e0 + i;
         if (e < 65) {
@@ -337,9 +339,11 @@ __device__ __forceinline__ void value_phase(const TowerRParams& p, int et, int l
 // checks.  Measured: +5 % SM clock, but the lock-step on a 4-stage ring costs 10 % more cycles: not the default.
 //
 // DEEP = true (launches whose units all have ONE chain, i.e. at most 4 boards per CTA: batches of up to 4 boards per
-// SM): the second chain's activation buffer is idle, so the weight ring grows from 4 to 8 stages into it (the four
-// extra stages sit right below the regular ones: one contiguous ring).  Such launches are bound by the latency of
-// the L2 -> SM weight stream (295 KB per layer through 64 KB in flight), which the deeper ring halves.
+// SM): the second chain's activation buffer is idle, so the weight ring grows into it (128 KB, contiguous with the
+// regular ring) and a stage becomes a WHOLE TAP: both 64-channel halves (2 x 16 KB, one barrier, one commit).  What
+// bounds such launches is the hand-off of a ring stage, not the stream or the MMAs (tools/exp_stage.cu, one SM alone:
+// wait + 4 MMAs + commit per 16 KB costs 349 cycles at N = 64 against an MMA floor of 192; 8 MMAs per barrier cost
+// 273 per 16 KB; N >= 192 runs at the MMA floor either way; one SM pulls up to 125 B/clk through TMA).
 template <bool BF16, bool DBG, bool CL2, bool DEEP = false>
 __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(const TowerRParams p) {
     const int dbg = DBG ? p.dbg : 0;
@@ -348,12 +352,13 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
     float* const dbg_backbone = DBG ? p.dbg_backbone : nullptr;
     using Cfg = TowerRCfg;
     constexpr int HID = 128;
-    constexpr int kWStages = DEEP ? 2 * Cfg::kWStages : Cfg::kWStages, kSE = 8;
+    constexpr int kWStages = Cfg::kWStages, kSE = 8;
+    constexpr int kStageBytes = DEEP ? 2 * Cfg::kWBytes : Cfg::kWBytes;   // DEEP: a stage is a whole tap (both halves)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* chain_base = smem;                                // [2][2 halves][kHalfBytes]
     uint8_t* w_base = chain_base + 2 * Cfg::kChainBytes - (DEEP ? Cfg::kWStages * Cfg::kWBytes : 0);
-    uint8_t* misc = w_base + kWStages * Cfg::kWBytes;
+    uint8_t* misc = w_base + kWStages * kStageBytes;
     static_assert(Cfg::kChainBytes >= Cfg::kWStages * Cfg::kWBytes, "the deep ring lives in the idle chain's buffer");
     uint64_t* w_full = reinterpret_cast<uint64_t*>(misc);      // [kWStages]
     uint64_t* w_empty = w_full + kWStages;                     // [kWStages]
@@ -369,6 +374,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
     if (cta_times && threadIdx.x == 0) cta_times[blockIdx.x * 4 + 0] = globaltimer_ns();
     // tap order: the first tap of a layer must cover every accumulator column (dy = 0)
     constexpr int kTapOrder[9] = {4, 3, 5, 1, 0, 2, 7, 6, 8};
+    constexpr unsigned long long kTapOrderPacked = 0x867201534ULL;   // the same, one nibble per tap (runtime-indexed uses)
 
     if (threadIdx.x == 0) {
         // this CTA is resident: a kernel launched as a programmatic dependent (the tree kernel of the other game
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
         for (int s = 0; s < kWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], CL2 ? 2 : 1); }
         for (int c = 0; c < 2; ++c) {
             ptx::mbar_init(&tmem_full[c], 1);
-            ptx::mbar_init(&chain_ready[c], Cfg::kEpiThreads);
+            ptx::mbar_init(&chain_ready[c], Cfg::kEpiThreads / 32);   // one arrival per epilogue warp
         }
         ptx::fence_barrier_init();
     }
@@ -403,7 +409,21 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     if (nbc[c] == 0) continue;
 #pragma unroll 1
                     for (int t = 0; t < ntaps; ++t) {
-                        const int tap = kTapOrder[t];
+                        const int tap = static_cast<int>((kTapOrderPacked >> (4 * t)) & 15u);
+                        if constexpr (DEEP) {
+                            ptx::mbar_wait(&w_empty[ws], wph ^ 1);
+                            if (ptx::elect_one()) {
+                                if (dbg & 16) {
+                                    ptx::mbar_arrive(&w_full[ws]);
+                                } else {
+                                    ptx::mbar_arrive_expect_tx(&w_full[ws], kc_in * Cfg::kWBytes);
+                                    for (int kc = 0; kc < kc_in; ++kc)
+                                        ptx::tma_load_2d(w_base + ws * kStageBytes + kc * Cfg::kWBytes, tm_w, &w_full[ws], kc * 64, tap * HID + w_row_off);
+                                }
+                            }
+                            __syncwarp();
+                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                        } else
                         for (int kc = 0; kc < kc_in; ++kc) {
                             ptx::mbar_wait(&w_empty[ws], wph ^ 1);
                             if (ptx::elect_one()) {
@@ -474,6 +494,21 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                         const uint32_t idesc = ptx::umma_idesc_f16(BF16 ? 1 : 0, 128, n);
                         const uint32_t b_lo_t = b_lo_c + start_row * 8;      // 128-byte rows in 16-byte units
                         const uint32_t d_t = d_tmem + dcol;
+                        if constexpr (DEEP) {
+                            ptx::mbar_wait(w_full + ws, wph);
+                            if (ptx::elect_one()) {
+                                for (int kc = 0; kc < kc_in && !(dbg & 1); ++kc) {
+                                    const uint32_t a_lo = a_lo0 + ws * (kStageBytes >> 4) + kc * (Cfg::kWBytes >> 4);
+                                    const uint32_t b_lo = b_lo_t + kc * (Cfg::kHalfBytes >> 4);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        ptx::umma_f16_lohi(d_t, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);   // bias preset
+                                }
+                                ptx::umma_commit(w_empty + ws);
+                            }
+                            __syncwarp();
+                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                        } else
                         for (int kc = 0; kc < kc_in; ++kc) {
                             ptx::mbar_wait(w_full + ws, wph);
                             if (ptx::elect_one()) {
@@ -567,7 +602,8 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                 }
                 ptx::tc_fence_before();
                 ptx::fence_proxy_async_smem();
-                ptx::mbar_arrive(&chain_ready[c]);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&chain_ready[c]);
             }
 
             for (int L = 0; L < p.num_layers; ++L) {
@@ -579,9 +615,20 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     const int nb = c ? nbc1 : nbc0;
                     if (nb == 0) continue;
                     const int halo = nb & 1;
-                    const bool active = bs < nb;      // this thread's board slot exists in the chain
+                    // Thread -> (board slot bsx, rows [y0, y0 + ny)).  Normally a thread owns all 8 rows of board slot bs.
+                    // DEEP (single-chain units, the small-batch launches, where nothing hides the epilogue): with one or
+                    // two boards in the chain the board teams that would idle take a share of the rows instead
+                    // (1 board: 2 rows per team; 2 boards: 4 rows).  Sums stay in the full-board order (see pass 1).
+                    int bsx = bs, y0 = 0, ny = 8;
+                    if constexpr (DEEP) {
+                        if (nb == 1) { bsx = 0; y0 = 2 * bs; ny = 2; }
+                        else if (nb == 2) { bsx = bs & 1; y0 = 4 * (bs >> 1); ny = 4; }
+                    }
+                    const bool rowsplit = DEEP && nb <= 2;
+                    const bool active = bsx < nb;     // this thread's board slot exists in the chain
                     const int cb0 = b0 + (c ? nbc0 : 0);
                     uint8_t* buf = chain_base + c * Cfg::kChainBytes;
+                    uint4* const my_res_x = my_res + (bsx - bs) * 8 * HID;
                     constexpr int kFc1 = 32 / (kEpi / 32);   // squeeze-FC outputs per warp
                     float w1r[kFc1][4], w2r[kSE];
                     uint4 rr[8];
@@ -596,20 +643,29 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                         // block input of my (channel, board): parked by this same thread earlier
                         if (active && !(dbg & 4)) {
 #pragma unroll
-                            for (int y = 0; y < 8; ++y) rr[y] = __ldcg(my_res + (c * 32 + y) * HID);
+                            for (int yy = 0; yy < 8; ++yy) {
+                                if (yy >= ny) break;
+                                rr[yy] = __ldcg(my_res_x + (c * 32 + y0 + yy) * HID);
+                            }
                         }
                     }
                     const float bias_next = last_layer ? 0.0f : __ldg(p.layers[L + 1].bias + ch);   // p_head: padded to 128
+                    // (everything the epilogue needs from the layer table is read BEFORE the wait: behind it, each of
+                    // these loads is an L2 round trip in front of the next layer's first MMA)
+                    const bool want_v = (mode == MODE_SE_RES) && ly->v_pre != nullptr;
+                    const float vw = want_v ? __ldg(ly->v_w + ch) : 0.0f;
+                    const bool save_res = ly->save_res != 0 && !(dbg & 4);
                     if (dbg & 64) ptx::mbar_wait(&tmem_full[c], (full_ph >> c) & 1u);
                     else ptx::mbar_wait_parked(&tmem_full[c], (full_ph >> c) & 1u);
                     full_ph ^= 1u << c;
                     ptx::tc_fence_after();
                     if (et == 0) trace_stamp(trace, L * 2 + c, 4);
                     // my board's 8 column groups: column (y * nb + bs) * 8
-                    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quadl * 32) << 16) + c * 256 + bs * 8;
+                    const uint32_t tcol_p = tmem_base + (static_cast<uint32_t>(quadl * 32) << 16) + c * 256 + bs * 8;
+                    const uint32_t tcol = tcol_p + (bsx - bs) * 8;
                     if (mode == MODE_POLICY) {
-                        if (active)
-                            heads_epilogue(p.po, cb0 + bs, bs, nb, ch, lane, quadl, tcol,
+                        if (bs < nb)     // a whole board team (128 threads) per board
+                            heads_epilogue(p.po, cb0 + bs, bs, nb, ch, lane, quadl, tcol_p,
                                            reinterpret_cast<float*>(buf) + bs * CB_POLICY_SIZE, s_part + 512 + bs * 32,
                                            s_vpart + bs * 256);
                         if (et == 0) trace_stamp(trace, L * 2 + c, 5);
@@ -621,8 +677,9 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                         // pass 1: my channel's sum over my board (the bias is already in the accumulator)
                         float sb = 0.0f;
                         if (active) {
-#pragma unroll
-                            for (int y = 0; y < 8; y += 2) {
+#pragma unroll(DEEP ? 1 : 4)
+                            for (int yy = 0; yy < ny; yy += 2) {
+                                const int y = y0 + yy;
                                 uint32_t r0[8], r1[8];
                                 ptx::tmem_ld_32x8(tcol + y * nb * 8, r0);
                                 ptx::tmem_ld_32x8(tcol + (y + 1) * nb * 8, r1);
@@ -630,16 +687,34 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                                 float g0 = 0.0f, g1 = 0.0f;
 #pragma unroll
                                 for (int x = 0; x < 8; ++x) { g0 += __uint_as_float(r0[x]); g1 += __uint_as_float(r1[x]); }
-                                sb += g0;
-                                sb += g1;
+                                if (rowsplit) {
+                                    // row sums go out one by one: the board sum is formed below in the order y = 0..7
+                                    s_part[(bsx * 8 + y) * HID + ch] = g0;
+                                    s_part[(bsx * 8 + y + 1) * HID + ch] = g1;
+                                } else {
+                                    sb += g0;
+                                    sb += g1;
+                                }
                             }
                         }
-                        s_part[bs * HID + ch] = sb;
+                        if (!rowsplit) s_part[bs * HID + ch] = sb;
                         ptx::named_bar_sync(1, kEpi);
+                        if (et == 0) trace_stamp(trace, L * 2 + c, 0);
 #pragma unroll
                         for (int i = 0; i < kFc1; ++i) {
                             const int o = ew * kFc1 + i, b = o >> 3, j = o & 7;
                             float s = 0.0f;
+                            if (rowsplit) {
+                                if (b < nb) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        float cs = 0.0f;
+#pragma unroll
+                                        for (int y = 0; y < 8; ++y) cs += s_part[(b * 8 + y) * HID + lane + 32 * k];
+                                        s = fmaf(w1r[i][k], cs, s);
+                                    }
+                                }
+                            } else
 #pragma unroll
                             for (int k = 0; k < 4; ++k) s = fmaf(w1r[i][k], s_part[b * HID + lane + 32 * k], s);
 #pragma unroll
@@ -647,32 +722,34 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             if (lane == 0) s_hid[b * kSE + j] = fmaxf(s * (1.0f / 64.0f), 0.0f);
                         }
                         ptx::named_bar_sync(1, kEpi);
+                        if (et == 0) trace_stamp(trace, L * 2 + c, 1);
                         float s = 0.0f;
 #pragma unroll
-                        for (int j = 0; j < kSE; ++j) s = fmaf(w2r[j], s_hid[bs * kSE + j], s);
+                        for (int j = 0; j < kSE; ++j) s = fmaf(w2r[j], s_hid[bsx * kSE + j], s);
                         scale = 1.0f / (1.0f + __expf(-s));
                     }
                     // main pass: (SE scale + residual), ReLU, 16-bit, transpose-store into the chain buffer
-                    const bool want_v = (mode == MODE_SE_RES) && ly->v_pre != nullptr;
-                    const float vw = want_v ? __ldg(ly->v_w + ch) : 0.0f;
-                    const bool save_res = ly->save_res != 0 && !(dbg & 4);
                     const bool dump = want_v && dbg_backbone != nullptr;
                     // The main pass is instantiated per (SE + residual, park the output, value conv) combination so that
                     // its 8 x 60 instructions carry no per-group runtime branches (the epilogue warps share their
                     // schedulers with the MMA issuer).
-                    auto main_pass = [&](auto se_c, auto save_c, auto wantv_c) {
+                    auto main_pass = [&](auto se_c, auto save_c, auto wantv_c, auto ny_c) {
                         constexpr bool kSe = decltype(se_c)::v, kSave = decltype(save_c)::v, kWantV = decltype(wantv_c)::v;
+                        constexpr int kNy = decltype(ny_c)::v;     // rows per thread: compile-time, so that a short pass is short CODE
+                                                                   // (the epilogue of a single-chain unit runs from a cold instruction cache)
                         const uint32_t buf_ch = ptx::smem_u32(buf) + kc_off + (cb2 & ~2u);   // the even channel of my pair
 #pragma unroll
-                        for (int y = 0; y < 8; ++y) {
+                        for (int yy = 0; yy < kNy; ++yy) {
+                            const int y = y0 + yy;
                             uint32_t r[8];
                             ptx::tmem_ld_32x8(tcol + y * nb * 8, r);
                             ptx::tmem_ld_wait();
+                            if (DBG && !kSe && yy == 0 && et == 0) trace_stamp(trace, L * 2 + c, 0);
                             float v[8];
 #pragma unroll
                             for (int x = 0; x < 8; ++x) v[x] = __uint_as_float(r[x]);
                             if constexpr (kSe) {
-                                const uint32_t w[4] = {rr[y].x, rr[y].y, rr[y].z, rr[y].w};
+                                const uint32_t w[4] = {rr[yy].x, rr[yy].y, rr[yy].z, rr[yy].w};
 #pragma unroll
                                 for (int x = 0; x < 8; ++x) {
                                     const uint32_t h = (x & 1) ? (w[x >> 1] >> 16) : (w[x >> 1] & 0xFFFFu);
@@ -686,7 +763,7 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             // Lane pairs (channels ch, ch ^ 1) trade halves of the group so that every store is one
                             // 32-bit word = two adjacent channels of one pixel: the even lane writes pixels 0..3, the
                             // odd lane pixels 4..7 (rows 4 apart flip the swizzle half: no bank conflicts).
-                            const uint32_t row0 = static_cast<uint32_t>(((y + halo) * nb + bs) * 9 + 1) + (odd ? 4u : 0u);
+                            const uint32_t row0 = static_cast<uint32_t>(((y + halo) * nb + bsx) * 9 + 1) + (odd ? 4u : 0u);
                             const uint32_t o0 = __shfl_xor_sync(0xffffffffu, odd ? pk[0] : pk[2], 1);
                             const uint32_t o1 = __shfl_xor_sync(0xffffffffu, odd ? pk[1] : pk[3], 1);
                             const uint32_t m0 = odd ? pk[2] : pk[0], m1 = odd ? pk[3] : pk[1];
@@ -698,42 +775,55 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                                 const uint32_t addr = buf_ch + row * 128 + ((cq ^ (row & 7)) << 4);
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(wd[x]) : "memory");
                             }
-                            if constexpr (kSave) __stcg(my_res + (c * 32 + y) * HID, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                            if constexpr (kSave) __stcg(my_res_x + (c * 32 + y) * HID, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                             if constexpr (kWantV) {
                                 // value 1x1 conv: sum over this warp's 32 channels for each of the 8 pixels
                                 float tv[8];
 #pragma unroll
                                 for (int x = 0; x < 8; ++x) tv[x] = fmaxf(v[x], 0.0f) * vw;
                                 const float t = warp_transpose_sum8(tv, lane);
-                                if (lane < 8) s_vpart[quadl * 256 + bs * 64 + y * 8 + lane] = t;
+                                if (lane < 8) s_vpart[quadl * 256 + bsx * 64 + y * 8 + lane] = t;
                             }
                             if (dump) {
 #pragma unroll
                                 for (int x = 0; x < 8; ++x) {
                                     const uint16_t h16 = static_cast<uint16_t>((x & 1) ? (pk[x >> 1] >> 16) : (pk[x >> 1] & 0xFFFFu));
-                                    dbg_backbone[(static_cast<size_t>(cb0 + bs) * HID + ch) * 64 + y * 8 + x] = from16bits<BF16>(h16);
+                                    dbg_backbone[(static_cast<size_t>(cb0 + bsx) * HID + ch) * 64 + y * 8 + x] = from16bits<BF16>(h16);
                                 }
                             }
                             // accumulator preset for the next layer of this chain
                             ptx::tmem_st_32x8_bcast(tcol + y * nb * 8, __float_as_uint(bias_next));
+                            if (DBG && !kSe && yy == 0 && et == 0) trace_stamp(trace, L * 2 + c, 1);
                         }
+                        if (DBG && et == 0) trace_stamp(trace, L * 2 + c, 7);
                         ptx::tmem_st_wait();
                     };
-                    if (active && !(dbg & 32)) {
+                    auto main_pass_rows = [&](auto ny_c) {
                         if (mode == MODE_SE_RES) {
-                            if (want_v) main_pass(BoolC<true>{}, BoolC<false>{}, BoolC<true>{});
-                            else if (save_res) main_pass(BoolC<true>{}, BoolC<true>{}, BoolC<false>{});
-                            else main_pass(BoolC<true>{}, BoolC<false>{}, BoolC<false>{});
+                            if (want_v) main_pass(BoolC<true>{}, BoolC<false>{}, BoolC<true>{}, ny_c);
+                            else if (save_res) main_pass(BoolC<true>{}, BoolC<true>{}, BoolC<false>{}, ny_c);
+                            else main_pass(BoolC<true>{}, BoolC<false>{}, BoolC<false>{}, ny_c);
                         } else {
-                            if (save_res) main_pass(BoolC<false>{}, BoolC<true>{}, BoolC<false>{});
-                            else main_pass(BoolC<false>{}, BoolC<false>{}, BoolC<false>{});
+                            if (save_res) main_pass(BoolC<false>{}, BoolC<true>{}, BoolC<false>{}, ny_c);
+                            else main_pass(BoolC<false>{}, BoolC<false>{}, BoolC<false>{}, ny_c);
+                        }
+                    };
+                    if (active && !(dbg & 32)) {
+                        if constexpr (DEEP) {
+                            if (ny == 2) main_pass_rows(IntC<2>{});
+                            else if (ny == 4) main_pass_rows(IntC<4>{});
+                            else main_pass_rows(IntC<8>{});
+                        } else {
+                            main_pass_rows(IntC<8>{});
                         }
                     }
+                    if (et == 0) trace_stamp(trace, L * 2 + c, 6);
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async_smem();
-                    ptx::mbar_arrive(&chain_ready[c]);
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&chain_ready[c]);
                     if (et == 0) trace_stamp(trace, L * 2 + c, 5);
-                    if (L == p.num_layers - 2 && c == 0) {
+                    if (!DEEP && L == p.num_layers - 2 && c == 0) {
                         // both chains' v_pre rows are complete (last SE layer): value heads of the whole unit,
                         // hidden under chain 1's p_conv MMAs
                         // (scratch: the SE partial sums and the v_conv staging are dead by now)
@@ -750,6 +840,11 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     }
                     // s_part / s_hid / s_vpart of this item are dead for every thread before the next item writes them
                     if (mode == MODE_SE_RES) ptx::named_bar_sync(1, kEpi);
+                    // single-chain units: the value heads run right behind the value conv, under the p_conv MMAs
+                    if (DEEP && want_v) {
+                        value_phase(p, et, lane, b0, nbc0, nbc1, s_part, s_vpart, s_vpart + 528);
+                        ptx::named_bar_sync(1, kEpi);   // its scratch is read to the end before the heads reuse it
+                    }
                 }
             }
         }
