@@ -370,6 +370,10 @@ __global__ void __launch_bounds__(TowerR2Cfg::kThreads, 1) tower_r2_umma_kernel(
                     float w2r[kSE];
                     uint4 rr[8];
                     const float bias_next = last_layer ? 0.0f : __ldg(p.layers[L + 1].bias + g);   // p_head: padded to 256
+                    // (layer-table fields are read before the wait: behind it each is an L2 round trip on the epilogue's path)
+                    const bool want_v = (mode == MODE_SE_RES) && ly->v_pre != nullptr;
+                    const float vw = want_v ? __ldg(ly->v_w + g) : 0.0f;
+                    const bool save_res = ly->save_res != 0;
                     ptx::mbar_wait_parked(&tmem_full[c], (full_ph >> c) & 1u);
                     full_ph ^= 1u << c;
                     ptx::tc_fence_after();
@@ -438,9 +442,6 @@ __global__ void __launch_bounds__(TowerR2Cfg::kThreads, 1) tower_r2_umma_kernel(
                     }
                     // main pass: (SE scale + residual), ReLU, 16-bit, transpose-store into the buffer of the CTA that holds
                     // my board
-                    const bool want_v = (mode == MODE_SE_RES) && ly->v_pre != nullptr;
-                    const float vw = want_v ? __ldg(ly->v_w + g) : 0.0f;
-                    const bool save_res = ly->save_res != 0;
                     const bool dump = want_v && p.dbg_backbone != nullptr;
                     auto main_pass = [&](auto se_c, auto save_c, auto wantv_c, auto remote_c) {
                         constexpr bool kSe = decltype(se_c)::v, kSave = decltype(save_c)::v, kWantV = decltype(wantv_c)::v,
