@@ -42,6 +42,7 @@ struct ConvLayer {
     int cin_pad = 0;      // padded to a multiple of 64 for the tensor-core path
     void* w16 = nullptr;  // [9][HID][cin_pad] 16-bit, BN scale folded
     float* w32 = nullptr; // [9][cin][HID] fp32, BN scale folded (exact mode)
+    void* w16s = nullptr; // CB_DTYPE_FP32 on the tensor cores: [2][9][HID][cin_pad] fp16, high halves then low halves
     float* bias = nullptr;
     CUtensorMap tm_w;
     CUtensorMap tm_w_half;   // 64-row box (cluster mode of the resident tower)
@@ -120,6 +121,8 @@ struct cb_handle {
     unsigned long long* d_cta_times = nullptr;   // set only inside cb_debug_cta_times
     bool tower_r_ready = false;
     bool use_resident = true;
+    bool use_split = true;               // CB_DTYPE_FP32 handles: fp16-pair operands on the tensor cores (CB_FP32_EXACT=1: CUDA cores)
+    void* p_w16s = nullptr;              // split mode: p_head [2][HID][HID] fp16 (high halves, low halves)
     bool chess_tables_uploaded = false;  // attack tables of the device-side tree kernels
 
     // pinned staging
@@ -224,6 +227,18 @@ int make_weight_map(cb_handle* h, ConvLayer& L) {
     return CB_OK;
 }
 
+// Split mode: one tensor [2 * taps * HID][cin_pad] (high halves, then low halves), 128-row boxes.
+int make_split_map(cb_handle* h, CUtensorMap* tm, void* w, int cin_pad, int taps) {
+    const cuuint64_t dims[2] = {(cuuint64_t)cin_pad, (cuuint64_t)2 * taps * h->hid};
+    const cuuint64_t strides[1] = {(cuuint64_t)cin_pad * 2};
+    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, CB_ECUDA, "cuTensorMapEncodeTiled(split weights) failed: " + std::to_string((int)r));
+    return CB_OK;
+}
+
 void free_buffers(cb_handle* h) {
     drop_graphs(h);
     free_dev(h->d_in); free_dev(h->d_out); free_dev(h->d_x0);
@@ -278,6 +293,13 @@ int ensure_capacity(cb_handle* h, int B) {
     CB_CUDA(h, cudaMalloc(&h->d_vpre, (size_t)cap * 64 * 4));
     h->cap = cap;
     h->csr_cap = csr;
+    if (h->dtype == CB_DTYPE_FP32 && h->hid == 128) {
+        free_dev(h->d_res_scratch);
+        h->d_res_scratch = nullptr;
+        CB_CUDA(h, cudaMalloc(&h->d_res_scratch, (size_t)h->sm_count * TowerRCfg::kScratchPerCta * sizeof(uint4)));
+        int rc;
+        if (h->loaded && (rc = build_tower_tables(h))) return rc;
+    }
     if (h->dtype != CB_DTYPE_FP32) {
         int rc = make_act_map(h, &h->tm_x0, h->d_x0, 64, cap, 10);
         if (rc) return rc;
@@ -298,8 +320,45 @@ int ensure_capacity(cb_handle* h, int B) {
 // Device-side tables of the fused tower kernel.  Rebuilt whenever buffers or weights change.
 int build_tower_tables(cb_handle* h) {
     h->tower_ready = false;
-    if (h->dtype == CB_DTYPE_FP32 || !h->cap || h->convs.empty()) return CB_OK;
+    if (!h->cap || h->convs.empty()) return CB_OK;
     const int nl = (int)h->convs.size();
+    if (h->dtype == CB_DTYPE_FP32) {
+        // fp16-pair mode of the resident tower (128 channels): the map table points at the split weight tensors
+        h->tower_r_ready = false;
+        if (h->hid != 128 || !h->p_w16s) return CB_OK;
+        std::vector<CUtensorMap> mr(nl + 1);
+        int rc;
+        for (int l = 0; l < nl; ++l)
+            if ((rc = make_split_map(h, &mr[l], h->convs[l].w16s, h->convs[l].cin_pad, 9))) return rc;
+        if ((rc = make_split_map(h, &mr[nl], h->p_w16s, h->hid, 1))) return rc;
+        std::vector<TowerRLayer> lr(nl + 1);
+        memset(lr.data(), 0, sizeof(TowerRLayer) * (nl + 1));
+        for (int l = 0; l < nl; ++l) {
+            lr[l].w_map = l;
+            lr[l].kc_in = l == 0 ? 1 : h->hid / 64;
+            lr[l].mode = (l >= 1 && l < nl - 1 && (l & 1) == 0) ? MODE_SE_RES : MODE_RELU;
+            lr[l].bias = h->convs[l].bias;
+            lr[l].ntaps = 9;
+            lr[l].w_lo_off = 9 * h->hid;
+        }
+        lr[nl].w_map = nl; lr[nl].kc_in = h->hid / 64; lr[nl].mode = MODE_POLICY; lr[nl].bias = h->p_bias_r;
+        lr[nl].ntaps = 1; lr[nl].w_row_off = -4 * h->hid; lr[nl].w_lo_off = h->hid;
+        lr[0].save_res = 1;
+        for (int i = 0; i < h->blocks; ++i) {
+            TowerRLayer& b = lr[2 + 2 * i];
+            b.se_w1 = h->se_w1[i]; b.se_w2 = h->se_w2[i];
+            b.save_res = i < h->blocks - 1;
+            if (i == h->blocks - 1) { b.v_w = h->v_w; b.v_pre = h->d_vpre; }
+        }
+        free_dev(h->d_maps_r); free_dev(h->d_layers_r);
+        h->d_maps_r = nullptr; h->d_layers_r = nullptr;
+        CB_CUDA(h, cudaMalloc(&h->d_maps_r, mr.size() * sizeof(CUtensorMap)));
+        CB_CUDA(h, cudaMalloc(&h->d_layers_r, lr.size() * sizeof(TowerRLayer)));
+        CB_CUDA(h, cudaMemcpy(h->d_maps_r, mr.data(), mr.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        CB_CUDA(h, cudaMemcpy(h->d_layers_r, lr.data(), lr.size() * sizeof(TowerRLayer), cudaMemcpyHostToDevice));
+        h->tower_r_ready = true;
+        return CB_OK;
+    }
     std::vector<CUtensorMap> maps(7 + nl);
     maps[0] = h->tm_x0;
     for (int i = 0; i < 3; ++i) { maps[1 + i] = h->tm_act_ld[i]; maps[4 + i] = h->tm_act_st[i]; }
@@ -377,7 +436,9 @@ int build_tower_tables(cb_handle* h) {
 // 128-channel ones with CB_TOWER_PAIR=1; 256-channel ones with it too), 3 the shared-memory-resident single-launch forward
 // (128-channel nets), 4 the resident forward on CTA pairs (256-channel nets: tower + policy head, then value_head_kernel).
 int fused_kind(const cb_handle* h) {
-    if (h->dtype == CB_DTYPE_FP32 || !h->use_fused || h->layer_limit != 0) return 0;
+    if (!h->use_fused || h->layer_limit != 0) return 0;
+    // CB_DTYPE_FP32: the resident forward with fp16-pair operands (128 channels), else the CUDA-core layers
+    if (h->dtype == CB_DTYPE_FP32) return (h->hid == 128 && h->use_split && h->use_resident && h->tower_r_ready) ? 3 : 0;
     if (h->hid == 128 && h->use_resident && h->tower_r_ready) return 3;
     if (h->hid == 256 && h->use_resident && h->tower_r_ready) return 4;
     return h->tower_ready ? 1 : 0;
@@ -434,8 +495,14 @@ int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bo
     tp.vp.k_out += board0;
     tp.num_layers = (int)h->convs.size() + 1;
     tp.num_boards = B;
+    const bool split = h->dtype == CB_DTYPE_FP32;   // fp16-pair operands: one chain of at most 4 boards per unit
     tp.num_units = tower_r_units(h, B);
-    if (unit_cap > 0 && tp.num_units > unit_cap && (long long)unit_cap * 8 >= B) tp.num_units = unit_cap;
+    if (split) {
+        const int even = h->sm_count * ((B + 4 * h->sm_count - 1) / (4 * h->sm_count));
+        tp.num_units = even < B ? even : B;
+    } else if (unit_cap > 0 && tp.num_units > unit_cap && (long long)unit_cap * 8 >= B) {
+        tp.num_units = unit_cap;
+    }
     tp.res_scratch = h->d_res_scratch;
     tp.dbg_backbone = h->d_dbg_backbone;
     tp.trace = h->d_trace;
@@ -448,11 +515,13 @@ int launch_tower_r(cb_handle* h, int B, const PolicyOut& po, int material_on, bo
     // cluster mode (pairs of CTAs share the weight stream): one unit per CTA, an even grid, and every unit with
     // the same number of chains (all of 5..8 boards, or all of 1..4), so both CTAs of a pair walk the same stages
     const int n_lo = B / tp.num_units, n_hi = (B + tp.num_units - 1) / tp.num_units;
-    const bool cl2 = h->use_cluster && !debug && tp.num_units == grid && (grid & 1) == 0 && (n_lo >= 5 || n_hi <= 4);
+    const bool cl2 = !split && h->use_cluster && !debug && tp.num_units == grid && (grid & 1) == 0 && (n_lo >= 5 || n_hi <= 4);
     // every unit a single chain (at most 4 boards per CTA): the deep weight ring (latency-bound small batches)
-    const bool deep = !cl2 && n_hi <= 4 && !getenv("CB_NO_DEEP_RING");
+    const bool deep = !split && !cl2 && n_hi <= 4 && !getenv("CB_NO_DEEP_RING");
     void (*kern)(const TowerRParams);
-    if (h->dtype == CB_DTYPE_BF16)
+    if (split)
+        kern = debug ? tower_r_umma_kernel<false, true, false, false, true> : tower_r_umma_kernel<false, false, false, false, true>;
+    else if (h->dtype == CB_DTYPE_BF16)
         kern = cl2 ? tower_r_umma_kernel<true, false, true>
              : debug ? (deep ? tower_r_umma_kernel<true, true, false, true> : tower_r_umma_kernel<true, true, false>)
              : deep ? tower_r_umma_kernel<true, false, false, true> : tower_r_umma_kernel<true, false, false>;
@@ -970,6 +1039,8 @@ int cb_create(cb_handle** out, int device, int num_blocks, int hidden, int dtype
     // cycles (sustained 195.9 us vs 188.1 us per forward at batch 1024).  CB_CLUSTER=1 turns it on.
     const char* nc = getenv("CB_CLUSTER");
     h->use_cluster = nc && nc[0] == '1';
+    const char* fe = getenv("CB_FP32_EXACT");   // CB_DTYPE_FP32 on CUDA cores (fp32 FMA: the exact mode) instead of fp16 pairs
+    h->use_split = !(fe && fe[0] == '1');
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         delete h;
@@ -1005,11 +1076,11 @@ void cb_destroy(cb_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_buffers(h);
-    for (auto& L : h->convs) { free_dev(L.w16); free_dev(L.w32); free_dev(L.bias); }
+    for (auto& L : h->convs) { free_dev(L.w16); free_dev(L.w16s); free_dev(L.w32); free_dev(L.bias); }
     for (auto p : h->se_w1) free_dev(p);
     for (auto p : h->se_w2) free_dev(p);
     free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
-    free_dev(h->p_w16); free_dev(h->p_w16r); free_dev(h->p_bias_r);
+    free_dev(h->p_w16); free_dev(h->p_w16r); free_dev(h->p_bias_r); free_dev(h->p_w16s);
     free_dev(h->d_maps); free_dev(h->d_layers);
     free_dev(h->d_maps_r); free_dev(h->d_layers_r); free_dev(h->d_res_scratch); free_dev(h->d_maps_r_half);
     free_dev(h->d_flush);
@@ -1053,13 +1124,13 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
     CB_CUDA(h, cudaSetDevice(h->device));
     CB_CUDA(h, cudaStreamSynchronize(h->stream));
     drop_graphs(h);
-    for (auto& L : h->convs) { free_dev(L.w16); free_dev(L.w32); free_dev(L.bias); }
+    for (auto& L : h->convs) { free_dev(L.w16); free_dev(L.w16s); free_dev(L.w32); free_dev(L.bias); }
     for (auto p : h->se_w1) free_dev(p);
     for (auto p : h->se_w2) free_dev(p);
     h->convs.clear(); h->se_w1.clear(); h->se_w2.clear();
     free_dev(h->p_wt); free_dev(h->p_bias); free_dev(h->v_w); free_dev(h->fc_wt); free_dev(h->fc_b); free_dev(h->out_w);
-    free_dev(h->p_w16); free_dev(h->p_w16r); free_dev(h->p_bias_r);
-    h->p_w16 = nullptr; h->p_w16r = nullptr; h->p_bias_r = nullptr;
+    free_dev(h->p_w16); free_dev(h->p_w16r); free_dev(h->p_bias_r); free_dev(h->p_w16s);
+    h->p_w16 = nullptr; h->p_w16r = nullptr; h->p_bias_r = nullptr; h->p_w16s = nullptr;
     h->p_wt = h->p_bias = h->v_w = h->fc_wt = h->fc_b = h->out_w = nullptr;
     h->loaded = false;
 
@@ -1092,6 +1163,22 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
                     for (int t = 0; t < 9; ++t)
                         w32[((size_t)t * cin + ci) * H + co] = w[((size_t)co * cin + ci) * 9 + t] * scale[co];
             if ((rc = upload(w32.data(), w32.size() * 4, (void**)&L.w32))) return rc;
+            if (H == 128) {
+                // fp16 pairs: w = hi + lo, hi = fp16(w), lo = fp16(w - hi); [2][9][H][cin_pad]
+                std::vector<uint16_t> ws((size_t)2 * 9 * H * L.cin_pad, 0);
+                const size_t lo_off = (size_t)9 * H * L.cin_pad;
+                for (int co = 0; co < H; ++co)
+                    for (int ci = 0; ci < cin; ++ci)
+                        for (int t = 0; t < 9; ++t) {
+                            const float v = w[((size_t)co * cin + ci) * 9 + t] * scale[co];
+                            const __half hi = __float2half_rn(v);
+                            const __half lo = __float2half_rn(v - __half2float(hi));
+                            const size_t at = ((size_t)t * H + co) * L.cin_pad + ci;
+                            memcpy(&ws[at], &hi, 2);
+                            memcpy(&ws[lo_off + at], &lo, 2);
+                        }
+                if ((rc = upload(ws.data(), ws.size() * 2, &L.w16s))) return rc;
+            }
         } else {
             std::vector<uint16_t> w16((size_t)9 * H * L.cin_pad, 0);
             for (int co = 0; co < H; ++co)
@@ -1124,6 +1211,21 @@ int cb_load_weights(cb_handle* h, const float* blob, size_t n_floats) {
         if ((rc = upload(wt.data(), wt.size() * 4, (void**)&h->p_wt))) return rc;
         const float* pb = take(73);
         if ((rc = upload(pb, 73 * 4, (void**)&h->p_bias))) return rc;
+        if (h->dtype == CB_DTYPE_FP32 && H == 128) {
+            std::vector<uint16_t> ws((size_t)2 * H * H, 0);
+            for (int c = 0; c < 73; ++c)
+                for (int k = 0; k < H; ++k) {
+                    const float v = pw[(size_t)c * H + k];
+                    const __half hi = __float2half_rn(v);
+                    const __half lo = __float2half_rn(v - __half2float(hi));
+                    memcpy(&ws[(size_t)c * H + k], &hi, 2);
+                    memcpy(&ws[(size_t)H * H + (size_t)c * H + k], &lo, 2);
+                }
+            if ((rc = upload(ws.data(), ws.size() * 2, &h->p_w16s))) return rc;
+            std::vector<float> br(H, 0.0f);
+            memcpy(br.data(), pb, 73 * 4);
+            if ((rc = upload(br.data(), (size_t)H * 4, (void**)&h->p_bias_r))) return rc;
+        }
         if (h->dtype != CB_DTYPE_FP32) {
             std::vector<uint16_t> w16((size_t)80 * H, 0);
             for (int c = 0; c < 73; ++c)

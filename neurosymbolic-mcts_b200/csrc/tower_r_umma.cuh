@@ -69,6 +69,7 @@ struct TowerRLayer {
     int save_res;                // 1: the output is a block input, park it for the residual add
     int ntaps;                   // 9 (3x3 conv) or 1 (1x1 conv: only the centre tap of the tap order)
     int w_row_off;               // added to tap * 128 to form the weight row coordinate (-512 for the 1x1 conv)
+    int w_lo_off;                // SPLIT: rows between a weight tile and the tile of its low halves (taps * 128)
     const float* bias;
     const float* se_w1;
     const float* se_w2;
@@ -155,6 +156,16 @@ __device__ __forceinline__ uint32_t pack_relu16(float lo, float hi) {
     if constexpr (BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     else asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
+}
+
+// lo, hi rounded to fp16 and packed (lo in the low half), no clamp: the low halves of the split mode are signed
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -344,8 +355,16 @@ __device__ __forceinline__ void value_phase(const TowerRParams& p, int et, int l
 // bounds such launches is the hand-off of a ring stage, not the stream or the MMAs (tools/exp_stage.cu, one SM alone:
 // wait + 4 MMAs + commit per 16 KB costs 349 cycles at N = 64 against an MMA floor of 192; 8 MMAs per barrier cost
 // 273 per 16 KB; N >= 192 runs at the MMA floor either way; one SM pulls up to 125 B/clk through TMA).
-template <bool BF16, bool DBG, bool CL2, bool DEEP = false>
+//
+// SPLIT = true (CB_DTYPE_FP32 on the tensor cores): every operand is a PAIR of fp16 numbers, x = x_hi + x_lo with
+// x_hi = fp16(x), x_lo = fp16(x - x_hi) (22 significant bits), and a product is three MMAs into the same fp32
+// accumulator: W_hi X_hi + W_hi X_lo + W_lo X_hi (the dropped W_lo X_lo term is 2^-22 relative).  The unit is ONE chain of up
+// to 4 boards: chain buffer 0 holds X_hi, chain buffer 1 X_lo (same row layout); the weight tensor carries the low halves
+// `w_lo_off` rows behind the high ones and streams as two stages per tap and 64-channel half; the epilogue writes both
+// halves and parks the block input as a pair.  Measured against the reference's fp32 outputs: see DESIGN section 5.
+template <bool BF16, bool DBG, bool CL2, bool DEEP = false, bool SPLIT = false>
 __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(const TowerRParams p) {
+    static_assert(!SPLIT || (!BF16 && !CL2 && !DEEP), "the split mode is fp16 pairs on the plain single-CTA ring");
     const int dbg = DBG ? p.dbg : 0;
     long long* const trace = DBG ? p.trace : nullptr;
     unsigned long long* const cta_times = DBG ? p.cta_times : nullptr;
@@ -442,6 +461,16 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             }
                             __syncwarp();
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                            if constexpr (SPLIT) {
+                                ptx::mbar_wait(&w_empty[ws], wph ^ 1);
+                                if (ptx::elect_one()) {
+                                    ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::kWBytes);
+                                    ptx::tma_load_2d(w_base + ws * Cfg::kWBytes, tm_w, &w_full[ws], kc * 64,
+                                                     tap * HID + w_row_off + ly->w_lo_off);
+                                }
+                                __syncwarp();
+                                if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                            }
                         }
                     }
                 }
@@ -518,12 +547,30 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
                                         ptx::umma_f16_lohi(d_t, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);   // bias preset
+                                    if constexpr (SPLIT) {   // W_hi X_lo: the low halves live in chain buffer 1
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            ptx::umma_f16_lohi(d_t, a_lo + 2 * k, a_hi, b_lo + (Cfg::kChainBytes >> 4) + 2 * k, b_hi, idesc, 1u);
+                                    }
                                 }
                                 if constexpr (CL2) ptx::umma_commit_mc(w_empty + ws, 3);   // release the slot in both CTAs
                                 else ptx::umma_commit(w_empty + ws);
                             }
                             __syncwarp();
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                            if constexpr (SPLIT) {       // W_lo X_hi
+                                ptx::mbar_wait(w_full + ws, wph);
+                                if (ptx::elect_one()) {
+                                    const uint32_t a_lo = a_lo0 + ws * (Cfg::kWBytes >> 4);
+                                    const uint32_t b_lo = b_lo_t + kc * (Cfg::kHalfBytes >> 4);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        ptx::umma_f16_lohi(d_t, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, 1u);
+                                    ptx::umma_commit(w_empty + ws);
+                                }
+                                __syncwarp();
+                                if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                            }
                         }
                     }
                     if (ptx::elect_one()) ptx::umma_commit(&tmem_full[c]);
@@ -590,6 +637,16 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                     if (!data) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) row1[i ^ (r & 7)] = make_uint4(0, 0, 0, 0);   // (rotated: no bank conflicts)
+                    }
+                    if constexpr (SPLIT) {   // X_lo: zero planes (0 / 1 are exact), zero padding rows
+                        uint4* lo0 = reinterpret_cast<uint4*>(buf + Cfg::kChainBytes + r * 128);
+                        uint4* lo1 = reinterpret_cast<uint4*>(buf + Cfg::kChainBytes + Cfg::kHalfBytes + r * 128);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) lo0[i ^ (r & 7)] = make_uint4(0, 0, 0, 0);
+                        if (!data) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) lo1[i ^ (r & 7)] = make_uint4(0, 0, 0, 0);
+                        }
                     }
                 }
                 // accumulator preset: the folded-BN bias of the first layer (every MMA accumulates)
@@ -738,9 +795,14 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                         constexpr int kNy = decltype(ny_c)::v;     // rows per thread: compile-time, so that a short pass is short CODE
                                                                    // (the epilogue of a single-chain unit runs from a cold instruction cache)
                         const uint32_t buf_ch = ptx::smem_u32(buf) + kc_off + (cb2 & ~2u);   // the even channel of my pair
+                        // SPLIT: the low halves of the block input, fetched one row ahead (the high halves sit in rr)
+                        uint4 rl = make_uint4(0, 0, 0, 0);
+                        if constexpr (SPLIT && kSe) rl = __ldcg(my_res_x + (32 + y0) * HID);
 #pragma unroll
                         for (int yy = 0; yy < kNy; ++yy) {
                             const int y = y0 + yy;
+                            [[maybe_unused]] const uint4 rl_cur = rl;
+                            if constexpr (SPLIT && kSe) { if (yy + 1 < kNy) rl = __ldcg(my_res_x + (32 + y + 1) * HID); }
                             uint32_t r[8];
                             ptx::tmem_ld_32x8(tcol + y * nb * 8, r);
                             ptx::tmem_ld_wait();
@@ -750,15 +812,33 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                             for (int x = 0; x < 8; ++x) v[x] = __uint_as_float(r[x]);
                             if constexpr (kSe) {
                                 const uint32_t w[4] = {rr[yy].x, rr[yy].y, rr[yy].z, rr[yy].w};
+                                if constexpr (SPLIT) {
+                                    const uint32_t wl[4] = {rl_cur.x, rl_cur.y, rl_cur.z, rl_cur.w};
 #pragma unroll
-                                for (int x = 0; x < 8; ++x) {
-                                    const uint32_t h = (x & 1) ? (w[x >> 1] >> 16) : (w[x >> 1] & 0xFFFFu);
-                                    v[x] = fmaf(v[x], scale, from16bits<BF16>(static_cast<uint16_t>(h)));
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 a = unpack_f16x2(w[q]), b = unpack_f16x2(wl[q]);
+                                        v[2 * q] = fmaf(v[2 * q], scale, a.x + b.x);
+                                        v[2 * q + 1] = fmaf(v[2 * q + 1], scale, a.y + b.y);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int x = 0; x < 8; ++x) {
+                                        const uint32_t h = (x & 1) ? (w[x >> 1] >> 16) : (w[x >> 1] & 0xFFFFu);
+                                        v[x] = fmaf(v[x], scale, from16bits<BF16>(static_cast<uint16_t>(h)));
+                                    }
                                 }
                             }
                             uint32_t pk[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) pk[q] = pack_relu16<BF16>(v[2 * q], v[2 * q + 1]);
+                            uint32_t pl[4] = {0, 0, 0, 0};    // SPLIT: what the fp16 rounding of max(v, 0) left over
+                            if constexpr (SPLIT) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 h2 = unpack_f16x2(pk[q]);
+                                    pl[q] = pack_f16x2(fmaxf(v[2 * q], 0.0f) - h2.x, fmaxf(v[2 * q + 1], 0.0f) - h2.y);
+                                }
+                            }
                             // rows of group (y, bs): ((y + halo) * nb + bs) * 9 + 1 + x, swizzled by absolute address.
                             // Lane pairs (channels ch, ch ^ 1) trade halves of the group so that every store is one
                             // 32-bit word = two adjacent channels of one pixel: the even lane writes pixels 0..3, the
@@ -775,7 +855,23 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
                                 const uint32_t addr = buf_ch + row * 128 + ((cq ^ (row & 7)) << 4);
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(wd[x]) : "memory");
                             }
-                            if constexpr (kSave) __stcg(my_res_x + (c * 32 + y) * HID, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                            if constexpr (SPLIT) {   // the same transpose-store for the low halves, into chain buffer 1
+                                const uint32_t p0 = __shfl_xor_sync(0xffffffffu, odd ? pl[0] : pl[2], 1);
+                                const uint32_t p1 = __shfl_xor_sync(0xffffffffu, odd ? pl[1] : pl[3], 1);
+                                const uint32_t n0 = odd ? pl[2] : pl[0], n1 = odd ? pl[3] : pl[1];
+                                const uint32_t wl[4] = {__byte_perm(n0, p0, sel_lo), __byte_perm(n0, p0, sel_hi),
+                                                        __byte_perm(n1, p1, sel_lo), __byte_perm(n1, p1, sel_hi)};
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) {
+                                    const uint32_t row = row0 + x;
+                                    const uint32_t addr = buf_ch + Cfg::kChainBytes + row * 128 + ((cq ^ (row & 7)) << 4);
+                                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(wl[x]) : "memory");
+                                }
+                            }
+                            if constexpr (kSave) {
+                                __stcg(my_res_x + (c * 32 + y) * HID, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                                if constexpr (SPLIT) __stcg(my_res_x + (32 + y) * HID, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+                            }
                             if constexpr (kWantV) {
                                 // value 1x1 conv: sum over this warp's 32 channels for each of the 8 pixels
                                 float tv[8];
@@ -788,7 +884,9 @@ __global__ void __launch_bounds__(TowerRCfg::kThreads, 1) tower_r_umma_kernel(co
 #pragma unroll
                                 for (int x = 0; x < 8; ++x) {
                                     const uint16_t h16 = static_cast<uint16_t>((x & 1) ? (pk[x >> 1] >> 16) : (pk[x >> 1] & 0xFFFFu));
-                                    dbg_backbone[(static_cast<size_t>(cb0 + bsx) * HID + ch) * 64 + y * 8 + x] = from16bits<BF16>(h16);
+                                    const uint16_t l16 = static_cast<uint16_t>((x & 1) ? (pl[x >> 1] >> 16) : (pl[x >> 1] & 0xFFFFu));
+                                    dbg_backbone[(static_cast<size_t>(cb0 + bsx) * HID + ch) * 64 + y * 8 + x] =
+                                        from16bits<BF16>(h16) + (SPLIT ? from16bits<false>(l16) : 0.0f);
                                 }
                             }
                             // accumulator preset for the next layer of this chain

@@ -68,19 +68,27 @@ def test_static_pesto_bit_exact(cb, positions):
 
 
 # ------------------------------------------------------------------ network: golden fixtures
-@pytest.mark.parametrize("name", ["6x128_A", "6x128_B", "2x128_B", "10x256_B"])
-def test_exact_mode_matches_reference(cb, golden, name):
+@pytest.mark.parametrize("name,cuda_cores", [("6x128_A", False), ("6x128_B", False), ("2x128_B", False), ("6x128_B", True),
+                                             ("2x128_B", True), ("10x256_B", True)])
+def test_exact_mode_matches_reference(cb, golden, name, cuda_cores, monkeypatch):
+    """CB_DTYPE_FP32, the mode that answers the north star's fp32 tolerance (|dV| <= 1e-3, KL <= 1e-4), held here to
+    1e-4 / 1e-5.  128-channel nets run it on the tensor cores: the resident forward with fp16-PAIR operands (x = hi + lo,
+    three MMAs per product, fp32 accumulation); CB_FP32_EXACT=1 and the 256-channel nets run fp32 FMA on CUDA cores."""
+    if cuda_cores:
+        monkeypatch.setenv("CB_FP32_EXACT", "1")
     g, blob = golden(name)
     ev = make_eval(cb, g, blob, "fp32")
     n = g["boards"].shape[0]
     pol, v, k = ev.predict_batch(g["boards"], g["q"], np.ones(n, dtype=np.uint8))
+    assert ev.launches_per_forward() == (1 if not cuda_cores else 3 * int(g["blocks"]) + 5)
     nf = g["log_policy_full"].shape[0]
     assert np.abs(v - g["v_logit"]).max() <= 1e-4 < TOL_V_FP32
     assert np.abs(k - g["k"]).max() <= 1e-6
     assert kl(np.exp(g["log_policy_full"]), pol[:nf]).max() <= 1e-5 < TOL_KL
     np.testing.assert_allclose(pol.sum(axis=1), 1.0, atol=1e-4)
     bb = ev.debug_backbone(4)
-    assert np.abs(bb - g["backbone"]).max() <= 1e-4
+    # (fp16 pairs carry 22 significant bits: measured 7.6e-5 on activations of magnitude ~30, fp32 FMA 1e-6)
+    assert np.abs(bb - g["backbone"]).max() <= (1e-4 if cuda_cores else 1e-5 * max(float(np.abs(g["backbone"]).max()), 10.0))
 
 
 @pytest.mark.parametrize("name,dtype", [("6x128_A", "bf16"), ("6x128_B", "bf16"), ("6x128_B", "fp16"),
@@ -144,7 +152,9 @@ def test_fused_leaf_eval_matches_reference(cb, golden, dtype):
     ev = make_eval(cb, g, blob, dtype)
     n = g["boards"].shape[0]
     pri, v, vf, k = ev.eval_leaves(g["boards"], g["q"], g["move_idx"], g["move_off"], material_on=True)
-    tol_p, tol_v = (2e-6, 1e-4) if dtype == "fp32" else (2e-3, TOL_V_16)
+    # (fp32 mode = fp16-pair operands on the tensor cores; its softmax uses the fast exp / log of the resident kernel)
+    tol_p, tol_v = (1e-5, 1e-4) if dtype == "fp32" else (2e-3, TOL_V_16)
+    print("%s: max |prior - reference| = %.3e" % (dtype, np.abs(pri - g["priors"]).max()))
     assert np.abs(pri - g["priors"]).max() <= tol_p
     for i in range(n):
         lo, hi = int(g["move_off"][i]), int(g["move_off"][i + 1])
@@ -293,19 +303,21 @@ def test_pair_kernel_batch_shapes_are_bit_identical(cb, golden, positions, dtype
     assert np.array_equal(vs, vg[800:]) and np.array_equal(small, pol[800:])
 
 
-def test_ragged_batch_sizes_are_bit_identical_to_the_full_batch(cb, golden, positions):
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_ragged_batch_sizes_are_bit_identical_to_the_full_batch(cb, golden, positions, dtype):
     """Every way the resident tower splits a batch into units / chains (1..4 boards per chain, with and
     without y-halo rows, one or several units per SM) must give each position exactly the result it gets
     inside the full batch: priors, v_logit and v_final bit for bit, for the first B positions."""
     g, blob = golden("6x128_B")
-    ev = make_eval(cb, g, blob, "bf16")
+    ev = make_eval(cb, g, blob, dtype)
     boards, idx, off, _ = positions
     Bmax = 2500
     q = O.static_q(boards[:Bmax])
     pri, v, vf, k = ev.eval_leaves(boards[:Bmax], q, idx[:off[Bmax]], off[:Bmax + 1])
     assert np.isfinite(pri).all() and np.isfinite(v).all()
-    for B in (1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 33, 147, 148, 149, 295, 296, 297, 443, 591, 1023, 1183, 1184,
-              1185, 1337, 2049):
+    sizes = (1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 33, 147, 148, 149, 295, 296, 297, 443, 591, 1023, 1183, 1184,
+             1185, 1337, 2049)
+    for B in sizes if dtype == "bf16" else (1, 2, 3, 4, 5, 9, 148, 149, 297, 591, 593, 1185):
         p_b, v_b, vf_b, _ = ev.eval_leaves(boards[:B], q[:B], idx[:off[B]], off[:B + 1])
         assert np.array_equal(v_b, v[:B]), "v_logit differs at batch %d" % B
         assert np.array_equal(vf_b, vf[:B]), "v_final differs at batch %d" % B
