@@ -45,7 +45,9 @@ enum {
 
 /* Arithmetic mode of the convolution tower. */
 enum {
-    CB_DTYPE_FP32 = 0, /* exact mode: fp32 CUDA-core implicit GEMM (validation, |dv| <= 1e-3 bar) */
+    CB_DTYPE_FP32 = 0, /* the mode of the fp32 tolerance (|dv| <= 1e-3): 128-channel nets run the resident forward on
+                          tcgen05 with fp16-PAIR operands (x = hi + lo, three MMAs per product, fp32 accumulate; measured
+                          1.2e-5); other nets, and every net under CB_FP32_EXACT=1, run fp32 FMA on CUDA cores (4e-7) */
     CB_DTYPE_BF16 = 1, /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate in TMEM */
     CB_DTYPE_FP16 = 2  /* tcgen05 kind::f16 with fp16 operands, fp32 accumulate in TMEM */
 };
