@@ -477,16 +477,18 @@ def main():
             np.zeros((0, D.RECORD_FLOATS), dtype=np.float32)
         ns = [None] * world
         dist.all_gather_object(ns, int(local.shape[0]))
-        D.gather_samples(local[:min(8, local.shape[0])], dst=0)          # communicator and kernels warm
-        D._pinned("in", (max(ns), D.RECORD_FLOATS))                       # staging buffers exist before the timed gather
-        if rank == 0:
-            D._pinned("out", (sum(ns), D.RECORD_FLOATS))
+        # the records travel in their lossless sparse wire form (caissa_b200/distributed.py pack_records: ~0.9 KB instead
+        # of 23,052 B per record); rank 0 expands them back into the reference's dense records
+        D.gather_samples_packed(local[:min(8, local.shape[0])], dst=0)   # communicator and kernels warm
         torch.cuda.synchronize()
         dist.barrier()
+        gt = {}
         t0 = time.perf_counter()
-        allrec = D.gather_samples(local, dst=0)
+        allrec, wire_bytes = D.gather_samples_packed(local, dst=0, timings=gt)
         torch.cuda.synchronize()
         gather_s = time.perf_counter() - t0
+        wires = [None] * world
+        dist.all_gather_object(wires, (int(wire_bytes), gt.get("pack_s", 0.0), gt.get("wire_s", 0.0), gt.get("unpack_s", 0.0)))
         sums = [None] * world
         dist.all_gather_object(sums, (int(local.shape[0]), zlib.crc32(local.tobytes())))
         ok = True
@@ -500,16 +502,17 @@ def main():
         # rank: collectives must pair up) spread over the run of a self-play pool
         # Small frequent flushes: the cost to the pool grows with the length of each NCCL kernel, not with the bytes per
         # second (tools/exchange_probe.py, 4 x B200: 100 x 128 records/s costs 0.6 %, 25 x 512 costs 2.9 %, 5 x 2560 more).
-        n_flush = max(1, int(args.selfplay_seconds * 100))
+        n_flush = max(1, int(args.selfplay_seconds * 50))
         flushes = [0]
+        host_group = dist.new_group(backend="gloo")   # block sizes are agreed on the host: ONE NCCL kernel per flush, ranks aligned
 
         def gather_loop():
             torch.cuda.set_device(local_rank)
-            chunk = local[:max(1, min(local.shape[0], 128))]
-            for _ in range(n_flush):          # 100 flushes/s x 128 records/rank (12.8 k records/s/rank): above the produced rate
-                D.gather_samples(chunk, dst=0)
+            chunk = local[:max(1, min(local.shape[0], 256))]
+            for _ in range(n_flush):          # 50 flushes/s x 256 records/rank (12.8 k records/s/rank): above the produced rate
+                D.gather_samples_packed(chunk, dst=0, size_group=host_group)
                 flushes[0] += 1
-                time.sleep(0.007)
+                time.sleep(0.012)
         dist.barrier()
         th = threading.Thread(target=gather_loop)
         th.start()
@@ -535,8 +538,12 @@ def main():
         n_all = int(sum(n_r for n_r, _ in sums))
         nccl = {"gather_records": n_all, "gather_seconds": gather_s,
                 "gather_GBps": n_all * D.RECORD_FLOATS * 4 / gather_s / 1e9, "gather_bit_equal_on_rank0": bool(ok),
-                "gather": "every rank's finished-game records of the run above -> rank 0 (one NCCL all-gather, host copy on "
-                          "rank 0 only), device staging included",
+                "gather": "every rank's finished-game records of the run above -> rank 0 in the lossless sparse wire form "
+                          "(pack on every rank, one NCCL all-gather, host copy and expansion to the dense 5763-f32 records on "
+                          "rank 0 only); gather_GBps counts the dense bytes delivered",
+                "gather_wire_bytes": int(sum(w[0] for w in wires)), "gather_dense_bytes": n_all * D.RECORD_FLOATS * 4,
+                "gather_pack_seconds_max": max(w[1] for w in wires), "gather_wire_seconds_rank0": wires[0][2],
+                "gather_unpack_seconds_rank0": wires[0][3],
                 "records_per_s_produced": None, "selfplay_seconds_with_gather": sp_g["seconds"], "selfplay_sims_with_gather": sp_g["sims"],
                 "gather_flushes_during_selfplay": int(flushes[0]),
                 "weights_broadcast_floats": int(got.size), "weights_broadcast_seconds": bcast_s,

@@ -22,6 +22,21 @@ def _worker(rank, world, port, out_dir):
     allrec = D.gather_samples(local)
     on0 = D.gather_samples(local, dst=0)
     assert np.array_equal(D.gather_samples(local, dst=0, transport="gather"), on0)
+    # the sparse wire form: lossless on arbitrary bit patterns, and on records shaped like the real ones
+    sparse = np.zeros((n_local + 2, D.RECORD_FLOATS), dtype=np.float32)
+    sparse[:, :1088] = rng.random((n_local + 2, 1088)) < 0.05
+    sparse[:, 1088:1091] = rng.normal(size=(n_local + 2, 3))
+    for i in range(n_local + 2):
+        sparse[i, 1091 + rng.choice(4672, size=30, replace=False)] = rng.random(30)
+    sparse[0, 7] = -0.0
+    sparse[-1, 5762] = np.float32(1e-42)                      # a denormal in the last column
+    for x in (local, sparse, sparse[:0]):
+        assert np.array_equal(D.unpack_records(D.pack_records(x)).view(np.uint32), np.ascontiguousarray(x).view(np.uint32))
+    assert D.pack_records(sparse).shape[0] < sparse.nbytes // 20
+    packed_all, _ = D.gather_samples_packed(sparse)
+    packed_on0, wire = D.gather_samples_packed(sparse, dst=0, size_group=dist.new_group(backend="gloo"))
+    assert np.array_equal(D.gather_samples(sparse).view(np.uint32), packed_all.view(np.uint32))
+    assert packed_on0.shape[0] == (packed_all.shape[0] if rank == 0 else 0) and wire < sparse.nbytes // 20
     blob = D.broadcast_weights(np.arange(1000, dtype=np.float32) if rank == 0 else None, 1000)
     lo, hi = D.shard_range(1024 + 1, rank, world)
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), local=local, allrec=allrec, on0=on0, blob=blob, lo=lo, hi=hi)
