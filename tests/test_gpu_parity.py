@@ -477,13 +477,13 @@ def test_device_search_equals_the_oracle_with_the_mock_evaluator(cb, golden, moc
         assert root_visits[i] == t.root_stats()["visits"]
 
 
-@pytest.mark.parametrize("material", [False, "pe"])
-def test_device_search_equals_the_oracle_with_the_network(cb, golden, material):
+@pytest.mark.parametrize("material,dtype", [(False, "bf16"), ("pe", "bf16"), (False, "fp32")])
+def test_device_search_equals_the_oracle_with_the_network(cb, golden, material, dtype):
     """The same comparison with the golden 6x128 network as evaluator: the oracle's callback evaluates each leaf through
     cb_eval_leaves (one board per call; the forward is bit-identical whatever the batch), so both searches see the same
     priors and values and must build the same tree — 64 positions x 200 simulations."""
     g, blob = golden("6x128_B")
-    ev = make_eval(cb, g, blob, "bf16")
+    ev = make_eval(cb, g, blob, dtype)     # fp32: the fp16-pair instantiation of the forward under the tree kernels
     boards = search_corpus(56)[:64]
     mode = dict(material_on=bool(material), qsearch="pe" if material else 0)
     kids, root_visits = ev.debug_device_search(boards, sims_per_move=200, seed=3, **mode)
