@@ -9,7 +9,7 @@ using namespace cb;
 
 struct P { const CUtensorMap* map; int iters; long long* out; };
 
-template <int N, int BOXES, int STAGES, int SKEW>
+template <int N, int BOXES, int STAGES, int SKEW, int M = 128>
 __global__ void __launch_bounds__(128, 1) stage_kernel(const P p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -37,9 +37,9 @@ __global__ void __launch_bounds__(128, 1) stage_kernel(const P p) {
         for (int it = 0; it < p.iters; ++it) {
             ptx::mbar_wait(&w_empty[ws], ph ^ 1);
             if (ptx::elect_one()) {
-                ptx::mbar_arrive_expect_tx(&w_full[ws], 16384 * BOXES);
+                ptx::mbar_arrive_expect_tx(&w_full[ws], M * 128 * BOXES);
 #pragma unroll
-                for (int b = 0; b < BOXES; ++b) { ptx::tma_load_2d(ring + (ws * BOXES + b) * 16384, p.map, &w_full[ws], 0, row); row = (row + 128) & 32767; }
+                for (int b = 0; b < BOXES; ++b) { ptx::tma_load_2d(ring + (ws * BOXES + b) * 16384, M == 64 ? p.map + 1 : p.map, &w_full[ws], 0, row); row = (row + M) & 32767; }
             }
             __syncwarp();
             if (++ws == STAGES) { ws = 0; ph ^= 1; }
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128, 1) stage_kernel(const P p) {
         int ws = 0; uint32_t ph = 0;
         const uint64_t a0 = ptx::umma_desc_sw128(ptx::smem_u32(ring)), b0 = ptx::umma_desc_sw128(ptx::smem_u32(bbuf));
         const uint32_t a_lo0 = (uint32_t)a0, a_hi = (uint32_t)(a0 >> 32), b_lo = (uint32_t)b0, b_hi = (uint32_t)(b0 >> 32);
-        constexpr uint32_t idesc = ptx::umma_idesc_f16(1, 128, N);
+        constexpr uint32_t idesc = ptx::umma_idesc_f16(1, M, N);
         long long t0 = clock64();
         if constexpr (SKEW == 0) {
         for (int it = 0; it < p.iters; ++it) {
@@ -98,30 +98,34 @@ __global__ void __launch_bounds__(128, 1) stage_kernel(const P p) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static P g_p; static long long* g_d;
-template <int N, int BOXES, int STAGES, int SKEW = 0>
+template <int N, int BOXES, int STAGES, int SKEW = 0, int M = 128>
 void run() {
     const int smem = 1024 + 8 * 16384 + 65536 + 256;
-    CK(cudaFuncSetAttribute(stage_kernel<N, BOXES, STAGES, SKEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(stage_kernel<N, BOXES, STAGES, SKEW, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     P p = g_p; p.iters = 2048 / BOXES;
     long long c = 0;
-    for (int rep = 0; rep < 2; ++rep) { stage_kernel<N, BOXES, STAGES, SKEW><<<1, 128, smem>>>(p); CK(cudaDeviceSynchronize()); CK(cudaMemcpy(&c, g_d, 8, cudaMemcpyDeviceToHost)); }
-    printf("N=%3d, skew %d, %d x 16 KB + %2d MMAs per barrier, %d slots: %7.1f cycles per 16 KB of weights (MMA floor %d, smem floor %d)\n", N, SKEW, BOXES, 4 * BOXES, STAGES,
-           (double)c / p.iters / BOXES, 4 * (N / 2), 4 * (128 + N) * 32 / 128);
+    for (int rep = 0; rep < 2; ++rep) { stage_kernel<N, BOXES, STAGES, SKEW, M><<<1, 128, smem>>>(p); CK(cudaDeviceSynchronize()); CK(cudaMemcpy(&c, g_d, 8, cudaMemcpyDeviceToHost)); }
+    printf("M=%3d N=%3d, skew %d, %d x 16 KB + %2d MMAs per barrier, %d slots: %7.1f cycles per box of M x 64 weights (MMA floor %d, smem floor %d)\n", M, N, SKEW, BOXES, 4 * BOXES, STAGES,
+           (double)c / p.iters / BOXES, 4 * (N / 2), 4 * (M + N) * 32 / 128);
 }
 int main() {
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
     void* w = nullptr; CK(cudaMalloc(&w, 32768 * 128)); CK(cudaMemset(w, 0, 32768 * 128));
-    CUtensorMap hm; const cuuint64_t dims[2] = {64, 32768}; const cuuint64_t str[1] = {128}; const cuuint32_t box[2] = {64, 128}; const cuuint32_t es[2] = {1, 1};
-    if (((EncodeTiledFn)fn)(&hm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 1;
-    CUtensorMap* dm; CK(cudaMalloc(&dm, sizeof(hm))); CK(cudaMemcpy(dm, &hm, sizeof(hm), cudaMemcpyHostToDevice));
+    CUtensorMap hm[2]; const cuuint64_t dims[2] = {64, 32768}; const cuuint64_t str[1] = {128}; const cuuint32_t es[2] = {1, 1};
+    for (int i = 0; i < 2; ++i) {
+        const cuuint32_t box[2] = {64, (cuuint32_t)(i ? 64 : 128)};
+        if (((EncodeTiledFn)fn)(&hm[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 1;
+    }
+    CUtensorMap* dm; CK(cudaMalloc(&dm, sizeof(hm))); CK(cudaMemcpy(dm, hm, sizeof(hm), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&g_d, 148 * 8));
     g_p = P{dm, 0, g_d};
-    run<64, 1, 4>(); run<64, 1, 4, 2>(); run<64, 1, 4, 3>();
-    run<64, 2, 4>(); run<64, 2, 4, 2>(); run<64, 2, 4, 3>(); run<64, 2, 4, 4>(); run<64, 2, 4, 6>();
-    run<128, 1, 4>(); run<128, 1, 4, 2>(); run<128, 2, 4>(); run<128, 2, 4, 2>(); run<128, 2, 4, 3>(); run<128, 2, 4, 4>();
-    run<192, 1, 4>(); run<192, 1, 4, 2>(); run<224, 1, 4>(); run<224, 1, 4, 2>();
-    run<256, 1, 4>(); run<256, 1, 4, 2>();
+    run<64, 1, 4>(); run<64, 2, 4>(); run<64, 4, 2>();
+    run<128, 1, 4>(); run<128, 2, 4>(); run<256, 1, 4>();
+    // M = 64: a CTA pair splitting the output channels (each CTA streams half of every weight tile)
+    run<64, 1, 4, 0, 64>(); run<64, 2, 4, 0, 64>(); run<64, 4, 2, 0, 64>();
+    run<128, 1, 4, 0, 64>(); run<128, 2, 4, 0, 64>(); run<128, 4, 2, 0, 64>();
+    run<256, 2, 4, 0, 64>();
     return 0;
 }
