@@ -225,7 +225,11 @@ typedef struct cb_selfplay_config {
     int tier1_light;      /* 1: the light Tier-1 gates (the reference's gate at depth 1): a leaf where the side to
                              move mates in one — or, with koth, steps onto the hill / faces a king already on it —
                              is terminal (+1 / -1, src/mcts/tactical_mcts.rs:619-708) and a game whose root hits a
-                             gate is adjudicated (src/bin/self_play.rs:241-283) */
+                             gate is adjudicated (src/bin/self_play.rs:241-283).
+                             2: the reference's Tier-1 gate as self-play runs it: at the leaves mate_search to
+                             mate-in-5 (checking moves only, src/search/mate_search.rs:64-289) and, with koth, the hill
+                             in 3 (src/search/koth.rs:43-65); at the root of every move hill in 3 or
+                             mate_search(board, 5, exhaustive 2); depths: the tier1_* fields at the end */
     int shuffle_children; /* 1: permute the child order of every expansion with the game's random stream.  The reference sets
                              randomize_move_order for self-play (src/bin/self_play.rs:224), but its shuffle never executes:
                              ensure_node_expanded (src/mcts/selection.rs:82-104) returns when the node already has children,
@@ -236,6 +240,10 @@ typedef struct cb_selfplay_config {
                              (InferenceServer::new_mock_biased, src/mcts/inference_server.rs:103-122): uniform priors,
                              v_logit = mock_v_logit, k = mock_k */
     float mock_v_logit, mock_k;
+    int tier1_mate_depth;       /* tier1_light = 2: mate_search_depth of the leaf gate; 0 = 5 (src/bin/self_play.rs:213) */
+    int tier1_exhaustive_depth; /* ... its exhaustive_mate_depth; 0 as in self-play: every level tries checking moves only
+                                   (src/mcts/tactical_mcts.rs:115) */
+    int tier1_koth_depth;       /* ... koth_depth; 0 = 3 (src/mcts/tactical_mcts.rs:124) */
 } cb_selfplay_config;
 
 typedef struct cb_selfplay_stats {
@@ -324,6 +332,15 @@ int cb_principal_exchange_device(cb_handle* h, const cb_board* boards, int n, fl
  * mate_search(board, 1) of src/search/mate_search.rs:64-108 and koth_center_in_n(board, 1) of
  * src/search/koth.rs:43-65, in the order of src/mcts/tactical_mcts.rs:619-708. */
 int cb_light_gates(const cb_board* boards, int n, int koth, int8_t* out);
+/* The Tier-1 leaf gate at full depth on the calling host thread (src/mcts/tactical_mcts.rs:619-708): out[i] as
+ * cb_light_gates; dist[i] (nullable) = terminal_distance of a hit (the hill's n; for a mate the score
+ * 1_000_000 + plies cast to u8, :701).  Self-play's leaf gate is (mate_depth 5, exhaustive_depth 0, koth_depth 3). */
+int cb_tier1_gates(const cb_board* boards, int n, int koth, int mate_depth, int exhaustive_depth, int koth_depth, int8_t* out,
+                   uint8_t* dist);
+/* mate_search (src/search/mate_search.rs:64-108): plies[i] = length of the forced mate found (odd), 0 = none. */
+int cb_mate_search(const cb_board* boards, int n, int max_depth, int exhaustive_depth, int32_t* plies);
+/* koth_center_in_n (src/search/koth.rs:43-65): out[i] = own moves to the hill against every defence (0..max_n), -1 = None. */
+int cb_koth_center_in_n(const cb_board* boards, int n, int max_n, int8_t* out);
 
 int cb_match_run(cb_handle* candidate, cb_handle* current, const cb_match_config* cfg, cb_match_stats* out);
 

@@ -35,7 +35,8 @@ class SelfplayConfig(ctypes.Structure):
                 ("max_sims", ctypes.c_longlong), ("max_games", ctypes.c_longlong), ("max_seconds", ctypes.c_double),
                 ("sample_path", ctypes.c_char_p), ("pipeline", ctypes.c_int), ("aux_handle", ctypes.c_void_p),
                 ("qsearch", ctypes.c_int), ("tier1_light", ctypes.c_int), ("shuffle_children", ctypes.c_int),
-                ("mock_eval", ctypes.c_int), ("mock_v_logit", ctypes.c_float), ("mock_k", ctypes.c_float)]
+                ("mock_eval", ctypes.c_int), ("mock_v_logit", ctypes.c_float), ("mock_k", ctypes.c_float),
+                ("tier1_mate_depth", ctypes.c_int), ("tier1_exhaustive_depth", ctypes.c_int), ("tier1_koth_depth", ctypes.c_int)]
 
 
 class SelfplayStats(ctypes.Structure):
@@ -65,11 +66,15 @@ class CaissaError(RuntimeError):
 
 def selfplay_config(games=1024, sims_per_move=200, max_plies=200, material_on=False, koth=False, threads=0, c_puct=1.414,
                     explore_base=0.80, seed=1, max_sims=0, max_games=0, max_seconds=0.0, sample_path=None, pipeline=1, aux=None,
-                    qsearch=0, tier1_light=False, shuffle_children=False, mock=None):
+                    qsearch=0, tier1_light=False, shuffle_children=False, mock=None, tier1_mate_depth=0, tier1_exhaustive_depth=0,
+                    tier1_koth_depth=0):
+    """tier1_light: False, True (gates at depth 1) or 2 / "deep" (the reference's gate: mate-in-5 by checks, hill in 3)."""
+    tier1_light = 2 if tier1_light == "deep" else int(tier1_light)
     return SelfplayConfig(games, sims_per_move, max_plies, int(bool(material_on)), int(koth), threads, c_puct, explore_base, seed,
                           max_sims, max_games, max_seconds, sample_path.encode() if sample_path else None, pipeline,
                           aux._h if aux is not None else None, _QSEARCH[qsearch], int(tier1_light), int(shuffle_children),
-                          int(mock is not None), float(mock[0]) if mock else 0.0, float(mock[1]) if mock else 0.5)
+                          int(mock is not None), float(mock[0]) if mock else 0.0, float(mock[1]) if mock else 0.5,
+                          int(tier1_mate_depth), int(tier1_exhaustive_depth), int(tier1_koth_depth))
 
 
 class _SearchOut:
@@ -165,6 +170,9 @@ SIGNATURES = {
     "cb_principal_exchange": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP]),
     "cb_principal_exchange_device": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
     "cb_light_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
+    "cb_tier1_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    "cb_mate_search": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
+    "cb_koth_center_in_n": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_debug_device_legal_moves": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_debug_device_light_gates": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_stage_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, _VP, _VP]),
@@ -518,6 +526,35 @@ def light_gates(boards, koth=False):
     out = np.empty(b.shape[0], dtype=np.int8)
     if load_library().cb_light_gates(_ptr(b), b.shape[0], int(koth), _ptr(out)):
         raise CaissaError("cb_light_gates failed")
+    return out
+
+
+def tier1_gates(boards, koth=False, mate_depth=5, exhaustive_depth=0, koth_depth=3):
+    """The Tier-1 leaf gate at full depth (cb_tier1_gates): (int8 value per board: +1 / -1 / 2 = none, uint8 terminal_distance)."""
+    b = _boards_u8(boards)
+    out = np.empty(b.shape[0], dtype=np.int8)
+    dist = np.empty(b.shape[0], dtype=np.uint8)
+    if load_library().cb_tier1_gates(_ptr(b), b.shape[0], int(koth), int(mate_depth), int(exhaustive_depth), int(koth_depth),
+                                     _ptr(out), _ptr(dist)):
+        raise CaissaError("cb_tier1_gates failed")
+    return out, dist
+
+
+def mate_search(boards, max_depth=5, exhaustive_depth=2):
+    """mate_search of the reference (cb_mate_search): plies of the forced mate found per board (odd), 0 = none."""
+    b = _boards_u8(boards)
+    out = np.empty(b.shape[0], dtype=np.int32)
+    if load_library().cb_mate_search(_ptr(b), b.shape[0], int(max_depth), int(exhaustive_depth), _ptr(out)):
+        raise CaissaError("cb_mate_search failed")
+    return out
+
+
+def koth_center_in_n(boards, max_n=3):
+    """koth_center_in_n (cb_koth_center_in_n): own moves to the hill against every defence per board, -1 = None."""
+    b = _boards_u8(boards)
+    out = np.empty(b.shape[0], dtype=np.int8)
+    if load_library().cb_koth_center_in_n(_ptr(b), b.shape[0], int(max_n), _ptr(out)):
+        raise CaissaError("cb_koth_center_in_n failed")
     return out
 
 

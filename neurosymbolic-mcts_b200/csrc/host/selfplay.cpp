@@ -60,6 +60,13 @@ struct Rng {
     double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
 };
 
+// Tier-1 pre-check of the game loop (src/bin/self_play.rs:241-283): does the side to move of `b` win at once?  With the
+// reference's gate: a hill in 3 or mate_search(board, 5, exhaustive 2); with the light gates the same at depth 1.
+bool root_adjudicated(const cb_board& b, const Move* legal, int n, int tier1, bool koth) {
+    if (tier1 >= 2) return (koth && cbchess::koth_center_in_n_host(b, 3) >= 0) || cbchess::mate_search_plies(b, 5, 2) != 0;
+    return cbchess::light_gates_hd(b, legal, n, koth) == 1;
+}
+
 // dM of a position in pawn units: stand pat or the principal-exchange line (qsearch.hpp)
 float material_q(const cb_board& b, int qsearch) {
     return (float)(qsearch == 1 ? cbchess::principal_exchange_cp(b) : cbchess::pesto_cp(b)) / 100.0f;
@@ -68,6 +75,7 @@ float material_q(const cb_board& b, int qsearch) {
 // What the search needs of cb_selfplay_config / cb_match_config.
 struct SearchCfg {
     int sims = 200, material_on = 0, qsearch = 0, koth = 0, tier1_light = 0, shuffle = 0, max_plies = 200;
+    int mate_depth = 5, exhaustive_depth = 0, koth_depth = 3;   // the leaf gate of tier1_light = 2 (src/bin/self_play.rs:213)
     double c_puct = 1.414, explore_base = 0.80;
 };
 
@@ -196,6 +204,8 @@ void select_leaf(Game& g, const SearchCfg& c, std::atomic<long long>& terminal_h
     int tv = 2, td = 0;
     const int us = board.w_to_move ? 0 : 1;
     if (g.leaf_n == 0) tv = in_check(board, us) ? -1 : 0;
+    else if (c.tier1_light >= 2 && cur != 0)
+        tv = cbchess::tier1_gates_host(board, c.koth != 0, c.mate_depth, c.exhaustive_depth, c.koth_depth, &td);
     else if (c.tier1_light && cur != 0) {
         if (c.koth && (board.pieces[(1 - us) * 6 + KING] & kKothCenter)) tv = -1;
         else if (c.koth && cbchess::koth_in_1_hd(board, g.leaf_moves, g.leaf_n)) {
@@ -334,7 +344,7 @@ int play_move(Game& g, const SearchCfg& c) {
             if (reps >= 3 || nb.halfmove >= 100 || g.ply > c.max_plies) result = 0;
             // the game goes on: a position where the side to move wins at once is adjudicated before it is
             // searched (Tier-1 pre-check of the self-play loop, src/bin/self_play.rs:241-283, at depth 1)
-            else if (c.tier1_light && cbchess::light_gates_hd(nb, tmp, n_legal, c.koth != 0) == 1) result = white_moved ? -1 : 1;
+            else if (c.tier1_light && root_adjudicated(nb, tmp, n_legal, c.tier1_light, c.koth != 0)) result = white_moved ? -1 : 1;
         }
     }
     return result;
@@ -455,6 +465,9 @@ SearchCfg search_cfg(const cb_selfplay_config* cfg) {
     c.qsearch = cfg->qsearch;
     c.koth = cfg->koth;
     c.tier1_light = cfg->tier1_light;
+    if (cfg->tier1_mate_depth > 0) c.mate_depth = cfg->tier1_mate_depth;
+    c.exhaustive_depth = cfg->tier1_exhaustive_depth;
+    if (cfg->tier1_koth_depth > 0) c.koth_depth = cfg->tier1_koth_depth;
     c.shuffle = cfg->shuffle_children;
     c.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     c.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414;
@@ -525,6 +538,29 @@ int cb_light_gates(const cb_board* boards, int n, int koth, int8_t* out) {
     return 0;
 }
 
+int cb_tier1_gates(const cb_board* boards, int n, int koth, int mate_depth, int exhaustive_depth, int koth_depth, int8_t* out,
+                   uint8_t* dist) {
+    if (n < 0 || (n > 0 && (!boards || !out))) return 1;
+    for (int i = 0; i < n; ++i) {
+        int d = 0;
+        out[i] = (int8_t)cbchess::tier1_gates_host(boards[i], koth != 0, mate_depth, exhaustive_depth, koth_depth, &d);
+        if (dist) dist[i] = (uint8_t)d;
+    }
+    return 0;
+}
+
+int cb_mate_search(const cb_board* boards, int n, int max_depth, int exhaustive_depth, int32_t* plies) {
+    if (n < 0 || (n > 0 && (!boards || !plies))) return 1;
+    for (int i = 0; i < n; ++i) plies[i] = cbchess::mate_search_plies(boards[i], max_depth, exhaustive_depth);
+    return 0;
+}
+
+int cb_koth_center_in_n(const cb_board* boards, int n, int max_n, int8_t* out) {
+    if (n < 0 || (n > 0 && (!boards || !out))) return 1;
+    for (int i = 0; i < n; ++i) out[i] = (int8_t)cbchess::koth_center_in_n_host(boards[i], max_n);
+    return 0;
+}
+
 int cb_debug_host_search(const cb_selfplay_config* cfg, const cb_board* boards, int n, cb_eval_callback eval, void* user,
                          uint16_t* moves, uint32_t* visits, double* value_sums, int32_t* counts, uint32_t* root_visits) {
     if (!cfg || !boards || n < 0 || !eval || !counts) return CB_EINVAL;
@@ -559,7 +595,7 @@ int cb_debug_host_game(const cb_selfplay_config* cfg, const cb_board* start, uin
     // the game loop's own pre-check of the start position (src/bin/self_play.rs:241-283 at depth 1)
     const int n0 = gen_legal(g.root_board, tmp);
     if (n0 == 0) result = in_check(g.root_board, g.root_board.w_to_move ? 0 : 1) ? (g.root_board.w_to_move ? -1 : 1) : 0;
-    else if (sc.tier1_light && cbchess::light_gates_hd(g.root_board, tmp, n0, sc.koth != 0) == 1) result = g.root_board.w_to_move ? 1 : -1;
+    else if (sc.tier1_light && root_adjudicated(g.root_board, tmp, n0, sc.tier1_light, sc.koth != 0)) result = g.root_board.w_to_move ? 1 : -1;
     while (result == 2) {
         search_with_callback(g, sc, eval, user);
         result = play_move(g, sc);

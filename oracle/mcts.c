@@ -432,25 +432,17 @@ static float leaf_material(const orc_board* b, const orc_mcts_config* cfg) {
 /* evaluate_leaf_node, tactical_mcts.rs:600-810 (gates at depth 1) */
 static double evaluate_leaf(orc_tree* t, node* n, const orc_mcts_config* cfg, orc_eval_fn eval, void* user) {
     if (n->has_term) { t->terminal_hits++; return n->term_value; }
-    if (cfg->koth && cfg->tier1_light) {
-        const int us = n->state.w_to_move ? 0 : 1;
-        if (n->state.pieces[(1 - us) * 6 + K] & CENTER) {
-            n->has_term = 1; n->term_value = -1.0; n->has_dist = 1; n->term_dist = 0; n->is_terminal = 1;
+    if (cfg->tier1_light) { /* hill first (:619-647), then the mate (:650-708); depths: 1, or the configured ones */
+        const int deep = cfg->tier1_light >= 2;
+        int dist = 0;
+        const int v = orc_tier1_gates(&n->state, cfg->koth, deep ? (cfg->mate_depth > 0 ? cfg->mate_depth : 5) : 1,
+                                      deep ? cfg->exhaustive_mate_depth : 0, deep ? (cfg->koth_depth > 0 ? cfg->koth_depth : 3) : 1, &dist);
+        if (v != 2) {
+            n->has_term = 1; n->term_value = (double)v; n->has_dist = 1; n->term_dist = (uint8_t)dist;
+            if (v < 0) n->is_terminal = 1;
             t->terminal_hits++;
-            return -1.0;
+            return (double)v;
         }
-        if (orc_koth_in_1(&n->state)) {
-            n->has_term = 1; n->term_value = 1.0; n->has_dist = 1;
-            n->term_dist = (n->state.pieces[us * 6 + K] & CENTER) ? 0 : 1;
-            t->terminal_hits++;
-            return 1.0;
-        }
-    }
-    if (cfg->tier1_light && orc_mate_in_1(&n->state)) {
-        n->has_term = 1; n->term_value = 1.0; n->has_dist = 1;
-        n->term_dist = (uint8_t)(1000001u); /* mate_result.0.unsigned_abs() as u8 with score 1_000_000 + 1 */
-        t->terminal_hits++;
-        return 1.0;
     }
     if (!n->has_nn) {
         orc_move mv[ORC_MAX_MOVES];
@@ -625,8 +617,11 @@ int orc_play_game(const orc_board* start, const orc_mcts_config* cfg, uint64_t s
     hist[nh++] = pos_key(&board);
     const int max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     for (;;) {
-        if (cfg->tier1_light) { /* Tier-1 pre-check, :241-283, at depth 1: the side to move wins at once */
-            if ((cfg->koth && orc_koth_in_1(&board)) || orc_mate_in_1(&board)) {
+        if (cfg->tier1_light) { /* Tier-1 pre-check, :241-283: hill in 3 or mate_search(board, 5, exhaustive 2) - the side to
+                                   move wins at once; tier1_light = 1 runs both at depth 1 */
+            const int deep = cfg->tier1_light >= 2;
+            if ((cfg->koth && orc_koth_center_in_n(&board, deep ? 3 : 1, NULL) >= 0) ||
+                orc_mate_search(&board, deep ? 5 : 1, deep ? 2 : 0, NULL, NULL) != 0) {
                 early = 1;
                 early_score = board.w_to_move ? 1 : -1;
                 break;

@@ -79,6 +79,12 @@ float orc_forced_principal_exchange(const orc_board* b, uint32_t* nodes, int* lo
 int   orc_mate_in_1(const orc_board* b);            /* src/search/mate_search.rs:64-108, max_depth 1 */
 int   orc_koth_in_1(const orc_board* b);            /* src/search/koth.rs:43-65, max_n 1 */
 int   orc_light_gates(const orc_board* b, int koth); /* src/mcts/tactical_mcts.rs:619-708: -1, +1 or 2 (none) */
+/* the Tier-1 gates at full depth (gates.c) */
+int   orc_mate_search(const orc_board* b, int max_depth, int exhaustive_depth, orc_move* best, int* nodes);
+                                                    /* src/search/mate_search.rs:64-289: 1_000_000 + plies, or 0 */
+int   orc_koth_center_in_n(const orc_board* b, int max_n, uint32_t* nodes); /* src/search/koth.rs:146-268: n, or -1 = None */
+int   orc_tier1_gates(const orc_board* b, int koth, int mate_depth, int exhaustive_depth, int koth_depth, int* dist);
+                                                    /* src/mcts/tactical_mcts.rs:619-708: -1, +1 or 2; *dist = terminal_distance */
 
 /* ---- tree operations (mcts.c): generation order, tactical-first selection, f64 PUCT, backup, reuse, game loop ---- */
 /* gen_pseudo_legal_moves in the reference's order, src/move_generation.rs:287-328: captures (pawns, knights, bishops,
@@ -98,12 +104,16 @@ typedef struct {
     int material_on;      /* enable_material_value */
     int qsearch;          /* dM: 0 static PeSTO / 100, 1 principal exchange */
     int koth;
-    int tier1_light;      /* Tier-1 gates at depth 1 */
+    int tier1_light;      /* Tier-1 gates: 1 at depth 1; 2 the reference's gate (leaves: mate_depth / exhaustive_mate_depth /
+                             koth_depth below; the game loop: hill in 3, mate_search(5, exhaustive 2), self_play.rs:241-283) */
     int shuffle;          /* permute every expansion's child order (the reference's randomize_move_order is dead code in its
                              search loop: selection.rs:82-104 returns before shuffling, the children already exist) */
     int max_plies;        /* game loop: 200 */
     double c_puct;        /* 1.414 */
     double explore_base;  /* 0.80 */
+    int mate_depth;            /* tier1_light = 2: mate_search_depth, 0 = 5 (src/bin/self_play.rs:213) */
+    int exhaustive_mate_depth; /* 0 as in self-play (src/mcts/tactical_mcts.rs:115) */
+    int koth_depth;            /* 0 = 3 (:124) */
 } orc_mcts_config;
 typedef struct orc_tree orc_tree;
 orc_tree* orc_mcts_new(const orc_board* root, uint64_t seed);

@@ -88,6 +88,13 @@ def lib():
             getattr(L, name).restype = ctypes.c_int
         L.orc_light_gates.argtypes = [bp, ctypes.c_int]
         L.orc_light_gates.restype = ctypes.c_int
+        # the Tier-1 gates at full depth (gates.c)
+        L.orc_mate_search.argtypes = [bp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint16), ip]
+        L.orc_mate_search.restype = ctypes.c_int
+        L.orc_koth_center_in_n.argtypes = [bp, ctypes.c_int, up]
+        L.orc_koth_center_in_n.restype = ctypes.c_int
+        L.orc_tier1_gates.argtypes = [bp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ip]
+        L.orc_tier1_gates.restype = ctypes.c_int
         # tree operations (mcts.c)
         L.orc_gen_pseudo_ref.argtypes = [bp, ctypes.POINTER(ctypes.c_uint16), ip]
         L.orc_gen_pseudo_ref.restype = ctypes.c_int
@@ -119,7 +126,8 @@ def lib():
 class MctsConfig(ctypes.Structure):
     _fields_ = [("sims", ctypes.c_int), ("material_on", ctypes.c_int), ("qsearch", ctypes.c_int), ("koth", ctypes.c_int),
                 ("tier1_light", ctypes.c_int), ("shuffle", ctypes.c_int), ("max_plies", ctypes.c_int),
-                ("c_puct", ctypes.c_double), ("explore_base", ctypes.c_double)]
+                ("c_puct", ctypes.c_double), ("explore_base", ctypes.c_double),
+                ("mate_depth", ctypes.c_int), ("exhaustive_mate_depth", ctypes.c_int), ("koth_depth", ctypes.c_int)]
 
 
 class GameSample(ctypes.Structure):
@@ -200,6 +208,14 @@ def make_move(b, m):
     return out
 
 
+def in_check(b, color=None):
+    """Is the king of `color` (0 white, 1 black; default: the side to move) attacked?"""
+    L = lib()
+    L.orc_in_check.argtypes = [ctypes.POINTER(Board), ctypes.c_int]
+    L.orc_in_check.restype = ctypes.c_int
+    return bool(L.orc_in_check(ctypes.byref(b), (0 if b.w_to_move else 1) if color is None else int(color)))
+
+
 def perft(b, depth):
     return lib().orc_perft(ctypes.byref(b), depth)
 
@@ -272,6 +288,29 @@ def light_gates(b, koth=False):
     return lib().orc_light_gates(ctypes.byref(b), int(koth))
 
 
+def mate_search(b, max_depth, exhaustive_depth=2):
+    """mate_search(board, max_depth, exhaustive_depth) -> (score, (from, to, promo) or None, nodes)."""
+    mv = ctypes.c_uint16(0)
+    nodes = ctypes.c_int(0)
+    score = lib().orc_mate_search(ctypes.byref(b), int(max_depth), int(exhaustive_depth), ctypes.byref(mv), ctypes.byref(nodes))
+    m = mv.value
+    return score, ((m & 63, (m >> 6) & 63, (m >> 12) & 7) if m else None), nodes.value
+
+
+def koth_center_in_n(b, max_n=3):
+    """koth_center_in_n_counted -> (n or None, nodes)."""
+    nodes = ctypes.c_uint32(0)
+    n = lib().orc_koth_center_in_n(ctypes.byref(b), int(max_n), ctypes.byref(nodes))
+    return (None if n < 0 else n), nodes.value
+
+
+def tier1_gates(b, koth=False, mate_depth=5, exhaustive_depth=0, koth_depth=3):
+    """The leaf gate at full depth -> (-1 / +1 / 2, terminal_distance)."""
+    dist = ctypes.c_int(0)
+    v = lib().orc_tier1_gates(ctypes.byref(b), int(koth), int(mate_depth), int(exhaustive_depth), int(koth_depth), ctypes.byref(dist))
+    return v, dist.value
+
+
 def pe_q(boards_u8):
     """Principal-exchange material scalar of every board (pawn units, side to move)."""
     q = np.zeros(boards_u8.shape[0], dtype=np.float32)
@@ -290,9 +329,12 @@ def static_q(boards_u8, clip=20.0):
 
 # ---------------------------------------------------------------- tree operations (mcts.c)
 def mcts_config(sims=200, material_on=False, qsearch=0, koth=False, tier1_light=False, shuffle=False, max_plies=200,
-                c_puct=1.414, explore_base=0.80):
-    return MctsConfig(int(sims), int(bool(material_on)), 1 if qsearch in (1, "pe") else 0, int(koth), int(tier1_light),
-                      int(shuffle), int(max_plies), float(c_puct), float(explore_base))
+                c_puct=1.414, explore_base=0.80, mate_depth=0, exhaustive_mate_depth=0, koth_depth=0):
+    """tier1_light: False / True (gates at depth 1) / 2 or "deep" (the reference's gate: mate-in-5 checks only, hill in 3)."""
+    tier1 = 2 if tier1_light == "deep" else int(tier1_light)
+    return MctsConfig(int(sims), int(bool(material_on)), 1 if qsearch in (1, "pe") else 0, int(koth), tier1,
+                      int(shuffle), int(max_plies), float(c_puct), float(explore_base), int(mate_depth),
+                      int(exhaustive_mate_depth), int(koth_depth))
 
 
 def gen_legal_ref(b):

@@ -87,6 +87,36 @@ def test_light_gates_equal_the_oracle(cb):
     assert (cb.light_gates(boards, koth=True) == -1).sum() >= 1
 
 
+def test_deep_gates_equal_the_oracle(cb):
+    """The Tier-1 gates at full depth on the host (csrc/host/gates.hpp: mate search to mate-in-5, hill in 3) against
+    oracle/gates.c, which is pinned to the reference's own tests: value and terminal distance of the leaf gate as self-play
+    runs it (checking moves only), the adjudication search (exhaustive to mate-in-2) and the hill distances."""
+    a, _, _, _ = O.random_positions(4242, 700, 200)
+    boards = np.concatenate([a, np.stack([u8(f) for f in PE_FENS + [
+        "6k1/5ppp/8/8/8/8/8/4R1K1 w - - 0 1", "4r1k1/8/8/8/8/8/5PPP/6K1 b - - 0 1", "7k/R7/5K2/8/8/8/8/8 w - - 0 1",
+        "r1bqkbnr/pppp1ppp/2n5/4p2Q/2B1P3/8/PPPP1PPP/RNB1K1NR w KQkq - 4 4", "k7/1R6/K7/8/8/8/8/8 b - - 0 1",
+        "6k1/5ppp/8/7Q/8/8/8/5RK1 w - - 0 1", "8/8/8/8/8/2K5/8/k7 w - - 0 1", "8/8/8/8/3k4/8/8/K7 w - - 0 1", "8/8/8/8/8/8/1K6/k7 w - - 0 1",
+        "rnbqkbnr/1pppppp1/p6p/8/8/4P3/PPPPKPPP/RNBQ1BNR w kq - 0 3", "rnbqkbnr/pppp1pp1/4p2p/8/8/4P3/PPPPKPPP/RNBQ1BNR w kq - 0 3"]])])
+    obs = [O.array_to_board(r) for r in boards]
+    for koth in (False, True):
+        got_v, got_d = cb.tier1_gates(boards, koth=koth)                                   # (5, 0, 3): self-play's leaf gate
+        want = [O.tier1_gates(b, koth=koth) for b in obs]
+        assert np.array_equal(got_v, np.array([w[0] for w in want], dtype=np.int8))
+        hit = got_v != 2
+        assert np.array_equal(got_d[hit], np.array([w[1] for w in want], dtype=np.uint8)[hit])
+        assert (got_v == 1).sum() >= 8
+    deep = cb.mate_search(boards, 5, 0)
+    assert np.array_equal(deep, np.array([max(0, O.mate_search(b, 5, 0)[0] - 1_000_000) for b in obs], dtype=np.int32))
+    assert (deep >= 3).sum() >= 3                                                          # mates longer than one move are in the corpus
+    sub = boards[:200]
+    adj = cb.mate_search(sub, 3, 2)                                                        # exhaustive levels (costly on the oracle side)
+    assert np.array_equal(adj, np.array([max(0, O.mate_search(b, 3, 2)[0] - 1_000_000) for b in obs[:200]], dtype=np.int32))
+    hill = cb.koth_center_in_n(boards, 3)
+    want_h = np.array([-1 if O.koth_center_in_n(b, 3)[0] is None else O.koth_center_in_n(b, 3)[0] for b in obs], dtype=np.int8)
+    assert np.array_equal(hill, want_h)
+    assert set(np.unique(hill)) >= {-1, 0, 1, 2}
+
+
 @pytest.fixture(scope="module")
 def host_test_exe(cb):
     exe = os.path.join(REPO, "tests", "cpp", "_host_mirror_test")

@@ -54,10 +54,23 @@ def corpus(n_random, seed=77):
 
 
 MODES = [dict(), dict(material_on=True, qsearch="pe"), dict(material_on=True, qsearch=0), dict(koth=True),
-         dict(koth=True, tier1_light=True, material_on=True, qsearch="pe"), dict(tier1_light=True), dict(shuffle_children=True)]
+         dict(koth=True, tier1_light=True, material_on=True, qsearch="pe"), dict(tier1_light=True), dict(shuffle_children=True),
+         dict(tier1_light="deep"), dict(tier1_light="deep", koth=True, material_on=True, qsearch="pe")]
 
 
-@pytest.mark.parametrize("mode", MODES, ids=lambda m: "-".join(sorted(m)) or "vanilla")
+def mode_id(m):
+    return "-".join(k if v is True else "%s=%s" % (k, v) for k, v in sorted(m.items())) or "vanilla"
+
+
+def root_is_adjudicated(b, mode):
+    """The game loop's pre-check (src/bin/self_play.rs:241-283): such roots are never searched."""
+    koth = mode.get("koth", False)
+    if mode.get("tier1_light") == "deep":
+        return (koth and O.koth_center_in_n(b, 3)[0] is not None) or O.mate_search(b, 5, 2)[0] != 0
+    return O.light_gates(b, koth=koth) == 1 or (koth and O.light_gates(b, koth=True) == -1)
+
+
+@pytest.mark.parametrize("mode", MODES, ids=mode_id)
 @pytest.mark.parametrize("fn", [uniform, hashed], ids=["uniform", "hashed"])
 def test_root_statistics_equal_the_oracle(mode, fn):
     boards = corpus(40)
@@ -65,7 +78,7 @@ def test_root_statistics_equal_the_oracle(mode, fn):
         # the game loop adjudicates a root that hits a gate before it is ever searched (src/bin/self_play.rs:241-283), which is
         # what lets the drivers test for mate when a child is first reached rather than when it is created (a node with a
         # mating child is resolved by the gate and never expanded) — so such roots are not part of the search's domain
-        keep = [i for i in range(boards.shape[0]) if O.light_gates(O.array_to_board(boards[i]), koth=mode.get("koth", False)) == 2]
+        keep = [i for i in range(boards.shape[0]) if not root_is_adjudicated(O.array_to_board(boards[i]), mode)]
         boards = boards[keep]
     sims = 200
     kids, root_visits = cb.debug_host_search(boards, host_eval(fn), sims_per_move=sims, seed=3, **mode)
@@ -94,7 +107,7 @@ def test_child_order_is_the_reference_generation_order():
 
 
 @pytest.mark.parametrize("mode", [dict(), dict(material_on=True, qsearch="pe"), dict(koth=True), dict(tier1_light=True, koth=True),
-                                  dict(shuffle_children=True)], ids=lambda m: "-".join(sorted(m)) or "vanilla")
+                                  dict(shuffle_children=True), dict(tier1_light="deep"), dict(tier1_light="deep", koth=True)], ids=mode_id)
 def test_whole_games_equal_the_oracle(mode):
     """Search + move choice + tree reuse + game end over whole games: same samples (positions, visit fractions,
     material scalars), same result, same length."""
