@@ -165,6 +165,10 @@ int cb_debug_backbone(cb_handle* h, int B, float* out);
 int cb_debug_device_legal_moves(cb_handle* h, const cb_board* boards, int n, uint16_t* moves, int32_t* counts);
 /* The device tree kernels' light Tier-1 gates (warp form) on n boards — must equal cb_light_gates (tests). */
 int cb_debug_device_light_gates(cb_handle* h, const cb_board* boards, int n, int koth, int8_t* out);
+/* The device tree kernels' gate at full depth (warp form, one warp per board, resumed in slices of `budget` positions as
+ * the self-play steps do; 0 = one slice) — must equal cb_tier1_gates (tests). */
+int cb_debug_device_tier1_gates(cb_handle* h, const cb_board* boards, int n, int koth, int mate_depth, int exhaustive_depth,
+                                int koth_depth, int budget, int8_t* out, uint8_t* dist);
 /* Same for activation ring buffer `buf` (0..2); with cb_debug_set_layer_limit(n) the tower stops
  * after n convolution launches so individual layers can be compared across arithmetic modes. */
 int cb_debug_act(cb_handle* h, int B, int buf, float* out);
@@ -252,6 +256,8 @@ typedef struct cb_selfplay_stats {
     double seconds, eval_seconds, tree_seconds;
     double mean_batch;
     long long overflow;   /* device pipelines: leaves left unexpanded because a game's node arena was full (0 in a sound run) */
+    long long gate_hits;  /* device pipelines, tier1_light = 2: leaves decided by the gate at full depth */
+    long long gate_waits; /* ... game-steps spent on a suspended gate job (the game completes no simulation in such a step) */
 } cb_selfplay_stats;
 
 int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out);

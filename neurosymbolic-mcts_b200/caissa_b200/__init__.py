@@ -43,7 +43,7 @@ class SelfplayStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_longlong) for n in ("sims", "nn_evals", "terminal_hits", "moves", "games_finished",
                                                  "samples", "steps", "white_wins", "black_wins", "draws")] + \
                [(n, ctypes.c_double) for n in ("seconds", "eval_seconds", "tree_seconds", "mean_batch")] + \
-               [("overflow", ctypes.c_longlong)]
+               [("overflow", ctypes.c_longlong), ("gate_hits", ctypes.c_longlong), ("gate_waits", ctypes.c_longlong)]
 
 
 class MatchConfig(ctypes.Structure):
@@ -175,6 +175,8 @@ SIGNATURES = {
     "cb_koth_center_in_n": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_debug_device_legal_moves": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_debug_device_light_gates": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP]),
+    "cb_debug_device_tier1_gates": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_int, _VP, _VP]),
     "cb_stage_leaves": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_time_resident": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_time_sustained": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_float),
@@ -461,9 +463,19 @@ class Evaluator:
     def debug_set_layer_limit(self, n):
         self._check(self._L.cb_debug_set_layer_limit(self._h, n))
 
+    def debug_device_tier1_gates(self, boards, koth=False, mate_depth=5, exhaustive_depth=0, koth_depth=3, budget=0):
+        """The tree kernels' gate at full depth (warp form) -> (int8 value per board: +1 / -1 / 2, uint8 terminal_distance)."""
+        b = _boards_u8(boards)
+        out = np.empty(b.shape[0], dtype=np.int8)
+        dist = np.empty(b.shape[0], dtype=np.uint8)
+        self._check(self._L.cb_debug_device_tier1_gates(self._h, _ptr(b), b.shape[0], int(koth), int(mate_depth), int(exhaustive_depth),
+                                                        int(koth_depth), int(budget), _ptr(out), _ptr(dist)))
+        return out, dist
+
     def selfplay(self, games=1024, sims_per_move=200, max_plies=200, material_on=False, koth=False, threads=0,
                  c_puct=1.414, explore_base=0.80, seed=1, max_sims=0, max_games=0, max_seconds=0.0, sample_path=None,
-                 pipeline=1, aux=None, qsearch=0, tier1_light=False, shuffle_children=False, mock=None):
+                 pipeline=1, aux=None, qsearch=0, tier1_light=False, shuffle_children=False, mock=None, tier1_mate_depth=0,
+                 tier1_exhaustive_depth=0, tier1_koth_depth=0):
         """Run the self-play pool on this evaluator; returns the stats as a dict.  `aux`: a second Evaluator
         with the same weights that serves the second half-pool in pipeline mode 2.  `qsearch`: 0 stand-pat
         material, 1 principal exchange ("pe").  `mock`: (v_logit, k) replaces the network by the reference's mock
@@ -471,7 +483,9 @@ class Evaluator:
         cfg = selfplay_config(games=games, sims_per_move=sims_per_move, max_plies=max_plies, material_on=material_on, koth=koth,
                               threads=threads, c_puct=c_puct, explore_base=explore_base, seed=seed, max_sims=max_sims,
                               max_games=max_games, max_seconds=max_seconds, sample_path=sample_path, pipeline=pipeline,
-                              aux=aux, qsearch=qsearch, tier1_light=tier1_light, shuffle_children=shuffle_children, mock=mock)
+                              aux=aux, qsearch=qsearch, tier1_light=tier1_light, shuffle_children=shuffle_children, mock=mock,
+                              tier1_mate_depth=tier1_mate_depth, tier1_exhaustive_depth=tier1_exhaustive_depth,
+                              tier1_koth_depth=tier1_koth_depth)
         st = SelfplayStats()
         self._check(self._L.cb_selfplay_run(self._h, ctypes.byref(cfg), ctypes.byref(st)))
         return {n: getattr(st, n) for n, _ in SelfplayStats._fields_}

@@ -15,6 +15,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/caissa_b200.h"
@@ -1374,6 +1375,64 @@ __global__ void __launch_bounds__(256) device_light_gates_kernel(const cb_board*
     if (lane == 0) out[i] = (int8_t)tv;
 }
 
+// One warp per board: the tree kernels' gate at full depth, run to completion (debug / test hook).
+__global__ void __launch_bounds__(128) device_tier1_gates_kernel(const cb_board* __restrict__ boards, int n, int koth, GateCfg gc, int budget,
+                                                                 GateJob* jobs, int8_t* __restrict__ out, uint8_t* __restrict__ dist) {
+    __shared__ GateStack s_st[4];
+    __shared__ Move s_pseudo[4][CB_MAX_MOVES];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * 4 + wl;
+    if (i >= n) return;
+    GateJob& job = jobs[i];
+    if (lane < 16) reinterpret_cast<uint64_t*>(&s_st[wl].boards[0])[lane] = reinterpret_cast<const uint64_t*>(&boards[i])[lane];
+    __syncwarp();
+    int v = 2, d = 0;
+    const int us = s_st[wl].boards[0].w_to_move ? 0 : 1;
+    if (koth && (s_st[wl].boards[0].pieces[(1 - us) * 6 + cbchess::KING] & cbchess::kKothCenter)) v = -1;
+    else {
+        // resumed in slices of `budget` positions, like the tree kernels do across steps (the shared stack is wiped in
+        // between, as another game's job would do)
+        bool fresh = true;
+        while (!tier1_gates_run(job, s_st[wl], gc, budget, fresh, s_pseudo[wl], lane, &v, &d)) {
+            fresh = false;
+            for (int k = lane; k < (int)(sizeof(GateStack) / 4); k += 32) reinterpret_cast<uint32_t*>(&s_st[wl])[k] = 0xDEADBEEFu;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) { out[i] = (int8_t)v; dist[i] = (uint8_t)d; }
+}
+
+int cb_debug_device_tier1_gates(cb_handle* h, const cb_board* boards, int n, int koth, int mate_depth, int exhaustive_depth, int koth_depth,
+                                int budget, int8_t* out, uint8_t* dist) {
+    if (!h || n < 0 || (n > 0 && (!boards || !out || !dist))) return CB_EINVAL;
+    if (mate_depth < 0 || mate_depth > 5 || koth_depth < 0 || koth_depth > 4 || exhaustive_depth < 0) return fail(h, CB_EINVAL, "tier1 depths");
+    if (n == 0) return CB_OK;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_capacity(h, n);
+    if (rc) return rc;
+    if (!h->chess_tables_uploaded) {
+        CB_CUDA(h, cudaMemcpyToSymbol(cbchess::d_chess_tables, &cbchess::host_tables(), sizeof(cbchess::Tables)));
+        h->chess_tables_uploaded = true;
+    }
+    GateJob* jobs = nullptr;
+    int8_t* d_out = nullptr;
+    CB_CUDA(h, cudaMalloc((void**)&jobs, (size_t)n * sizeof(GateJob)));
+    cudaError_t e = cudaMalloc((void**)&d_out, (size_t)n * 2);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_boards, boards, (size_t)n * sizeof(cb_board), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        const GateCfg gc = {koth ? koth_depth : 0, mate_depth, exhaustive_depth};
+        device_tier1_gates_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(h->d_boards, n, koth, gc, budget > 0 ? budget : 1 << 30, jobs, d_out,
+                                                                      (uint8_t*)d_out + n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dist, d_out + n, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(jobs);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(h, CB_ECUDA, std::string("device gates: ") + cudaGetErrorString(e));
+    return CB_OK;
+}
+
 int cb_debug_device_light_gates(cb_handle* h, const cb_board* boards, int n, int koth, int8_t* out) {
     if (!h || n < 0 || (n > 0 && (!boards || !out))) return CB_EINVAL;
     if (n == 0) return CB_OK;
@@ -1754,6 +1813,22 @@ static int mcts_alloc(cb_handle* h, MctsParams& mp, int G, std::vector<void*>& o
         (rc = dalloc((void**)&mp.eval_cnt, (size_t)G * 2)) || (rc = dalloc((void**)&mp.stats, MS_COUNT * 8)))
         return rc;
     CB_CUDA(h, cudaMemsetAsync(mp.idle, 0, (size_t)G, h->stream));
+    if (mp.tier1_light >= 2) {   // the stacks of the games' gate jobs (tier1_gates_run)
+        if ((rc = dalloc((void**)&mp.gate_jobs, (size_t)G * sizeof(GateJob)))) return rc;
+        CB_CUDA(h, cudaMemsetAsync(mp.gate_jobs, 0, (size_t)G * sizeof(GateJob), h->stream));
+    }
+    return CB_OK;
+}
+
+// The gate depths of tier1_light = 2 (the reference's self-play: mate-in-5 by checks, hill in 3) and the per-step budget.
+static int mcts_gate_params(cb_handle* h, MctsParams& mp, int mate_depth, int exhaustive_depth, int koth_depth) {
+    mp.t1_mate_depth = mate_depth > 0 ? mate_depth : 5;
+    mp.t1_exh_depth = exhaustive_depth;
+    mp.t1_koth_depth = koth_depth > 0 ? koth_depth : 3;
+    if (mp.t1_mate_depth > 5 || mp.t1_koth_depth > 4 || exhaustive_depth < 0)
+        return fail(h, CB_EINVAL, "tier1 depths: mate search up to 5, hill up to 4");
+    const char* e = getenv("CB_GATE_BUDGET");
+    mp.gate_budget = e && atoi(e) > 0 ? atoi(e) : 48;
     return CB_OK;
 }
 
@@ -1791,6 +1866,9 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     mp.material_on = cfg->material_on;
     mp.qsearch = cfg->qsearch;
     mp.tier1_light = cfg->tier1_light;
+    if (cfg->tier1_light >= 2) {
+        if ((rc = mcts_gate_params(h, mp, cfg->tier1_mate_depth, cfg->tier1_exhaustive_depth, cfg->tier1_koth_depth))) return rc;
+    }
     mp.koth = cfg->koth;
     mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414;
     mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.80;
@@ -1920,6 +1998,29 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
         mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
         for (int i = 0; i <= cfg->sims_per_move && !rc; ++i) rc = fused();
         cudaError_t e2 = cudaStreamSynchronize(h->stream);
+        long long dbg_steps = cfg->sims_per_move + 1;
+        if (mp.tier1_light >= 2) {   // games whose gate jobs were suspended need more steps: run until every game is idle
+            std::vector<uint8_t> idle(G);
+            // (a search whose leaves need ~2000 gate positions each, e.g. a king near the hill, takes sims x 2000 / budget steps)
+            for (int round = 0; round < (1 << 16) && !rc && e2 == cudaSuccess; ++round) {
+                e2 = cudaMemcpy(idle.data(), mp.idle, (size_t)G, cudaMemcpyDeviceToHost);
+                if (e2 != cudaSuccess || std::all_of(idle.begin(), idle.end(), [](uint8_t x) { return x != 0; })) break;
+                for (int i = 0; i < 64 && !rc; ++i) rc = fused();
+                dbg_steps += 64;
+                e2 = cudaStreamSynchronize(h->stream);
+            }
+            if (getenv("CB_GATE_DEBUG")) {
+                std::vector<int> sd(G);
+                cudaMemcpy(sd.data(), mp.sims_done, (size_t)G * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(idle.data(), mp.idle, (size_t)G, cudaMemcpyDeviceToHost);
+                for (int g = 0; g < G; ++g) {
+                    uint8_t js[16];
+                    cudaMemcpy(js, reinterpret_cast<uint8_t*>(mp.gate_jobs) + (size_t)g * kGateJobBytes + kGateJobActiveOffset, 16, cudaMemcpyDeviceToHost);
+                    if (!idle[g] || js[0]) fprintf(stderr, "game %d: idle %d sims_done %d job active %d phase %d it %d ply %d (steps %lld)\n", g, idle[g], sd[g], js[0], js[1], js[2], js[3], dbg_steps);
+                }
+                fprintf(stderr, "debug search: %lld steps\n", dbg_steps);
+            }
+        }
         std::vector<MNode> kids(CB_MAX_MOVES);
         std::vector<uint8_t> arena(G);
         unsigned long long st2[MS_COUNT] = {0};
@@ -1946,7 +2047,9 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
         out->nn_evals = (long long)st2[MS_EVALS];
         out->terminal_hits = (long long)st2[MS_TERMINAL];
         out->overflow = (long long)st2[MS_OVERFLOW];
-        out->steps = cfg->sims_per_move + 1;
+        out->gate_hits = (long long)st2[MS_GATE_HITS];
+        out->gate_waits = (long long)st2[MS_GATE_WAITS];
+        out->steps = dbg_steps;
         return CB_OK;
     }
     const long long target = cfg->max_sims > 0 ? (cfg->max_sims + G - 1) / G : 0;   // steps to run (0 = unbounded)
@@ -2047,7 +2150,8 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     release();
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(h, CB_ECUDA, std::string("device self-play: ") + cudaGetErrorString(ce));
-    out->sims = steps * G;
+    // (with the deep gates a game whose gate job is suspended completes no simulation in that step: count them)
+    out->sims = mp.tier1_light >= 2 ? (long long)st[MS_SIMS] : steps * G;
     out->nn_evals = (long long)st[MS_EVALS];
     out->terminal_hits = (long long)st[MS_TERMINAL];
     out->moves = (long long)st[MS_MOVES];
@@ -2058,6 +2162,8 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     out->black_wins = (long long)st[MS_BWINS];
     out->draws = (long long)st[MS_DRAWS];
     out->overflow = (long long)st[MS_OVERFLOW];
+    out->gate_hits = (long long)st[MS_GATE_HITS];
+    out->gate_waits = (long long)st[MS_GATE_WAITS];
     out->seconds = secs;
     const double tot = (double)ms_fwd + ms_tree;
     out->eval_seconds = tot > 0 ? secs * ms_fwd / tot : 0.0;
@@ -2135,6 +2241,7 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     mp.material_on = cfg->material_on;
     mp.qsearch = cfg->qsearch;
+    if (cfg->tier1_light >= 2) return fail(h, CB_EINVAL, "matches run the Tier-1 gates at depth 1 (tier1_light 0 / 1)");
     mp.tier1_light = cfg->tier1_light;
     mp.koth = cfg->koth;
     mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414;

@@ -56,12 +56,21 @@ constexpr int kMctsHist = 128;      // position keys since the last irreversible
 constexpr int kMctsMaxDepth = 512;  // longest root-to-leaf path kept
 constexpr int kMctsWarps = 4;       // games per CTA
 
-enum { MS_EVALS = 0, MS_TERMINAL, MS_MOVES, MS_GAMES, MS_SAMPLES, MS_WWINS, MS_BWINS, MS_DRAWS, MS_OVERFLOW, MS_COUNT = 16 };
+constexpr int kGatePlies = 10;   // mate-in-5: plies 0..8 move, ply 9 is the mated position; the hill in 3 enters ply 6
+constexpr size_t kGateJobBytes = (kGatePlies + 1) * sizeof(cb_board) + (size_t)kGatePlies * CB_MAX_MOVES * 2 + 64 + 16;
+constexpr size_t kGateJobActiveOffset = kGateJobBytes - 16;
+
+enum { MS_EVALS = 0, MS_TERMINAL, MS_MOVES, MS_GAMES, MS_SAMPLES, MS_WWINS, MS_BWINS, MS_DRAWS, MS_OVERFLOW, MS_SIMS, MS_GATE_HITS, MS_GATE_WAITS,
+       MS_COUNT = 16 };
 
 struct MctsParams {
     int G, sims_per_move, max_plies, material_on, koth;
     int qsearch;                  // dM: 0 stand pat, 1 principal exchange (host/qsearch.hpp)
-    int tier1_light;              // light Tier-1 gates at the leaves + adjudication at the root (host/gates.hpp)
+    int tier1_light;              // 1: light Tier-1 gates at the leaves + adjudication at the root (host/gates.hpp); 2: the
+                                  // reference's gate at full depth (tier1_gates_run below), run as resumable jobs
+    int t1_mate_depth, t1_exh_depth, t1_koth_depth;   // the leaf gate of tier1_light = 2 (5 / 0 / 3 in the reference's self-play)
+    int gate_budget;              // positions a game's gate job may enter per step before it is suspended
+    struct GateJob* gate_jobs;    // [G] (tier1_light = 2)
     int g0, gn;                   // the games [g0, g0 + gn) this launch works on (one pool of a two-pool run)
     unsigned int* pdl_done;       // nullable.  Set when the launch is a programmatic dependent of the forward kernel of the
                                   // OTHER pool: the last warp to finish (wrapping counter) waits for that kernel before it
@@ -174,6 +183,7 @@ __device__ __forceinline__ void mcts_reset_game(const MctsParams& p, int g, uint
     p.ply[g] = 0;
     p.sims_done[g] = 0;
     p.samples_in_game[g] = 0;
+    if (p.gate_jobs) reinterpret_cast<uint8_t*>(p.gate_jobs)[(size_t)g * kGateJobBytes + kGateJobActiveOffset] = 0;   // GateJob::active
 }
 
 __global__ void mcts_init_kernel(const MctsParams p) {
@@ -230,7 +240,10 @@ __device__ __forceinline__ bool mcts_early_terminate(const MNode* nodes, int lan
 __device__ __forceinline__ void mcts_sim_done(const MctsParams& p, const MNode* nodes, int g, int lane) {
     __syncwarp();
     const bool stop = p.tier1_light && mcts_early_terminate(nodes, lane);
-    if (lane == 0) p.sims_done[g] = stop ? p.sims_per_move : p.sims_done[g] + 1;
+    if (lane == 0) {
+        p.sims_done[g] = stop ? p.sims_per_move : p.sims_done[g] + 1;
+        atomicAdd(&p.stats[MS_SIMS], 1ull);
+    }
     __syncwarp();
 }
 
@@ -456,6 +469,207 @@ __device__ __forceinline__ int light_gates_warp(const cb_board& b, const Move* l
     return 2;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The Tier-1 gates at full depth, warp form of cbchess::tier1_gates_host (host/gates.hpp): the hill in n
+// (src/search/koth.rs:43-65,270-395) and the mate search (src/search/mate_search.rs:64-289) as ONE iterative any / all
+// minimax over an explicit stack in global memory.  Both searches answer "is there a move such that for every reply
+// ..." and their results do not depend on the order in which moves are tried, so a node is: the legal moves (warp
+// generator), optionally filtered on the lanes (attacker plies of the checks-only levels and the last attacker ply:
+// moves that give check; root-side plies of the hill search: moves after which the king is inside the ring that
+// still reaches the centre), and a cursor.  Even plies are ANY nodes (the side that wants to win), odd plies ALL nodes.
+//
+// A search of a quiet position enters a handful of nodes; one with many checks can enter thousands.  The games of a
+// pool advance in lock step, so a job that has entered `budget` positions in this step is SUSPENDED (its stack and
+// cursors stay in global memory) and resumed in the game's next step: that game skips simulations meanwhile, the
+// other games do not wait for it, and the trees come out the same because a game's simulations are sequential anyway.
+struct GateStack {                 // the search stack of one job: in shared memory while the job runs
+    cb_board boards[kGatePlies + 1];
+    uint16_t list[kGatePlies][CB_MAX_MOVES];
+};
+struct GateJob {                   // a game's job in global memory: where the stack rests between steps
+    GateStack st;
+    uint16_t idx[16], cnt[16];     // cursor and length of every ply's move list
+    uint8_t active;                // 0 none, 1 leaf gate, 2 adjudication of a new root
+    uint8_t phase;                 // 0 hill, 1 mate
+    uint8_t it;                    // iteration: the hill's n / the mate's d
+    uint8_t ply;
+    uint8_t pad[12];
+};
+static_assert(sizeof(GateJob) == kGateJobBytes && offsetof(GateJob, active) == kGateJobActiveOffset, "gate job layout");
+static_assert(sizeof(GateStack) % 16 == 0 && sizeof(cb_board) % 16 == 0, "stack copied as uint4");
+struct GateCfg { int koth_n, mate_d, exh_d; };
+
+// Does the side to move of `b` (shared memory) have a legal move?  King steps on eight lanes first, then the list.
+__device__ __forceinline__ bool has_legal_move_warp(const cb_board& b, Move* pseudo, int lane) {
+    using namespace cbchess;
+    const int us = b.w_to_move ? 0 : 1;
+    const uint64_t k = b.pieces[us * 6 + KING];
+    if (k) {
+        const int ks = lsb(k);
+        const uint64_t steps = tables().king[ks] & ~b.occ[us];
+        bool out = false;
+        if (lane < __popcll(steps)) {
+            cb_board t;
+            make_move_hd(b, make_mv(ks, nth_set_bit(steps, lane), 0), &t);
+            out = !in_check_hd(t, us);
+        }
+        if (__any_sync(0xffffffffu, out)) return true;
+    }
+    const int np = gen_pseudo_warp(b, pseudo, lane);
+    for (int base = 0; base < np; base += 32) {
+        bool ok = false;
+        if (base + lane < np) {
+            cb_board t;
+            make_move_hd(b, pseudo[base + lane], &t);
+            ok = !in_check_hd(t, us);
+        }
+        if (__any_sync(0xffffffffu, ok)) return true;
+    }
+    return false;
+}
+
+// The moves of a gate node in one pass over the pseudo-legal list: every lane makes its move once and tests legality,
+// and with it the node's filter (kind 1: the move gives check; kind 2: the mover's king ends inside `ring`).  The kept
+// moves go to `list` in generation order; returns their number, *n_legal = the number of legal moves.
+__device__ __forceinline__ int gate_moves_warp(const cb_board& b, Move* pseudo, uint16_t* list, int kind, uint64_t ring, int lane,
+                                               int* n_legal) {
+    using namespace cbchess;
+    const int np = gen_pseudo_warp(b, pseudo, lane);
+    const int us = b.w_to_move ? 0 : 1;
+    int n = 0, nl = 0;
+    for (int base = 0; base < np; base += 32) {
+        const int i = base + lane;
+        bool legal = false, keep = false;
+        Move m = 0;
+        if (i < np) {
+            m = pseudo[i];
+            cb_board t;
+            make_move_hd(b, m, &t);
+            legal = !in_check_hd(t, us);
+            keep = legal && (kind == 0 || (kind == 1 ? in_check_hd(t, 1 - us) : (t.pieces[us * 6 + KING] & ring) != 0));
+        }
+        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        if (keep) list[n + __popc(km & ((1u << lane) - 1u))] = m;
+        n += __popc(km);
+        nl += __popc(__ballot_sync(0xffffffffu, legal));
+    }
+    __syncwarp();
+    *n_legal = nl;
+    return n;
+}
+
+// Runs (fresh: st.boards[0] holds the position) or resumes the job (the stack is fetched from job.st).  true: finished,
+// *value = +1 (the side to move of the position wins: hill reached or mate) or 2 (no gate), *dist = terminal_distance
+// (src/mcts/tactical_mcts.rs:641,701).  false: suspended, the stack is back in job.st.  `st` / `pseudo`: the warp's
+// shared memory.  All lanes call and return alike.
+__device__ __forceinline__ bool tier1_gates_run(GateJob& job, GateStack& st, const GateCfg gc, int budget, bool fresh, Move* pseudo,
+                                                int lane, int* value, int* dist) {
+    using namespace cbchess;
+    int phase, it, ply, r_idx = 0, r_cnt = 0;   // lane p keeps the cursor of ply p
+    *value = 2;
+    *dist = 0;
+    if (fresh) {
+        if (gc.koth_n > 0) {   // koth_center_in_n: Some(0)
+            const int us = st.boards[0].w_to_move ? 0 : 1;
+            if (st.boards[0].pieces[us * 6 + KING] & kKothCenter) { *value = 1; return true; }
+        }
+        phase = gc.koth_n > 0 ? 0 : 1;
+        if (phase == 1 && gc.mate_d <= 0) return true;
+        it = 1;
+        ply = 0;
+    } else {
+        phase = job.phase;
+        it = job.it;
+        ply = job.ply;
+        if (lane <= kGatePlies) { r_idx = job.idx[lane]; r_cnt = job.cnt[lane]; }
+        // the boards up to `ply` and the move lists below it (the list of `ply` itself is generated on entry)
+        const int nb4 = (ply + 1) * (int)(sizeof(cb_board) / 16);
+        for (int i = lane; i < nb4; i += 32) reinterpret_cast<uint4*>(st.boards)[i] = reinterpret_cast<const uint4*>(job.st.boards)[i];
+        for (int q = 0; q < ply; ++q) {
+            const int n4 = (__shfl_sync(0xffffffffu, r_cnt, q) * 2 + 15) / 16;
+            for (int i = lane; i < n4; i += 32) reinterpret_cast<uint4*>(st.list[q])[i] = reinterpret_cast<const uint4*>(job.st.list[q])[i];
+        }
+        __syncwarp();
+    }
+    bool need_enter = true;   // a job starts, and is suspended, in front of a position
+    for (;;) {
+        const bool hill = phase == 0;
+        const int D = 2 * it - 1;                            // hill: max_ply; mate: depth in plies
+        const bool c_only = !hill && D > 2 * gc.exh_d - 1;   // checks-only level
+        int result = -1;
+        if (need_enter) {
+            if (budget-- <= 0) {
+                if (lane == 0) { job.phase = (uint8_t)phase; job.it = (uint8_t)it; job.ply = (uint8_t)ply; }
+                if (lane <= kGatePlies) { job.idx[lane] = (uint16_t)r_idx; job.cnt[lane] = (uint16_t)r_cnt; }
+                const int nb4 = (ply + 1) * (int)(sizeof(cb_board) / 16);
+                for (int i = lane; i < nb4; i += 32) reinterpret_cast<uint4*>(job.st.boards)[i] = reinterpret_cast<const uint4*>(st.boards)[i];
+                for (int q = 0; q < ply; ++q) {
+                    const int n4 = (__shfl_sync(0xffffffffu, r_cnt, q) * 2 + 15) / 16;
+                    for (int i = lane; i < n4; i += 32) reinterpret_cast<uint4*>(job.st.list[q])[i] = reinterpret_cast<const uint4*>(st.list[q])[i];
+                }
+                __syncwarp();
+                return false;
+            }
+            need_enter = false;
+            const cb_board& cur = st.boards[ply];
+            const int stm = cur.w_to_move ? 0 : 1;
+            const bool any_node = (ply & 1) == 0;
+            if (hill) {   // solve_koth's tests in front of the moves (koth.rs:272-300)
+                const int root_side = any_node ? stm : 1 - stm;
+                if (cur.pieces[root_side * 6 + KING] & kKothCenter) result = 1;
+                else if (cur.pieces[(1 - root_side) * 6 + KING] & kKothCenter) result = 0;
+                else if (ply > D) result = 0;
+            } else if (ply == D) {   // depth 0: the last move was a check; mate iff there is no answer (mate_search.rs:129-238)
+                result = has_legal_move_warp(cur, pseudo, lane) ? 0 : 1;
+            }
+            if (result < 0) {
+                const int kind = any_node ? (hill ? 2 : (c_only || D - ply == 1) ? 1 : 0) : 0;
+                int nl = 0;
+                const int cnt = gate_moves_warp(cur, pseudo, st.list[ply], kind, kind == 2 ? koth_ring_mask(gc.koth_n - ply / 2 - 1) : 0ull,
+                                                lane, &nl);
+                if (cnt == 0) {
+                    if (hill) result = 0;                                           // koth.rs:327,356,386-388
+                    else if (any_node) result = (ply != 0 && !c_only && nl == 0 && in_check_hd(cur, stm)) ? 1 : 0;   // :276-283
+                    else result = in_check_hd(cur, stm) ? 1 : 0;                    // mated / stalemate
+                }
+                if (lane == ply) { r_idx = 0; r_cnt = cnt; }
+            }
+        }
+        if (result < 0) {
+            const int idx = __shfl_sync(0xffffffffu, r_idx, ply), cnt = __shfl_sync(0xffffffffu, r_cnt, ply);
+            if (idx < cnt) {
+                if (lane == ply) r_idx = idx + 1;
+                __syncwarp();
+                if (lane == 0) make_move_hd(st.boards[ply], (Move)st.list[ply][idx], &st.boards[ply + 1]);
+                __syncwarp();
+                ++ply;
+                need_enter = true;
+                continue;
+            }
+            result = (ply & 1) ? 1 : 0;   // ALL node: every reply loses; ANY node: no move wins
+        }
+        while (ply > 0) {                 // hand the result up
+            --ply;
+            if (((ply & 1) == 0) ? result == 1 : result == 0) continue;   // decides the parent as well
+            result = -1;                  // the parent tries its next move
+            break;
+        }
+        if (result < 0) continue;
+        if (result == 1) {
+            *value = 1;
+            *dist = hill ? it : mate_dist_u8(D);
+            return true;
+        }
+        ++it;                             // nothing at this iteration
+        if (it > (hill ? gc.koth_n : gc.mate_d)) {
+            if (hill && gc.mate_d > 0) { phase = 1; it = 1; }
+            else return true;
+        }
+        ply = 0;
+        need_enter = true;
+    }
+}
+
 // Phase A of a simulation for every game: walk down (tactical phase, root force-visit, PUCT), stop at an unexpanded or
 // decided node.
 // Per-warp shared scratch of the tree kernels.
@@ -465,7 +679,28 @@ struct MctsSmem {
     Move pseudo[kMctsWarps][CB_MAX_MOVES];
     Move legal[kMctsWarps][CB_MAX_MOVES];
     uint8_t mailbox[kMctsWarps][64];   // piece codes of the position under the exchange line
+    GateStack gate[kMctsWarps];        // tier1_light = 2: the stack of the warp's gate job while it runs
 };
+
+// A self-play game in slot g is over (lane 0): count it, log the result record, start the next game.  `rs`: the game's
+// random stream after the draws of its last move.
+__device__ __forceinline__ void mcts_game_over(const MctsParams& p, int g, int result, uint64_t& rs) {
+    atomicAdd(&p.stats[result > 0 ? MS_WWINS : result < 0 ? MS_BWINS : MS_DRAWS], 1ull);
+    atomicAdd(&p.stats[MS_SAMPLES], (unsigned long long)p.samples_in_game[g]);
+    atomicAdd(&p.stats[MS_GAMES], 1ull);
+    if (p.sample_ring) {
+        const unsigned long long slot = atomicAdd(p.ring_cursor, 1ull);
+        uint8_t* rec = p.sample_ring + (size_t)(slot % p.ring_slots) * kSampleSlotBytes;
+        reinterpret_cast<uint32_t*>(rec)[0] = (uint32_t)g;
+        reinterpret_cast<uint32_t*>(rec)[1] = p.game_serial[g];
+        reinterpret_cast<uint16_t*>(rec)[4] = (uint16_t)p.ply[g];
+        reinterpret_cast<uint16_t*>(rec)[5] = 0xFFFFu;
+        reinterpret_cast<int32_t*>(rec)[3] = result;
+        p.game_serial[g]++;
+    }
+    const uint64_t seed = rng_next(rs) ^ ((uint64_t)g << 32);
+    mcts_reset_game(p, g, seed);
+}
 
 // The part of a child node the walk needs, packed for one round of shuffles.
 struct MChildLite {
@@ -487,12 +722,43 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; }
         return;
     }
+    // tier1_light = 2: a gate job of this game may be waiting (tier1_gates_run)
+    const bool deep = p.tier1_light >= 2;
+    GateJob* job = deep ? &p.gate_jobs[g] : nullptr;
+    int pending = deep ? job->active : 0;
+    if (pending == 2) {
+        // the game loop's pre-check of the new root (src/bin/self_play.rs:241-283): a hill in 3 or mate_search(board, 5,
+        // exhaustive 2) ends the game as a win of the side to move
+        const GateCfg gc = {p.koth ? 3 : 0, 5, 2};
+        int gv, gd;
+        if (!tier1_gates_run(*job, sm.gate[wl], gc, p.gate_budget, false, s_pseudo[wl], lane, &gv, &gd)) {
+            if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; atomicAdd(&p.stats[MS_GATE_WAITS], 1ull); }
+            return;
+        }
+        if (lane == 0) job->active = 0;
+        __syncwarp();
+        if (gv == 1) {   // adjudicated: the next game in this slot starts with this step's selection
+            if (lane == 0) {
+                uint64_t rs = p.rng[g];
+                mcts_game_over(p, g, p.root[g].w_to_move ? 1 : -1, rs);
+            }
+            __syncwarp();
+        }
+        pending = 0;
+    }
     MNode* nodes = p.nodes + ((size_t)g * 2 + p.arena[g]) * p.node_cap;
     uint32_t* path = p.path + (size_t)g * kMctsMaxDepth;
     cb_board& board = sm.board[wl];
+    uint32_t cur = 0;
+    int path_n = 1;
+    if (pending == 1) {   // the leaf gate of the simulation in flight was suspended: same leaf, same path
+        if (lane < 16) reinterpret_cast<uint64_t*>(&board)[lane] = reinterpret_cast<const uint64_t*>(&job->st.boards[0])[lane];
+        __syncwarp();
+        path_n = p.path_n[g];
+        cur = path[path_n - 1];
+    } else {
     if (lane < 16) reinterpret_cast<uint64_t*>(&board)[lane] = reinterpret_cast<const uint64_t*>(&p.root[g])[lane];
     __syncwarp();
-    uint32_t cur = 0;
     int depth = 0;
     if (lane == 0) path[0] = 0;
     // The node at the top of each level comes from the lane that scanned it as a child one level up (one
@@ -587,8 +853,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         n = nxt;
         ++depth;
     }
-    const int path_n = depth + 1;
-    MNode& leaf = nodes[cur];
+    path_n = depth + 1;
     const uint8_t leaf_state = (uint8_t)(n.st & 0xFFu);
     const int8_t leaf_term = (int8_t)((n.st >> 8) & 0xFFu);
     if (leaf_state == 2 || leaf_state == 1) {   // decided (or the depth cap): back its value up again
@@ -602,6 +867,8 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         mcts_sim_done(p, nodes, g, lane);
         return;
     }
+    }
+    MNode& leaf = nodes[cur];
     int n_tact = 0;
     const int n_moves = mcts_gen_legal_warp(board, s_pseudo[wl], s_legal[wl], lane, &n_tact);
     // mate / stalemate (MctsNode::new_child, src/mcts/node.rs:162-177), else the light Tier-1 gates; with the gates on, an
@@ -612,7 +879,29 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     if (n_moves == 0) tv = cbchess::in_check_hd(board, us) ? -1 : 0;
     else if (p.tier1_light && cur != 0) {
         if (p.koth && (board.pieces[(1 - us) * 6 + cbchess::KING] & cbchess::kKothCenter)) tv = -1;
-        else {
+        else if (deep) {
+            // the reference's leaf gate (src/mcts/tactical_mcts.rs:634-708): hill in koth_depth, then the mate search
+            if (pending != 1) {
+                if (lane < 16) reinterpret_cast<uint64_t*>(&sm.gate[wl].boards[0])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
+                __syncwarp();
+            }
+            const GateCfg gc = {p.koth ? p.t1_koth_depth : 0, p.t1_mate_depth, p.t1_exh_depth};
+            if (!tier1_gates_run(*job, sm.gate[wl], gc, p.gate_budget, pending != 1, s_pseudo[wl], lane, &tv, &td)) {
+                if (lane == 0) {
+                    job->active = 1;
+                    p.path_n[g] = path_n;
+                    p.wants_eval[g] = 0;
+                    p.eval_cnt[g] = 0;
+                    atomicAdd(&p.stats[MS_GATE_WAITS], 1ull);
+                }
+                return;
+            }
+            if (lane == 0) {
+                job->active = 0;
+                if (tv != 2) atomicAdd(&p.stats[MS_GATE_HITS], 1ull);
+            }
+            __syncwarp();
+        } else {
             tv = light_gates_warp(board, s_legal[wl], n_moves, p.koth != 0, sm.next[wl], s_pseudo[wl], lane, &td);
         }
     }
@@ -886,7 +1175,7 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
     const int n_legal = mcts_gen_legal_warp(nb, s_pseudo[wl], s_legal[wl], lane);
     // a root where the side to move wins at once is adjudicated (src/bin/self_play.rs:241-283 at depth 1; in a match
     // the reference's search returns the winning move there, src/mcts/tactical_mcts.rs:330-357,400-420: same result)
-    const int gate = (p.tier1_light && n_legal > 0) ? light_gates_warp(nb, s_legal[wl], n_legal, p.koth != 0, sm.board[wl], s_pseudo[wl], lane) : 2;
+    const int gate = (p.tier1_light == 1 && n_legal > 0) ? light_gates_warp(nb, s_legal[wl], n_legal, p.koth != 0, sm.board[wl], s_pseudo[wl], lane) : 2;
     if (lane == 0) {
         int result = 2;   // +1 white won, -1 black won, 0 draw, 2 continue
         if (p.koth && (nb.pieces[(white_moved ? 0 : 6) + cbchess::KING] & cbchess::kKothCenter)) result = white_moved ? 1 : -1;
@@ -912,23 +1201,17 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
             p.cand_white[g] = (k & 1ull) == 0;
             if ((long long)k >= p.total_games) p.idle[g] = 1;
         } else if (result != 2) {
-            atomicAdd(&p.stats[result > 0 ? MS_WWINS : result < 0 ? MS_BWINS : MS_DRAWS], 1ull);
-            atomicAdd(&p.stats[MS_SAMPLES], (unsigned long long)p.samples_in_game[g]);
-            atomicAdd(&p.stats[MS_GAMES], 1ull);
-            if (p.sample_ring) {
-                const unsigned long long slot = atomicAdd(p.ring_cursor, 1ull);
-                uint8_t* rec = p.sample_ring + (size_t)(slot % p.ring_slots) * kSampleSlotBytes;
-                reinterpret_cast<uint32_t*>(rec)[0] = (uint32_t)g;
-                reinterpret_cast<uint32_t*>(rec)[1] = p.game_serial[g];
-                reinterpret_cast<uint16_t*>(rec)[4] = (uint16_t)p.ply[g];
-                reinterpret_cast<uint16_t*>(rec)[5] = 0xFFFFu;
-                reinterpret_cast<int32_t*>(rec)[3] = result;
-                p.game_serial[g]++;
-            }
-            const uint64_t seed = rng_next(rs) ^ ((uint64_t)g << 32);
-            mcts_reset_game(p, g, seed);
+            mcts_game_over(p, g, result, rs);
         } else {
             p.rng[g] = rs;
+            if (p.tier1_light >= 2) {   // the new root's pre-check runs as a job in front of its first simulation
+                GateJob& job = p.gate_jobs[g];
+                job.st.boards[0] = nb;
+                job.phase = p.koth ? 0 : 1;
+                job.it = 1;
+                job.ply = 0;
+                job.active = 2;
+            }
         }
     }
 }

@@ -178,18 +178,34 @@ int orc_koth_center_in_n(const orc_board* b, int max_n, uint32_t* nodes_out) {
 
 /* The Tier-1 leaf gate, src/mcts/tactical_mcts.rs:619-708: -1 / +1 for the side to move, 2 = no gate.
  * *dist = terminal_distance of a hit. */
+static long g_gate_calls, g_gate_nodes, g_gate_max_nodes; /* positions entered by the leaf gates (a cost statistic for the tests) */
+void orc_gate_node_stats(long* calls, long* nodes, long* max_nodes, int reset) {
+    if (calls) *calls = g_gate_calls;
+    if (nodes) *nodes = g_gate_nodes;
+    if (max_nodes) *max_nodes = g_gate_max_nodes;
+    if (reset) g_gate_calls = g_gate_nodes = g_gate_max_nodes = 0;
+}
+
 int orc_tier1_gates(const orc_board* b, int koth, int mate_depth, int exhaustive_depth, int koth_depth, int* dist) {
     int d = 0, v = 2;
+    long total = 0;
     if (koth) {
         if (b->pieces[(b->w_to_move ? 1 : 0) * 6 + K] & CENTER) { v = -1; d = 0; goto done; }
-        const int n = orc_koth_center_in_n(b, koth_depth, NULL);
+        uint32_t hn = 0;
+        const int n = orc_koth_center_in_n(b, koth_depth, &hn);
+        total += hn;
         if (n >= 0) { v = 1; d = n; goto done; }
     }
     if (mate_depth > 0) {
-        const int score = orc_mate_search(b, mate_depth, exhaustive_depth, NULL, NULL);
+        int mn = 0;
+        const int score = orc_mate_search(b, mate_depth, exhaustive_depth, NULL, &mn);
+        total += mn;
         if (score != 0) { v = 1; d = (int)(uint8_t)(unsigned)score; } /* mate_result.0.unsigned_abs() as u8, :701 */
     }
 done:
+    g_gate_calls++;
+    g_gate_nodes += total;
+    if (total > g_gate_max_nodes) g_gate_max_nodes = total;
     if (dist) *dist = d;
     return v;
 }

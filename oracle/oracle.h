@@ -84,6 +84,7 @@ int   orc_mate_search(const orc_board* b, int max_depth, int exhaustive_depth, o
                                                     /* src/search/mate_search.rs:64-289: 1_000_000 + plies, or 0 */
 int   orc_koth_center_in_n(const orc_board* b, int max_n, uint32_t* nodes); /* src/search/koth.rs:146-268: n, or -1 = None */
 int   orc_tier1_gates(const orc_board* b, int koth, int mate_depth, int exhaustive_depth, int koth_depth, int* dist);
+void  orc_gate_node_stats(long* calls, long* nodes, long* max_nodes, int reset); /* positions entered by orc_tier1_gates so far */
                                                     /* src/mcts/tactical_mcts.rs:619-708: -1, +1 or 2; *dist = terminal_distance */
 
 /* ---- tree operations (mcts.c): generation order, tactical-first selection, f64 PUCT, backup, reuse, game loop ---- */

@@ -311,6 +311,13 @@ def tier1_gates(b, koth=False, mate_depth=5, exhaustive_depth=0, koth_depth=3):
     return v, dist.value
 
 
+def gate_node_stats(reset=False):
+    """Cost of the orc_tier1_gates calls so far: (calls, positions entered, largest single call)."""
+    c, n, m = ctypes.c_long(0), ctypes.c_long(0), ctypes.c_long(0)
+    lib().orc_gate_node_stats(ctypes.byref(c), ctypes.byref(n), ctypes.byref(m), int(reset))
+    return c.value, n.value, m.value
+
+
 def pe_q(boards_u8):
     """Principal-exchange material scalar of every board (pawn units, side to move)."""
     q = np.zeros(boards_u8.shape[0], dtype=np.float32)

@@ -440,20 +440,27 @@ SEARCH_FENS = ["r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -
                "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1"]
 
 
-def search_corpus(n_random, koth=None):
+def search_corpus(n_random, koth=None, deep=False):
     """Positions for the one-move searches; with the gates on, roots the game loop would adjudicate are left out
     (src/bin/self_play.rs:241-283; see tests/test_host_search.py)."""
     boards, _, _, _ = O.random_positions(99, n_random, 160)
     boards = np.concatenate([O.boards_to_array([O.from_fen(f) for f in SEARCH_FENS]), boards])
-    if koth is not None:
+    if koth is not None and deep:
+        def adjudicated(b):
+            return (koth and O.koth_center_in_n(b, 3)[0] is not None) or O.mate_search(b, 5, 2)[0] != 0 or \
+                   (koth and O.light_gates(b, koth=True) == -1)
+        boards = boards[[i for i in range(boards.shape[0]) if not adjudicated(O.array_to_board(boards[i]))]]
+    elif koth is not None:
         boards = boards[[i for i in range(boards.shape[0]) if O.light_gates(O.array_to_board(boards[i]), koth=koth) == 2]]
     return boards
 
 
 @pytest.mark.parametrize("mock,mode", [((0.0, 0.5), dict()), ((20.0, 0.5), dict()), ((-20.0, 0.5), dict(koth=True)),
                                        ((0.0, 0.5), dict(koth=True, tier1_light=True)), ((0.0, 0.5), dict(tier1_light=True)),
-                                       ((0.0, 0.5), dict(shuffle_children=True))],
-                         ids=["uniform", "biased+", "biased-koth", "uniform-koth-gates", "uniform-gates", "uniform-shuffle"])
+                                       ((0.0, 0.5), dict(shuffle_children=True)), ((0.0, 0.5), dict(tier1_light="deep")),
+                                       ((0.0, 0.5), dict(tier1_light="deep", koth=True)), ((-20.0, 0.5), dict(tier1_light="deep"))],
+                         ids=["uniform", "biased+", "biased-koth", "uniform-koth-gates", "uniform-gates", "uniform-shuffle",
+                              "uniform-deep-gates", "uniform-koth-deep-gates", "biased-deep-gates"])
 def test_device_search_equals_the_oracle_with_the_mock_evaluator(cb, golden, mock, mode):
     """The device tree kernels against oracle/mcts.c with the reference's mock evaluator (InferenceServer::new_mock_biased:
     uniform priors, constant v_logit — 0 and a saturated +-20 give exact values on both sides): ties everywhere, so child
@@ -461,8 +468,8 @@ def test_device_search_equals_the_oracle_with_the_mock_evaluator(cb, golden, moc
     from each of >= 64 positions; visit counts AND f64 value sums must be identical."""
     g, blob = golden("2x128_B")
     ev = make_eval(cb, g, blob, "bf16")
-    boards = search_corpus(72, koth=mode.get("koth", False) if mode.get("tier1_light") else None)
-    assert boards.shape[0] >= 64
+    boards = search_corpus(72, koth=mode.get("koth", False) if mode.get("tier1_light") else None, deep=mode.get("tier1_light") == "deep")
+    assert boards.shape[0] >= 64      # (deep gates: gate jobs are suspended after CB_GATE_BUDGET positions per step and resumed)
     kids, root_visits = ev.debug_device_search(boards, sims_per_move=200, seed=3, mock=mock, **mode)
     okw = dict(mode)
     okw["shuffle"] = okw.pop("shuffle_children", False)
@@ -506,6 +513,31 @@ def test_device_search_equals_the_oracle_with_the_network(cb, golden, material, 
     assert tactical > 500          # the tactical phase did steer leaves
 
 
+def test_device_search_with_the_deep_gates_equals_the_oracle_with_the_network(cb, golden, monkeypatch):
+    """The reference's self-play configuration of Tier 1 (mate-in-5 by checks at every leaf, src/bin/self_play.rs:213) under
+    the golden network, with a gate budget of 2 positions per step so that most gate jobs are suspended and resumed."""
+    monkeypatch.setenv("CB_GATE_BUDGET", "2")
+    g, blob = golden("6x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    boards = search_corpus(56, koth=False, deep=True)[:48]
+    mode = dict(material_on=True, qsearch="pe", tier1_light="deep")
+    kids, root_visits = ev.debug_device_search(boards, sims_per_move=200, seed=3, **mode)
+
+    def net(b, moves, q, material_on):
+        bu = np.frombuffer(bytes(b), dtype=np.uint8)[None]
+        idx = np.array([O.move_to_index_stm(m, b.w_to_move) for m in moves], dtype=np.uint16)
+        pri, _, vf, _ = ev.eval_leaves(bu, np.array([q], dtype=np.float32), idx, np.array([0, len(moves)], dtype=np.uint32),
+                                       material_on=material_on)
+        return pri, float(vf[0])
+    cfg = O.mcts_config(sims=200, **mode)
+    for i in range(boards.shape[0]):
+        t = O.Tree(O.array_to_board(boards[i]), 1)
+        t.search(cfg, net)
+        want = t.root_children()
+        assert [(m, v) for m, v, _ in kids[i]] == [(m, v) for m, v, _ in want], i
+        assert [s for _, _, s in kids[i]] == [s for _, _, s in want], i
+
+
 def test_device_search_equals_the_host_driver_hook(cb, golden):
     """cb_debug_host_search with the network behind its callback == cb_debug_device_search (three-way closure)."""
     g, blob = golden("6x128_B")
@@ -519,6 +551,61 @@ def test_device_search_equals_the_host_driver_hook(cb, golden):
         return pri, float(vf[0])
     hk, _ = cb.debug_host_search(boards, net, sims_per_move=64, seed=3, material_on=True, qsearch="pe")
     assert hk == kids
+
+
+def test_device_deep_gates_equal_the_host_form(cb, golden):
+    """tier1_gates_run (the tree kernels' resumable any / all minimax over the warp move generator) against
+    cb_tier1_gates (host/gates.hpp, itself equal to the oracle in tests/test_host.py): value and terminal distance of the
+    leaf gate as self-play runs it (mate-in-5 by checks, hill in 3), of the adjudication search (exhaustive to mate-in-2)
+    and of a run resumed every 3 positions."""
+    g, blob = golden("2x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    a, _, _, _ = O.random_positions(2718, 2500, 200)
+    fens = ["6k1/5ppp/8/8/8/8/8/4R1K1 w - - 0 1", "4r1k1/8/8/8/8/8/5PPP/6K1 b - - 0 1", "7k/R7/5K2/8/8/8/8/8 w - - 0 1",
+            "r1bqkbnr/pppp1ppp/2n5/4p2Q/2B1P3/8/PPPP1PPP/RNB1K1NR w KQkq - 4 4", "k7/1R6/K7/8/8/8/8/8 b - - 0 1",
+            "6k1/5ppp/8/7Q/8/8/8/5RK1 w - - 0 1", "8/8/8/8/8/2K5/8/k7 w - - 0 1", "8/8/8/8/3k4/8/8/K7 w - - 0 1", "8/8/8/8/8/8/1K6/k7 w - - 0 1",
+            "rnbqkbnr/1pppppp1/p6p/8/8/4P3/PPPPKPPP/RNBQ1BNR w kq - 0 3", "rnbqkbnr/pppp1pp1/4p2p/8/8/4P3/PPPPKPPP/RNBQ1BNR w kq - 0 3",
+            "4k3/8/R7/1R6/8/8/8/6K1 w - - 0 1", "7k/8/5BK1/8/8/8/8/R7 w - - 0 1"]
+    boards = np.concatenate([a, O.boards_to_array([O.from_fen(f) for f in fens])])
+    for koth in (False, True):
+        for depths in (dict(mate_depth=5, exhaustive_depth=0, koth_depth=3), dict(mate_depth=3, exhaustive_depth=2, koth_depth=3)):
+            sub = boards if depths["exhaustive_depth"] == 0 else boards[-600:]
+            want_v, want_d = cb.tier1_gates(sub, koth=koth, **depths)
+            for budget in (0, 3):
+                got_v, got_d = ev.debug_device_tier1_gates(sub, koth=koth, budget=budget, **depths)
+                assert np.array_equal(got_v, want_v), (koth, depths, budget)
+                hit = want_v != 2
+                assert np.array_equal(got_d[hit], want_d[hit]), (koth, depths, budget)
+            assert (want_v == 1).sum() >= 5
+
+
+@pytest.mark.parametrize("koth", [False, True], ids=["standard", "koth"])
+def test_device_self_play_with_the_deep_gates_equals_the_host_driver(cb, golden, tmp_path, monkeypatch, koth):
+    """Self-play with the reference's Tier-1 configuration (leaf gate mate-in-5 by checks + hill in 3; every new root
+    adjudicated by hill in 3 / mate_search(5, exhaustive 2)) on the device against the host driver.  With a budget no job
+    exceeds, the device runs in lock step with the host: identical counters and sample files.  With a small budget jobs
+    are suspended and resumed, games advance at different paces, and every game must still be the same game: the finished
+    games' samples are a subset of the host run's."""
+    g, blob = golden("6x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    kw = dict(games=16, sims_per_move=20, max_plies=40, koth=koth, seed=11, tier1_light="deep", material_on=True, qsearch="pe",
+              max_sims=16 * 20 * 60)
+    monkeypatch.setenv("CB_GATE_BUDGET", "100000000")
+    host = ev.selfplay(threads=1, pipeline=1, sample_path=str(tmp_path / "host.bin"), **kw)
+    dev = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "dev.bin"), **kw)
+    for k in ("steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins", "black_wins", "draws"):
+        assert host[k] == dev[k], (k, host[k], dev[k])
+    assert dev["games_finished"] >= 16 and dev["overflow"] == 0 and dev["gate_waits"] == 0
+    rh = np.fromfile(tmp_path / "host.bin", dtype=np.float32).reshape(-1, 5763)
+    rd = np.fromfile(tmp_path / "dev.bin", dtype=np.float32).reshape(-1, 5763)
+    key = lambda r: r[np.lexsort(r.T[::-1])]
+    assert rh.shape == rd.shape and rh.shape[0] > 0 and np.array_equal(key(rh), key(rd))
+    monkeypatch.setenv("CB_GATE_BUDGET", "24" if koth else "3")
+    slow = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "slow.bin"), **kw)
+    assert slow["gate_waits"] > 0 and slow["games_finished"] > 0
+    rs = np.fromfile(tmp_path / "slow.bin", dtype=np.float32).reshape(-1, 5763)
+    have = {r.tobytes() for r in rh}
+    assert rs.shape[0] > 0 and all(r.tobytes() in have for r in rs)
 
 
 @pytest.mark.parametrize("material,qsearch", [(False, 0), (True, "pe")])
