@@ -434,7 +434,7 @@ def main():
     # ---- self-play pool on this GPU (config 3 shape: 200 sims/move, 1024 concurrent games, vanilla mode): the
     # reference's search (tactical-first phase, f64 PUCT, tree reuse) with the tree operations on the device, and beside
     # it the host-driven pool (two half-pools, each with its own evaluator handle).
-    sp = sp_host = sp_koth = sp_two = sp_two_pe = sp_rec = None
+    sp = sp_host = sp_koth = sp_two = sp_two_pe = sp_rec = sp_deep = sp_deep4 = None
     nthreads = max(1, (os.cpu_count() or 1) // world - 2)
     rec_path = "/dev/shm/caissa_bench_samples_r%d.bin" % rank
     if args.selfplay_seconds > 0:
@@ -456,6 +456,16 @@ def main():
         barrier()
         sp_two_pe = ev.selfplay(games=2 * args.selfplay_games, sims_per_move=200, material_on=True, qsearch="pe",
                                 seed=401 + rank, max_seconds=T, pipeline=4)
+        barrier()
+        # the reference's own self-play configuration of Tier 1 (src/bin/self_play.rs:213,241-283): at every leaf the mate search
+        # to mate-in-5 by checking moves, at every new root mate_search(5, exhaustive 2); dM by the exchange line.  The gate
+        # searches run on the device as resumable jobs (a game whose job is suspended completes no simulation in that step, so
+        # the rate depends on the games in flight: the configured pool and one four times as large)
+        sp_deep = ev.selfplay(games=args.selfplay_games, sims_per_move=200, material_on=True, qsearch="pe", tier1_light="deep",
+                              seed=601 + rank, max_seconds=T, pipeline=3)
+        barrier()
+        sp_deep4 = ev.selfplay(games=4 * args.selfplay_games, sims_per_move=200, material_on=True, qsearch="pe", tier1_light="deep",
+                               seed=701 + rank, max_seconds=T, pipeline=3)
         barrier()
         # the one-pool run again with the training samples produced: every finished game is assembled on the host into
         # the reference's 5763-f32 records and written to a file (tmpfs) — the records the NCCL gather below moves
@@ -555,19 +565,24 @@ def main():
                       sp_host["seconds"] if sp_host else 0.0, sp_koth["seconds"] if sp_koth else 0.0,
                       sp_two["seconds"] if sp_two else 0.0, sp_two_pe["seconds"] if sp_two_pe else 0.0,
                       sp_rec["seconds"] if sp_rec else 0.0, sus_ms / max(sus_n, 1), e2e_long_s * 1e3 / n_long,
-                      nccl["selfplay_seconds_with_gather"] if nccl else 0.0],
+                      nccl["selfplay_seconds_with_gather"] if nccl else 0.0,
+                      sp_deep["seconds"] if sp_deep else 0.0, sp_deep4["seconds"] if sp_deep4 else 0.0],
                      dtype=torch.float64, device="cuda")
     tot = torch.tensor([sp["sims"] if sp else 0, sp["nn_evals"] if sp else 0, sp_host["sims"] if sp_host else 0,
                         sp_koth["sims"] if sp_koth else 0, sp_two["sims"] if sp_two else 0,
                         sp_two_pe["sims"] if sp_two_pe else 0, sp_rec["sims"] if sp_rec else 0,
                         sp_rec["samples"] if sp_rec else 0, nccl["selfplay_sims_with_gather"] if nccl else 0,
-                        sum(x["overflow"] for x in (sp, sp_koth, sp_two, sp_two_pe, sp_rec) if x)],
+                        sum(x["overflow"] for x in (sp, sp_koth, sp_two, sp_two_pe, sp_rec, sp_deep, sp_deep4) if x),
+                        sp_deep["sims"] if sp_deep else 0, sp_deep4["sims"] if sp_deep4 else 0,
+                        sp_deep["gate_hits"] if sp_deep else 0, sp_deep["gate_waits"] if sp_deep else 0,
+                        sp_deep["steps"] if sp_deep else 0],
                        dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     (dev_ms, e2e_ms, launch_ms, e2e_sync_ms, sp_seconds, sp_host_seconds, sp_koth_seconds, sp_two_seconds,
-     sp_two_pe_seconds, sp_rec_seconds, sus_ms_per_launch, e2e_long_ms_per_step, sp_g_seconds) = [float(x) for x in t.tolist()]
+     sp_two_pe_seconds, sp_rec_seconds, sus_ms_per_launch, e2e_long_ms_per_step, sp_g_seconds, sp_deep_seconds,
+     sp_deep4_seconds) = [float(x) for x in t.tolist()]
     value = world * B * K / (dev_ms * 1e-3)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
 
@@ -632,6 +647,17 @@ def main():
                                                   "the tree kernel of one beside the forward kernel of the other; "
                                                   "material_pe: dM by the principal-exchange line on the device",
                                 "host_threads_per_gpu": nthreads}
+            if sp_deep:
+                line["selfplay"]["tier1_deep"] = {
+                    "mode": "the reference's Tier-1 gate as its self-play runs it (tier1_light = 2): leaf gate mate_search to "
+                            "mate-in-5 by checking moves, every new root adjudicated by mate_search(5, exhaustive 2); dM by the "
+                            "exchange line; the gate searches are resumable any/all minimax jobs on the device (mcts_gate_kernel), "
+                            "trees bit-equal to oracle/mcts.c + oracle/gates.c (tests).  Measured from the start position for "
+                            "the run's seconds; the steady-state figures of longer runs are in profiles/r02_deep_gates_probe_long.json",
+                    "sims_per_s": float(tot[10].item()) / max(sp_deep_seconds, 1e-9), "games_per_gpu": args.selfplay_games,
+                    "sims_per_s_4x_games": float(tot[11].item()) / max(sp_deep4_seconds, 1e-9), "games_per_gpu_4x": 4 * args.selfplay_games,
+                    "leaves_decided_by_the_gate": int(tot[12].item()),
+                    "game_steps_waiting_for_a_gate_job_fraction": float(tot[13].item()) / max(float(tot[14].item()) * args.selfplay_games, 1.0)}
         if nccl:
             nccl["records_per_s_produced"] = float(tot[7].item()) / max(sp_rec_seconds, 1e-9)
             nccl["sims_per_s_with_gather_running"] = float(tot[8].item()) / max(sp_g_seconds, 1e-9)

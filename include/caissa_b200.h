@@ -343,6 +343,9 @@ int cb_light_gates(const cb_board* boards, int n, int koth, int8_t* out);
  * 1_000_000 + plies cast to u8, :701).  Self-play's leaf gate is (mate_depth 5, exhaustive_depth 0, koth_depth 3). */
 int cb_tier1_gates(const cb_board* boards, int n, int koth, int mate_depth, int exhaustive_depth, int koth_depth, int8_t* out,
                    uint8_t* dist);
+/* Test hook: the tree kernels' move tests that do not make the move (legal / gives check, csrc/host/chess_rules.hpp) against
+ * make-move + attack test on every pseudo-legal move of n boards; returns the number of disagreements. */
+long long cb_debug_move_flags(const cb_board* boards, int n, long long* n_moves);
 /* mate_search (src/search/mate_search.rs:64-108): plies[i] = length of the forced mate found (odd), 0 = none. */
 int cb_mate_search(const cb_board* boards, int n, int max_depth, int exhaustive_depth, int32_t* plies);
 /* koth_center_in_n (src/search/koth.rs:43-65): out[i] = own moves to the hill against every defence (0..max_n), -1 = None. */

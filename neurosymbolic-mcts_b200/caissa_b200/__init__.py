@@ -171,6 +171,7 @@ SIGNATURES = {
     "cb_principal_exchange_device": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP]),
     "cb_light_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_tier1_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    "cb_debug_move_flags": (ctypes.c_longlong, [_VP, ctypes.c_int, _VP]),
     "cb_mate_search": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_koth_center_in_n": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_debug_device_legal_moves": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP, _VP]),
@@ -552,6 +553,14 @@ def tier1_gates(boards, koth=False, mate_depth=5, exhaustive_depth=0, koth_depth
                                      _ptr(out), _ptr(dist)):
         raise CaissaError("cb_tier1_gates failed")
     return out, dist
+
+
+def debug_move_flags(boards):
+    """(disagreements, moves compared) of move_flags_hd against make-move + attack test (cb_debug_move_flags)."""
+    b = _boards_u8(boards)
+    n = ctypes.c_longlong(0)
+    bad = load_library().cb_debug_move_flags(_ptr(b), b.shape[0], ctypes.byref(n))
+    return int(bad), int(n.value)
 
 
 def mate_search(boards, max_depth=5, exhaustive_depth=2):

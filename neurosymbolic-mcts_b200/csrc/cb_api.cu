@@ -1828,7 +1828,7 @@ static int mcts_gate_params(cb_handle* h, MctsParams& mp, int mate_depth, int ex
     if (mp.t1_mate_depth > 5 || mp.t1_koth_depth > 4 || exhaustive_depth < 0)
         return fail(h, CB_EINVAL, "tier1 depths: mate search up to 5, hill up to 4");
     const char* e = getenv("CB_GATE_BUDGET");
-    mp.gate_budget = e && atoi(e) > 0 ? atoi(e) : 48;
+    mp.gate_budget = e && atoi(e) > 0 ? atoi(e) : 24;
     return CB_OK;
 }
 
@@ -1978,15 +1978,33 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
         at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at;
         lc.numAttrs = 1;
-        CB_CUDA(h, cudaLaunchKernelEx(&lc, mcts_step_kernel, q));
+        CB_CUDA(h, cudaLaunchKernelEx(&lc, mcts_step_kernel<0>, q));
         return CB_OK;
+    };
+    // tier1_light = 2 with one pool: the gate jobs run in their own kernel after the tree kernel (mcts_select_body<MODE>)
+    const bool split = mp.tier1_light >= 2 && pools == 1 && !getenv("CB_GATE_INLINE");
+    auto tree_step = [&] {   // expand + select of the one pool
+        if (split) {
+            mcts_step_kernel<1><<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+            mcts_gate_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+        } else {
+            mcts_step_kernel<0><<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+        }
+    };
+    auto first_select = [&](int pool) {
+        if (split) {
+            mcts_select_kernel<1><<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
+            mcts_gate_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
+        } else {
+            mcts_select_kernel<0><<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
+        }
     };
     // one step of every pool; leaves the run in the state it found it (pool 0 evaluated, the others selected)
     auto fused = [&]() -> int {
         int r;
         if (pools == 1) {
             if ((r = fwd(0))) return r;
-            mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+            tree_step();
             return CB_OK;
         }
         if ((r = fwd(1)) || (r = step_beside(0)) || (r = fwd(0)) || (r = step_beside(1))) return r;
@@ -1995,7 +2013,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     if (dbg) {
         // one move's search for every position: a fresh root asks for its policy first (one step that is no simulation),
         // then sims_per_move simulations; games that are done go idle.  Eager launches, then the root children are read.
-        mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+        first_select(0);
         for (int i = 0; i <= cfg->sims_per_move && !rc; ++i) rc = fused();
         cudaError_t e2 = cudaStreamSynchronize(h->stream);
         long long dbg_steps = cfg->sims_per_move + 1;
@@ -2054,7 +2072,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     }
     const long long target = cfg->max_sims > 0 ? (cfg->max_sims + G - 1) / G : 0;   // steps to run (0 = unbounded)
     long long done = 0;                        // completed steps; one more is always in flight
-    for (int pool = 0; pool < pools; ++pool) mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
+    for (int pool = 0; pool < pools; ++pool) first_select(pool);
     if (pools == 2) rc = fwd(0);
     // one eager fused step (sets the kernels' attributes outside capture)
     if (!rc && (target == 0 || target > 1)) {
@@ -2108,7 +2126,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
             cudaEventRecord(e[0], h->stream);
             rc = fwd(0);
             cudaEventRecord(e[1], h->stream);
-            mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+            tree_step();
             cudaEventRecord(e[2], h->stream);
             ce = cudaStreamSynchronize(h->stream);
             cudaEventElapsedTime(&ms_fwd, e[0], e[1]);
@@ -2293,10 +2311,10 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     auto fused = [&]() -> int {
         int r = forwards();
         if (r) return r;
-        mcts_step_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+        mcts_step_kernel<0><<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
         return CB_OK;
     };
-    mcts_select_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
+    mcts_select_kernel<0><<<grid, 32 * kMctsWarps, 0, h->stream>>>(mp);
     rc = fused();
     cudaError_t ce = cudaStreamSynchronize(h->stream);
     constexpr int kStepsPerGraph = 8;

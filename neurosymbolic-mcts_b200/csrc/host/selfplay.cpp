@@ -538,6 +538,31 @@ int cb_light_gates(const cb_board* boards, int n, int koth, int8_t* out) {
     return 0;
 }
 
+// move_flags_hd against make_move_hd + in_check_hd on every pseudo-legal move of n boards: returns the number of
+// moves whose flags differ (0 in a sound build); *n_moves (nullable) = moves compared.
+long long cb_debug_move_flags(const cb_board* boards, int n, long long* n_moves) {
+    if (n < 0 || (n > 0 && !boards)) return -1;
+    long long bad = 0, total = 0;
+    Move mv[kMaxMoves];
+    for (int i = 0; i < n; ++i) {
+        const cb_board& b = boards[i];
+        const cbchess::MoveCtx c = cbchess::move_ctx(b);
+        const int us = b.w_to_move ? 0 : 1;
+        const int np = cbchess::gen_pseudo(b, mv);
+        for (int k = 0; k < np; ++k) {
+            cb_board nb;
+            cbchess::make_move_hd(b, mv[k], &nb);
+            const bool legal = !cbchess::in_check_hd(nb, us);
+            const int want = legal ? (cbchess::in_check_hd(nb, 1 - us) ? 3 : 1) : 0;
+            bad += cbchess::move_flags_hd(b, c, mv[k], true) != want;
+            bad += cbchess::move_flags_hd(b, c, mv[k], false) != (want & 1);
+            ++total;
+        }
+    }
+    if (n_moves) *n_moves = total;
+    return bad;
+}
+
 int cb_tier1_gates(const cb_board* boards, int n, int koth, int mate_depth, int exhaustive_depth, int koth_depth, int8_t* out,
                    uint8_t* dist) {
     if (n < 0 || (n > 0 && (!boards || !out))) return 1;

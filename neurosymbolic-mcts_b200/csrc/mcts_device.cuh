@@ -499,43 +499,33 @@ static_assert(sizeof(GateJob) == kGateJobBytes && offsetof(GateJob, active) == k
 static_assert(sizeof(GateStack) % 16 == 0 && sizeof(cb_board) % 16 == 0, "stack copied as uint4");
 struct GateCfg { int koth_n, mate_d, exh_d; };
 
-// Does the side to move of `b` (shared memory) have a legal move?  King steps on eight lanes first, then the list.
+// Does the side to move of `b` (shared memory) have a legal move?  King steps on eight lanes first, then the list.  The
+// moves are tested without making them (cbchess::move_flags_hd).
 __device__ __forceinline__ bool has_legal_move_warp(const cb_board& b, Move* pseudo, int lane) {
     using namespace cbchess;
-    const int us = b.w_to_move ? 0 : 1;
-    const uint64_t k = b.pieces[us * 6 + KING];
-    if (k) {
-        const int ks = lsb(k);
-        const uint64_t steps = tables().king[ks] & ~b.occ[us];
+    const MoveCtx c = move_ctx(b);
+    if (c.ks >= 0) {
+        const uint64_t steps = tables().king[c.ks] & ~b.occ[c.us];
         bool out = false;
-        if (lane < __popcll(steps)) {
-            cb_board t;
-            make_move_hd(b, make_mv(ks, nth_set_bit(steps, lane), 0), &t);
-            out = !in_check_hd(t, us);
-        }
+        if (lane < __popcll(steps)) out = move_flags_hd(b, c, make_mv(c.ks, nth_set_bit(steps, lane), 0), false) != 0;
         if (__any_sync(0xffffffffu, out)) return true;
     }
     const int np = gen_pseudo_warp(b, pseudo, lane);
     for (int base = 0; base < np; base += 32) {
-        bool ok = false;
-        if (base + lane < np) {
-            cb_board t;
-            make_move_hd(b, pseudo[base + lane], &t);
-            ok = !in_check_hd(t, us);
-        }
+        const bool ok = base + lane < np && move_flags_hd(b, c, pseudo[base + lane], false) != 0;
         if (__any_sync(0xffffffffu, ok)) return true;
     }
     return false;
 }
 
-// The moves of a gate node in one pass over the pseudo-legal list: every lane makes its move once and tests legality,
-// and with it the node's filter (kind 1: the move gives check; kind 2: the mover's king ends inside `ring`).  The kept
-// moves go to `list` in generation order; returns their number, *n_legal = the number of legal moves.
+// The moves of a gate node in one pass over the pseudo-legal list: every lane tests its move's legality and with it the
+// node's filter (kind 1: the move gives check; kind 2: the mover's king ends inside `ring`).  The kept moves go to `list`
+// in generation order; returns their number, *n_legal = the number of legal moves.
 __device__ __forceinline__ int gate_moves_warp(const cb_board& b, Move* pseudo, uint16_t* list, int kind, uint64_t ring, int lane,
                                                int* n_legal) {
     using namespace cbchess;
+    const MoveCtx c = move_ctx(b);
     const int np = gen_pseudo_warp(b, pseudo, lane);
-    const int us = b.w_to_move ? 0 : 1;
     int n = 0, nl = 0;
     for (int base = 0; base < np; base += 32) {
         const int i = base + lane;
@@ -543,10 +533,9 @@ __device__ __forceinline__ int gate_moves_warp(const cb_board& b, Move* pseudo, 
         Move m = 0;
         if (i < np) {
             m = pseudo[i];
-            cb_board t;
-            make_move_hd(b, m, &t);
-            legal = !in_check_hd(t, us);
-            keep = legal && (kind == 0 || (kind == 1 ? in_check_hd(t, 1 - us) : (t.pieces[us * 6 + KING] & ring) != 0));
+            const int fl = move_flags_hd(b, c, m, kind == 1);
+            legal = (fl & 1) != 0;
+            keep = legal && (kind == 0 || (kind == 1 ? (fl & 2) != 0 : (ring >> (mv_from(m) == c.ks ? mv_to(m) : c.ks) & 1) != 0));
         }
         const uint32_t km = __ballot_sync(0xffffffffu, keep);
         if (keep) list[n + __popc(km & ((1u << lane) - 1u))] = m;
@@ -715,17 +704,28 @@ __device__ __forceinline__ MChildLite lite_of(const MNode& n) {
     return l;
 }
 
+// MODE 0: everything in this launch (gate jobs run inline).  With tier1_light = 2 and one pool the work is split over two
+// launches so that the gate jobs - long, latency-bound loops over a small body of code - run in a kernel of their own
+// (mcts_gate_kernel) instead of inside the 400 KB tree kernel: MODE 1 (tree kernel) walks down and, at a fresh leaf, files
+// the gate job; MODE 2 (gate kernel) runs the filed / suspended jobs and, when one finishes, completes the selection (decided
+// leaf: backup; else the evaluation request) or adjudicates the root.
+template <int MODE>
 __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& sm, int g, int wl, int lane) {
     Move (&s_pseudo)[kMctsWarps][CB_MAX_MOVES] = sm.pseudo;
     Move (&s_legal)[kMctsWarps][CB_MAX_MOVES] = sm.legal;
     if ((p.match_mode || p.search_only) && p.idle[g]) {
-        if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; }
+        if (MODE != 2 && lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; }
         return;
     }
     // tier1_light = 2: a gate job of this game may be waiting (tier1_gates_run)
     const bool deep = p.tier1_light >= 2;
     GateJob* job = deep ? &p.gate_jobs[g] : nullptr;
     int pending = deep ? job->active : 0;
+    if (MODE == 1 && pending) {   // the gate kernel carries the job on
+        if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; }
+        return;
+    }
+    if (MODE == 2 && !pending) return;
     if (pending == 2) {
         // the game loop's pre-check of the new root (src/bin/self_play.rs:241-283): a hill in 3 or mate_search(board, 5,
         // exhaustive 2) ends the game as a win of the side to move
@@ -744,6 +744,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
             }
             __syncwarp();
         }
+        if (MODE == 2) return;   // the tree kernel selects the first leaf under this root in the next step
         pending = 0;
     }
     MNode* nodes = p.nodes + ((size_t)g * 2 + p.arena[g]) * p.node_cap;
@@ -751,7 +752,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     cb_board& board = sm.board[wl];
     uint32_t cur = 0;
     int path_n = 1;
-    if (pending == 1) {   // the leaf gate of the simulation in flight was suspended: same leaf, same path
+    if (MODE == 2 || pending == 1) {   // the leaf gate of the simulation in flight was filed / suspended: same leaf, same path
         if (lane < 16) reinterpret_cast<uint64_t*>(&board)[lane] = reinterpret_cast<const uint64_t*>(&job->st.boards[0])[lane];
         __syncwarp();
         path_n = p.path_n[g];
@@ -881,12 +882,25 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         if (p.koth && (board.pieces[(1 - us) * 6 + cbchess::KING] & cbchess::kKothCenter)) tv = -1;
         else if (deep) {
             // the reference's leaf gate (src/mcts/tactical_mcts.rs:634-708): hill in koth_depth, then the mate search
-            if (pending != 1) {
+            if (MODE == 1) {   // file the job for the gate kernel
+                if (lane < 16) reinterpret_cast<uint64_t*>(&job->st.boards[0])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
+                if (lane == 0) {
+                    job->it = 0;       // not started
+                    job->active = 1;
+                    p.path_n[g] = path_n;
+                    p.wants_eval[g] = 0;
+                    p.eval_cnt[g] = 0;
+                }
+                return;
+            }
+            const bool fresh = MODE == 2 ? job->it == 0 : pending != 1;
+            __syncwarp();
+            if (fresh) {
                 if (lane < 16) reinterpret_cast<uint64_t*>(&sm.gate[wl].boards[0])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
                 __syncwarp();
             }
             const GateCfg gc = {p.koth ? p.t1_koth_depth : 0, p.t1_mate_depth, p.t1_exh_depth};
-            if (!tier1_gates_run(*job, sm.gate[wl], gc, p.gate_budget, pending != 1, s_pseudo[wl], lane, &tv, &td)) {
+            if (!tier1_gates_run(*job, sm.gate[wl], gc, p.gate_budget, fresh, s_pseudo[wl], lane, &tv, &td)) {
                 if (lane == 0) {
                     job->active = 1;
                     p.path_n[g] = path_n;
@@ -970,12 +984,22 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(32 * kMctsWarps) mcts_select_kernel(const MctsParams p) {
     __shared__ MctsSmem sm;
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = p.g0 + blockIdx.x * kMctsWarps + wl;
     if (g >= p.g0 + p.gn) return;
-    mcts_select_body(p, sm, g, wl, lane);
+    mcts_select_body<MODE>(p, sm, g, wl, lane);
+}
+
+// tier1_light = 2, one pool: the games' gate jobs (and what follows a finished one), between the tree kernel and the forward.
+__global__ void __launch_bounds__(32 * kMctsWarps) mcts_gate_kernel(const MctsParams p) {
+    __shared__ MctsSmem sm;
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = p.g0 + blockIdx.x * kMctsWarps + wl;
+    if (g >= p.g0 + p.gn) return;
+    mcts_select_body<2>(p, sm, g, wl, lane);
 }
 
 // Keep the subtree under `child` as the new tree, copied breadth first into the other arena (same node
@@ -1225,6 +1249,7 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_expand_kernel(const Mcts
 }
 
 // Steady state: expand the leaf of simulation n, then select the leaf of simulation n + 1, in one launch.
+template <int MODE>
 __global__ void __launch_bounds__(32 * kMctsWarps) mcts_step_kernel(const MctsParams p) {
     __shared__ MctsSmem sm;
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1232,7 +1257,7 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_step_kernel(const MctsPa
     if (g >= p.g0 + p.gn) return;
     mcts_expand_body(p, sm, g, wl, lane);
     __syncwarp();
-    mcts_select_body(p, sm, g, wl, lane);
+    mcts_select_body<MODE>(p, sm, g, wl, lane);
     if (p.pdl_done) {
         __syncwarp();
         unsigned int last = 0;

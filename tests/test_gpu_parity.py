@@ -582,15 +582,17 @@ def test_device_deep_gates_equal_the_host_form(cb, golden):
 @pytest.mark.parametrize("koth", [False, True], ids=["standard", "koth"])
 def test_device_self_play_with_the_deep_gates_equals_the_host_driver(cb, golden, tmp_path, monkeypatch, koth):
     """Self-play with the reference's Tier-1 configuration (leaf gate mate-in-5 by checks + hill in 3; every new root
-    adjudicated by hill in 3 / mate_search(5, exhaustive 2)) on the device against the host driver.  With a budget no job
-    exceeds, the device runs in lock step with the host: identical counters and sample files.  With a small budget jobs
-    are suspended and resumed, games advance at different paces, and every game must still be the same game: the finished
-    games' samples are a subset of the host run's."""
+    adjudicated by hill in 3 / mate_search(5, exhaustive 2)) on the device against the host driver.  With the gate jobs
+    inline in the tree kernel and a budget no job exceeds, the device runs in lock step with the host: identical counters
+    and sample files.  With the jobs in their own kernel (the default) and / or a small budget, games advance at different
+    paces (suspended jobs, one step between an adjudication and the next game) and every game must still be the same game:
+    the finished games' samples are a subset of the host run's."""
     g, blob = golden("6x128_B")
     ev = make_eval(cb, g, blob, "bf16")
     kw = dict(games=16, sims_per_move=20, max_plies=40, koth=koth, seed=11, tier1_light="deep", material_on=True, qsearch="pe",
               max_sims=16 * 20 * 60)
     monkeypatch.setenv("CB_GATE_BUDGET", "100000000")
+    monkeypatch.setenv("CB_GATE_INLINE", "1")
     host = ev.selfplay(threads=1, pipeline=1, sample_path=str(tmp_path / "host.bin"), **kw)
     dev = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "dev.bin"), **kw)
     for k in ("steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins", "black_wins", "draws"):
@@ -600,12 +602,16 @@ def test_device_self_play_with_the_deep_gates_equals_the_host_driver(cb, golden,
     rd = np.fromfile(tmp_path / "dev.bin", dtype=np.float32).reshape(-1, 5763)
     key = lambda r: r[np.lexsort(r.T[::-1])]
     assert rh.shape == rd.shape and rh.shape[0] > 0 and np.array_equal(key(rh), key(rd))
-    monkeypatch.setenv("CB_GATE_BUDGET", "24" if koth else "3")
-    slow = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "slow.bin"), **kw)
-    assert slow["gate_waits"] > 0 and slow["games_finished"] > 0
-    rs = np.fromfile(tmp_path / "slow.bin", dtype=np.float32).reshape(-1, 5763)
     have = {r.tobytes() for r in rh}
-    assert rs.shape[0] > 0 and all(r.tobytes() in have for r in rs)
+    monkeypatch.delenv("CB_GATE_INLINE")
+    for name, budget in (("split", "100000000"), ("slow", "24" if koth else "3")):
+        monkeypatch.setenv("CB_GATE_BUDGET", budget)
+        run = ev.selfplay(pipeline=3, sample_path=str(tmp_path / (name + ".bin")), **kw)
+        assert run["games_finished"] > 0 and run["overflow"] == 0 and (run["gate_waits"] > 0) == (name == "slow")
+        rs = np.fromfile(tmp_path / (name + ".bin"), dtype=np.float32).reshape(-1, 5763)
+        assert rs.shape[0] > 0 and all(r.tobytes() in have for r in rs), name
+        if name == "split":
+            assert rs.shape[0] >= 0.9 * rh.shape[0]
 
 
 @pytest.mark.parametrize("material,qsearch", [(False, 0), (True, "pe")])

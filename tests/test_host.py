@@ -87,6 +87,25 @@ def test_light_gates_equal_the_oracle(cb):
     assert (cb.light_gates(boards, koth=True) == -1).sum() >= 1
 
 
+def test_move_flags_equal_make_move(cb):
+    """cbchess::move_flags_hd (legality and "gives check" of a pseudo-legal move without making it: what the tree kernels'
+    gate searches run per move) against make_move_hd + in_check_hd on every pseudo-legal move of > 20,000 positions:
+    pins, evasions, en passant (including the rank pin through both pawns), castling, promotions, discovered checks."""
+    special = ["r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1", "8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1",
+               "r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1", "rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8",
+               "8/8/8/KPp4r/8/8/8/7k w - c6 0 2", "4k3/8/8/3pP3/8/8/8/4K3 w - d6 0 1", "8/8/8/8/k2Pp2R/8/8/4K3 b - d3 0 1",
+               "r3k2r/8/8/8/8/8/8/R3K2R w KQkq - 0 1", "r3k2r/8/8/8/8/8/8/R3K2R b KQkq - 0 1", "4k3/P7/8/8/8/8/8/4K3 w - - 0 1",
+               "3k4/P7/8/8/8/8/8/4K3 w - - 0 1", "8/8/8/8/8/5k2/4p3/4K3 b - - 0 1", "k7/8/8/8/8/8/1p6/R3K3 b - - 0 1",
+               "5k2/8/8/8/8/8/8/4K2R w K - 0 1", "8/8/8/2k5/3Pp3/8/8/4K2B b - d3 0 1"]
+    total = 0
+    for seed in range(9):
+        a, _, _, _ = O.random_positions(1000 + seed, 2500, 220)
+        bad, n = cb.debug_move_flags(np.concatenate([a, np.stack([u8(f) for f in special])]))
+        assert bad == 0
+        total += n
+    assert total > 600_000
+
+
 def test_deep_gates_equal_the_oracle(cb):
     """The Tier-1 gates at full depth on the host (csrc/host/gates.hpp: mate search to mate-in-5, hill in 3) against
     oracle/gates.c, which is pinned to the reference's own tests: value and terminal distance of the leaf gate as self-play

@@ -21,14 +21,33 @@ rows = []
 def run(label, budget=None, **kw):
     if budget is not None:
         os.environ["CB_GATE_BUDGET"] = str(budget)
-    st = ev.selfplay(games=kw.pop("games", 1024), sims_per_move=200, max_seconds=secs, seed=5, **kw)
+    st = ev.selfplay(games=kw.get("games", 1024), sims_per_move=200, max_seconds=secs, seed=5, **{k: v for k, v in kw.items() if k != 'games'})
     row = dict(config=label, budget=budget, sims_per_s=round(st["sims"] / st["seconds"]), steps_per_s=round(st["steps"] / st["seconds"]),
                evals_per_s=round(st["nn_evals"] / st["seconds"]), gate_hits=st["gate_hits"], gate_waits=st["gate_waits"],
-               wait_fraction=round(st["gate_waits"] / max(1, st["steps"] * 1024), 4), games=st["games_finished"], moves=st["moves"])
+               wait_fraction=round(st["gate_waits"] / max(1, st["steps"] * kw.get("games", 1024)), 4), games=st["games_finished"], moves=st["moves"])
     rows.append(row)
     print(json.dumps(row), flush=True)
 
 
+if len(sys.argv) > 2 and sys.argv[2] == "long":
+    # steady-state figures: runs long enough to leave the openings (a game is ~90 moves x 200 simulations)
+    for G, b in ((1024, 12), (1024, 24), (4096, 12), (4096, 24), (8192, 24)):
+        run("deep gates, one pool, %d games" % G, budget=b, pipeline=3, games=G, tier1_light="deep")
+    run("deep gates + dM by the exchange line, one pool, 4096 games", budget=24, pipeline=3, games=4096, tier1_light="deep", material_on=True, qsearch="pe")
+    run("KOTH, deep gates (hill in 3 + mate-in-5), 4096 games", budget=24, pipeline=3, games=4096, tier1_light="deep", koth=True)
+    run("light gates, one pool, 1024 games", pipeline=3, games=1024, tier1_light=True)
+    with open(os.path.join(REPO, "gpurun_out", "deep_gates_probe_long.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    sys.exit(0)
+if len(sys.argv) > 2 and sys.argv[2] == "games":
+    for G in (1024, 2048, 4096):
+        for b in (24, 48):
+            run("deep gates, one pool, %d games" % G, budget=b, pipeline=3, games=G, tier1_light="deep")
+    run("deep gates, two pools, 4096 games", budget=48, pipeline=4, games=4096, tier1_light="deep")
+    run("light gates, one pool, 4096 games", pipeline=3, games=4096, tier1_light=True)
+    with open(os.path.join(REPO, "gpurun_out", "deep_gates_probe_games.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    sys.exit(0)
 run("vanilla, one pool", pipeline=3)
 run("light gates, one pool", pipeline=3, tier1_light=True)
 for b in (8, 24, 48, 96, 192):

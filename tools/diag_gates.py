@@ -1,26 +1,20 @@
-"""Diagnostic: cost per position entered of the stand-alone gate kernel (cb_debug_device_tier1_gates)."""
-import os, sys, time
-import numpy as np
+"""Diagnostic: forward / tree split of a self-play step with the deep gates (CB_MCTS_TIMES)."""
+import os, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [REPO, os.path.join(REPO, "neurosymbolic-mcts_b200"), os.path.join(REPO, "tests")]
+sys.path[:0] = [REPO, os.path.join(REPO, "neurosymbolic-mcts_b200")]
 import caissa_b200 as cb
-from oracle import pyoracle as O, weights as W
-
-blob = W.flatten(W.make_weights(2, 128, 1405, "B"), 2, 128)
-ev = cb.Evaluator(2, 128, "bf16", device=0)
-ev.load_weights(blob)
-a, _, _, _ = O.random_positions(2718, 2500, 200)
-mn = np.array([O.mate_search(O.array_to_board(r), 5, 0)[2] for r in a])
-hn = np.array([O.koth_center_in_n(O.array_to_board(r), 3)[1] for r in a])
-for koth, nodes in ((False, mn), (True, mn + hn)):
-    ev.debug_device_tier1_gates(a[:64], koth=koth)
-    for rep in range(2):
-        t0 = time.perf_counter()
-        ev.debug_device_tier1_gates(a, koth=koth)
-        dt = time.perf_counter() - t0
-    # sorted by cost, to see the tail: time of the 148 * 4 cheapest-only subset
-    order = np.argsort(nodes)
-    cheap = a[order[:2000]]
-    t0 = time.perf_counter(); ev.debug_device_tier1_gates(cheap, koth=koth); dtc = time.perf_counter() - t0
-    print("koth", koth, "all 2500: %.2f ms, total nodes (approx) %d, max %d -> %.2f us per node of the longest job; cheapest 2000: %.2f ms, nodes %d max %d"
-          % (dt * 1e3, nodes.sum(), nodes.max(), dt * 1e6 / nodes.max(), dtc * 1e3, nodes[order[:2000]].sum(), nodes[order[:2000]].max()), flush=True)
+from oracle import weights as W
+os.environ["CB_MCTS_TIMES"] = "1"
+ev = cb.Evaluator(6, 128, "bf16", device=0)
+ev.load_weights(W.flatten(W.make_weights(6, 128, 1405, "B"), 6, 128))
+for label, kw in (("light", dict(tier1_light=True)), ("deep b1", dict(tier1_light="deep", budget=1)), ("deep b8", dict(tier1_light="deep", budget=8)),
+                  ("deep b24", dict(tier1_light="deep", budget=24)), ("deep b48", dict(tier1_light="deep", budget=48)),
+                  ("deep b24 inline", dict(tier1_light="deep", budget=24, inline=1))):
+    b = kw.pop("budget", None)
+    if b: os.environ["CB_GATE_BUDGET"] = str(b)
+    if kw.pop("inline", 0): os.environ["CB_GATE_INLINE"] = "1"
+    print(label, flush=True)
+    sys.stderr.flush()
+    st = ev.selfplay(games=1024, sims_per_move=200, max_seconds=2.0, seed=5, pipeline=3, **kw)
+    print("   sims/s %.0f steps/s %.0f waits/step %.1f evals/step %.1f" % (st["sims"] / st["seconds"], st["steps"] / st["seconds"],
+          st["gate_waits"] / st["steps"], st["nn_evals"] / st["steps"]), flush=True)
