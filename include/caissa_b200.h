@@ -314,8 +314,9 @@ typedef struct cb_match_config {
     double elo0, elo1, alpha, beta;   /* 0, 10, 0.05, 0.05 */
     double max_seconds;   /* wall-clock bound (0 = unlimited) */
     int qsearch;          /* as cb_selfplay_config.qsearch (src/bin/evaluate_models.rs:343-357) */
-    int tier1_light;      /* as cb_selfplay_config.tier1_light; a root that hits a gate is scored as the win it is (the
-                             reference's search returns the winning move there, src/mcts/tactical_mcts.rs:330-420) */
+    int tier1_light;      /* as cb_selfplay_config.tier1_light (2: the gate at the depths evaluate_models runs, mate-in-5 by
+                             checks and hill in 3, src/bin/evaluate_models.rs:251-282); a root that hits a gate is scored as the
+                             win it is (the reference's search returns the winning move there, src/mcts/tactical_mcts.rs:330-420) */
 } cb_match_config;
 
 typedef struct cb_match_stats {

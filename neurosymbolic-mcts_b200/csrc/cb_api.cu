@@ -2259,8 +2259,8 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     mp.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 200;
     mp.material_on = cfg->material_on;
     mp.qsearch = cfg->qsearch;
-    if (cfg->tier1_light >= 2) return fail(h, CB_EINVAL, "matches run the Tier-1 gates at depth 1 (tier1_light 0 / 1)");
     mp.tier1_light = cfg->tier1_light;
+    if (cfg->tier1_light >= 2 && (rc = mcts_gate_params(h, mp, 0, 0, 0))) return rc;   // 5 / 0 / 3: src/bin/evaluate_models.rs:251,270
     mp.koth = cfg->koth;
     mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414;
     mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.90;   // DEFAULT_EXPLORE_BASE, src/bin/evaluate_models.rs:85
@@ -2359,6 +2359,8 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     }
     cudaStreamSynchronize(h->stream);
     const double secs = elapsed();
+    unsigned long long sims_counted = 0;   // (with the gates at full depth a suspended game completes no simulation in a step)
+    if (mp.tier1_light >= 2) cudaMemcpy(&sims_counted, mp.stats + MS_SIMS, 8, cudaMemcpyDeviceToHost);
     if (gexec) cudaGraphExecDestroy(gexec);
     release();
     if (rc) return rc;
@@ -2370,7 +2372,7 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     out->decision = decision;
     if (decision != 0 && have_llr) { out->llr = llr_at_decision; out->llr_valid = 1; }
     else out->llr_valid = cb_sprt_llr(wins, losses, draws, cfg->elo0, cfg->elo1, &out->llr) == 1;
-    out->sims = steps * G;
+    out->sims = mp.tier1_light >= 2 ? (long long)sims_counted : steps * G;
     out->seconds = secs;
     return CB_OK;
 }

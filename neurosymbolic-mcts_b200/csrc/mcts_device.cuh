@@ -674,6 +674,20 @@ struct MctsSmem {
 // A self-play game in slot g is over (lane 0): count it, log the result record, start the next game.  `rs`: the game's
 // random stream after the draws of its last move.
 __device__ __forceinline__ void mcts_game_over(const MctsParams& p, int g, int result, uint64_t& rs) {
+    if (p.match_mode) {
+        // result from the candidate's point of view, logged in finish order for the SPRT; next game or idle
+        const int cand = result == 0 ? 0 : ((result > 0) == (p.cand_white[g] != 0) ? 1 : -1);
+        atomicAdd(&p.stats[cand > 0 ? MS_WWINS : cand < 0 ? MS_BWINS : MS_DRAWS], 1ull);
+        atomicAdd(&p.stats[MS_GAMES], 1ull);
+        const unsigned long long slot = atomicAdd(p.result_cursor, 1ull);
+        p.result_log[slot % p.result_cap] = cand;
+        const unsigned long long k = atomicAdd(p.games_started, 1ull);
+        const uint64_t seed = rng_next(rs) ^ ((uint64_t)g << 32);
+        mcts_reset_game(p, g, seed);
+        p.cand_white[g] = (k & 1ull) == 0;
+        if ((long long)k >= p.total_games) p.idle[g] = 1;
+        return;
+    }
     atomicAdd(&p.stats[result > 0 ? MS_WWINS : result < 0 ? MS_BWINS : MS_DRAWS], 1ull);
     atomicAdd(&p.stats[MS_SAMPLES], (unsigned long long)p.samples_in_game[g]);
     atomicAdd(&p.stats[MS_GAMES], 1ull);
@@ -728,8 +742,10 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     if (MODE == 2 && !pending) return;
     if (pending == 2) {
         // the game loop's pre-check of the new root (src/bin/self_play.rs:241-283): a hill in 3 or mate_search(board, 5,
-        // exhaustive 2) ends the game as a win of the side to move
-        const GateCfg gc = {p.koth ? 3 : 0, 5, 2};
+        // exhaustive 2) ends the game as a win of the side to move.  In a match the mover's search answers a root that its own
+        // gate decides with the winning move (src/mcts/tactical_mcts.rs:330-420, the search's depths), move after move until
+        // the win is on the board: the same result
+        const GateCfg gc = p.match_mode ? GateCfg{p.koth ? p.t1_koth_depth : 0, p.t1_mate_depth, p.t1_exh_depth} : GateCfg{p.koth ? 3 : 0, 5, 2};
         int gv, gd;
         if (!tier1_gates_run(*job, sm.gate[wl], gc, p.gate_budget, false, s_pseudo[wl], lane, &gv, &gd)) {
             if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; atomicAdd(&p.stats[MS_GATE_WAITS], 1ull); }
@@ -1212,19 +1228,7 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
             if (reps >= 3 || nb.halfmove >= 100 || p.ply[g] > p.max_plies) result = 0;
             else if (gate == 1) result = white_moved ? -1 : 1;
         }
-        if (result != 2 && p.match_mode) {
-            // result from the candidate's point of view, logged in finish order for the SPRT; next game or idle
-            const int cand = result == 0 ? 0 : ((result > 0) == (p.cand_white[g] != 0) ? 1 : -1);
-            atomicAdd(&p.stats[cand > 0 ? MS_WWINS : cand < 0 ? MS_BWINS : MS_DRAWS], 1ull);
-            atomicAdd(&p.stats[MS_GAMES], 1ull);
-            const unsigned long long slot = atomicAdd(p.result_cursor, 1ull);
-            p.result_log[slot % p.result_cap] = cand;
-            const unsigned long long k = atomicAdd(p.games_started, 1ull);
-            const uint64_t seed = rng_next(rs) ^ ((uint64_t)g << 32);
-            mcts_reset_game(p, g, seed);
-            p.cand_white[g] = (k & 1ull) == 0;
-            if ((long long)k >= p.total_games) p.idle[g] = 1;
-        } else if (result != 2) {
+        if (result != 2) {
             mcts_game_over(p, g, result, rs);
         } else {
             p.rng[g] = rs;

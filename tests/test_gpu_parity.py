@@ -715,6 +715,42 @@ def test_model_match_on_device(cb, golden):
     del cand2
 
 
+def test_model_match_with_the_deep_gates(cb, golden, monkeypatch):
+    """The match runner with the Tier-1 gate at full depth (the reference's evaluate_models default): the accounting holds,
+    and pacing (the per-step budget of the gate jobs) changes which games finish first, not what a game is - a model against
+    itself under King-of-the-Hill rules, where the gate decides many games, scores the same with two budgets."""
+    g, blob = golden("6x128_B")
+    cand = make_eval(cb, g, blob, "bf16")
+    curr = make_eval(cb, g, blob, "bf16")
+    kw = dict(games=16, total_games=16, sims_per_move=16, max_plies=40, seed=5, tier1_light=2, koth=True)
+    runs = []
+    for budget in ("1000000", "8"):
+        monkeypatch.setenv("CB_GATE_BUDGET", budget)
+        r = cand.match(curr, **kw)
+        assert r["games"] == 16 == r["candidate_wins"] + r["current_wins"] + r["draws"] and r["sims"] > 16 * 16
+        runs.append((r["candidate_wins"], r["current_wins"], r["draws"]))
+    assert runs[0] == runs[1]                 # 16 slots, 16 games: every slot plays exactly its first game
+    light = cand.match(curr, **dict(kw, tier1_light=1))
+    assert light["games"] == 16
+
+
+def test_two_pool_self_play_with_the_deep_gates(cb, golden, tmp_path, monkeypatch):
+    """pipeline 4 with tier1_light = 2 (gate jobs inline in the tree kernels that run beside the other pool's forward): the
+    games are the one-pool run's games."""
+    g, blob = golden("6x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    kw = dict(games=16, sims_per_move=20, max_plies=30, seed=4, tier1_light="deep", max_sims=16 * 20 * 50)
+    monkeypatch.setenv("CB_GATE_BUDGET", "6")
+    one = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "one.bin"), **kw)
+    two = ev.selfplay(pipeline=4, sample_path=str(tmp_path / "two.bin"), **kw)
+    r1 = np.fromfile(tmp_path / "one.bin", dtype=np.float32).reshape(-1, 5763)
+    r2 = np.fromfile(tmp_path / "two.bin", dtype=np.float32).reshape(-1, 5763)
+    assert one["games_finished"] > 0 and two["games_finished"] > 0 and one["overflow"] == two["overflow"] == 0
+    a, b = {r.tobytes() for r in r1}, {r.tobytes() for r in r2}
+    small, big = (a, b) if len(a) <= len(b) else (b, a)
+    assert len(small) > 0 and len(small & big) >= 0.8 * len(small)     # the slower run's finished games are the faster run's
+
+
 # ------------------------------------------------------------------ reference-shaped host interface
 def test_neural_net_policy_and_inference_server(cb, golden):
     import threading
