@@ -172,6 +172,7 @@ SIGNATURES = {
     "cb_light_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_tier1_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP]),
     "cb_debug_move_flags": (ctypes.c_longlong, [_VP, ctypes.c_int, _VP]),
+    "cb_cap1_qsearch": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP, _VP]),
     "cb_mate_search": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_koth_center_in_n": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_debug_device_legal_moves": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP, _VP]),
@@ -521,7 +522,7 @@ class Evaluator:
                 "d2h_ms": t.d2h_ms}
 
 
-_QSEARCH = {0: 0, 1: 1, "static": 0, "stand-pat": 0, "pe": 1, "principal-exchange": 1}
+_QSEARCH = {0: 0, 1: 1, 2: 2, "static": 0, "stand-pat": 0, "pe": 1, "principal-exchange": 1, "cap1": 2}
 
 
 def principal_exchange(boards, want_nodes=False):
@@ -553,6 +554,17 @@ def tier1_gates(boards, koth=False, mate_depth=5, exhaustive_depth=0, koth_depth
                                      _ptr(out), _ptr(dist)):
         raise CaissaError("cb_tier1_gates failed")
     return out, dist
+
+
+def cap1_qsearch(boards):
+    """The cap = 1 quiescence search on the host (cb_cap1_qsearch) -> (q f32 pawn units, completed u8, nodes u32, depth u8)."""
+    b = _boards_u8(boards)
+    n = b.shape[0]
+    q, c = np.empty(n, dtype=np.float32), np.empty(n, dtype=np.uint8)
+    nodes, d = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint8)
+    if load_library().cb_cap1_qsearch(_ptr(b), n, _ptr(q), _ptr(c), _ptr(nodes), _ptr(d)):
+        raise CaissaError("cb_cap1_qsearch failed")
+    return q, c, nodes, d
 
 
 def debug_move_flags(boards):

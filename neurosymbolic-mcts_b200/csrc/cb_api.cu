@@ -951,7 +951,7 @@ struct DevSample {
 
 // host/selfplay.cpp: one 5763-f32 record (src/training_data.rs:20-60)
 void cbsp_write_sample(FILE* f, const cb_board& b, float material, const std::pair<uint16_t, float>* policy, size_t n_policy,
-                       int result_white, std::vector<float>& rec);
+                       int result_white, std::vector<float>& rec, bool qsearch_completed = true);
 
 namespace {
 
@@ -1845,6 +1845,7 @@ struct DeviceSearchIO {
 static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out, const DeviceSearchIO* dbg) {
     if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
     if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
+    if (cfg->qsearch == 2) return fail(h, CB_EINVAL, "the cap1 q-search runs in the host-driven pools (pipeline 0-2); the device pipelines compute dM by the stand pat or the exchange line");
     CB_CUDA(h, cudaSetDevice(h->device));
     const int G = cfg->games;
     const int pools = (!dbg && cfg->pipeline == 4) ? 2 : 1;

@@ -168,6 +168,92 @@ CB_Q int principal_exchange_cp(const cb_board& root, uint32_t* nodes_out = nullp
     return pe_unwind(ap, depth, ret);
 }
 
+#if !defined(__CUDACC__)
+// The cap = 1 quiescence search (the reference's `--qsearch cap1`, src/search/quiescence.rs:808-1012), host form: at a node
+// that is not in check the stand pat, the FIRST LEGAL capture of the MVV-LVA order (the same keys as the exchange line) and -
+// once per side and branch - the first legal checking move of the generation order that is not that capture; in check every
+// legal evasion.  Window (-100000, 100000), depth 20 (:1000-1012).  "That capture" is identified the way the reference does
+// it (:933-944): by the from-square of the first entry of the capture list whose target is the played capture's target - an
+// illegal capture of the same target that sorts earlier makes the test miss, as written.
+struct Cap1Result {
+    int score;
+    bool completed;
+    uint32_t nodes;
+    int depth;
+};
+inline Cap1Result cap1_qsearch(const cb_board& b, int alpha, int beta, int max_depth, bool w_check_used, bool b_check_used) {
+    Cap1Result r = {0, true, 1, 0};
+    const int us = b.w_to_move ? 0 : 1;
+    const bool in_check = in_check_hd(b, us);
+    if (!in_check) {
+        const int sp = pesto_cp(b);
+        if (sp >= beta) { r.score = beta; return r; }
+        if (sp > alpha) alpha = sp;
+    }
+    if (max_depth == 0) { r.score = alpha; r.completed = !in_check; return r; }
+    cb_board nb;
+    auto child = [&](bool wu, bool bu) -> bool {   // searches `nb`; true = beta cut-off (r.score is set)
+        const Cap1Result c = cap1_qsearch(nb, -beta, -alpha, max_depth - 1, wu, bu);
+        r.nodes += c.nodes;
+        if (c.depth + 1 > r.depth) r.depth = c.depth + 1;
+        if (!c.completed) r.completed = false;
+        const int sc = -c.score;
+        if (sc >= beta) { r.score = beta; return true; }
+        if (sc > alpha) alpha = sc;
+        return false;
+    };
+    Move mv[kMaxMoves];
+    if (in_check) {
+        const int n = gen_pseudo(b, mv);
+        bool any = false;
+        for (int i = 0; i < n; ++i) {
+            make_move_hd(b, mv[i], &nb);
+            if (in_check_hd(nb, us)) continue;
+            any = true;
+            if (child(w_check_used, b_check_used)) return r;
+        }
+        r.score = any ? alpha : -1000000;
+        return r;
+    }
+    int best_to = -1, skip_from = -1;
+    uint16_t tried[kMaxMoves];   // the capture list's entries up to the played one, in order
+    int n_tried = 0;
+    for (uint32_t above = 0;;) {
+        uint32_t best = kPeNoCapture;
+        Move bm = 0;
+        for (int pt = 0; pt < 6; ++pt)
+            for (uint64_t bb = b.pieces[us * 6 + pt]; bb; bb &= bb - 1) {
+                Move m;
+                const uint32_t k = pe_piece_best(b, lsb(bb), pt, above, &m);
+                if (k < best) { best = k; bm = m; }
+            }
+        if (best == kPeNoCapture) break;
+        tried[n_tried++] = bm;
+        make_move_hd(b, bm, &nb);
+        if (!in_check_hd(nb, us)) { best_to = mv_to(bm); break; }
+        above = best;
+    }
+    if (best_to >= 0) {
+        for (int i = 0; i < n_tried && skip_from < 0; ++i)
+            if (mv_to(tried[i]) == best_to) skip_from = mv_from(tried[i]);
+        if (child(w_check_used, b_check_used)) return r;
+    }
+    if (!(us == 0 ? w_check_used : b_check_used)) {
+        const int n = gen_pseudo(b, mv);
+        for (int i = 0; i < n; ++i) {
+            if (best_to >= 0 && mv_from(mv[i]) == skip_from && mv_to(mv[i]) == best_to) continue;
+            make_move_hd(b, mv[i], &nb);
+            if (!in_check_hd(nb, 1 - us) || in_check_hd(nb, us)) continue;
+            if (child(us == 0 ? true : w_check_used, us == 1 ? true : b_check_used)) return r;
+            break;
+        }
+    }
+    r.score = alpha;
+    return r;
+}
+inline Cap1Result forced_cap1(const cb_board& b) { return cap1_qsearch(b, -kPeWindow, kPeWindow, kPeMaxDepth, false, false); }
+#endif
+
 #if defined(__CUDACC__)
 // k-th (0-based) set bit of a 64-bit set, k < popcount: binary search on popcounts
 __device__ __forceinline__ int nth_set_bit(uint64_t bb, int k) {

@@ -51,6 +51,7 @@ constexpr uint8_t kMateIn1Dist = (uint8_t)1000001u;   // `mate_result.0.unsigned
 struct Sample {
     cb_board board;
     float material;
+    bool completed = true;   // qsearch_completed of the sample's material search
     std::vector<std::pair<uint16_t, float>> policy;
 };
 
@@ -68,7 +69,13 @@ bool root_adjudicated(const cb_board& b, const Move* legal, int n, int tier1, bo
 }
 
 // dM of a position in pawn units: stand pat or the principal-exchange line (qsearch.hpp)
-float material_q(const cb_board& b, int qsearch) {
+float material_q(const cb_board& b, int qsearch, bool* completed = nullptr) {
+    if (completed) *completed = true;
+    if (qsearch == 2) {   // QSearchVariant::Cap1 (src/mcts/tactical_mcts.rs:725-727)
+        const cbchess::Cap1Result r = cbchess::forced_cap1(b);
+        if (completed) *completed = r.completed;
+        return (float)r.score / 100.0f;
+    }
     return (float)(qsearch == 1 ? cbchess::principal_exchange_cp(b) : cbchess::pesto_cp(b)) / 100.0f;
 }
 
@@ -292,7 +299,7 @@ int play_move(Game& g, const SearchCfg& c) {
     for (uint32_t i = 0; i < root.n_children; ++i) total += g.nodes[root.first_child + i].visits;
     Sample s;
     s.board = g.root_board;
-    s.material = material_q(g.root_board, c.qsearch);   // computed whatever material_on says (:315-329)
+    s.material = material_q(g.root_board, c.qsearch, &s.completed);   // computed whatever material_on says (:315-329)
     if (total > 0)
         for (uint32_t i = 0; i < root.n_children; ++i) {
             const Node& ch = g.nodes[root.first_child + i];
@@ -421,7 +428,7 @@ struct EvalJob {
 // One training sample in the reference's 5763-f32 record (src/training_data.rs:20-60): 1088 planes, material,
 // qsearch flag, z from the mover's point of view, dense 4672 policy.  `rec` is scratch of 5763 floats.
 void cbsp_write_sample(FILE* f, const cb_board& b, float material, const std::pair<uint16_t, float>* policy, size_t n_policy,
-                       int result_white, std::vector<float>& rec) {
+                       int result_white, std::vector<float>& rec, bool qsearch_completed) {
     rec.assign(5763, 0.0f);
     const bool white = b.w_to_move != 0;
     const int stm = white ? 0 : 1;
@@ -441,7 +448,7 @@ void cbsp_write_sample(FILE* f, const cb_board& b, float material, const std::pa
         if (b.castling & (white ? ow[i] : ob[i]))
             for (int j = 0; j < 64; ++j) rec[(13 + i) * 64 + j] = 1.0f;
     rec[1088] = material;
-    rec[1089] = 1.0f;  // qsearch_completed
+    rec[1089] = qsearch_completed ? 1.0f : 0.0f;  // (the stand pat and the exchange line always complete; cap1 can hit its depth in check)
     rec[1090] = result_white == 0 ? 0.0f : ((result_white > 0) == white ? 1.0f : -1.0f);
     for (size_t i = 0; i < n_policy; ++i)
         if (policy[i].first < CB_POLICY_SIZE) rec[1091 + policy[i].first] = policy[i].second;
@@ -524,6 +531,18 @@ int cb_principal_exchange(const cb_board* boards, int n, float* q, uint32_t* nod
         uint32_t nd = 0;
         q[i] = (float)cbchess::principal_exchange_cp(boards[i], &nd) / 100.0f;
         if (nodes) nodes[i] = nd;
+    }
+    return 0;
+}
+
+int cb_cap1_qsearch(const cb_board* boards, int n, float* q, uint8_t* completed, uint32_t* nodes, uint8_t* depth) {
+    if (n < 0 || (n > 0 && (!boards || !q))) return 1;
+    for (int i = 0; i < n; ++i) {
+        const cbchess::Cap1Result r = cbchess::forced_cap1(boards[i]);
+        q[i] = (float)r.score / 100.0f;
+        if (completed) completed[i] = r.completed ? 1 : 0;
+        if (nodes) nodes[i] = r.nodes;
+        if (depth) depth[i] = (uint8_t)r.depth;
     }
     return 0;
 }
@@ -679,7 +698,7 @@ int cb_selfplay_run(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_sta
             std::vector<float> rec(5763);
             std::lock_guard<std::mutex> l(file_mu);
             for (const Sample& s : g.samples)
-                cbsp_write_sample(sample_file, s.board, s.material, s.policy.data(), s.policy.size(), result_white, rec);
+                cbsp_write_sample(sample_file, s.board, s.material, s.policy.data(), s.policy.size(), result_white, rec, s.completed);
         }
         samples_written += (long long)g.samples.size();
         games_finished++;

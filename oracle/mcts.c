@@ -426,6 +426,7 @@ static node* select_leaf(orc_tree* t, const orc_mcts_config* cfg, orc_eval_fn ev
 
 static float leaf_material(const orc_board* b, const orc_mcts_config* cfg) {
     if (cfg->qsearch == 1) return orc_forced_principal_exchange(b, NULL, NULL);
+    if (cfg->qsearch == 2) return orc_forced_cap1(b, NULL, NULL, NULL, NULL); /* QSearchVariant::Cap1, tactical_mcts.rs:725-727 */
     return (float)orc_pst_eval_cp(b) / 100.0f;
 }
 

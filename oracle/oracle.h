@@ -75,6 +75,10 @@ int   orc_gen_captures_mvvlva(const orc_board* b, orc_move* out, int* long_list)
 int   orc_principal_exchange(const orc_board* b, int alpha, int beta, int max_depth, uint32_t* nodes,
                              int* long_list);                       /* src/search/quiescence.rs:756-794; *nodes accumulates */
 float orc_forced_principal_exchange(const orc_board* b, uint32_t* nodes, int* long_list); /* :797-804 */
+/* cap = 1 quiescence search (qsearch.c; the "cap1" dM search), src/search/quiescence.rs:808-1012 */
+int   orc_cap1_qsearch(const orc_board* b, int alpha, int beta, int max_depth, int w_check_used, int b_check_used, int* completed,
+                       uint32_t* nodes, int* depth_used, int* long_list);
+float orc_forced_cap1(const orc_board* b, int* completed, uint32_t* nodes, int* depth_used, int* long_list);
 /* light Tier-1 gates = the reference's gate at depth 1 (qsearch.c) */
 int   orc_mate_in_1(const orc_board* b);            /* src/search/mate_search.rs:64-108, max_depth 1 */
 int   orc_koth_in_1(const orc_board* b);            /* src/search/koth.rs:43-65, max_n 1 */
@@ -103,7 +107,7 @@ typedef void (*orc_eval_fn)(void* user, const orc_board* b, const orc_move* move
 typedef struct {
     int sims;             /* max_iterations */
     int material_on;      /* enable_material_value */
-    int qsearch;          /* dM: 0 static PeSTO / 100, 1 principal exchange */
+    int qsearch;          /* dM: 0 static PeSTO / 100, 1 principal exchange, 2 cap1 */
     int koth;
     int tier1_light;      /* Tier-1 gates: 1 at depth 1; 2 the reference's gate (leaves: mate_depth / exhaustive_mate_depth /
                              koth_depth below; the game loop: hill in 3, mate_search(5, exhaustive 2), self_play.rs:241-283) */

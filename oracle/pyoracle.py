@@ -83,6 +83,8 @@ def lib():
         L.orc_principal_exchange.restype = ctypes.c_int
         L.orc_forced_principal_exchange.argtypes = [bp, up, ip]
         L.orc_forced_principal_exchange.restype = ctypes.c_float
+        L.orc_forced_cap1.argtypes = [bp, ip, up, ip, ip]
+        L.orc_forced_cap1.restype = ctypes.c_float
         for name in ("orc_mate_in_1", "orc_koth_in_1"):
             getattr(L, name).argtypes = [bp]
             getattr(L, name).restype = ctypes.c_int
@@ -275,6 +277,22 @@ def forced_principal_exchange(b):
     return float(s), nodes.value
 
 
+def forced_cap1(b):
+    """forced_cap1_pesto_balance -> (pawn units as f32, completed, nodes, depth_used)."""
+    c, d, ll = ctypes.c_int(1), ctypes.c_int(0), ctypes.c_int(0)
+    n = ctypes.c_uint32(0)
+    s = lib().orc_forced_cap1(ctypes.byref(b), ctypes.byref(c), ctypes.byref(n), ctypes.byref(d), ctypes.byref(ll))
+    return float(s), bool(c.value), n.value, d.value
+
+
+def cap1_q(boards_u8):
+    """cap1 material scalar of every board (pawn units, side to move)."""
+    q = np.zeros(boards_u8.shape[0], dtype=np.float32)
+    for i in range(boards_u8.shape[0]):
+        q[i] = forced_cap1(array_to_board(boards_u8[i]))[0]
+    return q
+
+
 def mate_in_1(b):
     return bool(lib().orc_mate_in_1(ctypes.byref(b)))
 
@@ -339,7 +357,7 @@ def mcts_config(sims=200, material_on=False, qsearch=0, koth=False, tier1_light=
                 c_puct=1.414, explore_base=0.80, mate_depth=0, exhaustive_mate_depth=0, koth_depth=0):
     """tier1_light: False / True (gates at depth 1) / 2 or "deep" (the reference's gate: mate-in-5 checks only, hill in 3)."""
     tier1 = 2 if tier1_light == "deep" else int(tier1_light)
-    return MctsConfig(int(sims), int(bool(material_on)), 1 if qsearch in (1, "pe") else 0, int(koth), tier1,
+    return MctsConfig(int(sims), int(bool(material_on)), 1 if qsearch in (1, "pe") else 2 if qsearch in (2, "cap1") else 0, int(koth), tier1,
                       int(shuffle), int(max_plies), float(c_puct), float(explore_base), int(mate_depth),
                       int(exhaustive_mate_depth), int(koth_depth))
 

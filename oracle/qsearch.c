@@ -186,6 +186,107 @@ float orc_forced_principal_exchange(const orc_board* b, uint32_t* nodes, int* lo
     return (float)cp / 100.0f;
 }
 
+/* ---- cap = 1 quiescence search (variant "cap1"), src/search/quiescence.rs:808-1012 ----
+ * At a node not in check: stand pat (cut-off / raise alpha), then the FIRST LEGAL capture of the MVV-LVA list, then - once
+ * per side and branch - the first legal move of the generation-order list that gives check and is not "that capture"
+ * (identified as written, :933-944: by the from-square of the first entry of the capture list whose target is the played
+ * capture's target, and that target).  In check: every legal evasion, no stand pat; no legal move = -1_000_000.  Depth 0: in
+ * check = not completed.  Returns the score; *completed / *nodes / *depth_used as the reference's tuple.
+ * Pins: tests/unit/ext_qsearch_tests.rs:354-409,571-586 (inequalities, completion, node bound). */
+int orc_cap1_qsearch(const orc_board* b, int alpha, int beta, int max_depth, int w_check_used, int b_check_used, int* completed,
+                     uint32_t* nodes_out, int* depth_used, int* long_list) {
+    uint32_t nodes = 1;
+    int all_completed = 1, max_child_depth = 0, ret;
+    const int us = b->w_to_move ? 0 : 1;
+    const int in_check = orc_in_check(b, us);
+#define CAP1_RETURN(v, c, d) do { ret = (v); *completed = (c); *nodes_out = nodes; *depth_used = (d); return ret; } while (0)
+    if (!in_check) {
+        const int stand_pat = orc_pst_eval_cp(b);
+        if (stand_pat >= beta) CAP1_RETURN(beta, 1, 0);
+        if (stand_pat > alpha) alpha = stand_pat;
+    }
+    if (max_depth == 0) CAP1_RETURN(alpha, in_check ? 0 : 1, 0);
+    orc_move mv[ORC_MAX_MOVES];
+    int ncap;
+    if (in_check) {
+        const int n = orc_gen_pseudo_ref(b, mv, &ncap);
+        int any_legal = 0;
+        for (int i = 0; i < n; ++i) {
+            orc_board nb;
+            orc_make_move(b, mv[i], &nb);
+            if (orc_in_check(&nb, us)) continue;
+            any_legal = 1;
+            int cc, cd;
+            uint32_t cn;
+            const int score = -orc_cap1_qsearch(&nb, -beta, -alpha, max_depth - 1, w_check_used, b_check_used, &cc, &cn, &cd, long_list);
+            nodes += cn;
+            if (cd + 1 > max_child_depth) max_child_depth = cd + 1;
+            if (!cc) all_completed = 0;
+            if (score >= beta) CAP1_RETURN(beta, all_completed, max_child_depth);
+            if (score > alpha) alpha = score;
+        }
+        if (!any_legal) CAP1_RETURN(-1000000, 1, 0);
+        CAP1_RETURN(alpha, all_completed, max_child_depth);
+    }
+    orc_move caps[ORC_MAX_MOVES];
+    int ll = 0;
+    const int nc = orc_gen_captures_mvvlva(b, caps, &ll);
+    if (ll && long_list) *long_list = 1;
+    int best_to = -1;
+    for (int i = 0; i < nc; ++i) {
+        orc_board nb;
+        orc_make_move(b, caps[i], &nb);
+        if (orc_in_check(&nb, us)) continue;
+        best_to = ORC_TO(caps[i]);
+        int cc, cd;
+        uint32_t cn;
+        const int score = -orc_cap1_qsearch(&nb, -beta, -alpha, max_depth - 1, w_check_used, b_check_used, &cc, &cn, &cd, long_list);
+        nodes += cn;
+        if (cd + 1 > max_child_depth) max_child_depth = cd + 1;
+        if (!cc) all_completed = 0;
+        if (score >= beta) CAP1_RETURN(beta, all_completed, max_child_depth);
+        if (score > alpha) alpha = score;
+        break;
+    }
+    if (!(us == 0 ? w_check_used : b_check_used)) {
+        int skip_from = -1;
+        if (best_to >= 0)
+            for (int i = 0; i < nc; ++i)
+                if (ORC_TO(caps[i]) == best_to) { skip_from = ORC_FROM(caps[i]); break; }
+        const int n = orc_gen_pseudo_ref(b, mv, &ncap);
+        for (int i = 0; i < n; ++i) {
+            if (best_to >= 0 && ORC_FROM(mv[i]) == skip_from && ORC_TO(mv[i]) == best_to) continue;
+            orc_board nb;
+            orc_make_move(b, mv[i], &nb);
+            if (!orc_in_check(&nb, 1 - us)) continue; /* gives_check, src/board.rs:682-777 */
+            if (orc_in_check(&nb, us)) continue;
+            int cc, cd;
+            uint32_t cn;
+            const int score = -orc_cap1_qsearch(&nb, -beta, -alpha, max_depth - 1, us == 0 ? 1 : w_check_used, us == 1 ? 1 : b_check_used,
+                                                &cc, &cn, &cd, long_list);
+            nodes += cn;
+            if (cd + 1 > max_child_depth) max_child_depth = cd + 1;
+            if (!cc) all_completed = 0;
+            if (score >= beta) CAP1_RETURN(beta, all_completed, max_child_depth);
+            if (score > alpha) alpha = score;
+            break;
+        }
+    }
+    CAP1_RETURN(alpha, all_completed, max_child_depth);
+#undef CAP1_RETURN
+}
+
+float orc_forced_cap1(const orc_board* b, int* completed, uint32_t* nodes, int* depth_used, int* long_list) { /* :1000-1012 */
+    int c = 1, d = 0, ll = 0;
+    uint32_t n = 0;
+    const int cp = orc_cap1_qsearch(b, -100000, 100000, 20, 0, 0, &c, &n, &d, &ll);
+    if (completed) *completed = c;
+    if (nodes) *nodes = n;
+    if (depth_used) *depth_used = d;
+    if (long_list) *long_list = ll;
+    return (float)cp / 100.0f;
+}
+
 /* ---- light Tier-1 gates: the reference's gate at depth 1 ----
  *   mate in one     src/search/mate_search.rs:64-108 with max_depth = 1: a legal (checking) move after which the
  *                   opponent is in check without a legal move (:129-200)

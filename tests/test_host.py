@@ -72,6 +72,20 @@ def test_principal_exchange_equals_the_oracle(cb):
     assert cb.principal_exchange(boards[:0]).shape == (0,)
 
 
+def test_cap1_qsearch_equals_the_oracle(cb):
+    """cb_cap1_qsearch (the capture by MVV-LVA keys, no list, no sort) against oracle/qsearch.c's list-and-sort statement of
+    src/search/quiescence.rs:808-1012: score, completion flag, node count and depth of every position."""
+    a, _, _, _ = O.random_positions(4711, 4000, 220)
+    boards = np.concatenate([a, np.stack([u8(f) for f in PE_FENS + [
+        "r3k3/8/8/1N6/8/8/8/4K3 w - - 0 1", "6k1/5ppp/8/8/8/8/8/3RK3 w - - 0 1", "k7/8/8/8/8/8/1B6/R3K3 w - - 0 1",
+        "7k/1p1b1Qp1/1r6/p4pq1/1b1Np2p/4P3/K1rNR1PP/3R4 w - - 0 36"]])])
+    q, completed, nodes, depth = cb.cap1_qsearch(boards)
+    for i in range(boards.shape[0]):
+        w = O.forced_cap1(O.array_to_board(boards[i]))
+        assert (q[i], bool(completed[i]), int(nodes[i]), int(depth[i])) == (np.float32(w[0]), w[1], w[2], w[3]), i
+    assert (q != cb.principal_exchange(boards)).sum() > 800 and nodes.max() > 300     # the checks do change dM on this corpus
+
+
 def test_light_gates_equal_the_oracle(cb):
     """cb_light_gates (legal list + early-exit reply search) against the oracle's plain statement, both rule sets."""
     a, _, _, _ = O.random_positions(31337, 3000, 200)

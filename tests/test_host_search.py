@@ -55,7 +55,8 @@ def corpus(n_random, seed=77):
 
 MODES = [dict(), dict(material_on=True, qsearch="pe"), dict(material_on=True, qsearch=0), dict(koth=True),
          dict(koth=True, tier1_light=True, material_on=True, qsearch="pe"), dict(tier1_light=True), dict(shuffle_children=True),
-         dict(tier1_light="deep"), dict(tier1_light="deep", koth=True, material_on=True, qsearch="pe")]
+         dict(tier1_light="deep"), dict(tier1_light="deep", koth=True, material_on=True, qsearch="pe"),
+         dict(material_on=True, qsearch="cap1"), dict(material_on=True, qsearch="cap1", tier1_light="deep")]
 
 
 def mode_id(m):
@@ -107,7 +108,8 @@ def test_child_order_is_the_reference_generation_order():
 
 
 @pytest.mark.parametrize("mode", [dict(), dict(material_on=True, qsearch="pe"), dict(koth=True), dict(tier1_light=True, koth=True),
-                                  dict(shuffle_children=True), dict(tier1_light="deep"), dict(tier1_light="deep", koth=True)], ids=mode_id)
+                                  dict(shuffle_children=True), dict(tier1_light="deep"), dict(tier1_light="deep", koth=True),
+                                  dict(material_on=True, qsearch="cap1", tier1_light="deep")], ids=mode_id)
 def test_whole_games_equal_the_oracle(mode):
     """Search + move choice + tree reuse + game end over whole games: same samples (positions, visit fractions,
     material scalars), same result, same length."""

@@ -147,3 +147,36 @@ def test_hill_in_one_known_answers():  # tests/unit/koth_tests.rs:19-37,104-118
     b = O.from_fen("8/8/8/8/3k4/8/8/K7 w - - 0 1")
     assert O.light_gates(b, koth=True) == -1 and O.light_gates(b, koth=False) == 2
     assert O.light_gates(O.from_fen("6k1/5ppp/8/8/8/8/8/4R1K1 w - - 0 1")) == 1
+
+
+# ------------------------------------------------------------------ cap = 1 quiescence search (variant "cap1")
+def test_cap1_known_answers_of_the_reference():
+    """tests/unit/ext_qsearch_tests.rs:354-409,571-586: the start position is quiet and completes; a checking knight fork is
+    found where the exchange line sees nothing; the back-rank check is worth more than three pawns (the mate is returned as the
+    window's beta: 1000 pawn units); the "R3 blunder" position stays under 5000 nodes; a discovered check is searched."""
+    score, completed, nodes, _ = O.forced_cap1(O.from_fen("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1"))
+    assert abs(score) < 0.5 and completed and nodes >= 1
+    fork = O.from_fen("r3k3/8/8/1N6/8/8/8/4K3 w - - 0 1")
+    assert O.forced_cap1(fork)[0] > O.forced_principal_exchange(fork)[0]
+    score, _, nodes, _ = O.forced_cap1(O.from_fen("6k1/5ppp/8/8/8/8/8/3RK3 w - - 0 1"))
+    assert score > 3.0 and score == 1000.0 and nodes == 2
+    assert O.forced_cap1(O.from_fen("7k/1p1b1Qp1/1r6/p4pq1/1b1Np2p/4P3/K1rNR1PP/3R4 w - - 0 36"))[2] < 5000
+    score, completed, nodes, depth = O.forced_cap1(O.from_fen("k7/8/8/8/8/8/1B6/R3K3 w - - 0 1"))
+    assert completed and nodes >= 2 and depth >= 1
+    for fen in ["rnbqkb1r/pppp1ppp/8/4p3/2B1N3/8/PPPP1PPP/R1BQK1NR b KQkq - 0 4", "r1b2rk1/pp2nppp/2pBp3/q7/1nP4P/5BN1/P4P2/R2QK2R w KQ - 0 15",
+                "r1bq1rk1/ppp2ppp/2np1n2/2b1p3/2B1P3/2NP1N2/PPP2PPP/R1BQ1RK1 b - - 5 7"]:   # :410-455 (printed table: must run)
+        O.forced_cap1(O.from_fen(fen))
+
+
+def test_cap1_is_the_exchange_line_plus_one_check_per_side():
+    """Structure, on 1500 playout positions: a position without any checking move available to either side along the line
+    scores what the exchange line scores whenever no check exists at the root and cap1 used a single path; and the node count
+    is bounded by the narrow tree (two children per node, evasions aside)."""
+    boards, _, _, _ = O.random_positions(99, 1500, 200)
+    same = 0
+    for r in boards:
+        b = O.array_to_board(r)
+        s, completed, nodes, depth = O.forced_cap1(b)
+        assert depth <= 20 and nodes >= 1 and -1000.0 <= s <= 1000.0
+        same += s == O.forced_principal_exchange(b)[0]
+    assert 0.3 * len(boards) < same < len(boards)
