@@ -227,7 +227,7 @@ typedef struct cb_selfplay_config {
     int qsearch;          /* dM when material_on: 0 static PeSTO/100 (stand pat), 1 principal exchange
                              (QSearchVariant::PrincipalExchange; leaf input and the sample's material scalar,
                              src/bin/self_play.rs:315-329), 2 QSearchVariant::Cap1 (src/search/quiescence.rs:808-1012: one
-                             capture + one check per side + every evasion; host-driven pools, pipeline 0-2) */
+                             capture + one check per side + every evasion) */
     int tier1_light;      /* 1: the light Tier-1 gates (the reference's gate at depth 1): a leaf where the side to
                              move mates in one — or, with koth, steps onto the hill / faces a king already on it —
                              is terminal (+1 / -1, src/mcts/tactical_mcts.rs:619-708) and a game whose root hits a
@@ -349,6 +349,8 @@ int cb_tier1_gates(const cb_board* boards, int n, int koth, int mate_depth, int 
 /* forced_cap1_pesto_balance (src/search/quiescence.rs:1000-1012) of n boards on the calling host thread: q[i] in pawn units,
  * completed[i] / nodes[i] / depth[i] (nullable) the other members of the reference's tuple. */
 int cb_cap1_qsearch(const cb_board* boards, int n, float* q, uint8_t* completed, uint32_t* nodes, uint8_t* depth);
+/* The same on the handle's GPU, one warp per board (the tree kernels' warp form: must equal cb_cap1_qsearch). */
+int cb_cap1_qsearch_device(cb_handle* h, const cb_board* boards, int n, float* q, uint8_t* completed);
 /* Test hook: the tree kernels' move tests that do not make the move (legal / gives check, csrc/host/chess_rules.hpp) against
  * make-move + attack test on every pseudo-legal move of n boards; returns the number of disagreements. */
 long long cb_debug_move_flags(const cb_board* boards, int n, long long* n_moves);

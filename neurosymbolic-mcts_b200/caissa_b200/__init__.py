@@ -173,6 +173,7 @@ SIGNATURES = {
     "cb_tier1_gates": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP]),
     "cb_debug_move_flags": (ctypes.c_longlong, [_VP, ctypes.c_int, _VP]),
     "cb_cap1_qsearch": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP, _VP]),
+    "cb_cap1_qsearch_device": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP, _VP]),
     "cb_mate_search": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_koth_center_in_n": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP]),
     "cb_debug_device_legal_moves": (ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP, _VP]),
@@ -464,6 +465,14 @@ class Evaluator:
 
     def debug_set_layer_limit(self, n):
         self._check(self._L.cb_debug_set_layer_limit(self._h, n))
+
+    def cap1_qsearch_device(self, boards):
+        """The cap = 1 quiescence search on the GPU, one warp per board -> (q f32 pawn units, completed u8)."""
+        b = _boards_u8(boards)
+        q = np.empty(b.shape[0], dtype=np.float32)
+        c = np.empty(b.shape[0], dtype=np.uint8)
+        self._check(self._L.cb_cap1_qsearch_device(self._h, _ptr(b), b.shape[0], _ptr(q), _ptr(c)))
+        return q, c
 
     def debug_device_tier1_gates(self, boards, koth=False, mate_depth=5, exhaustive_depth=0, koth_depth=3, budget=0):
         """The tree kernels' gate at full depth (warp form) -> (int8 value per board: +1 / -1 / 2, uint8 terminal_distance)."""

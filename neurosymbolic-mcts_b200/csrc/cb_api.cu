@@ -946,6 +946,7 @@ int upload_leaves(cb_handle* h, const cb_board* boards, const float* q, int B, c
 struct DevSample {
     cb_board board;
     float material;
+    bool completed = true;   // qsearch_completed of the material search
     std::vector<std::pair<uint16_t, float>> policy;
 };
 
@@ -983,13 +984,14 @@ int drain_samples(cb_handle* h, const MctsParams& mp, unsigned long long& ring_r
         if (cnt == 0xFFFFu) {
             const int result = reinterpret_cast<const int32_t*>(r)[3];
             for (const DevSample& s : pending[game])
-                cbsp_write_sample(f, s.board, s.material, s.policy.data(), s.policy.size(), result, rec);
+                cbsp_write_sample(f, s.board, s.material, s.policy.data(), s.policy.size(), result, rec, s.completed);
             pending[game].clear();
             continue;
         }
         DevSample s;
         memcpy(&s.board, r + 16, sizeof(cb_board));
         s.material = reinterpret_cast<const float*>(r)[3];
+        s.completed = (reinterpret_cast<const uint16_t*>(r)[4] & 0x8000u) == 0;
         const uint32_t* pairs = reinterpret_cast<const uint32_t*>(r + 144);
         uint32_t total = 0;
         for (uint16_t k = 0; k < cnt; ++k) total += pairs[k] >> 16;
@@ -1464,6 +1466,42 @@ __global__ void __launch_bounds__(256) principal_exchange_kernel(const cb_board*
     if (lane == 0) q[i] = __fdiv_rn((float)cp, 100.0f);
 }
 
+// One warp per board: the cap = 1 quiescence search of mcts_device.cuh (cap1_cp_warp).
+__global__ void __launch_bounds__(128) cap1_qsearch_kernel(const cb_board* __restrict__ boards, int n, float* __restrict__ q,
+                                                           uint8_t* __restrict__ completed) {
+    __shared__ Cap1Scratch s_S[4];
+    __shared__ Move s_pseudo[4][CB_MAX_MOVES];
+    __shared__ uint8_t s_mailbox[4][64];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + wl;
+    if (i >= n) return;
+    if (lane < 16) reinterpret_cast<uint64_t*>(&s_S[wl].boards[0])[lane] = reinterpret_cast<const uint64_t*>(&boards[i])[lane];
+    __syncwarp();
+    bool c = true;
+    const int cp = cap1_cp_warp(s_S[wl], s_pseudo[wl], s_mailbox[wl], lane, &c);
+    if (lane == 0) { q[i] = __fdiv_rn((float)cp, 100.0f); completed[i] = c ? 1 : 0; }
+}
+
+int cb_cap1_qsearch_device(cb_handle* h, const cb_board* boards, int n, float* q, uint8_t* completed) {
+    if (!h || n < 0 || (n > 0 && (!boards || !q || !completed))) return CB_EINVAL;
+    if (n == 0) return CB_OK;
+    CB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->chess_tables_uploaded) {
+        CB_CUDA(h, cudaMemcpyToSymbol(cbchess::d_chess_tables, &cbchess::host_tables(), sizeof(cbchess::Tables)));
+        h->chess_tables_uploaded = true;
+    }
+    int rc = upload_leaves(h, boards, nullptr, n, nullptr, nullptr);
+    if (rc) return rc;
+    if ((rc = ensure_scratch(h, (size_t)n * 2))) return rc;
+    uint8_t* d_c = reinterpret_cast<uint8_t*>(h->d_scratch + n);
+    cap1_qsearch_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(h->d_boards, n, h->d_scratch, d_c);
+    CB_CUDA(h, cudaGetLastError());
+    CB_CUDA(h, cudaMemcpyAsync(q, h->d_scratch, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaMemcpyAsync(completed, d_c, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CB_OK;
+}
+
 int cb_principal_exchange_device(cb_handle* h, const cb_board* boards, int n, float* q) {
     if (!h || n < 0 || (n > 0 && (!boards || !q))) return CB_EINVAL;
     if (n == 0) return CB_OK;
@@ -1845,7 +1883,6 @@ struct DeviceSearchIO {
 static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_selfplay_stats* out, const DeviceSearchIO* dbg) {
     if (!h || !cfg || !out || cfg->games <= 0 || cfg->sims_per_move <= 0) return CB_EINVAL;
     if (!h->loaded) return fail(h, CB_ESTATE, "weights not loaded");
-    if (cfg->qsearch == 2) return fail(h, CB_EINVAL, "the cap1 q-search runs in the host-driven pools (pipeline 0-2); the device pipelines compute dM by the stand pat or the exchange line");
     CB_CUDA(h, cudaSetDevice(h->device));
     const int G = cfg->games;
     const int pools = (!dbg && cfg->pipeline == 4) ? 2 : 1;

@@ -132,7 +132,7 @@ struct MctsParams {
     unsigned long long* result_cursor;
 };
 
-// Sample record: u32 game | u32 serial | u16 ply | u16 n (0xFFFF = game end) | f32 material or i32 result |
+// Sample record: u32 game | u32 serial | u16 ply (bit 15: the material search did not complete) | u16 n (0xFFFF = game end) | f32 material or i32 result |
 // cb_board (128 B) | n x (u16 policy index, u16 visits)
 constexpr int kSampleSlotBytes = 1024;
 static_assert(16 + 128 + 4 * 218 <= kSampleSlotBytes, "sample slot");
@@ -659,6 +659,155 @@ __device__ __forceinline__ bool tier1_gates_run(GateJob& job, GateStack& st, con
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp form of cbchess::cap1_qsearch (host/qsearch.hpp; src/search/quiescence.rs:808-1012, `--qsearch cap1`): an
+// iterative alpha-beta over an explicit stack.  A frame is: stand pat -> the first legal capture of the MVV-LVA order (the
+// exchange line's keys, one own piece per lane) -> once per side and branch the first legal checking move of the
+// generation order that is not "that capture" (identified as the reference does, :933-944) -> done; a frame in check
+// walks its legal evasions.  Lane d keeps the scalars of ply d; the boards live in shared memory.
+struct Cap1Scratch {
+    cb_board boards[cbchess::kPeMaxDepth + 1];
+    uint16_t list[CB_MAX_MOVES];   // the evasions of the frame in hand / the capture-list entries tried so far
+};
+static_assert(sizeof(Cap1Scratch) <= sizeof(GateStack), "cap1 borrows the gate stack");
+
+// S.boards[0] holds the position.  Returns the score in centipawns; *completed as the reference's flag.  All lanes.
+__device__ __forceinline__ int cap1_cp_warp(Cap1Scratch& S, Move* pseudo, uint8_t* mailbox, int lane, bool* completed_out) {
+    using namespace cbchess;
+    enum { ENTER = 0, EVASIONS = 1, CAPTURE = 2, CHECK = 3, DONE = 4 };
+    int f_alpha = 0, f_beta = 0, f_state = 0, f_idx = 0, f_maxd = 0, f_skip = 0;   // this lane's frame
+    if (lane == 0) { f_alpha = -kPeWindow; f_beta = kPeWindow; f_state = ENTER; }
+    int d = 0;
+    for (;;) {
+        int alpha = __shfl_sync(0xffffffffu, f_alpha, d);
+        const int beta = __shfl_sync(0xffffffffu, f_beta, d);
+        const int st = __shfl_sync(0xffffffffu, f_state, d);
+        int idx = __shfl_sync(0xffffffffu, f_idx, d), maxd = __shfl_sync(0xffffffffu, f_maxd, d), skip = __shfl_sync(0xffffffffu, f_skip, d);
+        int stage = st & 7;
+        const bool wu = (st & 8) != 0, bu = (st & 16) != 0;
+        bool comp = (st & 32) != 0;
+        const cb_board& b = S.boards[d];
+        const int us = b.w_to_move ? 0 : 1;
+        bool ret = false, push = false, ret_c = true;
+        int ret_v = 0, ret_d = 0;
+        bool cwu = wu, cbu = bu;   // the child's check budgets
+        __syncwarp();
+        if (stage == ENTER) {
+            const bool inchk = in_check_warp(b, us, lane);
+            comp = true;
+            maxd = 0;
+            idx = 0;
+            skip = -1;
+            if (!inchk) {
+                const int sp = pesto_cp_warp(b, mailbox, lane);   // also fills the mailbox for the capture scan
+                if (sp >= beta) { ret = true; ret_v = beta; }
+                else if (sp > alpha) alpha = sp;
+            }
+            if (!ret && d == kPeMaxDepth) { ret = true; ret_v = alpha; ret_c = !inchk; }
+            stage = inchk ? EVASIONS : CAPTURE;
+        }
+        if (!ret && stage == EVASIONS) {
+            const int n = mcts_gen_legal_warp(b, pseudo, S.list, lane);
+            if (n == 0) { ret = true; ret_v = -1000000; }
+            else if (idx >= n) { ret = true; ret_v = alpha; ret_c = comp; ret_d = maxd; }
+            else {
+                if (lane == 0) make_move_hd(b, (Move)S.list[idx], &S.boards[d + 1]);
+                ++idx;
+                push = true;
+            }
+        } else if (!ret && stage == CAPTURE) {
+            stage = CHECK;
+            const uint64_t own = b.occ[us];
+            const bool has_piece = lane < __popcll(own);
+            int from = 0, pt = 0;
+            if (has_piece) {
+                from = nth_set_bit(own, lane);
+                pt = (int)mailbox[from] - 1 - 6 * us;
+            }
+            Move m = 0;
+            uint32_t key = has_piece ? pe_piece_best_mb(b, mailbox, from, pt, 0, &m) : kPeNoCapture;
+            int n_tried = 0;
+            Move played = 0;
+            for (;;) {
+                const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+                if (kmin == kPeNoCapture) break;
+                if (lane < 16) reinterpret_cast<uint64_t*>(&S.boards[d + 1])[lane] = reinterpret_cast<const uint64_t*>(&b)[lane];
+                __syncwarp();
+                const bool winner = key == kmin;
+                if (winner) {
+                    pe_apply_capture(S.boards[d + 1], m, pt, mailbox[mv_to(m)] ? (int)mailbox[mv_to(m)] - 1 - 6 * (1 - us) : -1);
+                    S.list[n_tried] = m;
+                }
+                ++n_tried;
+                __syncwarp();
+                if (!in_check_warp(S.boards[d + 1], us, lane)) { played = (Move)S.list[n_tried - 1]; break; }
+                if (winner) key = pe_piece_best_mb(b, mailbox, from, pt, kmin, &m);
+            }
+            if (played) {
+                const int best_to = mv_to(played);
+                int sf = 64;                       // from-square of the first list entry with that target
+                for (int i = n_tried - 1; i >= 0; --i)
+                    if (mv_to((Move)S.list[i]) == best_to) sf = mv_from((Move)S.list[i]);
+                skip = sf | (best_to << 8);
+                push = true;
+            }
+        }
+        if (!ret && !push && stage == CHECK) {
+            stage = DONE;
+            if (!(us == 0 ? wu : bu)) {
+                const MoveCtx c = move_ctx(b);
+                const int np = gen_pseudo_warp(b, pseudo, lane);
+                for (int base = 0; base < np && !push; base += 32) {
+                    const int i = base + lane;
+                    bool keep = false;
+                    if (i < np) {
+                        const Move m = pseudo[i];
+                        const bool same = skip >= 0 && mv_from(m) == (skip & 0xFF) && mv_to(m) == (skip >> 8);
+                        keep = !same && move_flags_hd(b, c, m, true) == 3;
+                    }
+                    const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+                    if (mask) {
+                        if (lane == 0) make_move_hd(b, pseudo[base + __ffs(mask) - 1], &S.boards[d + 1]);
+                        push = true;
+                        if (us == 0) cwu = true; else cbu = true;
+                    }
+                }
+            }
+        }
+        if (!ret && !push) { ret = true; ret_v = alpha; ret_c = comp; ret_d = maxd; }   // DONE
+        if (push) {
+            if (lane == d) {
+                f_alpha = alpha; f_state = stage | (wu ? 8 : 0) | (bu ? 16 : 0) | (comp ? 32 : 0);
+                f_idx = idx; f_maxd = maxd; f_skip = skip;
+            }
+            if (lane == d + 1) { f_alpha = -beta; f_beta = -alpha; f_state = ENTER | (cwu ? 8 : 0) | (cbu ? 16 : 0); }
+            __syncwarp();
+            ++d;
+            continue;
+        }
+        // hand the result up: a cut-off returns the parent's beta and cascades
+        for (;;) {
+            if (d == 0) {
+                *completed_out = ret_c;
+                return ret_v;
+            }
+            --d;
+            int pa = __shfl_sync(0xffffffffu, f_alpha, d);
+            const int pb = __shfl_sync(0xffffffffu, f_beta, d);
+            const int pst = __shfl_sync(0xffffffffu, f_state, d);
+            int pmax = __shfl_sync(0xffffffffu, f_maxd, d);
+            bool pcomp = (pst & 32) != 0;
+            if (ret_d + 1 > pmax) pmax = ret_d + 1;
+            if (!ret_c) pcomp = false;
+            const int sc = -ret_v;
+            if (sc >= pb) { ret_v = pb; ret_c = pcomp; ret_d = pmax; continue; }
+            if (sc > pa) pa = sc;
+            if (lane == d) { f_alpha = pa; f_maxd = pmax; f_state = (pst & ~32) | (pcomp ? 32 : 0); }
+            break;
+        }
+    }
+}
+
 // Phase A of a simulation for every game: walk down (tactical phase, root force-visit, PUCT), stop at an unexpanded or
 // decided node.
 // Per-warp shared scratch of the tree kernels.
@@ -703,6 +852,23 @@ __device__ __forceinline__ void mcts_game_over(const MctsParams& p, int g, int r
     }
     const uint64_t seed = rng_next(rs) ^ ((uint64_t)g << 32);
     mcts_reset_game(p, g, seed);
+}
+
+// dM of the position in `b` = sm.board[wl] (overwritten when a search runs) by the configured search; *completed (nullable)
+// = the search's completion flag (always true for the stand pat and the exchange line).  cap1 borrows the warp's gate stack,
+// which is idle whenever a material term is computed (the leaf's gate job has finished; a suspended job rests in global
+// memory).
+__device__ __forceinline__ float mcts_material_q_sm(const MctsParams& p, MctsSmem& sm, int wl, int lane, bool always, bool* completed) {
+    if (completed) *completed = true;
+    if (p.qsearch != 2 || (!p.material_on && !always)) return mcts_material_q(p, sm.board[wl], sm.next[wl], sm.mailbox[wl], lane, always);
+    Cap1Scratch& S = *reinterpret_cast<Cap1Scratch*>(&sm.gate[wl]);
+    __syncwarp();
+    if (lane < 16) reinterpret_cast<uint64_t*>(&S.boards[0])[lane] = reinterpret_cast<const uint64_t*>(&sm.board[wl])[lane];
+    __syncwarp();
+    bool c = true;
+    const int cp = cap1_cp_warp(S, sm.pseudo[wl], sm.mailbox[wl], lane, &c);
+    if (completed) *completed = c;
+    return __fdiv_rn((float)cp, 100.0f);
 }
 
 // The part of a child node the walk needs, packed for one round of shuffles.
@@ -989,7 +1155,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     if (lane < 16) reinterpret_cast<uint64_t*>(&p.eval_boards[g])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
     __syncwarp();
     // a root asks for its policy only, with dM = 0 (selection.rs:315-332)
-    const float leaf_q = cur == 0 ? 0.0f : mcts_material_q(p, board, sm.next[wl], sm.mailbox[wl], lane);   // `board` is dead after this
+    const float leaf_q = cur == 0 ? 0.0f : mcts_material_q_sm(p, sm, wl, lane, false, nullptr);   // `board` is dead after this
     if (lane == 0) {
         p.eval_q[g] = leaf_q;
         p.eval_cnt[g] = (uint16_t)n_moves;
@@ -1173,11 +1339,12 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
             reinterpret_cast<uint64_t*>(&sm.board[wl])[lane] = w;
         }
         __syncwarp();
-        const float root_q = mcts_material_q(p, sm.board[wl], sm.next[wl], sm.mailbox[wl], lane, true);
+        bool q_completed = true;
+        const float root_q = mcts_material_q_sm(p, sm, wl, lane, true, &q_completed);
         if (lane == 0) {
             reinterpret_cast<uint32_t*>(rec)[0] = (uint32_t)g;
             reinterpret_cast<uint32_t*>(rec)[1] = p.game_serial[g];
-            reinterpret_cast<uint16_t*>(rec)[4] = (uint16_t)p.ply[g];
+            reinterpret_cast<uint16_t*>(rec)[4] = (uint16_t)(p.ply[g] | (q_completed ? 0 : 0x8000));   // bit 15: qsearch_completed = false
             reinterpret_cast<uint16_t*>(rec)[5] = (uint16_t)n;
             reinterpret_cast<float*>(rec)[3] = root_q;
         }

@@ -484,7 +484,7 @@ def test_device_search_equals_the_oracle_with_the_mock_evaluator(cb, golden, moc
         assert root_visits[i] == t.root_stats()["visits"]
 
 
-@pytest.mark.parametrize("material,dtype", [(False, "bf16"), ("pe", "bf16"), (False, "fp32")])
+@pytest.mark.parametrize("material,dtype", [(False, "bf16"), ("pe", "bf16"), (False, "fp32"), ("cap1", "bf16")])
 def test_device_search_equals_the_oracle_with_the_network(cb, golden, material, dtype):
     """The same comparison with the golden 6x128 network as evaluator: the oracle's callback evaluates each leaf through
     cb_eval_leaves (one board per call; the forward is bit-identical whatever the batch), so both searches see the same
@@ -492,7 +492,7 @@ def test_device_search_equals_the_oracle_with_the_network(cb, golden, material, 
     g, blob = golden("6x128_B")
     ev = make_eval(cb, g, blob, dtype)     # fp32: the fp16-pair instantiation of the forward under the tree kernels
     boards = search_corpus(56)[:64]
-    mode = dict(material_on=bool(material), qsearch="pe" if material else 0)
+    mode = dict(material_on=bool(material), qsearch=material if material else 0)
     kids, root_visits = ev.debug_device_search(boards, sims_per_move=200, seed=3, **mode)
 
     def net(b, moves, q, material_on):
@@ -713,6 +713,31 @@ def test_model_match_on_device(cb, golden):
         assert cb.sprt_decision(s["candidate_wins"], s["current_wins"], s["draws"], 0.0, 400.0, 0.3, 0.3) == \
             {1: "H1", -1: "H0"}[s["decision"]]
     del cand2
+
+
+def test_device_cap1_qsearch_equals_the_host_form(cb, golden, tmp_path):
+    """cap1_cp_warp (iterative alpha-beta over an explicit stack, lane d keeping ply d) against cb_cap1_qsearch (recursive
+    host form, itself equal to the oracle in tests/test_host.py): score and completion flag on 5000 positions; then the
+    device self-play with dM by cap1 against the host driver (same counters, same sample files incl. the completion flag)."""
+    g, blob = golden("6x128_B")
+    ev = make_eval(cb, g, blob, "bf16")
+    a, _, _, _ = O.random_positions(4711, 5000, 220)
+    fens = ["r3k3/8/8/1N6/8/8/8/4K3 w - - 0 1", "6k1/5ppp/8/8/8/8/8/3RK3 w - - 0 1", "k7/8/8/8/8/8/1B6/R3K3 w - - 0 1",
+            "7k/1p1b1Qp1/1r6/p4pq1/1b1Np2p/4P3/K1rNR1PP/3R4 w - - 0 36", "8/8/8/KPp4r/8/8/8/7k w - c6 0 2", "4k3/P7/8/8/8/8/8/4K3 w - - 0 1"]
+    boards = np.concatenate([a, O.boards_to_array([O.from_fen(f) for f in fens])])
+    want_q, want_c, nodes, _ = cb.cap1_qsearch(boards)
+    got_q, got_c = ev.cap1_qsearch_device(boards)
+    assert np.array_equal(got_q, want_q) and np.array_equal(got_c, want_c)
+    assert (want_c == 0).sum() >= 1 and nodes.max() > 300 and (want_q != cb.principal_exchange(boards)).sum() > 1000
+    kw = dict(games=24, sims_per_move=20, max_plies=40, material_on=True, qsearch="cap1", seed=11, max_sims=24 * 20 * 50)
+    host = ev.selfplay(threads=1, pipeline=1, sample_path=str(tmp_path / "host.bin"), **kw)
+    dev = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "dev.bin"), **kw)
+    for k in ("sims", "steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins", "black_wins", "draws"):
+        assert host[k] == dev[k], (k, host[k], dev[k])
+    rh = np.fromfile(tmp_path / "host.bin", dtype=np.float32).reshape(-1, 5763)
+    rd = np.fromfile(tmp_path / "dev.bin", dtype=np.float32).reshape(-1, 5763)
+    key = lambda r: r[np.lexsort(r.T[::-1])]
+    assert rh.shape == rd.shape and rh.shape[0] > 0 and np.array_equal(key(rh), key(rd))
 
 
 def test_model_match_with_the_deep_gates(cb, golden, monkeypatch):

@@ -29,6 +29,15 @@ def run(label, budget=None, **kw):
     print(json.dumps(row), flush=True)
 
 
+if len(sys.argv) > 2 and sys.argv[2] == "cap1":
+    run("light gates + dM by the exchange line, one pool, 1024 games", pipeline=3, games=1024, tier1_light=True, material_on=True, qsearch="pe")
+    run("light gates + dM by cap1, one pool, 1024 games", pipeline=3, games=1024, tier1_light=True, material_on=True, qsearch="cap1")
+    run("light gates + dM by cap1, one pool, 4096 games", pipeline=3, games=4096, tier1_light=True, material_on=True, qsearch="cap1")
+    run("light gates + dM by cap1, two pools, 2048 games", pipeline=4, games=2048, tier1_light=True, material_on=True, qsearch="cap1")
+    run("deep gates + dM by cap1, one pool, 4096 games", budget=24, pipeline=3, games=4096, tier1_light="deep", material_on=True, qsearch="cap1")
+    with open(os.path.join(REPO, "gpurun_out", "cap1_probe.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == "long":
     # steady-state figures: runs long enough to leave the openings (a game is ~90 moves x 200 simulations)
     for G, b in ((1024, 12), (1024, 24), (4096, 12), (4096, 24), (8192, 24)):
@@ -36,6 +45,10 @@ if len(sys.argv) > 2 and sys.argv[2] == "long":
     run("deep gates + dM by the exchange line, one pool, 4096 games", budget=24, pipeline=3, games=4096, tier1_light="deep", material_on=True, qsearch="pe")
     run("KOTH, deep gates (hill in 3 + mate-in-5), 4096 games", budget=24, pipeline=3, games=4096, tier1_light="deep", koth=True)
     run("light gates, one pool, 1024 games", pipeline=3, games=1024, tier1_light=True)
+    run("light gates + dM by the exchange line, one pool, 1024 games", pipeline=3, games=1024, tier1_light=True, material_on=True, qsearch="pe")
+    run("light gates + dM by cap1, one pool, 1024 games", pipeline=3, games=1024, tier1_light=True, material_on=True, qsearch="cap1")
+    run("light gates + dM by cap1, one pool, 4096 games", pipeline=3, games=4096, tier1_light=True, material_on=True, qsearch="cap1")
+    run("deep gates + dM by cap1, one pool, 4096 games", budget=24, pipeline=3, games=4096, tier1_light="deep", material_on=True, qsearch="cap1")
     with open(os.path.join(REPO, "gpurun_out", "deep_gates_probe_long.json"), "w") as f:
         json.dump(rows, f, indent=1)
     sys.exit(0)
