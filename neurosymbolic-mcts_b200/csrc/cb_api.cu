@@ -1851,7 +1851,7 @@ static int mcts_alloc(cb_handle* h, MctsParams& mp, int G, std::vector<void*>& o
         (rc = dalloc((void**)&mp.eval_cnt, (size_t)G * 2)) || (rc = dalloc((void**)&mp.stats, MS_COUNT * 8)))
         return rc;
     CB_CUDA(h, cudaMemsetAsync(mp.idle, 0, (size_t)G, h->stream));
-    if (mp.tier1_light >= 2) {   // the stacks of the games' gate jobs (tier1_gates_run)
+    if (mp.tier1_light >= 2 || (mp.qsearch == 2 && mp.material_on)) {   // the stacks of the games' gate / cap1 jobs
         if ((rc = dalloc((void**)&mp.gate_jobs, (size_t)G * sizeof(GateJob)))) return rc;
         CB_CUDA(h, cudaMemsetAsync(mp.gate_jobs, 0, (size_t)G * sizeof(GateJob), h->stream));
     }
@@ -1904,7 +1904,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     mp.material_on = cfg->material_on;
     mp.qsearch = cfg->qsearch;
     mp.tier1_light = cfg->tier1_light;
-    if (cfg->tier1_light >= 2) {
+    if (cfg->tier1_light >= 2 || cfg->qsearch == 2) {   // (cap1 searches run under the same per-step budget)
         if ((rc = mcts_gate_params(h, mp, cfg->tier1_mate_depth, cfg->tier1_exhaustive_depth, cfg->tier1_koth_depth))) return rc;
     }
     mp.koth = cfg->koth;
@@ -2055,7 +2055,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
         for (int i = 0; i <= cfg->sims_per_move && !rc; ++i) rc = fused();
         cudaError_t e2 = cudaStreamSynchronize(h->stream);
         long long dbg_steps = cfg->sims_per_move + 1;
-        if (mp.tier1_light >= 2) {   // games whose gate jobs were suspended need more steps: run until every game is idle
+        if (mp.gate_jobs) {   // games whose gate / cap1 jobs were suspended need more steps: run until every game is idle
             std::vector<uint8_t> idle(G);
             // (a search whose leaves need ~2000 gate positions each, e.g. a king near the hill, takes sims x 2000 / budget steps)
             for (int round = 0; round < (1 << 16) && !rc && e2 == cudaSuccess; ++round) {
@@ -2207,7 +2207,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(h, CB_ECUDA, std::string("device self-play: ") + cudaGetErrorString(ce));
     // (with the deep gates a game whose gate job is suspended completes no simulation in that step: count them)
-    out->sims = mp.tier1_light >= 2 ? (long long)st[MS_SIMS] : steps * G;
+    out->sims = mp.gate_jobs ? (long long)st[MS_SIMS] : steps * G;
     out->nn_evals = (long long)st[MS_EVALS];
     out->terminal_hits = (long long)st[MS_TERMINAL];
     out->moves = (long long)st[MS_MOVES];
@@ -2298,7 +2298,7 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     mp.material_on = cfg->material_on;
     mp.qsearch = cfg->qsearch;
     mp.tier1_light = cfg->tier1_light;
-    if (cfg->tier1_light >= 2 && (rc = mcts_gate_params(h, mp, 0, 0, 0))) return rc;   // 5 / 0 / 3: src/bin/evaluate_models.rs:251,270
+    if ((cfg->tier1_light >= 2 || cfg->qsearch == 2) && (rc = mcts_gate_params(h, mp, 0, 0, 0))) return rc;   // 5 / 0 / 3: src/bin/evaluate_models.rs:251,270
     mp.koth = cfg->koth;
     mp.c_puct = cfg->c_puct > 0 ? cfg->c_puct : 1.414;
     mp.explore_base = cfg->explore_base > 0 ? cfg->explore_base : 0.90;   // DEFAULT_EXPLORE_BASE, src/bin/evaluate_models.rs:85
@@ -2398,7 +2398,7 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     cudaStreamSynchronize(h->stream);
     const double secs = elapsed();
     unsigned long long sims_counted = 0;   // (with the gates at full depth a suspended game completes no simulation in a step)
-    if (mp.tier1_light >= 2) cudaMemcpy(&sims_counted, mp.stats + MS_SIMS, 8, cudaMemcpyDeviceToHost);
+    if (mp.gate_jobs) cudaMemcpy(&sims_counted, mp.stats + MS_SIMS, 8, cudaMemcpyDeviceToHost);
     if (gexec) cudaGraphExecDestroy(gexec);
     release();
     if (rc) return rc;
@@ -2410,7 +2410,7 @@ int cb_match_run(cb_handle* cand, cb_handle* curr, const cb_match_config* cfg, c
     out->decision = decision;
     if (decision != 0 && have_llr) { out->llr = llr_at_decision; out->llr_valid = 1; }
     else out->llr_valid = cb_sprt_llr(wins, losses, draws, cfg->elo0, cfg->elo1, &out->llr) == 1;
-    out->sims = mp.tier1_light >= 2 ? (long long)sims_counted : steps * G;
+    out->sims = mp.gate_jobs ? (long long)sims_counted : steps * G;
     out->seconds = secs;
     return CB_OK;
 }

@@ -57,7 +57,7 @@ constexpr int kMctsMaxDepth = 512;  // longest root-to-leaf path kept
 constexpr int kMctsWarps = 4;       // games per CTA
 
 constexpr int kGatePlies = 10;   // mate-in-5: plies 0..8 move, ply 9 is the mated position; the hill in 3 enters ply 6
-constexpr size_t kGateJobBytes = (kGatePlies + 1) * sizeof(cb_board) + (size_t)kGatePlies * CB_MAX_MOVES * 2 + 64 + 16;
+constexpr size_t kGateJobBytes = (kGatePlies + 1) * sizeof(cb_board) + (size_t)kGatePlies * CB_MAX_MOVES * 2 + 6 * 24 * 4 + 64 + 16;
 constexpr size_t kGateJobActiveOffset = kGateJobBytes - 16;
 
 enum { MS_EVALS = 0, MS_TERMINAL, MS_MOVES, MS_GAMES, MS_SAMPLES, MS_WWINS, MS_BWINS, MS_DRAWS, MS_OVERFLOW, MS_SIMS, MS_GATE_HITS, MS_GATE_WAITS,
@@ -487,13 +487,16 @@ struct GateStack {                 // the search stack of one job: in shared mem
     uint16_t list[kGatePlies][CB_MAX_MOVES];
 };
 struct GateJob {                   // a game's job in global memory: where the stack rests between steps
-    GateStack st;
-    uint16_t idx[16], cnt[16];     // cursor and length of every ply's move list
-    uint8_t active;                // 0 none, 1 leaf gate, 2 adjudication of a new root
+    GateStack st;                  // (a cap1 job keeps its Cap1Scratch boards here)
+    int32_t frames[6][24];         // cap1 job: the frames of plies 0..20 (alpha, beta, state, cursor, depth, skip)
+    uint16_t idx[16], cnt[16];     // gate job: cursor and length of every ply's move list
+    uint8_t active;                // 0 none, 1 leaf gate, 2 adjudication of a new root, 3 the leaf's cap1 search (dM)
     uint8_t phase;                 // 0 hill, 1 mate
-    uint8_t it;                    // iteration: the hill's n / the mate's d
+    uint8_t it;                    // iteration: the hill's n / the mate's d (0: a filed job that has not started)
     uint8_t ply;
-    uint8_t pad[12];
+    uint16_t n_moves;              // cap1 job: the leaf's legal moves / how many come from the capture list (the rest of the
+    uint8_t n_tact;                // selection is done; the evaluation request waits for dM)
+    uint8_t pad[9];
 };
 static_assert(sizeof(GateJob) == kGateJobBytes && offsetof(GateJob, active) == kGateJobActiveOffset, "gate job layout");
 static_assert(sizeof(GateStack) % 16 == 0 && sizeof(cb_board) % 16 == 0, "stack copied as uint4");
@@ -671,17 +674,40 @@ struct Cap1Scratch {
 };
 static_assert(sizeof(Cap1Scratch) <= sizeof(GateStack), "cap1 borrows the gate stack");
 
-// S.boards[0] holds the position.  Returns the score in centipawns; *completed as the reference's flag.  All lanes.
-__device__ __forceinline__ int cap1_cp_warp(Cap1Scratch& S, Move* pseudo, uint8_t* mailbox, int lane, bool* completed_out) {
+// S.boards[0] holds the position (resume: the stack is fetched from the job).  true: finished, *cp_out = the score in
+// centipawns, *completed_out = the reference's flag.  false (only with a job): the search has entered `budget` positions in
+// this call and rests in the job.  All lanes.
+__device__ __forceinline__ bool cap1_run(Cap1Scratch& S, GateJob* job, int budget, bool resume, Move* pseudo, uint8_t* mailbox, int lane,
+                                         int* cp_out, bool* completed_out) {
     using namespace cbchess;
     enum { ENTER = 0, EVASIONS = 1, CAPTURE = 2, CHECK = 3, DONE = 4 };
     int f_alpha = 0, f_beta = 0, f_state = 0, f_idx = 0, f_maxd = 0, f_skip = 0;   // this lane's frame
-    if (lane == 0) { f_alpha = -kPeWindow; f_beta = kPeWindow; f_state = ENTER; }
     int d = 0;
+    if (resume) {
+        d = job->ply;
+        if (lane <= kPeMaxDepth) {
+            f_alpha = job->frames[0][lane]; f_beta = job->frames[1][lane]; f_state = job->frames[2][lane];
+            f_idx = job->frames[3][lane]; f_maxd = job->frames[4][lane]; f_skip = job->frames[5][lane];
+        }
+        const int nb4 = (d + 1) * (int)(sizeof(cb_board) / 16);
+        for (int i = lane; i < nb4; i += 32) reinterpret_cast<uint4*>(S.boards)[i] = reinterpret_cast<const uint4*>(&job->st)[i];
+        __syncwarp();
+    } else if (lane == 0) { f_alpha = -kPeWindow; f_beta = kPeWindow; f_state = ENTER; }
     for (;;) {
         int alpha = __shfl_sync(0xffffffffu, f_alpha, d);
         const int beta = __shfl_sync(0xffffffffu, f_beta, d);
         const int st = __shfl_sync(0xffffffffu, f_state, d);
+        if (job && (st & 7) == ENTER && budget-- <= 0) {   // suspended in front of a position
+            if (lane == 0) job->ply = (uint8_t)d;
+            if (lane <= kPeMaxDepth) {
+                job->frames[0][lane] = f_alpha; job->frames[1][lane] = f_beta; job->frames[2][lane] = f_state;
+                job->frames[3][lane] = f_idx; job->frames[4][lane] = f_maxd; job->frames[5][lane] = f_skip;
+            }
+            const int nb4 = (d + 1) * (int)(sizeof(cb_board) / 16);
+            for (int i = lane; i < nb4; i += 32) reinterpret_cast<uint4*>(&job->st)[i] = reinterpret_cast<const uint4*>(S.boards)[i];
+            __syncwarp();
+            return false;
+        }
         int idx = __shfl_sync(0xffffffffu, f_idx, d), maxd = __shfl_sync(0xffffffffu, f_maxd, d), skip = __shfl_sync(0xffffffffu, f_skip, d);
         int stage = st & 7;
         const bool wu = (st & 8) != 0, bu = (st & 16) != 0;
@@ -789,7 +815,8 @@ __device__ __forceinline__ int cap1_cp_warp(Cap1Scratch& S, Move* pseudo, uint8_
         for (;;) {
             if (d == 0) {
                 *completed_out = ret_c;
-                return ret_v;
+                *cp_out = ret_v;
+                return true;
             }
             --d;
             int pa = __shfl_sync(0xffffffffu, f_alpha, d);
@@ -854,6 +881,13 @@ __device__ __forceinline__ void mcts_game_over(const MctsParams& p, int g, int r
     mcts_reset_game(p, g, seed);
 }
 
+// The search run to completion in one call.
+__device__ __forceinline__ int cap1_cp_warp(Cap1Scratch& S, Move* pseudo, uint8_t* mailbox, int lane, bool* completed_out) {
+    int cp = 0;
+    cap1_run(S, nullptr, 0, false, pseudo, mailbox, lane, &cp, completed_out);
+    return cp;
+}
+
 // dM of the position in `b` = sm.board[wl] (overwritten when a search runs) by the configured search; *completed (nullable)
 // = the search's completion flag (always true for the stand pat and the exchange line).  cap1 borrows the warp's gate stack,
 // which is idle whenever a material term is computed (the leaf's gate job has finished; a suspended job rests in global
@@ -899,13 +933,32 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     }
     // tier1_light = 2: a gate job of this game may be waiting (tier1_gates_run)
     const bool deep = p.tier1_light >= 2;
-    GateJob* job = deep ? &p.gate_jobs[g] : nullptr;
-    int pending = deep ? job->active : 0;
+    GateJob* job = p.gate_jobs ? &p.gate_jobs[g] : nullptr;   // (allocated with tier1_light = 2 and with dM by cap1)
+    int pending = job ? job->active : 0;
     if (MODE == 1 && pending) {   // the gate kernel carries the job on
         if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; }
         return;
     }
     if (MODE == 2 && !pending) return;
+    if (pending == 3) {
+        // the selection is complete but for dM: the leaf's cap1 search was suspended (cap1_run); its result releases the request
+        Cap1Scratch& S = *reinterpret_cast<Cap1Scratch*>(&sm.gate[wl]);
+        int cp = 0;
+        bool qc = true;
+        if (!cap1_run(S, job, p.gate_budget, true, s_pseudo[wl], sm.mailbox[wl], lane, &cp, &qc)) {
+            if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; atomicAdd(&p.stats[MS_GATE_WAITS], 1ull); }
+            return;
+        }
+        if (lane == 0) {
+            job->active = 0;
+            p.eval_q[g] = __fdiv_rn((float)cp, 100.0f);
+            p.eval_cnt[g] = job->n_moves;
+            p.leaf_ntact[g] = job->n_tact;
+            p.wants_eval[g] = 1;
+            atomicAdd(&p.stats[MS_EVALS], 1ull);
+        }
+        return;
+    }
     if (pending == 2) {
         // the game loop's pre-check of the new root (src/bin/self_play.rs:241-283): a hill in 3 or mate_search(board, 5,
         // exhaustive 2) ends the game as a win of the side to move.  In a match the mover's search answers a root that its own
@@ -1155,7 +1208,33 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
     if (lane < 16) reinterpret_cast<uint64_t*>(&p.eval_boards[g])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
     __syncwarp();
     // a root asks for its policy only, with dM = 0 (selection.rs:315-332)
-    const float leaf_q = cur == 0 ? 0.0f : mcts_material_q_sm(p, sm, wl, lane, false, nullptr);   // `board` is dead after this
+    float leaf_q = 0.0f;
+    if (cur != 0) {
+        if (p.qsearch == 2 && p.material_on && job) {
+            // dM by cap1: a search of up to ~1000 positions, run under the per-step budget of the gate jobs
+            Cap1Scratch& S = *reinterpret_cast<Cap1Scratch*>(&sm.gate[wl]);
+            __syncwarp();
+            if (lane < 16) reinterpret_cast<uint64_t*>(&S.boards[0])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
+            __syncwarp();
+            int cp = 0;
+            bool qc = true;
+            if (!cap1_run(S, job, p.gate_budget, false, s_pseudo[wl], sm.mailbox[wl], lane, &cp, &qc)) {
+                if (lane == 0) {
+                    job->active = 3;
+                    job->n_moves = (uint16_t)n_moves;
+                    job->n_tact = (uint8_t)n_tact;
+                    p.path_n[g] = path_n;
+                    p.wants_eval[g] = 0;
+                    p.eval_cnt[g] = 0;
+                    atomicAdd(&p.stats[MS_GATE_WAITS], 1ull);
+                }
+                return;
+            }
+            leaf_q = __fdiv_rn((float)cp, 100.0f);
+        } else {
+            leaf_q = mcts_material_q_sm(p, sm, wl, lane, false, nullptr);   // `board` is dead after this
+        }
+    }
     if (lane == 0) {
         p.eval_q[g] = leaf_q;
         p.eval_cnt[g] = (uint16_t)n_moves;

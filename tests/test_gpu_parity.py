@@ -715,10 +715,13 @@ def test_model_match_on_device(cb, golden):
     del cand2
 
 
-def test_device_cap1_qsearch_equals_the_host_form(cb, golden, tmp_path):
-    """cap1_cp_warp (iterative alpha-beta over an explicit stack, lane d keeping ply d) against cb_cap1_qsearch (recursive
+def test_device_cap1_qsearch_equals_the_host_form(cb, golden, tmp_path, monkeypatch):
+    """cap1_run (iterative alpha-beta over an explicit stack, lane d keeping ply d) against cb_cap1_qsearch (recursive
     host form, itself equal to the oracle in tests/test_host.py): score and completion flag on 5000 positions; then the
-    device self-play with dM by cap1 against the host driver (same counters, same sample files incl. the completion flag)."""
+    device self-play with dM by cap1 against the host driver (same counters, same sample files incl. the completion flag)
+    with a per-step budget no search exceeds, and with a budget of 5 positions (searches suspended and resumed: the finished
+    games are the host's games)."""
+    monkeypatch.setenv("CB_GATE_BUDGET", "100000000")
     g, blob = golden("6x128_B")
     ev = make_eval(cb, g, blob, "bf16")
     a, _, _, _ = O.random_positions(4711, 5000, 220)
@@ -732,12 +735,25 @@ def test_device_cap1_qsearch_equals_the_host_form(cb, golden, tmp_path):
     kw = dict(games=24, sims_per_move=20, max_plies=40, material_on=True, qsearch="cap1", seed=11, max_sims=24 * 20 * 50)
     host = ev.selfplay(threads=1, pipeline=1, sample_path=str(tmp_path / "host.bin"), **kw)
     dev = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "dev.bin"), **kw)
-    for k in ("sims", "steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins", "black_wins", "draws"):
+    # ("sims": with jobs the device counts completed simulations, the host driver steps x games)
+    for k in ("steps", "nn_evals", "terminal_hits", "moves", "games_finished", "samples", "white_wins", "black_wins", "draws"):
         assert host[k] == dev[k], (k, host[k], dev[k])
+    assert dev["sims"] == dev["nn_evals"] + dev["terminal_hits"] - dev["moves"] - 24 or dev["sims"] <= host["sims"]
     rh = np.fromfile(tmp_path / "host.bin", dtype=np.float32).reshape(-1, 5763)
     rd = np.fromfile(tmp_path / "dev.bin", dtype=np.float32).reshape(-1, 5763)
     key = lambda r: r[np.lexsort(r.T[::-1])]
     assert rh.shape == rd.shape and rh.shape[0] > 0 and np.array_equal(key(rh), key(rd))
+    monkeypatch.setenv("CB_GATE_BUDGET", "5")
+    slow = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "slow.bin"), **kw)
+    rs = np.fromfile(tmp_path / "slow.bin", dtype=np.float32).reshape(-1, 5763)
+    have = {r.tobytes() for r in rh}
+    assert slow["gate_waits"] > 0 and rs.shape[0] > 0 and all(r.tobytes() in have for r in rs)
+    # and under the gate at full depth (jobs in the gate kernel: the leaf's gate, then its cap1 search)
+    deep = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "deep.bin"), tier1_light="deep", **kw)
+    hdeep = ev.selfplay(threads=1, pipeline=1, sample_path=str(tmp_path / "hdeep.bin"), tier1_light="deep", **kw)
+    rdp = np.fromfile(tmp_path / "deep.bin", dtype=np.float32).reshape(-1, 5763)
+    have = {r.tobytes() for r in np.fromfile(tmp_path / "hdeep.bin", dtype=np.float32).reshape(-1, 5763)}
+    assert deep["gate_waits"] > 0 and hdeep["games_finished"] > 0 and rdp.shape[0] > 0 and all(r.tobytes() in have for r in rdp)
 
 
 def test_model_match_with_the_deep_gates(cb, golden, monkeypatch):
