@@ -1394,7 +1394,7 @@ __global__ void __launch_bounds__(128) device_tier1_gates_kernel(const cb_board*
         // resumed in slices of `budget` positions, like the tree kernels do across steps (the shared stack is wiped in
         // between, as another game's job would do)
         bool fresh = true;
-        while (!tier1_gates_run(job, s_st[wl], gc, budget, fresh, s_pseudo[wl], lane, &v, &d)) {
+        while (!tier1_gates_run(job, s_st[wl], gc, GateBudget{budget, 0, nullptr, 0u}, fresh, s_pseudo[wl], lane, &v, &d)) {
             fresh = false;
             for (int k = lane; k < (int)(sizeof(GateStack) / 4); k += 32) reinterpret_cast<uint32_t*>(&s_st[wl])[k] = 0xDEADBEEFu;
             __syncwarp();
@@ -1867,6 +1867,11 @@ static int mcts_gate_params(cb_handle* h, MctsParams& mp, int mate_depth, int ex
         return fail(h, CB_EINVAL, "tier1 depths: mate search up to 5, hill up to 4");
     const char* e = getenv("CB_GATE_BUDGET");
     mp.gate_budget = e && atoi(e) > 0 ? atoi(e) : 24;
+    // a step whose jobs stop after `gate_budget` positions while most games are still inside long searches runs the forward for
+    // a handful of leaves: the gate kernel lets the jobs go on (up to gate_stretch more positions) until gate_target games
+    // of the launch are done with their step (CB_GATE_STRETCH = 0 turns it off; set where the pool size is known)
+    const char* s2 = getenv("CB_GATE_STRETCH");
+    mp.gate_stretch = s2 ? atoi(s2) : 400;
     return CB_OK;
 }
 
@@ -2020,7 +2025,13 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
         return CB_OK;
     };
     // tier1_light = 2 with one pool: the gate jobs run in their own kernel after the tree kernel (mcts_select_body<MODE>)
-    const bool split = mp.tier1_light >= 2 && pools == 1 && !getenv("CB_GATE_INLINE");
+    const bool split = mp.gate_jobs && pools == 1 && !getenv("CB_GATE_INLINE");
+    if (split && mp.gate_stretch > 0 && G <= 4096) {   // (every block of the gate kernel must be resident for the count to make sense)
+        if ((rc = dalloc((void**)&mp.gate_ready, 4))) { if (sample_file) fclose(sample_file); release(); return rc; }
+        cudaMemsetAsync(mp.gate_ready, 0, 4, h->stream);
+        const char* t = getenv("CB_GATE_TARGET_PCT");
+        mp.gate_target = (unsigned int)((long long)G * (t && atoi(t) > 0 ? atoi(t) : 50) / 100);
+    }
     auto tree_step = [&] {   // expand + select of the one pool
         if (split) {
             mcts_step_kernel<1><<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));

@@ -70,6 +70,9 @@ struct MctsParams {
                                   // reference's gate at full depth (tier1_gates_run below), run as resumable jobs
     int t1_mate_depth, t1_exh_depth, t1_koth_depth;   // the leaf gate of tier1_light = 2 (5 / 0 / 3 in the reference's self-play)
     int gate_budget;              // positions a game's gate job may enter per step before it is suspended
+    int gate_stretch;             // ... and how many more it may enter while fewer than gate_target games of the launch are done
+    unsigned int gate_target;     //     with their step (mcts_gate_kernel only): when most games are inside long searches, a step
+    unsigned int* gate_ready;     //     that stops after `gate_budget` positions would run the forward for a handful of leaves
     struct GateJob* gate_jobs;    // [G] (tier1_light = 2)
     int g0, gn;                   // the games [g0, g0 + gn) this launch works on (one pool of a two-pool run)
     unsigned int* pdl_done;       // nullable.  Set when the launch is a programmatic dependent of the forward kernel of the
@@ -502,6 +505,23 @@ static_assert(sizeof(GateJob) == kGateJobBytes && offsetof(GateJob, active) == k
 static_assert(sizeof(GateStack) % 16 == 0 && sizeof(cb_board) % 16 == 0, "stack copied as uint4");
 struct GateCfg { int koth_n, mate_d, exh_d; };
 
+// The per-step allowance of a job: `left` positions, then up to `stretch` more as long as fewer than `target` games of this
+// launch have finished their step (*ready, counted by mcts_gate_kernel; nullptr: no stretching).
+struct GateBudget {
+    int left, stretch;
+    const unsigned int* ready;
+    unsigned int target;
+    __device__ __forceinline__ bool spent() {
+        if (left-- > 0) return false;
+        if (!ready || stretch-- <= 0) return true;
+        return *reinterpret_cast<const volatile unsigned int*>(ready) >= target;
+    }
+};
+__device__ __forceinline__ GateBudget gate_budget_of(const MctsParams& p, bool stretchable) {
+    GateBudget b = {p.gate_budget, p.gate_stretch, stretchable ? p.gate_ready : nullptr, p.gate_target};
+    return b;
+}
+
 // Does the side to move of `b` (shared memory) have a legal move?  King steps on eight lanes first, then the list.  The
 // moves are tested without making them (cbchess::move_flags_hd).
 __device__ __forceinline__ bool has_legal_move_warp(const cb_board& b, Move* pseudo, int lane) {
@@ -554,7 +574,7 @@ __device__ __forceinline__ int gate_moves_warp(const cb_board& b, Move* pseudo, 
 // *value = +1 (the side to move of the position wins: hill reached or mate) or 2 (no gate), *dist = terminal_distance
 // (src/mcts/tactical_mcts.rs:641,701).  false: suspended, the stack is back in job.st.  `st` / `pseudo`: the warp's
 // shared memory.  All lanes call and return alike.
-__device__ __forceinline__ bool tier1_gates_run(GateJob& job, GateStack& st, const GateCfg gc, int budget, bool fresh, Move* pseudo,
+__device__ __forceinline__ bool tier1_gates_run(GateJob& job, GateStack& st, const GateCfg gc, GateBudget budget, bool fresh, Move* pseudo,
                                                 int lane, int* value, int* dist) {
     using namespace cbchess;
     int phase, it, ply, r_idx = 0, r_cnt = 0;   // lane p keeps the cursor of ply p
@@ -590,7 +610,7 @@ __device__ __forceinline__ bool tier1_gates_run(GateJob& job, GateStack& st, con
         const bool c_only = !hill && D > 2 * gc.exh_d - 1;   // checks-only level
         int result = -1;
         if (need_enter) {
-            if (budget-- <= 0) {
+            if (budget.spent()) {
                 if (lane == 0) { job.phase = (uint8_t)phase; job.it = (uint8_t)it; job.ply = (uint8_t)ply; }
                 if (lane <= kGatePlies) { job.idx[lane] = (uint16_t)r_idx; job.cnt[lane] = (uint16_t)r_cnt; }
                 const int nb4 = (ply + 1) * (int)(sizeof(cb_board) / 16);
@@ -677,7 +697,7 @@ static_assert(sizeof(Cap1Scratch) <= sizeof(GateStack), "cap1 borrows the gate s
 // S.boards[0] holds the position (resume: the stack is fetched from the job).  true: finished, *cp_out = the score in
 // centipawns, *completed_out = the reference's flag.  false (only with a job): the search has entered `budget` positions in
 // this call and rests in the job.  All lanes.
-__device__ __forceinline__ bool cap1_run(Cap1Scratch& S, GateJob* job, int budget, bool resume, Move* pseudo, uint8_t* mailbox, int lane,
+__device__ __forceinline__ bool cap1_run(Cap1Scratch& S, GateJob* job, GateBudget budget, bool resume, Move* pseudo, uint8_t* mailbox, int lane,
                                          int* cp_out, bool* completed_out) {
     using namespace cbchess;
     enum { ENTER = 0, EVASIONS = 1, CAPTURE = 2, CHECK = 3, DONE = 4 };
@@ -697,7 +717,7 @@ __device__ __forceinline__ bool cap1_run(Cap1Scratch& S, GateJob* job, int budge
         int alpha = __shfl_sync(0xffffffffu, f_alpha, d);
         const int beta = __shfl_sync(0xffffffffu, f_beta, d);
         const int st = __shfl_sync(0xffffffffu, f_state, d);
-        if (job && (st & 7) == ENTER && budget-- <= 0) {   // suspended in front of a position
+        if (job && (st & 7) == ENTER && budget.spent()) {   // suspended in front of a position
             if (lane == 0) job->ply = (uint8_t)d;
             if (lane <= kPeMaxDepth) {
                 job->frames[0][lane] = f_alpha; job->frames[1][lane] = f_beta; job->frames[2][lane] = f_state;
@@ -884,7 +904,7 @@ __device__ __forceinline__ void mcts_game_over(const MctsParams& p, int g, int r
 // The search run to completion in one call.
 __device__ __forceinline__ int cap1_cp_warp(Cap1Scratch& S, Move* pseudo, uint8_t* mailbox, int lane, bool* completed_out) {
     int cp = 0;
-    cap1_run(S, nullptr, 0, false, pseudo, mailbox, lane, &cp, completed_out);
+    cap1_run(S, nullptr, GateBudget{0, 0, nullptr, 0u}, false, pseudo, mailbox, lane, &cp, completed_out);
     return cp;
 }
 
@@ -945,7 +965,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         Cap1Scratch& S = *reinterpret_cast<Cap1Scratch*>(&sm.gate[wl]);
         int cp = 0;
         bool qc = true;
-        if (!cap1_run(S, job, p.gate_budget, true, s_pseudo[wl], sm.mailbox[wl], lane, &cp, &qc)) {
+        if (!cap1_run(S, job, gate_budget_of(p, MODE == 2), true, s_pseudo[wl], sm.mailbox[wl], lane, &cp, &qc)) {
             if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; atomicAdd(&p.stats[MS_GATE_WAITS], 1ull); }
             return;
         }
@@ -966,7 +986,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         // the win is on the board: the same result
         const GateCfg gc = p.match_mode ? GateCfg{p.koth ? p.t1_koth_depth : 0, p.t1_mate_depth, p.t1_exh_depth} : GateCfg{p.koth ? 3 : 0, 5, 2};
         int gv, gd;
-        if (!tier1_gates_run(*job, sm.gate[wl], gc, p.gate_budget, false, s_pseudo[wl], lane, &gv, &gd)) {
+        if (!tier1_gates_run(*job, sm.gate[wl], gc, gate_budget_of(p, MODE == 2), false, s_pseudo[wl], lane, &gv, &gd)) {
             if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; atomicAdd(&p.stats[MS_GATE_WAITS], 1ull); }
             return;
         }
@@ -1135,7 +1155,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
                 __syncwarp();
             }
             const GateCfg gc = {p.koth ? p.t1_koth_depth : 0, p.t1_mate_depth, p.t1_exh_depth};
-            if (!tier1_gates_run(*job, sm.gate[wl], gc, p.gate_budget, fresh, s_pseudo[wl], lane, &tv, &td)) {
+            if (!tier1_gates_run(*job, sm.gate[wl], gc, gate_budget_of(p, MODE == 2), fresh, s_pseudo[wl], lane, &tv, &td)) {
                 if (lane == 0) {
                     job->active = 1;
                     p.path_n[g] = path_n;
@@ -1218,7 +1238,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
             __syncwarp();
             int cp = 0;
             bool qc = true;
-            if (!cap1_run(S, job, p.gate_budget, false, s_pseudo[wl], sm.mailbox[wl], lane, &cp, &qc)) {
+            if (!cap1_run(S, job, gate_budget_of(p, MODE == 2), false, s_pseudo[wl], sm.mailbox[wl], lane, &cp, &qc)) {
                 if (lane == 0) {
                     job->active = 3;
                     job->n_moves = (uint16_t)n_moves;
@@ -1250,6 +1270,7 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_select_kernel(const Mcts
     __shared__ MctsSmem sm;
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = p.g0 + blockIdx.x * kMctsWarps + wl;
+    if (MODE == 1 && p.gate_ready && blockIdx.x == 0 && threadIdx.x == 0) *p.gate_ready = 0;   // counted by the gate kernel that follows
     if (g >= p.g0 + p.gn) return;
     mcts_select_body<MODE>(p, sm, g, wl, lane);
 }
@@ -1261,6 +1282,8 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_gate_kernel(const MctsPa
     const int g = p.g0 + blockIdx.x * kMctsWarps + wl;
     if (g >= p.g0 + p.gn) return;
     mcts_select_body<2>(p, sm, g, wl, lane);
+    __syncwarp();
+    if (lane == 0 && p.gate_ready && !p.gate_jobs[g].active) atomicAdd(p.gate_ready, 1u);   // this game's step is complete
 }
 
 // Keep the subtree under `child` as the new tree, copied breadth first into the other arena (same node
@@ -1504,6 +1527,7 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_step_kernel(const MctsPa
     __shared__ MctsSmem sm;
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = p.g0 + blockIdx.x * kMctsWarps + wl;
+    if (MODE == 1 && p.gate_ready && blockIdx.x == 0 && threadIdx.x == 0) *p.gate_ready = 0;   // counted by the gate kernel that follows
     if (g >= p.g0 + p.gn) return;
     mcts_expand_body(p, sm, g, wl, lane);
     __syncwarp();

@@ -604,10 +604,13 @@ def test_device_self_play_with_the_deep_gates_equals_the_host_driver(cb, golden,
     assert rh.shape == rd.shape and rh.shape[0] > 0 and np.array_equal(key(rh), key(rd))
     have = {r.tobytes() for r in rh}
     monkeypatch.delenv("CB_GATE_INLINE")
-    for name, budget in (("split", "100000000"), ("slow", "24" if koth else "3")):
+    # (CB_GATE_STRETCH: positions a job may go beyond its budget while fewer than half of the games are done with the step)
+    for name, budget, stretch in (("split", "100000000", "400"), ("slow", "24" if koth else "3", "0"), ("stretched", "2", "400")):
         monkeypatch.setenv("CB_GATE_BUDGET", budget)
+        monkeypatch.setenv("CB_GATE_STRETCH", stretch)
         run = ev.selfplay(pipeline=3, sample_path=str(tmp_path / (name + ".bin")), **kw)
-        assert run["games_finished"] > 0 and run["overflow"] == 0 and (run["gate_waits"] > 0) == (name == "slow")
+        assert run["games_finished"] > 0 and run["overflow"] == 0 and (name != "slow" or run["gate_waits"] > 0) and \
+            (name != "split" or run["gate_waits"] == 0)
         rs = np.fromfile(tmp_path / (name + ".bin"), dtype=np.float32).reshape(-1, 5763)
         assert rs.shape[0] > 0 and all(r.tobytes() in have for r in rs), name
         if name == "split":
@@ -744,6 +747,7 @@ def test_device_cap1_qsearch_equals_the_host_form(cb, golden, tmp_path, monkeypa
     key = lambda r: r[np.lexsort(r.T[::-1])]
     assert rh.shape == rd.shape and rh.shape[0] > 0 and np.array_equal(key(rh), key(rd))
     monkeypatch.setenv("CB_GATE_BUDGET", "5")
+    monkeypatch.setenv("CB_GATE_STRETCH", "0")
     slow = ev.selfplay(pipeline=3, sample_path=str(tmp_path / "slow.bin"), **kw)
     rs = np.fromfile(tmp_path / "slow.bin", dtype=np.float32).reshape(-1, 5763)
     have = {r.tobytes() for r in rh}

@@ -38,6 +38,16 @@ if len(sys.argv) > 2 and sys.argv[2] == "cap1":
     with open(os.path.join(REPO, "gpurun_out", "cap1_probe.json"), "w") as f:
         json.dump(rows, f, indent=1)
     sys.exit(0)
+if len(sys.argv) > 2 and sys.argv[2] == "stretch":
+    # the adaptive stretch of the per-step budget (CB_GATE_STRETCH positions more while fewer than half of the games are done)
+    for stretch in ("0", "400"):
+        os.environ["CB_GATE_STRETCH"] = stretch
+        run("deep gates, 1024 games, stretch %s" % stretch, budget=24, pipeline=3, games=1024, tier1_light="deep")
+        run("deep gates, 4096 games, stretch %s" % stretch, budget=24, pipeline=3, games=4096, tier1_light="deep")
+        run("light gates + dM by cap1, 1024 games, stretch %s" % stretch, budget=24, pipeline=3, games=1024, tier1_light=True, material_on=True, qsearch="cap1")
+    with open(os.path.join(REPO, "gpurun_out", "deep_gates_probe_stretch.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == "long":
     # steady-state figures: runs long enough to leave the openings (a game is ~90 moves x 200 simulations)
     for G, b in ((1024, 12), (1024, 24), (4096, 12), (4096, 24), (8192, 24)):
