@@ -535,6 +535,17 @@ int orc_mcts_root_children(const orc_tree* t, orc_move* moves, uint32_t* visits,
     }
     return r->n_children;
 }
+/* what the reference's tests read off a root child: terminal_or_mate_value / terminal_distance (if set) and whether it was expanded */
+int orc_mcts_root_child_info(const orc_tree* t, int i, int* has_term, double* term_value, int* term_dist, int* n_children) {
+    const node* r = t->root;
+    if (i < 0 || i >= r->n_children) return 0;
+    const node* c = r->children[i];
+    if (has_term) *has_term = c->has_term;
+    if (term_value) *term_value = c->term_value;
+    if (term_dist) *term_dist = c->has_dist ? c->term_dist : -1;
+    if (n_children) *n_children = c->n_children;
+    return 1;
+}
 void orc_mcts_root_stats(const orc_tree* t, uint32_t* visits, double* total_value, long* evals, long* terminal_hits, long* tactical) {
     if (visits) *visits = t->root->visits;
     if (total_value) *total_value = t->root->total_value;

@@ -125,6 +125,7 @@ orc_tree* orc_mcts_new(const orc_board* root, uint64_t seed);
 void      orc_mcts_free(orc_tree* t);
 int       orc_mcts_search(orc_tree* t, const orc_mcts_config* cfg, orc_eval_fn eval, void* user); /* returns iterations run */
 int       orc_mcts_root_children(const orc_tree* t, orc_move* moves, uint32_t* visits, double* total_value);
+int       orc_mcts_root_child_info(const orc_tree* t, int i, int* has_term, double* term_value, int* term_dist, int* n_children);
 void      orc_mcts_root_stats(const orc_tree* t, uint32_t* visits, double* total_value, long* evals, long* terminal_hits, long* tactical);
 orc_move  orc_mcts_best_move(const orc_tree* t);                  /* select_best_move_from_root; 0 = None */
 int       orc_mcts_advance(orc_tree* t, orc_move played);         /* reuse_subtree */

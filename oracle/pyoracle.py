@@ -412,6 +412,21 @@ class Tree:
         n = lib().orc_mcts_root_children(self.h, mv_, vis, tv)
         return [(mv_[i], vis[i], tv[i]) for i in range(n)]
 
+    def root_child_info(self):
+        """Per root child: (terminal_or_mate_value or None, terminal_distance or None, number of children)."""
+        L = lib()
+        L.orc_mcts_root_child_info.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
+        L.orc_mcts_root_child_info.restype = ctypes.c_int
+        out = []
+        i = 0
+        while True:
+            ht, td, nc = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+            tv = ctypes.c_double(0)
+            if not L.orc_mcts_root_child_info(self.h, i, ctypes.byref(ht), ctypes.byref(tv), ctypes.byref(td), ctypes.byref(nc)):
+                return out
+            out.append((tv.value if ht.value else None, td.value if ht.value and td.value >= 0 else None, nc.value))
+            i += 1
+
     def root_stats(self):
         v = ctypes.c_uint32(0)
         tv = ctypes.c_double(0)

@@ -101,6 +101,15 @@ def test_checking_move_filter_equals_check_after_the_move():
         assert abs(ms(fen, depth)[0]) < MATE
 
 
+def test_root_gate_of_the_search_entry_points():
+    """tests/unit/tactical_mcts_tests.rs:43-71,895-921: tactical_mcts_search answers a root with a forced mate from its gate,
+    mate_search(board, mate_search_depth = 2, exhaustive_mate_depth = 0) (src/mcts/tactical_mcts.rs:392-420): Re8#."""
+    score, mv, _ = ms(BACK_RANK, 2, 0)
+    assert score == MATE + 1 and mv[1] == 60
+    # koth_tests.rs:182-227: the root gate of a King-of-the-Hill search, koth_center_in_n(board, koth_depth = 3): forced in 2
+    assert hill("rnbqkbnr/1pppppp1/p6p/8/8/4P3/PPPPKPPP/RNBQ1BNR w kq - 0 3")[0] == 2
+
+
 def test_a_mate_in_three_by_checks():
     """Not a reference case: two rooks ladder a bare king (Ra7+? no - every move a check): the checks-only levels find it
     and report 1_000_000 + 5 plies; a depth too small reports 0."""

@@ -228,6 +228,31 @@ def test_gate_resolved_nodes_and_proven_losses():
     assert proven > 0 and others > 0
 
 
+def test_deep_koth_gate_values_are_not_diluted_and_gated_nodes_stay_unexpanded():
+    """tactical_mcts_tests.rs:258-352 on the reference's own position, which needs the gate at full depth (after a White move
+    that does not attend to it Black forces the hill in 2): every root child with a terminal_or_mate_value keeps
+    Q = -value however often it is visited, has no children, and there are such children.  (The reference runs the
+    test with its default q-search, `extended`, for the classical leaf values; the assertions do not depend on them.)"""
+    fen = "r1b4r/ppp1k2p/n3pq1n/5pp1/8/1PP1K3/P3PPPP/RNQ2BNR w - - 0 11"
+    for sims in (100, 1000):
+        t = O.Tree(O.from_fen(fen))
+        t.search(O.mcts_config(sims=sims, material_on=True, qsearch="pe", koth=True, tier1_light="deep"), CLASSICAL)
+        kids, info = t.root_children(), t.root_child_info()
+        gated = 0
+        for (m, visits, total), (tv, dist, n_children) in zip(kids, info):
+            if tv is None:
+                continue
+            gated += 1
+            assert n_children == 0, O.uci(m)
+            if visits:
+                assert abs(total / visits + tv) < 0.01, (O.uci(m), total, visits, tv)
+            nb = O.make_move(O.from_fen(fen), m)
+            assert O.tier1_gates(nb, koth=True)[0] == int(tv)          # and the value is the gate's
+        assert gated > 0
+        # the gate at depth 1 sees none of this: these are hills in 2 and 3
+        assert all(O.light_gates(O.make_move(O.from_fen(fen), m), koth=True) == 2 for (m, _, _), (tv, _, _) in zip(kids, info) if tv == 1.0)
+
+
 def test_koth_early_termination_and_best_move():
     # :433-465, :737-760 (training search): a king step onto the hill ends the search at once and is the move returned
     t = O.Tree(O.from_fen("3N4/k6p/p6P/2P1R3/2n3P1/P1rK4/8/5B2 w - - 4 47"))
