@@ -1852,8 +1852,9 @@ static int mcts_alloc(cb_handle* h, MctsParams& mp, int G, std::vector<void*>& o
         return rc;
     CB_CUDA(h, cudaMemsetAsync(mp.idle, 0, (size_t)G, h->stream));
     if (mp.tier1_light >= 2 || (mp.qsearch == 2 && mp.material_on)) {   // the stacks of the games' gate / cap1 jobs
-        if ((rc = dalloc((void**)&mp.gate_jobs, (size_t)G * sizeof(GateJob)))) return rc;
-        CB_CUDA(h, cudaMemsetAsync(mp.gate_jobs, 0, (size_t)G * sizeof(GateJob), h->stream));
+        if (mp.gate_warps < 1) mp.gate_warps = 1;
+        if ((rc = dalloc((void**)&mp.gate_jobs, (size_t)G * mp.gate_warps * sizeof(GateJob)))) return rc;
+        CB_CUDA(h, cudaMemsetAsync(mp.gate_jobs, 0, (size_t)G * mp.gate_warps * sizeof(GateJob), h->stream));
     }
     return CB_OK;
 }
@@ -1872,6 +1873,13 @@ static int mcts_gate_params(cb_handle* h, MctsParams& mp, int mate_depth, int ex
     // of the launch are done with their step (CB_GATE_STRETCH = 0 turns it off; set where the pool size is known)
     const char* s2 = getenv("CB_GATE_STRETCH");
     mp.gate_stretch = s2 ? atoi(s2) : 400;
+    // warps per game in the gate kernel: each takes every gate_warps-th move of the gate's root (1, 2, 4 or 8).  Measured
+    // (profiles/r02_deep_gates_probe_warps.json): more than one does not pay - from ~4 warps per scheduler the kernel is bound
+    // by instruction issue (1,400 instructions per position at a third of the lanes), and every share generates the root's
+    // moves again - so the default is 1
+    const char* w = getenv("CB_GATE_WARPS");
+    const int gw = w ? atoi(w) : 1;
+    mp.gate_warps = gw == 1 || gw == 2 || gw == 4 || gw == 8 ? gw : 1;
     return CB_OK;
 }
 
@@ -2026,16 +2034,17 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     };
     // tier1_light = 2 with one pool: the gate jobs run in their own kernel after the tree kernel (mcts_select_body<MODE>)
     const bool split = mp.gate_jobs && pools == 1 && !getenv("CB_GATE_INLINE");
-    if (split && mp.gate_stretch > 0 && G <= 4096) {   // (every block of the gate kernel must be resident for the count to make sense)
+    if (split && mp.gate_stretch > 0 && (long long)G * std::max(1, mp.gate_warps) <= 4096) {   // (every block of the gate kernel must be resident for the count to make sense)
         if ((rc = dalloc((void**)&mp.gate_ready, 4))) { if (sample_file) fclose(sample_file); release(); return rc; }
         cudaMemsetAsync(mp.gate_ready, 0, 4, h->stream);
         const char* t = getenv("CB_GATE_TARGET_PCT");
         mp.gate_target = (unsigned int)((long long)G * (t && atoi(t) > 0 ? atoi(t) : 50) / 100);
     }
+    const int gate_grid = (Gp * std::max(1, mp.gate_warps) + kMctsWarps - 1) / kMctsWarps;
     auto tree_step = [&] {   // expand + select of the one pool
         if (split) {
             mcts_step_kernel<1><<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
-            mcts_gate_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
+            mcts_gate_kernel<<<gate_grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
         } else {
             mcts_step_kernel<0><<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(0, false));
         }
@@ -2043,7 +2052,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     auto first_select = [&](int pool) {
         if (split) {
             mcts_select_kernel<1><<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
-            mcts_gate_kernel<<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
+            mcts_gate_kernel<<<gate_grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
         } else {
             mcts_select_kernel<0><<<grid, 32 * kMctsWarps, 0, h->stream>>>(pool_params(pool, false));
         }
@@ -2082,7 +2091,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
                 cudaMemcpy(idle.data(), mp.idle, (size_t)G, cudaMemcpyDeviceToHost);
                 for (int g = 0; g < G; ++g) {
                     uint8_t js[16];
-                    cudaMemcpy(js, reinterpret_cast<uint8_t*>(mp.gate_jobs) + (size_t)g * kGateJobBytes + kGateJobActiveOffset, 16, cudaMemcpyDeviceToHost);
+                    cudaMemcpy(js, reinterpret_cast<uint8_t*>(mp.gate_jobs) + (size_t)g * std::max(1, mp.gate_warps) * kGateJobBytes + kGateJobActiveOffset, 16, cudaMemcpyDeviceToHost);
                     if (!idle[g] || js[0]) fprintf(stderr, "game %d: idle %d sims_done %d job active %d phase %d it %d ply %d (steps %lld)\n", g, idle[g], sd[g], js[0], js[1], js[2], js[3], dbg_steps);
                 }
                 fprintf(stderr, "debug search: %lld steps\n", dbg_steps);
@@ -2115,7 +2124,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
         out->terminal_hits = (long long)st2[MS_TERMINAL];
         out->overflow = (long long)st2[MS_OVERFLOW];
         out->gate_hits = (long long)st2[MS_GATE_HITS];
-        out->gate_waits = (long long)st2[MS_GATE_WAITS];
+        out->gate_waits = (long long)st2[MS_GATE_WAITS] / std::max(1, mp.gate_warps);
         out->steps = dbg_steps;
         return CB_OK;
     }
@@ -2230,7 +2239,7 @@ static int selfplay_device_impl(cb_handle* h, const cb_selfplay_config* cfg, cb_
     out->draws = (long long)st[MS_DRAWS];
     out->overflow = (long long)st[MS_OVERFLOW];
     out->gate_hits = (long long)st[MS_GATE_HITS];
-    out->gate_waits = (long long)st[MS_GATE_WAITS];
+    out->gate_waits = (long long)st[MS_GATE_WAITS] / std::max(1, mp.gate_warps);   // (a share that is suspended counts 1 / gate_warps)
     out->seconds = secs;
     const double tot = (double)ms_fwd + ms_tree;
     out->eval_seconds = tot > 0 ? secs * ms_fwd / tot : 0.0;

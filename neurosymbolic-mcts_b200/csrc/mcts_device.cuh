@@ -73,7 +73,8 @@ struct MctsParams {
     int gate_stretch;             // ... and how many more it may enter while fewer than gate_target games of the launch are done
     unsigned int gate_target;     //     with their step (mcts_gate_kernel only): when most games are inside long searches, a step
     unsigned int* gate_ready;     //     that stops after `gate_budget` positions would run the forward for a handful of leaves
-    struct GateJob* gate_jobs;    // [G] (tier1_light = 2)
+    struct GateJob* gate_jobs;    // [G][gate_warps] (tier1_light = 2, dM by cap1): a game's jobs; game-level state in its first
+    int gate_warps;               // warps per game in mcts_gate_kernel: each takes every gate_warps-th move of the gate's root
     int g0, gn;                   // the games [g0, g0 + gn) this launch works on (one pool of a two-pool run)
     unsigned int* pdl_done;       // nullable.  Set when the launch is a programmatic dependent of the forward kernel of the
                                   // OTHER pool: the last warp to finish (wrapping counter) waits for that kernel before it
@@ -186,7 +187,7 @@ __device__ __forceinline__ void mcts_reset_game(const MctsParams& p, int g, uint
     p.ply[g] = 0;
     p.sims_done[g] = 0;
     p.samples_in_game[g] = 0;
-    if (p.gate_jobs) reinterpret_cast<uint8_t*>(p.gate_jobs)[(size_t)g * kGateJobBytes + kGateJobActiveOffset] = 0;   // GateJob::active
+    if (p.gate_jobs) reinterpret_cast<uint8_t*>(p.gate_jobs)[(size_t)g * p.gate_warps * kGateJobBytes + kGateJobActiveOffset] = 0;   // GateJob::active
 }
 
 __global__ void mcts_init_kernel(const MctsParams p) {
@@ -499,7 +500,10 @@ struct GateJob {                   // a game's job in global memory: where the s
     uint8_t ply;
     uint16_t n_moves;              // cap1 job: the leaf's legal moves / how many come from the capture list (the rest of the
     uint8_t n_tact;                // selection is done; the evaluation request waits for dM)
-    uint8_t pad[9];
+    uint8_t stripe_state;          // this warp's share of a gate job: 0 not started, 1 suspended, 2 done
+    uint8_t res_value, res_dist;   // ... its result
+    uint8_t pad[2];
+    uint32_t remaining;            // (first job of the game) shares of the gate job that are not done yet
 };
 static_assert(sizeof(GateJob) == kGateJobBytes && offsetof(GateJob, active) == kGateJobActiveOffset, "gate job layout");
 static_assert(sizeof(GateStack) % 16 == 0 && sizeof(cb_board) % 16 == 0, "stack copied as uint4");
@@ -574,8 +578,12 @@ __device__ __forceinline__ int gate_moves_warp(const cb_board& b, Move* pseudo, 
 // *value = +1 (the side to move of the position wins: hill reached or mate) or 2 (no gate), *dist = terminal_distance
 // (src/mcts/tactical_mcts.rs:641,701).  false: suspended, the stack is back in job.st.  `st` / `pseudo`: the warp's
 // shared memory.  All lanes call and return alike.
+// root_first / root_stride: this call's share of the work - at the gate's root (ply 0) only the moves first, first + stride,
+// ... of every iteration's move list are tried.  Both searches are "is there a root move such that ...", so the shares
+// of a job are independent searches and the job's answer is the earliest hit among them (smallest *dist: the hill's n
+// before the mate's 64 + plies, as the sequential search finds them).
 __device__ __forceinline__ bool tier1_gates_run(GateJob& job, GateStack& st, const GateCfg gc, GateBudget budget, bool fresh, Move* pseudo,
-                                                int lane, int* value, int* dist) {
+                                                int lane, int* value, int* dist, int root_first = 0, int root_stride = 1) {
     using namespace cbchess;
     int phase, it, ply, r_idx = 0, r_cnt = 0;   // lane p keeps the cursor of ply p
     *value = 2;
@@ -644,13 +652,13 @@ __device__ __forceinline__ bool tier1_gates_run(GateJob& job, GateStack& st, con
                     else if (any_node) result = (ply != 0 && !c_only && nl == 0 && in_check_hd(cur, stm)) ? 1 : 0;   // :276-283
                     else result = in_check_hd(cur, stm) ? 1 : 0;                    // mated / stalemate
                 }
-                if (lane == ply) { r_idx = 0; r_cnt = cnt; }
+                if (lane == ply) { r_idx = ply == 0 ? root_first : 0; r_cnt = cnt; }
             }
         }
         if (result < 0) {
             const int idx = __shfl_sync(0xffffffffu, r_idx, ply), cnt = __shfl_sync(0xffffffffu, r_cnt, ply);
             if (idx < cnt) {
-                if (lane == ply) r_idx = idx + 1;
+                if (lane == ply) r_idx = idx + (ply == 0 ? root_stride : 1);
                 __syncwarp();
                 if (lane == 0) make_move_hd(st.boards[ply], (Move)st.list[ply][idx], &st.boards[ply + 1]);
                 __syncwarp();
@@ -865,6 +873,7 @@ struct MctsSmem {
     Move legal[kMctsWarps][CB_MAX_MOVES];
     uint8_t mailbox[kMctsWarps][64];   // piece codes of the position under the exchange line
     GateStack gate[kMctsWarps];        // tier1_light = 2: the stack of the warp's gate job while it runs
+    uint8_t reporter[kMctsWarps];      // mcts_gate_kernel: this warp accounts for its game's step (gate_ready)
 };
 
 // A self-play game in slot g is over (lane 0): count it, log the result record, start the next game.  `rs`: the game's
@@ -943,30 +952,79 @@ __device__ __forceinline__ MChildLite lite_of(const MNode& n) {
 // (mcts_gate_kernel) instead of inside the 400 KB tree kernel: MODE 1 (tree kernel) walks down and, at a fresh leaf, files
 // the gate job; MODE 2 (gate kernel) runs the filed / suspended jobs and, when one finishes, completes the selection (decided
 // leaf: backup; else the evaluation request) or adjudicates the root.
+// In MODE 2 a game has gate_warps warps (`w` = this warp's index among them): each runs its share of the gate job (every
+// gate_warps-th move of the gate's root, tier1_gates_run), and the warp that finishes the last share goes on alone.
 template <int MODE>
-__device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& sm, int g, int wl, int lane) {
+__device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& sm, int g, int wl, int lane, int w = 0) {
     Move (&s_pseudo)[kMctsWarps][CB_MAX_MOVES] = sm.pseudo;
     Move (&s_legal)[kMctsWarps][CB_MAX_MOVES] = sm.legal;
     if ((p.match_mode || p.search_only) && p.idle[g]) {
         if (MODE != 2 && lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; }
+        if (MODE == 2 && w == 0 && lane == 0) sm.reporter[wl] = 1;
         return;
     }
     // tier1_light = 2: a gate job of this game may be waiting (tier1_gates_run)
     const bool deep = p.tier1_light >= 2;
-    GateJob* job = p.gate_jobs ? &p.gate_jobs[g] : nullptr;   // (allocated with tier1_light = 2 and with dM by cap1)
+    const int W = p.gate_warps > 0 ? p.gate_warps : 1;
+    GateJob* job = p.gate_jobs ? &p.gate_jobs[(size_t)g * W] : nullptr;   // (allocated with tier1_light = 2 and with dM by cap1)
     int pending = job ? job->active : 0;
     if (MODE == 1 && pending) {   // the gate kernel carries the job on
         if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; }
         return;
     }
-    if (MODE == 2 && !pending) return;
+    if (MODE == 2 && (!pending || pending == 3)) {
+        if (w != 0) return;                          // nothing to share: the game's first warp
+        if (lane == 0) sm.reporter[wl] = 1;
+        if (!pending) return;
+    }
+    int pre_tv = 2, pre_td = 0;   // MODE 2: the gate's answer, put together from the shares
+    if (MODE == 2 && pending != 3) {
+        GateJob* mine = job + w;
+        if (mine->stripe_state == 2) return;         // this share is done; others are still running
+        const bool fresh_share = mine->stripe_state == 0;
+        __syncwarp();
+        if (fresh_share) {
+            if (lane < 16) reinterpret_cast<uint64_t*>(&sm.gate[wl].boards[0])[lane] = reinterpret_cast<const uint64_t*>(&job->st.boards[0])[lane];
+            __syncwarp();
+        }
+        const GateCfg gc = (pending == 2 && !p.match_mode) ? GateCfg{p.koth ? 3 : 0, 5, 2}
+                                                           : GateCfg{p.koth ? p.t1_koth_depth : 0, p.t1_mate_depth, p.t1_exh_depth};
+        int v = 2, d = 0;
+        if (!tier1_gates_run(*mine, sm.gate[wl], gc, gate_budget_of(p, true), fresh_share, s_pseudo[wl], lane, &v, &d, w, W)) {
+            if (lane == 0) { mine->stripe_state = 1; atomicAdd(&p.stats[MS_GATE_WAITS], 1ull); }
+            return;
+        }
+        unsigned int old = 0;
+        if (lane == 0) {
+            mine->res_value = (uint8_t)v;
+            mine->res_dist = (uint8_t)d;
+            mine->stripe_state = 2;
+            __threadfence();
+            old = atomicSub(&job->remaining, 1u);
+        }
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old != 1u) return;                       // not the last share
+        __threadfence();
+        int best = 256;
+        for (int k = 0; k < W; ++k) {
+            const volatile GateJob* o = job + k;
+            if (o->res_value == 1 && (int)o->res_dist < best) { pre_tv = 1; best = o->res_dist; }
+        }
+        pre_td = pre_tv == 1 ? best : 0;
+        __syncwarp();
+        if (lane == 0) {
+            for (int k = 0; k < W; ++k) (job + k)->stripe_state = 0;
+            sm.reporter[wl] = 1;
+        }
+        __syncwarp();
+    }
     if (pending == 3) {
         // the selection is complete but for dM: the leaf's cap1 search was suspended (cap1_run); its result releases the request
         Cap1Scratch& S = *reinterpret_cast<Cap1Scratch*>(&sm.gate[wl]);
         int cp = 0;
         bool qc = true;
         if (!cap1_run(S, job, gate_budget_of(p, MODE == 2), true, s_pseudo[wl], sm.mailbox[wl], lane, &cp, &qc)) {
-            if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; atomicAdd(&p.stats[MS_GATE_WAITS], 1ull); }
+            if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; atomicAdd(&p.stats[MS_GATE_WAITS], (unsigned long long)W); }
             return;
         }
         if (lane == 0) {
@@ -985,9 +1043,9 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
         // gate decides with the winning move (src/mcts/tactical_mcts.rs:330-420, the search's depths), move after move until
         // the win is on the board: the same result
         const GateCfg gc = p.match_mode ? GateCfg{p.koth ? p.t1_koth_depth : 0, p.t1_mate_depth, p.t1_exh_depth} : GateCfg{p.koth ? 3 : 0, 5, 2};
-        int gv, gd;
-        if (!tier1_gates_run(*job, sm.gate[wl], gc, gate_budget_of(p, MODE == 2), false, s_pseudo[wl], lane, &gv, &gd)) {
-            if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; atomicAdd(&p.stats[MS_GATE_WAITS], 1ull); }
+        int gv = pre_tv, gd = pre_td;
+        if (MODE != 2 && !tier1_gates_run(*job, sm.gate[wl], gc, gate_budget_of(p, false), false, s_pseudo[wl], lane, &gv, &gd)) {
+            if (lane == 0) { p.wants_eval[g] = 0; p.eval_cnt[g] = 0; atomicAdd(&p.stats[MS_GATE_WAITS], (unsigned long long)W); }
             return;
         }
         if (lane == 0) job->active = 0;
@@ -1140,7 +1198,8 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
             if (MODE == 1) {   // file the job for the gate kernel
                 if (lane < 16) reinterpret_cast<uint64_t*>(&job->st.boards[0])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
                 if (lane == 0) {
-                    job->it = 0;       // not started
+                    for (int k = 0; k < W; ++k) (job + k)->stripe_state = 0;   // no share has started
+                    job->remaining = (uint32_t)W;
                     job->active = 1;
                     p.path_n[g] = path_n;
                     p.wants_eval[g] = 0;
@@ -1148,22 +1207,27 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
                 }
                 return;
             }
-            const bool fresh = MODE == 2 ? job->it == 0 : pending != 1;
-            __syncwarp();
-            if (fresh) {
-                if (lane < 16) reinterpret_cast<uint64_t*>(&sm.gate[wl].boards[0])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
+            if (MODE == 2) {   // the shares have answered
+                tv = pre_tv;
+                td = pre_td;
+            } else {
+                const bool fresh = pending != 1;
                 __syncwarp();
-            }
-            const GateCfg gc = {p.koth ? p.t1_koth_depth : 0, p.t1_mate_depth, p.t1_exh_depth};
-            if (!tier1_gates_run(*job, sm.gate[wl], gc, gate_budget_of(p, MODE == 2), fresh, s_pseudo[wl], lane, &tv, &td)) {
-                if (lane == 0) {
-                    job->active = 1;
-                    p.path_n[g] = path_n;
-                    p.wants_eval[g] = 0;
-                    p.eval_cnt[g] = 0;
-                    atomicAdd(&p.stats[MS_GATE_WAITS], 1ull);
+                if (fresh) {
+                    if (lane < 16) reinterpret_cast<uint64_t*>(&sm.gate[wl].boards[0])[lane] = reinterpret_cast<const uint64_t*>(&board)[lane];
+                    __syncwarp();
                 }
-                return;
+                const GateCfg gc = {p.koth ? p.t1_koth_depth : 0, p.t1_mate_depth, p.t1_exh_depth};
+                if (!tier1_gates_run(*job, sm.gate[wl], gc, gate_budget_of(p, false), fresh, s_pseudo[wl], lane, &tv, &td)) {
+                    if (lane == 0) {
+                        job->active = 1;
+                        p.path_n[g] = path_n;
+                        p.wants_eval[g] = 0;
+                        p.eval_cnt[g] = 0;
+                        atomicAdd(&p.stats[MS_GATE_WAITS], (unsigned long long)W);
+                    }
+                    return;
+                }
             }
             if (lane == 0) {
                 job->active = 0;
@@ -1246,7 +1310,7 @@ __device__ __forceinline__ void mcts_select_body(const MctsParams& p, MctsSmem& 
                     p.path_n[g] = path_n;
                     p.wants_eval[g] = 0;
                     p.eval_cnt[g] = 0;
-                    atomicAdd(&p.stats[MS_GATE_WAITS], 1ull);
+                    atomicAdd(&p.stats[MS_GATE_WAITS], (unsigned long long)W);
                 }
                 return;
             }
@@ -1276,14 +1340,20 @@ __global__ void __launch_bounds__(32 * kMctsWarps) mcts_select_kernel(const Mcts
 }
 
 // tier1_light = 2, one pool: the games' gate jobs (and what follows a finished one), between the tree kernel and the forward.
+// gate_warps warps per game.
 __global__ void __launch_bounds__(32 * kMctsWarps) mcts_gate_kernel(const MctsParams p) {
     __shared__ MctsSmem sm;
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = p.g0 + blockIdx.x * kMctsWarps + wl;
+    const int W = p.gate_warps > 0 ? p.gate_warps : 1;
+    const int widx = blockIdx.x * kMctsWarps + wl;
+    const int g = p.g0 + widx / W, w = widx % W;
     if (g >= p.g0 + p.gn) return;
-    mcts_select_body<2>(p, sm, g, wl, lane);
+    if (lane == 0) sm.reporter[wl] = 0;
     __syncwarp();
-    if (lane == 0 && p.gate_ready && !p.gate_jobs[g].active) atomicAdd(p.gate_ready, 1u);   // this game's step is complete
+    mcts_select_body<2>(p, sm, g, wl, lane, w);
+    __syncwarp();
+    // the warp that accounts for the game: its step is complete unless a job is still pending
+    if (lane == 0 && p.gate_ready && sm.reporter[wl] && !p.gate_jobs[(size_t)g * W].active) atomicAdd(p.gate_ready, 1u);
 }
 
 // Keep the subtree under `child` as the new tree, copied breadth first into the other arena (same node
@@ -1502,11 +1572,14 @@ __device__ __forceinline__ void mcts_expand_body(const MctsParams& p, MctsSmem& 
         } else {
             p.rng[g] = rs;
             if (p.tier1_light >= 2) {   // the new root's pre-check runs as a job in front of its first simulation
-                GateJob& job = p.gate_jobs[g];
+                const int W = p.gate_warps > 0 ? p.gate_warps : 1;
+                GateJob& job = p.gate_jobs[(size_t)g * W];
                 job.st.boards[0] = nb;
-                job.phase = p.koth ? 0 : 1;
+                job.phase = p.koth ? 0 : 1;     // (the inline form resumes it from here; the gate kernel's shares start afresh)
                 job.it = 1;
                 job.ply = 0;
+                for (int k = 0; k < W; ++k) (&job + k)->stripe_state = 0;
+                job.remaining = (uint32_t)W;
                 job.active = 2;
             }
         }

@@ -461,13 +461,15 @@ def search_corpus(n_random, koth=None, deep=False):
                                        ((0.0, 0.5), dict(tier1_light="deep", koth=True)), ((-20.0, 0.5), dict(tier1_light="deep"))],
                          ids=["uniform", "biased+", "biased-koth", "uniform-koth-gates", "uniform-gates", "uniform-shuffle",
                               "uniform-deep-gates", "uniform-koth-deep-gates", "biased-deep-gates"])
-def test_device_search_equals_the_oracle_with_the_mock_evaluator(cb, golden, mock, mode):
+def test_device_search_equals_the_oracle_with_the_mock_evaluator(cb, golden, mock, mode, monkeypatch):
     """The device tree kernels against oracle/mcts.c with the reference's mock evaluator (InferenceServer::new_mock_biased:
     uniform priors, constant v_logit — 0 and a saturated +-20 give exact values on both sides): ties everywhere, so child
     order, the tactical phase, the root's force-visit and the first-maximum rule decide every visit count.  200 simulations
     from each of >= 64 positions; visit counts AND f64 value sums must be identical."""
     g, blob = golden("2x128_B")
     ev = make_eval(cb, g, blob, "bf16")
+    if mode.get("tier1_light") == "deep" and mode.get("koth"):
+        monkeypatch.setenv("CB_GATE_WARPS", "4")      # the gate jobs shared by four warps per game (every fourth root move each)
     boards = search_corpus(72, koth=mode.get("koth", False) if mode.get("tier1_light") else None, deep=mode.get("tier1_light") == "deep")
     assert boards.shape[0] >= 64      # (deep gates: gate jobs are suspended after CB_GATE_BUDGET positions per step and resumed)
     kids, root_visits = ev.debug_device_search(boards, sims_per_move=200, seed=3, mock=mock, **mode)
@@ -605,9 +607,12 @@ def test_device_self_play_with_the_deep_gates_equals_the_host_driver(cb, golden,
     have = {r.tobytes() for r in rh}
     monkeypatch.delenv("CB_GATE_INLINE")
     # (CB_GATE_STRETCH: positions a job may go beyond its budget while fewer than half of the games are done with the step)
-    for name, budget, stretch in (("split", "100000000", "400"), ("slow", "24" if koth else "3", "0"), ("stretched", "2", "400")):
+    # (CB_GATE_WARPS: warps per game in the gate kernel, each with every W-th move of the gate's root)
+    for name, budget, stretch, warps in (("split", "100000000", "400", "1"), ("slow", "24" if koth else "3", "0", "1"),
+                                         ("stretched", "2", "400", "1"), ("shared", "6", "0", "4")):
         monkeypatch.setenv("CB_GATE_BUDGET", budget)
         monkeypatch.setenv("CB_GATE_STRETCH", stretch)
+        monkeypatch.setenv("CB_GATE_WARPS", warps)
         run = ev.selfplay(pipeline=3, sample_path=str(tmp_path / (name + ".bin")), **kw)
         assert run["games_finished"] > 0 and run["overflow"] == 0 and (name != "slow" or run["gate_waits"] > 0) and \
             (name != "split" or run["gate_waits"] == 0)

@@ -38,6 +38,19 @@ if len(sys.argv) > 2 and sys.argv[2] == "cap1":
     with open(os.path.join(REPO, "gpurun_out", "cap1_probe.json"), "w") as f:
         json.dump(rows, f, indent=1)
     sys.exit(0)
+if len(sys.argv) > 2 and sys.argv[2] == "warps":
+    # warps per game in the gate kernel (each takes every W-th move of the gate's root)
+    for W in ("1", "4", "8"):
+        os.environ["CB_GATE_WARPS"] = W
+        run("deep gates, 1024 games, %s warps per game" % W, budget=24, pipeline=3, games=1024, tier1_light="deep")
+        run("deep gates, 4096 games, %s warps per game" % W, budget=24, pipeline=3, games=4096, tier1_light="deep")
+    os.environ["CB_GATE_WARPS"] = "4"
+    run("KOTH, deep gates, 1024 games, 4 warps per game", budget=24, pipeline=3, games=1024, tier1_light="deep", koth=True)
+    os.environ["CB_GATE_WARPS"] = "8"
+    run("KOTH, deep gates, 1024 games, 8 warps per game", budget=24, pipeline=3, games=1024, tier1_light="deep", koth=True)
+    with open(os.path.join(REPO, "gpurun_out", "deep_gates_probe_warps.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == "stretch":
     # the adaptive stretch of the per-step budget (CB_GATE_STRETCH positions more while fewer than half of the games are done)
     for stretch in ("0", "400"):
