@@ -21,6 +21,7 @@ namespace cbchess {
 struct Tables {
     uint64_t knight[64], king[64], pawn[2][64];
     uint64_t ray[8][64];  // N NE E SE S SW W NW
+    uint64_t line[4][64]; // file, rank, diagonal (NE-SW), antidiagonal (NW-SE) through the square, without the square
 };
 
 inline void build_tables(Tables* t) {
@@ -39,6 +40,10 @@ inline void build_tables(Tables* t) {
                 line |= 1ull << (rr * 8 + ff);
             t->ray[i][sq] = line;
         }
+        t->line[0][sq] = t->ray[0][sq] | t->ray[4][sq];
+        t->line[1][sq] = t->ray[2][sq] | t->ray[6][sq];
+        t->line[2][sq] = t->ray[1][sq] | t->ray[5][sq];
+        t->line[3][sq] = t->ray[7][sq] | t->ray[3][sq];
         for (int c = 0; c < 2; ++c) {
             const int rr = r + (c == 0 ? 1 : -1);
             if (rr >= 0 && rr < 8) {
@@ -89,11 +94,33 @@ CB_HD uint64_t ray_attack(int dir, int sq, uint64_t occ) {
     }
     return att;
 }
+// Sliding attacks along one line by subtraction ("hyperbola quintessence"): with o the occupied squares of the line and r the
+// slider, (o - 2r) flips the squares from r up to the first blocker above it; the same on the bit-reversed board gives the
+// squares below it.  A dozen instructions per line instead of two table-and-scan rays.
+CB_HD uint64_t bit_reverse64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brevll(x);
+#else
+    x = __builtin_bswap64(x);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    return x;
+#endif
+}
+CB_HD uint64_t line_attack(uint64_t mask, int sq, uint64_t occ) {
+    const uint64_t o = occ & mask;
+    const uint64_t up = o - (2ull << sq);
+    const uint64_t down = bit_reverse64(bit_reverse64(o) - (2ull << (63 - sq)));
+    return (up ^ down) & mask;
+}
 CB_HD uint64_t rook_att(int sq, uint64_t occ) {
-    return ray_attack(0, sq, occ) | ray_attack(2, sq, occ) | ray_attack(4, sq, occ) | ray_attack(6, sq, occ);
+    const Tables& T = tables();
+    return line_attack(T.line[0][sq], sq, occ) | line_attack(T.line[1][sq], sq, occ);
 }
 CB_HD uint64_t bishop_att(int sq, uint64_t occ) {
-    return ray_attack(1, sq, occ) | ray_attack(3, sq, occ) | ray_attack(5, sq, occ) | ray_attack(7, sq, occ);
+    const Tables& T = tables();
+    return line_attack(T.line[2][sq], sq, occ) | line_attack(T.line[3][sq], sq, occ);
 }
 
 CB_HD bool attacked(const cb_board& b, int sq, int by) {
@@ -109,9 +136,15 @@ CB_HD bool attacked(const cb_board& b, int sq, int by) {
 }
 
 CB_HD int piece_on(const cb_board& b, int color, uint64_t bit) {
-    for (int p = 0; p < 6; ++p)
-        if (b.pieces[color * 6 + p] & bit) return p;
-    return -1;
+    const uint64_t* pc = &b.pieces[color * 6];
+    int p = -1;   // (a square holds one piece: the order of the tests is free; no early exit, no divergence)
+    p = (pc[5] & bit) ? 5 : p;
+    p = (pc[4] & bit) ? 4 : p;
+    p = (pc[3] & bit) ? 3 : p;
+    p = (pc[2] & bit) ? 2 : p;
+    p = (pc[1] & bit) ? 1 : p;
+    p = (pc[0] & bit) ? 0 : p;
+    return p;
 }
 
 CB_HD int add_pawn(Move* out, int n, int from, int to, int promo_rank) {
@@ -223,17 +256,22 @@ CB_HD void make_move_hd(const cb_board& src, Move m, cb_board* out) {
     const int us = b.w_to_move ? 0 : 1, them = 1 - us;
     const uint64_t fbit = 1ull << from, tbit = 1ull << to;
     const int pt = piece_on(b, us, fbit);
-    const int captured = piece_on(b, them, tbit);
+    const int captured = (b.occ[them] & tbit) ? piece_on(b, them, tbit) : -1;
     const bool reset_clock = pt == PAWN || captured >= 0;
+    uint64_t occ_us = (b.occ[us] & ~fbit) | tbit, occ_them = b.occ[them] & ~tbit;   // kept up to date move by move
     if (captured >= 0) b.pieces[them * 6 + captured] &= ~tbit;
-    if (pt == PAWN && b.en_passant != 0xFF && to == b.en_passant && captured < 0 && ((from ^ to) & 7))
-        b.pieces[them * 6 + PAWN] &= ~(1ull << (us == 0 ? to - 8 : to + 8));
+    if (pt == PAWN && b.en_passant != 0xFF && to == b.en_passant && captured < 0 && ((from ^ to) & 7)) {
+        const uint64_t epb = 1ull << (us == 0 ? to - 8 : to + 8);
+        b.pieces[them * 6 + PAWN] &= ~epb;
+        occ_them &= ~epb;
+    }
     b.pieces[us * 6 + pt] &= ~fbit;
     b.pieces[us * 6 + (promo ? promo : pt)] |= tbit;
     if (pt == KING && (to - from == 2 || from - to == 2)) {
         const int rf = to > from ? from + 3 : from - 4, rt = to > from ? from + 1 : from - 1;
         b.pieces[us * 6 + ROOK] &= ~(1ull << rf);
         b.pieces[us * 6 + ROOK] |= 1ull << rt;
+        occ_us = (occ_us & ~(1ull << rf)) | (1ull << rt);
     }
     if (pt == KING) b.castling &= us == 0 ? (uint8_t)~(WK | WQ) : (uint8_t)~(BK | BQ);
     if (from == 0 || to == 0) b.castling &= (uint8_t)~WQ;
@@ -244,11 +282,8 @@ CB_HD void make_move_hd(const cb_board& src, Move m, cb_board* out) {
     if (pt == PAWN && (to - from == 16 || from - to == 16)) b.en_passant = (uint8_t)((from + to) / 2);
     b.halfmove = reset_clock ? 0 : (uint8_t)(b.halfmove < 255 ? b.halfmove + 1 : 255);
     b.w_to_move = (uint8_t)!b.w_to_move;
-    for (int c = 0; c < 2; ++c) {
-        uint64_t o = 0;
-        for (int p = 0; p < 6; ++p) o |= b.pieces[c * 6 + p];
-        b.occ[c] = o;
-    }
+    b.occ[us] = occ_us;
+    b.occ[them] = occ_them;
     *out = b;
 }
 
