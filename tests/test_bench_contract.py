@@ -13,7 +13,7 @@ REQUIRED = {"metric": str, "value": float, "unit": str, "n_gpus": int, "steps": 
             "gpu_launches": int, "clocks": dict, "roofline": dict}
 
 
-@pytest.mark.parametrize("name,n", [("r02_bench_v11.json", 1), ("r02_bench_v10.json", 1), ("r02_bench_v10_n2.json", 2), ("r02_bench_v6.json", 1), ("r02_bench_v5_n2.json", 2), ("r02_bench_v5_n8.json", 8), ("r01_bench_v15.json", 1), ("r01_bench_v15_n8.json", 8), ("r01_bench_v16_n2.json", 2), ("r01_bench_v14.json", 1), ("r01_bench_v13.json", 1), ("r01_bench_v13_n2.json", 2), ("r01_bench_v13_n4.json", 4),
+@pytest.mark.parametrize("name,n", [("r02_bench_v12.json", 1), ("r02_bench_v11.json", 1), ("r02_bench_v10.json", 1), ("r02_bench_v10_n2.json", 2), ("r02_bench_v6.json", 1), ("r02_bench_v5_n2.json", 2), ("r02_bench_v5_n8.json", 8), ("r01_bench_v15.json", 1), ("r01_bench_v15_n8.json", 8), ("r01_bench_v16_n2.json", 2), ("r01_bench_v14.json", 1), ("r01_bench_v13.json", 1), ("r01_bench_v13_n2.json", 2), ("r01_bench_v13_n4.json", 4),
                                     ("r01_bench_v13_n8.json", 8)])
 def test_committed_lines_follow_the_contract(name, n):
     d = json.load(open(os.path.join(REPO, "profiles", name)))
@@ -40,7 +40,7 @@ def test_committed_lines_follow_the_contract(name, n):
         else:
             x = d["nccl_exchange"]
             assert x["gather_bit_equal_on_rank0"] and x["weights_spot_check_identical_on_all_ranks"] and x["gather_records"] > 1000
-    if "v10" in name or "v11" in name:  # the end-of-round lines: self-play with the reference's Tier-1 gate at full depth
+    if "v10" in name or "v11" in name or "v12" in name:  # the end-of-round lines: self-play with the reference's Tier-1 gate at full depth
         t1 = d["selfplay"]["tier1_deep"]
         assert t1["sims_per_s"] > 0 and t1["sims_per_s_4x_games"] > t1["sims_per_s"] and t1["games_per_gpu_4x"] == 4 * t1["games_per_gpu"]
         assert 0.0 <= t1["game_steps_waiting_for_a_gate_job_fraction"] < 1.0
