@@ -248,3 +248,39 @@ def test_deep_gates_agree_with_an_unpruned_minimax_on_random_positions(koth):
         assert got == want, i
         hits += want
     assert koth or hits >= 0
+
+
+def test_exhaustive_levels_agree_with_a_plain_minimax_on_small_positions():
+    """The adjudication search (mate_search(board, 2, exhaustive 2): every legal move at the attacker's plies) against a
+    mate-in-2 minimax written here from the rules, on playout positions with few legal moves (the reference's rule for a
+    side without moves on an attacker ply, src/search/mate_search.rs:276-283, never fires in these: it needs the defender to
+    deliver mate)."""
+    boards, _, _, _ = O.random_positions(2024, 1200, 220)
+
+    def kids(b):
+        return [O.make_move(b, int(m)) for m in O.legal_moves(b)]
+
+    def mated(b):
+        return O.in_check(b) and not O.legal_moves(b)
+
+    def mate_in(b, d):
+        for c in kids(b):
+            if mated(c):
+                return True
+            if d > 1:
+                replies = kids(c)
+                if replies and not any(mated(r) for r in replies) and all(mate_in(r, d - 1) for r in replies):
+                    return True
+        return False
+
+    checked = hits = 0
+    for i in range(boards.shape[0]):
+        b = O.array_to_board(boards[i])
+        if len(O.legal_moves(b)) > 12 or checked >= 60:
+            continue
+        checked += 1
+        want = mate_in(b, 2)
+        got = O.mate_search(b, 2, 2)[0]
+        assert (got != 0) == want, i
+        hits += want
+    assert checked >= 40
