@@ -200,8 +200,8 @@ uint64_t cb_chess_perft(const cb_board* b, int depth);
  * evaluated in ONE cb_eval_leaves batch per step.  dM (material_on) is the static PeSTO stand pat, or with
  * qsearch = 1 the reference's principal-exchange line on top of it (`--qsearch pe`,
  * src/mcts/tactical_mcts.rs:715-731); tier1_light = 1 adds the Tier-1 gate at depth 1, tier1_light = 2 the gate at the depths
- * the reference's self-play runs (mate search to mate-in-5, hill in 3; on the device as resumable jobs).  The wider q-searches
- * (cap1, extended) are host CPU searches outside this path. */
+ * the reference's self-play runs (mate search to mate-in-5, hill in 3; on the device as resumable jobs).  qsearch = 2 computes dM
+ * by the reference's cap1 search (on the device as resumable jobs too); its widest q-search (`extended`) is not built. */
 typedef struct cb_selfplay_config {
     int games;            /* concurrent games in the pool */
     int sims_per_move;    /* 200 / 800 */
